@@ -1,0 +1,311 @@
+// torch <-> edl_b200 kernel bindings.  Only this file includes torch headers; the kernels are in
+// torch-free .cu files (see kernels.h).  Every entry point launches on the current CUDA stream so
+// the ops are capturable into CUDA graphs.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include "gemm.h"
+#include "kernels.h"
+
+namespace {
+
+using torch::Tensor;
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+inline void check_bf16(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == at::kBFloat16, name, " must be bf16");
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+}
+inline void check_f32(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == at::kFloat, name, " must be fp32");
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+}
+template <typename T>
+inline T* opt_ptr(const c10::optional<Tensor>& t) {
+  return t.has_value() && t->defined() ? reinterpret_cast<T*>(t->data_ptr()) : nullptr;
+}
+
+// ------------------------------------------------------------------ batch norm (NHWC, [M, C])
+void bn_stats(const Tensor& x, Tensor& sums) {
+  check_bf16(x, "x");
+  check_f32(sums, "sums");
+  const int C = x.size(-1);
+  const int64_t M = x.numel() / C;
+  TORCH_CHECK(C % 8 == 0 && sums.numel() == 2 * C);
+  c10::cuda::CUDAGuard g(x.device());
+  edl::bn_stats(x.data_ptr(), sums.data_ptr<float>(), M, C, cur_stream());
+}
+
+void bn_apply(const Tensor& x, const c10::optional<Tensor>& res, Tensor& y, const Tensor& sums,
+              const Tensor& gamma, const Tensor& beta, const c10::optional<Tensor>& running_mean,
+              const c10::optional<Tensor>& running_var, Tensor& saved_mean, Tensor& saved_rstd,
+              double eps, double momentum, bool relu) {
+  check_bf16(x, "x");
+  check_bf16(y, "y");
+  check_f32(gamma, "gamma");
+  check_f32(beta, "beta");
+  const int C = x.size(-1);
+  const int64_t M = x.numel() / C;
+  c10::cuda::CUDAGuard g(x.device());
+  edl::bn_apply(x.data_ptr(), opt_ptr<void>(res), y.data_ptr(), sums.data_ptr<float>(),
+                gamma.data_ptr<float>(), beta.data_ptr<float>(), opt_ptr<float>(running_mean),
+                opt_ptr<float>(running_var), saved_mean.data_ptr<float>(),
+                saved_rstd.data_ptr<float>(), M, C, (float)eps, (float)momentum, relu,
+                cur_stream());
+}
+
+void scale_shift_act(const Tensor& x, const c10::optional<Tensor>& res, Tensor& y,
+                     const Tensor& scale, const Tensor& shift, bool relu) {
+  check_bf16(x, "x");
+  check_bf16(y, "y");
+  check_f32(scale, "scale");
+  check_f32(shift, "shift");
+  const int C = x.size(-1);
+  const int64_t M = x.numel() / C;
+  c10::cuda::CUDAGuard g(x.device());
+  edl::scale_shift_act(x.data_ptr(), opt_ptr<void>(res), y.data_ptr(), scale.data_ptr<float>(),
+                       shift.data_ptr<float>(), M, C, relu, cur_stream());
+}
+
+void bn_bwd_reduce(const Tensor& dy, const Tensor& x, const c10::optional<Tensor>& y,
+                   const Tensor& saved_mean, const Tensor& saved_rstd, Tensor& dsums, bool relu) {
+  check_bf16(dy, "dy");
+  check_bf16(x, "x");
+  const int C = x.size(-1);
+  const int64_t M = x.numel() / C;
+  TORCH_CHECK(!relu || (y.has_value() && y->defined()), "relu backward needs y");
+  c10::cuda::CUDAGuard g(x.device());
+  edl::bn_bwd_reduce(dy.data_ptr(), x.data_ptr(), opt_ptr<void>(y), saved_mean.data_ptr<float>(),
+                     saved_rstd.data_ptr<float>(), dsums.data_ptr<float>(), M, C, relu,
+                     cur_stream());
+}
+
+void bn_bwd_apply(const Tensor& dy, const Tensor& x, const c10::optional<Tensor>& y,
+                  const Tensor& gamma, const Tensor& saved_mean, const Tensor& saved_rstd,
+                  const Tensor& dsums, Tensor& dx, const c10::optional<Tensor>& dres,
+                  const c10::optional<Tensor>& dgamma, const c10::optional<Tensor>& dbeta,
+                  bool relu, bool accumulate) {
+  check_bf16(dy, "dy");
+  check_bf16(x, "x");
+  check_bf16(dx, "dx");
+  const int C = x.size(-1);
+  const int64_t M = x.numel() / C;
+  c10::cuda::CUDAGuard g(x.device());
+  edl::bn_bwd_apply(dy.data_ptr(), x.data_ptr(), opt_ptr<void>(y), gamma.data_ptr<float>(),
+                    saved_mean.data_ptr<float>(), saved_rstd.data_ptr<float>(),
+                    dsums.data_ptr<float>(), dx.data_ptr(), opt_ptr<void>(dres),
+                    opt_ptr<float>(dgamma), opt_ptr<float>(dbeta), M, C, relu, accumulate,
+                    cur_stream());
+}
+
+// ------------------------------------------------------------------ optimizers
+void sgd_momentum(const c10::optional<Tensor>& param_lp, Tensor& master, Tensor& mom,
+                  const Tensor& grad, const c10::optional<Tensor>& wd_mask, const Tensor& lr,
+                  const c10::optional<Tensor>& grad_scale, const c10::optional<Tensor>& found_inf,
+                  double momentum, double wd, bool nesterov) {
+  check_f32(master, "master");
+  check_f32(mom, "mom");
+  check_f32(lr, "lr");
+  TORCH_CHECK(grad.is_cuda() && grad.is_contiguous());
+  const bool gbf = grad.scalar_type() == at::kBFloat16;
+  TORCH_CHECK(gbf || grad.scalar_type() == at::kFloat);
+  const int64_t n = master.numel();
+  TORCH_CHECK(grad.numel() == n && mom.numel() == n);
+  c10::cuda::CUDAGuard g(master.device());
+  edl::sgd_momentum(opt_ptr<void>(param_lp), master.data_ptr<float>(), mom.data_ptr<float>(),
+                    grad.data_ptr(), gbf, opt_ptr<float>(wd_mask), n, lr.data_ptr<float>(),
+                    opt_ptr<float>(grad_scale), opt_ptr<int>(found_inf), (float)momentum,
+                    (float)wd, nesterov, cur_stream());
+}
+
+void adam_step(const c10::optional<Tensor>& param_lp, Tensor& master, Tensor& m, Tensor& v,
+               const Tensor& grad, const Tensor& lr, const c10::optional<Tensor>& grad_scale,
+               const c10::optional<Tensor>& found_inf, const Tensor& step, double beta1,
+               double beta2, double eps, double wd, bool decoupled) {
+  check_f32(master, "master");
+  const bool gbf = grad.scalar_type() == at::kBFloat16;
+  const int64_t n = master.numel();
+  c10::cuda::CUDAGuard g(master.device());
+  edl::adam_step(opt_ptr<void>(param_lp), master.data_ptr<float>(), m.data_ptr<float>(),
+                 v.data_ptr<float>(), grad.data_ptr(), gbf, n, lr.data_ptr<float>(),
+                 opt_ptr<float>(grad_scale), opt_ptr<int>(found_inf), step.data_ptr<float>(),
+                 (float)beta1, (float)beta2, (float)eps, (float)wd, decoupled, cur_stream());
+}
+
+// ------------------------------------------------------------------ losses
+void soft_ce_fwd(const Tensor& logits, const c10::optional<Tensor>& target,
+                 const c10::optional<Tensor>& labels, Tensor& loss_out, Tensor& row_stats,
+                 int64_t mode, double s_temp, double t_temp, double label_smooth, bool kl,
+                 double loss_scale) {
+  TORCH_CHECK(logits.is_cuda() && logits.is_contiguous() && logits.dim() == 2);
+  const int N = logits.size(0), C = logits.size(1);
+  const bool lbf = logits.scalar_type() == at::kBFloat16;
+  bool tbf = false;
+  if (mode != 2) {
+    TORCH_CHECK(target.has_value() && target->is_contiguous() && target->numel() == logits.numel());
+    tbf = target->scalar_type() == at::kBFloat16;
+    TORCH_CHECK(tbf || target->scalar_type() == at::kFloat);
+  } else {
+    TORCH_CHECK(labels.has_value() && labels->scalar_type() == at::kLong);
+  }
+  c10::cuda::CUDAGuard g(logits.device());
+  edl::soft_ce_fwd(logits.data_ptr(), lbf, opt_ptr<void>(target), tbf, opt_ptr<int64_t>(labels),
+                   loss_out.data_ptr<float>(), row_stats.data_ptr<float>(), N, C, (int)mode,
+                   (float)s_temp, (float)t_temp, (float)label_smooth, kl, (float)loss_scale,
+                   cur_stream());
+}
+
+void soft_ce_bwd(const Tensor& logits, const c10::optional<Tensor>& target,
+                 const c10::optional<Tensor>& labels, const Tensor& row_stats,
+                 const c10::optional<Tensor>& grad_out, Tensor& dlogits, int64_t mode,
+                 double s_temp, double t_temp, double label_smooth, double loss_scale) {
+  const int N = logits.size(0), C = logits.size(1);
+  const bool lbf = logits.scalar_type() == at::kBFloat16;
+  const bool tbf = mode != 2 && target->scalar_type() == at::kBFloat16;
+  c10::cuda::CUDAGuard g(logits.device());
+  edl::soft_ce_bwd(logits.data_ptr(), lbf, opt_ptr<void>(target), tbf, opt_ptr<int64_t>(labels),
+                   row_stats.data_ptr<float>(), opt_ptr<float>(grad_out), dlogits.data_ptr(), N, C,
+                   (int)mode, (float)s_temp, (float)t_temp, (float)label_smooth,
+                   (float)loss_scale, cur_stream());
+}
+
+void topk_acc(const Tensor& logits, const Tensor& labels, Tensor& counts) {
+  const int N = logits.size(0), C = logits.size(1);
+  c10::cuda::CUDAGuard g(logits.device());
+  edl::topk_acc(logits.data_ptr(), logits.scalar_type() == at::kBFloat16,
+                labels.data_ptr<int64_t>(), counts.data_ptr<float>(), N, C, cur_stream());
+}
+
+// ------------------------------------------------------------------ pooling (NHWC)
+void maxpool3x3s2_fwd(const Tensor& x, Tensor& y, Tensor& idx) {
+  check_bf16(x, "x");
+  c10::cuda::CUDAGuard g(x.device());
+  edl::maxpool3x3s2_fwd(x.data_ptr(), y.data_ptr(), idx.data_ptr<uint8_t>(), x.size(0), x.size(1),
+                        x.size(2), x.size(3), cur_stream());
+}
+void maxpool3x3s2_bwd(const Tensor& dy, const Tensor& idx, Tensor& dx) {
+  check_bf16(dy, "dy");
+  c10::cuda::CUDAGuard g(dy.device());
+  edl::maxpool3x3s2_bwd(dy.data_ptr(), idx.data_ptr<uint8_t>(), dx.data_ptr(), dx.size(0),
+                        dx.size(1), dx.size(2), dx.size(3), cur_stream());
+}
+void avgpool2x2_fwd(const Tensor& x, Tensor& y) {
+  check_bf16(x, "x");
+  c10::cuda::CUDAGuard g(x.device());
+  edl::avgpool2x2_fwd(x.data_ptr(), y.data_ptr(), x.size(0), x.size(1), x.size(2), x.size(3),
+                      cur_stream());
+}
+void avgpool2x2_bwd(const Tensor& dy, Tensor& dx) {
+  check_bf16(dy, "dy");
+  c10::cuda::CUDAGuard g(dy.device());
+  edl::avgpool2x2_bwd(dy.data_ptr(), dx.data_ptr(), dx.size(0), dx.size(1), dx.size(2),
+                      dx.size(3), cur_stream());
+}
+void gap_fwd(const Tensor& x, Tensor& y) {
+  check_bf16(x, "x");
+  c10::cuda::CUDAGuard g(x.device());
+  edl::gap_fwd(x.data_ptr(), y.data_ptr(), x.size(0), x.size(1) * x.size(2), x.size(3),
+               cur_stream());
+}
+void gap_bwd(const Tensor& dy, Tensor& dx) {
+  check_bf16(dy, "dy");
+  c10::cuda::CUDAGuard g(dy.device());
+  edl::gap_bwd(dy.data_ptr(), dx.data_ptr(), dx.size(0), dx.size(1) * dx.size(2), dx.size(3),
+               cur_stream());
+}
+
+// ------------------------------------------------------------------ collectives
+edl::CommHandles make_handles(const std::vector<int64_t>& data_ptrs,
+                              const std::vector<int64_t>& sig_ptrs, int64_t mc_ptr, int64_t rank,
+                              double timeout_s) {
+  edl::CommHandles h{};
+  const int world = (int)data_ptrs.size();
+  TORCH_CHECK(world >= 1 && world <= edl::comm_max_world(), "unsupported world size ", world);
+  TORCH_CHECK(sig_ptrs.size() == data_ptrs.size());
+  for (int i = 0; i < world; ++i) {
+    h.data[i] = reinterpret_cast<void*>(data_ptrs[i]);
+    h.sig[i] = reinterpret_cast<void*>(sig_ptrs[i]);
+  }
+  h.mc_data = reinterpret_cast<void*>(mc_ptr);
+  h.rank = (int)rank;
+  h.world = world;
+  h.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  return h;
+}
+
+void allreduce_oneshot(const std::vector<int64_t>& data_ptrs, const std::vector<int64_t>& sig_ptrs,
+                       int64_t rank, Tensor& out, int64_t n, double scale,
+                       const c10::optional<Tensor>& found_inf, const c10::optional<Tensor>& sqnorm,
+                       int64_t nblocks, double timeout_s) {
+  auto h = make_handles(data_ptrs, sig_ptrs, 0, rank, timeout_s);
+  c10::cuda::CUDAGuard g(out.device());
+  edl::allreduce_oneshot(h, out.data_ptr(), out.scalar_type() == at::kBFloat16, n, (float)scale,
+                         opt_ptr<int>(found_inf), opt_ptr<float>(sqnorm), (int)nblocks,
+                         cur_stream());
+}
+
+void allreduce_twoshot(const std::vector<int64_t>& data_ptrs, const std::vector<int64_t>& sig_ptrs,
+                       int64_t mc_ptr, int64_t rank, const Tensor& local, int64_t n, double scale,
+                       const c10::optional<Tensor>& found_inf, const c10::optional<Tensor>& sqnorm,
+                       bool multimem, int64_t nblocks, double timeout_s) {
+  auto h = make_handles(data_ptrs, sig_ptrs, mc_ptr, rank, timeout_s);
+  const bool bf = local.scalar_type() == at::kBFloat16;
+  const int ve = bf ? 8 : 4;
+  TORCH_CHECK(n % ve == 0, "two-shot needs n to be a multiple of 16 bytes");
+  c10::cuda::CUDAGuard g(local.device());
+  edl::allreduce_twoshot(h, bf, n, (float)scale, opt_ptr<int>(found_inf), opt_ptr<float>(sqnorm),
+                         multimem, (int)nblocks, cur_stream());
+}
+
+void comm_broadcast(const std::vector<int64_t>& data_ptrs, const std::vector<int64_t>& sig_ptrs,
+                    int64_t rank, int64_t root, int64_t nbytes, int64_t nblocks, double timeout_s,
+                    const Tensor& local) {
+  auto h = make_handles(data_ptrs, sig_ptrs, 0, rank, timeout_s);
+  c10::cuda::CUDAGuard g(local.device());
+  edl::comm_broadcast(h, (int)root, nbytes, (int)nblocks, cur_stream());
+}
+
+void comm_allgather_scalars(const std::vector<int64_t>& data_ptrs,
+                            const std::vector<int64_t>& sig_ptrs, int64_t rank, const Tensor& in,
+                            Tensor& out, double timeout_s) {
+  auto h = make_handles(data_ptrs, sig_ptrs, 0, rank, timeout_s);
+  TORCH_CHECK(in.numel() <= 8);
+  c10::cuda::CUDAGuard g(in.device());
+  edl::comm_allgather_scalars(h, in.data_ptr<float>(), out.data_ptr<float>(), (int)in.numel(),
+                              cur_stream());
+}
+
+}  // namespace
+
+void register_gemm_bindings(pybind11::module_& m);  // gemm_bindings.cpp
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "edl_b200 sm_100a kernels";
+  m.def("bn_stats", &bn_stats);
+  m.def("bn_apply", &bn_apply);
+  m.def("scale_shift_act", &scale_shift_act);
+  m.def("bn_bwd_reduce", &bn_bwd_reduce);
+  m.def("bn_bwd_apply", &bn_bwd_apply);
+  m.def("sgd_momentum", &sgd_momentum);
+  m.def("adam_step", &adam_step);
+  m.def("soft_ce_fwd", &soft_ce_fwd);
+  m.def("soft_ce_bwd", &soft_ce_bwd);
+  m.def("topk_acc", &topk_acc);
+  m.def("maxpool3x3s2_fwd", &maxpool3x3s2_fwd);
+  m.def("maxpool3x3s2_bwd", &maxpool3x3s2_bwd);
+  m.def("avgpool2x2_fwd", &avgpool2x2_fwd);
+  m.def("avgpool2x2_bwd", &avgpool2x2_bwd);
+  m.def("gap_fwd", &gap_fwd);
+  m.def("gap_bwd", &gap_bwd);
+  m.def("allreduce_oneshot", &allreduce_oneshot);
+  m.def("allreduce_twoshot", &allreduce_twoshot);
+  m.def("comm_broadcast", &comm_broadcast);
+  m.def("comm_allgather_scalars", &comm_allgather_scalars);
+  m.def("comm_sig_words", &edl::comm_sig_words);
+  m.def("comm_error_word_offset", &edl::comm_error_word_offset);
+  register_gemm_bindings(m);
+}

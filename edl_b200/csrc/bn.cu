@@ -1,0 +1,354 @@
+// Fused NHWC batch-norm kernels (training + inference) for sm_100a.
+//
+// Covers SURVEY K2/K3: batch_norm(act=relu|None) + elementwise_add(act=relu)
+// (reference call sites: example/distill/resnet/models/resnet_vd.py:167-173,254,276 -- those are
+// Paddle/cuDNN library calls in the reference; this is an independent implementation).
+//
+// Layout: activations are [M, C] bf16 with C contiguous (NHWC flattened, M = N*H*W), C % 8 == 0.
+// Training forward  = bn_stats (per-channel sum / sum-of-squares, fp32 atomics)
+//                   + bn_apply (normalise, scale/shift, optional residual add, optional ReLU,
+//                               running-stat update, saved mean/rstd).
+// Training backward = bn_bwd_reduce (dbeta, dgamma with the ReLU mask folded in)
+//                   + bn_bwd_apply  (dx, optional dresidual, param grads).
+// All kernels are HBM-bound streaming kernels: 128-bit loads, 8 channels per thread, grid sized
+// to a multiple of the 148 SMs.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace edl {
+
+namespace {
+
+constexpr int kBnThreads = 256;
+constexpr int kUnroll = 4;
+
+struct BnGrid {
+  dim3 grid, block;
+};
+
+inline BnGrid bn_grid(int64_t M, int C, int target_blocks) {
+  int cvecs = C / 8;
+  int tx = cvecs < 32 ? cvecs : 32;
+  // tx must divide 256: cvecs is 4,8,16,... (C multiple of 32) or capped at 32.
+  int t = 1;
+  while (t * 2 <= tx) t *= 2;
+  tx = t;
+  int ty = kBnThreads / tx;
+  int gx = (cvecs + tx - 1) / tx;
+  int64_t row_iters = (M + (int64_t)ty * kUnroll - 1) / ((int64_t)ty * kUnroll);
+  int64_t gy = target_blocks / gx;
+  if (gy < 1) gy = 1;
+  if (gy > row_iters) gy = row_iters;
+  if (gy < 1) gy = 1;
+  BnGrid g;
+  g.grid = dim3(gx, (unsigned)gy);
+  g.block = dim3(tx, ty);
+  return g;
+}
+
+// Block-level reduction over threadIdx.y of NV float values per thread, result valid for ty==0.
+template <int NV>
+EDL_DEVICE void reduce_over_y(float (&v)[NV], float* smem) {
+  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+  // layout: smem[ty][k][tx] to keep bank conflicts away
+#pragma unroll
+  for (int k = 0; k < NV; ++k) smem[(ty * NV + k) * TX + tx] = v[k];
+  __syncthreads();
+  for (int s = TY >> 1; s > 0; s >>= 1) {
+    if (ty < s) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        smem[(ty * NV + k) * TX + tx] += smem[((ty + s) * NV + k) * TX + tx];
+    }
+    __syncthreads();
+  }
+  if (ty == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = smem[k * TX + tx];
+  }
+}
+
+__global__ void __launch_bounds__(kBnThreads)
+bn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, int64_t M, int C) {
+  extern __shared__ float smem[];
+  const int cvec = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = cvec * 8 < C;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  if (active) {
+    const int64_t stride = (int64_t)gridDim.y * blockDim.y;
+    int64_t r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+    const __nv_bfloat16* base = x + (int64_t)cvec * 8;
+    for (; r + (kUnroll - 1) * stride < M; r += kUnroll * stride) {
+      bf16x8 v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream(base + (r + u * stride) * C);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i] += f[i];
+          acc[8 + i] = fmaf(f[i], f[i], acc[8 + i]);
+        }
+      }
+    }
+    for (; r < M; r += stride) {
+      float f[8];
+      unpack8(ld_stream(base + r * C), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += f[i];
+        acc[8 + i] = fmaf(f[i], f[i], acc[8 + i]);
+      }
+    }
+  }
+  reduce_over_y<16>(acc, smem);
+  if (active && threadIdx.y == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sums[cvec * 8 + i], acc[i]);
+      atomicAdd(&sums[C + cvec * 8 + i], acc[8 + i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBnThreads)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                __nv_bfloat16* __restrict__ y, const float* __restrict__ sums,
+                const float* __restrict__ gamma, const float* __restrict__ beta,
+                float* __restrict__ running_mean, float* __restrict__ running_var,
+                float* __restrict__ saved_mean, float* __restrict__ saved_rstd, int64_t M, int C,
+                float eps, float momentum, int relu) {
+  const int cvec = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cvec * 8 >= C) return;
+  const int c0 = cvec * 8;
+  float scale[8], shift[8];
+  const float inv_m = 1.f / (float)M;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float mean = sums[c0 + i] * inv_m;
+    float var = fmaxf(sums[C + c0 + i] * inv_m - mean * mean, 0.f);
+    float rstd = rsqrtf(var + eps);
+    scale[i] = gamma[c0 + i] * rstd;
+    shift[i] = beta[c0 + i] - mean * scale[i];
+    if (blockIdx.y == 0 && threadIdx.y == 0) {
+      saved_mean[c0 + i] = mean;
+      saved_rstd[c0 + i] = rstd;
+      if (running_mean != nullptr) {
+        float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+        running_mean[c0 + i] = (1.f - momentum) * running_mean[c0 + i] + momentum * mean;
+        running_var[c0 + i] = (1.f - momentum) * running_var[c0 + i] + momentum * unbiased;
+      }
+    }
+  }
+  const int64_t stride = (int64_t)gridDim.y * blockDim.y;
+  for (int64_t r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y; r < M; r += stride) {
+    const int64_t off = r * C + c0;
+    float f[8];
+    unpack8(ld_stream(x + off), f);
+    if (res != nullptr) {
+      float g[8];
+      unpack8(ld_stream(res + off), g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], scale[i], shift[i]) + g[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], scale[i], shift[i]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
+    st_vec(y + off, pack8(f));
+  }
+}
+
+// Inference / folded form: y = act(x * scale + shift (+ res)).
+__global__ void __launch_bounds__(kBnThreads)
+scale_shift_act_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                       __nv_bfloat16* __restrict__ y, const float* __restrict__ scale_p,
+                       const float* __restrict__ shift_p, int64_t M, int C, int relu) {
+  const int cvec = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cvec * 8 >= C) return;
+  const int c0 = cvec * 8;
+  float scale[8], shift[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    scale[i] = scale_p[c0 + i];
+    shift[i] = shift_p[c0 + i];
+  }
+  const int64_t stride = (int64_t)gridDim.y * blockDim.y;
+  for (int64_t r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y; r < M; r += stride) {
+    const int64_t off = r * C + c0;
+    float f[8];
+    unpack8(ld_stream(x + off), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], scale[i], shift[i]);
+    if (res != nullptr) {
+      float g[8];
+      unpack8(ld_stream(res + off), g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += g[i];
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
+    st_vec(y + off, pack8(f));
+  }
+}
+
+// dsums[0:C] = sum(dy_masked), dsums[C:2C] = sum(dy_masked * xhat)
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ saved_mean,
+                     const float* __restrict__ saved_rstd, float* __restrict__ dsums, int64_t M,
+                     int C, int relu) {
+  extern __shared__ float smem[];
+  const int cvec = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = cvec * 8 < C;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  if (active) {
+    const int c0 = cvec * 8;
+    float mean[8], rstd[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mean[i] = saved_mean[c0 + i];
+      rstd[i] = saved_rstd[c0 + i];
+    }
+    const int64_t stride = (int64_t)gridDim.y * blockDim.y;
+    for (int64_t r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y; r < M; r += stride) {
+      const int64_t off = r * C + c0;
+      float g[8], f[8];
+      unpack8(ld_stream(dy + off), g);
+      unpack8(ld_stream(x + off), f);
+      if (relu) {
+        float o[8];
+        unpack8(ld_stream(y + off), o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += g[i];
+        acc[8 + i] = fmaf(g[i], (f[i] - mean[i]) * rstd[i], acc[8 + i]);
+      }
+    }
+  }
+  reduce_over_y<16>(acc, smem);
+  if (active && threadIdx.y == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&dsums[cvec * 8 + i], acc[i]);
+      atomicAdd(&dsums[C + cvec * 8 + i], acc[8 + i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
+                    const float* __restrict__ saved_mean, const float* __restrict__ saved_rstd,
+                    const float* __restrict__ dsums, __nv_bfloat16* __restrict__ dx,
+                    __nv_bfloat16* __restrict__ dres, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, int64_t M, int C, int relu, int accumulate) {
+  const int cvec = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cvec * 8 >= C) return;
+  const int c0 = cvec * 8;
+  const float inv_m = 1.f / (float)M;
+  float mean[8], rstd[8], k0[8], k1[8], k2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mean[i] = saved_mean[c0 + i];
+    rstd[i] = saved_rstd[c0 + i];
+    float db = dsums[c0 + i], dg = dsums[C + c0 + i];
+    float gr = gamma[c0 + i] * rstd[i];
+    // dx = gr * (dy - db/M - xhat * dg/M)
+    k0[i] = gr;
+    k1[i] = db * inv_m;
+    k2[i] = dg * inv_m;
+    if (blockIdx.y == 0 && threadIdx.y == 0 && dgamma != nullptr) {
+      if (accumulate) {
+        dgamma[c0 + i] += dg;
+        dbeta[c0 + i] += db;
+      } else {
+        dgamma[c0 + i] = dg;
+        dbeta[c0 + i] = db;
+      }
+    }
+  }
+  const int64_t stride = (int64_t)gridDim.y * blockDim.y;
+  for (int64_t r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y; r < M; r += stride) {
+    const int64_t off = r * C + c0;
+    float g[8], f[8];
+    unpack8(ld_stream(dy + off), g);
+    unpack8(ld_stream(x + off), f);
+    if (relu) {
+      float o[8];
+      unpack8(ld_stream(y + off), o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+    }
+    if (dres != nullptr) st_vec(dres + off, pack8(g));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float xhat = (f[i] - mean[i]) * rstd[i];
+      f[i] = k0[i] * (g[i] - k1[i] - xhat * k2[i]);
+    }
+    st_vec(dx + off, pack8(f));
+  }
+}
+
+}  // namespace
+
+#define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+#define BFW(p) reinterpret_cast<__nv_bfloat16*>(p)
+
+void bn_stats(const void* x, float* sums, int64_t M, int C, cudaStream_t stream) {
+  BnGrid g = bn_grid(M, C, kNumSMs * 4);
+  size_t smem = (size_t)kBnThreads * 16 * sizeof(float);
+  bn_stats_kernel<<<g.grid, g.block, smem, stream>>>(BF(x), sums, M, C);
+}
+
+void bn_apply(const void* x, const void* res, void* y, const float* sums, const float* gamma,
+              const float* beta, float* running_mean, float* running_var, float* saved_mean,
+              float* saved_rstd, int64_t M, int C, float eps, float momentum, bool relu,
+              cudaStream_t stream) {
+  BnGrid g = bn_grid(M, C, kNumSMs * 8);
+  bn_apply_kernel<<<g.grid, g.block, 0, stream>>>(BF(x), BF(res), BFW(y), sums, gamma, beta,
+                                                  running_mean, running_var, saved_mean,
+                                                  saved_rstd, M, C, eps, momentum, relu ? 1 : 0);
+}
+
+void scale_shift_act(const void* x, const void* res, void* y, const float* scale,
+                     const float* shift, int64_t M, int C, bool relu, cudaStream_t stream) {
+  BnGrid g = bn_grid(M, C, kNumSMs * 8);
+  scale_shift_act_kernel<<<g.grid, g.block, 0, stream>>>(BF(x), BF(res), BFW(y), scale, shift, M,
+                                                         C, relu ? 1 : 0);
+}
+
+void bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* saved_mean,
+                   const float* saved_rstd, float* dsums, int64_t M, int C, bool relu,
+                   cudaStream_t stream) {
+  BnGrid g = bn_grid(M, C, kNumSMs * 4);
+  size_t smem = (size_t)kBnThreads * 16 * sizeof(float);
+  bn_bwd_reduce_kernel<<<g.grid, g.block, smem, stream>>>(BF(dy), BF(x), BF(y), saved_mean,
+                                                          saved_rstd, dsums, M, C, relu ? 1 : 0);
+}
+
+void bn_bwd_apply(const void* dy, const void* x, const void* y, const float* gamma,
+                  const float* saved_mean, const float* saved_rstd, const float* dsums, void* dx,
+                  void* dres, float* dgamma, float* dbeta, int64_t M, int C, bool relu,
+                  bool accumulate, cudaStream_t stream) {
+  BnGrid g = bn_grid(M, C, kNumSMs * 8);
+  bn_bwd_apply_kernel<<<g.grid, g.block, 0, stream>>>(
+      BF(dy), BF(x), BF(y), gamma, saved_mean, saved_rstd, dsums, BFW(dx), BFW(dres), dgamma,
+      dbeta, M, C, relu ? 1 : 0, accumulate ? 1 : 0);
+}
+
+}  // namespace edl

@@ -1,0 +1,67 @@
+// Shared device helpers for the edl_b200 sm_100a kernels.
+// Pure CUDA (no torch headers) so each .cu compiles in seconds with nvcc.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#define EDL_DEVICE __device__ __forceinline__
+
+namespace edl {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+EDL_DEVICE void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+EDL_DEVICE bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+// 128-bit streaming load/store (no L1 allocation) for one-touch data.
+EDL_DEVICE bf16x8 ld_stream(const void* ptr) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(ptr));
+  return *reinterpret_cast<bf16x8*>(&r);
+}
+EDL_DEVICE bf16x8 ld_vec(const void* ptr) { return *reinterpret_cast<const bf16x8*>(ptr); }
+EDL_DEVICE void st_vec(void* ptr, const bf16x8& v) { *reinterpret_cast<bf16x8*>(ptr) = v; }
+EDL_DEVICE void st_stream(void* ptr, const bf16x8& v) {
+  const int4& r = *reinterpret_cast<const int4*>(&v);
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(ptr), "r"(r.x),
+               "r"(r.y), "r"(r.z), "r"(r.w));
+}
+
+EDL_DEVICE float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+EDL_DEVICE float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <typename T>
+EDL_DEVICE T ceil_div(T a, T b) {
+  return (a + b - 1) / b;
+}
+
+}  // namespace edl

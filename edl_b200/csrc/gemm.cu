@@ -1,0 +1,364 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a with fused epilogues (SURVEY K1, K5 and the conv-as-GEMM
+// half of K2).  The reference gets these from cuDNN/cuBLAS via Paddle
+// (example/distill/resnet/models/resnet_vd.py:153-162 conv2d, :135-141 fc); this is an
+// independent Blackwell-native implementation.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T          (NHWC 1x1 conv fwd, FC)      A K-major,  B K-major
+//   D[M,N] = A[M,K] * B[K,N]            (1x1 conv dgrad)             A K-major,  B MN-major
+//   D[M,N] = A[K,M]^T * B[K,N]          (1x1 conv wgrad, split-K)    A MN-major, B MN-major
+//
+// Structure (one CTA per 128 x BLOCK_N output tile, 2 CTAs resident per SM):
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (fp32 accumulators in TMEM)
+//   warps 2..5  : epilogue: tcgen05.ld TMEM -> registers -> per-channel scale/shift/ReLU ->
+//                 bf16 -> swizzled smem -> TMA store; per-channel sum / sum^2 of the stored values
+//                 (train-mode BatchNorm statistics) reduced from the staged tile and pushed with
+//                 fp32 atomics, so BN needs no extra pass over the conv output.
+//                 Split-K variant: fp32 vector reductions (red.global.add.v4.f32) instead.
+#include <cuda.h>
+#include <cstdio>
+#include <mutex>
+
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace edl {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle span
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kEpiThreads = 128;
+
+struct GemmParams {
+  int M, N, K;
+  int kb_per_split;
+  const float* col_scale;
+  const float* col_shift;
+  int relu;
+  float* col_stats;  // [2N]
+  float* out_f32;    // split-K accumulation target, row-major [M, N]
+};
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kDBytes = BLOCK_M * BLOCK_N * 2;
+  static constexpr int kTileBytes =
+      STAGES * kStageBytes > kDBytes ? STAGES * kStageBytes : kDBytes;
+  static constexpr int kBarOffset = kTileBytes;
+  static constexpr int kTotal = kTileBytes + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 2)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int tile = blockIdx.x;
+  const int m0 = (tile / tiles_n) * BLOCK_M;
+  const int n0 = (tile % tiles_n) * BLOCK_N;
+  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  int kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > total_kb) kb_end = total_kb;
+  const int num_kb = kb_end - kb_begin;
+
+  constexpr uint32_t kTmemCols = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    if (EPI == 0) ptx::prefetch_tmap(&tmD);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      // ------------------------------------------------------------ TMA producer
+      if (lane == 0) {
+        for (int i = 0; i < num_kb; ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (i / STAGES) & 1;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
+          const int k0 = (kb_begin + i) * BLOCK_K;
+          if (!A_MN) {
+            ptx::tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
+          } else {
+#pragma unroll
+            for (int h = 0; h < BLOCK_M / 64; ++h)
+              ptx::tma_load_2d(sa + h * 8192, &tmA, &full_bar[s], m0 + h * 64, k0);
+          }
+          if (!B_MN) {
+            ptx::tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+          } else {
+#pragma unroll
+            for (int h = 0; h < BLOCK_N / 64; ++h)
+              ptx::tma_load_2d(sb + h * 8192, &tmB, &full_bar[s], n0 + h * 64, k0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------ MMA issuer (one thread)
+      if (lane == 0) {
+        constexpr uint32_t idesc =
+            ptx::make_idesc(1, 1, BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+        for (int i = 0; i < num_kb; ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (i / STAGES) & 1;
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + s * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = A_MN ? ptx::make_smem_desc(sa + k * 2048, 8192, 1024)
+                                     : ptx::make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? ptx::make_smem_desc(sb + k * 2048, 8192, 1024)
+                                     : ptx::make_smem_desc(sb + k * 32, 16, 1024);
+            ptx::umma_f16(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs have read it
+        }
+        ptx::umma_commit(tmem_full_bar);  // accumulator complete
+      }
+    } else {
+      // ------------------------------------------------------------ epilogue (warps 2..5)
+      const int q = warp & 3;             // TMEM lane quarter this warp may access
+      const int row = q * 32 + lane;      // accumulator row within the tile
+      const int et = threadIdx.x - 64;    // 0..127 epilogue thread id
+      ptx::mbar_wait(tmem_full_bar, 0);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      if (EPI == 0) {
+        uint8_t* sd = smem;  // pipeline stages are drained: reuse them as the store staging tile
+#pragma unroll 1
+        for (int c32 = 0; c32 < BLOCK_N / 32; ++c32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + c32 * 32, r);
+          ptx::tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
+          if (p.col_scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = n0 + c32 * 32 + j;
+              const float sc = col < p.N ? p.col_scale[col] : 0.f;
+              f[j] *= sc;
+            }
+          }
+          if (p.col_shift != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = n0 + c32 * 32 + j;
+              f[j] += col < p.N ? p.col_shift[col] : 0.f;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          const int half = c32 >> 1;
+          uint8_t* rowp = sd + half * (BLOCK_M * 128) + row * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int chunk = (c32 & 1) * 4 + c;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = f[c * 8 + j];
+            st_vec(rowp + ((chunk ^ (row & 7)) << 4), pack8(v));
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+#pragma unroll
+          for (int h = 0; h < (BLOCK_N + 63) / 64; ++h)
+            if (n0 + h * 64 < p.N) ptx::tma_store_2d(&tmD, sd + h * (BLOCK_M * 128), n0 + h * 64, m0);
+          ptx::tma_store_commit();
+        }
+        if (p.col_stats != nullptr) {
+          int rows_valid = p.M - m0;
+          if (rows_valid > BLOCK_M) rows_valid = BLOCK_M;
+          for (int col = et; col < BLOCK_N; col += kEpiThreads) {
+            if (n0 + col >= p.N) continue;
+            const int half = col >> 6, cc = col & 63, chunk = cc >> 3, within = cc & 7;
+            const uint8_t* base = sd + half * (BLOCK_M * 128) + within * 2;
+            float s = 0.f, sq = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < rows_valid; ++rr) {
+              const __nv_bfloat16 hv = *reinterpret_cast<const __nv_bfloat16*>(
+                  base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+              const float v = __bfloat162float(hv);
+              s += v;
+              sq = fmaf(v, v, sq);
+            }
+            atomicAdd(&p.col_stats[n0 + col], s);
+            atomicAdd(&p.col_stats[p.N + n0 + col], sq);
+          }
+        }
+        if (et == 0) ptx::tma_store_wait_read0();
+      } else {
+        // split-K: accumulate the fp32 partial tile into out_f32 with vector reductions
+        const int grow = m0 + row;
+#pragma unroll 1
+        for (int c32 = 0; c32 < BLOCK_N / 32; ++c32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + c32 * 32, r);
+          ptx::tmem_ld_wait();
+          if (grow < p.M) {
+            float* dst = p.out_f32 + (int64_t)grow * p.N + n0 + c32 * 32;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              if (n0 + c32 * 32 + c * 4 + 3 < p.N) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + c * 4),
+                             "f"(__uint_as_float(r[c * 4])), "f"(__uint_as_float(r[c * 4 + 1])),
+                             "f"(__uint_as_float(r[c * 4 + 2])), "f"(__uint_as_float(r[c * 4 + 3]))
+                             : "memory");
+              } else {
+                for (int j = 0; j < 4; ++j)
+                  if (n0 + c32 * 32 + c * 4 + j < p.N)
+                    atomicAdd(dst + c * 4 + j, __uint_as_float(r[c * 4 + j]));
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// host side
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: dims {inner, outer}, row pitch in elements, box {box_inner, box_outer}.
+bool make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
+                  uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int EPI>
+const char* launch_variant(const GemmArgs& g, cudaStream_t stream) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  CUtensorMap tmA, tmB, tmD;
+  bool ok = true;
+  // A: K-major -> global [M rows][K] ; MN-major -> global [K rows][M]
+  if (!A_MN) ok &= make_tmap_2d(&tmA, g.A, g.K, g.M, g.lda, BLOCK_K, BLOCK_M);
+  else ok &= make_tmap_2d(&tmA, g.A, g.M, g.K, g.lda, 64, BLOCK_K);
+  if (!B_MN) ok &= make_tmap_2d(&tmB, g.B, g.K, g.N, g.ldb, BLOCK_K, BLOCK_N);
+  else ok &= make_tmap_2d(&tmB, g.B, g.N, g.K, g.ldb, 64, BLOCK_K);
+  if (EPI == 0) ok &= make_tmap_2d(&tmD, g.D, g.N, g.M, g.ldd, BLOCK_N < 64 ? BLOCK_N : 64, BLOCK_M);
+  else tmD = tmA;
+  if (!ok) return "cuTensorMapEncodeTiled failed";
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, STAGES, A_MN, B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    attr_set = true;
+  }
+  GemmParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  const int total_kb = (g.K + BLOCK_K - 1) / BLOCK_K;
+  int split = EPI == 1 ? (g.split_k < 1 ? 1 : g.split_k) : 1;
+  if (split > total_kb) split = total_kb;
+  p.kb_per_split = (total_kb + split - 1) / split;
+  split = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.col_scale = g.col_scale;
+  p.col_shift = g.col_shift;
+  p.relu = g.relu ? 1 : 0;
+  p.col_stats = g.col_stats;
+  p.out_f32 = g.out_f32;
+  const int tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M;
+  const int tiles_n = (g.N + BLOCK_N - 1) / BLOCK_N;
+  dim3 grid(tiles_m * tiles_n, 1, split);
+  kern<<<grid, kGemmThreads, L::kTotal, stream>>>(tmA, tmB, tmD, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace
+
+const char* gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return "empty GEMM";
+  const bool n64 = g.N <= 64;
+  if (g.out_f32 != nullptr) {
+    // split-K fp32 accumulation (wgrad): both operands MN-major or both K-major
+    if (g.a_mn_major && g.b_mn_major)
+      return n64 ? launch_variant<64, 4, true, true, 1>(g, stream)
+                 : launch_variant<128, 3, true, true, 1>(g, stream);
+    if (!g.a_mn_major && !g.b_mn_major)
+      return n64 ? launch_variant<64, 4, false, false, 1>(g, stream)
+                 : launch_variant<128, 3, false, false, 1>(g, stream);
+    return "unsupported split-K operand layout";
+  }
+  if (!g.a_mn_major && !g.b_mn_major)
+    return n64 ? launch_variant<64, 4, false, false, 0>(g, stream)
+               : launch_variant<128, 3, false, false, 0>(g, stream);
+  if (!g.a_mn_major && g.b_mn_major)
+    return n64 ? launch_variant<64, 4, false, true, 0>(g, stream)
+               : launch_variant<128, 3, false, true, 0>(g, stream);
+  return "unsupported operand layout";
+}
+
+}  // namespace edl

@@ -1,0 +1,27 @@
+// Host API of the tcgen05 GEMM / implicit-GEMM conv kernels (gemm.cu, conv.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace edl {
+
+struct GemmArgs {
+  const void* A = nullptr;  // bf16
+  const void* B = nullptr;  // bf16
+  void* D = nullptr;        // bf16 [M, N] (ignored when out_f32 != nullptr)
+  int M = 0, N = 0, K = 0;
+  int64_t lda = 0, ldb = 0, ldd = 0;  // row pitches in elements of the *stored* 2-D arrays
+  bool a_mn_major = false;            // A stored as [K, M] (M contiguous)
+  bool b_mn_major = false;            // B stored as [K, N] (N contiguous); default B is [N, K]
+  const float* col_scale = nullptr;   // per-output-column scale (folded BN) or nullptr
+  const float* col_shift = nullptr;   // per-output-column shift / bias or nullptr
+  bool relu = false;
+  float* col_stats = nullptr;         // [2N] fp32: += sum, sum of squares of the stored outputs
+  float* out_f32 = nullptr;           // split-K target: fp32 [M, N], += A*B
+  int split_k = 1;
+};
+
+// Returns nullptr on success, else a static error string.
+const char* gemm_bf16(const GemmArgs& args, cudaStream_t stream);
+
+}  // namespace edl

@@ -1,0 +1,62 @@
+// torch bindings for the tcgen05 GEMM (gemm.cu).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include "gemm.h"
+
+namespace {
+using torch::Tensor;
+
+template <typename T>
+inline T* optp(const c10::optional<Tensor>& t) {
+  return t.has_value() && t->defined() ? reinterpret_cast<T*>(t->data_ptr()) : nullptr;
+}
+
+// D[M,N] = A * B with the operand layouts described in gemm.h.  A, B, D are 2-D bf16 tensors whose
+// last dimension is contiguous (row pitch = stride(0)).
+void gemm_bf16(const Tensor& A, const Tensor& B, const c10::optional<Tensor>& D, bool a_mn_major,
+               bool b_mn_major, const c10::optional<Tensor>& col_scale,
+               const c10::optional<Tensor>& col_shift, bool relu,
+               const c10::optional<Tensor>& col_stats, const c10::optional<Tensor>& out_f32,
+               int64_t split_k) {
+  TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.dim() == 2 && B.dim() == 2);
+  TORCH_CHECK(A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1, "operands need a contiguous last dim");
+  edl::GemmArgs g;
+  g.A = A.data_ptr();
+  g.B = B.data_ptr();
+  g.a_mn_major = a_mn_major;
+  g.b_mn_major = b_mn_major;
+  g.M = a_mn_major ? A.size(1) : A.size(0);
+  g.K = a_mn_major ? A.size(0) : A.size(1);
+  g.N = b_mn_major ? B.size(1) : B.size(0);
+  const int64_t kb = b_mn_major ? B.size(0) : B.size(1);
+  TORCH_CHECK(kb == g.K, "K mismatch: ", kb, " vs ", g.K);
+  g.lda = A.stride(0);
+  g.ldb = B.stride(0);
+  TORCH_CHECK(g.lda % 8 == 0 && g.ldb % 8 == 0, "row pitch must be a multiple of 16 bytes");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(g.A) % 16 == 0 && reinterpret_cast<uintptr_t>(g.B) % 16 == 0);
+  if (out_f32.has_value() && out_f32->defined()) {
+    TORCH_CHECK(out_f32->scalar_type() == at::kFloat && out_f32->is_contiguous());
+    TORCH_CHECK(out_f32->size(0) == g.M && out_f32->size(1) == g.N);
+    g.out_f32 = out_f32->data_ptr<float>();
+    g.split_k = (int)split_k;
+  } else {
+    TORCH_CHECK(D.has_value() && D->defined() && D->scalar_type() == at::kBFloat16);
+    TORCH_CHECK(D->dim() == 2 && D->size(0) == g.M && D->size(1) == g.N && D->stride(1) == 1);
+    g.D = D->data_ptr();
+    g.ldd = D->stride(0);
+    TORCH_CHECK(g.ldd % 8 == 0 && reinterpret_cast<uintptr_t>(g.D) % 16 == 0);
+  }
+  g.col_scale = optp<float>(col_scale);
+  g.col_shift = optp<float>(col_shift);
+  g.relu = relu;
+  g.col_stats = optp<float>(col_stats);
+  c10::cuda::CUDAGuard guard(A.device());
+  const char* err = edl::gemm_bf16(g, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(err == nullptr, "edl gemm_bf16 failed: ", err);
+}
+}  // namespace
+
+void register_gemm_bindings(pybind11::module_& m) { m.def("gemm_bf16", &gemm_bf16); }

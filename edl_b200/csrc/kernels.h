@@ -1,0 +1,78 @@
+// Host-side launcher declarations for the edl_b200 sm_100a kernels.
+// Kernels live in torch-free .cu files; bindings.cpp adapts torch tensors to these entry points.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace edl {
+
+// ---- bn.cu ----
+void bn_stats(const void* x, float* sums, int64_t M, int C, cudaStream_t stream);
+void bn_apply(const void* x, const void* res, void* y, const float* sums, const float* gamma,
+              const float* beta, float* running_mean, float* running_var, float* saved_mean,
+              float* saved_rstd, int64_t M, int C, float eps, float momentum, bool relu,
+              cudaStream_t stream);
+void scale_shift_act(const void* x, const void* res, void* y, const float* scale,
+                     const float* shift, int64_t M, int C, bool relu, cudaStream_t stream);
+void bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* saved_mean,
+                   const float* saved_rstd, float* dsums, int64_t M, int C, bool relu,
+                   cudaStream_t stream);
+void bn_bwd_apply(const void* dy, const void* x, const void* y, const float* gamma,
+                  const float* saved_mean, const float* saved_rstd, const float* dsums, void* dx,
+                  void* dres, float* dgamma, float* dbeta, int64_t M, int C, bool relu,
+                  bool accumulate, cudaStream_t stream);
+
+// ---- optim.cu ----
+void sgd_momentum(void* param_lp, float* master, float* mom, const void* grad, bool grad_is_bf16,
+                  const float* wd_mask, int64_t n, const float* lr, const float* grad_scale,
+                  const int* found_inf, float momentum, float wd, bool nesterov,
+                  cudaStream_t stream);
+void adam_step(void* param_lp, float* master, float* m, float* v, const void* grad,
+               bool grad_is_bf16, int64_t n, const float* lr, const float* grad_scale,
+               const int* found_inf, const float* step, float beta1, float beta2, float eps,
+               float wd, bool decoupled, cudaStream_t stream);
+
+// ---- loss.cu ----
+void soft_ce_fwd(const void* logits, bool logits_bf16, const void* target, bool target_bf16,
+                 const int64_t* labels, float* loss_out, float* row_stats, int N, int C, int mode,
+                 float s_temp, float t_temp, float label_smooth, bool kl, float loss_scale,
+                 cudaStream_t stream);
+void soft_ce_bwd(const void* logits, bool logits_bf16, const void* target, bool target_bf16,
+                 const int64_t* labels, const float* row_stats, const float* grad_out,
+                 void* dlogits, int N, int C, int mode, float s_temp, float t_temp,
+                 float label_smooth, float loss_scale, cudaStream_t stream);
+void topk_acc(const void* logits, bool logits_bf16, const int64_t* labels, float* counts, int N,
+              int C, cudaStream_t stream);
+
+// ---- pool.cu ----
+void maxpool3x3s2_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C,
+                      cudaStream_t s);
+void maxpool3x3s2_bwd(const void* dy, const uint8_t* idx, void* dx, int N, int H, int W, int C,
+                      cudaStream_t s);
+void avgpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, cudaStream_t s);
+void avgpool2x2_bwd(const void* dy, void* dx, int N, int H, int W, int C, cudaStream_t s);
+void gap_fwd(const void* x, void* y, int N, int HW, int C, cudaStream_t s);
+void gap_bwd(const void* dy, void* dx, int N, int HW, int C, cudaStream_t s);
+
+// ---- allreduce.cu ----
+struct CommHandles {
+  void* data[16];
+  void* sig[16];
+  void* mc_data;
+  int rank;
+  int world;
+  unsigned long long timeout_ns;
+};
+int comm_sig_words();
+int comm_max_world();
+int comm_error_word_offset();
+void allreduce_oneshot(const CommHandles& h, void* out, bool is_bf16, int64_t n, float scale,
+                       int* found_inf, float* sqnorm, int nblocks, cudaStream_t stream);
+void allreduce_twoshot(const CommHandles& h, bool is_bf16, int64_t n, float scale, int* found_inf,
+                       float* sqnorm, bool multimem, int nblocks, cudaStream_t stream);
+void comm_broadcast(const CommHandles& h, int root, int64_t nbytes, int nblocks,
+                    cudaStream_t stream);
+void comm_allgather_scalars(const CommHandles& h, const float* in, float* out, int count,
+                            cudaStream_t stream);
+
+}  // namespace edl

@@ -1,0 +1,190 @@
+"""ResNet-vd family (the distillation *student*), NHWC / bf16, built from the fused sm_100a ops.
+
+Architecture follows the reference definition example/distill/resnet/models/resnet_vd.py:43-143,
+213-291 (3x3x3 deep stem, stride on the 3x3 of the bottleneck, avg-pool + 1x1 "vd" shortcut) --
+re-expressed as ConvBNAct units whose 1x1 convolutions run on the tcgen05 GEMM with the BatchNorm
+statistics reduced in the GEMM epilogue, and whose BN-apply / residual-add / ReLU are one kernel.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..ops.bn import BatchNormAct2d
+
+
+class ConvBNAct(nn.Module):
+    """conv (no bias) -> train-mode BN -> (+ residual) -> (ReLU), as 2-3 kernels.
+
+    The weight is stored KRSC (``[Cout, kh, kw, Cin]``), i.e. already in the layout the NHWC
+    implicit GEMM consumes; torch/cuDNN sees it through a zero-copy ``permute`` view."""
+
+    def __init__(self, cin, cout, k, stride=1, relu=True, groups=1, impl="auto"):
+        super().__init__()
+        self.cin, self.cout, self.k, self.stride, self.groups = cin, cout, k, stride, groups
+        self.weight = nn.Parameter(torch.empty(cout, k, k, cin // groups))
+        std = math.sqrt(2.0 / (k * k * cin // groups))
+        nn.init.normal_(self.weight, 0.0, std)
+        self.bn = BatchNormAct2d(cout, relu=relu)
+        self.impl = impl
+        self.fwd_stats: Optional[torch.Tensor] = None  # arena slice [2*cout], zeroed every step
+
+    def _use_gemm(self, x):
+        if self.impl == "cudnn":
+            return False
+        return (self.k == 1 and self.stride == 1 and self.groups == 1 and x.is_cuda
+                and x.dtype == torch.bfloat16 and self.cin % 8 == 0 and self.cout % 8 == 0)
+
+    def conv(self, x, want_stats):
+        if self._use_gemm(x):
+            stats = None
+            if want_stats:
+                stats = self.fwd_stats if self.fwd_stats is not None else torch.zeros(
+                    2 * self.cout, device=x.device, dtype=torch.float32)
+            return ops.conv1x1(x, self.weight, stats), stats
+        w = self.weight.permute(0, 3, 1, 2)
+        y = F.conv2d(x, w, None, self.stride, (self.k - 1) // 2, 1, self.groups)
+        return y, None
+
+    def forward(self, x, residual=None):
+        y, stats = self.conv(x, self.training)
+        if stats is None and self.training and y.is_cuda and self.fwd_stats is not None:
+            stats = ops.bn_stats_into(y, self.fwd_stats)  # arena slice: no per-layer alloc/memset
+        return self.bn(y, residual=residual, sums=stats)
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, cin, width, stride, if_first, impl):
+        super().__init__()
+        cout = width * 4
+        self.a = ConvBNAct(cin, width, 1, 1, True, impl=impl)
+        self.b = ConvBNAct(width, width, 3, stride, True, impl=impl)
+        self.c = ConvBNAct(width, cout, 1, 1, True, impl=impl)  # ReLU applied after the residual add
+        self.pool = False
+        self.short = None
+        if cin != cout or stride != 1 or if_first:
+            # vd shortcut: 2x2 avg-pool (ceil) then 1x1 conv; the very first block keeps a plain 1x1
+            self.pool = not if_first and stride != 1
+            self.short = ConvBNAct(cin, cout, 1, stride if (if_first or not self.pool) else 1, False,
+                                   impl=impl)
+
+    def forward(self, x):
+        if self.short is not None:
+            s = ops.avg_pool_2x2(x) if self.pool else x
+            s = self.short(s)
+        else:
+            s = x
+        y = self.a(x)
+        y = self.b(y)
+        return self.c(y, residual=s)
+
+
+class BasicBlock(nn.Module):
+    def __init__(self, cin, width, stride, if_first, impl):
+        super().__init__()
+        self.a = ConvBNAct(cin, width, 3, stride, True, impl=impl)
+        self.b = ConvBNAct(width, width, 3, 1, True, impl=impl)
+        self.pool = False
+        self.short = None
+        if cin != width or stride != 1 or if_first:
+            self.pool = not if_first and stride != 1
+            self.short = ConvBNAct(cin, width, 1, stride if (if_first or not self.pool) else 1,
+                                   False, impl=impl)
+
+    def forward(self, x):
+        if self.short is not None:
+            s = ops.avg_pool_2x2(x) if self.pool else x
+            s = self.short(s)
+        else:
+            s = x
+        return self.b(self.a(x), residual=s)
+
+
+class FCHead(nn.Module):
+    """Classifier parameters (uniform +-1/sqrt(fan_in) like the reference, resnet_vd.py:133-141)."""
+
+    def __init__(self, cin, class_dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(class_dim, cin))
+        self.bias = nn.Parameter(torch.zeros(class_dim, dtype=torch.float32))
+        stdv = 1.0 / math.sqrt(cin)
+        nn.init.uniform_(self.weight, -stdv, stdv)
+
+
+_DEPTHS = {18: [2, 2, 2, 2], 34: [3, 4, 6, 3], 50: [3, 4, 6, 3], 101: [3, 4, 23, 3],
+           152: [3, 8, 36, 3], 200: [3, 12, 48, 3]}
+
+
+class ResNetVd(nn.Module):
+    def __init__(self, layers=50, class_dim=1000, impl="auto", width_mult=1.0):
+        super().__init__()
+        assert layers in _DEPTHS, "supported layers are %s" % sorted(_DEPTHS)
+        depth = _DEPTHS[layers]
+        bottleneck = layers >= 50
+        w = [int(c * width_mult) for c in (64, 128, 256, 512)]
+        s0, s1 = max(8, int(32 * width_mult)), max(8, int(64 * width_mult))
+        self.stem = nn.Sequential(ConvBNAct(3, s0, 3, 2, True, impl=impl),
+                                  ConvBNAct(s0, s0, 3, 1, True, impl=impl),
+                                  ConvBNAct(s0, s1, 3, 1, True, impl=impl))
+        blocks: List[nn.Module] = []
+        cin = s1
+        for stage, n in enumerate(depth):
+            for i in range(n):
+                stride = 2 if i == 0 and stage != 0 else 1
+                if_first = stage == 0 and i == 0
+                if bottleneck:
+                    blocks.append(Bottleneck(cin, w[stage], stride, if_first, impl))
+                    cin = w[stage] * 4
+                else:
+                    blocks.append(BasicBlock(cin, w[stage], stride, if_first, impl))
+                    cin = w[stage]
+        self.blocks = nn.Sequential(*blocks)
+        # registered last (as a child module) so that reverse registration order == the order in
+        # which gradients become ready during backward (see parallel/flat.py)
+        self.fc = FCHead(cin, class_dim)
+        self.feat_dim = cin
+        self.impl = impl
+
+    @property
+    def fc_weight(self):
+        return self.fc.weight
+
+    @property
+    def fc_bias(self):
+        return self.fc.bias
+
+    def forward(self, x):
+        x = self.stem(x)
+        x = ops.max_pool_3x3_s2(x)
+        x = self.blocks(x)
+        x = ops.global_avg_pool(x)
+        if x.is_cuda and x.dtype == torch.bfloat16 and self.impl != "cudnn":
+            return ops.linear_bf16(x, self.fc_weight, self.fc_bias)
+        return F.linear(x, self.fc_weight, self.fc_bias.to(x.dtype))
+
+    def conv_bn_units(self):
+        return [m for m in self.modules() if isinstance(m, ConvBNAct)]
+
+
+def to_train_dtype(model: nn.Module, dtype=torch.bfloat16, device=None):
+    """Cast conv/fc weights to ``dtype`` while BN parameters, biases and running stats stay fp32."""
+    for m in model.modules():
+        for name, p in list(m.named_parameters(recurse=False)):
+            keep_fp32 = isinstance(m, BatchNormAct2d) or name.endswith("bias")
+            p.data = p.data.to(device=device, dtype=torch.float32 if keep_fp32 else dtype)
+        for name, b in list(m.named_buffers(recurse=False)):
+            m._buffers[name] = b.to(device=device)
+    return model
+
+
+def ResNet18_vd(**kw): return ResNetVd(18, **kw)
+def ResNet34_vd(**kw): return ResNetVd(34, **kw)
+def ResNet50_vd(**kw): return ResNetVd(50, **kw)
+def ResNet101_vd(**kw): return ResNetVd(101, **kw)
+def ResNet152_vd(**kw): return ResNetVd(152, **kw)
+def ResNet200_vd(**kw): return ResNetVd(200, **kw)

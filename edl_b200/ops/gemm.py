@@ -1,0 +1,148 @@
+"""tcgen05 GEMM front-end (csrc/gemm.cu): plain GEMM, Linear and NHWC 1x1 convolution with the
+train-mode BatchNorm statistics fused into the GEMM epilogue.
+
+Reference call sites are library ops: ``fluid.layers.conv2d`` (cuDNN) and ``fluid.layers.fc``
+(cuBLAS) in example/distill/resnet/models/resnet_vd.py:153-162,135-141."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .bn import _cl
+
+_NUM_SMS = 148
+
+
+def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, col_scale=None, col_shift=None,
+              relu=False, col_stats=None, out_f32=None, split_k=1):
+    """D = op(A) @ op(B): see csrc/gemm.h for the operand conventions.
+
+    default        : A [M, K], B [N, K]  -> D [M, N] = A @ B^T
+    b_mn_major     : B [K, N]            -> D = A @ B
+    a_mn_major     : A [K, M]            -> D = A^T @ op(B)
+    out_f32 given  : fp32 [M, N] += result, split over K across CTAs (no bf16 output)."""
+    from . import native, count_launch
+
+    m = a.shape[1] if a_mn_major else a.shape[0]
+    n = b.shape[1] if b_mn_major else b.shape[0]
+    if not a.is_cuda:
+        af = a.float().t() if a_mn_major else a.float()
+        bf = b.float() if b_mn_major else b.float().t()
+        d = af @ bf
+        if out_f32 is not None:
+            out_f32.add_(d)
+            return out_f32
+        if col_scale is not None:
+            d = d * col_scale.float()
+        if col_shift is not None:
+            d = d + col_shift.float()
+        if relu:
+            d = torch.relu(d)
+        d = d.to(torch.bfloat16)
+        if col_stats is not None:
+            col_stats[:n] += d.float().sum(0)
+            col_stats[n:] += (d.float() ** 2).sum(0)
+        if out is not None:
+            out.copy_(d)
+            return out
+        return d
+    if out_f32 is None and out is None:
+        out = torch.empty((m, n), device=a.device, dtype=torch.bfloat16)
+    native().gemm_bf16(a, b, out, a_mn_major, b_mn_major, col_scale, col_shift, relu, col_stats,
+                       out_f32, int(split_k))
+    count_launch()
+    return out if out_f32 is None else out_f32
+
+
+def _split_k_for(m, n, k):
+    tiles = ((m + 127) // 128) * ((n + 127) // 128 if n > 64 else 1)
+    kb = (k + 63) // 64
+    want = max(1, (2 * _NUM_SMS + tiles - 1) // tiles)
+    return max(1, min(want, max(1, kb // 2)))
+
+
+def _wgrad(dy2, x2, weight_shape, sink, ready):
+    """dW[Cout, Cin] = dy2[M, Cout]^T @ x2[M, Cin] with fp32 split-K accumulation."""
+    cout, cin = dy2.shape[1], x2.shape[1]
+    acc = torch.zeros((cout, cin), device=dy2.device, dtype=torch.float32)
+    gemm_bf16(dy2, x2, a_mn_major=True, b_mn_major=True, out_f32=acc,
+              split_k=_split_k_for(cout, cin, dy2.shape[0]))
+    if sink is not None:
+        sink.view(cout, cin).add_(acc)
+        if ready is not None:
+            ready()
+        return None
+    return acc.to(torch.bfloat16).view(weight_shape)
+
+
+class _Conv1x1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, stats, sink, ready):
+        x = _cl(x)
+        n, cin, h, wd = x.shape
+        cout = w.shape[0]
+        x2 = x.permute(0, 2, 3, 1).reshape(-1, cin)
+        w2 = w.reshape(cout, cin)
+        y = torch.empty((n, cout, h, wd), device=x.device, dtype=x.dtype,
+                        memory_format=torch.channels_last)
+        y2 = y.permute(0, 2, 3, 1).reshape(-1, cout)
+        gemm_bf16(x2, w2, out=y2, col_stats=stats)
+        ctx.save_for_backward(x, w)
+        ctx.sink, ctx.ready = sink, ready
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _cl(dy)
+        n, cin, h, wd = x.shape
+        cout = w.shape[0]
+        dy2 = dy.permute(0, 2, 3, 1).reshape(-1, cout)
+        x2 = x.permute(0, 2, 3, 1).reshape(-1, cin)
+        w2 = w.reshape(cout, cin)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm_bf16(dy2, w2, out=dx.permute(0, 2, 3, 1).reshape(-1, cin), b_mn_major=True)
+        dw = _wgrad(dy2, x2, w.shape, ctx.sink, ctx.ready) if ctx.needs_input_grad[1] else None
+        return dx, dw, None, None, None
+
+
+def conv1x1(x, weight, stats: Optional[torch.Tensor] = None):
+    """NHWC 1x1 stride-1 convolution as a tcgen05 GEMM.  ``weight``: [Cout, 1, 1, Cin] or
+    [Cout, Cin] bf16.  If ``stats`` (pre-zeroed fp32 [2*Cout]) is given, the epilogue accumulates
+    per-channel sum / sum-of-squares of the output for the following train-mode BatchNorm."""
+    sink = getattr(weight, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
+    ready = getattr(weight, "_edl_grad_ready", None) if sink is not None else None
+    return _Conv1x1Fn.apply(x, weight, stats, sink, ready)
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, relu):
+        x = x.contiguous()
+        y = gemm_bf16(x, w, col_shift=bias.float() if bias is not None else None, relu=relu)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.has_bias = bias is not None
+        ctx.bias_dtype = bias.dtype if bias is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        if y is not None:
+            dy = dy * (y > 0)
+        dx = gemm_bf16(dy, w, b_mn_major=True) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(dy, x, w.shape, None, None)
+        db = dy.float().sum(0).to(ctx.bias_dtype) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db, None
+
+
+def linear_bf16(x, weight, bias=None, relu=False):
+    """y = act(x @ weight^T + bias) on the tcgen05 GEMM (bias/activation fused in the epilogue).
+    x [M, K] bf16, weight [N, K] bf16, bias [N] (any float dtype)."""
+    return _LinearFn.apply(x, weight, bias, relu)

@@ -1,0 +1,6 @@
+"""Data-parallel engine: flat parameter storage, NVSwitch symmetric memory, fused all-reduce
+planning / overlap, elastic re-planning."""
+from .flat import FlatParams
+from .ddp import ElasticDataParallel, plan_buckets, choose_algo
+
+__all__ = ["FlatParams", "ElasticDataParallel", "plan_buckets", "choose_algo"]

@@ -1,0 +1,155 @@
+"""Public training-step API: ``StudentTrainer``.
+
+One object owns the model, the elastic data-parallel engine, the flat fused optimizer, the per-step
+scratch arena and (on CUDA) a captured CUDA graph of the WHOLE step:
+
+    zero grads/arena -> forward -> fused soft-CE -> backward (+ overlapped fused all-reduce buckets)
+    -> fused SGD-momentum
+
+so a replay costs one graph launch instead of ~600 kernel launches from Python.  The user-facing
+call is ``trainer.step(images, targets)`` with *host* (pinned) tensors: the H2D copies, the graph
+replay and the D2H read of the loss are what the end-to-end benchmark times.
+
+This is the B200 counterpart of the reference's ``train_exe.run(train_prog, feed=data)`` hot loop
+(example/distill/resnet/train_with_fleet.py:468-524).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .models.resnet_vd import ConvBNAct
+from .parallel import ElasticDataParallel
+
+
+class StepArena:
+    """One flat fp32 scratch buffer holding every BN layer's forward (sum, sum^2) and backward
+    (dbeta, dgamma) accumulators; zeroed with a single memset per step."""
+
+    def __init__(self, model: torch.nn.Module, device):
+        units = [m for m in model.modules() if isinstance(m, ConvBNAct)]
+        total = sum(4 * u.cout for u in units)
+        self.buf = torch.zeros(max(total, 4), dtype=torch.float32, device=device)
+        off = 0
+        for u in units:
+            u.fwd_stats = self.buf[off:off + 2 * u.cout]
+            off += 2 * u.cout
+            u.bn.bwd_ws = self.buf[off:off + 2 * u.cout]
+            off += 2 * u.cout
+
+    def zero(self):
+        self.buf.zero_()
+
+
+class StudentTrainer:
+    def __init__(self, model: torch.nn.Module, batch_size: int, image_shape=(3, 224, 224),
+                 num_classes: int = 1000, lr: float = 0.1, momentum: float = 0.9,
+                 weight_decay: float = 1e-4, target_kind: str = "probs",
+                 group: Optional[dist.ProcessGroup] = None, use_graph: bool = True,
+                 bucket_cap_mb: float = 16.0, comm_blocks: int = 32, algo: str = "auto",
+                 overlap: bool = True, dtype=torch.bfloat16, input_dtype=None,
+                 loss_fn: Optional[Callable] = None):
+        self.model = model
+        self.device = next(model.parameters()).device
+        self.cuda = self.device.type == "cuda"
+        self.batch_size = batch_size
+        self.dtype = dtype
+        self.target_kind = target_kind
+        self.loss_fn = loss_fn
+        self.dp = ElasticDataParallel(model, group=group, bucket_cap_mb=bucket_cap_mb,
+                                      comm_blocks=comm_blocks, algo=algo, overlap=overlap)
+        self.opt = ops.FlatSGDMomentum(self.dp.flat, lr=lr, momentum=momentum,
+                                       weight_decay=weight_decay)
+        self.arena = StepArena(model, self.device) if self.cuda else None
+        in_dtype = input_dtype if input_dtype is not None else dtype
+        self.static_x = torch.zeros((batch_size,) + tuple(image_shape), dtype=in_dtype,
+                                    device=self.device).contiguous(memory_format=torch.channels_last)
+        if target_kind == "labels":
+            self.static_t = torch.zeros(batch_size, dtype=torch.int64, device=self.device)
+        else:
+            self.static_t = torch.zeros(batch_size, num_classes, dtype=dtype, device=self.device)
+        self.static_loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.use_graph = use_graph and self.cuda
+        self.graph = None
+        self.steps_done = 0
+
+    # ------------------------------------------------------------------ one step on device
+    def _step_body(self):
+        self.dp.zero_grad()
+        if self.arena is not None:
+            self.arena.zero()
+        x = self.static_x
+        if x.dtype != self.dtype:
+            x = x.to(self.dtype)
+        logits = self.model(x)
+        if self.loss_fn is not None:
+            loss = self.loss_fn(logits, self.static_t)
+        else:
+            loss = ops.soft_cross_entropy(logits, self.static_t, target_kind=self.target_kind)
+        loss.backward()
+        self.dp.finish()
+        self.opt.step()
+        self.static_loss.copy_(loss.detach())
+
+    def capture(self, warmup: int = 3):
+        """Warm up on a side stream (cuDNN autotune, allocator) then capture the step graph."""
+        if not self.use_graph:
+            return
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step_body()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        if self.dp.world > 1:
+            dist.barrier(self.dp.group)
+        self.graph = torch.cuda.CUDAGraph()
+        before = ops.launches()
+        with torch.cuda.graph(self.graph):
+            self._step_body()
+        self.launches_per_step = ops.launches() - before
+        torch.cuda.synchronize(self.device)
+
+    def step_device(self):
+        """Run one optimizer step on whatever is currently in the static input buffers."""
+        if self.use_graph:
+            if self.graph is None:
+                self.capture()
+            self.graph.replay()
+            ops.count_launch(self.launches_per_step)
+        else:
+            self._step_body()
+        self.steps_done += 1
+        return self.static_loss
+
+    def step(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        """Public per-step call.  ``images`` / ``targets`` may live on the host (ideally pinned):
+        they are copied into the static device buffers, the step runs, and the device-resident
+        scalar loss is returned (``.item()`` it to read it back)."""
+        self.static_x.copy_(images, non_blocking=True)
+        self.static_t.copy_(targets, non_blocking=True)
+        return self.step_device()
+
+    def set_lr(self, lr: float):
+        self.opt.set_lr(lr)
+
+    # ------------------------------------------------------------------ elastic
+    def rebuild(self, group):
+        """World-size change: re-plan the communication, drop the captured graph."""
+        self.graph = None
+        self.dp.rebuild(group)
+
+    def state_dict(self):
+        return {"model": {k: v for k, v in self.model.state_dict().items()},
+                "optim": self.opt.state_dict(), "steps_done": self.steps_done}
+
+    def load_state_dict(self, sd):
+        self.model.load_state_dict(sd["model"])
+        self.dp.flat.sync_master_from_params()
+        self.opt.load_state_dict(sd["optim"])
+        self.steps_done = sd.get("steps_done", 0)
+        self.graph = None

@@ -1,0 +1,112 @@
+"""CPU-side logic of the training engine: flat storage, bucket planning, fused-optimizer reference
+path, gloo data-parallel equivalence (world_size 2)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from edl_b200 import ops
+from edl_b200.models import ResNetVd
+from edl_b200.parallel import ElasticDataParallel, FlatParams, plan_buckets, choose_algo
+
+
+def test_flat_params_views_and_order():
+    m = torch.nn.Sequential(torch.nn.Linear(10, 7), torch.nn.Linear(7, 3))
+    w0 = m[0].weight.detach().clone()
+    flat = FlatParams(m)
+    g = flat.groups[torch.float32]
+    assert torch.equal(m[0].weight, w0)
+    # reverse registration order: last layer's bias first
+    assert g.entries[0].name == "1.bias" and g.entries[-1].name == "0.weight"
+    for e in g.entries:
+        assert e.offset % 128 == 0
+        assert e.param.data_ptr() == g.param.data_ptr() + e.offset * 4
+        assert e.param.grad.data_ptr() == g.grad.data_ptr() + e.offset * 4
+    m(torch.randn(4, 10)).sum().backward()
+    assert g.grad.abs().sum() > 0
+    flat.zero_grad()
+    assert g.grad.abs().sum() == 0
+
+
+def test_bucket_plan_covers_everything():
+    m = ResNetVd(18, class_dim=10, width_mult=0.25)
+    flat = FlatParams(m)
+    buckets = plan_buckets(flat, 64 * 1024)
+    for dt, g in flat.groups.items():
+        bs = sorted([b for b in buckets if b.dtype == dt], key=lambda b: b.start)
+        assert bs[0].start == 0
+        for a, b in zip(bs, bs[1:]):
+            assert a.start + a.numel == b.start
+        assert bs[-1].start + bs[-1].numel == g.numel
+    assert [b.order for b in buckets] == sorted(b.order for b in buckets)
+    assert sum(len(b.entry_ids) for b in buckets) == len(list(flat.entries()))
+
+
+def test_choose_algo():
+    assert choose_algo(1 << 20, 1, False) == "none"
+    assert choose_algo(1 << 20, 8, True) == "multimem"
+    assert choose_algo(1 << 20, 8, False) == "twoshot"
+    assert choose_algo(1024, 8, True) == "twoshot"
+    assert choose_algo(1 << 20, 6, True, prefer="twoshot") == "twoshot"
+
+
+def test_sgd_cpu_matches_torch():
+    torch.manual_seed(0)
+    m = torch.nn.Linear(20, 5)
+    ref = torch.nn.Linear(20, 5)
+    ref.load_state_dict(m.state_dict())
+    flat = FlatParams(m)
+    opt = ops.FlatSGDMomentum(flat, lr=0.1, momentum=0.9, weight_decay=1e-3)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-3)
+    x = torch.randn(8, 20)
+    for _ in range(4):
+        flat.zero_grad()
+        ropt.zero_grad()
+        m(x).pow(2).sum().backward()
+        ref(x).pow(2).sum().backward()
+        opt.step()
+        ropt.step()
+    for p, q in zip(m.parameters(), ref.parameters()):
+        assert torch.allclose(p, q, atol=1e-5)
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    m = ResNetVd(18, class_dim=8, width_mult=0.125)
+    dp = ElasticDataParallel(m, bucket_cap_mb=0.05)
+    opt = ops.FlatSGDMomentum(dp.flat, lr=0.05)
+    torch.manual_seed(100)
+    xs = torch.randn(4, 3, 32, 32)
+    ts = torch.softmax(torch.randn(4, 8), -1)
+    x, t = xs[rank * 2:(rank + 1) * 2], ts[rank * 2:(rank + 1) * 2]
+    for _ in range(2):
+        dp.zero_grad()
+        loss = ops.soft_cross_entropy(dp(x.contiguous(memory_format=torch.channels_last)), t)
+        loss.backward()
+        dp.finish()
+        opt.step()
+    flat = torch.cat([g.param.flatten() for g in dp.flat.groups.values()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    if rank == 0:
+        q.put(float((gathered[0] - gathered[1]).abs().max()))
+    dist.destroy_process_group()
+
+
+def test_gloo_data_parallel_keeps_ranks_in_sync():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) < 1e-6
