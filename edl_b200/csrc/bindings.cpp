@@ -72,20 +72,22 @@ void scale_shift_act(const Tensor& x, const c10::optional<Tensor>& res, Tensor& 
 }
 
 void bn_bwd_reduce(const Tensor& dy, const Tensor& x, const c10::optional<Tensor>& y,
-                   const Tensor& saved_mean, const Tensor& saved_rstd, Tensor& dsums, bool relu) {
+                   const Tensor& gamma, const Tensor& beta, const Tensor& saved_mean,
+                   const Tensor& saved_rstd, Tensor& dsums, bool relu) {
   check_bf16(dy, "dy");
   check_bf16(x, "x");
   const int C = x.size(-1);
   const int64_t M = x.numel() / C;
-  TORCH_CHECK(!relu || (y.has_value() && y->defined()), "relu backward needs y");
   c10::cuda::CUDAGuard g(x.device());
-  edl::bn_bwd_reduce(dy.data_ptr(), x.data_ptr(), opt_ptr<void>(y), saved_mean.data_ptr<float>(),
+  edl::bn_bwd_reduce(dy.data_ptr(), x.data_ptr(), opt_ptr<void>(y), gamma.data_ptr<float>(),
+                     beta.data_ptr<float>(), saved_mean.data_ptr<float>(),
                      saved_rstd.data_ptr<float>(), dsums.data_ptr<float>(), M, C, relu,
                      cur_stream());
 }
 
 void bn_bwd_apply(const Tensor& dy, const Tensor& x, const c10::optional<Tensor>& y,
-                  const Tensor& gamma, const Tensor& saved_mean, const Tensor& saved_rstd,
+                  const Tensor& gamma, const Tensor& beta, const Tensor& saved_mean,
+                  const Tensor& saved_rstd,
                   const Tensor& dsums, Tensor& dx, const c10::optional<Tensor>& dres,
                   const c10::optional<Tensor>& dgamma, const c10::optional<Tensor>& dbeta,
                   bool relu, bool accumulate) {
@@ -96,7 +98,8 @@ void bn_bwd_apply(const Tensor& dy, const Tensor& x, const c10::optional<Tensor>
   const int64_t M = x.numel() / C;
   c10::cuda::CUDAGuard g(x.device());
   edl::bn_bwd_apply(dy.data_ptr(), x.data_ptr(), opt_ptr<void>(y), gamma.data_ptr<float>(),
-                    saved_mean.data_ptr<float>(), saved_rstd.data_ptr<float>(),
+                    beta.data_ptr<float>(), saved_mean.data_ptr<float>(),
+                    saved_rstd.data_ptr<float>(),
                     dsums.data_ptr<float>(), dx.data_ptr(), opt_ptr<void>(dres),
                     opt_ptr<float>(dgamma), opt_ptr<float>(dbeta), M, C, relu, accumulate,
                     cur_stream());

@@ -145,18 +145,46 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
     }
   }
   const int64_t stride = (int64_t)gridDim.y * blockDim.y;
-  for (int64_t r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y; r < M; r += stride) {
+  int64_t r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  // 4 rows per iteration: 4 (8 with a residual) independent 128-bit loads in flight per thread
+  for (; r + (kUnroll - 1) * stride < M; r += kUnroll * stride) {
+    bf16x8 xv[kUnroll], rv[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) xv[u] = ld_stream(x + (r + u * stride) * C + c0);
+    if (res != nullptr) {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) rv[u] = ld_stream(res + (r + u * stride) * C + c0);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      float f[8];
+      unpack8(xv[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], scale[i], shift[i]);
+      if (res != nullptr) {
+        float g[8];
+        unpack8(rv[u], g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += g[i];
+      }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+      }
+      st_vec(y + (r + u * stride) * C + c0, pack8(f));
+    }
+  }
+  for (; r < M; r += stride) {
     const int64_t off = r * C + c0;
     float f[8];
     unpack8(ld_stream(x + off), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], scale[i], shift[i]);
     if (res != nullptr) {
       float g[8];
       unpack8(ld_stream(res + off), g);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], scale[i], shift[i]) + g[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], scale[i], shift[i]);
+      for (int i = 0; i < 8; ++i) f[i] += g[i];
     }
     if (relu) {
 #pragma unroll
@@ -201,12 +229,47 @@ scale_shift_act_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward.  ReLU mask source:
+//   y != nullptr : mask = (y > 0)                      (needed when a residual was added)
+//   y == nullptr : mask = (x * scale + shift > 0)      recomputed with the forward's exact fmaf, so
+//                  the saved output is not read at all (one fewer pass over the activation)
 // dsums[0:C] = sum(dy_masked), dsums[C:2C] = sum(dy_masked * xhat)
+struct BwdCoef {
+  float mean[8], rstd[8], scale[8], shift[8];
+};
+
+EDL_DEVICE void load_coef(BwdCoef& k, const float* saved_mean, const float* saved_rstd,
+                          const float* gamma, const float* beta, int c0) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    k.mean[i] = saved_mean[c0 + i];
+    k.rstd[i] = saved_rstd[c0 + i];
+    k.scale[i] = gamma[c0 + i] * k.rstd[i];
+    k.shift[i] = beta[c0 + i] - k.mean[i] * k.scale[i];
+  }
+}
+
+template <bool HAS_Y>
+EDL_DEVICE void mask_grad(float (&g)[8], const float (&f)[8], const bf16x8& yv, const BwdCoef& k) {
+  if (HAS_Y) {
+    float o[8];
+    unpack8(yv, o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = fmaf(f[i], k.scale[i], k.shift[i]) > 0.f ? g[i] : 0.f;
+  }
+}
+
+template <bool RELU, bool HAS_Y>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
-                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ saved_mean,
+                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ saved_mean,
                      const float* __restrict__ saved_rstd, float* __restrict__ dsums, int64_t M,
-                     int C, int relu) {
+                     int C) {
   extern __shared__ float smem[];
   const int cvec = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = cvec * 8 < C;
@@ -215,28 +278,44 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   if (active) {
     const int c0 = cvec * 8;
-    float mean[8], rstd[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      mean[i] = saved_mean[c0 + i];
-      rstd[i] = saved_rstd[c0 + i];
-    }
+    BwdCoef k;
+    load_coef(k, saved_mean, saved_rstd, gamma, beta, c0);
     const int64_t stride = (int64_t)gridDim.y * blockDim.y;
-    for (int64_t r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y; r < M; r += stride) {
+    int64_t r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+    for (; r + (kUnroll - 1) * stride < M; r += kUnroll * stride) {
+      bf16x8 gv[kUnroll], xv[kUnroll], yv[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t off = (r + u * stride) * C + c0;
+        gv[u] = ld_stream(dy + off);
+        xv[u] = ld_stream(x + off);
+        if (RELU && HAS_Y) yv[u] = ld_stream(y + off);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        float g[8], f[8];
+        unpack8(gv[u], g);
+        unpack8(xv[u], f);
+        if (RELU) mask_grad<HAS_Y>(g, f, yv[u], k);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i] += g[i];
+          acc[8 + i] = fmaf(g[i], (f[i] - k.mean[i]) * k.rstd[i], acc[8 + i]);
+        }
+      }
+    }
+    for (; r < M; r += stride) {
       const int64_t off = r * C + c0;
       float g[8], f[8];
       unpack8(ld_stream(dy + off), g);
       unpack8(ld_stream(x + off), f);
-      if (relu) {
-        float o[8];
-        unpack8(ld_stream(y + off), o);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
-      }
+      bf16x8 yv;
+      if (RELU && HAS_Y) yv = ld_stream(y + off);
+      if (RELU) mask_grad<HAS_Y>(g, f, yv, k);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         acc[i] += g[i];
-        acc[8 + i] = fmaf(g[i], (f[i] - mean[i]) * rstd[i], acc[8 + i]);
+        acc[8 + i] = fmaf(g[i], (f[i] - k.mean[i]) * k.rstd[i], acc[8 + i]);
       }
     }
   }
@@ -250,26 +329,26 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   }
 }
 
+template <bool RELU, bool HAS_Y>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
-                    const float* __restrict__ saved_mean, const float* __restrict__ saved_rstd,
-                    const float* __restrict__ dsums, __nv_bfloat16* __restrict__ dx,
-                    __nv_bfloat16* __restrict__ dres, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta, int64_t M, int C, int relu, int accumulate) {
+                    const float* __restrict__ beta, const float* __restrict__ saved_mean,
+                    const float* __restrict__ saved_rstd, const float* __restrict__ dsums,
+                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int C,
+                    int accumulate) {
   const int cvec = blockIdx.x * blockDim.x + threadIdx.x;
   if (cvec * 8 >= C) return;
   const int c0 = cvec * 8;
   const float inv_m = 1.f / (float)M;
-  float mean[8], rstd[8], k0[8], k1[8], k2[8];
+  BwdCoef k;
+  load_coef(k, saved_mean, saved_rstd, gamma, beta, c0);
+  float k1[8], k2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    mean[i] = saved_mean[c0 + i];
-    rstd[i] = saved_rstd[c0 + i];
-    float db = dsums[c0 + i], dg = dsums[C + c0 + i];
-    float gr = gamma[c0 + i] * rstd[i];
-    // dx = gr * (dy - db/M - xhat * dg/M)
-    k0[i] = gr;
+    const float db = dsums[c0 + i], dg = dsums[C + c0 + i];
+    // dx = gamma*rstd * (dy - db/M - xhat * dg/M)
     k1[i] = db * inv_m;
     k2[i] = dg * inv_m;
     if (blockIdx.y == 0 && threadIdx.y == 0 && dgamma != nullptr) {
@@ -283,22 +362,45 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
     }
   }
   const int64_t stride = (int64_t)gridDim.y * blockDim.y;
-  for (int64_t r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y; r < M; r += stride) {
+  int64_t r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  for (; r + (kUnroll - 1) * stride < M; r += kUnroll * stride) {
+    bf16x8 gv[kUnroll], xv[kUnroll], yv[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t off = (r + u * stride) * C + c0;
+      gv[u] = ld_stream(dy + off);
+      xv[u] = ld_stream(x + off);
+      if (RELU && HAS_Y) yv[u] = ld_stream(y + off);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t off = (r + u * stride) * C + c0;
+      float g[8], f[8];
+      unpack8(gv[u], g);
+      unpack8(xv[u], f);
+      if (RELU) mask_grad<HAS_Y>(g, f, yv[u], k);
+      if (dres != nullptr) st_vec(dres + off, pack8(g));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xhat = (f[i] - k.mean[i]) * k.rstd[i];
+        f[i] = k.scale[i] * (g[i] - k1[i] - xhat * k2[i]);
+      }
+      st_vec(dx + off, pack8(f));
+    }
+  }
+  for (; r < M; r += stride) {
     const int64_t off = r * C + c0;
     float g[8], f[8];
     unpack8(ld_stream(dy + off), g);
     unpack8(ld_stream(x + off), f);
-    if (relu) {
-      float o[8];
-      unpack8(ld_stream(y + off), o);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
-    }
+    bf16x8 yv;
+    if (RELU && HAS_Y) yv = ld_stream(y + off);
+    if (RELU) mask_grad<HAS_Y>(g, f, yv, k);
     if (dres != nullptr) st_vec(dres + off, pack8(g));
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float xhat = (f[i] - mean[i]) * rstd[i];
-      f[i] = k0[i] * (g[i] - k1[i] - xhat * k2[i]);
+      const float xhat = (f[i] - k.mean[i]) * k.rstd[i];
+      f[i] = k.scale[i] * (g[i] - k1[i] - xhat * k2[i]);
     }
     st_vec(dx + off, pack8(f));
   }
@@ -332,23 +434,34 @@ void scale_shift_act(const void* x, const void* res, void* y, const float* scale
                                                          C, relu ? 1 : 0);
 }
 
-void bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* saved_mean,
-                   const float* saved_rstd, float* dsums, int64_t M, int C, bool relu,
-                   cudaStream_t stream) {
+void bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* gamma,
+                   const float* beta, const float* saved_mean, const float* saved_rstd,
+                   float* dsums, int64_t M, int C, bool relu, cudaStream_t stream) {
   BnGrid g = bn_grid(M, C, kNumSMs * 4);
   size_t smem = (size_t)kBnThreads * 16 * sizeof(float);
-  bn_bwd_reduce_kernel<<<g.grid, g.block, smem, stream>>>(BF(dy), BF(x), BF(y), saved_mean,
-                                                          saved_rstd, dsums, M, C, relu ? 1 : 0);
+#define LAUNCH(R, Y)                                                                         \
+  bn_bwd_reduce_kernel<R, Y><<<g.grid, g.block, smem, stream>>>(BF(dy), BF(x), BF(y), gamma, \
+                                                                beta, saved_mean, saved_rstd, \
+                                                                dsums, M, C)
+  if (!relu) LAUNCH(false, false);
+  else if (y != nullptr) LAUNCH(true, true);
+  else LAUNCH(true, false);
+#undef LAUNCH
 }
 
 void bn_bwd_apply(const void* dy, const void* x, const void* y, const float* gamma,
-                  const float* saved_mean, const float* saved_rstd, const float* dsums, void* dx,
-                  void* dres, float* dgamma, float* dbeta, int64_t M, int C, bool relu,
-                  bool accumulate, cudaStream_t stream) {
+                  const float* beta, const float* saved_mean, const float* saved_rstd,
+                  const float* dsums, void* dx, void* dres, float* dgamma, float* dbeta, int64_t M,
+                  int C, bool relu, bool accumulate, cudaStream_t stream) {
   BnGrid g = bn_grid(M, C, kNumSMs * 8);
-  bn_bwd_apply_kernel<<<g.grid, g.block, 0, stream>>>(
-      BF(dy), BF(x), BF(y), gamma, saved_mean, saved_rstd, dsums, BFW(dx), BFW(dres), dgamma,
-      dbeta, M, C, relu ? 1 : 0, accumulate ? 1 : 0);
+#define LAUNCH(R, Y)                                                                          \
+  bn_bwd_apply_kernel<R, Y><<<g.grid, g.block, 0, stream>>>(                                  \
+      BF(dy), BF(x), BF(y), gamma, beta, saved_mean, saved_rstd, dsums, BFW(dx), BFW(dres),   \
+      dgamma, dbeta, M, C, accumulate ? 1 : 0)
+  if (!relu) LAUNCH(false, false);
+  else if (y != nullptr) LAUNCH(true, true);
+  else LAUNCH(true, false);
+#undef LAUNCH
 }
 
 }  // namespace edl

@@ -39,6 +39,12 @@ struct GemmParams {
   int relu;
   float* col_stats;  // [2N]
   float* out_f32;    // split-K accumulation target, row-major [M, N]
+  // fused split-K finalize: the last CTA of each output tile converts the fp32 tile to bf16 into
+  // out_bf16 (+= when accumulate) and re-zeroes the fp32 workspace + its tile counter
+  __nv_bfloat16* out_bf16;
+  long long ldo;
+  int* tile_counters;
+  int accumulate;
 };
 
 template <int BLOCK_N, int STAGES>
@@ -251,6 +257,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
+        if (p.tile_counters != nullptr) {
+          // ---- fused finalize by the last-arriving CTA of this output tile ----
+          uint32_t* s_last = tmem_slot + 1;
+          __threadfence();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            const int old = atomicAdd(&p.tile_counters[tile], 1);
+            const int last = old == (int)gridDim.z - 1;
+            if (last) p.tile_counters[tile] = 0;
+            *s_last = (uint32_t)last;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (*s_last != 0u && grow < p.M) {
+            __threadfence();
+            float* wrow = p.out_f32 + (int64_t)grow * p.N + n0;
+            __nv_bfloat16* orow = p.out_bf16 + (int64_t)grow * p.ldo + n0;
+            int ncols = p.N - n0;
+            if (ncols > BLOCK_N) ncols = BLOCK_N;
+            for (int c = 0; c + 3 < ncols; c += 4) {
+              float4 v = __ldcg(reinterpret_cast<const float4*>(wrow + c));
+              *reinterpret_cast<float4*>(wrow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+              __nv_bfloat162 lo, hi;
+              if (p.accumulate) {
+                const uint2 o = *reinterpret_cast<const uint2*>(orow + c);
+                const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.x));
+                const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.y));
+                v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
+              }
+              lo = __floats2bfloat162_rn(v.x, v.y);
+              hi = __floats2bfloat162_rn(v.z, v.w);
+              uint2 packed;
+              packed.x = *reinterpret_cast<uint32_t*>(&lo);
+              packed.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(orow + c) = packed;
+            }
+            for (int c = ncols & ~3; c < ncols; ++c) {
+              float v = __ldcg(wrow + c);
+              wrow[c] = 0.f;
+              if (p.accumulate) v += __bfloat162float(orow[c]);
+              orow[c] = __float2bfloat16(v);
+            }
+          }
+        }
       }
     }
   }
@@ -282,11 +331,16 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+thread_local char g_tmap_err[256];
+
 // 2-D bf16 tensor map: dims {inner, outer}, row pitch in elements, box {box_inner, box_outer}.
 bool make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
                   uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn fn = get_encode_fn();
-  if (fn == nullptr) return false;
+  if (fn == nullptr) {
+    snprintf(g_tmap_err, sizeof(g_tmap_err), "cuTensorMapEncodeTiled entry point not found");
+    return false;
+  }
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {pitch_elems * 2};
   cuuint32_t box[2] = {box_inner, box_outer};
@@ -294,6 +348,11 @@ bool make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t ou
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    snprintf(g_tmap_err, sizeof(g_tmap_err),
+             "cuTensorMapEncodeTiled failed: CUresult=%d ptr=%p dims={%llu,%llu} pitch=%llu box={%u,%u}",
+             (int)r, ptr, (unsigned long long)inner, (unsigned long long)outer,
+             (unsigned long long)pitch_elems, box_inner, box_outer);
   return r == CUDA_SUCCESS;
 }
 
@@ -309,7 +368,7 @@ const char* launch_variant(const GemmArgs& g, cudaStream_t stream) {
   else ok &= make_tmap_2d(&tmB, g.B, g.N, g.K, g.ldb, 64, BLOCK_K);
   if (EPI == 0) ok &= make_tmap_2d(&tmD, g.D, g.N, g.M, g.ldd, BLOCK_N < 64 ? BLOCK_N : 64, BLOCK_M);
   else tmD = tmA;
-  if (!ok) return "cuTensorMapEncodeTiled failed";
+  if (!ok) return g_tmap_err;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, STAGES, A_MN, B_MN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -329,6 +388,10 @@ const char* launch_variant(const GemmArgs& g, cudaStream_t stream) {
   p.relu = g.relu ? 1 : 0;
   p.col_stats = g.col_stats;
   p.out_f32 = g.out_f32;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(g.out_bf16);
+  p.ldo = g.ldo;
+  p.tile_counters = g.tile_counters;
+  p.accumulate = g.accumulate_out ? 1 : 0;
   const int tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M;
   const int tiles_n = (g.N + BLOCK_N - 1) / BLOCK_N;
   dim3 grid(tiles_m * tiles_n, 1, split);

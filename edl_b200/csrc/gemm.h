@@ -19,6 +19,13 @@ struct GemmArgs {
   float* col_stats = nullptr;         // [2N] fp32: += sum, sum of squares of the stored outputs
   float* out_f32 = nullptr;           // split-K target: fp32 [M, N], += A*B
   int split_k = 1;
+  // fused split-K finalize (optional, with out_f32 as an all-zero workspace on entry):
+  // the last CTA per tile writes bf16(out_f32 tile) (+= if accumulate_out) to out_bf16 [M, N] with
+  // row pitch ldo, then re-zeroes the workspace tile and its counter.
+  void* out_bf16 = nullptr;
+  int64_t ldo = 0;
+  int* tile_counters = nullptr;       // >= ceil(M/128)*ceil(N/BLOCK_N) zero-initialised ints
+  bool accumulate_out = false;
 };
 
 // Returns nullptr on success, else a static error string.

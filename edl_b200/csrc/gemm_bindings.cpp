@@ -19,7 +19,8 @@ void gemm_bf16(const Tensor& A, const Tensor& B, const c10::optional<Tensor>& D,
                bool b_mn_major, const c10::optional<Tensor>& col_scale,
                const c10::optional<Tensor>& col_shift, bool relu,
                const c10::optional<Tensor>& col_stats, const c10::optional<Tensor>& out_f32,
-               int64_t split_k) {
+               int64_t split_k, const c10::optional<Tensor>& out_bf16,
+               const c10::optional<Tensor>& tile_counters, bool accumulate_out) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.dim() == 2 && B.dim() == 2);
   TORCH_CHECK(A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16);
   TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1, "operands need a contiguous last dim");
@@ -39,9 +40,20 @@ void gemm_bf16(const Tensor& A, const Tensor& B, const c10::optional<Tensor>& D,
   TORCH_CHECK(reinterpret_cast<uintptr_t>(g.A) % 16 == 0 && reinterpret_cast<uintptr_t>(g.B) % 16 == 0);
   if (out_f32.has_value() && out_f32->defined()) {
     TORCH_CHECK(out_f32->scalar_type() == at::kFloat && out_f32->is_contiguous());
-    TORCH_CHECK(out_f32->size(0) == g.M && out_f32->size(1) == g.N);
+    TORCH_CHECK(out_f32->numel() >= (int64_t)g.M * g.N);
     g.out_f32 = out_f32->data_ptr<float>();
     g.split_k = (int)split_k;
+    if (out_bf16.has_value() && out_bf16->defined()) {
+      TORCH_CHECK(out_bf16->scalar_type() == at::kBFloat16 && out_bf16->dim() == 2);
+      TORCH_CHECK(out_bf16->size(0) == g.M && out_bf16->size(1) == g.N && out_bf16->stride(1) == 1);
+      TORCH_CHECK(g.N % 4 == 0 && out_bf16->stride(0) % 4 == 0, "fused finalize needs N % 4 == 0");
+      TORCH_CHECK(tile_counters.has_value() && tile_counters->scalar_type() == at::kInt);
+      TORCH_CHECK(tile_counters->numel() >= (int64_t)((g.M + 127) / 128) * ((g.N + 63) / 64));
+      g.out_bf16 = out_bf16->data_ptr();
+      g.ldo = out_bf16->stride(0);
+      g.tile_counters = tile_counters->data_ptr<int>();
+      g.accumulate_out = accumulate_out;
+    }
   } else {
     TORCH_CHECK(D.has_value() && D->defined() && D->scalar_type() == at::kBFloat16);
     TORCH_CHECK(D->dim() == 2 && D->size(0) == g.M && D->size(1) == g.N && D->stride(1) == 1);

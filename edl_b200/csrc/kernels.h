@@ -14,13 +14,14 @@ void bn_apply(const void* x, const void* res, void* y, const float* sums, const 
               cudaStream_t stream);
 void scale_shift_act(const void* x, const void* res, void* y, const float* scale,
                      const float* shift, int64_t M, int C, bool relu, cudaStream_t stream);
-void bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* saved_mean,
-                   const float* saved_rstd, float* dsums, int64_t M, int C, bool relu,
-                   cudaStream_t stream);
+// y == nullptr with relu: the ReLU mask is recomputed from x (no residual case)
+void bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* gamma,
+                   const float* beta, const float* saved_mean, const float* saved_rstd,
+                   float* dsums, int64_t M, int C, bool relu, cudaStream_t stream);
 void bn_bwd_apply(const void* dy, const void* x, const void* y, const float* gamma,
-                  const float* saved_mean, const float* saved_rstd, const float* dsums, void* dx,
-                  void* dres, float* dgamma, float* dbeta, int64_t M, int C, bool relu,
-                  bool accumulate, cudaStream_t stream);
+                  const float* beta, const float* saved_mean, const float* saved_rstd,
+                  const float* dsums, void* dx, void* dres, float* dgamma, float* dbeta, int64_t M,
+                  int C, bool relu, bool accumulate, cudaStream_t stream);
 
 // ---- optim.cu ----
 void sgd_momentum(void* param_lp, float* master, float* mom, const void* grad, bool grad_is_bf16,

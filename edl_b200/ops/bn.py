@@ -68,7 +68,7 @@ class _BNActFn(torch.autograd.Function):
         ctx.bwd_ws = bwd_ws
         if not x.is_cuda:
             y, mean, rstd = _ref_forward(x, res, gamma, beta, rm, rv, relu, True, momentum, eps)
-            ctx.save_for_backward(x, y, gamma, mean, rstd)
+            ctx.save_for_backward(x, y, gamma, mean, rstd, beta)
             return y
         C = native()
         ch = gamma.numel()
@@ -83,14 +83,16 @@ class _BNActFn(torch.autograd.Function):
         C.bn_apply(x2, _mc(res) if res is not None else None, _mc(y), sums, gamma, beta, rm, rv,
                    mean, rstd, eps, momentum, relu)
         count_launch()
-        ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
+        # the saved output is only needed for the ReLU mask when a residual was added; otherwise the
+        # backward kernels recompute the mask from x (one fewer pass over the activation)
+        ctx.save_for_backward(x, y if (relu and res is not None) else None, gamma, mean, rstd, beta)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         from . import native, count_launch
 
-        x, y, gamma, mean, rstd = ctx.saved_tensors
+        x, y, gamma, mean, rstd, beta = ctx.saved_tensors
         relu, has_res = ctx.relu, ctx.has_res
         sink_g, sink_b = ctx.sinks
         dy = _cl(dy)
@@ -123,8 +125,8 @@ class _BNActFn(torch.autograd.Function):
         if dsums is None:
             dsums = torch.zeros(2 * ch, device=x.device, dtype=torch.float32)
         x2, dy2 = _mc(x), _mc(dy)
-        y2 = _mc(y) if relu else None
-        C.bn_bwd_reduce(dy2, x2, y2, mean, rstd, dsums, relu)
+        y2 = _mc(y) if (relu and y is not None) else None
+        C.bn_bwd_reduce(dy2, x2, y2, gamma, beta, mean, rstd, dsums, relu)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
         if sink_g is not None:
@@ -133,7 +135,7 @@ class _BNActFn(torch.autograd.Function):
             dg = torch.empty_like(gamma)
             db = torch.empty_like(gamma)
             acc = False
-        C.bn_bwd_apply(dy2, x2, y2, gamma, mean, rstd, dsums, _mc(dx),
+        C.bn_bwd_apply(dy2, x2, y2, gamma, beta, mean, rstd, dsums, _mc(dx),
                        _mc(dres) if has_res else None, dg, db, relu, acc)
         count_launch(2)
         if sink_g is not None:

@@ -15,21 +15,29 @@ _NUM_SMS = 148
 
 
 def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, col_scale=None, col_shift=None,
-              relu=False, col_stats=None, out_f32=None, split_k=1):
+              relu=False, col_stats=None, out_f32=None, split_k=1, out_bf16=None, tile_counters=None,
+              accumulate_out=False):
     """D = op(A) @ op(B): see csrc/gemm.h for the operand conventions.
 
     default        : A [M, K], B [N, K]  -> D [M, N] = A @ B^T
     b_mn_major     : B [K, N]            -> D = A @ B
     a_mn_major     : A [K, M]            -> D = A^T @ op(B)
-    out_f32 given  : fp32 [M, N] += result, split over K across CTAs (no bf16 output)."""
+    out_f32 given  : fp32 [M, N] += result, split over K across CTAs (no bf16 output).
+    out_bf16 given : (with out_f32 as an all-zero workspace) the last CTA of every output tile writes
+                     bf16(result) (+= if accumulate_out) into out_bf16 and re-zeroes the workspace."""
     from . import native, count_launch
 
     m = a.shape[1] if a_mn_major else a.shape[0]
     n = b.shape[1] if b_mn_major else b.shape[0]
-    if not a.is_cuda:
+    if not a.is_cuda or not _tma_compatible(a, b, out, n):
+        # CPU tensors, or CUDA shapes TMA cannot describe (row pitch / base not 16-byte aligned):
+        # plain PyTorch math with identical semantics
         af = a.float().t() if a_mn_major else a.float()
         bf = b.float() if b_mn_major else b.float().t()
         d = af @ bf
+        if out_bf16 is not None:
+            out_bf16.copy_((out_bf16.float() + d) if accumulate_out else d)
+            return out_bf16
         if out_f32 is not None:
             out_f32.add_(d)
             return out_f32
@@ -50,9 +58,20 @@ def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, col_scale=None
     if out_f32 is None and out is None:
         out = torch.empty((m, n), device=a.device, dtype=torch.bfloat16)
     native().gemm_bf16(a, b, out, a_mn_major, b_mn_major, col_scale, col_shift, relu, col_stats,
-                       out_f32, int(split_k))
+                       out_f32, int(split_k), out_bf16, tile_counters, bool(accumulate_out))
     count_launch()
+    if out_bf16 is not None:
+        return out_bf16
     return out if out_f32 is None else out_f32
+
+
+def _tma_compatible(a, b, out, n):
+    for t in (a, b, out):
+        if t is None:
+            continue
+        if t.dtype != torch.bfloat16 or t.stride(-1) != 1 or t.stride(0) % 8 != 0 or t.data_ptr() % 16 != 0:
+            return False
+    return out is not None or n % 8 == 0
 
 
 def _split_k_for(m, n, k):
@@ -62,12 +81,43 @@ def _split_k_for(m, n, k):
     return max(1, min(want, max(1, kb // 2)))
 
 
+_WS = {}
+
+
+def _splitk_workspace(device, numel, tiles):
+    """Persistent all-zero fp32 workspace + tile counters (per device and stream): the fused
+    split-K finalize leaves both zeroed again, so no per-call memset is needed."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws[0].numel() < numel or ws[1].numel() < tiles:
+        ws = (torch.zeros(max(numel, 4 << 20), device=device, dtype=torch.float32),
+              torch.zeros(max(tiles, 4096), device=device, dtype=torch.int32))
+        _WS[key] = ws
+    return ws
+
+
 def _wgrad(dy2, x2, weight_shape, sink, ready):
-    """dW[Cout, Cin] = dy2[M, Cout]^T @ x2[M, Cin] with fp32 split-K accumulation."""
+    """dW[Cout, Cin] = dy2[M, Cout]^T @ x2[M, Cin]: fp32 split-K accumulation whose last CTA per
+    tile converts to bf16 straight into the (flat gradient bucket) sink -- no memset / cast / add
+    kernels around it."""
     cout, cin = dy2.shape[1], x2.shape[1]
+    split = _split_k_for(cout, cin, dy2.shape[0])
+    if dy2.is_cuda and cin % 4 == 0:
+        tiles = ((cout + 127) // 128) * ((cin + 63) // 64)
+        ws, counters = _splitk_workspace(dy2.device, cout * cin, tiles)
+        if sink is not None:
+            out, acc = sink.view(cout, cin), True
+        else:
+            out, acc = torch.empty((cout, cin), device=dy2.device, dtype=torch.bfloat16), False
+        gemm_bf16(dy2, x2, a_mn_major=True, b_mn_major=True, out_f32=ws[:cout * cin].view(cout, cin),
+                  split_k=split, out_bf16=out, tile_counters=counters, accumulate_out=acc)
+        if sink is not None:
+            if ready is not None:
+                ready()
+            return None
+        return out.view(weight_shape)
     acc = torch.zeros((cout, cin), device=dy2.device, dtype=torch.float32)
-    gemm_bf16(dy2, x2, a_mn_major=True, b_mn_major=True, out_f32=acc,
-              split_k=_split_k_for(cout, cin, dy2.shape[0]))
+    gemm_bf16(dy2, x2, a_mn_major=True, b_mn_major=True, out_f32=acc, split_k=split)
     if sink is not None:
         sink.view(cout, cin).add_(acc)
         if ready is not None:
@@ -120,12 +170,13 @@ def conv1x1(x, weight, stats: Optional[torch.Tensor] = None):
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, bias, relu):
+    def forward(ctx, x, w, bias, relu, sink, ready):
         x = x.contiguous()
         y = gemm_bf16(x, w, col_shift=bias.float() if bias is not None else None, relu=relu)
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.has_bias = bias is not None
         ctx.bias_dtype = bias.dtype if bias is not None else None
+        ctx.sink, ctx.ready = sink, ready
         return y
 
     @staticmethod
@@ -137,12 +188,14 @@ class _LinearFn(torch.autograd.Function):
         dx = gemm_bf16(dy, w, b_mn_major=True) if ctx.needs_input_grad[0] else None
         dw = None
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(dy, x, w.shape, None, None)
+            dw = _wgrad(dy, x, w.shape, ctx.sink, ctx.ready)
         db = dy.float().sum(0).to(ctx.bias_dtype) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        return dx, dw, db, None
+        return dx, dw, db, None, None, None
 
 
 def linear_bf16(x, weight, bias=None, relu=False):
     """y = act(x @ weight^T + bias) on the tcgen05 GEMM (bias/activation fused in the epilogue).
     x [M, K] bf16, weight [N, K] bf16, bias [N] (any float dtype)."""
-    return _LinearFn.apply(x, weight, bias, relu)
+    sink = getattr(weight, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
+    ready = getattr(weight, "_edl_grad_ready", None) if sink is not None else None
+    return _LinearFn.apply(x, weight, bias, relu, sink, ready)
