@@ -1,0 +1,147 @@
+"""The elastic launcher: rendezvous -> barrier -> spawn trainers -> supervise -> re-barrier and
+restart on membership change -> publish the final status
+(reference: python/edl/utils/launcher.py:33-261, call stack in SURVEY 3.1)."""
+import time
+
+from . import cluster as edl_cluster
+from . import (cluster_watcher, constants, exceptions, leader_pod, pod_server, pod_server_client,
+               resource_pods, status as edl_status, train_process)
+from .log_utils import logger
+
+
+class Launcher:
+    def __init__(self, job_env, pod, etcd, args):
+        self._job_env, self._pod, self._etcd, self._args = job_env, pod, etcd, args
+        self._pod_server = None
+        self._resource_register = None
+        self._leader_register = None
+        self._watcher = None
+        self._procs = []
+        self._cluster = None
+        self.rescales = 0          # number of stage changes survived
+        self.last_rescale_s = None  # wall seconds from "change seen" to "trainers restarted"
+
+    # ------------------------------------------------------------------ set-up
+    def init(self):
+        self._pod_server = pod_server.PodServer(self._job_env, self._pod.id, etcd=self._etcd).start()
+        self._pod.port = self._pod_server.port
+        edl_status.save_pod_status_to_etcd(self._etcd, self._pod.id, edl_status.Status.INITIAL, timeout=30)
+        return self
+
+    def _barrier(self, timeout):
+        """Wait until every pod of the current stage has arrived at the leader; returns the cluster."""
+        begin = time.time()
+        last_err = None
+        while time.time() - begin < timeout:
+            try:
+                leader = leader_pod.load_from_etcd(self._etcd, timeout=3)
+                c = pod_server_client.Client(leader.endpoint)
+                try:
+                    return c.barrier(self._job_env.job_id, self._pod.id,
+                                     timeout=min(15.0, max(1.0, timeout - (time.time() - begin))))
+                finally:
+                    c.close()
+            except exceptions.EdlException as e:
+                last_err = e
+                time.sleep(min(1.0, constants.POLL_INTERVAL))
+        raise exceptions.EdlBarrierError("barrier did not complete in {}s: {}".format(timeout, last_err))
+
+    def _adopt(self, cluster):
+        """Take this pod's record (rank, global trainer ranks) from the agreed cluster; False if evicted."""
+        mine = cluster.get_pod_by_id(self._pod.id)
+        if mine is None:
+            return False
+        mine.port = self._pod.port
+        self._pod = mine
+        self._cluster = cluster
+        return True
+
+    # ------------------------------------------------------------------ main loop
+    def launch(self):
+        ok = False
+        try:
+            ok = self._launch()
+        except Exception:
+            logger.exception("launcher of pod %s failed", self._pod.id)
+            ok = False
+        finally:
+            self._exit(ok)
+        return ok
+
+    def _launch(self):
+        je = self._job_env
+        self._resource_register = resource_pods.Register(je, self._pod.id, self._pod.to_json(), etcd=self._etcd)
+        self._leader_register = leader_pod.Register(je, self._pod.id, etcd=self._etcd)
+        cluster = self._barrier(constants.BARRIER_TIMEOUT)
+        if not self._adopt(cluster):
+            logger.info("pod %s was not admitted (cluster is full); exiting quietly", self._pod.id)
+            return True
+        edl_status.save_pod_status_to_etcd(self._etcd, self._pod.id, edl_status.Status.RUNNING, timeout=30)
+        self._watcher = cluster_watcher.Watcher(je, self._cluster, etcd=self._etcd)
+        self._procs = train_process.start(je, self._cluster, self._pod, self._args.training_script,
+                                          self._args.training_script_args, log_dir=je.log_dir)
+        poll = min(constants.POLL_INTERVAL, 1.0)
+        while True:
+            alive, failed = train_process.watch(self._procs)
+            if failed is not None:
+                logger.error("a trainer exited with code %s", failed)
+                train_process.terminate(self._procs)
+                return False
+            if not alive:
+                logger.info("all trainers of pod %s finished", self._pod.id)
+                return True
+            if self._resource_register.is_stopped() or self._leader_register.is_stopped():
+                logger.error("lost the store registration; stopping trainers")
+                train_process.terminate(self._procs)
+                return False
+            if self._watcher.changed:
+                t0 = time.time()
+                logger.info("cluster changed; re-barrier")
+                new_cluster = self._barrier(constants.RESCALE_BARRIER_TIMEOUT)
+                train_process.terminate(self._procs)
+                self._watcher.stop()
+                if not self._adopt(new_cluster):
+                    logger.info("pod %s is not part of the new cluster; exiting", self._pod.id)
+                    return True
+                self._watcher = cluster_watcher.Watcher(je, self._cluster, etcd=self._etcd)
+                self._procs = train_process.start(je, self._cluster, self._pod, self._args.training_script,
+                                                  self._args.training_script_args, log_dir=je.log_dir)
+                self.rescales += 1
+                self.last_rescale_s = time.time() - t0
+                logger.info("rescaled to %d trainers in %.2fs", self._cluster.get_trainers_nranks(),
+                            self.last_rescale_s)
+            time.sleep(poll)
+
+    # ------------------------------------------------------------------ tear-down
+    def _exit(self, ok):
+        try:
+            edl_status.save_pod_flag_to_etcd(self._etcd, self._pod.id, ok, timeout=15)
+        except Exception:  # noqa: BLE001
+            logger.warning("could not persist pod status")
+        is_leader = self._leader_register is not None and self._leader_register.is_leader()
+        if self._watcher is not None:
+            self._watcher.stop()
+        if self._resource_register is not None:
+            self._resource_register.stop()
+        if is_leader:
+            # the leader declares the job status after every follower has released its resource key
+            released = resource_pods.wait_followers_release(self._etcd, self._pod.id,
+                                                            timeout=constants.ETCD_TTL * 2 + 5)
+            try:
+                _, _, _, failed = edl_status.load_pods_status_from_etcd(self._etcd, timeout=5)
+                job_ok = ok and released and not failed
+                edl_status.save_job_flag_to_etcd(self._etcd, self._pod.id, job_ok, timeout=15)
+            except Exception:  # noqa: BLE001
+                logger.warning("could not persist job status")
+        if self._leader_register is not None:
+            self._leader_register.stop()
+        if self._procs:
+            train_process.terminate(self._procs)
+        if self._pod_server is not None:
+            self._pod_server.stop()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        pass

@@ -3,6 +3,13 @@ import sys
 
 import pytest
 
+# fast control-plane timing for tests (the defaults mirror the reference: 15 s TTL, 3 s polls)
+os.environ.setdefault("EDL_ETCD_TTL", "1.5")
+os.environ.setdefault("EDL_POLL_INTERVAL", "0.3")
+os.environ.setdefault("EDL_KILL_GRACE", "1")
+os.environ.setdefault("EDL_BARRIER_TIMEOUT", "60")
+os.environ.setdefault("EDL_RESCALE_BARRIER_TIMEOUT", "30")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -28,3 +35,39 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip_gpu)
         if "multigpu" in item.keywords and ngpu < 2:
             item.add_marker(skip_multi)
+
+
+@pytest.fixture
+def kv_server():
+    from edl_b200.store import KVServer
+
+    srv = KVServer().start()
+    yield srv
+    srv.stop()
+
+
+@pytest.fixture
+def etcd(kv_server):
+    import uuid
+    from edl_b200.discovery.etcd_client import EtcdClient
+
+    c = EtcdClient([kv_server.endpoint], root="job_" + uuid.uuid4().hex[:8])
+    c.init()
+    yield c
+    c.close()
+
+
+class FakeJobEnv:
+    """Minimal JobEnv stand-in for in-process multi-pod tests (the reference's EtcdTestBase injects
+    a fake PaddleCloud environment instead, tests/unittests/etcd_test_base.py:26-61)."""
+
+    def __init__(self, endpoint, job_id, min_nodes=2, max_nodes=2, nproc=1):
+        self.etcd_endpoints = [endpoint]
+        self.job_id = job_id
+        self.min_nodes, self.max_nodes = min_nodes, max_nodes
+        self.nproc_per_node = nproc
+        self.gpus = [str(i) for i in range(nproc)]
+        from edl_b200.utils.network_utils import find_free_ports
+        self.trainer_ports = [str(p) for p in find_free_ports(nproc)]
+        self.log_dir = None
+        self.hdfs_path = ""
