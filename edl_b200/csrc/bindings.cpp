@@ -288,6 +288,7 @@ void register_gemm_bindings(pybind11::module_& m);  // gemm_bindings.cpp
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "edl_b200 sm_100a kernels";
+  m.def("bn_set_stream_kernels", &edl::bn_set_stream_kernels);
   m.def("bn_stats", &bn_stats);
   m.def("bn_apply", &bn_apply);
   m.def("scale_shift_act", &scale_shift_act);

@@ -20,7 +20,7 @@ namespace edl {
 namespace {
 
 constexpr int kBnThreads = 256;
-constexpr int kUnroll = 4;
+constexpr int kUnroll = 4;  // must stay 4: ld_stream_x4
 
 struct BnGrid {
   dim3 grid, block;
@@ -82,8 +82,8 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, i
     const __nv_bfloat16* base = x + (int64_t)cvec * 8;
     for (; r + (kUnroll - 1) * stride < M; r += kUnroll * stride) {
       bf16x8 v[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream(base + (r + u * stride) * C);
+      ld_stream_x4(base + r * C, base + (r + stride) * C, base + (r + 2 * stride) * C,
+                   base + (r + 3 * stride) * C, v);
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         float f[8];
@@ -149,12 +149,10 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   // 4 rows per iteration: 4 (8 with a residual) independent 128-bit loads in flight per thread
   for (; r + (kUnroll - 1) * stride < M; r += kUnroll * stride) {
     bf16x8 xv[kUnroll], rv[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) xv[u] = ld_stream(x + (r + u * stride) * C + c0);
-    if (res != nullptr) {
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) rv[u] = ld_stream(res + (r + u * stride) * C + c0);
-    }
+    const int64_t o0 = r * C + c0, o1 = (r + stride) * C + c0, o2 = (r + 2 * stride) * C + c0,
+                  o3 = (r + 3 * stride) * C + c0;
+    ld_stream_x4(x + o0, x + o1, x + o2, x + o3, xv);
+    if (res != nullptr) ld_stream_x4(res + o0, res + o1, res + o2, res + o3, rv);
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       float f[8];
@@ -284,12 +282,12 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     int64_t r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
     for (; r + (kUnroll - 1) * stride < M; r += kUnroll * stride) {
       bf16x8 gv[kUnroll], xv[kUnroll], yv[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const int64_t off = (r + u * stride) * C + c0;
-        gv[u] = ld_stream(dy + off);
-        xv[u] = ld_stream(x + off);
-        if (RELU && HAS_Y) yv[u] = ld_stream(y + off);
+      {
+        const int64_t o0 = r * C + c0, o1 = (r + stride) * C + c0, o2 = (r + 2 * stride) * C + c0,
+                      o3 = (r + 3 * stride) * C + c0;
+        ld_stream_x4(dy + o0, dy + o1, dy + o2, dy + o3, gv);
+        ld_stream_x4(x + o0, x + o1, x + o2, x + o3, xv);
+        if (RELU && HAS_Y) ld_stream_x4(y + o0, y + o1, y + o2, y + o3, yv);
       }
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
@@ -365,12 +363,12 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
   int64_t r = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
   for (; r + (kUnroll - 1) * stride < M; r += kUnroll * stride) {
     bf16x8 gv[kUnroll], xv[kUnroll], yv[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int64_t off = (r + u * stride) * C + c0;
-      gv[u] = ld_stream(dy + off);
-      xv[u] = ld_stream(x + off);
-      if (RELU && HAS_Y) yv[u] = ld_stream(y + off);
+    {
+      const int64_t o0 = r * C + c0, o1 = (r + stride) * C + c0, o2 = (r + 2 * stride) * C + c0,
+                    o3 = (r + 3 * stride) * C + c0;
+      ld_stream_x4(dy + o0, dy + o1, dy + o2, dy + o3, gv);
+      ld_stream_x4(x + o0, x + o1, x + o2, x + o3, xv);
+      if (RELU && HAS_Y) ld_stream_x4(y + o0, y + o1, y + o2, y + o3, yv);
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -411,7 +409,11 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
 #define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 #define BFW(p) reinterpret_cast<__nv_bfloat16*>(p)
 
+static bool g_use_stream = true;
+void bn_set_stream_kernels(bool enabled) { g_use_stream = enabled; }
+
 void bn_stats(const void* x, float* sums, int64_t M, int C, cudaStream_t stream) {
+  if (g_use_stream && bn_stream_supported(M, C)) return bn_stats_stream(x, sums, M, C, stream);
   BnGrid g = bn_grid(M, C, kNumSMs * 4);
   size_t smem = (size_t)kBnThreads * 16 * sizeof(float);
   bn_stats_kernel<<<g.grid, g.block, smem, stream>>>(BF(x), sums, M, C);
@@ -421,6 +423,9 @@ void bn_apply(const void* x, const void* res, void* y, const float* sums, const 
               const float* beta, float* running_mean, float* running_var, float* saved_mean,
               float* saved_rstd, int64_t M, int C, float eps, float momentum, bool relu,
               cudaStream_t stream) {
+  if (g_use_stream && bn_stream_supported(M, C))
+    return bn_apply_stream(x, res, y, sums, gamma, beta, running_mean, running_var, saved_mean,
+                           saved_rstd, M, C, eps, momentum, relu, stream);
   BnGrid g = bn_grid(M, C, kNumSMs * 8);
   bn_apply_kernel<<<g.grid, g.block, 0, stream>>>(BF(x), BF(res), BFW(y), sums, gamma, beta,
                                                   running_mean, running_var, saved_mean,
@@ -437,6 +442,9 @@ void scale_shift_act(const void* x, const void* res, void* y, const float* scale
 void bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* gamma,
                    const float* beta, const float* saved_mean, const float* saved_rstd,
                    float* dsums, int64_t M, int C, bool relu, cudaStream_t stream) {
+  if (g_use_stream && bn_stream_supported(M, C))
+    return bn_bwd_reduce_stream(dy, x, y, gamma, beta, saved_mean, saved_rstd, dsums, M, C, relu,
+                                stream);
   BnGrid g = bn_grid(M, C, kNumSMs * 4);
   size_t smem = (size_t)kBnThreads * 16 * sizeof(float);
 #define LAUNCH(R, Y)                                                                         \
@@ -453,6 +461,9 @@ void bn_bwd_apply(const void* dy, const void* x, const void* y, const float* gam
                   const float* beta, const float* saved_mean, const float* saved_rstd,
                   const float* dsums, void* dx, void* dres, float* dgamma, float* dbeta, int64_t M,
                   int C, bool relu, bool accumulate, cudaStream_t stream) {
+  if (g_use_stream && bn_stream_supported(M, C))
+    return bn_bwd_apply_stream(dy, x, y, gamma, beta, saved_mean, saved_rstd, dsums, dx, dres,
+                               dgamma, dbeta, M, C, relu, accumulate, stream);
   BnGrid g = bn_grid(M, C, kNumSMs * 8);
 #define LAUNCH(R, Y)                                                                          \
   bn_bwd_apply_kernel<R, Y><<<g.grid, g.block, 0, stream>>>(                                  \

@@ -32,13 +32,34 @@ EDL_DEVICE bf16x8 pack8(const float (&f)[8]) {
   return p;
 }
 
-// 128-bit streaming load/store (no L1 allocation) for one-touch data.
+// 128-bit streaming load (read-only path, no L1 allocation) for one-touch data.  NOT volatile: the
+// compiler may hoist / batch it freely (the data is never written by the same kernel).
 EDL_DEVICE bf16x8 ld_stream(const void* ptr) {
   int4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(ptr));
+  asm("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+      : "l"(ptr));
   return *reinterpret_cast<bf16x8*>(&r);
+}
+
+// Four independent 128-bit streaming loads issued back to back from ONE asm block: guarantees the
+// memory-level parallelism (ptxas otherwise interleaves each load with the math that consumes it,
+// which measured at 10% of HBM bandwidth on the BN kernels -- profiles/ round-1 ncu capture).
+EDL_DEVICE void ld_stream_x4(const void* p0, const void* p1, const void* p2, const void* p3,
+                             bf16x8 (&v)[4]) {
+  int4 a, b, c, d;
+  asm volatile(
+      "ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%16];\n\t"
+      "ld.global.nc.L1::no_allocate.v4.s32 {%4,%5,%6,%7}, [%17];\n\t"
+      "ld.global.nc.L1::no_allocate.v4.s32 {%8,%9,%10,%11}, [%18];\n\t"
+      "ld.global.nc.L1::no_allocate.v4.s32 {%12,%13,%14,%15}, [%19];"
+      : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w),
+        "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w), "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w)
+      : "l"(p0), "l"(p1), "l"(p2), "l"(p3));
+  v[0] = *reinterpret_cast<bf16x8*>(&a);
+  v[1] = *reinterpret_cast<bf16x8*>(&b);
+  v[2] = *reinterpret_cast<bf16x8*>(&c);
+  v[3] = *reinterpret_cast<bf16x8*>(&d);
 }
 EDL_DEVICE bf16x8 ld_vec(const void* ptr) { return *reinterpret_cast<const bf16x8*>(ptr); }
 EDL_DEVICE void st_vec(void* ptr, const bf16x8& v) { *reinterpret_cast<bf16x8*>(ptr) = v; }

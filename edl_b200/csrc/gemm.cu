@@ -233,32 +233,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (et == 0) ptx::tma_store_wait_read0();
       } else {
-        // split-K: accumulate the fp32 partial tile into out_f32 with vector reductions
-        const int grow = m0 + row;
+        // split-K: stage the fp32 partial tile in smem (the pipeline stages are drained), then push
+        // it to the fp32 workspace with COALESCED vector reductions: consecutive threads cover
+        // consecutive 16-byte pieces of a row (row-per-thread reds touch 32 cache lines per warp
+        // instruction and measured 5-20x slower, profiles/kernels_r1.txt).
+        constexpr int kPitch = BLOCK_N * 4 + 16;        // bytes; +16 keeps v4 stores off one bank
+        constexpr int kVecPerRow = BLOCK_N / 4;         // float4 per row
+        uint8_t* sf = smem;
 #pragma unroll 1
         for (int c32 = 0; c32 < BLOCK_N / 32; ++c32) {
           uint32_t r[32];
           ptx::tmem_ld_32x32(taddr + c32 * 32, r);
           ptx::tmem_ld_wait();
-          if (grow < p.M) {
-            float* dst = p.out_f32 + (int64_t)grow * p.N + n0 + c32 * 32;
+          float4* dst = reinterpret_cast<float4*>(sf + row * kPitch + c32 * 128);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              if (n0 + c32 * 32 + c * 4 + 3 < p.N) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + c * 4),
-                             "f"(__uint_as_float(r[c * 4])), "f"(__uint_as_float(r[c * 4 + 1])),
-                             "f"(__uint_as_float(r[c * 4 + 2])), "f"(__uint_as_float(r[c * 4 + 3]))
-                             : "memory");
-              } else {
-                for (int j = 0; j < 4; ++j)
-                  if (n0 + c32 * 32 + c * 4 + j < p.N)
-                    atomicAdd(dst + c * 4 + j, __uint_as_float(r[c * 4 + j]));
-              }
-            }
+          for (int c = 0; c < 8; ++c)
+            dst[c] = make_float4(__uint_as_float(r[c * 4]), __uint_as_float(r[c * 4 + 1]),
+                                 __uint_as_float(r[c * 4 + 2]), __uint_as_float(r[c * 4 + 3]));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        int rows_valid = p.M - m0;
+        if (rows_valid > BLOCK_M) rows_valid = BLOCK_M;
+        int cols_valid = p.N - n0;
+        if (cols_valid > BLOCK_N) cols_valid = BLOCK_N;
+        const bool vec_ok = (p.N % 4) == 0;
+        for (int f = et; f < rows_valid * kVecPerRow; f += kEpiThreads) {
+          const int rr = f / kVecPerRow, c4 = (f % kVecPerRow) * 4;
+          if (c4 >= cols_valid) continue;
+          const float4 v = *reinterpret_cast<const float4*>(sf + rr * kPitch + c4 * 4);
+          float* dst = p.out_f32 + (int64_t)(m0 + rr) * p.N + n0 + c4;
+          if (vec_ok && c4 + 3 < cols_valid) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(v.x), "f"(v.y),
+                         "f"(v.z), "f"(v.w)
+                         : "memory");
+          } else {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            for (int j = 0; j < 4; ++j)
+              if (c4 + j < cols_valid) atomicAdd(dst + j, vv[j]);
           }
         }
         if (p.tile_counters != nullptr) {
-          // ---- fused finalize by the last-arriving CTA of this output tile ----
+          // ---- fused finalize by the last-arriving CTA of this output tile (coalesced) ----
           uint32_t* s_last = tmem_slot + 1;
           __threadfence();
           asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -269,34 +284,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             *s_last = (uint32_t)last;
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (*s_last != 0u && grow < p.M) {
+          if (*s_last != 0u) {
             __threadfence();
-            float* wrow = p.out_f32 + (int64_t)grow * p.N + n0;
-            __nv_bfloat16* orow = p.out_bf16 + (int64_t)grow * p.ldo + n0;
-            int ncols = p.N - n0;
-            if (ncols > BLOCK_N) ncols = BLOCK_N;
-            for (int c = 0; c + 3 < ncols; c += 4) {
-              float4 v = __ldcg(reinterpret_cast<const float4*>(wrow + c));
-              *reinterpret_cast<float4*>(wrow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-              __nv_bfloat162 lo, hi;
-              if (p.accumulate) {
-                const uint2 o = *reinterpret_cast<const uint2*>(orow + c);
-                const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.x));
-                const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.y));
-                v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
+            const int total = rows_valid * kVecPerRow;
+            constexpr int U = 4;
+            for (int f0 = et; f0 < total; f0 += kEpiThreads * U) {
+              float4 v[U];
+              bool ok[U];
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                const int f = f0 + u * kEpiThreads;
+                const int rr = f / kVecPerRow, c4 = (f % kVecPerRow) * 4;
+                ok[u] = f < total && c4 + 3 < cols_valid;
+                if (ok[u])
+                  v[u] = __ldcg(reinterpret_cast<const float4*>(
+                      p.out_f32 + (int64_t)(m0 + rr) * p.N + n0 + c4));
               }
-              lo = __floats2bfloat162_rn(v.x, v.y);
-              hi = __floats2bfloat162_rn(v.z, v.w);
-              uint2 packed;
-              packed.x = *reinterpret_cast<uint32_t*>(&lo);
-              packed.y = *reinterpret_cast<uint32_t*>(&hi);
-              *reinterpret_cast<uint2*>(orow + c) = packed;
-            }
-            for (int c = ncols & ~3; c < ncols; ++c) {
-              float v = __ldcg(wrow + c);
-              wrow[c] = 0.f;
-              if (p.accumulate) v += __bfloat162float(orow[c]);
-              orow[c] = __float2bfloat16(v);
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                if (!ok[u]) continue;
+                const int f = f0 + u * kEpiThreads;
+                const int rr = f / kVecPerRow, c4 = (f % kVecPerRow) * 4;
+                float* w = p.out_f32 + (int64_t)(m0 + rr) * p.N + n0 + c4;
+                __nv_bfloat16* o = p.out_bf16 + (int64_t)(m0 + rr) * p.ldo + n0 + c4;
+                *reinterpret_cast<float4*>(w) = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 t = v[u];
+                if (p.accumulate) {
+                  const uint2 old = *reinterpret_cast<const uint2*>(o);
+                  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old.x));
+                  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old.y));
+                  t.x += a.x; t.y += a.y; t.z += b.x; t.w += b.y;
+                }
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y);
+                const __nv_bfloat162 hi = __floats2bfloat162_rn(t.z, t.w);
+                uint2 packed;
+                packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+                packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(o) = packed;
+              }
             }
           }
         }
@@ -404,6 +429,13 @@ const char* launch_variant(const GemmArgs& g, cudaStream_t stream) {
 
 const char* gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return "empty GEMM";
+  // cuTensorMapEncodeTiled is a driver call and needs a current context on THIS thread.  Autograd
+  // worker threads may not have one yet (torch binds lazily; observed CUDA_ERROR_INVALID_CONTEXT
+  // = 201 when a dgrad GEMM was the first CUDA work of the backward thread).
+  if (g.device >= 0) {
+    cudaError_t e = cudaSetDevice(g.device);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+  }
   const bool n64 = g.N <= 64;
   if (g.out_f32 != nullptr) {
     // split-K fp32 accumulation (wgrad): both operands MN-major or both K-major

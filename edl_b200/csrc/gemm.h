@@ -26,6 +26,7 @@ struct GemmArgs {
   int64_t ldo = 0;
   int* tile_counters = nullptr;       // >= ceil(M/128)*ceil(N/BLOCK_N) zero-initialised ints
   bool accumulate_out = false;
+  int device = -1;                    // CUDA device ordinal of the operands (binds the context)
 };
 
 // Returns nullptr on success, else a static error string.

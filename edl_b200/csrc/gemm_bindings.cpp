@@ -65,6 +65,7 @@ void gemm_bf16(const Tensor& A, const Tensor& B, const c10::optional<Tensor>& D,
   g.col_shift = optp<float>(col_shift);
   g.relu = relu;
   g.col_stats = optp<float>(col_stats);
+  g.device = A.device().index();
   c10::cuda::CUDAGuard guard(A.device());
   const char* err = edl::gemm_bf16(g, at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(err == nullptr, "edl gemm_bf16 failed: ", err);

@@ -23,6 +23,22 @@ void bn_bwd_apply(const void* dy, const void* x, const void* y, const float* gam
                   const float* dsums, void* dx, void* dres, float* dgamma, float* dbeta, int64_t M,
                   int C, bool relu, bool accumulate, cudaStream_t stream);
 
+// ---- bn_stream.cu (cp.async.bulk + mbarrier streaming variants; used when supported) ----
+bool bn_stream_supported(int64_t M, int C);
+void bn_stats_stream(const void* x, float* sums, int64_t M, int C, cudaStream_t s);
+void bn_apply_stream(const void* x, const void* res, void* y, const float* sums, const float* gamma,
+                     const float* beta, float* running_mean, float* running_var, float* saved_mean,
+                     float* saved_rstd, int64_t M, int C, float eps, float momentum, bool relu,
+                     cudaStream_t s);
+void bn_bwd_reduce_stream(const void* dy, const void* x, const void* y, const float* gamma,
+                          const float* beta, const float* saved_mean, const float* saved_rstd,
+                          float* dsums, int64_t M, int C, bool relu, cudaStream_t s);
+void bn_bwd_apply_stream(const void* dy, const void* x, const void* y, const float* gamma,
+                         const float* beta, const float* saved_mean, const float* saved_rstd,
+                         const float* dsums, void* dx, void* dres, float* dgamma, float* dbeta,
+                         int64_t M, int C, bool relu, bool accumulate, cudaStream_t s);
+void bn_set_stream_kernels(bool enabled);  // runtime switch (A/B measurements); default on
+
 // ---- optim.cu ----
 void sgd_momentum(void* param_lp, float* master, float* mom, const void* grad, bool grad_is_bf16,
                   const float* wd_mask, int64_t n, const float* lr, const float* grad_scale,
