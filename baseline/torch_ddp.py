@@ -66,8 +66,16 @@ class TorchDDPTrainer:
         self.model = TorchResNet50vd(depth=depth).to(device=device, dtype=torch.bfloat16)
         self.model = self.model.to(memory_format=torch.channels_last).train()
         self.world = dist.get_world_size() if dist.is_initialized() else 1
-        self.net = nn.parallel.DistributedDataParallel(self.model, device_ids=[device.index], bucket_cap_mb=16,
-                                                       gradient_as_bucket_view=True) if self.world > 1 else self.model
+        if self.world > 1:
+            # DDP + whole-step CUDA-graph capture recipe: build DDP under a side stream
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.net = nn.parallel.DistributedDataParallel(self.model, device_ids=[device.index],
+                                                               bucket_cap_mb=16, gradient_as_bucket_view=True)
+            torch.cuda.current_stream().wait_stream(side)
+        else:
+            self.net = self.model
         self.opt = torch.optim.SGD(self.model.parameters(), lr=lr, momentum=0.9, weight_decay=1e-4)
         self.static_x = torch.zeros(batch_size, 3, 224, 224, dtype=torch.bfloat16, device=device).contiguous(
             memory_format=torch.channels_last)
@@ -99,7 +107,17 @@ class TorchDDPTrainer:
     def step_device(self):
         if self.use_graph:
             if self.graph is None:
-                self.capture()
+                try:
+                    self.capture()
+                except Exception as e:  # noqa: BLE001 - stock DDP is not always capturable: run eagerly
+                    import sys
+                    print("torch baseline: CUDA-graph capture failed (%s); running eagerly" % type(e).__name__,
+                          file=sys.stderr)
+                    torch.cuda.synchronize()
+                    self.use_graph = False
+                    self.graph = None
+                    self._body()
+                    return self.static_loss
             self.graph.replay()
         else:
             self._body()
