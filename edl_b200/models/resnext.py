@@ -1,0 +1,128 @@
+"""ResNeXt (the distillation *teacher*: ResNeXt101_32x16d_wsl), inference-only, NHWC / bf16.
+
+The reference never contains this network -- it downloads a pre-exported Paddle Serving model
+(README.md:51-57, example/distill/resnet/scripts/start_local_teacher.sh:19-30); the architecture is
+the public WSL / torchvision ResNeXt (groups 32, width-per-group 16, depths 3-4-23-3; 194.0 M
+params, 72.3 GFLOP/img -- SURVEY App. F.2).
+
+Inference formulation: every BatchNorm is folded into a per-output-channel (scale, shift), so a
+layer is  conv -> *scale + shift (+ residual) -> ReLU :
+  * 1x1 convolutions run on the tcgen05 GEMM with scale/shift/ReLU fused in the epilogue
+    (``ops.gemm_bf16(col_scale=, col_shift=, relu=)``),
+  * grouped 3x3 convolutions use the library conv followed by the fused scale-shift-(add)-ReLU kernel,
+  * the block's last 1x1 adds the shortcut and applies ReLU in one fused kernel.
+"""
+import math
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+
+
+class FoldedConv(nn.Module):
+    """conv (+ folded BN scale/shift) (+ residual) (+ ReLU) for inference."""
+
+    def __init__(self, cin, cout, k, stride=1, groups=1, relu=True):
+        super().__init__()
+        self.cin, self.cout, self.k, self.stride, self.groups, self.relu = cin, cout, k, stride, groups, relu
+        self.weight = nn.Parameter(torch.empty(cout, k, k, cin // groups), requires_grad=False)   # KRSC
+        nn.init.normal_(self.weight, 0.0, math.sqrt(2.0 / (k * k * cin // groups)))
+        # folded BN: scale = gamma / sqrt(var + eps), shift = beta - mean * scale  (random-init teacher:
+        # gamma=1, beta=0, running stats (0, 1) => identity; real weights load through load_bn())
+        self.register_buffer("scale", torch.ones(cout, dtype=torch.float32))
+        self.register_buffer("shift", torch.zeros(cout, dtype=torch.float32))
+
+    def load_bn(self, gamma, beta, mean, var, eps=1e-5):
+        s = gamma.float() * torch.rsqrt(var.float() + eps)
+        self.scale.copy_(s)
+        self.shift.copy_(beta.float() - mean.float() * s)
+
+    def forward(self, x, residual=None):
+        fast = (x.is_cuda and x.dtype == torch.bfloat16 and self.k == 1 and self.groups == 1
+                and self.cin % 8 == 0 and self.cout % 8 == 0)
+        if fast:
+            if self.stride != 1:
+                x = x[:, :, ::self.stride, ::self.stride].contiguous(memory_format=torch.channels_last)
+            n, c, h, w = x.shape
+            x2 = x.permute(0, 2, 3, 1).reshape(-1, c)
+            y = torch.empty((n, self.cout, h, w), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+            y2 = y.permute(0, 2, 3, 1).reshape(-1, self.cout)
+            if residual is None:
+                ops.gemm_bf16(x2, self.weight.view(self.cout, self.cin), out=y2, col_scale=self.scale,
+                              col_shift=self.shift, relu=self.relu)
+                return y
+            ops.gemm_bf16(x2, self.weight.view(self.cout, self.cin), out=y2)
+            return ops.scale_shift_act(y, self.scale, self.shift, residual, self.relu)
+        y = F.conv2d(x, self.weight.permute(0, 3, 1, 2), None, self.stride, (self.k - 1) // 2, 1, self.groups)
+        return ops.scale_shift_act(y, self.scale, self.shift, residual, self.relu)
+
+
+class ResNeXtBlock(nn.Module):
+    def __init__(self, cin, planes, stride, groups, width_per_group, downsample):
+        super().__init__()
+        width = int(planes * (width_per_group / 64.0)) * groups
+        cout = planes * 4
+        self.c1 = FoldedConv(cin, width, 1)
+        self.c2 = FoldedConv(width, width, 3, stride, groups)
+        self.c3 = FoldedConv(width, cout, 1, relu=True)           # ReLU after the residual add
+        self.ds = FoldedConv(cin, cout, 1, stride, relu=False) if downsample else None
+
+    def forward(self, x):
+        s = self.ds(x) if self.ds is not None else x
+        return self.c3(self.c2(self.c1(x)), residual=s)
+
+
+class ResNeXt(nn.Module):
+    def __init__(self, depths: List[int], groups=32, width_per_group=16, class_dim=1000, base=64):
+        super().__init__()
+        self.stem = FoldedConv(3, base, 7, 2)
+        blocks, cin = [], base
+        for stage, n in enumerate(depths):
+            planes = base << stage
+            for i in range(n):
+                stride = 2 if (i == 0 and stage > 0) else 1
+                blocks.append(ResNeXtBlock(cin, planes, stride, groups, width_per_group, downsample=(i == 0)))
+                cin = planes * 4
+        self.blocks = nn.Sequential(*blocks)
+        self.fc_weight = nn.Parameter(torch.empty(class_dim, cin), requires_grad=False)
+        self.fc_bias = nn.Parameter(torch.zeros(class_dim, dtype=torch.float32), requires_grad=False)
+        nn.init.uniform_(self.fc_weight, -1.0 / math.sqrt(cin), 1.0 / math.sqrt(cin))
+
+    @torch.no_grad()
+    def forward(self, x, return_logits=True):
+        x = self.stem(x)
+        x = ops.max_pool_3x3_s2(x) if x.is_cuda else F.max_pool2d(x, 3, 2, 1)
+        x = self.blocks(x)
+        x = ops.global_avg_pool(x)
+        if x.is_cuda and x.dtype == torch.bfloat16:
+            logits = ops.gemm_bf16(x, self.fc_weight, col_shift=self.fc_bias)
+        else:
+            logits = F.linear(x, self.fc_weight, self.fc_bias.to(x.dtype))
+        return logits if return_logits else torch.softmax(logits.float(), -1)
+
+
+def ResNeXt101_32x16d(class_dim=1000):
+    """The WSL teacher: 194 M parameters, 72.3 GFLOP / image at 224x224."""
+    return ResNeXt([3, 4, 23, 3], 32, 16, class_dim)
+
+
+def ResNeXt50_32x4d(class_dim=1000):
+    return ResNeXt([3, 4, 6, 3], 32, 4, class_dim)
+
+
+def ResNeXt_tiny(class_dim=16):
+    """2-2-2-2 / 8 groups x 4: unit-test sized."""
+    return ResNeXt([1, 1, 1, 1], 8, 4, class_dim, base=32)
+
+
+def to_inference_dtype(model, dtype=torch.bfloat16, device=None):
+    for m in model.modules():
+        for name, p in list(m.named_parameters(recurse=False)):
+            keep = name.endswith("bias")
+            p.data = p.data.to(device=device, dtype=torch.float32 if keep else dtype)
+        for name, b in list(m.named_buffers(recurse=False)):
+            m._buffers[name] = b.to(device=device)
+    return model.eval()
