@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--comm-blocks", type=int, default=32)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--layers", type=int, default=50)
+    ap.add_argument("--no-fused-bn", action="store_true", help="A/B: disable the SM-resident fused BN kernels")
+    ap.add_argument("--no-stream-bn", action="store_true", help="A/B: disable the cp.async.bulk BN kernels")
     return ap.parse_args()
 
 
@@ -144,6 +146,10 @@ def main():
         from edl_b200.models import ResNetVd, to_train_dtype
         from edl_b200.trainer import StudentTrainer
 
+        if args.no_fused_bn:
+            ops.set_fused_bn(False)
+        if args.no_stream_bn:
+            ops.native().bn_set_stream_kernels(False)
         model = to_train_dtype(ResNetVd(args.layers, impl=args.conv_impl), torch.bfloat16, dev)
         model.train()
         trainer = StudentTrainer(model, B, lr=0.1 * B * world / 256.0, use_graph=not args.no_graph,

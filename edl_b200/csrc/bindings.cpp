@@ -105,6 +105,48 @@ void bn_bwd_apply(const Tensor& dy, const Tensor& x, const c10::optional<Tensor>
                     cur_stream());
 }
 
+bool bn_fused_fits(int64_t M, int64_t C, int64_t num_operands) {
+  return edl::bn_fused_fits(M, (int)C, (int)num_operands);
+}
+
+void bn_fwd_fused(const Tensor& x, const c10::optional<Tensor>& res, Tensor& y, Tensor& sums,
+                  const Tensor& gamma, const Tensor& beta, const c10::optional<Tensor>& running_mean,
+                  const c10::optional<Tensor>& running_var, Tensor& saved_mean, Tensor& saved_rstd,
+                  double eps, double momentum, bool relu, Tensor& sync_counter) {
+  check_bf16(x, "x");
+  check_bf16(y, "y");
+  check_f32(sums, "sums");
+  TORCH_CHECK(sync_counter.scalar_type() == at::kInt && sync_counter.is_cuda());
+  const int C = x.size(-1);
+  const int64_t M = x.numel() / C;
+  c10::cuda::CUDAGuard g(x.device());
+  const char* err = edl::bn_fwd_fused(
+      x.data_ptr(), opt_ptr<void>(res), y.data_ptr(), sums.data_ptr<float>(), gamma.data_ptr<float>(),
+      beta.data_ptr<float>(), opt_ptr<float>(running_mean), opt_ptr<float>(running_var),
+      saved_mean.data_ptr<float>(), saved_rstd.data_ptr<float>(), M, C, (float)eps, (float)momentum, relu,
+      reinterpret_cast<unsigned int*>(sync_counter.data_ptr<int>()), cur_stream());
+  TORCH_CHECK(err == nullptr, "bn_fwd_fused: ", err);
+}
+
+void bn_bwd_fused(const Tensor& dy, const Tensor& x, const c10::optional<Tensor>& y, const Tensor& gamma,
+                  const Tensor& beta, const Tensor& saved_mean, const Tensor& saved_rstd, Tensor& dsums,
+                  Tensor& dx, const c10::optional<Tensor>& dres, const c10::optional<Tensor>& dgamma,
+                  const c10::optional<Tensor>& dbeta, bool relu, bool accumulate, Tensor& sync_counter) {
+  check_bf16(dy, "dy");
+  check_bf16(x, "x");
+  check_bf16(dx, "dx");
+  TORCH_CHECK(sync_counter.scalar_type() == at::kInt && sync_counter.is_cuda());
+  const int C = x.size(-1);
+  const int64_t M = x.numel() / C;
+  c10::cuda::CUDAGuard g(x.device());
+  const char* err = edl::bn_bwd_fused(
+      dy.data_ptr(), x.data_ptr(), opt_ptr<void>(y), gamma.data_ptr<float>(), beta.data_ptr<float>(),
+      saved_mean.data_ptr<float>(), saved_rstd.data_ptr<float>(), dsums.data_ptr<float>(), dx.data_ptr(),
+      opt_ptr<void>(dres), opt_ptr<float>(dgamma), opt_ptr<float>(dbeta), M, C, relu, accumulate,
+      reinterpret_cast<unsigned int*>(sync_counter.data_ptr<int>()), cur_stream());
+  TORCH_CHECK(err == nullptr, "bn_bwd_fused: ", err);
+}
+
 // ------------------------------------------------------------------ optimizers
 void sgd_momentum(const c10::optional<Tensor>& param_lp, Tensor& master, Tensor& mom,
                   const Tensor& grad, const c10::optional<Tensor>& wd_mask, const Tensor& lr,
@@ -282,6 +324,51 @@ void comm_allgather_scalars(const std::vector<int64_t>& data_ptrs,
                               cur_stream());
 }
 
+// ------------------------------------------------------------------ logit ship / device distill feed
+// Raw peer addresses (ints) come from parallel.symm.SymmSlice; local tensors are torch tensors.
+void peer_ship(const Tensor& src, int64_t dst_peer, int64_t nbytes, int64_t flag_peer,
+               const c10::optional<Tensor>& seq, int64_t seq_imm, Tensor& done) {
+  TORCH_CHECK(src.is_cuda() && src.is_contiguous() && nbytes % 16 == 0);
+  c10::cuda::CUDAGuard g(src.device());
+  edl::peer_ship(src.data_ptr(), reinterpret_cast<void*>(dst_peer), nbytes, reinterpret_cast<void*>(flag_peer),
+                 opt_ptr<void>(seq), (uint32_t)seq_imm, done.data_ptr(), cur_stream());
+}
+
+void logit_ship(const Tensor& logits, int64_t slot_peer, int64_t stats_peer, double temperature,
+                int64_t flag_peer, const c10::optional<Tensor>& seq, int64_t seq_imm, Tensor& done) {
+  check_bf16(logits, "logits");
+  TORCH_CHECK(logits.dim() == 2);
+  c10::cuda::CUDAGuard g(logits.device());
+  edl::logit_ship(logits.data_ptr(), reinterpret_cast<void*>(slot_peer), reinterpret_cast<float*>(stats_peer),
+                  logits.size(0), logits.size(1), (float)temperature, reinterpret_cast<void*>(flag_peer),
+                  opt_ptr<void>(seq), (uint32_t)seq_imm, done.data_ptr(), cur_stream());
+}
+
+void soft_ce_recv(const Tensor& logits, const Tensor& slot, const Tensor& slot_stats, const Tensor& flag,
+                  const c10::optional<Tensor>& seq, int64_t seq_imm, Tensor& loss_out, Tensor& row_stats,
+                  double s_temp, double t_temp, bool kl, double loss_scale, double timeout_s,
+                  const c10::optional<Tensor>& err) {
+  TORCH_CHECK(logits.is_cuda() && logits.is_contiguous() && logits.dim() == 2);
+  c10::cuda::CUDAGuard g(logits.device());
+  edl::soft_ce_recv(logits.data_ptr(), logits.scalar_type() == at::kBFloat16, slot.data_ptr(),
+                    slot_stats.data_ptr<float>(), flag.data_ptr(), opt_ptr<void>(seq), (uint32_t)seq_imm,
+                    loss_out.data_ptr<float>(), row_stats.data_ptr<float>(), logits.size(0), logits.size(1),
+                    (float)s_temp, (float)t_temp, kl, (float)loss_scale, timeout_s, opt_ptr<void>(err),
+                    cur_stream());
+}
+
+void slot_ack(int64_t ack_peer, const c10::optional<Tensor>& seq, int64_t seq_imm, const Tensor& any_local) {
+  c10::cuda::CUDAGuard g(any_local.device());
+  edl::slot_ack(reinterpret_cast<void*>(ack_peer), opt_ptr<void>(seq), (uint32_t)seq_imm, cur_stream());
+}
+
+void wait_flag_async(const Tensor& flag, const c10::optional<Tensor>& seq, int64_t seq_imm, double timeout_s,
+                     const c10::optional<Tensor>& err) {
+  c10::cuda::CUDAGuard g(flag.device());
+  edl::wait_flag_async(flag.data_ptr(), opt_ptr<void>(seq), (uint32_t)seq_imm, timeout_s, opt_ptr<void>(err),
+                       cur_stream());
+}
+
 }  // namespace
 
 void register_gemm_bindings(pybind11::module_& m);  // gemm_bindings.cpp
@@ -289,6 +376,9 @@ void register_gemm_bindings(pybind11::module_& m);  // gemm_bindings.cpp
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "edl_b200 sm_100a kernels";
   m.def("bn_set_stream_kernels", &edl::bn_set_stream_kernels);
+  m.def("bn_fused_fits", &bn_fused_fits);
+  m.def("bn_fwd_fused", &bn_fwd_fused);
+  m.def("bn_bwd_fused", &bn_bwd_fused);
   m.def("bn_stats", &bn_stats);
   m.def("bn_apply", &bn_apply);
   m.def("scale_shift_act", &scale_shift_act);
@@ -311,5 +401,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("comm_allgather_scalars", &comm_allgather_scalars);
   m.def("comm_sig_words", &edl::comm_sig_words);
   m.def("comm_error_word_offset", &edl::comm_error_word_offset);
+  m.def("peer_ship", &peer_ship);
+  m.def("logit_ship", &logit_ship);
+  m.def("soft_ce_recv", &soft_ce_recv);
+  m.def("slot_ack", &slot_ack);
+  m.def("wait_flag_async", &wait_flag_async);
   register_gemm_bindings(m);
 }

@@ -257,6 +257,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int cols_valid = p.N - n0;
         if (cols_valid > BLOCK_N) cols_valid = BLOCK_N;
         const bool vec_ok = (p.N % 4) == 0;
+        if (gridDim.z == 1 && p.out_bf16 != nullptr) {
+          // no split: this CTA owns the tile -> write bf16 (+= sink) straight from the staged tile,
+          // coalesced, without touching the fp32 workspace, atomics or tile counters
+          for (int f = et; f < rows_valid * kVecPerRow; f += kEpiThreads) {
+            const int rr = f / kVecPerRow, c4 = (f % kVecPerRow) * 4;
+            if (c4 + 3 >= cols_valid) continue;
+            float4 t = *reinterpret_cast<const float4*>(sf + rr * kPitch + c4 * 4);
+            __nv_bfloat16* o = p.out_bf16 + (int64_t)(m0 + rr) * p.ldo + n0 + c4;
+            if (p.accumulate) {
+              const uint2 old = *reinterpret_cast<const uint2*>(o);
+              const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old.x));
+              const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old.y));
+              t.x += a.x; t.y += a.y; t.z += b.x; t.w += b.y;
+            }
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(t.z, t.w);
+            uint2 packed;
+            packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+            packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(o) = packed;
+          }
+        } else {
         for (int f = et; f < rows_valid * kVecPerRow; f += kEpiThreads) {
           const int rr = f / kVecPerRow, c4 = (f % kVecPerRow) * 4;
           if (c4 >= cols_valid) continue;
@@ -272,7 +294,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (c4 + j < cols_valid) atomicAdd(dst + j, vv[j]);
           }
         }
-        if (p.tile_counters != nullptr) {
+        }
+        if (p.tile_counters != nullptr && gridDim.z > 1) {
           // ---- fused finalize by the last-arriving CTA of this output tile (coalesced) ----
           uint32_t* s_last = tmem_slot + 1;
           __threadfence();

@@ -37,7 +37,19 @@ void bn_bwd_apply_stream(const void* dy, const void* x, const void* y, const flo
                          const float* beta, const float* saved_mean, const float* saved_rstd,
                          const float* dsums, void* dx, void* dres, float* dgamma, float* dbeta,
                          int64_t M, int C, bool relu, bool accumulate, cudaStream_t s);
-void bn_set_stream_kernels(bool enabled);  // runtime switch (A/B measurements); default on
+void bn_set_stream_kernels(bool enabled);
+
+// ---- bn_fused.cu (SM-resident single-launch BN forward / backward with a grid barrier) ----
+bool bn_fused_fits(int64_t M, int C, int num_operands);
+const char* bn_fwd_fused(const void* x, const void* res, void* y, float* sums, const float* gamma,
+                         const float* beta, float* running_mean, float* running_var,
+                         float* saved_mean, float* saved_rstd, int64_t M, int C, float eps,
+                         float momentum, bool relu, unsigned int* sync_counter, cudaStream_t s);
+const char* bn_bwd_fused(const void* dy, const void* x, const void* y, const float* gamma,
+                         const float* beta, const float* saved_mean, const float* saved_rstd,
+                         float* dsums, void* dx, void* dres, float* dgamma, float* dbeta, int64_t M,
+                         int C, bool relu, bool accumulate, unsigned int* sync_counter,
+                         cudaStream_t s);  // runtime switch (A/B measurements); default on
 
 // ---- optim.cu ----
 void sgd_momentum(void* param_lp, float* master, float* mom, const void* grad, bool grad_is_bf16,
@@ -91,5 +103,19 @@ void comm_broadcast(const CommHandles& h, int root, int64_t nbytes, int nblocks,
                     cudaStream_t stream);
 void comm_allgather_scalars(const CommHandles& h, const float* in, float* out, int count,
                             cudaStream_t stream);
+
+// ---- logit_ship.cu (teacher -> student over NVSwitch peer memory, fused with the loss) ----
+void peer_ship(const void* src, void* dst_peer, int64_t nbytes, void* flag_peer, const void* seq_ptr,
+               uint32_t seq_imm, void* done_counter, cudaStream_t s);
+void logit_ship(const void* logits, void* slot_peer, float* stats_peer, int B, int C, float temperature,
+                void* flag_peer, const void* seq_ptr, uint32_t seq_imm, void* done_counter,
+                cudaStream_t s);
+void soft_ce_recv(const void* logits, bool logits_bf16, const void* slot, const float* slot_stats,
+                  const void* flag, const void* seq_ptr, uint32_t seq_imm, float* loss_out,
+                  float* row_stats, int B, int C, float s_temp, float t_temp, bool kl, float loss_scale,
+                  double timeout_s, void* err, cudaStream_t s);
+void slot_ack(void* ack_peer, const void* seq_ptr, uint32_t seq_imm, cudaStream_t s);
+void wait_flag_async(const void* flag, const void* seq_ptr, uint32_t seq_imm, double timeout_s, void* err,
+                     cudaStream_t s);
 
 }  // namespace edl

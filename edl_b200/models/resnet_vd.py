@@ -53,8 +53,8 @@ class ConvBNAct(nn.Module):
 
     def forward(self, x, residual=None):
         y, stats = self.conv(x, self.training)
-        if stats is None and self.training and y.is_cuda and self.fwd_stats is not None:
-            stats = ops.bn_stats_into(y, self.fwd_stats)  # arena slice: no per-layer alloc/memset
+        # stats is None for library convs: the BN op then computes them itself (SM-resident fused
+        # kernel when the tensor fits, else the streaming stats kernel into its arena slice)
         return self.bn(y, residual=residual, sums=stats)
 
 

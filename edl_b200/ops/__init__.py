@@ -54,7 +54,7 @@ def reset_launches() -> None:
     _launches = 0
 
 
-from .bn import batch_norm_act, BatchNormAct2d, scale_shift_act, bn_stats_into  # noqa: E402
+from .bn import batch_norm_act, BatchNormAct2d, scale_shift_act, bn_stats_into, set_fused_bn  # noqa: E402
 from .loss import soft_cross_entropy, topk_accuracy  # noqa: E402
 from .pool import max_pool_3x3_s2, avg_pool_2x2, global_avg_pool  # noqa: E402
 from .optim import FlatSGDMomentum, FlatAdam  # noqa: E402

@@ -10,6 +10,14 @@ import torch
 import torch.nn as nn
 
 
+_FUSED = True   # SM-resident single-launch BN kernels (bn_fused.cu) when the tensor fits
+
+
+def set_fused_bn(enabled: bool) -> None:
+    global _FUSED
+    _FUSED = bool(enabled)
+
+
 def _mc(x: torch.Tensor) -> torch.Tensor:
     """View an activation as a contiguous [M, C] matrix (C fastest)."""
     if x.dim() == 2:
@@ -55,7 +63,7 @@ def _ref_forward(x, res, gamma, beta, rm, rv, relu, training, momentum, eps):
 
 class _BNActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, rm, rv, sums, bwd_ws, sink_g, sink_b, relu, momentum,
+    def forward(ctx, x, res, gamma, beta, rm, rv, sums, ws, sink_g, sink_b, relu, momentum,
                 eps):
         from . import native, count_launch
 
@@ -65,7 +73,9 @@ class _BNActFn(torch.autograd.Function):
         ctx.has_res = res is not None
         sink_g, ctx.ready = sink_g if isinstance(sink_g, tuple) else (sink_g, None)
         ctx.sinks = (sink_g, sink_b)
-        ctx.bwd_ws = bwd_ws
+        # ws = (fwd_stats[2C] | None, bwd_sums[2C] | None, sync int32[2] | None): pre-zeroed arena slices
+        fwd_ws, bwd_ws, sync_ws = ws if ws is not None else (None, None, None)
+        ctx.bwd_ws, ctx.sync_ws = bwd_ws, sync_ws
         if not x.is_cuda:
             y, mean, rstd = _ref_forward(x, res, gamma, beta, rm, rv, relu, True, momentum, eps)
             ctx.save_for_backward(x, y, gamma, mean, rstd, beta)
@@ -73,16 +83,23 @@ class _BNActFn(torch.autograd.Function):
         C = native()
         ch = gamma.numel()
         x2 = _mc(x)
-        if sums is None:
-            sums = torch.zeros(2 * ch, device=x.device, dtype=torch.float32)
-            C.bn_stats(x2, sums)
-            count_launch()
         y = torch.empty_like(x)
         mean = torch.empty(ch, device=x.device, dtype=torch.float32)
         rstd = torch.empty(ch, device=x.device, dtype=torch.float32)
-        C.bn_apply(x2, _mc(res) if res is not None else None, _mc(y), sums, gamma, beta, rm, rv,
-                   mean, rstd, eps, momentum, relu)
-        count_launch()
+        res2 = _mc(res) if res is not None else None
+        if sums is None and _FUSED and C.bn_fused_fits(x2.shape[0], ch, 2 if res is not None else 1):
+            # statistics + normalise in ONE SM-resident kernel (tensor crosses HBM once)
+            sums = fwd_ws if fwd_ws is not None else torch.zeros(2 * ch, device=x.device, dtype=torch.float32)
+            sync = sync_ws[0:1] if sync_ws is not None else torch.zeros(1, device=x.device, dtype=torch.int32)
+            C.bn_fwd_fused(x2, res2, _mc(y), sums, gamma, beta, rm, rv, mean, rstd, eps, momentum, relu, sync)
+            count_launch()
+        else:
+            if sums is None:
+                sums = fwd_ws if fwd_ws is not None else torch.zeros(2 * ch, device=x.device, dtype=torch.float32)
+                C.bn_stats(x2, sums)
+                count_launch()
+            C.bn_apply(x2, res2, _mc(y), sums, gamma, beta, rm, rv, mean, rstd, eps, momentum, relu)
+            count_launch()
         # the saved output is only needed for the ReLU mask when a residual was added; otherwise the
         # backward kernels recompute the mask from x (one fewer pass over the activation)
         ctx.save_for_backward(x, y if (relu and res is not None) else None, gamma, mean, rstd, beta)
@@ -126,7 +143,6 @@ class _BNActFn(torch.autograd.Function):
             dsums = torch.zeros(2 * ch, device=x.device, dtype=torch.float32)
         x2, dy2 = _mc(x), _mc(dy)
         y2 = _mc(y) if (relu and y is not None) else None
-        C.bn_bwd_reduce(dy2, x2, y2, gamma, beta, mean, rstd, dsums, relu)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
         if sink_g is not None:
@@ -135,9 +151,17 @@ class _BNActFn(torch.autograd.Function):
             dg = torch.empty_like(gamma)
             db = torch.empty_like(gamma)
             acc = False
-        C.bn_bwd_apply(dy2, x2, y2, gamma, beta, mean, rstd, dsums, _mc(dx),
-                       _mc(dres) if has_res else None, dg, db, relu, acc)
-        count_launch(2)
+        if _FUSED and C.bn_fused_fits(x2.shape[0], ch, 3 if y2 is not None else 2):
+            sync = ctx.sync_ws[1:2] if ctx.sync_ws is not None else torch.zeros(1, device=x.device,
+                                                                               dtype=torch.int32)
+            C.bn_bwd_fused(dy2, x2, y2, gamma, beta, mean, rstd, dsums, _mc(dx),
+                           _mc(dres) if has_res else None, dg, db, relu, acc, sync)
+            count_launch()
+        else:
+            C.bn_bwd_reduce(dy2, x2, y2, gamma, beta, mean, rstd, dsums, relu)
+            C.bn_bwd_apply(dy2, x2, y2, gamma, beta, mean, rstd, dsums, _mc(dx),
+                           _mc(dres) if has_res else None, dg, db, relu, acc)
+            count_launch(2)
         if sink_g is not None:
             dg = db = None
             if ctx.ready is not None:
@@ -146,7 +170,7 @@ class _BNActFn(torch.autograd.Function):
 
 
 def batch_norm_act(x, gamma, beta, running_mean=None, running_var=None, residual=None, relu=False,
-                   training=True, momentum=0.1, eps=1e-5, sums=None, bwd_ws=None, sinks=None):
+                   training=True, momentum=0.1, eps=1e-5, sums=None, bwd_ws=None, sinks=None, ws=None):
     """y = act(BN(x) (+ residual)).  ``sums`` may carry per-channel (sum, sum^2) already produced
     by the conv/GEMM epilogue; ``bwd_ws`` is an optional pre-zeroed [2C] fp32 scratch; ``sinks`` is
     an optional ``(dgamma_view, dbeta_view[, ready_callback])`` tuple: the backward accumulates the
@@ -156,7 +180,9 @@ def batch_norm_act(x, gamma, beta, running_mean=None, running_var=None, residual
         shift = beta.float() - running_mean.float() * scale
         return scale_shift_act(x, scale, shift, residual, relu)
     sink_g, sink_b, ready = (tuple(sinks) + (None,))[:3] if sinks is not None else (None, None, None)
-    return _BNActFn.apply(x, residual, gamma, beta, running_mean, running_var, sums, bwd_ws,
+    if ws is None and bwd_ws is not None:
+        ws = (None, bwd_ws, None)
+    return _BNActFn.apply(x, residual, gamma, beta, running_mean, running_var, sums, ws,
                           (sink_g, ready), sink_b, relu, momentum, eps)
 
 
@@ -212,7 +238,7 @@ class BatchNormAct2d(nn.Module):
         self.bias = nn.Parameter(torch.zeros(num_features, dtype=torch.float32))
         self.register_buffer("running_mean", torch.zeros(num_features, dtype=torch.float32))
         self.register_buffer("running_var", torch.ones(num_features, dtype=torch.float32))
-        self.bwd_ws = None  # optional arena slice, see parallel.engine.StepArena
+        self.ws = None      # optional (fwd_stats, bwd_sums, sync) arena slices, see trainer.StepArena
 
     def _sinks(self):
         sg = getattr(self.weight, "_edl_grad_sink", None)
@@ -226,7 +252,7 @@ class BatchNormAct2d(nn.Module):
     def forward(self, x, residual=None, sums=None):
         return batch_norm_act(x, self.weight, self.bias, self.running_mean, self.running_var,
                               residual=residual, relu=self.relu, training=self.training,
-                              momentum=self.momentum, eps=self.eps, sums=sums, bwd_ws=self.bwd_ws,
+                              momentum=self.momentum, eps=self.eps, sums=sums, ws=self.ws,
                               sinks=self._sinks())
 
     def extra_repr(self):

@@ -75,9 +75,13 @@ def _tma_compatible(a, b, out, n):
 
 
 def _split_k_for(m, n, k):
+    """Split-K factor of the wgrad GEMM.  fp32 atomics cost ~2 us per million element-updates at L2
+    (measured, profiles/), so the split is chosen to fill ~one wave of SMs and never more: outputs
+    with >= 148 tiles are not split at all (direct bf16 store), tiny outputs (stage-2 layers, 1-8
+    tiles with K ~ 100k) take the full 148-way split because they have few elements to update."""
     tiles = ((m + 127) // 128) * ((n + 127) // 128 if n > 64 else 1)
     kb = (k + 63) // 64
-    want = max(1, (2 * _NUM_SMS + tiles - 1) // tiles)
+    want = max(1, _NUM_SMS // tiles)
     return max(1, min(want, max(1, kb // 2)))
 
 

@@ -31,14 +31,17 @@ class StepArena:
 
     def __init__(self, model: torch.nn.Module, device):
         units = [m for m in model.modules() if isinstance(m, ConvBNAct)]
-        total = sum(4 * u.cout for u in units)
+        total = sum(4 * u.cout + 4 for u in units)
         self.buf = torch.zeros(max(total, 4), dtype=torch.float32, device=device)
         off = 0
         for u in units:
             u.fwd_stats = self.buf[off:off + 2 * u.cout]
             off += 2 * u.cout
-            u.bn.bwd_ws = self.buf[off:off + 2 * u.cout]
+            bwd = self.buf[off:off + 2 * u.cout]
             off += 2 * u.cout
+            sync = self.buf[off:off + 4].view(torch.int32)   # grid-barrier counters (fwd, bwd)
+            off += 4
+            u.bn.ws = (u.fwd_stats, bwd, sync)
 
     def zero(self):
         self.buf.zero_()

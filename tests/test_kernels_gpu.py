@@ -19,9 +19,21 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("shape", [(4, 32, 28, 28), (2, 64, 56, 56), (3, 256, 14, 14), (2, 2048, 7, 7),
-                                   (1, 1000 // 8 * 8, 5, 5)])
+                                   (1, 1000 // 8 * 8, 5, 5), (32, 128, 28, 28), (16, 64, 112, 112)])
 @pytest.mark.parametrize("relu,res", [(False, False), (True, False), (True, True)])
-def test_bn_fwd_bwd(shape, relu, res):
+@pytest.mark.parametrize("path", ["fused", "stream", "regs"])
+def test_bn_fwd_bwd(shape, relu, res, path):
+    """path: SM-resident fused kernels / cp.async.bulk streaming kernels / register kernels."""
+    ops.set_fused_bn(path == "fused")
+    ops.native().bn_set_stream_kernels(path != "regs")
+    try:
+        _bn_fwd_bwd(shape, relu, res)
+    finally:
+        ops.set_fused_bn(True)
+        ops.native().bn_set_stream_kernels(True)
+
+
+def _bn_fwd_bwd(shape, relu, res):
     torch.manual_seed(0)
     n, c, h, w = shape
     x = _cl((torch.randn(shape, device=DEV) * 2 + 0.5).bfloat16()).requires_grad_(True)
