@@ -324,6 +324,42 @@ void comm_allgather_scalars(const std::vector<int64_t>& data_ptrs,
                               cur_stream());
 }
 
+// ------------------------------------------------------------------ misc fused ops
+void rope(const Tensor& x, const Tensor& cosv, const Tensor& sinv, Tensor& y, bool inverse) {
+  check_bf16(x, "x");
+  check_f32(cosv, "cos");
+  check_f32(sinv, "sin");
+  TORCH_CHECK(x.dim() == 3 && x.size(2) % 2 == 0 && cosv.size(0) == x.size(0) && cosv.size(1) == x.size(2) / 2);
+  c10::cuda::CUDAGuard g(x.device());
+  edl::rope(x.data_ptr(), cosv.data_ptr<float>(), sinv.data_ptr<float>(), y.data_ptr(), x.size(0), x.size(1),
+            x.size(2), inverse, cur_stream());
+}
+
+void embedding_bag_fwd(const Tensor& table, const Tensor& ids, Tensor& out) {
+  TORCH_CHECK(table.is_cuda() && table.is_contiguous() && ids.is_contiguous() && ids.scalar_type() == at::kLong);
+  c10::cuda::CUDAGuard g(table.device());
+  edl::embedding_bag_fwd(table.data_ptr(), table.scalar_type() == at::kBFloat16, ids.data_ptr<int64_t>(),
+                         out.data_ptr(), ids.size(0), ids.size(1), table.size(1), cur_stream());
+}
+
+void embedding_bag_bwd(const Tensor& dout, const Tensor& ids, Tensor& dtable) {
+  check_f32(dtable, "dtable");
+  c10::cuda::CUDAGuard g(dout.device());
+  edl::embedding_bag_bwd(dout.data_ptr(), dout.scalar_type() == at::kBFloat16, ids.data_ptr<int64_t>(),
+                         dtable.data_ptr<float>(), ids.size(0), ids.size(1), dtable.size(1), cur_stream());
+}
+
+void normalize_u8(const Tensor& x, Tensor& y, std::vector<double> mean, std::vector<double> stdv,
+                  const c10::optional<Tensor>& flip) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kByte && x.is_contiguous() && x.dim() == 4 && x.size(3) == 3);
+  check_bf16(y, "y");
+  const float m[3] = {(float)mean[0], (float)mean[1], (float)mean[2]};
+  const float sd[3] = {(float)stdv[0], (float)stdv[1], (float)stdv[2]};
+  c10::cuda::CUDAGuard g(x.device());
+  edl::normalize_u8(x.data_ptr<uint8_t>(), y.data_ptr(), x.size(0), x.size(1), x.size(2), m, sd,
+                    opt_ptr<uint8_t>(flip), cur_stream());
+}
+
 // ------------------------------------------------------------------ logit ship / device distill feed
 // Raw peer addresses (ints) come from parallel.symm.SymmSlice; local tensors are torch tensors.
 void peer_ship(const Tensor& src, int64_t dst_peer, int64_t nbytes, int64_t flag_peer,
@@ -401,6 +437,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("comm_allgather_scalars", &comm_allgather_scalars);
   m.def("comm_sig_words", &edl::comm_sig_words);
   m.def("comm_error_word_offset", &edl::comm_error_word_offset);
+  m.def("rope", &rope);
+  m.def("embedding_bag_fwd", &embedding_bag_fwd);
+  m.def("embedding_bag_bwd", &embedding_bag_bwd);
+  m.def("normalize_u8", &normalize_u8);
   m.def("peer_ship", &peer_ship);
   m.def("logit_ship", &logit_ship);
   m.def("soft_ce_recv", &soft_ce_recv);

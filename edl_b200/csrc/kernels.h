@@ -104,6 +104,16 @@ void comm_broadcast(const CommHandles& h, int root, int64_t nbytes, int nblocks,
 void comm_allgather_scalars(const CommHandles& h, const float* in, float* out, int count,
                             cudaStream_t stream);
 
+// ---- misc.cu ----
+void rope(const void* x, const float* cosv, const float* sinv, void* y, int64_t T, int H, int D,
+          bool inverse, cudaStream_t s);
+void embedding_bag_fwd(const void* table, bool bf16, const int64_t* ids, void* out, int64_t B, int L,
+                       int D, cudaStream_t s);
+void embedding_bag_bwd(const void* dout, bool bf16, const int64_t* ids, float* dtable, int64_t B, int L,
+                       int D, cudaStream_t s);
+void normalize_u8(const uint8_t* x, void* y, int64_t N, int H, int W, const float* mean,
+                  const float* stdv, const uint8_t* flip, cudaStream_t s);
+
 // ---- logit_ship.cu (teacher -> student over NVSwitch peer memory, fused with the loss) ----
 void peer_ship(const void* src, void* dst_peer, int64_t nbytes, void* flag_peer, const void* seq_ptr,
                uint32_t seq_imm, void* done_counter, cudaStream_t s);

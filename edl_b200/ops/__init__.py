@@ -59,6 +59,7 @@ from .loss import soft_cross_entropy, topk_accuracy  # noqa: E402
 from .pool import max_pool_3x3_s2, avg_pool_2x2, global_avg_pool  # noqa: E402
 from .optim import FlatSGDMomentum, FlatAdam  # noqa: E402
 from .gemm import gemm_bf16, linear_bf16, conv1x1  # noqa: E402
+from .misc import rope, rope_tables, embedding_bag_mean, normalize_u8, DynamicLossScaler  # noqa: E402
 
 __all__ = [
     "native", "native_available", "launches", "reset_launches",
@@ -66,4 +67,5 @@ __all__ = [
     "soft_cross_entropy", "topk_accuracy",
     "max_pool_3x3_s2", "avg_pool_2x2", "global_avg_pool",
     "FlatSGDMomentum", "FlatAdam", "gemm_bf16", "linear_bf16", "conv1x1",
+    "rope", "rope_tables", "embedding_bag_mean", "normalize_u8", "DynamicLossScaler", "set_fused_bn",
 ]

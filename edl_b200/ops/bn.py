@@ -10,7 +10,12 @@ import torch
 import torch.nn as nn
 
 
-_FUSED = True   # SM-resident single-launch BN kernels (bn_fused.cu) when the tensor fits
+# SM-resident single-launch BN kernels (bn_fused.cu).  Measured on B200 (profiles/): one fused launch
+# costs about as much as the two streaming launches it replaces (both are latency- not bandwidth-bound
+# at per-GPU batch 32), so the streaming pair stays the default; EDL_FUSED_BN=1 / set_fused_bn(True) enables it.
+import os as _os
+
+_FUSED = _os.environ.get("EDL_FUSED_BN", "0") == "1"
 
 
 def set_fused_bn(enabled: bool) -> None:

@@ -209,3 +209,43 @@ def test_fused_adam():
         ropt.step()
     for p, q in zip(lin.parameters(), ref.parameters()):
         assert _rel(p, q) < 1e-4
+
+
+def test_rope_fwd_bwd():
+    torch.manual_seed(0)
+    t, h, d = 77, 8, 64
+    cos, sin = ops.rope_tables(t, d, device=DEV)
+    x = torch.randn(t, h, d, device=DEV).bfloat16().requires_grad_(True)
+    y = ops.rope(x, cos, sin)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_(True)
+    yr = ops.misc._rope_ref(xr, cos, sin)
+    yr.backward(dy.float())
+    assert _rel(y, yr) < 1e-2 and _rel(x.grad, xr.grad) < 1e-2
+    # rotation preserves the norm of every (x1_j, x2_j) pair
+    assert abs(y.float().norm().item() - x.float().norm().item()) / x.float().norm().item() < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_embedding_bag(dtype):
+    torch.manual_seed(0)
+    table = torch.randn(5000, 10, device=DEV).to(dtype).requires_grad_(True)
+    ids = torch.randint(0, 5000, (1000, 3), device=DEV)
+    out = ops.embedding_bag_mean(table, ids)
+    g = torch.randn_like(out)
+    out.backward(g)
+    tr = table.detach().float().requires_grad_(True)
+    ref = tr[ids].mean(1)
+    ref.backward(g.float())
+    assert _rel(out, ref) < 1e-2 and _rel(table.grad, tr.grad) < 2e-2
+
+
+def test_normalize_u8():
+    torch.manual_seed(0)
+    x = torch.randint(0, 256, (4, 20, 24, 3), device=DEV, dtype=torch.uint8)
+    flip = torch.tensor([0, 1, 0, 1], device=DEV, dtype=torch.uint8)
+    y = ops.normalize_u8(x, flip=flip)
+    ref = ops.normalize_u8(x.cpu(), flip=flip.cpu())
+    assert y.shape == (4, 3, 20, 24) and y.is_contiguous(memory_format=torch.channels_last)
+    assert _rel(y.cpu(), ref) < 1e-2

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Run ONE op a few times so that `ncu --set full -k regex:<kernel> -s 3 -c 1 python tools/prof_one.py <op> ...`
+captures exactly the kernel of interest.
+
+  wgrad  COUT CIN M      split-K wgrad GEMM (dy[M,COUT]^T @ x[M,CIN]) with fused finalize into a bf16 sink
+  fwd    M K N           1x1-conv forward GEMM with BN-statistics epilogue
+  dgrad  M K N
+  bnbwd  N C H W [fused|stream|regs] [res]
+  bnfwd  N C H W [fused|stream|regs] [res]
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from edl_b200 import ops  # noqa: E402
+from edl_b200.ops.gemm import _wgrad  # noqa: E402
+
+op = sys.argv[1]
+a = sys.argv[2:]
+dev = "cuda"
+torch.manual_seed(0)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def run(fn, iters=6):
+    for _ in range(iters):
+        flush.zero_()
+        fn()
+    torch.cuda.synchronize()
+
+
+if op == "wgrad":
+    cout, cin, m = int(a[0]), int(a[1]), int(a[2])
+    dy = torch.randn(m, cout, device=dev).bfloat16()
+    x = torch.randn(m, cin, device=dev).bfloat16()
+    sink = torch.zeros(cout, cin, device=dev, dtype=torch.bfloat16)
+    run(lambda: _wgrad(dy, x, (cout, cin), sink, None))
+elif op in ("fwd", "dgrad"):
+    m, k, n = int(a[0]), int(a[1]), int(a[2])
+    x = torch.randn(m, k, device=dev).bfloat16()
+    y = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+    if op == "fwd":
+        w = torch.randn(n, k, device=dev).bfloat16()
+        st = torch.zeros(2 * n, device=dev)
+        run(lambda: ops.gemm_bf16(x, w, out=y, col_stats=st))
+    else:
+        w = torch.randn(k, n, device=dev).bfloat16()
+        run(lambda: ops.gemm_bf16(x, w, out=y, b_mn_major=True))
+elif op in ("bnbwd", "bnfwd"):
+    n, c, h, w = [int(v) for v in a[:4]]
+    path = a[4] if len(a) > 4 else "stream"
+    res = len(a) > 5 and a[5] == "res"
+    ops.set_fused_bn(path == "fused")
+    ops.native().bn_set_stream_kernels(path != "regs")
+    x = torch.randn(n, c, h, w, device=dev).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    r = torch.randn_like(x).requires_grad_(True) if res else None
+    g, b = torch.ones(c, device=dev, requires_grad=True), torch.zeros(c, device=dev, requires_grad=True)
+    rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+    dyv = torch.randn_like(x)
+
+    def f():
+        y = ops.batch_norm_act(x, g, b, rm, rv, residual=r, relu=True, training=True)
+        if op == "bnbwd":
+            y.backward(dyv)
+    run(f)
+else:
+    raise SystemExit("unknown op " + op)
