@@ -29,7 +29,7 @@ def test_bn_fwd_bwd(shape, relu, res, path):
     try:
         _bn_fwd_bwd(shape, relu, res)
     finally:
-        ops.set_fused_bn(True)
+        ops.set_fused_bn(False)
         ops.native().bn_set_stream_kernels(True)
 
 
