@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--comm-blocks", type=int, default=32)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--layers", type=int, default=50)
+    ap.add_argument("--teacher", default="resnext101_32x16d", choices=["resnext101_32x16d", "resnext50_32x4d"])
     ap.add_argument("--no-fused-bn", action="store_true", help="A/B: disable the SM-resident fused BN kernels")
     ap.add_argument("--no-stream-bn", action="store_true", help="A/B: disable the cp.async.bulk BN kernels")
     return ap.parse_args()
@@ -112,6 +113,103 @@ def reference_arm(args):
     return 0
 
 
+def distill_main(args, world, rank, dev):
+    """Distill-service mode: ranks [0, N/2) are students, [N/2, N) teachers (ResNeXt101_32x16d); the
+    images go student -> teacher and the logits teacher -> student through NVSwitch peer memory."""
+    import torch
+    import torch.distributed as dist
+
+    import edl_b200.ops as ops
+    from edl_b200.distill.device_feed import DeviceDistillLink, pool_bytes_needed
+    from edl_b200.distill.device_trainer import DistillStudentTrainer, TeacherWorker, split_roles
+    from edl_b200.models import ResNetVd, to_train_dtype
+    from edl_b200.models.resnext import ResNeXt101_32x16d, ResNeXt50_32x4d, to_inference_dtype
+    from edl_b200.parallel.symm import SymmetricPool
+
+    B = args.batch_per_gpu
+    n_students, students, teachers = split_roles(world)
+    sgroup = dist.new_group(ranks=students)
+    dist.new_group(ranks=teachers)
+    pool = SymmetricPool(pool_bytes_needed(B, slots=1) + (8 << 20), device=dev)
+    is_student = rank < n_students
+    peer = rank + n_students if is_student else rank - n_students
+    link = DeviceDistillLink(pool, peer, "student" if is_student else "teacher", B, slots=1, timeout_s=120.0)
+    total_steps = max(args.warmup, 3) + args.steps * (1 if args.no_e2e else 2)
+    if is_student:
+        model = to_train_dtype(ResNetVd(args.layers, impl=args.conv_impl), torch.bfloat16, dev).train()
+        trainer = DistillStudentTrainer(model, B, link, lr=0.1 * B * n_students / 256.0, use_graph=not args.no_graph,
+                                        group=sgroup if n_students > 1 else None, bucket_cap_mb=args.bucket_mb,
+                                        comm_blocks=args.comm_blocks, algo=args.algo)
+    else:
+        tm = ResNeXt50_32x4d() if args.teacher == "resnext50_32x4d" else ResNeXt101_32x16d()
+        worker = TeacherWorker(to_inference_dtype(tm, torch.bfloat16, dev), link, use_graph=not args.no_graph)
+    pool_n = 4
+    host_x = [torch.randn(B, 3, 224, 224).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).pin_memory()
+              for _ in range(pool_n)] if is_student else None
+
+    def sync_all():
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def run(n, e2e):
+        last = 0.0
+        for i in range(n):
+            if is_student:
+                if e2e:
+                    last = float(trainer.step(host_x[i % pool_n]).item())
+                else:
+                    trainer.step_device()
+            else:
+                worker.step()
+        return last
+
+    run(max(args.warmup, 3), True)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    sampler.start()
+    ops.reset_launches()
+    ev0.record()
+    run(args.steps, False)
+    ev1.record()
+    sync_all()
+    launches = ops.launches()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    e2e = None
+    if not args.no_e2e:
+        sync_all()
+        t0 = time.perf_counter()
+        last = run(args.steps, True)
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        e2e = {"value": B * n_students * args.steps / (e2e_ms / 1e3), "unit": "img/s", "ms_per_step": e2e_ms / args.steps,
+               "h2d_bytes_per_step": B * 3 * 224 * 224 * 2, "d2h_bytes_per_step": 4, "last_loss": last,
+               "timing": "host wall clock around K public-API steps (student: pinned H2D images + loss.item())"}
+    clocks = sampler.stop()
+    err = link.check_error()
+    value = B * n_students * args.steps / (dev_ms / 1e3)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "ResNet50_vd student img/s with same-box distill service (teacher logits over NVSwitch)",
+            "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": value / 1514.0, "dtype": "bf16",
+            "data": "synthetic images, random-init student and teacher", "impl": "edl",
+            "config": {"model": "ResNet%d_vd student + %s teacher" % (args.layers, args.teacher),
+                       "students": n_students, "teachers": n_students, "batch_per_gpu": B,
+                       "global_batch": B * n_students, "transport": "peer_ship / logit_ship over NVSwitch peer memory",
+                       "parallelism": "dp%d + %d teacher GPUs" % (n_students, n_students),
+                       "baseline_note": "vs_baseline divides by the published 1514 img/s (8xV100 + 40xP4, BASELINE.md P3)"},
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "link_error": err}))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -135,6 +233,8 @@ def main():
 
     torch.manual_seed(1234 + rank)
     B = args.batch_per_gpu
+    if args.mode == "distill":
+        return distill_main(args, world, rank, dev)
     if args.impl == "torch":
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
         from baseline.torch_ddp import TorchDDPTrainer

@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""Elastic ResNet training (reference workload: example/collective/resnet50/train_with_fleet.py,
+launched through ``python -m paddle_edl.collective.launch``, train_pretrain.sh:36-61).
+
+Every (re)start: join the stage's process group, reload the newest atomic checkpoint, rescale the
+learning rate to the world size (``lr = base_lr * batch * world / 256`` -- the reference's rule,
+:129-141) and continue from ``train_status.next()``.  Data is synthetic unless ``--data_dir`` points
+at a directory of ``.pt`` shards (uint8 NHWC images + int64 labels).
+
+    python -m paddle_edl.collective.launch --nodes_range 1:8 --nproc_per_node 8 --etcd_endpoints H:P \
+        --job_id rn50 --hdfs_path /ckpt/rn50 examples/collective/resnet50/train.py --epochs 90
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, ROOT)
+
+import edl_b200 as edl  # noqa: E402
+from edl_b200 import ops  # noqa: E402
+from edl_b200.checkpoint import LocalFS, TrainStatus, load_check_point, save_check_point  # noqa: E402
+from edl_b200.models import ResNetVd, to_train_dtype  # noqa: E402
+from edl_b200.ops.optim import cosine_decay_with_warmup, piecewise_decay_with_warmup, scaled_lr  # noqa: E402
+from edl_b200.trainer import StudentTrainer  # noqa: E402
+from edl_b200.utils import train_status as edl_train_status  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layers", type=int, default=50)
+    ap.add_argument("--epochs", type=int, default=90)
+    ap.add_argument("--batch_size", type=int, default=32, help="per trainer")
+    ap.add_argument("--total_batch_size", type=int, default=0, help="if set, per-trainer batch = total / world")
+    ap.add_argument("--lr", type=float, default=0.1)
+    ap.add_argument("--lr_strategy", default="cosine_decay_with_warmup", choices=["cosine_decay_with_warmup", "piecewise_decay"])
+    ap.add_argument("--steps_per_epoch", type=int, default=0, help="0 = total_images / (batch * world)")
+    ap.add_argument("--total_images", type=int, default=1281167)
+    ap.add_argument("--class_dim", type=int, default=1000)
+    ap.add_argument("--image_size", type=int, default=224)
+    ap.add_argument("--label_smoothing", type=float, default=0.0)
+    ap.add_argument("--width_mult", type=float, default=1.0)
+    ap.add_argument("--ckpt", default=os.environ.get("PADDLE_EDL_HDFS_PATH") or "./resnet_ckpt")
+    ap.add_argument("--max_steps", type=int, default=0, help="stop an epoch early (smoke runs)")
+    return ap.parse_args()
+
+
+def main():
+    args = parse()
+    env = edl.init_distributed()
+    world, rank = env.size, env.global_rank
+    cuda = torch.cuda.is_available()
+    dev = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
+    bs = args.batch_size if not args.total_batch_size else max(1, args.total_batch_size // world)
+    torch.manual_seed(0)
+    dtype = torch.bfloat16 if cuda else torch.float32
+    model = to_train_dtype(ResNetVd(args.layers, args.class_dim, width_mult=args.width_mult), dtype, dev).train()
+    base_lr = scaled_lr(args.lr, bs, world)
+    tr = StudentTrainer(model, bs, image_shape=(3, args.image_size, args.image_size), num_classes=args.class_dim,
+                        lr=base_lr, target_kind="labels", use_graph=cuda, dtype=dtype,
+                        loss_fn=lambda z, t: ops.soft_cross_entropy(z, t, "labels", label_smoothing=args.label_smoothing))
+    fs = LocalFS()
+    tensors, ts, _ = load_check_point(args.ckpt, fs, trainer_id=rank, map_location=dev)
+    if tensors is not None:
+        tr.load_state_dict(tensors)
+    steps_per_epoch = args.steps_per_epoch or max(1, args.total_images // (bs * world))
+    step = ts.global_step
+    etcd = None
+    if env.etcd_endpoints:
+        from edl_b200.discovery.etcd_client import EtcdClient
+        etcd = EtcdClient(env.etcd_endpoints, root=env.job_id)
+        etcd.init()
+    for epoch in range(ts.next(), args.epochs):
+        g = torch.Generator().manual_seed(epoch * 1000 + rank)       # pass_id as seed: reproducible after resume
+        t0, seen = time.time(), 0
+        n_steps = steps_per_epoch if not args.max_steps else min(steps_per_epoch, args.max_steps)
+        for it in range(n_steps):
+            lr = (cosine_decay_with_warmup(step, base_lr, steps_per_epoch, args.epochs) if args.lr_strategy.startswith("cosine")
+                  else piecewise_decay_with_warmup(step, base_lr, steps_per_epoch, [30, 60, 80]))
+            tr.set_lr(lr)
+            x = torch.randn(bs, 3, args.image_size, args.image_size, generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
+            y = torch.randint(0, args.class_dim, (bs,), generator=g)
+            loss = tr.step(x.pin_memory() if cuda else x, y.pin_memory() if cuda else y)
+            step += 1
+            seen += bs
+            if it % 10 == 0 and rank == 0:
+                print("Pass %d trainbatch %d loss %.4f lr %.5f speed %.1f img/s" % (
+                    epoch, it, float(loss), lr, seen * world / max(1e-6, time.time() - t0)), flush=True)
+        if etcd is not None and epoch >= args.epochs - 2 and env.pod_id:
+            edl_train_status.save_to_etcd(etcd, env.pod_id, edl_train_status.TrainStatus.NEARTHEEND)   # no more scale-out
+        if rank == 0:
+            save_check_point(args.ckpt, tr.state_dict(), TrainStatus(epoch, step), fs, trainer_id=0,
+                             state_json=json.dumps({"world": world, "lr": lr}))
+        if world > 1:
+            dist.barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
