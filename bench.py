@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--comm-blocks", type=int, default=32)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--layers", type=int, default=50)
+    ap.add_argument("--kineto", type=str, default="", help="write a torch.profiler per-kernel table of 5 replayed steps here")
     ap.add_argument("--teacher", default="resnext101_32x16d", choices=["resnext101_32x16d", "resnext50_32x4d"])
     ap.add_argument("--no-fused-bn", action="store_true", help="A/B: disable the SM-resident fused BN kernels")
     ap.add_argument("--no-stream-bn", action="store_true", help="A/B: disable the cp.async.bulk BN kernels")
@@ -295,6 +296,18 @@ def main():
     sync_all()
     launches = ops.launches()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+
+    if args.kineto and rank == 0:
+        # per-kernel device times inside the REAL pipelined execution (graph replays, warm caches) --
+        # complements ncu, whose serialised cold-cache timings overstate small kernels
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(5):
+                trainer.step_device()
+            torch.cuda.synchronize(dev)
+        with open(args.kineto, "w") as fh:
+            fh.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
 
     # ---- end-to-end region: public API, H2D every step, D2H loss every step ----
     e2e = None
