@@ -412,6 +412,7 @@ void register_gemm_bindings(pybind11::module_& m);  // gemm_bindings.cpp
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "edl_b200 sm_100a kernels";
   m.def("bn_set_stream_kernels", &edl::bn_set_stream_kernels);
+  m.def("set_smem_carveout_policy", &edl::set_smem_carveout_policy);
   m.def("bn_fused_fits", &bn_fused_fits);
   m.def("bn_fwd_fused", &bn_fwd_fused);
   m.def("bn_bwd_fused", &bn_bwd_fused);

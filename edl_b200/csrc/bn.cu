@@ -409,6 +409,17 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
 #define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 #define BFW(p) reinterpret_cast<__nv_bfloat16*>(p)
 
+static bool g_prefer_max_shared = false;
+void set_smem_carveout_policy(bool prefer_max_shared) {
+  g_prefer_max_shared = prefer_max_shared;
+  cudaDeviceSetCacheConfig(prefer_max_shared ? cudaFuncCachePreferShared : cudaFuncCachePreferNone);
+}
+bool smem_carveout_policy() { return g_prefer_max_shared; }
+void apply_carveout(const void* kernel) {
+  if (g_prefer_max_shared)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 static bool g_use_stream = true;
 void bn_set_stream_kernels(bool enabled) { g_use_stream = enabled; }
 

@@ -354,6 +354,7 @@ const char* launch_coop(K kern, int grid, size_t smem, cudaStream_t stream, Args
   if (!found) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return cudaGetErrorString(e);
+    apply_carveout((const void*)kern);
     if (n < 16) done[n++] = (const void*)kern;
   }
   cudaLaunchConfig_t cfg{};

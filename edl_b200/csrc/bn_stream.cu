@@ -390,6 +390,7 @@ inline void set_smem(K kern, size_t bytes) {
   for (int i = 0; i < n; ++i)
     if (done[i] == (const void*)kern) return;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  apply_carveout((const void*)kern);
   if (n < 32) done[n++] = (const void*)kern;
 }
 

@@ -20,6 +20,7 @@
 #include <mutex>
 
 #include "gemm.h"
+#include "kernels.h"
 #include "ptx.cuh"
 
 namespace edl {
@@ -422,6 +423,7 @@ const char* launch_variant(const GemmArgs& g, cudaStream_t stream) {
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return cudaGetErrorString(e);
+    apply_carveout((const void*)kern);
     attr_set = true;
   }
   GemmParams p;

@@ -51,6 +51,12 @@ const char* bn_bwd_fused(const void* dy, const void* x, const void* y, const flo
                          int C, bool relu, bool accumulate, unsigned int* sync_counter,
                          cudaStream_t s);  // runtime switch (A/B measurements); default on
 
+// ---- runtime policy (bn.cu): keep every SM in the max-shared-memory carveout so that kernels with
+// large dynamic smem (TMA rings, GEMM stages) never force an L1/smem re-partition between launches ----
+void set_smem_carveout_policy(bool prefer_max_shared);
+bool smem_carveout_policy();
+void apply_carveout(const void* kernel);   // call after cudaFuncSetAttribute(MaxDynamicSharedMemorySize)
+
 // ---- optim.cu ----
 void sgd_momentum(void* param_lp, float* master, float* mom, const void* grad, bool grad_is_bf16,
                   const float* wd_mask, int64_t n, const float* lr, const float* grad_scale,

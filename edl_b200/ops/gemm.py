@@ -86,6 +86,21 @@ def _split_k_for(m, n, k):
 
 
 _WS = {}
+_SIDE = {"stream": None, "keep": []}
+
+
+def set_wgrad_stream(stream):
+    """Run weight-gradient GEMMs on ``stream`` (the DP engine passes its communication stream): they
+    then overlap the dgrad / BN-backward chain of the main stream, and the bucket all-reduces that
+    follow on the same stream are naturally ordered behind them.  ``None`` disables the overlap."""
+    _SIDE["stream"] = stream
+    _SIDE["keep"].clear()
+
+
+def release_wgrad_keepalive():
+    """Drop the references that kept side-stream operands alive (call after the streams were joined)."""
+    _SIDE["keep"].clear()
+
 
 
 def _splitk_workspace(device, numel, tiles):
@@ -106,6 +121,19 @@ def _wgrad(dy2, x2, weight_shape, sink, ready):
     kernels around it."""
     cout, cin = dy2.shape[1], x2.shape[1]
     split = _split_k_for(cout, cin, dy2.shape[0])
+    side = _SIDE["stream"] if (dy2.is_cuda and sink is not None) else None
+    if side is not None:
+        cur = torch.cuda.current_stream(dy2.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        side.wait_event(ev)
+        _SIDE["keep"].append((dy2, x2))          # operands must outlive the side-stream kernel
+        with torch.cuda.stream(side):
+            return _wgrad_impl(dy2, x2, weight_shape, sink, ready, cout, cin, split)
+    return _wgrad_impl(dy2, x2, weight_shape, sink, ready, cout, cin, split)
+
+
+def _wgrad_impl(dy2, x2, weight_shape, sink, ready, cout, cin, split):
     if dy2.is_cuda and cin % 4 == 0:
         tiles = ((cout + 127) // 128) * ((cin + 63) // 64)
         ws, counters = _splitk_workspace(dy2.device, cout * cin, tiles)

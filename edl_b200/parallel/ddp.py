@@ -105,6 +105,7 @@ class ElasticDataParallel:
                 self.found_inf = torch.zeros(1, dtype=torch.int32, device=self.device)
             if track_sqnorm:
                 self.sqnorm = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.overlap_wgrad = os.environ.get("EDL_OVERLAP_WGRAD", "1") == "1"
         self._bind_group(group)
         self.flat = FlatParams(module, grad_alloc=self._grad_alloc if self.pool is not None else None)
         self._plan()
@@ -230,9 +231,11 @@ class ElasticDataParallel:
         for b in self.buckets:
             b.pending = 0
         self._launch_ready()
-        if self.device.type == "cuda" and self.world > 1:
-            if self.use_symm:
+        if self.device.type == "cuda" and (self.world > 1 or self.overlap_wgrad):
+            if self.use_symm or self.overlap_wgrad:
                 torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+                from ..ops import gemm as _gemm
+                _gemm.release_wgrad_keepalive()
             for w, view, scale in self._works:
                 w.wait()
                 if self.average:
@@ -244,6 +247,21 @@ class ElasticDataParallel:
         return self.module(*a, **kw)
 
     def zero_grad(self):
+        if self.device.type == "cuda":
+            from ..ops import gemm as _gemm
+            # the zeroing memsets run on the main stream: the side stream must not start writing
+            # gradients before them
+            self.flat.zero_grad()
+            if self.overlap_wgrad:
+                self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+                _gemm.set_wgrad_stream(self.comm_stream)
+            else:
+                _gemm.set_wgrad_stream(None)
+            if self.found_inf is not None:
+                self.found_inf.zero_()
+            if self.sqnorm is not None:
+                self.sqnorm.zero_()
+            return
         self.flat.zero_grad()
         if self.found_inf is not None:
             self.found_inf.zero_()
