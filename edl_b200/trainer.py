@@ -140,6 +140,31 @@ class StudentTrainer:
     def set_lr(self, lr: float):
         self.opt.set_lr(lr)
 
+    @torch.no_grad()
+    def evaluate(self, batches):
+        """Per-rank evaluation + all-reduce of the counters (the reference evaluates on trainer 0 with a
+        single-process multi-GPU ``CompiledProgram.with_data_parallel``,
+        example/distill/resnet/train_with_fleet.py:403-404,537-575).  ``batches`` yields (images, int64
+        labels); returns {"acc1", "acc5", "n"} over all ranks."""
+        was_training = self.model.training
+        self.model.eval()
+        counts = torch.zeros(3, device=self.device, dtype=torch.float32)
+        for images, labels in batches:
+            x = images.to(self.device, non_blocking=True)
+            if x.dtype != self.dtype:
+                x = x.to(self.dtype)
+            if x.dim() == 4:
+                x = x.contiguous(memory_format=torch.channels_last)
+            labels = labels.to(self.device, non_blocking=True).view(-1)
+            hits = ops.topk_accuracy(self.model(x), labels)
+            counts[:2] += hits.to(counts.device)
+            counts[2] += labels.numel()
+        if self.dp.world > 1:
+            dist.all_reduce(counts, group=self.dp.group)
+        self.model.train(was_training)
+        n = max(1.0, float(counts[2]))
+        return {"acc1": float(counts[0]) / n, "acc5": float(counts[1]) / n, "n": int(counts[2])}
+
     # ------------------------------------------------------------------ elastic
     def rebuild(self, group):
         """World-size change: re-plan the communication, drop the captured graph."""
