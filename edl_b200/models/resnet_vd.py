@@ -121,8 +121,13 @@ _DEPTHS = {18: [2, 2, 2, 2], 34: [3, 4, 6, 3], 50: [3, 4, 6, 3], 101: [3, 4, 23,
 
 
 class ResNetVd(nn.Module):
-    def __init__(self, layers=50, class_dim=1000, impl="auto", width_mult=1.0):
+    def __init__(self, layers=50, class_dim=1000, impl="auto", width_mult=1.0, recompute=False):
         super().__init__()
+        # recompute: drop every residual block's inner activations after forward and re-run the block
+        # during backward (reference: dist_strategy.forward_recompute + model.checkpoints = the block
+        # outputs, example/distill/resnet/train_with_fleet.py:328-331).  Trades ~1/3 more compute for
+        # ~3x less activation memory; off on the benchmark path (180 GB of HBM3e do not need it).
+        self.recompute = recompute
         assert layers in _DEPTHS, "supported layers are %s" % sorted(_DEPTHS)
         depth = _DEPTHS[layers]
         bottleneck = layers >= 50
@@ -161,7 +166,12 @@ class ResNetVd(nn.Module):
     def forward(self, x):
         x = self.stem(x)
         x = ops.max_pool_3x3_s2(x)
-        x = self.blocks(x)
+        if self.recompute and self.training and torch.is_grad_enabled():
+            from torch.utils.checkpoint import checkpoint
+            for blk in self.blocks:
+                x = checkpoint(blk, x, use_reentrant=False)
+        else:
+            x = self.blocks(x)
         x = ops.global_avg_pool(x)
         if x.is_cuda and x.dtype == torch.bfloat16 and self.impl != "cudnn":
             return ops.linear_bf16(x, self.fc_weight, self.fc_bias)

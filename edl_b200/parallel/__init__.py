@@ -2,5 +2,6 @@
 planning / overlap, elastic re-planning."""
 from .flat import FlatParams
 from .ddp import ElasticDataParallel, plan_buckets, choose_algo
+from .dgc import DGCMomentum
 
-__all__ = ["FlatParams", "ElasticDataParallel", "plan_buckets", "choose_algo"]
+__all__ = ["FlatParams", "ElasticDataParallel", "plan_buckets", "choose_algo", "DGCMomentum"]

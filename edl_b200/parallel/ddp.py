@@ -100,12 +100,12 @@ class ElasticDataParallel:
         self.slices = {}
         self.found_inf = None
         self.sqnorm = None
-        if self.device.type == "cuda":
-            if check_finite:
-                self.found_inf = torch.zeros(1, dtype=torch.int32, device=self.device)
-            if track_sqnorm:
-                self.sqnorm = torch.zeros(1, dtype=torch.float32, device=self.device)
+        if check_finite:
+            self.found_inf = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if track_sqnorm and self.device.type == "cuda":
+            self.sqnorm = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.overlap_wgrad = os.environ.get("EDL_OVERLAP_WGRAD", "1") == "1"
+        self.enabled = True     # False: gradients stay local (DGC exchanges them itself)
         self._bind_group(group)
         self.flat = FlatParams(module, grad_alloc=self._grad_alloc if self.pool is not None else None)
         self._plan()
@@ -192,7 +192,7 @@ class ElasticDataParallel:
             self._next += 1
 
     def _launch(self, b: Bucket):
-        if b.launched or self.world <= 1:
+        if b.launched or self.world <= 1 or not self.enabled:
             b.launched = True
             return
         b.launched = True
@@ -240,6 +240,13 @@ class ElasticDataParallel:
                 w.wait()
                 if self.average:
                     view.mul_(scale)
+        if self.found_inf is not None and not (self.use_symm and self.world > 1):
+            # the fused all-reduce epilogue raises the flag itself; without it (one rank, NCCL / gloo
+            # path) the gradients are scanned here.  Summed gradients carry every rank's inf/nan, so
+            # all ranks agree without another collective.
+            for g in self.flat.groups.values():
+                bad = (~torch.isfinite(g.grad).all()).to(torch.int32).view(1)
+                self.found_inf.copy_(torch.maximum(self.found_inf, bad))
         self._reset_pending()
 
     # ------------------------------------------------------------------ user-facing

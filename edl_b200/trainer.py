@@ -54,7 +54,8 @@ class StudentTrainer:
                  group: Optional[dist.ProcessGroup] = None, use_graph: bool = True,
                  bucket_cap_mb: float = 16.0, comm_blocks: int = 32, algo: str = "auto",
                  overlap: bool = True, dtype=torch.bfloat16, input_dtype=None,
-                 loss_fn: Optional[Callable] = None):
+                 loss_fn: Optional[Callable] = None, loss_scaling: Optional[float] = None,
+                 dynamic_loss_scaling: bool = True, optimizer: Optional[Callable] = None):
         self.model = model
         self.device = next(model.parameters()).device
         self.cuda = self.device.type == "cuda"
@@ -63,10 +64,27 @@ class StudentTrainer:
         self.target_kind = target_kind
         self.loss_fn = loss_fn
         self.dp = ElasticDataParallel(model, group=group, bucket_cap_mb=bucket_cap_mb,
-                                      comm_blocks=comm_blocks, algo=algo, overlap=overlap)
-        self.opt = ops.FlatSGDMomentum(self.dp.flat, lr=lr, momentum=momentum,
-                                       weight_decay=weight_decay)
-        self.arena = StepArena(model, self.device) if self.cuda else None
+                                      comm_blocks=comm_blocks, algo=algo, overlap=overlap,
+                                      check_finite=loss_scaling is not None)
+        if optimizer is not None:
+            self.opt = optimizer(self.dp.flat)
+        else:
+            self.opt = ops.FlatSGDMomentum(self.dp.flat, lr=lr, momentum=momentum,
+                                           weight_decay=weight_decay)
+        # fp16-style loss scaling (reference: mixed_precision.decorate(init_loss_scaling,
+        # use_dynamic_loss_scaling), example/distill/resnet/train_with_fleet.py:324-327); bf16 runs
+        # leave it off
+        self.scaler = None
+        if loss_scaling is not None:
+            self.scaler = ops.DynamicLossScaler(
+                self.device, init_scale=loss_scaling,
+                growth_interval=1000 if dynamic_loss_scaling else (1 << 30),
+                backoff_factor=0.5 if dynamic_loss_scaling else 1.0)
+            self.scaler.found_inf = self.dp.found_inf
+            self.scaler.attach(self.opt, self.dp)
+        # recompute runs every block's forward twice: the pre-zeroed accumulate-into arena slices would
+        # be summed twice, so those runs let each op allocate its own scratch
+        self.arena = StepArena(model, self.device) if self.cuda and not getattr(model, "recompute", False) else None
         in_dtype = input_dtype if input_dtype is not None else dtype
         self.static_x = torch.zeros((batch_size,) + tuple(image_shape), dtype=in_dtype,
                                     device=self.device).contiguous(memory_format=torch.channels_last)
@@ -92,9 +110,11 @@ class StudentTrainer:
             loss = self.loss_fn(logits, self.static_t)
         else:
             loss = ops.soft_cross_entropy(logits, self.static_t, target_kind=self.target_kind)
-        loss.backward()
+        (self.scaler.scale_loss(loss) if self.scaler is not None else loss).backward()
         self.dp.finish()
         self.opt.step()
+        if self.scaler is not None:
+            self.scaler.update()
         self.static_loss.copy_(loss.detach())
 
     def capture(self, warmup: int = 3):

@@ -134,3 +134,64 @@ def test_trainer_cpu_step_eval_and_state_roundtrip():
     assert tr2.opt.lr == tr.opt.lr
     a, b = float(tr.step(x, y)), float(tr2.step(x, y))
     assert abs(a - b) < 1e-4      # identical params + momentum => identical next step
+
+
+def test_recompute_matches_plain_backward():
+    from edl_b200.models import to_train_dtype
+
+    torch.manual_seed(1)
+    a = to_train_dtype(ResNetVd(18, class_dim=6, width_mult=0.125), torch.float32)
+    b = to_train_dtype(ResNetVd(18, class_dim=6, width_mult=0.125, recompute=True), torch.float32)
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(3, 3, 32, 32)
+    for m in (a, b):
+        m.train()
+        m(x).square().mean().backward()
+    for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.allclose(p.grad, q.grad, atol=1e-5, rtol=1e-4), n
+
+
+def test_loss_scaling_skips_overflow_and_matches_unscaled():
+    from edl_b200.models import to_train_dtype
+    from edl_b200.trainer import StudentTrainer
+
+    def make(scale):
+        torch.manual_seed(3)
+        m = to_train_dtype(ResNetVd(18, class_dim=8, width_mult=0.125), torch.float32)
+        return StudentTrainer(m, 4, image_shape=(3, 32, 32), num_classes=8, lr=0.05, target_kind="labels",
+                              dtype=torch.float32, loss_scaling=scale)
+
+    x = torch.randn(4, 3, 32, 32).contiguous(memory_format=torch.channels_last)
+    y = torch.tensor([0, 1, 2, 3])
+    plain, scaled = make(None), make(1024.0)
+    for _ in range(3):
+        a, b = float(plain.step(x, y)), float(scaled.step(x, y))
+        assert abs(a - b) < 1e-3 * max(1.0, abs(a))
+    # poison one step: the update must be skipped and the scale halved
+    before = [p.detach().clone() for p in scaled.model.parameters()]
+    bad = x.clone()
+    bad[0, 0, 0, 0] = float("inf")
+    scaled.step(bad, y)
+    for p, q in zip(scaled.model.parameters(), before):
+        assert torch.equal(p, q)
+    assert float(scaled.scaler.scale) == 512.0
+
+
+def test_dgc_world1_sparse_steps_reduce_loss():
+    from edl_b200.models import to_train_dtype
+    from edl_b200.parallel import DGCMomentum
+    from edl_b200.trainer import StudentTrainer
+
+    torch.manual_seed(5)
+    m = to_train_dtype(ResNetVd(18, class_dim=8, width_mult=0.125), torch.float32)
+    tr = StudentTrainer(m, 4, image_shape=(3, 32, 32), num_classes=8, target_kind="labels", dtype=torch.float32,
+                        optimizer=lambda flat: DGCMomentum(flat, lr=0.05, momentum=0.9, weight_decay=0.0,
+                                                           rampup_begin_step=2, rampup_step=4,
+                                                           sparsity=(0.5, 0.9)))
+    x = torch.randn(4, 3, 32, 32).contiguous(memory_format=torch.channels_last)
+    y = torch.tensor([0, 1, 2, 3])
+    losses = [float(tr.step(x, y)) for _ in range(25)]
+    assert losses[-1] < losses[0]
+    assert tr.opt.t == 25 and tr.opt.current_sparsity() == 0.9
+    numel = sum(g.numel for g in tr.dp.flat.groups.values())
+    assert tr.opt.sent_elems < 23 * numel * 0.6      # compressed steps shipped a fraction of the gradient
