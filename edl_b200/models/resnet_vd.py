@@ -185,7 +185,7 @@ def to_train_dtype(model: nn.Module, dtype=torch.bfloat16, device=None):
     """Cast conv/fc weights to ``dtype`` while BN parameters, biases and running stats stay fp32."""
     for m in model.modules():
         for name, p in list(m.named_parameters(recurse=False)):
-            keep_fp32 = isinstance(m, BatchNormAct2d) or name.endswith("bias")
+            keep_fp32 = isinstance(m, BatchNormAct2d) or (name.endswith("bias") and not isinstance(m, nn.Conv2d))
             p.data = p.data.to(device=device, dtype=torch.float32 if keep_fp32 else dtype)
         for name, b in list(m.named_buffers(recurse=False)):
             m._buffers[name] = b.to(device=device)

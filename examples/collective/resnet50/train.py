@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 import edl_b200 as edl  # noqa: E402
 from edl_b200 import ops  # noqa: E402
 from edl_b200.checkpoint import LocalFS, TrainStatus, load_check_point, save_check_point  # noqa: E402
-from edl_b200.models import ResNetVd, to_train_dtype  # noqa: E402
+from edl_b200.models import VGG, ResNet, ResNetVd, to_train_dtype  # noqa: E402
 from edl_b200.ops.optim import cosine_decay_with_warmup, piecewise_decay_with_warmup, scaled_lr  # noqa: E402
 from edl_b200.trainer import StudentTrainer  # noqa: E402
 from edl_b200.utils import train_status as edl_train_status  # noqa: E402
@@ -33,7 +33,8 @@ from edl_b200.utils import train_status as edl_train_status  # noqa: E402
 
 def parse():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--layers", type=int, default=50)
+    ap.add_argument("--model", default="ResNet50_vd", help="ResNet{18,34,50,101,152}[_vd] or VGG{11,13,16,19}")
+    ap.add_argument("--layers", type=int, default=0, help="deprecated: overrides the depth in --model")
     ap.add_argument("--epochs", type=int, default=90)
     ap.add_argument("--batch_size", type=int, default=32, help="per trainer")
     ap.add_argument("--total_batch_size", type=int, default=0, help="if set, per-trainer batch = total / world")
@@ -59,7 +60,14 @@ def main():
     bs = args.batch_size if not args.total_batch_size else max(1, args.total_batch_size // world)
     torch.manual_seed(0)
     dtype = torch.bfloat16 if cuda else torch.float32
-    model = to_train_dtype(ResNetVd(args.layers, args.class_dim, width_mult=args.width_mult), dtype, dev).train()
+    depth = args.layers or int("".join(ch for ch in args.model.split("_")[0] if ch.isdigit()))
+    if args.model.upper().startswith("VGG"):
+        net = VGG(depth, args.class_dim, width_mult=args.width_mult, image_size=args.image_size)
+    elif args.model.endswith("_vd"):
+        net = ResNetVd(depth, args.class_dim, width_mult=args.width_mult)
+    else:
+        net = ResNet(depth, args.class_dim, width_mult=args.width_mult)
+    model = to_train_dtype(net, dtype, dev).train()
     base_lr = scaled_lr(args.lr, bs, world)
     tr = StudentTrainer(model, bs, image_shape=(3, args.image_size, args.image_size), num_classes=args.class_dim,
                         lr=base_lr, target_kind="labels", use_graph=cuda, dtype=dtype,

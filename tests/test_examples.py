@@ -46,3 +46,10 @@ def test_dgc_and_recompute_flags(tmp_path):
                "--class_dim", "10", "--batch_size", "4", "--total_images", "24", "--num_epochs", "1", "--use_dgc", "1",
                "--rampup_begin_step", "2", "--use_recompute", "1", "--fetch_steps", "1", "--checkpoint", str(tmp_path / "ck")])
     assert "Pass 0, batch 5" in out
+
+
+@pytest.mark.parametrize("model", ["ResNet50", "VGG11", "ResNet18_vd"])
+def test_collective_resnet_example_models(tmp_path, model):
+    out = run(["examples/collective/resnet50/train.py", "--model", model, "--width_mult", "0.125", "--image_size", "32",
+               "--class_dim", "10", "--batch_size", "4", "--epochs", "1", "--steps_per_epoch", "3", "--ckpt", str(tmp_path / "ck")])
+    assert "Pass 0 trainbatch 0" in out
