@@ -195,3 +195,48 @@ def test_dgc_world1_sparse_steps_reduce_loss():
     assert tr.opt.t == 25 and tr.opt.current_sparsity() == 0.9
     numel = sum(g.numel for g in tr.dp.flat.groups.values())
     assert tr.opt.sent_elems < 23 * numel * 0.6      # compressed steps shipped a fraction of the gradient
+
+
+def _dgc_worker(rank, world, port, q):
+    from edl_b200.parallel import DGCMomentum
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    m = ResNetVd(18, class_dim=8, width_mult=0.125)
+    dp = ElasticDataParallel(m, bucket_cap_mb=0.05)
+    opt = DGCMomentum(dp.flat, dp=dp, lr=0.05, weight_decay=0.0, rampup_begin_step=1, rampup_step=2, sparsity=(0.9,))
+    torch.manual_seed(100)
+    xs = torch.randn(4, 3, 32, 32)
+    ts = torch.softmax(torch.randn(4, 8), -1)
+    x, t = xs[rank * 2:(rank + 1) * 2], ts[rank * 2:(rank + 1) * 2]
+    enabled = []
+    for _ in range(4):
+        dp.zero_grad()
+        loss = ops.soft_cross_entropy(dp(x.contiguous(memory_format=torch.channels_last)), t)
+        loss.backward()
+        enabled.append(dp.enabled)
+        dp.finish()
+        opt.step()
+    flat = torch.cat([g.param.flatten() for g in dp.flat.groups.values()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    if rank == 0:
+        q.put((float((gathered[0] - gathered[1]).abs().max()), enabled))
+    dist.destroy_process_group()
+
+
+def test_dgc_gloo_ranks_stay_in_sync_with_sparse_exchange():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dgc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    diff, enabled = q.get(timeout=5)
+    assert diff < 1e-6                         # sparse all-gather applies the same update everywhere
+    assert enabled == [True, False, False, False]   # dense all-reduce only during the ramp-up step
