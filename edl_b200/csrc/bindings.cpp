@@ -380,14 +380,14 @@ void logit_ship(const Tensor& logits, int64_t slot_peer, int64_t stats_peer, dou
                   opt_ptr<void>(seq), (uint32_t)seq_imm, done.data_ptr(), cur_stream());
 }
 
-void soft_ce_recv(const Tensor& logits, const Tensor& slot, const Tensor& slot_stats, const Tensor& flag,
+void soft_ce_recv(const Tensor& logits, const Tensor& slot, const c10::optional<Tensor>& slot_stats, const Tensor& flag,
                   const c10::optional<Tensor>& seq, int64_t seq_imm, Tensor& loss_out, Tensor& row_stats,
                   double s_temp, double t_temp, bool kl, double loss_scale, double timeout_s,
                   const c10::optional<Tensor>& err) {
   TORCH_CHECK(logits.is_cuda() && logits.is_contiguous() && logits.dim() == 2);
   c10::cuda::CUDAGuard g(logits.device());
   edl::soft_ce_recv(logits.data_ptr(), logits.scalar_type() == at::kBFloat16, slot.data_ptr(),
-                    slot_stats.data_ptr<float>(), flag.data_ptr(), opt_ptr<void>(seq), (uint32_t)seq_imm,
+                    opt_ptr<float>(slot_stats), flag.data_ptr(), opt_ptr<void>(seq), (uint32_t)seq_imm,
                     loss_out.data_ptr<float>(), row_stats.data_ptr<float>(), logits.size(0), logits.size(1),
                     (float)s_temp, (float)t_temp, kl, (float)loss_scale, timeout_s, opt_ptr<void>(err),
                     cur_stream());

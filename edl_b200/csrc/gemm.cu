@@ -46,6 +46,11 @@ struct GemmParams {
   long long ldo;
   int* tile_counters;
   int accumulate;
+  // GEMM -> peer ship (see gemm.h)
+  uint32_t* ship_flag;
+  const uint32_t* ship_seq_ptr;
+  uint32_t ship_seq_imm;
+  unsigned int* ship_done;
 };
 
 template <int BLOCK_N, int STAGES>
@@ -232,7 +237,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             atomicAdd(&p.col_stats[p.N + n0 + col], sq);
           }
         }
-        if (et == 0) ptx::tma_store_wait_read0();
+        if (et == 0) {
+          if (p.ship_flag == nullptr) {
+            ptx::tma_store_wait_read0();
+          } else {
+            // the tile went to a peer GPU: wait until the bulk store has fully completed (not just
+            // read its smem source), order it system-wide, count this CTA in; the last one raises
+            // the consumer's flag.
+            ptx::tma_store_wait0();
+            __threadfence_system();
+            const unsigned int prev = atomicAdd(p.ship_done, 1u);
+            if (prev == gridDim.x - 1) {
+              *p.ship_done = 0u;
+              __threadfence_system();
+              const uint32_t seq = p.ship_seq_ptr != nullptr ? *p.ship_seq_ptr : p.ship_seq_imm;
+              asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.ship_flag), "r"(seq) : "memory");
+            }
+          }
+        }
       } else {
         // split-K: stage the fp32 partial tile in smem (the pipeline stages are drained), then push
         // it to the fp32 workspace with COALESCED vector reductions: consecutive threads cover
@@ -442,6 +464,10 @@ const char* launch_variant(const GemmArgs& g, cudaStream_t stream) {
   p.ldo = g.ldo;
   p.tile_counters = g.tile_counters;
   p.accumulate = g.accumulate_out ? 1 : 0;
+  p.ship_flag = EPI == 0 ? reinterpret_cast<uint32_t*>(g.ship_flag) : nullptr;
+  p.ship_seq_ptr = reinterpret_cast<const uint32_t*>(g.ship_seq_ptr);
+  p.ship_seq_imm = g.ship_seq_imm;
+  p.ship_done = reinterpret_cast<unsigned int*>(g.ship_done);
   const int tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M;
   const int tiles_n = (g.N + BLOCK_N - 1) / BLOCK_N;
   dim3 grid(tiles_m * tiles_n, 1, split);

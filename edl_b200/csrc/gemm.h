@@ -27,6 +27,13 @@ struct GemmArgs {
   int* tile_counters = nullptr;       // >= ceil(M/128)*ceil(N/BLOCK_N) zero-initialised ints
   bool accumulate_out = false;
   int device = -1;                    // CUDA device ordinal of the operands (binds the context)
+  // fused "GEMM -> peer ship" (EPI 0 only): D may be a PEER GPU's buffer (NVLink-mapped address);
+  // every CTA TMA-stores its tile there, and the CTA that completes last publishes
+  // *ship_flag (peer address) = seq with release/system semantics -- no separate copy kernel.
+  void* ship_flag = nullptr;
+  const void* ship_seq_ptr = nullptr;  // device uint32 (graph-replayable) or nullptr -> ship_seq_imm
+  uint32_t ship_seq_imm = 0;
+  void* ship_done = nullptr;           // local zero-initialised uint32 counter (re-armed by the kernel)
 };
 
 // Returns nullptr on success, else a static error string.

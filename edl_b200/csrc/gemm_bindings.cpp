@@ -70,6 +70,41 @@ void gemm_bf16(const Tensor& A, const Tensor& B, const c10::optional<Tensor>& D,
   const char* err = edl::gemm_bf16(g, at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(err == nullptr, "edl gemm_bf16 failed: ", err);
 }
+
+// Fused "linear -> peer ship": D = A[M,K] * B[N,K]^T (+ bias) TMA-stored straight into a peer GPU's
+// buffer at `d_ptr` (row pitch ldd elements); the last CTA releases `flag_ptr` (peer) = seq.
+void gemm_bf16_ship(const Tensor& A, const Tensor& B, int64_t d_ptr, int64_t ldd,
+                    const c10::optional<Tensor>& col_shift, int64_t flag_ptr,
+                    const c10::optional<Tensor>& seq, int64_t seq_imm, const Tensor& done) {
+  TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.dim() == 2 && B.dim() == 2);
+  TORCH_CHECK(A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1 && A.size(1) == B.size(1));
+  TORCH_CHECK(done.is_cuda() && done.scalar_type() == at::kInt && done.numel() >= 1);
+  edl::GemmArgs g;
+  g.A = A.data_ptr();
+  g.B = B.data_ptr();
+  g.M = A.size(0);
+  g.K = A.size(1);
+  g.N = B.size(0);
+  g.lda = A.stride(0);
+  g.ldb = B.stride(0);
+  g.D = reinterpret_cast<void*>(d_ptr);
+  g.ldd = ldd;
+  TORCH_CHECK(g.lda % 8 == 0 && g.ldb % 8 == 0 && g.ldd % 8 == 0 && d_ptr % 16 == 0,
+              "row pitches / base must be 16-byte aligned");
+  g.col_shift = optp<float>(col_shift);
+  g.ship_flag = reinterpret_cast<void*>(flag_ptr);
+  g.ship_seq_ptr = seq.has_value() && seq->defined() ? seq->data_ptr() : nullptr;
+  g.ship_seq_imm = (uint32_t)seq_imm;
+  g.ship_done = done.data_ptr();
+  g.device = A.device().index();
+  c10::cuda::CUDAGuard guard(A.device());
+  const char* err = edl::gemm_bf16(g, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(err == nullptr, "edl gemm_bf16_ship failed: ", err);
+}
 }  // namespace
 
-void register_gemm_bindings(pybind11::module_& m) { m.def("gemm_bf16", &gemm_bf16); }
+void register_gemm_bindings(pybind11::module_& m) {
+  m.def("gemm_bf16", &gemm_bf16);
+  m.def("gemm_bf16_ship", &gemm_bf16_ship);
+}

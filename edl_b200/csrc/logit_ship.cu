@@ -151,7 +151,19 @@ soft_ce_recv_kernel(const LT* __restrict__ logits, const __nv_bfloat16* __restri
   for (int j = threadIdx.x; j < C; j += kRowThreads) zsum += __expf(ldz(j) - zmax);
   zsum = blk_sum(zsum, sh, kRowThreads / 32);
   const float lse = zmax + __logf(zsum);
-  const float tlse = slot_stats[row * 2 + 1];
+  float tlse;
+  if (slot_stats != nullptr) {
+    tlse = slot_stats[row * 2 + 1];
+  } else {
+    // the slot was filled by the fused GEMM->ship epilogue (raw logits only): reduce the teacher row here
+    float tmax = -INFINITY;
+    for (int j = threadIdx.x; j < C; j += kRowThreads) tmax = fmaxf(tmax, __bfloat162float(t[j]) * inv_tt);
+    tmax = blk_max(tmax, sh, kRowThreads / 32);
+    float tsum = 0.f;
+    for (int j = threadIdx.x; j < C; j += kRowThreads) tsum += __expf(__bfloat162float(t[j]) * inv_tt - tmax);
+    tsum = blk_sum(tsum, sh, kRowThreads / 32);
+    tlse = tmax + __logf(tsum);
+  }
   float pz = 0.f, plogp = 0.f;
   for (int j = threadIdx.x; j < C; j += kRowThreads) {
     const float lt = __bfloat162float(t[j]) * inv_tt - tlse;

@@ -8,8 +8,10 @@ Data path per step ``n`` (ring slot ``n % slots``), no host involvement, no NCCL
   student : ``send_images(x)``     peer_ship: x -> TEACHER's HBM slot, release-flag img_ready = n+1
   teacher : ``wait_images()``      device-side acquire of img_ready, returns the slot view
             forward(...)           (ResNeXt101_32x16d)
-            ``send_logits(z)``     logit_ship: z -> STUDENT's HBM slot + per-row softmax stats,
-                                   release-flag logit_ready = n+1
+            ``ship_linear(f,W,b)`` fused path (default): the classifier GEMM's epilogue TMA-stores its
+                                   logit tiles straight into the STUDENT's HBM slot and the last CTA
+                                   releases logit_ready = n+1 (csrc/gemm.cu, "GEMM -> peer ship")
+            ``send_logits(z)``     unfused path: logit_ship copies z + per-row softmax stats
   student : ``loss(logits)``       soft_ce_recv: acquires logit_ready, fused soft-label CE on the slot;
                                    backward = soft_ce_bwd on the same slot
 
@@ -49,13 +51,16 @@ class _Regions:
 class DeviceDistillLink:
     def __init__(self, pool: SymmetricPool, peer_rank: int, role: str, batch: int, image_shape=(3, 224, 224),
                  num_classes: int = 1000, slots: int = 2, dtype=torch.bfloat16, temperature: float = 1.0,
-                 timeout_s: float = 60.0):
+                 timeout_s: float = 60.0, fused_fc: bool = True):
         assert role in ("student", "teacher")
         self.pool, self.peer, self.role = pool, peer_rank, role
         self.rank = pool.rank
         self.r = _Regions(pool, batch, image_shape, num_classes, slots, dtype)
         self.slots, self.batch, self.num_classes = slots, batch, num_classes
         self.temperature, self.timeout_s = temperature, timeout_s
+        # fused GEMM->ship leaves the row statistics to the receiving loss kernel; both ends of a link
+        # must agree (same constructor arguments on both ranks).  TMA needs a 16-byte row pitch.
+        self.fused_fc = fused_fc and num_classes % 8 == 0
         dev = pool.device
         self.seq = torch.zeros(1, dtype=torch.int32, device=dev)      # device step counter (graph-safe)
         self.done = torch.zeros(4, dtype=torch.int32, device=dev)     # per-kernel block counters
@@ -67,7 +72,9 @@ class DeviceDistillLink:
         from ..ops import native, count_launch
 
         assert self.role == "student"
-        x = x.contiguous(memory_format=torch.channels_last) if x.dim() == 4 else x.contiguous()
+        if x.dim() == 4:      # ship the NHWC bytes; the flat view is what the copy kernel wants
+            x = x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+        x = x.contiguous().view(-1)
         native().peer_ship(x, self.r.img[slot].data_ptrs[self.peer], x.numel() * x.element_size(),
                            self.r.img_flag_ptr(self.peer, slot), seq, seq_imm, self.done[0:1])
         count_launch()
@@ -98,6 +105,19 @@ class DeviceDistillLink:
                             self.r.logit_flag_ptr(self.peer, slot), seq, seq_imm, self.done[1:2])
         count_launch()
 
+    def ship_linear(self, feats: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], slot: int,
+                    seq: Optional[torch.Tensor] = None, seq_imm: int = 0):
+        """logits = feats @ weight.T + bias, written by the GEMM epilogue directly into the student's
+        slot (one kernel: tcgen05 GEMM + NVLink store + flag release)."""
+        from ..ops import native, count_launch
+
+        assert self.role == "teacher" and self.fused_fc
+        feats = feats.contiguous()
+        assert feats.shape[0] == self.batch and weight.shape[0] == self.num_classes
+        native().gemm_bf16_ship(feats, weight, self.r.logit[slot].data_ptrs[self.peer], self.num_classes, bias,
+                                self.r.logit_flag_ptr(self.peer, slot), seq, seq_imm, self.done[2:3])
+        count_launch()
+
     def check_error(self) -> int:
         return int(self.err.item())
 
@@ -112,7 +132,7 @@ class _RecvLossFn(torch.autograd.Function):
         loss = torch.zeros((), device=logits.device, dtype=torch.float32)
         row_stats = torch.empty(n, 4, device=logits.device, dtype=torch.float32)
         slot_t = link.r.logit[slot].tensor.view(n, c)
-        stats_t = link.r.stats[slot].tensor.view(n, 2)
+        stats_t = None if link.fused_fc else link.r.stats[slot].tensor.view(n, 2)
         flag = link.r.flags.tensor[16 + slot:17 + slot]
         native().soft_ce_recv(logits, slot_t, stats_t, flag, seq, seq_imm, loss, row_stats, s_temp,
                               link.temperature, kl, loss_scale, link.timeout_s, link.err)

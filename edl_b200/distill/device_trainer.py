@@ -55,8 +55,13 @@ class TeacherWorker:
     def _body(self):
         self.link.seq.add_(1)
         img = self.link.wait_images(0, seq=self.link.seq)
-        logits = self.model(img if img.dtype == self.dtype else img.to(self.dtype))
-        self.link.send_logits(logits.to(torch.bfloat16), 0, seq=self.link.seq)
+        img = img if img.dtype == self.dtype else img.to(self.dtype)
+        if self.link.fused_fc and hasattr(self.model, "forward_features") and self.dtype == torch.bfloat16:
+            feats = self.model.forward_features(img)
+            self.link.ship_linear(feats, self.model.fc_weight, self.model.fc_bias, 0, seq=self.link.seq)
+        else:
+            assert not self.link.fused_fc, "link was built with fused_fc=True but the model cannot use it"
+            self.link.send_logits(self.model(img).to(torch.bfloat16), 0, seq=self.link.seq)
 
     def capture(self, warmup: int = 3):
         s = torch.cuda.Stream(device=self.device)

@@ -92,11 +92,17 @@ class ResNeXt(nn.Module):
         nn.init.uniform_(self.fc_weight, -1.0 / math.sqrt(cin), 1.0 / math.sqrt(cin))
 
     @torch.no_grad()
-    def forward(self, x, return_logits=True):
+    def forward_features(self, x):
+        """Everything up to the classifier: pooled [N, feat] features (the distill link fuses the FC
+        GEMM with the NVLink ship of its output, distill/device_feed.py:ship_linear)."""
         x = self.stem(x)
         x = ops.max_pool_3x3_s2(x) if x.is_cuda else F.max_pool2d(x, 3, 2, 1)
         x = self.blocks(x)
-        x = ops.global_avg_pool(x)
+        return ops.global_avg_pool(x)
+
+    @torch.no_grad()
+    def forward(self, x, return_logits=True):
+        x = self.forward_features(x)
         if x.is_cuda and x.dtype == torch.bfloat16:
             logits = ops.gemm_bf16(x, self.fc_weight, col_shift=self.fc_bias)
         else:

@@ -5,6 +5,7 @@ connection plus server-pushed watch events, with transparent reconnect to any li
 from __future__ import annotations
 
 import itertools
+import queue
 import logging
 import random
 import socket
@@ -50,9 +51,10 @@ class KVClient:
         self._watch_ids = itertools.count(1)
         self._watches: Dict[int, dict] = {}
         self._reader: Optional[threading.Thread] = None
+        self._cb_thread: Optional[threading.Thread] = None
+        self._cb_queue: "queue.Queue" = queue.Queue()
         self._closed = False
         self._conn_lock = threading.RLock()
-        self._cb_queue: List = []
 
     # ------------------------------------------------------------------ connection
     def connect(self):
@@ -101,10 +103,9 @@ class KVClient:
                 w = self._watches.get(msg["watch_id"])
                 if w is not None:
                     w["last_rev"] = max(w.get("last_rev", 0), msg.get("revision", 0))
-                    try:
-                        w["cb"](msg["events"], msg.get("revision", 0))
-                    except Exception:  # noqa: BLE001
-                        logger.exception("watch callback failed")
+                    # callbacks run on their own thread, in arrival order: a callback that issues a
+                    # store request must not block the reader that has to deliver its response
+                    self._dispatch(w["cb"], msg["events"], msg.get("revision", 0))
                 continue
             with self._plock:
                 slot = self._pending.get(msg.get("id"))
@@ -119,6 +120,24 @@ class KVClient:
             for slot in self._pending.values():
                 slot["resp"] = None
                 slot["ev"].set()
+
+    def _dispatch(self, cb, events, rev):
+        with self._plock:
+            if self._cb_thread is None or not self._cb_thread.is_alive():
+                self._cb_thread = threading.Thread(target=self._cb_loop, daemon=True, name="kv-client-watch-cb")
+                self._cb_thread.start()
+        self._cb_queue.put((cb, events, rev))
+
+    def _cb_loop(self):
+        while not self._closed:
+            try:
+                cb, events, rev = self._cb_queue.get(timeout=1.0)
+            except queue.Empty:
+                continue
+            try:
+                cb(events, rev)
+            except Exception:  # noqa: BLE001
+                logger.exception("watch callback failed")
 
     def _rewatch(self):
         for wid, w in list(self._watches.items()):

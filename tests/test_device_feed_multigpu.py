@@ -23,14 +23,17 @@ def _worker(rank, world, port, q):
         from edl_b200.parallel.symm import SymmetricPool
 
         B, C, shape, T = 16, 1000, (3, 32, 32), 2.0
-        pool = SymmetricPool(pool_bytes_needed(B, shape, C, slots=2), device=dev)
+        pool = SymmetricPool(2 * pool_bytes_needed(B, shape, C, slots=2), device=dev)
         role = "student" if rank == 0 else "teacher"
-        link = DeviceDistillLink(pool, peer_rank=1 - rank, role=role, batch=B, image_shape=shape, num_classes=C,
-                                 slots=2, temperature=T, timeout_s=20.0)
+        links = {f: DeviceDistillLink(pool, peer_rank=1 - rank, role=role, batch=B, image_shape=shape, num_classes=C,
+                                      slots=2, temperature=T, timeout_s=20.0, fused_fc=f) for f in (False, True)}
         torch.manual_seed(7)
         proj = (torch.randn(3 * 32 * 32, C, device=dev) * 0.05).bfloat16()      # same "teacher" on both ranks
-        for step in range(6):
-            slot, seq = step % 2, step + 1
+        proj_t = proj.t().contiguous()                                           # [C, K] for the fused GEMM
+        for step in range(12):
+            fused = step >= 6            # first the copy-kernel path, then GEMM -> peer ship
+            link = links[fused]
+            slot, seq = step % 2, step % 6 + 1
             if role == "student":
                 torch.manual_seed(100 + step)
                 x = torch.randn(B, *shape, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
@@ -53,10 +56,13 @@ def _worker(rank, world, port, q):
             else:
                 img = link.wait_images(slot, seq_imm=seq)                          # NCHW view of NHWC memory
                 feats = img.permute(0, 2, 3, 1).reshape(B, -1)
-                logits = (feats.float() @ proj.float()).bfloat16()
-                link.send_logits(logits, slot, seq_imm=seq)
+                if fused:
+                    link.ship_linear(feats.contiguous(), proj_t, None, slot, seq_imm=seq)
+                else:
+                    logits = (feats.float() @ proj.float()).bfloat16()
+                    link.send_logits(logits, slot, seq_imm=seq)
                 torch.cuda.synchronize()
-            assert link.check_error() == 0
+            assert link.check_error() == 0, (step, fused)
         dist.barrier()
         if rank == 0:
             q.put(("ok", ""))
