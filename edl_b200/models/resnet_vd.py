@@ -8,6 +8,7 @@ statistics reduced in the GEMM epilogue, and whose BN-apply / residual-add / ReL
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -33,6 +34,7 @@ class ConvBNAct(nn.Module):
         self.bn = BatchNormAct2d(cout, relu=relu)
         self.impl = impl
         self.fwd_stats: Optional[torch.Tensor] = None  # arena slice [2*cout], zeroed every step
+        self.split_backward = os.environ.get("EDL_SPLIT_CONV_BWD", "1") == "1"
 
     def _use_gemm(self, x):
         if self.impl == "cudnn":
@@ -47,6 +49,9 @@ class ConvBNAct(nn.Module):
                 stats = self.fwd_stats if self.fwd_stats is not None else torch.zeros(
                     2 * self.cout, device=x.device, dtype=torch.float32)
             return ops.conv1x1(x, self.weight, stats), stats
+        if self.split_backward and torch.is_grad_enabled() and self.weight.requires_grad:
+            # library conv whose wgrad half runs on the side stream (ops/gemm.py:_ConvLibFn)
+            return ops.conv_lib(x, self.weight, self.stride, (self.k - 1) // 2, self.groups), None
         w = self.weight.permute(0, 3, 1, 2)
         y = F.conv2d(x, w, None, self.stride, (self.k - 1) // 2, 1, self.groups)
         return y, None

@@ -231,3 +231,67 @@ def linear_bf16(x, weight, bias=None, relu=False):
     sink = getattr(weight, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
     ready = getattr(weight, "_edl_grad_ready", None) if sink is not None else None
     return _LinearFn.apply(x, weight, bias, relu, sink, ready)
+
+
+class _ConvLibFn(torch.autograd.Function):
+    """k x k / strided / grouped convolution on the library kernel (cuDNN) with the backward split in
+    two: dgrad stays on the critical path, wgrad runs on the side stream next to the tcgen05 wgrad
+    GEMMs and lands in the flat gradient bucket (sink) without going through ``param.grad``.
+    ``w`` is stored KRSC ([Cout, kh, kw, Cin/groups]); the library sees a zero-copy NCHW-shaped view."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, padding, groups, sink, ready):
+        wv = w.permute(0, 3, 1, 2)
+        y = torch.ops.aten.convolution(x, wv, None, [stride, stride], [padding, padding], [1, 1], False, [0, 0], groups)
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, padding, groups)
+        ctx.sink, ctx.ready = sink, ready
+        return y
+
+    @staticmethod
+    def _bwd(dy, x, wv, cfg, mask):
+        stride, padding, groups = cfg
+        return torch.ops.aten.convolution_backward(dy, x, wv, None, [stride, stride], [padding, padding], [1, 1],
+                                                   False, [0, 0], groups, mask)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        wv = w.permute(0, 3, 1, 2)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _ConvLibFn._bwd(dy, x, wv, ctx.cfg, [True, False, False])[0]
+        dw = None
+        if ctx.needs_input_grad[1]:
+            sink, ready = ctx.sink, ctx.ready
+            side = _SIDE["stream"] if (dy.is_cuda and sink is not None) else None
+
+            def wgrad():
+                gw = _ConvLibFn._bwd(dy, x, wv, ctx.cfg, [False, True, False])[1].permute(0, 2, 3, 1)
+                if sink is None:
+                    return gw.contiguous()
+                sink.view(w.shape).add_(gw)
+                if ready is not None:
+                    ready()
+                return None
+
+            if side is not None:
+                cur = torch.cuda.current_stream(dy.device)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                side.wait_event(ev)
+                _SIDE["keep"].append((dy, x))
+                with torch.cuda.stream(side):
+                    dw = wgrad()
+                    # temporaries of the side stream must not be recycled by main-stream allocations
+                    # before the streams are joined
+                    _SIDE["keep"].append(None)
+            else:
+                dw = wgrad()
+        return dx, dw, None, None, None, None, None
+
+
+def conv_lib(x, weight_krsc, stride=1, padding=0, groups=1):
+    sink = getattr(weight_krsc, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
+    ready = getattr(weight_krsc, "_edl_grad_ready", None) if sink is not None else None
+    return _ConvLibFn.apply(x, weight_krsc, stride, padding, groups, sink, ready)
