@@ -139,7 +139,7 @@ def distill_main(args, world, rank, dev):
     if is_student:
         model = to_train_dtype(ResNetVd(args.layers, impl=args.conv_impl), torch.bfloat16, dev).train()
         trainer = DistillStudentTrainer(model, B, link, lr=0.1 * B * n_students / 256.0, use_graph=not args.no_graph,
-                                        group=sgroup if n_students > 1 else None, bucket_cap_mb=args.bucket_mb,
+                                        group=sgroup, bucket_cap_mb=args.bucket_mb,
                                         comm_blocks=args.comm_blocks, algo=args.algo)
     else:
         tm = ResNeXt50_32x4d() if args.teacher == "resnext50_32x4d" else ResNeXt101_32x16d()

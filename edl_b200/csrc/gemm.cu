@@ -427,6 +427,33 @@ bool make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t ou
   return r == CUDA_SUCCESS;
 }
 
+}  // namespace
+
+// N-d bf16 tensor map (128B swizzle, zero OOB fill) for the other TMA kernels (conv3x3.cu).
+// dims / box are innermost-first; strides_bytes has rank-1 entries (dims 1..rank-1).
+const char* encode_tmap_bf16(void* out, const void* ptr, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return "cuTensorMapEncodeTiled entry point not found";
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+                  const_cast<void*>(ptr), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_tmap_err, sizeof(g_tmap_err),
+             "cuTensorMapEncodeTiled(rank %d) failed: CUresult=%d ptr=%p dims={%llu,%llu,..} box={%u,%u,..}",
+             rank, (int)r, ptr, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return g_tmap_err;
+  }
+  return nullptr;
+}
+
+namespace {
+
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int EPI>
 const char* launch_variant(const GemmArgs& g, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, STAGES>;

@@ -39,4 +39,24 @@ struct GemmArgs {
 // Returns nullptr on success, else a static error string.
 const char* gemm_bf16(const GemmArgs& args, cudaStream_t stream);
 
+// 3x3 / stride 1 / pad 1 NHWC convolution as an implicit GEMM (conv3x3.cu): nine shifted TMA tile loads
+// per input-channel block (out-of-bounds rows/columns are zero-filled by the TMA unit = the padding)
+// accumulate into one TMEM tile.  `dgrad` computes the data gradient with the same kernel (mirrored
+// taps, weight tile read MN-major).
+struct Conv3x3Args {
+  const void* X = nullptr;   // bf16 NHWC [N, H, W, Cx]  (fwd: input; dgrad: dY)
+  const void* Wt = nullptr;  // bf16 KRSC [Cout, 3, 3, Cin]
+  void* Y = nullptr;         // bf16 NHWC [N, H, W, Cy]  (fwd: output; dgrad: dX)
+  int N = 0, H = 0, W = 0, Cin = 0, Cout = 0;
+  bool dgrad = false;
+  float* col_stats = nullptr;  // fwd only: [2*Cout] += per-channel sum / sum of squares of Y
+  int device = -1;
+};
+bool conv3x3_supported(int N, int H, int W, int Cin, int Cout, bool dgrad);
+const char* conv3x3_bf16(const Conv3x3Args& args, cudaStream_t stream);
+
+// internal: N-d bf16 tensor-map encoder shared by the TMA kernels (defined in gemm.cu)
+const char* encode_tmap_bf16(void* out, const void* ptr, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box);
+
 }  // namespace edl

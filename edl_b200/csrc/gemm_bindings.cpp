@@ -102,9 +102,43 @@ void gemm_bf16_ship(const Tensor& A, const Tensor& B, int64_t d_ptr, int64_t ldd
   const char* err = edl::gemm_bf16(g, at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(err == nullptr, "edl gemm_bf16_ship failed: ", err);
 }
+
+// 3x3 / stride 1 / pad 1 convolution (conv3x3.cu).  x, y: logical NCHW tensors in channels_last memory
+// (= NHWC); w: KRSC [Cout, 3, 3, Cin].  dgrad: x is dY [N, Cout, H, W], y is dX [N, Cin, H, W].
+void conv3x3(const Tensor& x, const Tensor& w, Tensor& y, bool dgrad, const c10::optional<Tensor>& col_stats) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 4 && y.dim() == 4 && w.dim() == 4);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && y.scalar_type() == at::kBFloat16 &&
+              w.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast) && y.is_contiguous(at::MemoryFormat::ChannelsLast),
+              "conv3x3 needs channels_last activations");
+  TORCH_CHECK(w.is_contiguous() && w.size(1) == 3 && w.size(2) == 3, "weight must be KRSC [Cout,3,3,Cin]");
+  edl::Conv3x3Args a;
+  a.X = x.data_ptr();
+  a.Wt = w.data_ptr();
+  a.Y = y.data_ptr();
+  a.N = x.size(0);
+  a.H = x.size(2);
+  a.W = x.size(3);
+  a.Cout = w.size(0);
+  a.Cin = w.size(3);
+  a.dgrad = dgrad;
+  TORCH_CHECK(x.size(1) == (dgrad ? a.Cout : a.Cin) && y.size(1) == (dgrad ? a.Cin : a.Cout));
+  TORCH_CHECK(y.size(0) == a.N && y.size(2) == a.H && y.size(3) == a.W);
+  a.col_stats = optp<float>(col_stats);
+  a.device = x.device().index();
+  c10::cuda::CUDAGuard guard(x.device());
+  const char* err = edl::conv3x3_bf16(a, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(err == nullptr, "edl conv3x3 failed: ", err);
+}
+
+bool conv3x3_supported(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cout, bool dgrad) {
+  return edl::conv3x3_supported((int)n, (int)h, (int)w, (int)cin, (int)cout, dgrad);
+}
 }  // namespace
 
 void register_gemm_bindings(pybind11::module_& m) {
   m.def("gemm_bf16", &gemm_bf16);
+  m.def("conv3x3", &conv3x3);
+  m.def("conv3x3_supported", &conv3x3_supported);
   m.def("gemm_bf16_ship", &gemm_bf16_ship);
 }

@@ -35,6 +35,7 @@ class ConvBNAct(nn.Module):
         self.impl = impl
         self.fwd_stats: Optional[torch.Tensor] = None  # arena slice [2*cout], zeroed every step
         self.split_backward = os.environ.get("EDL_SPLIT_CONV_BWD", "1") == "1"
+        self.own_conv3 = os.environ.get("EDL_OWN_CONV3", "1") == "1"
 
     def _use_gemm(self, x):
         if self.impl == "cudnn":
@@ -49,6 +50,14 @@ class ConvBNAct(nn.Module):
                 stats = self.fwd_stats if self.fwd_stats is not None else torch.zeros(
                     2 * self.cout, device=x.device, dtype=torch.float32)
             return ops.conv1x1(x, self.weight, stats), stats
+        if (self.k == 3 and self.stride == 1 and self.groups == 1 and self.impl != "cudnn" and self.own_conv3
+                and ops.conv3x3_supported(x, self.weight)):
+            # own tcgen05 implicit-GEMM 3x3 (csrc/conv3x3.cu) with the BN statistics in its epilogue
+            stats = None
+            if want_stats:
+                stats = self.fwd_stats if self.fwd_stats is not None else torch.zeros(
+                    2 * self.cout, device=x.device, dtype=torch.float32)
+            return ops.conv3x3(x, self.weight, stats), stats
         if self.split_backward and torch.is_grad_enabled() and self.weight.requires_grad:
             # library conv whose wgrad half runs on the side stream (ops/gemm.py:_ConvLibFn)
             return ops.conv_lib(x, self.weight, self.stride, (self.k - 1) // 2, self.groups), None

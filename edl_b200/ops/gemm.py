@@ -295,3 +295,81 @@ def conv_lib(x, weight_krsc, stride=1, padding=0, groups=1):
     sink = getattr(weight_krsc, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
     ready = getattr(weight_krsc, "_edl_grad_ready", None) if sink is not None else None
     return _ConvLibFn.apply(x, weight_krsc, stride, padding, groups, sink, ready)
+
+
+def conv3x3_supported(x, weight_krsc, dgrad=False) -> bool:
+    from . import native
+
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and weight_krsc.dtype == torch.bfloat16):
+        return False
+    n, _, h, w = x.shape
+    cout, kh, kw, cin = weight_krsc.shape
+    return kh == 3 and kw == 3 and native().conv3x3_supported(n, h, w, cin, cout, dgrad)
+
+
+class _Conv3x3Fn(torch.autograd.Function):
+    """3x3 / stride 1 / pad 1 convolution on the tcgen05 implicit-GEMM kernel (csrc/conv3x3.cu): fprop
+    with the BatchNorm statistics in its epilogue, dgrad on the same kernel with mirrored taps; the
+    weight gradient uses the library kernel on the side stream (off the critical path)."""
+
+    @staticmethod
+    def forward(ctx, x, w, stats, sink, ready):
+        from . import native, count_launch
+
+        x = _cl(x)
+        n, _, h, wd = x.shape
+        y = torch.empty((n, w.shape[0], h, wd), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+        native().conv3x3(x, w, y, False, stats)
+        count_launch()
+        ctx.save_for_backward(x, w)
+        ctx.sink, ctx.ready = sink, ready
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import native, count_launch
+
+        x, w = ctx.saved_tensors
+        dy = _cl(dy)
+        wv = w.permute(0, 3, 1, 2)
+        cfg = (1, 1, 1)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if conv3x3_supported(dy, w, dgrad=True):
+                dx = torch.empty_like(x)
+                native().conv3x3(dy, w, dx, True, None)
+                count_launch()
+            else:
+                dx = _ConvLibFn._bwd(dy, x, wv, cfg, [True, False, False])[0]
+        dw = None
+        if ctx.needs_input_grad[1]:
+            sink, ready = ctx.sink, ctx.ready
+            side = _SIDE["stream"] if sink is not None else None
+
+            def wgrad():
+                gw = _ConvLibFn._bwd(dy, x, wv, cfg, [False, True, False])[1].permute(0, 2, 3, 1)
+                if sink is None:
+                    return gw.contiguous()
+                sink.view(w.shape).add_(gw)
+                if ready is not None:
+                    ready()
+                return None
+
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dy.device))
+                side.wait_event(ev)
+                _SIDE["keep"].append((dy, x))
+                with torch.cuda.stream(side):
+                    dw = wgrad()
+            else:
+                dw = wgrad()
+        return dx, dw, None, None, None
+
+
+def conv3x3(x, weight_krsc, stats: Optional[torch.Tensor] = None):
+    """NHWC 3x3 stride-1 pad-1 convolution; ``stats`` (pre-zeroed fp32 [2*Cout]) receives the per-channel
+    sum / sum of squares of the output for the following train-mode BatchNorm."""
+    sink = getattr(weight_krsc, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
+    ready = getattr(weight_krsc, "_edl_grad_ready", None) if sink is not None else None
+    return _Conv3x3Fn.apply(x, weight_krsc, stats, sink, ready)
