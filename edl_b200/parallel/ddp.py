@@ -312,6 +312,16 @@ class ElasticDataParallel:
                 if g.master is not None:
                     g.param.copy_(g.master.to(g.param.dtype))
 
+    @torch.no_grad()
+    def broadcast_tensor(self, t: torch.Tensor, root: int = 0):
+        """Broadcast any contiguous device tensor (e.g. optimizer state) from ``root`` of the current group."""
+        if self.world <= 1:
+            return
+        if self.use_symm:
+            self._broadcast_tensor(t, root)
+        else:
+            dist.broadcast(t, src=dist.get_global_rank(self.group, root) if self.group else root, group=self.group)
+
     def _broadcast_tensor(self, t: torch.Tensor, root: int):
         """Chunked broadcast through the gradient slab (it is idle outside backward)."""
         from ..ops import native, count_launch

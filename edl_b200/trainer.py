@@ -191,6 +191,18 @@ class StudentTrainer:
         self.graph = None
         self.dp.rebuild(group)
 
+    @torch.no_grad()
+    def sync_from(self, root: int = 0):
+        """After a join: take parameters, fp32 masters and optimizer state from ``root`` over the fabric
+        (NVSwitch broadcast kernel) instead of re-reading the checkpoint from the file system."""
+        self.dp.broadcast_parameters(root)
+        for st in getattr(self.opt, "state", {}).values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    self.dp.broadcast_tensor(v, root)
+        if self.cuda:
+            torch.cuda.synchronize(self.device)
+
     def state_dict(self):
         return {"model": {k: v for k, v in self.model.state_dict().items()},
                 "optim": self.opt.state_dict(), "steps_done": self.steps_done}

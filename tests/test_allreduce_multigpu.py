@@ -111,6 +111,24 @@ def _worker(rank, world, port, q):
             assert torch.isfinite(flat).all()
             assert tr.dp.comm_launches > 0
             res["comm_launches_graph_%s" % use_graph] = tr.dp.comm_launches
+
+        # ---- elastic resize without restarting the processes: 2 -> 1 (each rank alone) -> 2
+        solo = [dist.new_group(ranks=[r]) for r in range(world)][rank]
+        tr.rebuild(solo)
+        assert tr.dp.world == 1
+        for _ in range(2):
+            tr.step(x, t)                      # different data per rank: replicas drift apart
+        tr.rebuild(None)                       # back to the full group: new slab, new bucket plan
+        assert tr.dp.world == world
+        tr.sync_from(0)                        # "joiners" take params + momentum from rank 0
+        for _ in range(2):
+            tr.step(x, t)
+        torch.cuda.synchronize()
+        flat = torch.cat([g.param.flatten().float() for g in tr.dp.flat.groups.values()])
+        outs = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(outs, flat)
+        assert all(torch.equal(outs[0], o) for o in outs), "ranks diverged after the elastic resize"
+        assert tr.dp.check_comm_error() == 0
         if rank == 0:
             q.put(("ok", res))
         dist.barrier()

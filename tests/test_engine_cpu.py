@@ -240,3 +240,53 @@ def test_dgc_gloo_ranks_stay_in_sync_with_sparse_exchange():
     diff, enabled = q.get(timeout=5)
     assert diff < 1e-6                         # sparse all-gather applies the same update everywhere
     assert enabled == [True, False, False, False]   # dense all-reduce only during the ramp-up step
+
+
+def _elastic_worker(rank, world, port, q):
+    from edl_b200.models import to_train_dtype
+    from edl_b200.trainer import StudentTrainer
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    m = to_train_dtype(ResNetVd(18, class_dim=8, width_mult=0.125), torch.float32)
+    tr = StudentTrainer(m, 2, image_shape=(3, 32, 32), num_classes=8, lr=0.05, target_kind="labels", dtype=torch.float32,
+                        bucket_cap_mb=0.05)
+    torch.manual_seed(50 + rank)
+    x = torch.randn(2, 3, 32, 32).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 8, (2,))
+
+    def spread():
+        flat = torch.cat([g.param.flatten() for g in tr.dp.flat.groups.values()])
+        g = [torch.zeros_like(flat) for _ in range(world)]
+        dist.all_gather(g, flat)
+        return float((g[0] - g[1]).abs().max())
+
+    tr.step(x, y)
+    d0 = spread()
+    solo = [dist.new_group(ranks=[r]) for r in range(world)][rank]
+    tr.rebuild(solo)
+    tr.step(x, y)
+    d1 = spread()
+    tr.rebuild(None)
+    tr.sync_from(0)
+    tr.step(x, y)
+    d2 = spread()
+    if rank == 0:
+        q.put((d0, d1, d2, tr.dp.world))
+    dist.destroy_process_group()
+
+
+def test_elastic_rebuild_in_place_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_elastic_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    d0, d1, d2, world = q.get(timeout=5)
+    assert d0 < 1e-6 and d1 > 1e-6 and d2 < 1e-6 and world == 2
