@@ -158,3 +158,64 @@ SERVICES = {
         "GetConf": (predict.ConfRequest, predict.ConfResponse),
     },
 }
+
+
+# ---------------------------------------------------------------------------------- .proto renderings
+_FILES = []   # FileDescriptorProtos in registration order (filled lazily from the pool)
+_TYPE_NAMES = {v: k for k, v in _SCALARS.items()}
+
+
+def render_proto(file_name: str) -> str:
+    """Human-readable ``.proto`` text of one runtime-built schema file, services included
+    (``python -m edl_b200.protos.schema`` rewrites ``edl_b200/protos/*.proto``)."""
+    fdp = descriptor_pb2.FileDescriptorProto()
+    _pool.FindFileByName(file_name).CopyToProto(fdp)
+    out = ['// Rendered from edl_b200/protos/schema.py -- do not edit.', 'syntax = "proto3";', ""]
+    if fdp.package:
+        out += ["package %s;" % fdp.package, ""]
+    for d in fdp.dependency:
+        out.append('import "%s";' % d)
+    if fdp.dependency:
+        out.append("")
+    for e in fdp.enum_type:
+        out.append("enum %s {" % e.name)
+        out += ["  %s = %d;" % (v.name, v.number) for v in e.value]
+        out += ["}", ""]
+    for m in fdp.message_type:
+        if not m.field:
+            out += ["message %s {}" % m.name, ""]
+            continue
+        out.append("message %s {" % m.name)
+        for f in m.field:
+            t = f.type_name.lstrip(".") if f.type == _F.TYPE_MESSAGE else _TYPE_NAMES[f.type]
+            if fdp.package and t.startswith(fdp.package + "."):
+                t = t[len(fdp.package) + 1:]
+            out.append("  %s%s %s = %d;" % ("repeated " if f.label == _F.LABEL_REPEATED else "", t, f.name, f.number))
+        out += ["}", ""]
+    for svc, methods in SERVICES.items():
+        pkg, _, sname = svc.rpartition(".")
+        if pkg != fdp.package:
+            continue
+        out.append("service %s {" % sname)
+        for mname, (req, resp) in methods.items():
+            def short(cls):
+                full = cls.DESCRIPTOR.full_name
+                return full[len(pkg) + 1:] if full.startswith(pkg + ".") else full
+            out.append("  rpc %s(%s) returns (%s) {}" % (mname, short(req), short(resp)))
+        out += ["}", ""]
+    return "\n".join(out).rstrip() + "\n"
+
+
+PROTO_FILES = ["edl/common.proto", "edl/pod_server.proto", "edl/data_server.proto", "edl/distill_discovery.proto",
+               "edl/predict.proto"]
+
+
+if __name__ == "__main__":
+    import os
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name in PROTO_FILES:
+        path = os.path.join(here, os.path.basename(name))
+        with open(path, "w") as f:
+            f.write(render_proto(name))
+        print("wrote", path)

@@ -158,3 +158,14 @@ def test_cluster_watcher(etcd, kv_server):
         time.sleep(0.05)
     assert w.changed and w.get_new_cluster().stage == c.stage
     w.stop()
+
+
+def test_proto_renderings_match_runtime_schema():
+    import os
+    from edl_b200.protos import schema
+
+    here = os.path.dirname(schema.__file__)
+    for name in schema.PROTO_FILES:
+        text = schema.render_proto(name)
+        assert open(os.path.join(here, os.path.basename(name))).read() == text, name + " is stale: python -m edl_b200.protos.schema"
+    assert "rpc Barrier(BarrierRequest) returns (BarrierResponse)" in schema.render_proto("edl/pod_server.proto")
