@@ -53,3 +53,45 @@ def test_collective_resnet_example_models(tmp_path, model):
     out = run(["examples/collective/resnet50/train.py", "--model", model, "--width_mult", "0.125", "--image_size", "32",
                "--class_dim", "10", "--batch_size", "4", "--epochs", "1", "--steps_per_epoch", "3", "--ckpt", str(tmp_path / "ck")])
     assert "Pass 0 trainbatch 0" in out
+
+
+def test_seqfile_roundtrip_and_ctr_dump(tmp_path):
+    import io
+    import struct
+    sys.path.insert(0, os.path.join(ROOT, "examples", "ctr"))
+    from seqfile import SequenceFileReader, SequenceFileWriter
+
+    buf = io.BytesIO()
+    w = SequenceFileWriter(buf)
+    recs = [(struct.pack(">Q", i), os.urandom(40)) for i in range(300)]     # > SYNC_INTERVAL: sync escapes are exercised
+    for k, v in recs:
+        w.write(k, v)
+    buf.seek(0)
+    r = SequenceFileReader(buf)
+    assert r.key_class == b"org.apache.hadoop.io.BytesWritable"
+    assert list(r) == recs
+
+    import torch
+    from edl_b200.models.ctr_dnn import CtrDnn
+    m = CtrDnn(sparse_feature_dim=50, embedding_size=4, num_sparse=3, hidden=(8,))
+    torch.save({"model": m.state_dict()}, tmp_path / "ctr.pt")
+    out = run(["examples/ctr/dumper.py", "--model_path", str(tmp_path / "ctr.pt"), "--output_dir", str(tmp_path / "dump"), "--shards", "2"])
+    assert "dumped 150 rows" in out
+    rows = []
+    for i in range(2):
+        rows += list(SequenceFileReader(open(tmp_path / "dump" / ("part-%05d" % i), "rb")))
+    assert len(rows) == 150 and all(len(v) == 16 for _, v in rows)
+
+
+def test_collector_tracks_job_phases():
+    sys.path.insert(0, os.path.join(ROOT, "examples", "fit_a_line"))
+    from collector import Collector
+
+    state = {"pods": [{"name": "a-0", "job": "a", "phase": "Pending", "gpus": 8}]}
+    c = Collector(lister=lambda: state["pods"], nodes=lambda: 16)
+    assert c.run_once()["jobs"] == {"a": "PENDING:0"}
+    state["pods"] = [{"name": "a-0", "job": "a", "phase": "Running", "gpus": 8}, {"name": "a-1", "job": "a", "phase": "Running", "gpus": 8}]
+    r = c.run_once()
+    assert r["jobs"] == {"a": "RUNNING:2"} and r["gpu_util"] == "16/16" and r["running_trainers"] == 2
+    state["pods"] = []
+    assert c.run_once()["jobs"] == {"a": "FINISH:0"}
