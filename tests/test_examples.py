@@ -95,3 +95,10 @@ def test_collector_tracks_job_phases():
     assert r["jobs"] == {"a": "RUNNING:2"} and r["gpu_util"] == "16/16" and r["running_trainers"] == 2
     state["pods"] = []
     assert c.run_once()["jobs"] == {"a": "FINISH:0"}
+
+
+@pytest.mark.parametrize("nn_type", ["mlp", "conv"])
+def test_recognize_digits_example(tmp_path, nn_type):
+    out = run(["examples/fit_a_line/recognize_digits.py", "--nn_type", nn_type, "--epochs", "2", "--samples", "256",
+               "--ckpt", str(tmp_path / "ck")])
+    assert "epoch 1 loss" in out
