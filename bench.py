@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--layers", type=int, default=50)
     ap.add_argument("--kineto", type=str, default="", help="write a torch.profiler per-kernel table of 5 replayed steps here")
     ap.add_argument("--teacher", default="resnext101_32x16d", choices=["resnext101_32x16d", "resnext50_32x4d"])
+    ap.add_argument("--teacher-fp8", action="store_true", help="distill mode: e4m3 tcgen05 GEMMs for the teacher's 1x1 convs")
     ap.add_argument("--no-fused-bn", action="store_true", help="A/B: disable the SM-resident fused BN kernels")
     ap.add_argument("--no-stream-bn", action="store_true", help="A/B: disable the cp.async.bulk BN kernels")
     return ap.parse_args()
@@ -143,7 +144,11 @@ def distill_main(args, world, rank, dev):
                                         comm_blocks=args.comm_blocks, algo=args.algo)
     else:
         tm = ResNeXt50_32x4d() if args.teacher == "resnext50_32x4d" else ResNeXt101_32x16d()
-        worker = TeacherWorker(to_inference_dtype(tm, torch.bfloat16, dev), link, use_graph=not args.no_graph)
+        tm = to_inference_dtype(tm, torch.bfloat16, dev)
+        if args.teacher_fp8:
+            calib = torch.randn(B, 3, 224, 224, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            tm.enable_fp8(calib)
+        worker = TeacherWorker(tm, link, use_graph=not args.no_graph)
     pool_n = 4
     host_x = [torch.randn(B, 3, 224, 224).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).pin_memory()
               for _ in range(pool_n)] if is_student else None
@@ -202,7 +207,8 @@ def distill_main(args, world, rank, dev):
             "data": "synthetic images, random-init student and teacher", "impl": "edl",
             "config": {"model": "ResNet%d_vd student + %s teacher" % (args.layers, args.teacher),
                        "students": n_students, "teachers": n_students, "batch_per_gpu": B,
-                       "global_batch": B * n_students, "transport": "peer_ship / logit_ship over NVSwitch peer memory",
+                       "global_batch": B * n_students, "transport": "peer_ship + GEMM->peer-ship epilogue over NVSwitch peer memory",
+                       "teacher_dtype": "e4m3 1x1 convs + bf16" if args.teacher_fp8 else "bf16",
                        "parallelism": "dp%d + %d teacher GPUs" % (n_students, n_students),
                        "baseline_note": "vs_baseline divides by the published 1514 img/s (8xV100 + 40xP4, BASELINE.md P3)"},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "link_error": err}))

@@ -433,13 +433,19 @@ bool make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t ou
 // dims / box are innermost-first; strides_bytes has rank-1 entries (dims 1..rank-1).
 const char* encode_tmap_bf16(void* out, const void* ptr, int rank, const uint64_t* dims,
                              const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_tmap(out, ptr, rank, dims, strides_bytes, box, 2);
+}
+
+const char* encode_tmap(void* out, const void* ptr, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return "cuTensorMapEncodeTiled entry point not found";
   cuuint64_t d[5], st[4];
   cuuint32_t b[5], es[5];
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
-  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out),
+                  elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
                   const_cast<void*>(ptr), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -58,5 +58,26 @@ const char* conv3x3_bf16(const Conv3x3Args& args, cudaStream_t stream);
 // internal: N-d bf16 tensor-map encoder shared by the TMA kernels (defined in gemm.cu)
 const char* encode_tmap_bf16(void* out, const void* ptr, int rank, const uint64_t* dims,
                              const uint64_t* strides_bytes, const uint32_t* box);
+const char* encode_tmap(void* out, const void* ptr, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes);
+
+// FP8 (e4m3) inference GEMM (gemm_fp8.cu): D[M,N] bf16 = relu?((A[M,K] * B[N,K]^T) * col_scale[n] + col_shift[n])
+// A, B e4m3 bytes, K-major; col_scale carries act_scale * weight_scale[n] (* folded BN scale).
+struct GemmFp8Args {
+  const void* A = nullptr;
+  const void* B = nullptr;
+  void* D = nullptr;
+  int M = 0, N = 0, K = 0;
+  int64_t lda = 0, ldb = 0, ldd = 0;   // row pitches in elements
+  const float* col_scale = nullptr;
+  const float* col_shift = nullptr;
+  bool relu = false;
+  int device = -1;
+};
+const char* gemm_fp8(const GemmFp8Args& args, cudaStream_t stream);
+
+// bf16 -> e4m3 with a per-tensor scale (q = sat(x / scale)); amax_out (optional) receives max|x| for
+// calibration / delayed scaling.
+void quantize_e4m3(const void* x_bf16, void* q, int64_t n, const float* scale, float* amax_out, cudaStream_t s);
 
 }  // namespace edl

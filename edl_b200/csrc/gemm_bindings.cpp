@@ -131,6 +131,41 @@ void conv3x3(const Tensor& x, const Tensor& w, Tensor& y, bool dgrad, const c10:
   TORCH_CHECK(err == nullptr, "edl conv3x3 failed: ", err);
 }
 
+// D bf16 [M,N] = relu?((A8[M,K] * B8[N,K]^T) * col_scale + col_shift); A8/B8 are e4m3 bytes (uint8 / float8 tensors)
+void gemm_fp8(const Tensor& A, const Tensor& B, Tensor& D, const c10::optional<Tensor>& col_scale,
+              const c10::optional<Tensor>& col_shift, bool relu) {
+  TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.dim() == 2 && B.dim() == 2 && D.dim() == 2);
+  TORCH_CHECK(A.element_size() == 1 && B.element_size() == 1 && D.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1 && D.stride(1) == 1 && A.size(1) == B.size(1));
+  TORCH_CHECK(D.size(0) == A.size(0) && D.size(1) == B.size(0));
+  edl::GemmFp8Args g;
+  g.A = A.data_ptr();
+  g.B = B.data_ptr();
+  g.D = D.data_ptr();
+  g.M = A.size(0);
+  g.K = A.size(1);
+  g.N = B.size(0);
+  g.lda = A.stride(0);
+  g.ldb = B.stride(0);
+  g.ldd = D.stride(0);
+  g.col_scale = optp<float>(col_scale);
+  g.col_shift = optp<float>(col_shift);
+  g.relu = relu;
+  g.device = A.device().index();
+  c10::cuda::CUDAGuard guard(A.device());
+  const char* err = edl::gemm_fp8(g, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(err == nullptr, "edl gemm_fp8 failed: ", err);
+}
+
+void quantize_e4m3(const Tensor& x, Tensor& q, const Tensor& scale, const c10::optional<Tensor>& amax) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.is_contiguous());
+  TORCH_CHECK(q.is_cuda() && q.element_size() == 1 && q.is_contiguous() && q.numel() == x.numel());
+  TORCH_CHECK(scale.scalar_type() == at::kFloat && scale.numel() >= 1);
+  c10::cuda::CUDAGuard guard(x.device());
+  edl::quantize_e4m3(x.data_ptr(), q.data_ptr(), x.numel(), scale.data_ptr<float>(), optp<float>(amax),
+                     at::cuda::getCurrentCUDAStream().stream());
+}
+
 bool conv3x3_supported(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cout, bool dgrad) {
   return edl::conv3x3_supported((int)n, (int)h, (int)w, (int)cin, (int)cout, dgrad);
 }
@@ -139,6 +174,8 @@ bool conv3x3_supported(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cou
 void register_gemm_bindings(pybind11::module_& m) {
   m.def("gemm_bf16", &gemm_bf16);
   m.def("conv3x3", &conv3x3);
+  m.def("gemm_fp8", &gemm_fp8);
+  m.def("quantize_e4m3", &quantize_e4m3);
   m.def("conv3x3_supported", &conv3x3_supported);
   m.def("gemm_bf16_ship", &gemm_bf16_ship);
 }

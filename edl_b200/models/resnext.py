@@ -40,9 +40,33 @@ class FoldedConv(nn.Module):
         self.scale.copy_(s)
         self.shift.copy_(beta.float() - mean.float() * s)
 
+    # ---- fp8 (e4m3) mode of the 1x1 convolutions: see ops/fp8.py -------------------------------
+    def fp8_eligible(self):
+        return self.k == 1 and self.groups == 1 and self.cin % 16 == 0 and self.cout % 8 == 0
+
+    def begin_calibration(self):
+        self._amax = torch.zeros(1, dtype=torch.float32, device=self.weight.device)
+
+    def finish_calibration(self, margin: float = 1.0):
+        """Freeze the activation scale from the recorded max|x| and quantise the weights per output channel."""
+        from ..ops.fp8 import E4M3_MAX, quantize_weight_rows
+
+        amax = float(self._amax.item()) if getattr(self, "_amax", None) is not None else 0.0
+        self._amax = None
+        if not self.fp8_eligible() or amax <= 0.0:
+            return False
+        q, ws = quantize_weight_rows(self.weight.view(self.cout, self.cin))
+        self.w8 = q
+        self.act_scale = torch.full((1,), amax * margin / E4M3_MAX, dtype=torch.float32, device=q.device)
+        self.deq_scale = (self.act_scale * ws.to(q.device) * self.scale).contiguous()   # act * weight * folded BN
+        self._ones, self._zeros = torch.ones_like(self.scale), torch.zeros_like(self.scale)
+        return True
+
     def forward(self, x, residual=None):
         fast = (x.is_cuda and x.dtype == torch.bfloat16 and self.k == 1 and self.groups == 1
                 and self.cin % 8 == 0 and self.cout % 8 == 0)
+        if getattr(self, "_amax", None) is not None and self.fp8_eligible():
+            self._amax.copy_(torch.maximum(self._amax, x.detach().float().abs().max()))
         if fast:
             if self.stride != 1:
                 x = x[:, :, ::self.stride, ::self.stride].contiguous(memory_format=torch.channels_last)
@@ -50,6 +74,15 @@ class FoldedConv(nn.Module):
             x2 = x.permute(0, 2, 3, 1).reshape(-1, c)
             y = torch.empty((n, self.cout, h, w), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
             y2 = y.permute(0, 2, 3, 1).reshape(-1, self.cout)
+            if getattr(self, "w8", None) is not None:
+                from ..ops.fp8 import gemm_fp8, quantize_e4m3
+
+                x8 = quantize_e4m3(x2, self.act_scale)
+                if residual is None:
+                    gemm_fp8(x8, self.w8, self.deq_scale, self.shift, self.relu, out=y2)
+                    return y
+                gemm_fp8(x8, self.w8, self.deq_scale, self.shift, False, out=y2)
+                return ops.scale_shift_act(y, self._ones, self._zeros, residual, self.relu)
             if residual is None:
                 ops.gemm_bf16(x2, self.weight.view(self.cout, self.cin), out=y2, col_scale=self.scale,
                               col_shift=self.shift, relu=self.relu)
@@ -90,6 +123,16 @@ class ResNeXt(nn.Module):
         self.fc_weight = nn.Parameter(torch.empty(class_dim, cin), requires_grad=False)
         self.fc_bias = nn.Parameter(torch.zeros(class_dim, dtype=torch.float32), requires_grad=False)
         nn.init.uniform_(self.fc_weight, -1.0 / math.sqrt(cin), 1.0 / math.sqrt(cin))
+
+    @torch.no_grad()
+    def enable_fp8(self, calib_batch: torch.Tensor, margin: float = 1.0) -> int:
+        """Calibrate activation ranges on ``calib_batch`` (one bf16 forward) and switch every eligible 1x1
+        convolution to the e4m3 tcgen05 GEMM.  Returns the number of converted layers."""
+        convs = [m for m in self.modules() if isinstance(m, FoldedConv)]
+        for c in convs:
+            c.begin_calibration()
+        self.forward_features(calib_batch)
+        return sum(1 for c in convs if c.finish_calibration(margin))
 
     @torch.no_grad()
     def forward_features(self, x):

@@ -140,7 +140,7 @@ def _worker(rank, world, port, q):
         raise
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_allreduce_kernels_and_engine(world):
     if torch.cuda.device_count() < world:
         pytest.skip("not enough GPUs")
