@@ -162,13 +162,20 @@ def main(argv=None):
     ap.add_argument("--thread", type=int, default=4)
     ap.add_argument("--max_batch", type=int, default=64)
     ap.add_argument("--mem_optim", action="store_true", help="accepted for CLI parity; no-op")
+    ap.add_argument("--fp8", action="store_true", help="e4m3 tcgen05 GEMMs for the 1x1 convolutions (calibrated on random data)")
     args = ap.parse_args(argv)
     logging.basicConfig(level=logging.INFO)
     dev = "cuda:%s" % args.gpu_ids.split(",")[0] if torch.cuda.is_available() else "cpu"
     model, feed_names, fetch_names, feed_shapes = build_model(args.model)
     dtype = torch.bfloat16 if dev.startswith("cuda") else torch.float32
     srv = TeacherServer(model, feed_names, fetch_names, feed_shapes, device=dev, dtype=dtype, port=args.port,
-                        max_batch=args.max_batch, workers=max(4, args.thread)).start()
+                        max_batch=args.max_batch, workers=max(4, args.thread))
+    net = getattr(srv.model, "net", srv.model)
+    if args.fp8 and dev.startswith("cuda") and hasattr(net, "enable_fp8"):
+        shape = feed_shapes[feed_names[0]]
+        calib = torch.randn(8, *shape, device=dev).to(dtype).contiguous(memory_format=torch.channels_last)
+        logging.info("fp8: converted %d layers", net.enable_fp8(calib))
+    srv.start()
     try:
         while True:
             time.sleep(3600)

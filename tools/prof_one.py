@@ -7,6 +7,7 @@ captures exactly the kernel of interest.
   dgrad  M K N
   bnbwd  N C H W [fused|stream|regs] [res]
   bnfwd  N C H W [fused|stream|regs] [res]
+  conv3 / conv3dgrad  N CIN COUT H W   tcgen05 implicit-GEMM 3x3 convolution
 """
 import os
 import sys
@@ -65,5 +66,12 @@ elif op in ("bnbwd", "bnfwd"):
         if op == "bnbwd":
             y.backward(dyv)
     run(f)
+elif op in ("conv3", "conv3dgrad"):
+    n, c, k, h, w = [int(v) for v in a[:5]]          # batch, Cin, Cout, H, W
+    x = torch.randn(n, c if op == "conv3" else k, h, w, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(k, 3, 3, c, device=dev) * 0.05).bfloat16()
+    y = torch.empty(n, k if op == "conv3" else c, h, w, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    st = torch.zeros(2 * k, device=dev)
+    run(lambda: ops.native().conv3x3(x, wt, y, op != "conv3", st if op == "conv3" else None))
 else:
     raise SystemExit("unknown op " + op)
