@@ -162,11 +162,8 @@ bn_stats_stream_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ 
   }
   reduce_groups<16>(acc, cvecs, reinterpret_cast<float*>(r.data), consumer);
   if (consumer && tid < cvecs) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sums[tid * 8 + i], acc[i]);
-      atomicAdd(&sums[C + tid * 8 + i], acc[8 + i]);
-    }
+    red_add8(&sums[tid * 8], acc);
+    red_add8(&sums[C + tid * 8], acc + 8);
   }
 }
 
@@ -310,11 +307,8 @@ bn_bwd_reduce_stream_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfl
   }
   reduce_groups<16>(acc, cvecs, reinterpret_cast<float*>(r.data), consumer);
   if (consumer && tid < cvecs) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&dsums[tid * 8 + i], acc[i]);
-      atomicAdd(&dsums[C + tid * 8 + i], acc[8 + i]);
-    }
+    red_add8(&dsums[tid * 8], acc);
+    red_add8(&dsums[C + tid * 8], acc + 8);
   }
 }
 
@@ -382,6 +376,13 @@ inline int stream_grid(int64_t total) {
   int64_t n_chunks = (total + kChunkElems - 1) / kChunkElems;
   return (int)(n_chunks < kNumSMs ? n_chunks : kNumSMs);
 }
+// Reduction kernels end with 2C global reductions per CTA into the same few KB: fewer, fatter CTAs
+// (a full ring of chunks each) for small tensors keep that tail short.
+inline int reduce_grid(int64_t total) {
+  int64_t n_chunks = (total + kChunkElems - 1) / kChunkElems;
+  int64_t g = (n_chunks + kStages - 1) / kStages;
+  return (int)(g < 1 ? 1 : (g < kNumSMs ? g : kNumSMs));
+}
 
 template <class K>
 inline void set_smem(K kern, size_t bytes) {
@@ -408,7 +409,7 @@ void bn_stats_stream(const void* x, float* sums, int64_t M, int C, cudaStream_t 
   const int64_t total = M * C;
   const size_t smem = ring_smem_bytes<1>() > kConsumers * 16 * 4 ? ring_smem_bytes<1>() : kConsumers * 16 * 4 + 256;
   set_smem(bn_stats_stream_kernel, smem);
-  bn_stats_stream_kernel<<<stream_grid(total), kThreads, smem, s>>>(BF(x), sums, total, C);
+  bn_stats_stream_kernel<<<reduce_grid(total), kThreads, smem, s>>>(BF(x), sums, total, C);
 }
 
 void bn_apply_stream(const void* x, const void* res, void* y, const float* sums, const float* gamma,
@@ -436,7 +437,7 @@ void bn_bwd_reduce_stream(const void* dy, const void* x, const void* y, const fl
 #define LAUNCH(R, Y, NT)                                                                                   \
   {                                                                                                        \
     set_smem(bn_bwd_reduce_stream_kernel<R, Y>, ring_smem_bytes<NT>());                                    \
-    bn_bwd_reduce_stream_kernel<R, Y><<<stream_grid(total), kThreads, ring_smem_bytes<NT>(), s>>>(         \
+    bn_bwd_reduce_stream_kernel<R, Y><<<reduce_grid(total), kThreads, ring_smem_bytes<NT>(), s>>>(         \
         BF(dy), BF(x), BF(y), gamma, beta, saved_mean, saved_rstd, dsums, total, C);                       \
   }
   if (!relu) LAUNCH(false, false, 2)

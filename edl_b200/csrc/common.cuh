@@ -74,6 +74,23 @@ EDL_DEVICE float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// fp32 reductions into global memory.  Hot accumulators (per-channel BatchNorm sums: a few KB hit by
+// every CTA) are limited by the number of reduction REQUESTS the L2 can retire (~12 / ns measured when
+// all SMs hammer ~1k addresses, profiles/prof_bnstats_small), so four floats go in one request.
+EDL_DEVICE void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// dst[0..7] += v[0..7]; vectorised when dst is 16-byte aligned
+EDL_DEVICE void red_add8(float* dst, const float* v) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    red_add_v4(dst, v[0], v[1], v[2], v[3]);
+    red_add_v4(dst + 4, v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(dst + i, v[i]);
+  }
+}
+
 EDL_DEVICE float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

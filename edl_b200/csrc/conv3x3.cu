@@ -196,12 +196,12 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       // rows of the patch that lie inside the tensor (partial patches at the bottom / last images)
       const int rows_per_img = p.BH * p.W;
       for (int col = et; col < BLOCK_N; col += kEpiThreads) {
-        if (n0 + col >= p.n_out) continue;
+        const bool valid = n0 + col < p.n_out;     // no early exit: the whole warp shuffles below
         const int half = col >> 6, cc = col & 63, chunk = cc >> 3, within = cc & 7;
         const uint8_t* base = sd + half * (kBlockM * 128) + within * 2;
         float s = 0.f, sq = 0.f;
         for (int b = 0; b < p.BN; ++b) {
-          if (img0 + b >= p.n_img) break;
+          if (img0 + b >= p.n_img || !valid) break;
           int hv = p.H - h0;
           if (hv > p.BH) hv = p.BH;
           const int r_begin = b * rows_per_img, r_end = r_begin + hv * p.W;
@@ -214,8 +214,25 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             sq = fmaf(v, v, sq);
           }
         }
-        atomicAdd(&p.col_stats[n0 + col], s);
-        atomicAdd(&p.col_stats[p.n_out + n0 + col], sq);
+        // four neighbouring columns -> one vector reduction (lane 4i collects lanes 4i..4i+3)
+        const float s1 = __shfl_down_sync(0xffffffffu, s, 1), s2 = __shfl_down_sync(0xffffffffu, s, 2),
+                    s3 = __shfl_down_sync(0xffffffffu, s, 3);
+        const float q1 = __shfl_down_sync(0xffffffffu, sq, 1), q2 = __shfl_down_sync(0xffffffffu, sq, 2),
+                    q3 = __shfl_down_sync(0xffffffffu, sq, 3);
+        float* ps = &p.col_stats[n0 + col];
+        float* pq = &p.col_stats[p.n_out + n0 + col];
+        const int c4 = col & ~3;   // the decision is per group of four columns, identical in its 4 lanes
+        const bool vec = (p.n_out % 4 == 0) && n0 + c4 + 3 < p.n_out &&
+                         ((reinterpret_cast<uintptr_t>(&p.col_stats[n0 + c4]) & 15) == 0);
+        if (vec) {
+          if ((col & 3) == 0) {
+            red_add_v4(ps, s, s1, s2, s3);
+            red_add_v4(pq, sq, q1, q2, q3);
+          }
+        } else if (valid) {
+          atomicAdd(ps, s);
+          atomicAdd(pq, sq);
+        }
       }
     }
     if (et == 0) ptx::tma_store_wait_read0();

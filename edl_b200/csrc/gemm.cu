@@ -221,20 +221,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           int rows_valid = p.M - m0;
           if (rows_valid > BLOCK_M) rows_valid = BLOCK_M;
           for (int col = et; col < BLOCK_N; col += kEpiThreads) {
-            if (n0 + col >= p.N) continue;
+            const bool valid = n0 + col < p.N;     // no early exit: the whole warp shuffles below
             const int half = col >> 6, cc = col & 63, chunk = cc >> 3, within = cc & 7;
             const uint8_t* base = sd + half * (BLOCK_M * 128) + within * 2;
             float s = 0.f, sq = 0.f;
 #pragma unroll 8
-            for (int rr = 0; rr < rows_valid; ++rr) {
+            for (int rr = 0; rr < (valid ? rows_valid : 0); ++rr) {
               const __nv_bfloat16 hv = *reinterpret_cast<const __nv_bfloat16*>(
                   base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
               const float v = __bfloat162float(hv);
               s += v;
               sq = fmaf(v, v, sq);
             }
-            atomicAdd(&p.col_stats[n0 + col], s);
-            atomicAdd(&p.col_stats[p.N + n0 + col], sq);
+            // four neighbouring columns -> one vector reduction (lane 4i collects lanes 4i..4i+3)
+            const float s1 = __shfl_down_sync(0xffffffffu, s, 1), s2 = __shfl_down_sync(0xffffffffu, s, 2),
+                        s3 = __shfl_down_sync(0xffffffffu, s, 3);
+            const float q1 = __shfl_down_sync(0xffffffffu, sq, 1), q2 = __shfl_down_sync(0xffffffffu, sq, 2),
+                        q3 = __shfl_down_sync(0xffffffffu, sq, 3);
+            float* ps = &p.col_stats[n0 + col];
+            float* pq = &p.col_stats[p.N + n0 + col];
+            const int c4 = col & ~3;   // the decision is per group of four columns, identical in its 4 lanes
+            const bool vec = (p.N % 4 == 0) && n0 + c4 + 3 < p.N &&
+                             ((reinterpret_cast<uintptr_t>(&p.col_stats[n0 + c4]) & 15) == 0);
+            if (vec) {
+              if ((col & 3) == 0) {
+                red_add_v4(ps, s, s1, s2, s3);
+                red_add_v4(pq, sq, q1, q2, q3);
+              }
+            } else if (valid) {
+              atomicAdd(ps, s);
+              atomicAdd(pq, sq);
+            }
           }
         }
         if (et == 0) {
