@@ -314,6 +314,11 @@ def main():
             torch.cuda.synchronize(dev)
         with open(args.kineto, "w") as fh:
             fh.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+        # timeline of ONE replayed step for tools/trace_timeline.py (stream overlap / idle-gap analysis)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof1:
+            trainer.step_device()
+            torch.cuda.synchronize(dev)
+        prof1.export_chrome_trace(args.kineto + ".trace.json")
 
     # ---- end-to-end region: public API, H2D every step, D2H loss every step ----
     e2e = None

@@ -343,6 +343,8 @@ const char* conv3x3_bf16(const Conv3x3Args& a, cudaStream_t stream) {
   }
   const Geometry geo = plan(a.N, a.H, a.W);
   const int cy = a.dgrad ? a.Cin : a.Cout;
+  if (persistent_gemm_enabled())
+    return conv3x3_bf16_persistent(a, geo.BH, geo.BN, geo.tiles_h, geo.tiles_img, stream);
   if (!a.dgrad)
     return cy <= 64 ? launch<64, 4, false>(a, geo, stream) : launch<128, 3, false>(a, geo, stream);
   return cy <= 64 ? launch<64, 4, true>(a, geo, stream) : launch<128, 3, true>(a, geo, stream);

@@ -55,6 +55,14 @@ struct Conv3x3Args {
 bool conv3x3_supported(int N, int H, int W, int Cin, int Cout, bool dgrad);
 const char* conv3x3_bf16(const Conv3x3Args& args, cudaStream_t stream);
 
+// Persistent variants (gemm_persist.cu): one CTA per SM streams tiles, double-buffered TMEM accumulators,
+// epilogue overlapped with the next tile's MMAs.  Used by gemm_bf16 / conv3x3_bf16 when enabled (default).
+void set_persistent_gemm(bool on);
+bool persistent_gemm_enabled();
+const char* gemm_bf16_persistent(const GemmArgs& args, cudaStream_t stream);
+const char* conv3x3_bf16_persistent(const Conv3x3Args& args, int BH, int BN, int tiles_h, int tiles_img,
+                                    cudaStream_t stream);
+
 // internal: N-d bf16 tensor-map encoder shared by the TMA kernels (defined in gemm.cu)
 const char* encode_tmap_bf16(void* out, const void* ptr, int rank, const uint64_t* dims,
                              const uint64_t* strides_bytes, const uint32_t* box);

@@ -174,6 +174,8 @@ bool conv3x3_supported(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cou
 void register_gemm_bindings(pybind11::module_& m) {
   m.def("gemm_bf16", &gemm_bf16);
   m.def("conv3x3", &conv3x3);
+  m.def("set_persistent_gemm", &edl::set_persistent_gemm);
+  m.def("persistent_gemm_enabled", &edl::persistent_gemm_enabled);
   m.def("gemm_fp8", &gemm_fp8);
   m.def("quantize_e4m3", &quantize_e4m3);
   m.def("conv3x3_supported", &conv3x3_supported);

@@ -1,0 +1,420 @@
+// Persistent tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+// gemm.cu / conv3x3.cu launch one CTA per output tile.  The layers of ResNet50_vd at batch 32 have SHORT
+// K loops (1..36 k-blocks), so a CTA's fixed work (barrier init, TMEM allocation, tensor-map fetch,
+// pipeline fill, epilogue, teardown) dominated: profiles/prof_conv3_56 shows 10 us of CTA lifetime for
+// nine k-steps and the tensor pipe 16 % busy.  This kernel keeps ONE CTA per SM alive and streams tiles
+// through it:
+//
+//   warp 0      TMA producer: one smem ring shared by all tiles of the CTA, never drained between tiles
+//   warp 1      TMEM allocator + tcgen05.mma issuer; TWO accumulators in TMEM (2 x BLOCK_N columns), so
+//               the MMAs of tile i+1 run while tile i is still being read out
+//   warps 2..9  epilogue (two warpgroups, each owns half of the tile's columns): tcgen05.ld -> scale /
+//               shift / ReLU -> bf16 -> swizzled staging tile -> TMA store, BatchNorm statistics of the
+//               stored values -> vector reductions; releases the accumulator as soon as it is in registers
+//
+// Modes: 0 = D = A * B^T (B K-major: 1x1 conv fprop, FC), 1 = D = A * B (B MN-major: 1x1 conv dgrad),
+//        2 = 3x3/s1/p1 conv fprop, 3 = 3x3/s1/p1 conv dgrad (see conv3x3.cu for the shifted-box trick).
+#include <cuda.h>
+#include <cstdio>
+
+#include "gemm.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace edl {
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;   // 320
+constexpr int kEpiThreads = kEpiWarps * 32;     // 256
+
+struct PersistParams {
+  // GEMM view
+  int M, N, K;
+  int tiles_m, tiles_n;
+  int num_kb;                 // k-blocks per tile (conv: 9 * kc_blocks)
+  const float* col_scale;
+  const float* col_shift;
+  int relu;
+  float* col_stats;
+  // conv view (modes 2, 3)
+  int n_img, H, W, kc_blocks, c_in_w, BH, BN, tiles_h;
+};
+
+template <int BLOCK_N, int STAGES>
+struct PSmem {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kDBytes = kBlockM * BLOCK_N * 2;
+  static constexpr int kRingBytes = STAGES * kStageBytes;
+  static constexpr int kBarOffset = kRingBytes + kDBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;
+};
+
+EDL_DEVICE void tma_store_4d_p(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(ptx::smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+template <int BLOCK_N, int STAGES, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmD, const PersistParams p) {
+  using L = PSmem<BLOCK_N, STAGES>;
+  constexpr bool kConv = MODE >= 2;
+  constexpr bool kBMN = MODE == 1 || MODE == 3;
+  constexpr bool kDgrad = MODE == 3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sd = smem + L::kRingBytes;                    // dedicated store-staging tile
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;              // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.tiles_n;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : 256));
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmD);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], kEpiWarps);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int rows_tile = kConv ? p.BN * p.BH * p.W : kBlockM;
+  const uint32_t a_bytes = kConv ? (uint32_t)rows_tile * 128u : (uint32_t)L::kABytes;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int tile_m = t / p.tiles_n;
+        const int n0 = (t - tile_m * p.tiles_n) * BLOCK_N;
+        const int m0 = tile_m * kBlockM;
+        const int img0 = kConv ? (tile_m / p.tiles_h) * p.BN : 0;
+        const int h0 = kConv ? (tile_m % p.tiles_h) * p.BH : 0;
+        for (int i = 0; i < p.num_kb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[s], a_bytes + L::kBBytes);
+          if (!kConv) {
+            const int k0 = i * kBlockK;
+            ptx::tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
+            if (!kBMN) {
+              ptx::tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+            } else {
+#pragma unroll
+              for (int hh = 0; hh < BLOCK_N / 64; ++hh)
+                ptx::tma_load_2d(sb + hh * 8192, &tmB, &full_bar[s], n0 + hh * 64, k0);
+            }
+          } else {
+            const int tap = i / p.kc_blocks;
+            const int kc = i - tap * p.kc_blocks;
+            const int r = tap / 3, sft = tap - r * 3;
+            const int dh = kDgrad ? 1 - r : r - 1;
+            const int dw = kDgrad ? 1 - sft : sft - 1;
+            ptx::tma_load_4d(sa, &tmA, &full_bar[s], kc * kBlockK, dw, h0 + dh, img0);
+            if (!kBMN) {
+              ptx::tma_load_2d(sb, &tmB, &full_bar[s], tap * p.c_in_w + kc * kBlockK, n0);
+            } else {
+#pragma unroll
+              for (int hh = 0; hh < BLOCK_N / 64; ++hh)
+                ptx::tma_load_2d(sb + hh * 8192, &tmB, &full_bar[s], tap * p.c_in_w + n0 + hh * 64, kc * kBlockK);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc(1, 1, kBlockM, BLOCK_N, 0, kBMN ? 1 : 0);
+      uint32_t it = 0, tc = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
+        const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[slot], aph ^ 1);      // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t acc = tmem_base + slot * BLOCK_N;
+        for (int i = 0; i < p.num_kb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + s * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = ptx::make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = kBMN ? ptx::make_smem_desc(sb + k * 2048, 8192, 1024)
+                                     : ptx::make_smem_desc(sb + k * 32, 16, 1024);
+            ptx::umma_f16(acc, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);
+        }
+        ptx::umma_commit(&tmem_full[slot]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int ew = warp - 2;                 // 0..7
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int grp = ew >> 2;                 // column half owned by this warpgroup
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;         // 0..255
+    constexpr int kColsPerGrp = BLOCK_N / 2;
+    uint32_t tc = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
+      const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
+      const int tile_m = t / p.tiles_n;
+      const int n0 = (t - tile_m * p.tiles_n) * BLOCK_N;
+      const int m0 = tile_m * kBlockM;
+      const int img0 = kConv ? (tile_m / p.tiles_h) * p.BN : 0;
+      const int h0 = kConv ? (tile_m % p.tiles_h) * p.BH : 0;
+      // the staging tile must have been read by the previous TMA store and by every stats thread
+      if (et == 0) ptx::tma_store_wait_read0();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      ptx::mbar_wait(&tmem_full[slot], aph);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + slot * BLOCK_N + grp * kColsPerGrp + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c32 = 0; c32 < kColsPerGrp / 32; ++c32) {
+        uint32_t rg[32];
+        ptx::tmem_ld_32x32(taddr + c32 * 32, rg);
+        ptx::tmem_ld_wait();
+        if (c32 == kColsPerGrp / 32 - 1) {
+          // accumulator fully in registers: hand it back to the MMA warp before the slow part
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty[slot]);
+        }
+        const int cbase = grp * kColsPerGrp + c32 * 32;   // first tile column of this chunk
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(rg[j]);
+        if (!kConv) {
+          if (p.col_scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = n0 + cbase + j;
+              f[j] *= col < p.N ? p.col_scale[col] : 0.f;
+            }
+          }
+          if (p.col_shift != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = n0 + cbase + j;
+              f[j] += col < p.N ? p.col_shift[col] : 0.f;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+        }
+        const int half = cbase >> 6;
+        uint8_t* rowp = sd + half * (kBlockM * 128) + row * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int chunk = ((cbase >> 5) & 1) * 4 + c;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = f[c * 8 + j];
+          st_vec(rowp + ((chunk ^ (row & 7)) << 4), pack8(v));
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et == 0) {
+#pragma unroll
+        for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) {
+          if (n0 + hh * 64 >= p.N) continue;
+          if (!kConv) ptx::tma_store_2d(&tmD, sd + hh * (kBlockM * 128), n0 + hh * 64, m0);
+          else tma_store_4d_p(&tmD, sd + hh * (kBlockM * 128), n0 + hh * 64, 0, h0, img0);
+        }
+        ptx::tma_store_commit();
+      }
+      if (p.col_stats != nullptr) {
+        // 256 threads, BLOCK_N columns: kSplit threads share a column, each sums an interleaved row subset
+        constexpr int kSplit = kEpiThreads / BLOCK_N;          // 2 (N=128) or 4 (N=64)
+        const int col = et % BLOCK_N;
+        const int part = et / BLOCK_N;
+        const bool valid = n0 + col < p.N;
+        const int half = col >> 6, cc = col & 63, chunk = cc >> 3, within = cc & 7;
+        const uint8_t* base = sd + half * (kBlockM * 128) + within * 2;
+        float s = 0.f, sq = 0.f;
+        if (valid) {
+          if (!kConv) {
+            int rows_valid = p.M - m0;
+            if (rows_valid > kBlockM) rows_valid = kBlockM;
+            for (int rr = part; rr < rows_valid; rr += kSplit) {
+              const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
+                  base + rr * 128 + ((chunk ^ (rr & 7)) << 4)));
+              s += v;
+              sq = fmaf(v, v, sq);
+            }
+          } else {
+            const int rows_per_img = p.BH * p.W;
+            int hv = p.H - h0;
+            if (hv > p.BH) hv = p.BH;
+            for (int b = 0; b < p.BN && img0 + b < p.n_img; ++b) {
+              const int r_begin = b * rows_per_img, r_end = r_begin + hv * p.W;
+              for (int rr = r_begin + part; rr < r_end; rr += kSplit) {
+                const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
+                    base + rr * 128 + ((chunk ^ (rr & 7)) << 4)));
+                s += v;
+                sq = fmaf(v, v, sq);
+              }
+            }
+          }
+        }
+        // four neighbouring columns of one row subset -> one vector reduction
+        const float s1 = __shfl_down_sync(0xffffffffu, s, 1), s2 = __shfl_down_sync(0xffffffffu, s, 2),
+                    s3 = __shfl_down_sync(0xffffffffu, s, 3);
+        const float q1 = __shfl_down_sync(0xffffffffu, sq, 1), q2 = __shfl_down_sync(0xffffffffu, sq, 2),
+                    q3 = __shfl_down_sync(0xffffffffu, sq, 3);
+        const int c4 = col & ~3;
+        float* ps4 = &p.col_stats[n0 + c4];
+        const bool vec = (p.N % 4 == 0) && n0 + c4 + 3 < p.N && ((reinterpret_cast<uintptr_t>(ps4) & 15) == 0);
+        if (vec) {
+          if ((col & 3) == 0) {
+            red_add_v4(ps4, s, s1, s2, s3);
+            red_add_v4(ps4 + p.N, sq, q1, q2, q3);
+          }
+        } else if (valid) {
+          atomicAdd(&p.col_stats[n0 + col], s);
+          atomicAdd(&p.col_stats[p.N + n0 + col], sq);
+        }
+      }
+    }
+    if (et == 0) ptx::tma_store_wait_read0();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+bool g_persistent = true;
+
+template <int BLOCK_N, int STAGES, int MODE>
+const char* launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const PersistParams& p,
+                     cudaStream_t stream) {
+  using L = PSmem<BLOCK_N, STAGES>;
+  auto kern = gemm_persist_kernel<BLOCK_N, STAGES, MODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    apply_carveout((const void*)kern);
+    attr_set = true;
+  }
+  const int total = p.tiles_m * p.tiles_n;
+  const int grid = total < kNumSMs ? total : kNumSMs;
+  kern<<<grid, kThreads, L::kTotal, stream>>>(tmA, tmB, tmD, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* tmap2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                   uint32_t box_inner, uint32_t box_outer) {
+  const uint64_t dims[2] = {inner, outer};
+  const uint64_t st[1] = {pitch_elems * 2};
+  const uint32_t box[2] = {box_inner, box_outer};
+  return encode_tmap_bf16(out, ptr, 2, dims, st, box);
+}
+
+}  // namespace
+
+void set_persistent_gemm(bool on) { g_persistent = on; }
+bool persistent_gemm_enabled() { return g_persistent; }
+
+// GEMM front end (EPI 0 semantics of gemm.cu; A K-major)
+const char* gemm_bf16_persistent(const GemmArgs& g, cudaStream_t stream) {
+  alignas(64) CUtensorMap tmA, tmB, tmD;
+  const bool n64 = g.N <= 64;
+  const int bn = n64 ? 64 : 128;
+  if (const char* e = tmap2d(&tmA, g.A, g.K, g.M, g.lda, kBlockK, kBlockM)) return e;
+  if (!g.b_mn_major) {
+    if (const char* e = tmap2d(&tmB, g.B, g.K, g.N, g.ldb, kBlockK, bn)) return e;
+  } else {
+    if (const char* e = tmap2d(&tmB, g.B, g.N, g.K, g.ldb, 64, kBlockK)) return e;
+  }
+  if (const char* e = tmap2d(&tmD, g.D, g.N, g.M, g.ldd, 64, kBlockM)) return e;
+  PersistParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.tiles_m = (g.M + kBlockM - 1) / kBlockM;
+  p.tiles_n = (g.N + bn - 1) / bn;
+  p.num_kb = (g.K + kBlockK - 1) / kBlockK;
+  p.col_scale = g.col_scale; p.col_shift = g.col_shift; p.relu = g.relu ? 1 : 0;
+  p.col_stats = g.col_stats;
+  if (!g.b_mn_major)
+    return n64 ? launch_p<64, 6, 0>(tmA, tmB, tmD, p, stream) : launch_p<128, 5, 0>(tmA, tmB, tmD, p, stream);
+  return n64 ? launch_p<64, 6, 1>(tmA, tmB, tmD, p, stream) : launch_p<128, 5, 1>(tmA, tmB, tmD, p, stream);
+}
+
+// conv front end: geometry comes from conv3x3.cu's planner
+const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int tiles_h, int tiles_img,
+                                    cudaStream_t stream) {
+  const bool dg = a.dgrad;
+  const int cx = dg ? a.Cout : a.Cin, cy = dg ? a.Cin : a.Cout;
+  const bool n64 = cy <= 64;
+  const int bn = n64 ? 64 : 128;
+  alignas(64) CUtensorMap tmX, tmW, tmY;
+  {
+    const uint64_t dims[4] = {(uint64_t)cx, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
+    const uint64_t st[3] = {(uint64_t)cx * 2, (uint64_t)a.W * cx * 2, (uint64_t)a.H * a.W * cx * 2};
+    const uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)BH, (uint32_t)BN};
+    if (const char* e = encode_tmap_bf16(&tmX, a.X, 4, dims, st, box)) return e;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)cy, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
+    const uint64_t st[3] = {(uint64_t)cy * 2, (uint64_t)a.W * cy * 2, (uint64_t)a.H * a.W * cy * 2};
+    const uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)BH, (uint32_t)BN};
+    if (const char* e = encode_tmap_bf16(&tmY, a.Y, 4, dims, st, box)) return e;
+  }
+  if (const char* e = tmap2d(&tmW, a.Wt, (uint64_t)9 * a.Cin, a.Cout, (uint64_t)9 * a.Cin, 64, dg ? kBlockK : bn))
+    return e;
+  PersistParams p{};
+  p.M = tiles_img * tiles_h * kBlockM; p.N = cy; p.K = 9 * cx;
+  p.tiles_m = tiles_img * tiles_h;
+  p.tiles_n = (cy + bn - 1) / bn;
+  p.kc_blocks = cx / kBlockK;
+  p.num_kb = 9 * p.kc_blocks;
+  p.col_stats = dg ? nullptr : a.col_stats;
+  p.n_img = a.N; p.H = a.H; p.W = a.W; p.c_in_w = a.Cin; p.BH = BH; p.BN = BN; p.tiles_h = tiles_h;
+  if (!dg) return n64 ? launch_p<64, 6, 2>(tmX, tmW, tmY, p, stream) : launch_p<128, 5, 2>(tmX, tmW, tmY, p, stream);
+  return n64 ? launch_p<64, 6, 3>(tmX, tmW, tmY, p, stream) : launch_p<128, 5, 3>(tmX, tmW, tmY, p, stream);
+}
+
+}  // namespace edl

@@ -1,0 +1,78 @@
+"""Persistent tcgen05 GEMM / conv kernel (csrc/gemm_persist.cu) against the one-tile-per-CTA kernels and
+the fp32 reference: many tiles per CTA (accumulator double-buffering, ring wrap-around across tiles)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from edl_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+@pytest.fixture(autouse=True)
+def _restore():
+    yield
+    ops.native().set_persistent_gemm(True)
+
+
+@pytest.mark.parametrize("m,n,k", [(100352, 64, 64), (100352, 256, 64), (25088, 512, 128), (6272, 1024, 256),
+                                   (1568, 2048, 512), (40000, 192, 72), (300, 128, 64), (128 * 148 * 3 + 5, 128, 64)])
+@pytest.mark.parametrize("b_mn", [False, True])
+def test_persistent_gemm_matches_reference_and_stats(m, n, k, b_mn):
+    torch.manual_seed(0)
+    a = torch.randn(m, k, device=DEV).bfloat16()
+    b = (torch.randn(k, n, device=DEV) if b_mn else torch.randn(n, k, device=DEV)).bfloat16()
+    ref = a.float() @ (b.float() if b_mn else b.float().t())
+    outs = []
+    for persistent in (True, False):
+        ops.native().set_persistent_gemm(persistent)
+        stats = torch.zeros(2 * n, device=DEV)
+        d = ops.gemm_bf16(a, b, b_mn_major=b_mn, col_stats=None if b_mn else stats)
+        assert _rel(d, ref) < 1e-2, persistent
+        if not b_mn:
+            assert _rel(stats[:n], d.float().sum(0)) < 2e-3
+            assert _rel(stats[n:], (d.float() ** 2).sum(0)) < 2e-3
+        outs.append(d)
+    assert torch.equal(outs[0], outs[1])          # same MMA order => bit-identical results
+
+
+def test_persistent_gemm_epilogue_scale_shift_relu():
+    torch.manual_seed(1)
+    m, n, k = 5000, 256, 192
+    a = torch.randn(m, k, device=DEV).bfloat16()
+    b = torch.randn(n, k, device=DEV).bfloat16()
+    sc, sh = torch.rand(n, device=DEV) + 0.5, torch.randn(n, device=DEV)
+    d = ops.gemm_bf16(a, b, col_scale=sc, col_shift=sh, relu=True)
+    assert _rel(d, torch.relu((a.float() @ b.float().t()) * sc + sh)) < 1e-2
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w", [(32, 64, 64, 56, 56), (32, 128, 128, 28, 28), (32, 256, 256, 14, 14),
+                                            (32, 512, 512, 7, 7), (5, 64, 192, 11, 20)])
+def test_persistent_conv3x3_matches_tile_kernel(n, cin, cout, h, w):
+    torch.manual_seed(2)
+    x = torch.randn(n, cin, h, w, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, 3, 3, cin, device=DEV) * 0.05).bfloat16()
+    res = []
+    for persistent in (True, False):
+        ops.native().set_persistent_gemm(persistent)
+        st = torch.zeros(2 * cout, device=DEV)
+        y = ops.conv3x3(x, wt, st)
+        res.append((y, st))
+    assert torch.equal(res[0][0], res[1][0])
+    assert _rel(res[0][1], res[1][1]) < 1e-4
+    ref = F.conv2d(x.float(), wt.permute(0, 3, 1, 2).float(), None, 1, 1)
+    assert _rel(res[0][0], ref) < 1e-2
+    if cin <= 64 or cin % 128 == 0:
+        dy = torch.randn_like(res[0][0])
+        dxs = []
+        for persistent in (True, False):
+            ops.native().set_persistent_gemm(persistent)
+            dx = torch.empty_like(x)
+            ops.native().conv3x3(dy, wt, dx, True, None)
+            dxs.append(dx)
+        assert torch.equal(dxs[0], dxs[1])
