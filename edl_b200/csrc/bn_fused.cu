@@ -182,11 +182,8 @@ bn_fwd_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
   });
   reduce_groups<16>(acc, cvecs, s.scratch);
   if (tid < cvecs) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sums[tid * 8 + i], acc[i]);
-      atomicAdd(&sums[C + tid * 8 + i], acc[8 + i]);
-    }
+    red_add8(&sums[tid * 8], acc);
+    red_add8(&sums[C + tid * 8], acc + 8);
   }
   grid_barrier(sync_counter, gridDim.x);
   const int64_t M = L.total / C;
@@ -292,11 +289,8 @@ bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
   });
   reduce_groups<16>(acc, cvecs, s.scratch);
   if (tid < cvecs) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&dsums[tid * 8 + i], acc[i]);
-      atomicAdd(&dsums[C + tid * 8 + i], acc[8 + i]);
-    }
+    red_add8(&dsums[tid * 8], acc);
+    red_add8(&dsums[C + tid * 8], acc + 8);
   }
   grid_barrier(sync_counter, gridDim.x);
   const float inv_m = 1.f / (float)(L.total / C);
