@@ -263,55 +263,72 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         ptx::tma_store_commit();
       }
       if (p.col_stats != nullptr) {
-        // 256 threads, BLOCK_N columns: kSplit threads share a column, each sums an interleaved row subset
-        constexpr int kSplit = kEpiThreads / BLOCK_N;          // 2 (N=128) or 4 (N=64)
-        const int col = et % BLOCK_N;
-        const int part = et / BLOCK_N;
+        // Per-channel sum / sum of squares of the STORED bf16 values, from the staged tile.  A thread owns
+        // a PAIR of adjacent columns (one 32-bit shared load per row) and every kSplit-th row; eight
+        // independent loads are in flight per thread (the naive one-column, one-accumulator loop was the
+        // bottleneck of short-K tiles: ~1 us of exposed LDS latency per tile, profiles/prof_persist_fwd).
+        constexpr int kPairs = BLOCK_N / 2;                    // 64 (N=128) or 32 (N=64)
+        constexpr int kSplit = kEpiThreads / kPairs;           // 4 or 8 row subsets
+        const int pair = et % kPairs;
+        const int part = et / kPairs;
+        const int col = pair * 2;
         const bool valid = n0 + col < p.N;
         const int half = col >> 6, cc = col & 63, chunk = cc >> 3, within = cc & 7;
         const uint8_t* base = sd + half * (kBlockM * 128) + within * 2;
-        float s = 0.f, sq = 0.f;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        auto accum_rows = [&](int r_begin, int r_end) {
+          int rr = r_begin + part;
+          for (; rr + 7 * kSplit < r_end; rr += 8 * kSplit) {
+            uint32_t w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int r = rr + u * kSplit;
+              w[u] = *reinterpret_cast<const uint32_t*>(base + r * 128 + ((chunk ^ (r & 7)) << 4));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[u]));
+              s0 += v.x; q0 = fmaf(v.x, v.x, q0);
+              s1 += v.y; q1 = fmaf(v.y, v.y, q1);
+            }
+          }
+          for (; rr < r_end; rr += kSplit) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+            s0 += v.x; q0 = fmaf(v.x, v.x, q0);
+            s1 += v.y; q1 = fmaf(v.y, v.y, q1);
+          }
+        };
         if (valid) {
           if (!kConv) {
             int rows_valid = p.M - m0;
             if (rows_valid > kBlockM) rows_valid = kBlockM;
-            for (int rr = part; rr < rows_valid; rr += kSplit) {
-              const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
-                  base + rr * 128 + ((chunk ^ (rr & 7)) << 4)));
-              s += v;
-              sq = fmaf(v, v, sq);
-            }
+            accum_rows(0, rows_valid);
           } else {
             const int rows_per_img = p.BH * p.W;
             int hv = p.H - h0;
             if (hv > p.BH) hv = p.BH;
-            for (int b = 0; b < p.BN && img0 + b < p.n_img; ++b) {
-              const int r_begin = b * rows_per_img, r_end = r_begin + hv * p.W;
-              for (int rr = r_begin + part; rr < r_end; rr += kSplit) {
-                const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
-                    base + rr * 128 + ((chunk ^ (rr & 7)) << 4)));
-                s += v;
-                sq = fmaf(v, v, sq);
-              }
-            }
+            for (int b = 0; b < p.BN && img0 + b < p.n_img; ++b) accum_rows(b * rows_per_img, b * rows_per_img + hv * p.W);
           }
         }
-        // four neighbouring columns of one row subset -> one vector reduction
-        const float s1 = __shfl_down_sync(0xffffffffu, s, 1), s2 = __shfl_down_sync(0xffffffffu, s, 2),
-                    s3 = __shfl_down_sync(0xffffffffu, s, 3);
-        const float q1 = __shfl_down_sync(0xffffffffu, sq, 1), q2 = __shfl_down_sync(0xffffffffu, sq, 2),
-                    q3 = __shfl_down_sync(0xffffffffu, sq, 3);
+        // lanes 2i, 2i+1 hold four neighbouring columns -> one vector reduction each for sum and sum^2
+        const float s2 = __shfl_down_sync(0xffffffffu, s0, 1), s3 = __shfl_down_sync(0xffffffffu, s1, 1);
+        const float q2 = __shfl_down_sync(0xffffffffu, q0, 1), q3 = __shfl_down_sync(0xffffffffu, q1, 1);
         const int c4 = col & ~3;
         float* ps4 = &p.col_stats[n0 + c4];
         const bool vec = (p.N % 4 == 0) && n0 + c4 + 3 < p.N && ((reinterpret_cast<uintptr_t>(ps4) & 15) == 0);
         if (vec) {
-          if ((col & 3) == 0) {
-            red_add_v4(ps4, s, s1, s2, s3);
-            red_add_v4(ps4 + p.N, sq, q1, q2, q3);
+          if ((pair & 1) == 0) {
+            red_add_v4(ps4, s0, s1, s2, s3);
+            red_add_v4(ps4 + p.N, q0, q1, q2, q3);
           }
         } else if (valid) {
-          atomicAdd(&p.col_stats[n0 + col], s);
-          atomicAdd(&p.col_stats[p.N + n0 + col], sq);
+          atomicAdd(&p.col_stats[n0 + col], s0);
+          atomicAdd(&p.col_stats[p.N + n0 + col], q0);
+          if (n0 + col + 1 < p.N) {
+            atomicAdd(&p.col_stats[n0 + col + 1], s1);
+            atomicAdd(&p.col_stats[p.N + n0 + col + 1], q1);
+          }
         }
       }
     }

@@ -133,9 +133,13 @@ class ElasticDataParallel:
                     need += (p.numel() + 256) * p.element_size()
             need += 4 << 20
             self.pool = SymmetricPool(need, group=group, device=self.device)
+        if self.device.type == "cuda" and getattr(self, "comm_stream", None) is None:
+            # all-reduce kernels: high priority (few CTAs, on the critical path of the optimizer step);
+            # weight-gradient kernels: LOW priority -- they only have to finish before their bucket is
+            # reduced, and must not take SMs from the dgrad / BN-backward chain of the main stream
             self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
-        elif self.device.type == "cuda":
-            self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+            self.wgrad_stream = torch.cuda.Stream(device=self.device, priority=0)
+            self._main_stream = None
 
     def _grad_alloc(self, numel, dtype, device):
         sl = self.pool.alloc(numel, dtype)
@@ -204,10 +208,13 @@ class ElasticDataParallel:
             sl = self.slices[b.dtype]
             esz = g.grad.element_size()
             off = b.start * esz
-            cur = torch.cuda.current_stream(self.device)
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            self.comm_stream.wait_event(ev)
+            # the bucket's gradients were written on the main stream (BN, pools, ...) and on the
+            # weight-gradient stream: the reduction waits for both
+            for st in {torch.cuda.current_stream(self.device), self._main_stream, self.wgrad_stream}:
+                if st is not None and st != self.comm_stream:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    self.comm_stream.wait_event(ev)
             with torch.cuda.stream(self.comm_stream):
                 native().allreduce_twoshot(
                     [p + off for p in sl.data_ptrs], sl.sig_ptrs, (sl.mc_ptr + off) if sl.mc_ptr else 0,
@@ -233,7 +240,9 @@ class ElasticDataParallel:
         self._launch_ready()
         if self.device.type == "cuda" and (self.world > 1 or self.overlap_wgrad):
             if self.use_symm or self.overlap_wgrad:
-                torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_stream(self.comm_stream)
+                cur.wait_stream(self.wgrad_stream)
                 from ..ops import gemm as _gemm
                 _gemm.release_wgrad_keepalive()
             for w, view, scale in self._works:
@@ -259,9 +268,10 @@ class ElasticDataParallel:
             # the zeroing memsets run on the main stream: the side stream must not start writing
             # gradients before them
             self.flat.zero_grad()
+            self._main_stream = torch.cuda.current_stream(self.device)
             if self.overlap_wgrad:
-                self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
-                _gemm.set_wgrad_stream(self.comm_stream)
+                self.wgrad_stream.wait_stream(self._main_stream)
+                _gemm.set_wgrad_stream(self.wgrad_stream)
             else:
                 _gemm.set_wgrad_stream(None)
             if self.found_inf is not None:

@@ -121,7 +121,9 @@ class StudentTrainer:
         """Warm up on a side stream (cuDNN autotune, allocator) then capture the step graph."""
         if not self.use_graph:
             return
-        s = torch.cuda.Stream(device=self.device)
+        # the step is captured on a HIGH-priority stream: its kernels are the critical chain, the
+        # weight-gradient side stream (parallel/ddp.py) runs at low priority underneath it
+        s = torch.cuda.Stream(device=self.device, priority=-1)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             for _ in range(warmup):
@@ -132,7 +134,7 @@ class StudentTrainer:
             dist.barrier(self.dp.group)
         self.graph = torch.cuda.CUDAGraph()
         before = ops.launches()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=s):
             self._step_body()
         self.launches_per_step = ops.launches() - before
         torch.cuda.synchronize(self.device)
