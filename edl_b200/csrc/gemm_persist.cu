@@ -241,14 +241,16 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         const int half = cbase >> 6;
-        uint8_t* rowp = sd + half * (kBlockM * 128) + row * 128;
+        const uint32_t rowp = ptx::smem_u32(sd) + half * (kBlockM * 128) + row * 128;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int chunk = ((cbase >> 5) & 1) * 4 + c;
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = f[c * 8 + j];
-          st_vec(rowp + ((chunk ^ (row & 7)) << 4), pack8(v));
+          const bf16x8 pk = pack8(v);
+          const uint4 u = *reinterpret_cast<const uint4*>(&pk);
+          ptx::sts128(rowp + ((chunk ^ (row & 7)) << 4), u.x, u.y, u.z, u.w);
         }
       }
       ptx::fence_proxy_async_smem();
@@ -274,7 +276,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int col = pair * 2;
         const bool valid = n0 + col < p.N;
         const int half = col >> 6, cc = col & 63, chunk = cc >> 3, within = cc & 7;
-        const uint8_t* base = sd + half * (kBlockM * 128) + within * 2;
+        const uint32_t base = ptx::smem_u32(sd) + half * (kBlockM * 128) + within * 2;
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
         auto accum_rows = [&](int r_begin, int r_end) {
           int rr = r_begin + part;
@@ -283,7 +285,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int r = rr + u * kSplit;
-              w[u] = *reinterpret_cast<const uint32_t*>(base + r * 128 + ((chunk ^ (r & 7)) << 4));
+              w[u] = ptx::lds32(base + r * 128 + ((chunk ^ (r & 7)) << 4));
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -293,7 +295,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           for (; rr < r_end; rr += kSplit) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+            const uint32_t w = ptx::lds32(base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
             const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
             s0 += v.x; q0 = fmaf(v.x, v.x, q0);
             s1 += v.y; q1 = fmaf(v.y, v.y, q1);

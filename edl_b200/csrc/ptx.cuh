@@ -44,6 +44,16 @@ EDL_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// shared-memory accesses by 32-bit shared address (no generic-pointer 64-bit address arithmetic)
+EDL_DEVICE uint32_t lds32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+EDL_DEVICE void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ---------------------------------------------------------------- TMA
 EDL_DEVICE void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -140,6 +140,7 @@ class ElasticDataParallel:
             self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
             self.wgrad_stream = torch.cuda.Stream(device=self.device, priority=0)
             self._main_stream = None
+            self._comm_used = False
 
     def _grad_alloc(self, numel, dtype, device):
         sl = self.pool.alloc(numel, dtype)
@@ -210,11 +211,13 @@ class ElasticDataParallel:
             off = b.start * esz
             # the bucket's gradients were written on the main stream (BN, pools, ...) and on the
             # weight-gradient stream: the reduction waits for both
-            for st in {torch.cuda.current_stream(self.device), self._main_stream, self.wgrad_stream}:
+            for st in {torch.cuda.current_stream(self.device), self._main_stream,
+                       self.wgrad_stream if self.overlap_wgrad else None}:
                 if st is not None and st != self.comm_stream:
                     ev = torch.cuda.Event()
                     ev.record(st)
                     self.comm_stream.wait_event(ev)
+            self._comm_used = True
             with torch.cuda.stream(self.comm_stream):
                 native().allreduce_twoshot(
                     [p + off for p in sl.data_ptrs], sl.sig_ptrs, (sl.mc_ptr + off) if sl.mc_ptr else 0,
@@ -241,8 +244,12 @@ class ElasticDataParallel:
         if self.device.type == "cuda" and (self.world > 1 or self.overlap_wgrad):
             if self.use_symm or self.overlap_wgrad:
                 cur = torch.cuda.current_stream(self.device)
-                cur.wait_stream(self.comm_stream)
-                cur.wait_stream(self.wgrad_stream)
+                # only streams that took part in this step (a stream without forked work is not part
+                # of a CUDA-graph capture and must not be joined into it)
+                if self._comm_used:
+                    cur.wait_stream(self.comm_stream)
+                if self.overlap_wgrad:
+                    cur.wait_stream(self.wgrad_stream)
                 from ..ops import gemm as _gemm
                 _gemm.release_wgrad_keepalive()
             for w, view, scale in self._works:
@@ -269,6 +276,7 @@ class ElasticDataParallel:
             # gradients before them
             self.flat.zero_grad()
             self._main_stream = torch.cuda.current_stream(self.device)
+            self._comm_used = False
             if self.overlap_wgrad:
                 self.wgrad_stream.wait_stream(self._main_stream)
                 _gemm.set_wgrad_stream(self.wgrad_stream)
