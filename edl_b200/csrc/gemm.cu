@@ -540,6 +540,7 @@ const char* gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   const bool n64 = g.N <= 64;
   if (g.out_f32 == nullptr && !g.a_mn_major && g.ship_flag == nullptr && persistent_gemm_enabled())
     return gemm_bf16_persistent(g, stream);
+  if (g.add_src != nullptr) return "gemm add_src is implemented by the persistent kernel only";
   if (g.out_f32 != nullptr) {
     // split-K fp32 accumulation (wgrad): both operands MN-major or both K-major
     if (g.a_mn_major && g.b_mn_major)

@@ -27,6 +27,10 @@ struct GemmArgs {
   int* tile_counters = nullptr;       // >= ceil(M/128)*ceil(N/BLOCK_N) zero-initialised ints
   bool accumulate_out = false;
   int device = -1;                    // CUDA device ordinal of the operands (binds the context)
+  // D = A*B + add_src (bf16 [M, N], row pitch ld_add): fuses the gradient accumulation of a tensor with two
+  // consumers (residual branch + 1x1 conv) into the dgrad epilogue.  Persistent kernel only.
+  const void* add_src = nullptr;
+  int64_t ld_add = 0;
   // fused "GEMM -> peer ship" (EPI 0 only): D may be a PEER GPU's buffer (NVLink-mapped address);
   // every CTA TMA-stores its tile there, and the CTA that completes last publishes
   // *ship_flag (peer address) = seq with release/system semantics -- no separate copy kernel.

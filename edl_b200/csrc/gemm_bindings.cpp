@@ -20,7 +20,8 @@ void gemm_bf16(const Tensor& A, const Tensor& B, const c10::optional<Tensor>& D,
                const c10::optional<Tensor>& col_shift, bool relu,
                const c10::optional<Tensor>& col_stats, const c10::optional<Tensor>& out_f32,
                int64_t split_k, const c10::optional<Tensor>& out_bf16,
-               const c10::optional<Tensor>& tile_counters, bool accumulate_out) {
+               const c10::optional<Tensor>& tile_counters, bool accumulate_out,
+               const c10::optional<Tensor>& add_src) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.dim() == 2 && B.dim() == 2);
   TORCH_CHECK(A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16);
   TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1, "operands need a contiguous last dim");
@@ -65,6 +66,12 @@ void gemm_bf16(const Tensor& A, const Tensor& B, const c10::optional<Tensor>& D,
   g.col_shift = optp<float>(col_shift);
   g.relu = relu;
   g.col_stats = optp<float>(col_stats);
+  if (add_src.has_value() && add_src->defined()) {
+    TORCH_CHECK(add_src->scalar_type() == at::kBFloat16 && add_src->dim() == 2 && add_src->stride(1) == 1);
+    TORCH_CHECK(add_src->size(0) == g.M && add_src->size(1) == g.N);
+    g.add_src = add_src->data_ptr();
+    g.ld_add = add_src->stride(0);
+  }
   g.device = A.device().index();
   c10::cuda::CUDAGuard guard(A.device());
   const char* err = edl::gemm_bf16(g, at::cuda::getCurrentCUDAStream().stream());

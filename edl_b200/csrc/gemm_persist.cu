@@ -31,6 +31,11 @@ constexpr int kUmmaK = 16;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;   // 320
 constexpr int kEpiThreads = kEpiWarps * 32;     // 256
+// BatchNorm statistics are accumulated per CTA in shared memory over ALL the tiles it processes and
+// pushed to global memory once at the end: with one reduction request per tile and column group the
+// L2 retires ~12 requests/ns into the few hot lines, which made the 1568-tile 1x1 convs atomic-bound
+// (400k requests = 33 us; profiles/prof_persist_fwd2).  N <= kMaxStatsN, else direct reductions.
+constexpr int kMaxStatsN = 2048;
 
 struct PersistParams {
   // GEMM view
@@ -41,6 +46,8 @@ struct PersistParams {
   const float* col_shift;
   int relu;
   float* col_stats;
+  const __nv_bfloat16* add_src;   // optional addend tile source (GEMM modes)
+  long long ld_add;
   // conv view (modes 2, 3)
   int n_img, H, W, kc_blocks, c_in_w, BH, BN, tiles_h;
 };
@@ -52,7 +59,9 @@ struct PSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kDBytes = kBlockM * BLOCK_N * 2;
   static constexpr int kRingBytes = STAGES * kStageBytes;
-  static constexpr int kBarOffset = kRingBytes + kDBytes;
+  static constexpr int kStatsBytes = 2 * kMaxStatsN * 4;   // CTA-local per-channel (sum, sum^2) accumulators
+  static constexpr int kStatsOffset = kRingBytes + kDBytes;
+  static constexpr int kBarOffset = kStatsOffset + kStatsBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;
 };
 
@@ -76,6 +85,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sd = smem + L::kRingBytes;                    // dedicated store-staging tile
+  float* sstats = reinterpret_cast<float*>(smem + L::kStatsOffset);
+  const bool local_stats = p.col_stats != nullptr && p.N <= kMaxStatsN;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;              // [2]
@@ -102,6 +113,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  if (local_stats)
+    for (int i = threadIdx.x; i < 2 * p.N; i += kThreads) sstats[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -202,6 +215,19 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // the staging tile must have been read by the previous TMA store and by every stats thread
       if (et == 0) ptx::tma_store_wait_read0();
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      // addend (if any): fetch this thread's row segment while the MMAs of the tile are still running
+      uint4 addv[kColsPerGrp / 32][4];
+      const bool has_add = !kConv && p.add_src != nullptr && m0 + row < p.M;
+      if (has_add) {
+        const __nv_bfloat16* ap = p.add_src + (long long)(m0 + row) * p.ld_add + n0 + grp * kColsPerGrp;
+#pragma unroll
+        for (int c32 = 0; c32 < kColsPerGrp / 32; ++c32)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int col = n0 + grp * kColsPerGrp + c32 * 32 + c * 8;
+            addv[c32][c] = col + 7 < p.N ? *reinterpret_cast<const uint4*>(ap + c32 * 32 + c * 8) : make_uint4(0, 0, 0, 0);
+          }
+      }
       ptx::mbar_wait(&tmem_full[slot], aph);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + slot * BLOCK_N + grp * kColsPerGrp + ((uint32_t)(q * 32) << 16);
@@ -220,6 +246,19 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(rg[j]);
+        if (has_add) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 u = addv[c32][c];
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]));
+              f[c * 8 + 2 * j] += t2.x;
+              f[c * 8 + 2 * j + 1] += t2.y;
+            }
+          }
+        }
         if (!kConv) {
           if (p.col_scale != nullptr) {
 #pragma unroll
@@ -313,25 +352,50 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int b = 0; b < p.BN && img0 + b < p.n_img; ++b) accum_rows(b * rows_per_img, b * rows_per_img + hv * p.W);
           }
         }
-        // lanes 2i, 2i+1 hold four neighbouring columns -> one vector reduction each for sum and sum^2
-        const float s2 = __shfl_down_sync(0xffffffffu, s0, 1), s3 = __shfl_down_sync(0xffffffffu, s1, 1);
-        const float q2 = __shfl_down_sync(0xffffffffu, q0, 1), q3 = __shfl_down_sync(0xffffffffu, q1, 1);
-        const int c4 = col & ~3;
-        float* ps4 = &p.col_stats[n0 + c4];
-        const bool vec = (p.N % 4 == 0) && n0 + c4 + 3 < p.N && ((reinterpret_cast<uintptr_t>(ps4) & 15) == 0);
-        if (vec) {
-          if ((pair & 1) == 0) {
-            red_add_v4(ps4, s0, s1, s2, s3);
-            red_add_v4(ps4 + p.N, q0, q1, q2, q3);
+        if (local_stats) {
+          if (valid) {
+            atomicAdd(&sstats[n0 + col], s0);
+            atomicAdd(&sstats[p.N + n0 + col], q0);
+            if (n0 + col + 1 < p.N) {
+              atomicAdd(&sstats[n0 + col + 1], s1);
+              atomicAdd(&sstats[p.N + n0 + col + 1], q1);
+            }
           }
-        } else if (valid) {
-          atomicAdd(&p.col_stats[n0 + col], s0);
-          atomicAdd(&p.col_stats[p.N + n0 + col], q0);
-          if (n0 + col + 1 < p.N) {
-            atomicAdd(&p.col_stats[n0 + col + 1], s1);
-            atomicAdd(&p.col_stats[p.N + n0 + col + 1], q1);
+        } else {
+          // lanes 2i, 2i+1 hold four neighbouring columns -> one vector reduction each for sum and sum^2
+          const float s2 = __shfl_down_sync(0xffffffffu, s0, 1), s3 = __shfl_down_sync(0xffffffffu, s1, 1);
+          const float q2 = __shfl_down_sync(0xffffffffu, q0, 1), q3 = __shfl_down_sync(0xffffffffu, q1, 1);
+          const int c4 = col & ~3;
+          float* ps4 = &p.col_stats[n0 + c4];
+          const bool vec = (p.N % 4 == 0) && n0 + c4 + 3 < p.N && ((reinterpret_cast<uintptr_t>(ps4) & 15) == 0);
+          if (vec) {
+            if ((pair & 1) == 0) {
+              red_add_v4(ps4, s0, s1, s2, s3);
+              red_add_v4(ps4 + p.N, q0, q1, q2, q3);
+            }
+          } else if (valid) {
+            atomicAdd(&p.col_stats[n0 + col], s0);
+            atomicAdd(&p.col_stats[p.N + n0 + col], q0);
+            if (n0 + col + 1 < p.N) {
+              atomicAdd(&p.col_stats[n0 + col + 1], s1);
+              atomicAdd(&p.col_stats[p.N + n0 + col + 1], q1);
+            }
           }
         }
+      }
+    }
+    if (local_stats) {
+      // one flush per CTA: only the column groups this CTA touched are non-zero
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const bool vec_ok = (p.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.col_stats) & 15) == 0);
+      if (vec_ok) {
+        for (int i = et * 4; i < 2 * p.N; i += kEpiThreads * 4) {
+          const float4 v = *reinterpret_cast<const float4*>(&sstats[i]);
+          if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_v4(&p.col_stats[i], v.x, v.y, v.z, v.w);
+        }
+      } else {
+        for (int i = et; i < 2 * p.N; i += kEpiThreads)
+          if (sstats[i] != 0.f) atomicAdd(&p.col_stats[i], sstats[i]);
       }
     }
     if (et == 0) ptx::tma_store_wait_read0();
@@ -397,6 +461,10 @@ const char* gemm_bf16_persistent(const GemmArgs& g, cudaStream_t stream) {
   p.num_kb = (g.K + kBlockK - 1) / kBlockK;
   p.col_scale = g.col_scale; p.col_shift = g.col_shift; p.relu = g.relu ? 1 : 0;
   p.col_stats = g.col_stats;
+  p.add_src = reinterpret_cast<const __nv_bfloat16*>(g.add_src);
+  p.ld_add = g.ld_add;
+  if (g.add_src != nullptr && (g.N % 8 != 0 || g.ld_add % 8 != 0 || (reinterpret_cast<uintptr_t>(g.add_src) & 15) != 0))
+    return "gemm add_src needs N % 8 == 0 and 16-byte aligned rows";
   if (!g.b_mn_major)
     return n64 ? launch_p<64, 6, 0>(tmA, tmB, tmD, p, stream) : launch_p<128, 5, 0>(tmA, tmB, tmD, p, stream);
   return n64 ? launch_p<64, 6, 1>(tmA, tmB, tmD, p, stream) : launch_p<128, 5, 1>(tmA, tmB, tmD, p, stream);

@@ -43,13 +43,13 @@ class ConvBNAct(nn.Module):
         return (self.k == 1 and self.stride == 1 and self.groups == 1 and x.is_cuda
                 and x.dtype == torch.bfloat16 and self.cin % 8 == 0 and self.cout % 8 == 0)
 
-    def conv(self, x, want_stats):
+    def conv(self, x, want_stats, fork=False):
         if self._use_gemm(x):
             stats = None
             if want_stats:
                 stats = self.fwd_stats if self.fwd_stats is not None else torch.zeros(
                     2 * self.cout, device=x.device, dtype=torch.float32)
-            return ops.conv1x1(x, self.weight, stats), stats
+            return ops.conv1x1(x, self.weight, stats, fork=fork), stats
         if (self.k == 3 and self.stride == 1 and self.groups == 1 and self.impl != "cudnn" and self.own_conv3
                 and ops.conv3x3_supported(x, self.weight)):
             # own tcgen05 implicit-GEMM 3x3 (csrc/conv3x3.cu) with the BN statistics in its epilogue
@@ -65,11 +65,20 @@ class ConvBNAct(nn.Module):
         y = F.conv2d(x, w, None, self.stride, (self.k - 1) // 2, 1, self.groups)
         return y, None
 
-    def forward(self, x, residual=None):
-        y, stats = self.conv(x, self.training)
+    def can_fork(self, x):
+        """True if forward(x, fork=True) can hand back an alias of ``x`` whose gradient is summed inside
+        this convolution's dgrad epilogue (tcgen05 1x1 path, training)."""
+        return self._use_gemm(x) and torch.is_grad_enabled() and x.requires_grad
+
+    def forward(self, x, residual=None, fork=False):
+        y, stats = self.conv(x, self.training, fork)
+        xa = None
+        if fork:
+            y, xa = y
         # stats is None for library convs: the BN op then computes them itself (SM-resident fused
         # kernel when the tensor fits, else the streaming stats kernel into its arena slice)
-        return self.bn(y, residual=residual, sums=stats)
+        out = self.bn(y, residual=residual, sums=stats)
+        return (out, xa) if fork else out
 
 
 class Bottleneck(nn.Module):
@@ -88,12 +97,17 @@ class Bottleneck(nn.Module):
                                    impl=impl)
 
     def forward(self, x):
+        # x has two consumers (conv a and the shortcut): route the shortcut through the alias returned by
+        # conv a so that both gradients are summed in a's dgrad epilogue
+        if self.a.can_fork(x):
+            y, xs = self.a(x, fork=True)
+        else:
+            y, xs = self.a(x), x
         if self.short is not None:
-            s = ops.avg_pool_2x2(x) if self.pool else x
+            s = ops.avg_pool_2x2(xs) if self.pool else xs
             s = self.short(s)
         else:
-            s = x
-        y = self.a(x)
+            s = xs
         y = self.b(y)
         return self.c(y, residual=s)
 

@@ -16,7 +16,7 @@ _NUM_SMS = 148
 
 def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, col_scale=None, col_shift=None,
               relu=False, col_stats=None, out_f32=None, split_k=1, out_bf16=None, tile_counters=None,
-              accumulate_out=False):
+              accumulate_out=False, add=None):
     """D = op(A) @ op(B): see csrc/gemm.h for the operand conventions.
 
     default        : A [M, K], B [N, K]  -> D [M, N] = A @ B^T
@@ -24,7 +24,8 @@ def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, col_scale=None
     a_mn_major     : A [K, M]            -> D = A^T @ op(B)
     out_f32 given  : fp32 [M, N] += result, split over K across CTAs (no bf16 output).
     out_bf16 given : (with out_f32 as an all-zero workspace) the last CTA of every output tile writes
-                     bf16(result) (+= if accumulate_out) into out_bf16 and re-zeroes the workspace."""
+                     bf16(result) (+= if accumulate_out) into out_bf16 and re-zeroes the workspace.
+    add given      : D = result + add (bf16 [M, N]) in the epilogue (gradient accumulation fused into dgrad)."""
     from . import native, count_launch
 
     m = a.shape[1] if a_mn_major else a.shape[0]
@@ -35,6 +36,8 @@ def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, col_scale=None
         af = a.float().t() if a_mn_major else a.float()
         bf = b.float() if b_mn_major else b.float().t()
         d = af @ bf
+        if add is not None:
+            d = d + add.float()
         if out_bf16 is not None:
             out_bf16.copy_((out_bf16.float() + d) if accumulate_out else d)
             return out_bf16
@@ -57,8 +60,16 @@ def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, col_scale=None
         return d
     if out_f32 is None and out is None:
         out = torch.empty((m, n), device=a.device, dtype=torch.bfloat16)
+    if add is not None and not (native().persistent_gemm_enabled() and n % 8 == 0 and add.stride(-1) == 1
+                                and add.stride(0) % 8 == 0 and add.data_ptr() % 16 == 0 and out_f32 is None):
+        # the fused addend lives in the persistent kernel's epilogue; otherwise one extra elementwise pass
+        native().gemm_bf16(a, b, out, a_mn_major, b_mn_major, col_scale, col_shift, relu, col_stats,
+                           out_f32, int(split_k), out_bf16, tile_counters, bool(accumulate_out), None)
+        count_launch()
+        out.add_(add)
+        return out
     native().gemm_bf16(a, b, out, a_mn_major, b_mn_major, col_scale, col_shift, relu, col_stats,
-                       out_f32, int(split_k), out_bf16, tile_counters, bool(accumulate_out))
+                       out_f32, int(split_k), out_bf16, tile_counters, bool(accumulate_out), add)
     count_launch()
     if out_bf16 is not None:
         return out_bf16
@@ -159,8 +170,12 @@ def _wgrad_impl(dy2, x2, weight_shape, sink, ready, cout, cin, split):
 
 
 class _Conv1x1Fn(torch.autograd.Function):
+    """``fork=True`` also returns the input as a second output: a tensor that feeds this convolution AND a
+    second consumer (the residual branch) then receives ONE gradient, summed inside the dgrad epilogue,
+    instead of two gradients that autograd adds with an extra elementwise kernel."""
+
     @staticmethod
-    def forward(ctx, x, w, stats, sink, ready):
+    def forward(ctx, x, w, stats, sink, ready, fork=False):
         x = _cl(x)
         n, cin, h, wd = x.shape
         cout = w.shape[0]
@@ -172,11 +187,15 @@ class _Conv1x1Fn(torch.autograd.Function):
         gemm_bf16(x2, w2, out=y2, col_stats=stats)
         ctx.save_for_backward(x, w)
         ctx.sink, ctx.ready = sink, ready
+        if fork:
+            return y, x.view_as(x)
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dfork=None):
         x, w = ctx.saved_tensors
+        if dy is None:      # only the forked alias was used downstream
+            return dfork, None, None, None, None, None
         dy = _cl(dy)
         n, cin, h, wd = x.shape
         cout = w.shape[0]
@@ -186,18 +205,21 @@ class _Conv1x1Fn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            gemm_bf16(dy2, w2, out=dx.permute(0, 2, 3, 1).reshape(-1, cin), b_mn_major=True)
+            add = None
+            if dfork is not None:
+                add = _cl(dfork).permute(0, 2, 3, 1).reshape(-1, cin)
+            gemm_bf16(dy2, w2, out=dx.permute(0, 2, 3, 1).reshape(-1, cin), b_mn_major=True, add=add)
         dw = _wgrad(dy2, x2, w.shape, ctx.sink, ctx.ready) if ctx.needs_input_grad[1] else None
-        return dx, dw, None, None, None
+        return dx, dw, None, None, None, None
 
 
-def conv1x1(x, weight, stats: Optional[torch.Tensor] = None):
+def conv1x1(x, weight, stats: Optional[torch.Tensor] = None, fork: bool = False):
     """NHWC 1x1 stride-1 convolution as a tcgen05 GEMM.  ``weight``: [Cout, 1, 1, Cin] or
     [Cout, Cin] bf16.  If ``stats`` (pre-zeroed fp32 [2*Cout]) is given, the epilogue accumulates
     per-channel sum / sum-of-squares of the output for the following train-mode BatchNorm."""
     sink = getattr(weight, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
     ready = getattr(weight, "_edl_grad_ready", None) if sink is not None else None
-    return _Conv1x1Fn.apply(x, weight, stats, sink, ready)
+    return _Conv1x1Fn.apply(x, weight, stats, sink, ready, fork)
 
 
 class _LinearFn(torch.autograd.Function):

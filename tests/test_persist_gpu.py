@@ -76,3 +76,26 @@ def test_persistent_conv3x3_matches_tile_kernel(n, cin, cout, h, w):
             ops.native().conv3x3(dy, wt, dx, True, None)
             dxs.append(dx)
         assert torch.equal(dxs[0], dxs[1])
+
+
+def test_conv1x1_fork_sums_both_gradients_in_the_dgrad_epilogue():
+    torch.manual_seed(3)
+    x = torch.randn(8, 256, 14, 14, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = (torch.randn(64, 1, 1, 256, device=DEV) * 0.05).bfloat16().requires_grad_(True)
+    r = torch.randn(8, 256, 14, 14, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(8, 64, 14, 14, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    y, xa = ops.conv1x1(x, w, None, fork=True)
+    torch.autograd.backward([y, xa], [dy, r])
+    xr = x.detach().float().requires_grad_(True)
+    wr = w.detach().float().requires_grad_(True)
+    yr = F.conv2d(xr, wr.view(64, 256, 1, 1))
+    torch.autograd.backward([yr, xr * 1.0], [dy.float(), r.float()])
+    assert _rel(x.grad, xr.grad) < 1e-2
+    assert _rel(w.grad, wr.grad.view_as(w)) < 1e-2
+    # alias unused downstream: plain dgrad
+    x2 = x.detach().clone().requires_grad_(True)
+    y2, _ = ops.conv1x1(x2, w, None, fork=True)
+    y2.backward(dy)
+    xr2 = x.detach().float().requires_grad_(True)
+    F.conv2d(xr2, wr.detach().view(64, 256, 1, 1)).backward(dy.float())
+    assert _rel(x2.grad, xr2.grad) < 1e-2
