@@ -76,7 +76,8 @@ EDL_DEVICE void tma_store_4d_p(const CUtensorMap* m, const void* smem_src, int c
 template <int BLOCK_N, int STAGES, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmD, const PersistParams p) {
+                    const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
+                    const PersistParams p) {
   using L = PSmem<BLOCK_N, STAGES>;
   constexpr bool kConv = MODE >= 2;
   constexpr bool kBMN = MODE == 1 || MODE == 3;
@@ -91,7 +92,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;              // [2]
   uint64_t* tmem_empty = tmem_full + 2;                  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* add_bar = tmem_empty + 2;                    // addend tile landed in the staging buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(add_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,6 +112,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::mbar_init(&tmem_full[a], 1);
       ptx::mbar_init(&tmem_empty[a], kEpiWarps);
     }
+    ptx::mbar_init(add_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_slot);
@@ -215,18 +218,20 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // the staging tile must have been read by the previous TMA store and by every stats thread
       if (et == 0) ptx::tma_store_wait_read0();
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      // addend (if any): fetch this thread's row segment while the MMAs of the tile are still running
-      uint4 addv[kColsPerGrp / 32][4];
-      const bool has_add = !kConv && p.add_src != nullptr && m0 + row < p.M;
+      // addend (if any): TMA-load its tile into the staging buffer (same swizzled layout as the output)
+      // while the MMAs of this tile are still running; every thread later adds its own 16-byte pieces
+      const bool has_add = !kConv && p.add_src != nullptr;
       if (has_add) {
-        const __nv_bfloat16* ap = p.add_src + (long long)(m0 + row) * p.ld_add + n0 + grp * kColsPerGrp;
+        if (et == 0) {
+          uint32_t halves = 0;
 #pragma unroll
-        for (int c32 = 0; c32 < kColsPerGrp / 32; ++c32)
+          for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) halves += (n0 + hh * 64 < p.N) ? 1u : 0u;
+          ptx::mbar_arrive_expect_tx(add_bar, halves * (kBlockM * 128));
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int col = n0 + grp * kColsPerGrp + c32 * 32 + c * 8;
-            addv[c32][c] = col + 7 < p.N ? *reinterpret_cast<const uint4*>(ap + c32 * 32 + c * 8) : make_uint4(0, 0, 0, 0);
-          }
+          for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh)
+            if (n0 + hh * 64 < p.N) ptx::tma_load_2d(sd + hh * (kBlockM * 128), &tmAdd, add_bar, n0 + hh * 64, m0);
+        }
+        ptx::mbar_wait(add_bar, tc & 1);
       }
       ptx::mbar_wait(&tmem_full[slot], aph);
       ptx::tc_fence_after();
@@ -247,10 +252,14 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(rg[j]);
         if (has_add) {
+          const uint32_t arow = ptx::smem_u32(sd) + (cbase >> 6) * (kBlockM * 128) + row * 128;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const uint4 u = addv[c32][c];
-            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+            const int chunk = ((cbase >> 5) & 1) * 4 + c;
+            uint32_t w4[4];
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3])
+                         : "r"(arow + ((chunk ^ (row & 7)) << 4)));
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]));
@@ -412,7 +421,7 @@ bool g_persistent = true;
 
 template <int BLOCK_N, int STAGES, int MODE>
 const char* launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const PersistParams& p,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const CUtensorMap* tmAdd = nullptr) {
   using L = PSmem<BLOCK_N, STAGES>;
   auto kern = gemm_persist_kernel<BLOCK_N, STAGES, MODE>;
   static bool attr_set = false;
@@ -424,7 +433,7 @@ const char* launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   }
   const int total = p.tiles_m * p.tiles_n;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  kern<<<grid, kThreads, L::kTotal, stream>>>(tmA, tmB, tmD, p);
+  kern<<<grid, kThreads, L::kTotal, stream>>>(tmA, tmB, tmD, tmAdd != nullptr ? *tmAdd : tmD, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -463,11 +472,17 @@ const char* gemm_bf16_persistent(const GemmArgs& g, cudaStream_t stream) {
   p.col_stats = g.col_stats;
   p.add_src = reinterpret_cast<const __nv_bfloat16*>(g.add_src);
   p.ld_add = g.ld_add;
-  if (g.add_src != nullptr && (g.N % 8 != 0 || g.ld_add % 8 != 0 || (reinterpret_cast<uintptr_t>(g.add_src) & 15) != 0))
-    return "gemm add_src needs N % 8 == 0 and 16-byte aligned rows";
+  alignas(64) CUtensorMap tmAdd;
+  const CUtensorMap* padd = nullptr;
+  if (g.add_src != nullptr) {
+    if (g.N % 8 != 0 || g.ld_add % 8 != 0 || (reinterpret_cast<uintptr_t>(g.add_src) & 15) != 0)
+      return "gemm add_src needs N % 8 == 0 and 16-byte aligned rows";
+    if (const char* e = tmap2d(&tmAdd, g.add_src, g.N, g.M, g.ld_add, 64, kBlockM)) return e;
+    padd = &tmAdd;
+  }
   if (!g.b_mn_major)
-    return n64 ? launch_p<64, 6, 0>(tmA, tmB, tmD, p, stream) : launch_p<128, 5, 0>(tmA, tmB, tmD, p, stream);
-  return n64 ? launch_p<64, 6, 1>(tmA, tmB, tmD, p, stream) : launch_p<128, 5, 1>(tmA, tmB, tmD, p, stream);
+    return n64 ? launch_p<64, 6, 0>(tmA, tmB, tmD, p, stream, padd) : launch_p<128, 5, 0>(tmA, tmB, tmD, p, stream, padd);
+  return n64 ? launch_p<64, 6, 1>(tmA, tmB, tmD, p, stream, padd) : launch_p<128, 5, 1>(tmA, tmB, tmD, p, stream, padd);
 }
 
 // conv front end: geometry comes from conv3x3.cu's planner
