@@ -5,6 +5,20 @@
 
 namespace edl {
 
+// Fused BatchNorm-backward reduction (persistent dgrad kernels): the GEMM / conv output D is the gradient
+// dy of a BN layer's output; the epilogue accumulates dsums[0:C] += sum(dy_m), dsums[C:2C] += sum(dy_m * xhat)
+// (dy_m = dy masked by the layer's ReLU) so that the BN backward needs no reduction pass of its own.
+struct BnBwdFuse {
+  const void* x = nullptr;       // bf16, BN input (conv output), same shape / layout as D
+  const void* y = nullptr;       // bf16, BN output: only for ReLU after a residual add (mask = y > 0)
+  const float* mean = nullptr;
+  const float* rstd = nullptr;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float* dsums = nullptr;        // fp32 [2C], pre-zeroed
+  bool relu = false;
+};
+
 struct GemmArgs {
   const void* A = nullptr;  // bf16
   const void* B = nullptr;  // bf16
@@ -31,6 +45,7 @@ struct GemmArgs {
   // consumers (residual branch + 1x1 conv) into the dgrad epilogue.  Persistent kernel only.
   const void* add_src = nullptr;
   int64_t ld_add = 0;
+  BnBwdFuse bn;                        // bn.x != nullptr enables the fused BN-backward reduction (row pitch = ldd)
   // fused "GEMM -> peer ship" (EPI 0 only): D may be a PEER GPU's buffer (NVLink-mapped address);
   // every CTA TMA-stores its tile there, and the CTA that completes last publishes
   // *ship_flag (peer address) = seq with release/system semantics -- no separate copy kernel.
@@ -54,6 +69,7 @@ struct Conv3x3Args {
   int N = 0, H = 0, W = 0, Cin = 0, Cout = 0;
   bool dgrad = false;
   float* col_stats = nullptr;  // fwd only: [2*Cout] += per-channel sum / sum of squares of Y
+  BnBwdFuse bn;                // dgrad only: fused BN-backward reduction over Y (= dX)
   int device = -1;
 };
 bool conv3x3_supported(int N, int H, int W, int Cin, int Cout, bool dgrad);

@@ -13,6 +13,31 @@ inline T* optp(const c10::optional<Tensor>& t) {
   return t.has_value() && t->defined() ? reinterpret_cast<T*>(t->data_ptr()) : nullptr;
 }
 
+// bn = [x, y | None, mean, rstd, gamma, beta, dsums] (+ relu flag): see gemm.h BnBwdFuse
+edl::BnBwdFuse parse_bn(const c10::optional<std::vector<c10::optional<Tensor>>>& bn, bool relu, int64_t numel,
+                        int64_t channels) {
+  edl::BnBwdFuse f;
+  if (!bn.has_value()) return f;
+  const auto& v = *bn;
+  TORCH_CHECK(v.size() == 7, "bn fuse list needs 7 entries");
+  TORCH_CHECK(v[0].has_value() && v[0]->scalar_type() == at::kBFloat16 && v[0]->numel() == numel);
+  f.x = v[0]->data_ptr();
+  if (v[1].has_value() && v[1]->defined()) {
+    TORCH_CHECK(v[1]->scalar_type() == at::kBFloat16 && v[1]->numel() == numel);
+    f.y = v[1]->data_ptr();
+  }
+  for (int i = 2; i < 7; ++i)
+    TORCH_CHECK(v[i].has_value() && v[i]->scalar_type() == at::kFloat && v[i]->is_contiguous() &&
+                v[i]->numel() >= (i == 6 ? 2 : 1) * channels, "bn fuse tensor ", i);
+  f.mean = v[2]->data_ptr<float>();
+  f.rstd = v[3]->data_ptr<float>();
+  f.gamma = v[4]->data_ptr<float>();
+  f.beta = v[5]->data_ptr<float>();
+  f.dsums = v[6]->data_ptr<float>();
+  f.relu = relu;
+  return f;
+}
+
 // D[M,N] = A * B with the operand layouts described in gemm.h.  A, B, D are 2-D bf16 tensors whose
 // last dimension is contiguous (row pitch = stride(0)).
 void gemm_bf16(const Tensor& A, const Tensor& B, const c10::optional<Tensor>& D, bool a_mn_major,
@@ -21,7 +46,8 @@ void gemm_bf16(const Tensor& A, const Tensor& B, const c10::optional<Tensor>& D,
                const c10::optional<Tensor>& col_stats, const c10::optional<Tensor>& out_f32,
                int64_t split_k, const c10::optional<Tensor>& out_bf16,
                const c10::optional<Tensor>& tile_counters, bool accumulate_out,
-               const c10::optional<Tensor>& add_src) {
+               const c10::optional<Tensor>& add_src,
+               const c10::optional<std::vector<c10::optional<Tensor>>>& bn, bool bn_relu) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.dim() == 2 && B.dim() == 2);
   TORCH_CHECK(A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16);
   TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1, "operands need a contiguous last dim");
@@ -72,6 +98,10 @@ void gemm_bf16(const Tensor& A, const Tensor& B, const c10::optional<Tensor>& D,
     g.add_src = add_src->data_ptr();
     g.ld_add = add_src->stride(0);
   }
+  if (bn.has_value()) {
+    TORCH_CHECK(g.D != nullptr && g.ldd == g.N, "fused BN reduction needs a dense bf16 output");
+    g.bn = parse_bn(bn, bn_relu, (int64_t)g.M * g.N, g.N);
+  }
   g.device = A.device().index();
   c10::cuda::CUDAGuard guard(A.device());
   const char* err = edl::gemm_bf16(g, at::cuda::getCurrentCUDAStream().stream());
@@ -112,7 +142,8 @@ void gemm_bf16_ship(const Tensor& A, const Tensor& B, int64_t d_ptr, int64_t ldd
 
 // 3x3 / stride 1 / pad 1 convolution (conv3x3.cu).  x, y: logical NCHW tensors in channels_last memory
 // (= NHWC); w: KRSC [Cout, 3, 3, Cin].  dgrad: x is dY [N, Cout, H, W], y is dX [N, Cin, H, W].
-void conv3x3(const Tensor& x, const Tensor& w, Tensor& y, bool dgrad, const c10::optional<Tensor>& col_stats) {
+void conv3x3(const Tensor& x, const Tensor& w, Tensor& y, bool dgrad, const c10::optional<Tensor>& col_stats,
+             const c10::optional<std::vector<c10::optional<Tensor>>>& bn, bool bn_relu) {
   TORCH_CHECK(x.is_cuda() && x.dim() == 4 && y.dim() == 4 && w.dim() == 4);
   TORCH_CHECK(x.scalar_type() == at::kBFloat16 && y.scalar_type() == at::kBFloat16 &&
               w.scalar_type() == at::kBFloat16);
@@ -132,6 +163,10 @@ void conv3x3(const Tensor& x, const Tensor& w, Tensor& y, bool dgrad, const c10:
   TORCH_CHECK(x.size(1) == (dgrad ? a.Cout : a.Cin) && y.size(1) == (dgrad ? a.Cin : a.Cout));
   TORCH_CHECK(y.size(0) == a.N && y.size(2) == a.H && y.size(3) == a.W);
   a.col_stats = optp<float>(col_stats);
+  if (bn.has_value()) {
+    TORCH_CHECK(dgrad, "fused BN reduction belongs to the dgrad launch");
+    a.bn = parse_bn(bn, bn_relu, y.numel(), y.size(1));
+  }
   a.device = x.device().index();
   c10::cuda::CUDAGuard guard(x.device());
   const char* err = edl::conv3x3_bf16(a, at::cuda::getCurrentCUDAStream().stream());

@@ -48,11 +48,18 @@ struct PersistParams {
   float* col_stats;
   const __nv_bfloat16* add_src;   // optional addend tile source (GEMM modes)
   long long ld_add;
+  // fused BatchNorm-backward reduction (BNR kernels): D is the gradient dy of a BN layer's output
+  const float* bn_mean;
+  const float* bn_rstd;
+  const float* bn_gamma;
+  const float* bn_beta;
+  float* bn_dsums;                // [2N]: += sum(dy_masked), sum(dy_masked * xhat)
+  int bn_relu, bn_has_y;
   // conv view (modes 2, 3)
   int n_img, H, W, kc_blocks, c_in_w, BH, BN, tiles_h;
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool BNR = false>
 struct PSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -60,7 +67,11 @@ struct PSmem {
   static constexpr int kDBytes = kBlockM * BLOCK_N * 2;
   static constexpr int kRingBytes = STAGES * kStageBytes;
   static constexpr int kStatsBytes = 2 * kMaxStatsN * 4;   // CTA-local per-channel (sum, sum^2) accumulators
-  static constexpr int kStatsOffset = kRingBytes + kDBytes;
+  static constexpr int kXOffset = kRingBytes + kDBytes;           // BNR: BN input tile x, then BN output tile y
+  static constexpr int kXYBytes = BNR ? 2 * kDBytes : 0;
+  static constexpr int kConstOffset = kXOffset + kXYBytes;        // BNR: mean, rstd, scale, shift of the tile's columns
+  static constexpr int kConstBytes = BNR ? 4 * BLOCK_N * 4 : 0;
+  static constexpr int kStatsOffset = kConstOffset + kConstBytes;
   static constexpr int kBarOffset = kStatsOffset + kStatsBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;
 };
@@ -73,12 +84,29 @@ EDL_DEVICE void tma_store_4d_p(const CUtensorMap* m, const void* smem_src, int c
       : "memory");
 }
 
-template <int BLOCK_N, int STAGES, int MODE>
+// 32 x 32 transpose-reduce: every lane passes its 32 per-column values, lane j gets column j summed over
+// the 32 lanes (= 32 accumulator rows) with 31 shuffles instead of 160.
+EDL_DEVICE float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = hi ? v[i] : v[i + off];
+      const float keep = hi ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BLOCK_N, int STAGES, int MODE, bool BNR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
+                    const __grid_constant__ CUtensorMap tmBnX, const __grid_constant__ CUtensorMap tmBnY,
                     const PersistParams p) {
-  using L = PSmem<BLOCK_N, STAGES>;
+  using L = PSmem<BLOCK_N, STAGES, BNR>;
   constexpr bool kConv = MODE >= 2;
   constexpr bool kBMN = MODE == 1 || MODE == 3;
   constexpr bool kDgrad = MODE == 3;
@@ -87,13 +115,18 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sd = smem + L::kRingBytes;                    // dedicated store-staging tile
   float* sstats = reinterpret_cast<float*>(smem + L::kStatsOffset);
-  const bool local_stats = p.col_stats != nullptr && p.N <= kMaxStatsN;
+  uint8_t* sx = smem + L::kXOffset;                       // BNR only
+  uint8_t* sy = sx + L::kDBytes;
+  float* sconst = reinterpret_cast<float*>(smem + L::kConstOffset);
+  float* const stats_dst = BNR ? p.bn_dsums : p.col_stats;
+  const bool local_stats = stats_dst != nullptr && p.N <= kMaxStatsN;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;              // [2]
   uint64_t* tmem_empty = tmem_full + 2;                  // [2]
   uint64_t* add_bar = tmem_empty + 2;                    // addend tile landed in the staging buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(add_bar + 1);
+  uint64_t* bn_bar = add_bar + 1;                        // BN x (/ y) tiles landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bn_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,6 +146,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::mbar_init(&tmem_empty[a], kEpiWarps);
     }
     ptx::mbar_init(add_bar, 1);
+    ptx::mbar_init(bn_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_slot);
@@ -233,6 +267,47 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         ptx::mbar_wait(add_bar, tc & 1);
       }
+      // rows of this tile that are real pixels of the tensor (conv: partial patches, tail images)
+      bool row_ok = true;
+      if (BNR) {
+        if (!kConv) {
+          row_ok = m0 + row < p.M;
+        } else {
+          const int rows_per_img = p.BH * p.W;
+          const int bi = row / rows_per_img, rr = row - bi * rows_per_img;
+          row_ok = row < rows_tile && img0 + bi < p.n_img && h0 + rr / p.W < p.H;
+        }
+        if (et == 0) {
+          uint32_t halves = 0;
+#pragma unroll
+          for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) halves += (n0 + hh * 64 < p.N) ? 1u : 0u;
+          const uint32_t tile_bytes = kConv ? (uint32_t)rows_tile * 128u : (uint32_t)(kBlockM * 128);
+          ptx::mbar_arrive_expect_tx(bn_bar, halves * tile_bytes * (p.bn_has_y ? 2u : 1u));
+#pragma unroll
+          for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) {
+            if (n0 + hh * 64 >= p.N) continue;
+            if (!kConv) {
+              ptx::tma_load_2d(sx + hh * (kBlockM * 128), &tmBnX, bn_bar, n0 + hh * 64, m0);
+              if (p.bn_has_y) ptx::tma_load_2d(sy + hh * (kBlockM * 128), &tmBnY, bn_bar, n0 + hh * 64, m0);
+            } else {
+              ptx::tma_load_4d(sx + hh * (kBlockM * 128), &tmBnX, bn_bar, n0 + hh * 64, 0, h0, img0);
+              if (p.bn_has_y) ptx::tma_load_4d(sy + hh * (kBlockM * 128), &tmBnY, bn_bar, n0 + hh * 64, 0, h0, img0);
+            }
+          }
+        }
+        if (et < BLOCK_N) {
+          const int col = n0 + et;
+          const bool in = col < p.N;
+          const float mean = in ? p.bn_mean[col] : 0.f, rstd = in ? p.bn_rstd[col] : 0.f;
+          const float scale = in ? p.bn_gamma[col] * rstd : 0.f;
+          sconst[et] = mean;
+          sconst[BLOCK_N + et] = rstd;
+          sconst[2 * BLOCK_N + et] = scale;
+          sconst[3 * BLOCK_N + et] = in ? p.bn_beta[col] - mean * scale : 0.f;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");     // constants visible to every epilogue thread
+        ptx::mbar_wait(bn_bar, tc & 1);
+      }
       ptx::mbar_wait(&tmem_full[slot], aph);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + slot * BLOCK_N + grp * kColsPerGrp + ((uint32_t)(q * 32) << 16);
@@ -288,6 +363,53 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
         }
+        if (BNR) {
+          // dy = the bf16 value this tile stores; masked by the ReLU of the BN layer, reduced per channel
+          const uint32_t xrow = ptx::smem_u32(sx) + (cbase >> 6) * (kBlockM * 128) + row * 128;
+          const uint32_t yrow = ptx::smem_u32(sy) + (cbase >> 6) * (kBlockM * 128) + row * 128;
+          float g1[32], g2[32];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int chunk = ((cbase >> 5) & 1) * 4 + c;
+            const uint32_t off = (chunk ^ (row & 7)) << 4;
+            uint32_t xw[4], yw[4] = {0, 0, 0, 0};
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(xw[0]), "=r"(xw[1]), "=r"(xw[2]), "=r"(xw[3]) : "r"(xrow + off));
+            if (p.bn_has_y)
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(yw[0]), "=r"(yw[1]), "=r"(yw[2]), "=r"(yw[3]) : "r"(yrow + off));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[j]));
+              const float2 yv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[j]));
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int jj = c * 8 + 2 * j + e;
+                const int cc = c32 * 32 + grp * kColsPerGrp + jj;        // column inside the tile
+                const float xe = e == 0 ? xv.x : xv.y, ye = e == 0 ? yv.x : yv.y;
+                const float dyv = __bfloat162float(__float2bfloat16_rn(f[jj]));
+                bool keep = row_ok;
+                if (p.bn_relu)
+                  keep = keep && (p.bn_has_y ? ye > 0.f : fmaf(xe, sconst[2 * BLOCK_N + cc], sconst[3 * BLOCK_N + cc]) > 0.f);
+                const float g = keep ? dyv : 0.f;
+                g1[jj] = g;
+                g2[jj] = g * ((xe - sconst[cc]) * sconst[BLOCK_N + cc]);
+              }
+            }
+          }
+          const float r1 = warp_colsum32(g1, lane);
+          const float r2 = warp_colsum32(g2, lane);
+          const int col = n0 + cbase + lane;
+          if (col < p.N) {
+            if (local_stats) {
+              atomicAdd(&sstats[col], r1);
+              atomicAdd(&sstats[p.N + col], r2);
+            } else {
+              atomicAdd(&p.bn_dsums[col], r1);
+              atomicAdd(&p.bn_dsums[p.N + col], r2);
+            }
+          }
+        }
         const int half = cbase >> 6;
         const uint32_t rowp = ptx::smem_u32(sd) + half * (kBlockM * 128) + row * 128;
 #pragma unroll
@@ -312,7 +434,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         ptx::tma_store_commit();
       }
-      if (p.col_stats != nullptr) {
+      if (!BNR && p.col_stats != nullptr) {
         // Per-channel sum / sum of squares of the STORED bf16 values, from the staged tile.  A thread owns
         // a PAIR of adjacent columns (one 32-bit shared load per row) and every kSplit-th row; eight
         // independent loads are in flight per thread (the naive one-column, one-accumulator loop was the
@@ -396,15 +518,15 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (local_stats) {
       // one flush per CTA: only the column groups this CTA touched are non-zero
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const bool vec_ok = (p.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.col_stats) & 15) == 0);
+      const bool vec_ok = (p.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(stats_dst) & 15) == 0);
       if (vec_ok) {
         for (int i = et * 4; i < 2 * p.N; i += kEpiThreads * 4) {
           const float4 v = *reinterpret_cast<const float4*>(&sstats[i]);
-          if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_v4(&p.col_stats[i], v.x, v.y, v.z, v.w);
+          if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_v4(&stats_dst[i], v.x, v.y, v.z, v.w);
         }
       } else {
         for (int i = et; i < 2 * p.N; i += kEpiThreads)
-          if (sstats[i] != 0.f) atomicAdd(&p.col_stats[i], sstats[i]);
+          if (sstats[i] != 0.f) atomicAdd(&stats_dst[i], sstats[i]);
       }
     }
     if (et == 0) ptx::tma_store_wait_read0();
@@ -419,11 +541,13 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 bool g_persistent = true;
 
-template <int BLOCK_N, int STAGES, int MODE>
+template <int BLOCK_N, int STAGES, int MODE, bool BNR = false>
 const char* launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const PersistParams& p,
-                     cudaStream_t stream, const CUtensorMap* tmAdd = nullptr) {
-  using L = PSmem<BLOCK_N, STAGES>;
-  auto kern = gemm_persist_kernel<BLOCK_N, STAGES, MODE>;
+                     cudaStream_t stream, const CUtensorMap* tmAdd = nullptr, const CUtensorMap* tmBnX = nullptr,
+                     const CUtensorMap* tmBnY = nullptr) {
+  using L = PSmem<BLOCK_N, STAGES, BNR>;
+  static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
+  auto kern = gemm_persist_kernel<BLOCK_N, STAGES, MODE, BNR>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -433,7 +557,8 @@ const char* launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   }
   const int total = p.tiles_m * p.tiles_n;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  kern<<<grid, kThreads, L::kTotal, stream>>>(tmA, tmB, tmD, tmAdd != nullptr ? *tmAdd : tmD, p);
+  kern<<<grid, kThreads, L::kTotal, stream>>>(tmA, tmB, tmD, tmAdd != nullptr ? *tmAdd : tmD,
+                                              tmBnX != nullptr ? *tmBnX : tmD, tmBnY != nullptr ? *tmBnY : tmD, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -446,6 +571,15 @@ const char* tmap2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t o
   return encode_tmap_bf16(out, ptr, 2, dims, st, box);
 }
 
+}  // namespace
+
+namespace {
+void fill_bn(PersistParams& p, const BnBwdFuse& bn) {
+  p.bn_mean = bn.mean; p.bn_rstd = bn.rstd; p.bn_gamma = bn.gamma; p.bn_beta = bn.beta;
+  p.bn_dsums = bn.dsums;
+  p.bn_relu = bn.relu ? 1 : 0;
+  p.bn_has_y = (bn.relu && bn.y != nullptr) ? 1 : 0;
+}
 }  // namespace
 
 void set_persistent_gemm(bool on) { g_persistent = on; }
@@ -479,6 +613,18 @@ const char* gemm_bf16_persistent(const GemmArgs& g, cudaStream_t stream) {
       return "gemm add_src needs N % 8 == 0 and 16-byte aligned rows";
     if (const char* e = tmap2d(&tmAdd, g.add_src, g.N, g.M, g.ld_add, 64, kBlockM)) return e;
     padd = &tmAdd;
+  }
+  if (g.bn.x != nullptr) {
+    // dgrad whose output is the gradient of a BatchNorm output: reduce it in the epilogue
+    if (!g.b_mn_major || g.col_stats != nullptr) return "fused BN-backward reduction is a dgrad (B MN-major) feature";
+    alignas(64) CUtensorMap tmBx, tmBy;
+    if (const char* e = tmap2d(&tmBx, g.bn.x, g.N, g.M, g.ldd, 64, kBlockM)) return e;
+    const bool has_y = g.bn.relu && g.bn.y != nullptr;
+    if (has_y)
+      if (const char* e = tmap2d(&tmBy, g.bn.y, g.N, g.M, g.ldd, 64, kBlockM)) return e;
+    fill_bn(p, g.bn);
+    return n64 ? launch_p<64, 4, 1, true>(tmA, tmB, tmD, p, stream, padd, &tmBx, has_y ? &tmBy : nullptr)
+               : launch_p<128, 3, 1, true>(tmA, tmB, tmD, p, stream, padd, &tmBx, has_y ? &tmBy : nullptr);
   }
   if (!g.b_mn_major)
     return n64 ? launch_p<64, 6, 0>(tmA, tmB, tmD, p, stream, padd) : launch_p<128, 5, 0>(tmA, tmB, tmD, p, stream, padd);
@@ -515,6 +661,19 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
   p.num_kb = 9 * p.kc_blocks;
   p.col_stats = dg ? nullptr : a.col_stats;
   p.n_img = a.N; p.H = a.H; p.W = a.W; p.c_in_w = a.Cin; p.BH = BH; p.BN = BN; p.tiles_h = tiles_h;
+  if (dg && a.bn.x != nullptr) {
+    alignas(64) CUtensorMap tmBx, tmBy;
+    const uint64_t dims[4] = {(uint64_t)cy, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
+    const uint64_t st[3] = {(uint64_t)cy * 2, (uint64_t)a.W * cy * 2, (uint64_t)a.H * a.W * cy * 2};
+    const uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)BH, (uint32_t)BN};
+    if (const char* e = encode_tmap_bf16(&tmBx, a.bn.x, 4, dims, st, box)) return e;
+    const bool has_y = a.bn.relu && a.bn.y != nullptr;
+    if (has_y)
+      if (const char* e = encode_tmap_bf16(&tmBy, a.bn.y, 4, dims, st, box)) return e;
+    fill_bn(p, a.bn);
+    return n64 ? launch_p<64, 4, 3, true>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr)
+               : launch_p<128, 3, 3, true>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr);
+  }
   if (!dg) return n64 ? launch_p<64, 6, 2>(tmX, tmW, tmY, p, stream) : launch_p<128, 5, 2>(tmX, tmW, tmY, p, stream);
   return n64 ? launch_p<64, 6, 3>(tmX, tmW, tmY, p, stream) : launch_p<128, 5, 3>(tmX, tmW, tmY, p, stream);
 }

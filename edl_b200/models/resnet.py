@@ -22,8 +22,13 @@ class _Bottleneck(nn.Module):
         self.short = ConvBNAct(cin, cout, 1, stride, False, impl=impl) if (cin != cout or stride != 1) else None
 
     def forward(self, x):
-        s = self.short(x) if self.short is not None else x
-        return self.c(self.b(self.a(x)), residual=s)
+        if self.a.can_fork(x):           # both gradients of x are summed in conv a's dgrad epilogue
+            y, xs = self.a(x, fork=True)
+        else:
+            ops.drop_bn_hook(x)
+            y, xs = self.a(x), x
+        s = self.short(xs) if self.short is not None else xs
+        return self.c(self.b(y), residual=s)
 
 
 class _Basic(nn.Module):
@@ -34,6 +39,7 @@ class _Basic(nn.Module):
         self.short = ConvBNAct(cin, width, 1, stride, False, impl=impl) if (cin != width or stride != 1) else None
 
     def forward(self, x):
+        ops.drop_bn_hook(x)
         s = self.short(x) if self.short is not None else x
         return self.b(self.a(x), residual=s)
 

@@ -102,6 +102,7 @@ class Bottleneck(nn.Module):
         if self.a.can_fork(x):
             y, xs = self.a(x, fork=True)
         else:
+            ops.drop_bn_hook(x)          # two consumers, no fork: nobody sees x's complete gradient
             y, xs = self.a(x), x
         if self.short is not None:
             s = ops.avg_pool_2x2(xs) if self.pool else xs
@@ -125,6 +126,7 @@ class BasicBlock(nn.Module):
                                    False, impl=impl)
 
     def forward(self, x):
+        ops.drop_bn_hook(x)              # x feeds conv a (3x3) and the shortcut
         if self.short is not None:
             s = ops.avg_pool_2x2(x) if self.pool else x
             s = self.short(s)

@@ -54,7 +54,7 @@ def reset_launches() -> None:
     _launches = 0
 
 
-from .bn import batch_norm_act, BatchNormAct2d, scale_shift_act, bn_stats_into, set_fused_bn  # noqa: E402
+from .bn import batch_norm_act, BatchNormAct2d, scale_shift_act, bn_stats_into, set_fused_bn, drop_bn_hook  # noqa: E402
 from .loss import soft_cross_entropy, topk_accuracy  # noqa: E402
 from .pool import max_pool_3x3_s2, avg_pool_2x2, global_avg_pool  # noqa: E402
 from .optim import FlatSGDMomentum, FlatAdam  # noqa: E402
@@ -67,5 +67,5 @@ __all__ = [
     "soft_cross_entropy", "topk_accuracy",
     "max_pool_3x3_s2", "avg_pool_2x2", "global_avg_pool",
     "FlatSGDMomentum", "FlatAdam", "gemm_bf16", "linear_bf16", "conv1x1", "conv_lib", "conv3x3", "conv3x3_supported",
-    "rope", "rope_tables", "embedding_bag_mean", "normalize_u8", "DynamicLossScaler", "set_fused_bn",
+    "rope", "rope_tables", "embedding_bag_mean", "normalize_u8", "DynamicLossScaler", "set_fused_bn", "drop_bn_hook",
 ]

@@ -66,11 +66,39 @@ def _ref_forward(x, res, gamma, beta, rm, rv, relu, training, momentum, eps):
     return out, mean, rstd
 
 
+class BNBackwardHook:
+    """Left by a train-mode BatchNorm on its output tensor (``y._edl_bn_hook``).  The consumer of ``y`` (a
+    tcgen05 1x1 / 3x3 convolution) computes d(loss)/dy in its dgrad kernel; with this hook that kernel's
+    epilogue also accumulates the BN-backward reduction (sum dy_masked, sum dy_masked * xhat) into ``dsums``
+    and sets ``done``, and the BN backward then skips its own reduction pass over (dy, x)."""
+
+    __slots__ = ("x", "y", "mean", "rstd", "gamma", "beta", "relu", "dsums", "done")
+
+    def __init__(self):
+        self.x = self.y = self.mean = self.rstd = self.gamma = self.beta = self.dsums = None
+        self.relu = False
+        self.done = False
+
+    def as_list(self, rows, channels):
+        assert self.x.numel() == rows * channels
+        return [self.x, self.y, self.mean, self.rstd, self.gamma, self.beta, self.dsums]
+
+
+def drop_bn_hook(t):
+    """Call on a BatchNorm output that feeds MORE than one consumer without the fork mechanism of
+    ``conv1x1``: no single dgrad kernel sees its complete gradient, so nobody may fuse the reduction."""
+    if getattr(t, "_edl_bn_hook", None) is not None:
+        t._edl_bn_hook = None
+    return t
+
+
 class _BNActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, res, gamma, beta, rm, rv, sums, ws, sink_g, sink_b, relu, momentum,
-                eps):
+                eps, hook=None):
         from . import native, count_launch
+
+        ctx.hook = None
 
         x = _cl(x)
         res = _cl(res) if res is not None else None
@@ -108,6 +136,14 @@ class _BNActFn(torch.autograd.Function):
         # the saved output is only needed for the ReLU mask when a residual was added; otherwise the
         # backward kernels recompute the mask from x (one fewer pass over the activation)
         ctx.save_for_backward(x, y if (relu and res is not None) else None, gamma, mean, rstd, beta)
+        if hook is not None:
+            # let the consumer's dgrad kernel carry this layer's backward reduction
+            if bwd_ws is None:
+                bwd_ws = ctx.bwd_ws = torch.zeros(2 * ch, device=x.device, dtype=torch.float32)
+            hook.x, hook.y = x, (y if (relu and res is not None) else None)
+            hook.mean, hook.rstd, hook.gamma, hook.beta = mean, rstd, gamma, beta
+            hook.relu, hook.dsums = relu, bwd_ws
+            ctx.hook = hook
         return y
 
     @staticmethod
@@ -140,7 +176,7 @@ class _BNActFn(torch.autograd.Function):
                 dgo = dbo = None
                 if ctx.ready is not None:
                     ctx.ready()
-            return dx, dres, dgo, dbo, None, None, None, None, None, None, None, None, None
+            return dx, dres, dgo, dbo, None, None, None, None, None, None, None, None, None, None
         C = native()
         ch = gamma.numel()
         dsums = ctx.bwd_ws
@@ -163,15 +199,18 @@ class _BNActFn(torch.autograd.Function):
                            _mc(dres) if has_res else None, dg, db, relu, acc, sync)
             count_launch()
         else:
-            C.bn_bwd_reduce(dy2, x2, y2, gamma, beta, mean, rstd, dsums, relu)
+            if ctx.hook is not None and ctx.hook.done:
+                count_launch(1)      # the reduction already rode in the consumer's dgrad epilogue
+            else:
+                C.bn_bwd_reduce(dy2, x2, y2, gamma, beta, mean, rstd, dsums, relu)
+                count_launch(2)
             C.bn_bwd_apply(dy2, x2, y2, gamma, beta, mean, rstd, dsums, _mc(dx),
                            _mc(dres) if has_res else None, dg, db, relu, acc)
-            count_launch(2)
         if sink_g is not None:
             dg = db = None
             if ctx.ready is not None:
                 ctx.ready()
-        return dx, dres, dg, db, None, None, None, None, None, None, None, None, None
+        return dx, dres, dg, db, None, None, None, None, None, None, None, None, None, None
 
 
 def batch_norm_act(x, gamma, beta, running_mean=None, running_var=None, residual=None, relu=False,
@@ -187,8 +226,12 @@ def batch_norm_act(x, gamma, beta, running_mean=None, running_var=None, residual
     sink_g, sink_b, ready = (tuple(sinks) + (None,))[:3] if sinks is not None else (None, None, None)
     if ws is None and bwd_ws is not None:
         ws = (None, bwd_ws, None)
-    return _BNActFn.apply(x, residual, gamma, beta, running_mean, running_var, sums, ws,
-                          (sink_g, ready), sink_b, relu, momentum, eps)
+    hook = BNBackwardHook() if (x.is_cuda and x.dtype == torch.bfloat16 and torch.is_grad_enabled() and not _FUSED) else None
+    y = _BNActFn.apply(x, residual, gamma, beta, running_mean, running_var, sums, ws,
+                       (sink_g, ready), sink_b, relu, momentum, eps, hook)
+    if hook is not None and hook.x is not None:
+        y._edl_bn_hook = hook
+    return y
 
 
 def bn_stats_into(x, sums):

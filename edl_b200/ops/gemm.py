@@ -16,7 +16,7 @@ _NUM_SMS = 148
 
 def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, col_scale=None, col_shift=None,
               relu=False, col_stats=None, out_f32=None, split_k=1, out_bf16=None, tile_counters=None,
-              accumulate_out=False, add=None):
+              accumulate_out=False, add=None, bn=None):
     """D = op(A) @ op(B): see csrc/gemm.h for the operand conventions.
 
     default        : A [M, K], B [N, K]  -> D [M, N] = A @ B^T
@@ -25,7 +25,9 @@ def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, col_scale=None
     out_f32 given  : fp32 [M, N] += result, split over K across CTAs (no bf16 output).
     out_bf16 given : (with out_f32 as an all-zero workspace) the last CTA of every output tile writes
                      bf16(result) (+= if accumulate_out) into out_bf16 and re-zeroes the workspace.
-    add given      : D = result + add (bf16 [M, N]) in the epilogue (gradient accumulation fused into dgrad)."""
+    add given      : D = result + add (bf16 [M, N]) in the epilogue (gradient accumulation fused into dgrad).
+    bn given       : a ``BNBackwardHook`` (ops/bn.py): D is the gradient of that BatchNorm's output and the
+                     epilogue accumulates its backward reduction (sum dy, sum dy * xhat) into hook.dsums."""
     from . import native, count_launch
 
     m = a.shape[1] if a_mn_major else a.shape[0]
@@ -64,13 +66,16 @@ def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, col_scale=None
                                 and add.stride(0) % 8 == 0 and add.data_ptr() % 16 == 0 and out_f32 is None):
         # the fused addend lives in the persistent kernel's epilogue; otherwise one extra elementwise pass
         native().gemm_bf16(a, b, out, a_mn_major, b_mn_major, col_scale, col_shift, relu, col_stats,
-                           out_f32, int(split_k), out_bf16, tile_counters, bool(accumulate_out), None)
+                           out_f32, int(split_k), out_bf16, tile_counters, bool(accumulate_out), None, None, False)
         count_launch()
         out.add_(add)
         return out
+    bn_list, bn_relu = (bn.as_list(m, n), bn.relu) if bn is not None else (None, False)
     native().gemm_bf16(a, b, out, a_mn_major, b_mn_major, col_scale, col_shift, relu, col_stats,
-                       out_f32, int(split_k), out_bf16, tile_counters, bool(accumulate_out), add)
+                       out_f32, int(split_k), out_bf16, tile_counters, bool(accumulate_out), add, bn_list, bn_relu)
     count_launch()
+    if bn is not None:
+        bn.done = True
     if out_bf16 is not None:
         return out_bf16
     return out if out_f32 is None else out_f32
@@ -175,7 +180,8 @@ class _Conv1x1Fn(torch.autograd.Function):
     instead of two gradients that autograd adds with an extra elementwise kernel."""
 
     @staticmethod
-    def forward(ctx, x, w, stats, sink, ready, fork=False):
+    def forward(ctx, x, w, stats, sink, ready, fork=False, bn_hook=None):
+        ctx.bn_hook = bn_hook
         x = _cl(x)
         n, cin, h, wd = x.shape
         cout = w.shape[0]
@@ -195,7 +201,7 @@ class _Conv1x1Fn(torch.autograd.Function):
     def backward(ctx, dy, dfork=None):
         x, w = ctx.saved_tensors
         if dy is None:      # only the forked alias was used downstream
-            return dfork, None, None, None, None, None
+            return dfork, None, None, None, None, None, None
         dy = _cl(dy)
         n, cin, h, wd = x.shape
         cout = w.shape[0]
@@ -208,9 +214,12 @@ class _Conv1x1Fn(torch.autograd.Function):
             add = None
             if dfork is not None:
                 add = _cl(dfork).permute(0, 2, 3, 1).reshape(-1, cin)
-            gemm_bf16(dy2, w2, out=dx.permute(0, 2, 3, 1).reshape(-1, cin), b_mn_major=True, add=add)
+            # dx is the gradient of the BatchNorm output that fed this conv: its backward reduction
+            # rides in this epilogue when the producing BN left a hook on the tensor
+            hook = ctx.bn_hook if _bn_fusable(ctx.bn_hook, x, cin) else None
+            gemm_bf16(dy2, w2, out=dx.permute(0, 2, 3, 1).reshape(-1, cin), b_mn_major=True, add=add, bn=hook)
         dw = _wgrad(dy2, x2, w.shape, ctx.sink, ctx.ready) if ctx.needs_input_grad[1] else None
-        return dx, dw, None, None, None, None
+        return dx, dw, None, None, None, None, None
 
 
 def conv1x1(x, weight, stats: Optional[torch.Tensor] = None, fork: bool = False):
@@ -219,7 +228,19 @@ def conv1x1(x, weight, stats: Optional[torch.Tensor] = None, fork: bool = False)
     per-channel sum / sum-of-squares of the output for the following train-mode BatchNorm."""
     sink = getattr(weight, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
     ready = getattr(weight, "_edl_grad_ready", None) if sink is not None else None
-    return _Conv1x1Fn.apply(x, weight, stats, sink, ready, fork)
+    return _Conv1x1Fn.apply(x, weight, stats, sink, ready, fork, getattr(x, "_edl_bn_hook", None))
+
+
+def _bn_fusable(hook, x, channels) -> bool:
+    """The consumer's dgrad may carry the BN-backward reduction iff the hook belongs to exactly this input,
+    the persistent kernels are on and the layout is what the fused epilogue expects."""
+    from . import native
+
+    return (hook is not None and FUSE_BN_BWD and not hook.done and x.is_cuda and hook.x.shape == x.shape
+            and channels % 8 == 0 and native().persistent_gemm_enabled())
+
+
+FUSE_BN_BWD = __import__("os").environ.get("EDL_FUSE_BN_BWD", "1") == "1"
 
 
 class _LinearFn(torch.autograd.Function):
@@ -335,13 +356,14 @@ class _Conv3x3Fn(torch.autograd.Function):
     weight gradient uses the library kernel on the side stream (off the critical path)."""
 
     @staticmethod
-    def forward(ctx, x, w, stats, sink, ready):
+    def forward(ctx, x, w, stats, sink, ready, bn_hook=None):
         from . import native, count_launch
 
+        ctx.bn_hook = bn_hook
         x = _cl(x)
         n, _, h, wd = x.shape
         y = torch.empty((n, w.shape[0], h, wd), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
-        native().conv3x3(x, w, y, False, stats)
+        native().conv3x3(x, w, y, False, stats, None, False)
         count_launch()
         ctx.save_for_backward(x, w)
         ctx.sink, ctx.ready = sink, ready
@@ -359,7 +381,12 @@ class _Conv3x3Fn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if conv3x3_supported(dy, w, dgrad=True):
                 dx = torch.empty_like(x)
-                native().conv3x3(dy, w, dx, True, None)
+                hook = ctx.bn_hook if _bn_fusable(ctx.bn_hook, x, x.shape[1]) else None
+                if hook is not None:
+                    native().conv3x3(dy, w, dx, True, None, hook.as_list(dx.numel() // dx.shape[1], dx.shape[1]), hook.relu)
+                    hook.done = True
+                else:
+                    native().conv3x3(dy, w, dx, True, None, None, False)
                 count_launch()
             else:
                 dx = _ConvLibFn._bwd(dy, x, wv, cfg, [True, False, False])[0]
@@ -386,7 +413,7 @@ class _Conv3x3Fn(torch.autograd.Function):
                     dw = wgrad()
             else:
                 dw = wgrad()
-        return dx, dw, None, None, None
+        return dx, dw, None, None, None, None
 
 
 def conv3x3(x, weight_krsc, stats: Optional[torch.Tensor] = None):
@@ -394,4 +421,4 @@ def conv3x3(x, weight_krsc, stats: Optional[torch.Tensor] = None):
     sum / sum of squares of the output for the following train-mode BatchNorm."""
     sink = getattr(weight_krsc, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
     ready = getattr(weight_krsc, "_edl_grad_ready", None) if sink is not None else None
-    return _Conv3x3Fn.apply(x, weight_krsc, stats, sink, ready)
+    return _Conv3x3Fn.apply(x, weight_krsc, stats, sink, ready, getattr(x, "_edl_bn_hook", None))

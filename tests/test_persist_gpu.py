@@ -73,7 +73,7 @@ def test_persistent_conv3x3_matches_tile_kernel(n, cin, cout, h, w):
         for persistent in (True, False):
             ops.native().set_persistent_gemm(persistent)
             dx = torch.empty_like(x)
-            ops.native().conv3x3(dy, wt, dx, True, None)
+            ops.native().conv3x3(dy, wt, dx, True, None, None, False)
             dxs.append(dx)
         assert torch.equal(dxs[0], dxs[1])
 
@@ -99,3 +99,34 @@ def test_conv1x1_fork_sums_both_gradients_in_the_dgrad_epilogue():
     xr2 = x.detach().float().requires_grad_(True)
     F.conv2d(xr2, wr.detach().view(64, 256, 1, 1)).backward(dy.float())
     assert _rel(x2.grad, xr2.grad) < 1e-2
+
+
+@pytest.mark.parametrize("layers,width", [(50, 0.5), (18, 1.0)])
+def test_bn_backward_reduction_fused_into_dgrad_matches_separate_kernels(layers, width):
+    """conv -> BN -> conv chains: the second conv's dgrad epilogue carries the BN-backward reduction
+    (1x1, 3x3 and fork/residual variants); gradients must match the path with the separate reduce kernel."""
+    from edl_b200.models import ResNetVd, to_train_dtype
+    from edl_b200.ops import gemm as G
+
+    torch.manual_seed(0)
+    m = to_train_dtype(ResNetVd(layers, class_dim=32, width_mult=width), torch.bfloat16, DEV).train()
+    x = torch.randn(8, 3, 64, 64, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    t = torch.softmax(torch.randn(8, 32, device=DEV), -1)
+    grads = []
+    launches = []
+    try:
+        for fuse in (True, False):
+            G.FUSE_BN_BWD = fuse
+            for p in m.parameters():
+                p.grad = None
+            ops.reset_launches()
+            ops.soft_cross_entropy(m(x), t).backward()
+            torch.cuda.synchronize()
+            launches.append(ops.launches())
+            grads.append([p.grad.detach().float().clone() for p in m.parameters()])
+    finally:
+        G.FUSE_BN_BWD = True
+    if layers == 50:
+        assert launches[0] <= launches[1] - 30        # >= 30 BN reduce kernels disappeared
+    worst = max(_rel(a, b) for a, b in zip(*grads))
+    assert worst < 2e-2, worst

@@ -72,6 +72,6 @@ elif op in ("conv3", "conv3dgrad"):
     wt = (torch.randn(k, 3, 3, c, device=dev) * 0.05).bfloat16()
     y = torch.empty(n, k if op == "conv3" else c, h, w, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
     st = torch.zeros(2 * k, device=dev)
-    run(lambda: ops.native().conv3x3(x, wt, y, op != "conv3", st if op == "conv3" else None))
+    run(lambda: ops.native().conv3x3(x, wt, y, op != "conv3", st if op == "conv3" else None, None, False))
 else:
     raise SystemExit("unknown op " + op)
