@@ -326,7 +326,14 @@ const char* launch(const Conv3x3Args& a, const Geometry& geo, cudaStream_t strea
 
 }  // namespace
 
-bool conv3x3_supported(int N, int H, int W, int Cin, int Cout, bool dgrad) {
+bool conv3x3_supported(int N, int H, int W, int Cin, int Cout, bool dgrad, int groups) {
+  if (groups > 1) {
+    // grouped fprop (persistent kernel): every N tile must lie inside one group
+    if (dgrad || Cin % groups != 0 || Cout % groups != 0 || !persistent_gemm_enabled()) return false;
+    const int cin_g = Cin / groups, cout_g = Cout / groups;
+    if (cin_g % 64 != 0 || !(cout_g == 64 || cout_g % 128 == 0)) return false;
+    return N >= 1 && plan(N, H, W).ok;
+  }
   const int cx = dgrad ? Cout : Cin, cy = dgrad ? Cin : Cout;
   if (N < 1 || cx % 64 != 0 || cy % 8 != 0) return false;
   // dgrad reads the weight tile MN-major inside one tap: the N tile must not run into the next tap
@@ -336,7 +343,9 @@ bool conv3x3_supported(int N, int H, int W, int Cin, int Cout, bool dgrad) {
 }
 
 const char* conv3x3_bf16(const Conv3x3Args& a, cudaStream_t stream) {
-  if (!conv3x3_supported(a.N, a.H, a.W, a.Cin, a.Cout, a.dgrad)) return "conv3x3: unsupported shape";
+  if (!conv3x3_supported(a.N, a.H, a.W, a.Cin, a.Cout, a.dgrad, a.groups)) return "conv3x3: unsupported shape";
+  if (!persistent_gemm_enabled() && (a.groups > 1 || a.col_scale != nullptr || a.col_shift != nullptr || a.relu))
+    return "conv3x3: groups / inference epilogue need the persistent kernel";
   if (a.device >= 0) {
     cudaError_t e = cudaSetDevice(a.device);   // tensor-map encoding needs a bound context (see gemm.cu)
     if (e != cudaSuccess) return cudaGetErrorString(e);

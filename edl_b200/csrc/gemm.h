@@ -70,9 +70,15 @@ struct Conv3x3Args {
   bool dgrad = false;
   float* col_stats = nullptr;  // fwd only: [2*Cout] += per-channel sum / sum of squares of Y
   BnBwdFuse bn;                // dgrad only: fused BN-backward reduction over Y (= dX)
+  // inference epilogue (fprop, persistent kernel): Y = relu?(conv * col_scale[c] + col_shift[c]) (folded BN)
+  const float* col_scale = nullptr;
+  const float* col_shift = nullptr;
+  bool relu = false;
+  int groups = 1;              // grouped fprop: Cin/groups % 64 == 0, Cout/groups == 64 or % 128 == 0; Wt is
+                               // [Cout, 3, 3, Cin/groups]
   int device = -1;
 };
-bool conv3x3_supported(int N, int H, int W, int Cin, int Cout, bool dgrad);
+bool conv3x3_supported(int N, int H, int W, int Cin, int Cout, bool dgrad, int groups = 1);
 const char* conv3x3_bf16(const Conv3x3Args& args, cudaStream_t stream);
 
 // Persistent variants (gemm_persist.cu): one CTA per SM streams tiles, double-buffered TMEM accumulators,

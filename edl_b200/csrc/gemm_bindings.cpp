@@ -208,8 +208,35 @@ void quantize_e4m3(const Tensor& x, Tensor& q, const Tensor& scale, const c10::o
                      at::cuda::getCurrentCUDAStream().stream());
 }
 
-bool conv3x3_supported(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cout, bool dgrad) {
-  return edl::conv3x3_supported((int)n, (int)h, (int)w, (int)cin, (int)cout, dgrad);
+bool conv3x3_supported(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cout, bool dgrad, int64_t groups) {
+  return edl::conv3x3_supported((int)n, (int)h, (int)w, (int)cin, (int)cout, dgrad, (int)groups);
+}
+
+// inference 3x3 conv (optionally grouped) with the folded-BN scale / shift / ReLU epilogue
+void conv3x3_infer(const Tensor& x, const Tensor& w, Tensor& y, const c10::optional<Tensor>& col_scale,
+                   const c10::optional<Tensor>& col_shift, bool relu, int64_t groups) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 4 && y.dim() == 4 && w.dim() == 4);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && y.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast) && y.is_contiguous(at::MemoryFormat::ChannelsLast));
+  TORCH_CHECK(w.is_contiguous() && w.size(1) == 3 && w.size(2) == 3);
+  edl::Conv3x3Args a;
+  a.X = x.data_ptr();
+  a.Wt = w.data_ptr();
+  a.Y = y.data_ptr();
+  a.N = x.size(0);
+  a.H = x.size(2);
+  a.W = x.size(3);
+  a.Cin = x.size(1);
+  a.Cout = w.size(0);
+  a.groups = (int)groups;
+  TORCH_CHECK(w.size(3) * groups == a.Cin && y.size(1) == a.Cout && y.size(0) == a.N && y.size(2) == a.H && y.size(3) == a.W);
+  a.col_scale = optp<float>(col_scale);
+  a.col_shift = optp<float>(col_shift);
+  a.relu = relu;
+  a.device = x.device().index();
+  c10::cuda::CUDAGuard guard(x.device());
+  const char* err = edl::conv3x3_bf16(a, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(err == nullptr, "edl conv3x3_infer failed: ", err);
 }
 }  // namespace
 
@@ -221,5 +248,6 @@ void register_gemm_bindings(pybind11::module_& m) {
   m.def("gemm_fp8", &gemm_fp8);
   m.def("quantize_e4m3", &quantize_e4m3);
   m.def("conv3x3_supported", &conv3x3_supported);
+  m.def("conv3x3_infer", &conv3x3_infer);
   m.def("gemm_bf16_ship", &gemm_bf16_ship);
 }

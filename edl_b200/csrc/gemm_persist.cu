@@ -57,6 +57,7 @@ struct PersistParams {
   int bn_relu, bn_has_y;
   // conv view (modes 2, 3)
   int n_img, H, W, kc_blocks, c_in_w, BH, BN, tiles_h;
+  int cin_g, cout_g;              // grouped fprop: channels per group (cout_g == N for a dense conv)
 };
 
 template <int BLOCK_N, int STAGES, bool BNR = false>
@@ -192,7 +193,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int r = tap / 3, sft = tap - r * 3;
             const int dh = kDgrad ? 1 - r : r - 1;
             const int dw = kDgrad ? 1 - sft : sft - 1;
-            ptx::tma_load_4d(sa, &tmA, &full_bar[s], kc * kBlockK, dw, h0 + dh, img0);
+            // grouped fprop: the N tile lies in one group; its input channels start at group * cin_g
+            const int cbase_in = (MODE == 2) ? (n0 / p.cout_g) * p.cin_g : 0;
+            ptx::tma_load_4d(sa, &tmA, &full_bar[s], cbase_in + kc * kBlockK, dw, h0 + dh, img0);
             if (!kBMN) {
               ptx::tma_load_2d(sb, &tmB, &full_bar[s], tap * p.c_in_w + kc * kBlockK, n0);
             } else {
@@ -343,7 +346,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
-        if (!kConv) {
+        if (!BNR) {
           if (p.col_scale != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -391,9 +394,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 bool keep = row_ok;
                 if (p.bn_relu)
                   keep = keep && (p.bn_has_y ? ye > 0.f : fmaf(xe, sconst[2 * BLOCK_N + cc], sconst[3 * BLOCK_N + cc]) > 0.f);
-                const float g = keep ? dyv : 0.f;
-                g1[jj] = g;
-                g2[jj] = g * ((xe - sconst[cc]) * sconst[BLOCK_N + cc]);
+                // rows beyond the tensor hold stale shared memory (possibly NaN): select, never multiply
+                g1[jj] = keep ? dyv : 0.f;
+                g2[jj] = keep ? dyv * ((xe - sconst[cc]) * sconst[BLOCK_N + cc]) : 0.f;
               }
             }
           }
@@ -636,7 +639,9 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
                                     cudaStream_t stream) {
   const bool dg = a.dgrad;
   const int cx = dg ? a.Cout : a.Cin, cy = dg ? a.Cin : a.Cout;
-  const bool n64 = cy <= 64;
+  const int groups = dg ? 1 : a.groups;
+  const int cin_g = cx / groups, cout_g = cy / groups;
+  const bool n64 = cout_g <= 64;
   const int bn = n64 ? 64 : 128;
   alignas(64) CUtensorMap tmX, tmW, tmY;
   {
@@ -651,16 +656,21 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
     const uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)BH, (uint32_t)BN};
     if (const char* e = encode_tmap_bf16(&tmY, a.Y, 4, dims, st, box)) return e;
   }
-  if (const char* e = tmap2d(&tmW, a.Wt, (uint64_t)9 * a.Cin, a.Cout, (uint64_t)9 * a.Cin, 64, dg ? kBlockK : bn))
+  const int w_cin = a.Cin / a.groups;      // channel extent of the KRSC weight tensor
+  if (const char* e = tmap2d(&tmW, a.Wt, (uint64_t)9 * w_cin, a.Cout, (uint64_t)9 * w_cin, 64, dg ? kBlockK : bn))
     return e;
   PersistParams p{};
   p.M = tiles_img * tiles_h * kBlockM; p.N = cy; p.K = 9 * cx;
   p.tiles_m = tiles_img * tiles_h;
   p.tiles_n = (cy + bn - 1) / bn;
-  p.kc_blocks = cx / kBlockK;
+  p.kc_blocks = cin_g / kBlockK;
   p.num_kb = 9 * p.kc_blocks;
   p.col_stats = dg ? nullptr : a.col_stats;
-  p.n_img = a.N; p.H = a.H; p.W = a.W; p.c_in_w = a.Cin; p.BH = BH; p.BN = BN; p.tiles_h = tiles_h;
+  p.col_scale = dg ? nullptr : a.col_scale;
+  p.col_shift = dg ? nullptr : a.col_shift;
+  p.relu = (!dg && a.relu) ? 1 : 0;
+  p.cin_g = cin_g; p.cout_g = cout_g;
+  p.n_img = a.N; p.H = a.H; p.W = a.W; p.c_in_w = w_cin; p.BH = BH; p.BN = BN; p.tiles_h = tiles_h;
   if (dg && a.bn.x != nullptr) {
     alignas(64) CUtensorMap tmBx, tmBy;
     const uint64_t dims[4] = {(uint64_t)cy, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};

@@ -13,6 +13,7 @@ layer is  conv -> *scale + shift (+ residual) -> ReLU :
   * the block's last 1x1 adds the shortcut and applies ReLU in one fused kernel.
 """
 import math
+import os
 from typing import List
 
 import torch
@@ -34,6 +35,7 @@ class FoldedConv(nn.Module):
         # gamma=1, beta=0, running stats (0, 1) => identity; real weights load through load_bn())
         self.register_buffer("scale", torch.ones(cout, dtype=torch.float32))
         self.register_buffer("shift", torch.zeros(cout, dtype=torch.float32))
+        self.own_conv3 = os.environ.get("EDL_OWN_CONV3", "1") == "1"
 
     def load_bn(self, gamma, beta, mean, var, eps=1e-5):
         s = gamma.float() * torch.rsqrt(var.float() + eps)
@@ -89,6 +91,10 @@ class FoldedConv(nn.Module):
                 return y
             ops.gemm_bf16(x2, self.weight.view(self.cout, self.cin), out=y2)
             return ops.scale_shift_act(y, self.scale, self.shift, residual, self.relu)
+        if (self.k == 3 and self.stride == 1 and residual is None and self.own_conv3
+                and ops.conv3x3_infer_supported(x, self.weight, self.groups)):
+            # dense or grouped 3x3 on the persistent tcgen05 kernel, folded BN + ReLU in its epilogue
+            return ops.conv3x3_infer(x, self.weight, self.scale, self.shift, self.relu, self.groups)
         y = F.conv2d(x, self.weight.permute(0, 3, 1, 2), None, self.stride, (self.k - 1) // 2, 1, self.groups)
         return ops.scale_shift_act(y, self.scale, self.shift, residual, self.relu)
 

@@ -347,7 +347,7 @@ def conv3x3_supported(x, weight_krsc, dgrad=False) -> bool:
         return False
     n, _, h, w = x.shape
     cout, kh, kw, cin = weight_krsc.shape
-    return kh == 3 and kw == 3 and native().conv3x3_supported(n, h, w, cin, cout, dgrad)
+    return kh == 3 and kw == 3 and native().conv3x3_supported(n, h, w, cin, cout, dgrad, 1)
 
 
 class _Conv3x3Fn(torch.autograd.Function):
@@ -422,3 +422,30 @@ def conv3x3(x, weight_krsc, stats: Optional[torch.Tensor] = None):
     sink = getattr(weight_krsc, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
     ready = getattr(weight_krsc, "_edl_grad_ready", None) if sink is not None else None
     return _Conv3x3Fn.apply(x, weight_krsc, stats, sink, ready, getattr(x, "_edl_bn_hook", None))
+
+
+def conv3x3_infer_supported(x, weight_krsc, groups=1) -> bool:
+    from . import native
+
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and weight_krsc.dtype == torch.bfloat16 and x.dim() == 4):
+        return False
+    n, c, h, w = x.shape
+    cout, kh, kw, cin_g = weight_krsc.shape
+    return (kh == 3 and kw == 3 and cin_g * groups == c
+            and native().conv3x3_supported(n, h, w, c, cout, False, groups))
+
+
+@torch.no_grad()
+def conv3x3_infer(x, weight_krsc, scale=None, shift=None, relu=False, groups=1):
+    """Inference 3x3 / stride 1 / pad 1 convolution (dense or grouped) on the persistent tcgen05 kernel with
+    the folded-BatchNorm scale / shift and the ReLU in its epilogue.  The grouped form is what the
+    ResNeXt teacher needs: cuDNN's grouped bf16 NHWC kernel takes 26 ms for ONE 7x7x4096 (g=32) layer at
+    batch 32 (profiles/teacher_r1.txt)."""
+    from . import native, count_launch
+
+    x = _cl(x)
+    n, _, h, w = x.shape
+    y = torch.empty((n, weight_krsc.shape[0], h, w), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    native().conv3x3_infer(x, weight_krsc, y, scale, shift, relu, groups)
+    count_launch()
+    return y

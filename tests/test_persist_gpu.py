@@ -130,3 +130,17 @@ def test_bn_backward_reduction_fused_into_dgrad_matches_separate_kernels(layers,
         assert launches[0] <= launches[1] - 30        # >= 30 BN reduce kernels disappeared
     worst = max(_rel(a, b) for a, b in zip(*grads))
     assert worst < 2e-2, worst
+
+
+@pytest.mark.parametrize("n,c,cout,h,w,groups", [(4, 2048, 2048, 14, 14, 32), (4, 4096, 4096, 7, 7, 32), (2, 256, 256, 12, 12, 4),
+                                                 (3, 128, 256, 9, 9, 1)])
+def test_grouped_conv3x3_inference_with_folded_bn_epilogue(n, c, cout, h, w, groups):
+    torch.manual_seed(4)
+    x = torch.randn(n, c, h, w, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, 3, 3, c // groups, device=DEV) * 0.05).bfloat16()
+    scale, shift = torch.rand(cout, device=DEV) + 0.5, torch.randn(cout, device=DEV) * 0.1
+    assert ops.conv3x3_infer_supported(x, wt, groups)
+    y = ops.conv3x3_infer(x, wt, scale, shift, True, groups)
+    ref = F.conv2d(x.float(), wt.permute(0, 3, 1, 2).float(), None, 1, 1, 1, groups)
+    ref = torch.relu(ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    assert _rel(y, ref) < 1e-2
