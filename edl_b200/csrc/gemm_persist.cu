@@ -71,7 +71,7 @@ struct PSmem {
   static constexpr int kXOffset = kRingBytes + kDBytes;           // BNR: BN input tile x, then BN output tile y
   static constexpr int kXYBytes = BNR ? 2 * kDBytes : 0;
   static constexpr int kConstOffset = kXOffset + kXYBytes;        // BNR: mean, rstd, scale, shift of the tile's columns
-  static constexpr int kConstBytes = BNR ? 4 * BLOCK_N * 4 : 0;
+  static constexpr int kConstBytes = BNR ? 4 * BLOCK_N * 4 : 0;    // float4 {mean, rstd, scale, shift} per column
   static constexpr int kStatsOffset = kConstOffset + kConstBytes;
   static constexpr int kBarOffset = kStatsOffset + kStatsBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;
@@ -99,6 +99,33 @@ EDL_DEVICE float warp_colsum32(float (&v)[32], int lane) {
     }
   }
   return v[0];
+}
+
+// BNR: TMA loads of the BN input (and output) tile that belongs to output tile `tt`
+template <int BLOCK_N, bool CONV>
+EDL_DEVICE void issue_bn_tiles(const PersistParams& p, int tt, int rows_tile, uint8_t* sx, uint8_t* sy,
+                               const CUtensorMap* tmX, const CUtensorMap* tmY, uint64_t* bar) {
+  const int tm = tt / p.tiles_n;
+  const int nn0 = (tt - tm * p.tiles_n) * BLOCK_N;
+  const int mm0 = tm * kBlockM;
+  const int im0 = CONV ? (tm / p.tiles_h) * p.BN : 0;
+  const int hh0 = CONV ? (tm % p.tiles_h) * p.BH : 0;
+  uint32_t halves = 0;
+#pragma unroll
+  for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) halves += (nn0 + hh * 64 < p.N) ? 1u : 0u;
+  const uint32_t tile_bytes = CONV ? (uint32_t)rows_tile * 128u : (uint32_t)(kBlockM * 128);
+  ptx::mbar_arrive_expect_tx(bar, halves * tile_bytes * (p.bn_has_y ? 2u : 1u));
+#pragma unroll
+  for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) {
+    if (nn0 + hh * 64 >= p.N) continue;
+    if (!CONV) {
+      ptx::tma_load_2d(sx + hh * (kBlockM * 128), tmX, bar, nn0 + hh * 64, mm0);
+      if (p.bn_has_y) ptx::tma_load_2d(sy + hh * (kBlockM * 128), tmY, bar, nn0 + hh * 64, mm0);
+    } else {
+      ptx::tma_load_4d(sx + hh * (kBlockM * 128), tmX, bar, nn0 + hh * 64, 0, hh0, im0);
+      if (p.bn_has_y) ptx::tma_load_4d(sy + hh * (kBlockM * 128), tmY, bar, nn0 + hh * 64, 0, hh0, im0);
+    }
+  }
 }
 
 template <int BLOCK_N, int STAGES, int MODE, bool BNR>
@@ -244,6 +271,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;         // 0..255
     constexpr int kColsPerGrp = BLOCK_N / 2;
+    int const_n0 = -1;
     uint32_t tc = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
       const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
@@ -280,35 +308,21 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int bi = row / rows_per_img, rr = row - bi * rows_per_img;
           row_ok = row < rows_tile && img0 + bi < p.n_img && h0 + rr / p.W < p.H;
         }
-        if (et == 0) {
-          uint32_t halves = 0;
-#pragma unroll
-          for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) halves += (n0 + hh * 64 < p.N) ? 1u : 0u;
-          const uint32_t tile_bytes = kConv ? (uint32_t)rows_tile * 128u : (uint32_t)(kBlockM * 128);
-          ptx::mbar_arrive_expect_tx(bn_bar, halves * tile_bytes * (p.bn_has_y ? 2u : 1u));
-#pragma unroll
-          for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) {
-            if (n0 + hh * 64 >= p.N) continue;
-            if (!kConv) {
-              ptx::tma_load_2d(sx + hh * (kBlockM * 128), &tmBnX, bn_bar, n0 + hh * 64, m0);
-              if (p.bn_has_y) ptx::tma_load_2d(sy + hh * (kBlockM * 128), &tmBnY, bn_bar, n0 + hh * 64, m0);
-            } else {
-              ptx::tma_load_4d(sx + hh * (kBlockM * 128), &tmBnX, bn_bar, n0 + hh * 64, 0, h0, img0);
-              if (p.bn_has_y) ptx::tma_load_4d(sy + hh * (kBlockM * 128), &tmBnY, bn_bar, n0 + hh * 64, 0, h0, img0);
-            }
+        if (tc == 0 && et == 0)                               // later tiles are prefetched one tile ahead
+          issue_bn_tiles<BLOCK_N, kConv>(p, t, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
+        if (n0 != const_n0) {
+          // per-column constants of the BN layer for this N tile (a CTA usually keeps its N tile)
+          if (tc != 0) asm volatile("bar.sync 2, 256;" ::: "memory");   // everybody is done with the old ones
+          if (et < BLOCK_N) {
+            const int col = n0 + et;
+            const bool in = col < p.N;
+            const float mean = in ? p.bn_mean[col] : 0.f, rstd = in ? p.bn_rstd[col] : 0.f;
+            const float scale = in ? p.bn_gamma[col] * rstd : 0.f;
+            reinterpret_cast<float4*>(sconst)[et] = make_float4(mean, rstd, scale, in ? p.bn_beta[col] - mean * scale : 0.f);
           }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          const_n0 = n0;
         }
-        if (et < BLOCK_N) {
-          const int col = n0 + et;
-          const bool in = col < p.N;
-          const float mean = in ? p.bn_mean[col] : 0.f, rstd = in ? p.bn_rstd[col] : 0.f;
-          const float scale = in ? p.bn_gamma[col] * rstd : 0.f;
-          sconst[et] = mean;
-          sconst[BLOCK_N + et] = rstd;
-          sconst[2 * BLOCK_N + et] = scale;
-          sconst[3 * BLOCK_N + et] = in ? p.bn_beta[col] - mean * scale : 0.f;
-        }
-        asm volatile("bar.sync 2, 256;" ::: "memory");     // constants visible to every epilogue thread
         ptx::mbar_wait(bn_bar, tc & 1);
       }
       ptx::mbar_wait(&tmem_full[slot], aph);
@@ -370,38 +384,42 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // dy = the bf16 value this tile stores; masked by the ReLU of the BN layer, reduced per channel
           const uint32_t xrow = ptx::smem_u32(sx) + (cbase >> 6) * (kBlockM * 128) + row * 128;
           const uint32_t yrow = ptx::smem_u32(sy) + (cbase >> 6) * (kBlockM * 128) + row * 128;
-          float g1[32], g2[32];
+          // two passes (sum dy_m, then sum dy_m * xhat) so that only one 32-value array is live at a time
+          float rsum[2];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int chunk = ((cbase >> 5) & 1) * 4 + c;
-            const uint32_t off = (chunk ^ (row & 7)) << 4;
-            uint32_t xw[4], yw[4] = {0, 0, 0, 0};
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(xw[0]), "=r"(xw[1]), "=r"(xw[2]), "=r"(xw[3]) : "r"(xrow + off));
-            if (p.bn_has_y)
+          for (int pass = 0; pass < 2; ++pass) {
+            float g[32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int chunk = ((cbase >> 5) & 1) * 4 + c;
+              const uint32_t off = (chunk ^ (row & 7)) << 4;
+              uint32_t xw[4], yw[4] = {0, 0, 0, 0};
               asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                           : "=r"(yw[0]), "=r"(yw[1]), "=r"(yw[2]), "=r"(yw[3]) : "r"(yrow + off));
+                           : "=r"(xw[0]), "=r"(xw[1]), "=r"(xw[2]), "=r"(xw[3]) : "r"(xrow + off));
+              if (p.bn_has_y)
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(yw[0]), "=r"(yw[1]), "=r"(yw[2]), "=r"(yw[3]) : "r"(yrow + off));
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[j]));
-              const float2 yv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[j]));
+              for (int j = 0; j < 4; ++j) {
+                const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[j]));
+                const float2 yv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[j]));
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int jj = c * 8 + 2 * j + e;
-                const int cc = c32 * 32 + grp * kColsPerGrp + jj;        // column inside the tile
-                const float xe = e == 0 ? xv.x : xv.y, ye = e == 0 ? yv.x : yv.y;
-                const float dyv = __bfloat162float(__float2bfloat16_rn(f[jj]));
-                bool keep = row_ok;
-                if (p.bn_relu)
-                  keep = keep && (p.bn_has_y ? ye > 0.f : fmaf(xe, sconst[2 * BLOCK_N + cc], sconst[3 * BLOCK_N + cc]) > 0.f);
-                // rows beyond the tensor hold stale shared memory (possibly NaN): select, never multiply
-                g1[jj] = keep ? dyv : 0.f;
-                g2[jj] = keep ? dyv * ((xe - sconst[cc]) * sconst[BLOCK_N + cc]) : 0.f;
+                for (int e = 0; e < 2; ++e) {
+                  const int jj = c * 8 + 2 * j + e;
+                  const int cc = cbase + jj;                                        // column inside the tile
+                  const float xe = e == 0 ? xv.x : xv.y, ye = e == 0 ? yv.x : yv.y;
+                  const float dyv = __bfloat162float(__float2bfloat16_rn(f[jj]));
+                  const float4 kc4 = reinterpret_cast<const float4*>(sconst)[cc];   // mean, rstd, scale, shift
+                  bool keep = row_ok;
+                  if (p.bn_relu) keep = keep && (p.bn_has_y ? ye > 0.f : fmaf(xe, kc4.z, kc4.w) > 0.f);
+                  // rows beyond the tensor hold stale shared memory (possibly NaN): select, never multiply
+                  g[jj] = keep ? (pass == 0 ? dyv : dyv * ((xe - kc4.x) * kc4.y)) : 0.f;
+                }
               }
             }
+            rsum[pass] = warp_colsum32(g, lane);
           }
-          const float r1 = warp_colsum32(g1, lane);
-          const float r2 = warp_colsum32(g2, lane);
+          const float r1 = rsum[0], r2 = rsum[1];
           const int col = n0 + cbase + lane;
           if (col < p.N) {
             if (local_stats) {
@@ -428,6 +446,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       ptx::fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (BNR && et == 0 && t + (int)gridDim.x < total_tiles)   // x / y buffers are free: prefetch the next tile's
+        issue_bn_tiles<BLOCK_N, kConv>(p, t + (int)gridDim.x, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
       if (et == 0) {
 #pragma unroll
         for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) {

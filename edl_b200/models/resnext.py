@@ -91,10 +91,16 @@ class FoldedConv(nn.Module):
                 return y
             ops.gemm_bf16(x2, self.weight.view(self.cout, self.cin), out=y2)
             return ops.scale_shift_act(y, self.scale, self.shift, residual, self.relu)
-        if (self.k == 3 and self.stride == 1 and residual is None and self.own_conv3
+        if (self.k == 3 and residual is None and self.own_conv3 and self.stride in (1, 2)
                 and ops.conv3x3_infer_supported(x, self.weight, self.groups)):
             # dense or grouped 3x3 on the persistent tcgen05 kernel, folded BN + ReLU in its epilogue
-            return ops.conv3x3_infer(x, self.weight, self.scale, self.shift, self.relu, self.groups)
+            y = ops.conv3x3_infer(x, self.weight, self.scale, self.shift, self.relu, self.groups)
+            if self.stride == 2:
+                # 3x3 / pad 1 / stride 2 == the stride-1 result sampled at even positions.  4x the MMA work
+                # of a strided kernel, still ~100x faster than the library's grouped stride-2 path
+                # (conv2d_grouped_direct_kernel: 26 ms per layer, profiles/teacher_r1.txt)
+                y = y[:, :, ::2, ::2].contiguous(memory_format=torch.channels_last)
+            return y
         y = F.conv2d(x, self.weight.permute(0, 3, 1, 2), None, self.stride, (self.k - 1) // 2, 1, self.groups)
         return ops.scale_shift_act(y, self.scale, self.shift, residual, self.relu)
 
