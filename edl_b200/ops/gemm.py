@@ -240,7 +240,12 @@ def _bn_fusable(hook, x, channels) -> bool:
             and channels % 8 == 0 and native().persistent_gemm_enabled())
 
 
-FUSE_BN_BWD = __import__("os").environ.get("EDL_FUSE_BN_BWD", "1") == "1"
+# EXPERIMENTAL, off by default.  The epilogue reduction itself is exact (tests/test_persist_gpu.py checks it
+# against the fp32 reference for 1x1 / 3x3 / residual-mask / partial-tile cases), but (a) with 31+31 shuffles
+# and 64 extra shared loads per 32 columns the short-K dgrad kernels become epilogue-bound: 46-59 us instead
+# of 15 us + a 12-14 us streaming reduce kernel (profiles/README.md), and (b) the model-level gradient
+# comparison still shows a mismatch that is not understood yet.  Kept for round 2.
+FUSE_BN_BWD = __import__("os").environ.get("EDL_FUSE_BN_BWD", "0") == "1"
 
 
 class _LinearFn(torch.autograd.Function):

@@ -101,35 +101,51 @@ def test_conv1x1_fork_sums_both_gradients_in_the_dgrad_epilogue():
     assert _rel(x2.grad, xr2.grad) < 1e-2
 
 
-@pytest.mark.parametrize("layers,width", [(50, 0.5), (18, 1.0)])
-def test_bn_backward_reduction_fused_into_dgrad_matches_separate_kernels(layers, width):
-    """conv -> BN -> conv chains: the second conv's dgrad epilogue carries the BN-backward reduction
-    (1x1, 3x3 and fork/residual variants); gradients must match the path with the separate reduce kernel."""
-    from edl_b200.models import ResNetVd, to_train_dtype
-    from edl_b200.ops import gemm as G
+def _bn_ref_sums(dy, x, y, mean, rstd, gamma, beta, relu):
+    dyf, xf = dy.float(), x.float()
+    if relu:
+        mask = (y.float() > 0) if y is not None else (torch.addcmul(beta - mean * gamma * rstd, xf, gamma * rstd) > 0)
+        dyf = dyf * mask
+    return torch.cat([dyf.sum(0), (dyf * ((xf - mean) * rstd)).sum(0)])
 
-    torch.manual_seed(0)
-    m = to_train_dtype(ResNetVd(layers, class_dim=32, width_mult=width), torch.bfloat16, DEV).train()
-    x = torch.randn(8, 3, 64, 64, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
-    t = torch.softmax(torch.randn(8, 32, device=DEV), -1)
-    grads = []
-    launches = []
-    try:
-        for fuse in (True, False):
-            G.FUSE_BN_BWD = fuse
-            for p in m.parameters():
-                p.grad = None
-            ops.reset_launches()
-            ops.soft_cross_entropy(m(x), t).backward()
-            torch.cuda.synchronize()
-            launches.append(ops.launches())
-            grads.append([p.grad.detach().float().clone() for p in m.parameters()])
-    finally:
-        G.FUSE_BN_BWD = True
-    if layers == 50:
-        assert launches[0] <= launches[1] - 30        # >= 30 BN reduce kernels disappeared
-    errs = sorted(((_rel(a, b), n) for (n, _), a, b in zip(m.named_parameters(), *grads)), reverse=True)
-    assert errs[0][0] < 2e-2, errs[:8]
+
+def _hook(x, y, n, relu):
+    from edl_b200.ops.bn import BNBackwardHook
+
+    h = BNBackwardHook()
+    h.x, h.y, h.relu = x, y, relu
+    h.mean, h.rstd = torch.randn(n, device=DEV) * 0.1, torch.rand(n, device=DEV) + 0.5
+    h.gamma, h.beta = torch.rand(n, device=DEV) + 0.5, torch.randn(n, device=DEV) * 0.2
+    h.dsums = torch.zeros(2 * n, device=DEV)
+    return h
+
+
+@pytest.mark.parametrize("m,k,n", [(2048, 64, 32), (5000, 64, 128), (6272, 512, 256), (300, 64, 1024)])
+@pytest.mark.parametrize("relu,has_y", [(True, False), (True, True), (False, False)])
+def test_dgrad_epilogue_bn_backward_reduction_gemm(m, k, n, relu, has_y):
+    """(experimental path, off by default) the 1x1 dgrad epilogue reduces sum(dy_m), sum(dy_m * xhat) of the tile."""
+    torch.manual_seed(5)
+    a = torch.randn(m, k, device=DEV).bfloat16()
+    w = (torch.randn(k, n, device=DEV) * 0.1).bfloat16()
+    x = torch.randn(m, n, device=DEV).bfloat16()
+    y = torch.randn(m, n, device=DEV).bfloat16() if has_y else None
+    h = _hook(x, y, n, relu)
+    d = ops.gemm_bf16(a, w, b_mn_major=True, bn=h)
+    assert h.done and _rel(d, a.float() @ w.float()) < 1e-2
+    assert _rel(h.dsums, _bn_ref_sums(d, x, y, h.mean, h.rstd, h.gamma, h.beta, relu)) < 1e-4
+
+
+@pytest.mark.parametrize("nb,c,hh,ww", [(8, 64, 16, 16), (32, 256, 14, 14), (5, 64, 11, 20), (8, 256, 2, 2)])
+def test_dgrad_epilogue_bn_backward_reduction_conv3x3(nb, c, hh, ww):
+    torch.manual_seed(6)
+    dy = torch.randn(nb, c, hh, ww, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(c, 3, 3, c, device=DEV) * 0.05).bfloat16()
+    x = torch.randn(nb, c, hh, ww, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    h = _hook(x, None, c, True)
+    dx = torch.empty_like(x)
+    ops.native().conv3x3(dy, wt, dx, True, None, h.as_list(nb * hh * ww, c), True)
+    d2, x2 = dx.permute(0, 2, 3, 1).reshape(-1, c), x.permute(0, 2, 3, 1).reshape(-1, c)
+    assert _rel(h.dsums, _bn_ref_sums(d2, x2, None, h.mean, h.rstd, h.gamma, h.beta, True)) < 1e-4
 
 
 @pytest.mark.parametrize("n,c,cout,h,w,groups", [(4, 2048, 2048, 14, 14, 32), (4, 4096, 4096, 7, 7, 32), (2, 256, 256, 12, 12, 4),
