@@ -15,74 +15,104 @@ from ..trainer import StudentTrainer
 from .device_feed import DeviceDistillLink
 
 
+_EAGER_STEPS = 4     # protocol steps run eagerly on both sides before the per-slot CUDA graphs are captured
+
+
 class DistillStudentTrainer(StudentTrainer):
-    """StudentTrainer whose targets arrive from the paired teacher GPU instead of the host."""
+    """StudentTrainer whose targets arrive from the paired teacher GPU instead of the host.
+
+    Software-pipelined by one batch: protocol step ``k`` ships batch ``k`` to the teacher (ring slot
+    ``k % 2``) and trains on batch ``k - 1``, whose logits the teacher produced while the student was busy
+    with step ``k - 1``.  Student and teacher therefore overlap completely and the pair runs at
+    max(student step, teacher forward) instead of their sum.  Step 0 only ships.  One CUDA graph per slot."""
 
     def __init__(self, model, batch_size, link: DeviceDistillLink, **kw):
         kw.setdefault("target_kind", "logits")
         super().__init__(model, batch_size, **kw)
+        assert link.slots >= 2, "the pipelined student needs a 2-slot link"
         self.link = link
+        self.static_xs = [self.static_x, torch.zeros_like(self.static_x)]
+        self.seq_prev = torch.zeros_like(link.seq)           # sequence number of the batch being trained on
+        self.k = 0
+        self.graphs = [None, None]
+        self.launches_per_slot = [0, 0]
 
-    def _step_body(self):
-        self.link.seq.add_(1)                       # device-side step counter (graph replay safe)
+    def _body(self, p: int, train: bool):
+        self.seq_prev.copy_(self.link.seq)
+        self.link.seq.add_(1)                                # device-side counters (graph replay safe)
         self.dp.zero_grad()
         if self.arena is not None:
             self.arena.zero()
-        x = self.static_x
-        self.link.send_images(x, 0, seq=self.link.seq)      # -> teacher HBM, flag release
+        self.link.send_images(self.static_xs[p], p, seq=self.link.seq)      # batch k -> teacher HBM
+        if not train:
+            return
+        x = self.static_xs[1 - p]
         logits = self.model(x if x.dtype == self.dtype else x.to(self.dtype))
-        loss = self.link.loss(logits, 0, seq=self.link.seq)  # acquires the teacher's logits, fused soft-CE
+        loss = self.link.loss(logits, 1 - p, seq=self.seq_prev)  # acquires the teacher's logits of batch k-1
         loss.backward()
         self.dp.finish()
         self.opt.step()
         self.static_loss.copy_(loss.detach())
 
+    def step_device(self):
+        p = self.k % 2
+        if not self.use_graph or self.k < _EAGER_STEPS:
+            self._body(p, train=self.k > 0)
+        else:
+            if self.graphs[p] is None:
+                s = torch.cuda.Stream(device=self.device, priority=-1)
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                before = ops.launches()
+                with torch.cuda.graph(g, stream=s):
+                    self._body(p, train=True)
+                self.launches_per_slot[p] = ops.launches() - before
+                self.graphs[p] = g
+            self.graphs[p].replay()
+            ops.count_launch(self.launches_per_slot[p])
+        self.k += 1
+        self.steps_done += 1
+        return self.static_loss
+
     def step(self, images, targets=None):
-        self.static_x.copy_(images, non_blocking=True)
+        self.static_xs[self.k % 2].copy_(images, non_blocking=True)
         return self.step_device()
 
 
 class TeacherWorker:
-    """Teacher side of the link: wait for the student's batch, forward, ship logits."""
+    """Teacher side of the link: wait for the student's batch in slot ``k % 2``, forward, ship the logits
+    (classifier GEMM epilogue -> student's HBM).  Same eager-then-graph schedule as the student."""
 
     def __init__(self, model, link: DeviceDistillLink, use_graph: bool = True, dtype=torch.bfloat16):
         self.model, self.link, self.dtype = model, link, dtype
         self.use_graph = use_graph
-        self.graph = None
+        self.graphs = [None, None]
         self.device = link.pool.device
         self.steps_done = 0
 
-    def _body(self):
+    def _body(self, slot: int):
         self.link.seq.add_(1)
-        img = self.link.wait_images(0, seq=self.link.seq)
+        img = self.link.wait_images(slot, seq=self.link.seq)
         img = img if img.dtype == self.dtype else img.to(self.dtype)
         if self.link.fused_fc and hasattr(self.model, "forward_features") and self.dtype == torch.bfloat16:
             feats = self.model.forward_features(img)
-            self.link.ship_linear(feats, self.model.fc_weight, self.model.fc_bias, 0, seq=self.link.seq)
+            self.link.ship_linear(feats, self.model.fc_weight, self.model.fc_bias, slot, seq=self.link.seq)
         else:
             assert not self.link.fused_fc, "link was built with fused_fc=True but the model cannot use it"
-            self.link.send_logits(self.model(img).to(torch.bfloat16), 0, seq=self.link.seq)
-
-    def capture(self, warmup: int = 3):
-        s = torch.cuda.Stream(device=self.device)
-        s.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(s):
-            for _ in range(warmup):
-                self._body()
-        torch.cuda.current_stream(self.device).wait_stream(s)
-        torch.cuda.synchronize(self.device)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._body()
-        torch.cuda.synchronize(self.device)
+            self.link.send_logits(self.model(img).to(torch.bfloat16), slot, seq=self.link.seq)
 
     def step(self):
-        if self.use_graph:
-            if self.graph is None:
-                self.capture()
-            self.graph.replay()
+        slot = self.steps_done % 2
+        if not self.use_graph or self.steps_done < _EAGER_STEPS:
+            self._body(slot)
         else:
-            self._body()
+            if self.graphs[slot] is None:
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._body(slot)
+                self.graphs[slot] = g
+            self.graphs[slot].replay()
         self.steps_done += 1
 
 
