@@ -78,7 +78,8 @@ def parse():
     a("--service_name", default="ResNeXt101_32x16d")
     a("--teacher_batch_size", type=int, default=16)
     a("--checkpoint", default=os.environ.get("PADDLE_EDL_HDFS_PATH") or "./distill_resnet_ckpt")
-    a("--data_dir", default=None, help="directory of .pt shards {'images': uint8 NHWC, 'labels': int64}; synthetic if unset")
+    a("--data_dir", default=None, help="ImageNet-style directory with train_list.txt ('path label' lines, JPEGs decoded by "
+      "paddle_edl.utils.image_pipeline) or a directory of .pt shards {'images': uint8 NHWC, 'labels': int64}; synthetic if unset")
     a("--max_steps", type=int, default=0)
     a("--width_mult", type=float, default=1.0)
     return ap.parse_args()
@@ -87,6 +88,20 @@ def parse():
 def sample_stream(args, rank, world, epoch):
     """Yields per-sample (image float32 CHW, label int64[1]) -- the 'sample list' reader format."""
     c, h, w = (int(v) for v in args.image_shape.split(","))
+    if args.data_dir and os.path.exists(os.path.join(args.data_dir, "train_list.txt")):
+        # JPEG files: threaded decode + random-resized crop into uint8 NHWC, normalised per sample here because the
+        # DistillReader protocol is per sample (the pure-DP path below the reader ships uint8 batches instead)
+        from edl_b200.utils import image_pipeline as ip
+        samples = ip.read_file_list(os.path.join(args.data_dir, "train_list.txt"))
+        ld = ip.ImageBatchLoader(samples, 64, size=h, train=True, rank=rank, world=world, seed=epoch, pin=False, drop_last=False)
+        mean = np.array([0.485, 0.456, 0.406], dtype="float32").reshape(3, 1, 1) * 255
+        std = np.array([0.229, 0.224, 0.225], dtype="float32").reshape(3, 1, 1) * 255
+        for img, lab, flip in ld:
+            arr = img.numpy()
+            for i in range(arr.shape[0]):
+                x = arr[i][:, ::-1] if int(flip[i]) else arr[i]
+                yield ((x.transpose(2, 0, 1).astype("float32") - mean) / std), np.array([int(lab[i])], dtype="int64")
+        return
     if args.data_dir:
         shards = sorted(f for f in os.listdir(args.data_dir) if f.endswith(".pt"))[rank::world]
         mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1) * 255
