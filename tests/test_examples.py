@@ -102,3 +102,14 @@ def test_recognize_digits_example(tmp_path, nn_type):
     out = run(["examples/fit_a_line/recognize_digits.py", "--nn_type", nn_type, "--epochs", "2", "--samples", "256",
                "--ckpt", str(tmp_path / "ck")])
     assert "epoch 1 loss" in out
+
+
+def test_nlp_student_and_teacher_examples(tmp_path):
+    out = run(["examples/distill/nlp/train.py", "--epochs", "2", "--samples", "256", "--vocab", "400"])
+    assert "epoch 1 loss" in out
+    tsv = tmp_path / "train.tsv"
+    tsv.write_text("text_a\tlabel\n" + "".join("good nice fine great %d\t1\nbad awful poor sad %d\t0\n" % (i, i) for i in range(40)))
+    out = run(["examples/distill/nlp/train.py", "--epochs", "3", "--train_tsv", str(tsv)])
+    assert float(out.strip().splitlines()[-1].split()[-1]) > 0.9          # dev acc on the separable toy corpus
+    out = run(["examples/distill/nlp/fine_tune.py", "--epochs", "1", "--samples", "128", "--vocab", "400", "--save", str(tmp_path / "t.pt")])
+    assert "epoch 0 loss" in out and (tmp_path / "t.pt").exists()
