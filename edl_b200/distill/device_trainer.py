@@ -36,6 +36,9 @@ class DistillStudentTrainer(StudentTrainer):
         self.k = 0
         self.graphs = [None, None]
         self.launches_per_slot = [0, 0]
+        # eager warm-up steps and the captures share ONE stream: autograd binds every parameter's gradient
+        # accumulator to the stream it first ran on, and a capture may not depend on work of another stream
+        self._stream = torch.cuda.Stream(device=self.device, priority=-1) if self.cuda else None
 
     def _body(self, p: int, train: bool):
         self.seq_prev.copy_(self.link.seq)
@@ -57,14 +60,17 @@ class DistillStudentTrainer(StudentTrainer):
     def step_device(self):
         p = self.k % 2
         if not self.use_graph or self.k < _EAGER_STEPS:
-            self._body(p, train=self.k > 0)
+            cur = torch.cuda.current_stream(self.device)
+            self._stream.wait_stream(cur)                    # the H2D copy of step() ran on the caller's stream
+            with torch.cuda.stream(self._stream):
+                self._body(p, train=self.k > 0)
+            cur.wait_stream(self._stream)
         else:
             if self.graphs[p] is None:
-                s = torch.cuda.Stream(device=self.device, priority=-1)
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
                 before = ops.launches()
-                with torch.cuda.graph(g, stream=s):
+                with torch.cuda.graph(g, stream=self._stream):
                     self._body(p, train=True)
                 self.launches_per_slot[p] = ops.launches() - before
                 self.graphs[p] = g

@@ -18,6 +18,7 @@ Here:
 from __future__ import annotations
 
 import os
+import weakref
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional
 
@@ -88,6 +89,12 @@ class ElasticDataParallel:
                  bucket_cap_mb: float = 16.0, overlap: bool = True, comm_blocks: int = 32,
                  algo: str = "auto", timeout_s: float = 60.0, average: bool = True,
                  check_finite: bool = False, track_sqnorm: bool = False):
+        # one engine per module: a second engine on the same parameters would leave the first one's
+        # autograd hooks installed (they would fire, and launch reductions, during the new engine's backward)
+        old = getattr(module, "_edl_dp_engine", None)
+        if old is not None and old() is not None:
+            old().detach()
+        module._edl_dp_engine = weakref.ref(self)
         self.module = module
         self.bucket_cap = int(bucket_cap_mb * (1 << 20))
         self.overlap = overlap
@@ -176,6 +183,12 @@ class ElasticDataParallel:
             e.param._edl_grad_ready = cb
             self._hook_handles.append(
                 e.param.register_post_accumulate_grad_hook(lambda p, _cb=cb: _cb()))
+
+    def detach(self):
+        """Remove this engine's autograd hooks (another engine is taking over the module)."""
+        for h in getattr(self, "_hook_handles", []):
+            h.remove()
+        self._hook_handles = []
 
     def _make_ready(self, eid) -> Callable[[], None]:
         def ready():
