@@ -250,13 +250,14 @@ FUSE_BN_BWD = __import__("os").environ.get("EDL_FUSE_BN_BWD", "0") == "1"
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, bias, relu, sink, ready):
+    def forward(ctx, x, w, bias, relu, sink, ready, bias_sink, bias_ready):
         x = x.contiguous()
         y = gemm_bf16(x, w, col_shift=bias.float() if bias is not None else None, relu=relu)
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.has_bias = bias is not None
         ctx.bias_dtype = bias.dtype if bias is not None else None
         ctx.sink, ctx.ready = sink, ready
+        ctx.bias_sink, ctx.bias_ready = bias_sink, bias_ready
         return y
 
     @staticmethod
@@ -269,16 +270,29 @@ class _LinearFn(torch.autograd.Function):
         dw = None
         if ctx.needs_input_grad[1]:
             dw = _wgrad(dy, x, w.shape, ctx.sink, ctx.ready)
-        db = dy.float().sum(0).to(ctx.bias_dtype) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        return dx, dw, db, None, None, None
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.float().sum(0).to(ctx.bias_dtype)
+            if ctx.bias_sink is not None:
+                # straight into the flat gradient bucket: no autograd AccumulateGrad node runs for this
+                # parameter (those are pinned to the stream of their first use, which breaks graph capture
+                # on another stream after eager steps)
+                ctx.bias_sink.add_(db)
+                if ctx.bias_ready is not None:
+                    ctx.bias_ready()
+                db = None
+        return dx, dw, db, None, None, None, None, None
 
 
 def linear_bf16(x, weight, bias=None, relu=False):
     """y = act(x @ weight^T + bias) on the tcgen05 GEMM (bias/activation fused in the epilogue).
     x [M, K] bf16, weight [N, K] bf16, bias [N] (any float dtype)."""
-    sink = getattr(weight, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
+    grad = torch.is_grad_enabled()
+    sink = getattr(weight, "_edl_grad_sink", None) if grad else None
     ready = getattr(weight, "_edl_grad_ready", None) if sink is not None else None
-    return _LinearFn.apply(x, weight, bias, relu, sink, ready)
+    bsink = getattr(bias, "_edl_grad_sink", None) if (grad and bias is not None) else None
+    bready = getattr(bias, "_edl_grad_ready", None) if bsink is not None else None
+    return _LinearFn.apply(x, weight, bias, relu, sink, ready, bsink, bready)
 
 
 class _ConvLibFn(torch.autograd.Function):
