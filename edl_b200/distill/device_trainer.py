@@ -38,7 +38,7 @@ class DistillStudentTrainer(StudentTrainer):
         self.launches_per_slot = [0, 0]
         # eager warm-up steps and the captures share ONE stream: autograd binds every parameter's gradient
         # accumulator to the stream it first ran on, and a capture may not depend on work of another stream
-        self._stream = torch.cuda.Stream(device=self.device, priority=-1) if self.cuda else None
+        self._stream = self._cap_stream                     # the module's step stream (see StudentTrainer)
 
     def _body(self, p: int, train: bool):
         self.seq_prev.copy_(self.link.seq)

@@ -96,6 +96,18 @@ class StudentTrainer:
         self.use_graph = use_graph and self.cuda
         self.graph = None
         self.steps_done = 0
+        # ONE stream per module for every optimizer step, eager or captured, of every trainer that ever
+        # drives it.  autograd pins each parameter's gradient-accumulator node to the stream of its first
+        # use and joins those "leaf streams" at the end of every backward -- a CUDA-graph capture on any
+        # other stream then fails with "dependency created on uncaptured work in another stream"
+        # (tools/diag_seq.py reproduces it with two trainers on one model).  High priority: the step is the
+        # critical chain, weight gradients run below it (parallel/ddp.py).
+        self._cap_stream = None
+        if self.cuda:
+            self._cap_stream = getattr(model, "_edl_step_stream", None)
+            if self._cap_stream is None:
+                self._cap_stream = torch.cuda.Stream(device=self.device, priority=-1)
+                model._edl_step_stream = self._cap_stream
 
     # ------------------------------------------------------------------ one step on device
     def _step_body(self):
@@ -123,7 +135,7 @@ class StudentTrainer:
             return
         # the step is captured on a HIGH-priority stream: its kernels are the critical chain, the
         # weight-gradient side stream (parallel/ddp.py) runs at low priority underneath it
-        s = torch.cuda.Stream(device=self.device, priority=-1)
+        s = self._cap_stream
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             for _ in range(warmup):
@@ -146,6 +158,12 @@ class StudentTrainer:
                 self.capture()
             self.graph.replay()
             ops.count_launch(self.launches_per_step)
+        elif self._cap_stream is not None:
+            cur = torch.cuda.current_stream(self.device)
+            self._cap_stream.wait_stream(cur)            # inputs were copied on the caller's stream
+            with torch.cuda.stream(self._cap_stream):
+                self._step_body()
+            cur.wait_stream(self._cap_stream)
         else:
             self._step_body()
         self.steps_done += 1
