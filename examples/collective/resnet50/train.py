@@ -29,6 +29,7 @@ from edl_b200.models import VGG, ResNet, ResNetVd, to_train_dtype  # noqa: E402
 from edl_b200.ops.optim import cosine_decay_with_warmup, piecewise_decay_with_warmup, scaled_lr  # noqa: E402
 from edl_b200.trainer import StudentTrainer  # noqa: E402
 from edl_b200.utils import train_status as edl_train_status  # noqa: E402
+from edl_b200.utils.metrics import StepMeter, write_benchmark_log  # noqa: E402
 
 
 def parse():
@@ -83,6 +84,7 @@ def main():
         from edl_b200.discovery.etcd_client import EtcdClient
         etcd = EtcdClient(env.etcd_endpoints, root=env.job_id)
         etcd.init()
+    meter = StepMeter(bs, world)
     for epoch in range(ts.next(), args.epochs):
         g = torch.Generator().manual_seed(epoch * 1000 + rank)       # pass_id as seed: reproducible after resume
         t0, seen = time.time(), 0
@@ -96,6 +98,7 @@ def main():
             loss = tr.step(x.pin_memory() if cuda else x, y.pin_memory() if cuda else y)
             step += 1
             seen += bs
+            meter.step()
             if it % 10 == 0 and rank == 0:
                 print("Pass %d trainbatch %d loss %.4f lr %.5f speed %.1f img/s" % (
                     epoch, it, float(loss), lr, seen * world / max(1e-6, time.time() - t0)), flush=True)
@@ -106,6 +109,7 @@ def main():
                              state_json=json.dumps({"world": world, "lr": lr}))
         if world > 1:
             dist.barrier()
+    write_benchmark_log(rank, dict(meter.summary(), model=args.model, batch_size=bs))   # reference: benchmark_logs/log_<id>
     if world > 1:
         dist.destroy_process_group()
 

@@ -169,3 +169,27 @@ def test_proto_renderings_match_runtime_schema():
         text = schema.render_proto(name)
         assert open(os.path.join(here, os.path.basename(name))).read() == text, name + " is stale: python -m edl_b200.protos.schema"
     assert "rpc Barrier(BarrierRequest) returns (BarrierResponse)" in schema.render_proto("edl/pod_server.proto")
+
+
+def test_step_meter_benchmark_log_and_metrics_endpoint(tmp_path):
+    import json
+    import time
+    import urllib.request
+    from edl_b200.utils.metrics import MetricsExporter, StepMeter, write_benchmark_log
+
+    m = StepMeter(batch_per_trainer=32, world=8, window=5)
+    for _ in range(12):
+        time.sleep(0.002)
+        m.step()
+    s = m.summary()
+    assert s["steps"] == 12 and 0 < s["avg_step_time_s"] < 0.1 and s["best_img_per_s"] > 0
+    p = write_benchmark_log(3, s, str(tmp_path / "benchmark_logs"))
+    assert json.load(open(p))["world"] == 8 and p.endswith("log_3")
+    exp = MetricsExporter(port=0, host="127.0.0.1").start()
+    try:
+        exp.set("edl_img_per_s", 6700.5, {"job": "rn50", "stage": "s1"})
+        exp.set("edl_world_size", 8)
+        body = urllib.request.urlopen("http://127.0.0.1:%d/metrics" % exp.port, timeout=5).read().decode()
+    finally:
+        exp.stop()
+    assert 'edl_img_per_s{job="rn50",stage="s1"} 6700.5' in body and "edl_world_size 8" in body
