@@ -59,7 +59,17 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (host arrival time, csv line)
+        self.windows = []        # [t_begin, t_end] of the timed regions (host clock)
+
+    def begin(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def end(self):
+        self.windows[-1][1] = time.perf_counter()
+
+    def in_window_samples(self) -> int:
+        return sum(1 for t, _ in list(self.lines) if any(a <= t <= (b or 1e30) for a, b in self.windows))
 
     def start(self):
         try:
@@ -74,7 +84,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -86,7 +96,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], 0, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # nvidia-smi was started before the warm-up (its start-up takes longer than a short timed region);
+        # only samples that arrived inside a timed window count
+        for t, ln in list(self.lines):
+            if self.windows and not any(a <= t <= (b or 1e30) for a, b in self.windows):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -169,16 +183,18 @@ def distill_main(args, world, rank, dev):
         return last
 
     warm = max(args.warmup, 7)      # 4 eager protocol steps + one graph capture per ring slot + one replay
-    run(warm, True)
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    run(warm, True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
-    sampler.start()
+    sampler.begin()
     ops.reset_launches()
     ev0.record()
     run(args.steps, False)
     ev1.record()
     sync_all()
+    sampler.end()
     launches = ops.launches()
     t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -195,6 +211,13 @@ def distill_main(args, world, rank, dev):
         e2e = {"value": B * n_students * args.steps / (e2e_ms / 1e3), "unit": "img/s", "ms_per_step": e2e_ms / args.steps,
                "h2d_bytes_per_step": B * 3 * 224 * 224 * 2, "d2h_bytes_per_step": 4, "last_loss": last,
                "timing": "host wall clock around K public-API steps (student: pinned H2D images + loss.item())"}
+    flag = torch.tensor([1.0 if (sampler.proc is not None and sampler.in_window_samples() < 3) else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)              # all ranks take the same decision: pairs step in lockstep
+    if float(flag.item()) > 0.5:
+        sampler.begin()
+        run(60, False)
+        torch.cuda.synchronize(dev)
+        sampler.end()
     clocks = sampler.stop()
     err = link.check_error()
     value = B * n_students * args.steps / (dev_ms / 1e3)
@@ -277,6 +300,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()              # streams samples from now on; only those inside the timed windows are used
     # ---- warm-up (also captures the CUDA graph) ----
     for i in range(max(args.warmup, 3)):
         loss = trainer.step(host_x[i % pool], host_t[i % pool])
@@ -289,17 +314,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sampler = ClockSampler(local_rank)
     # ---- device-timed region: K steps, inputs resident on device ----
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
-    sampler.start()
+    sampler.begin()
     ops.reset_launches()
     ev0.record()
     for _ in range(args.steps):
         trainer.step_device()
     ev1.record()
     sync_all()
+    sampler.end()
     launches = ops.launches()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
 
@@ -324,6 +349,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         sync_all()
+        sampler.begin()
         t0 = time.perf_counter()
         last = 0.0
         for i in range(args.steps):
@@ -331,11 +357,32 @@ def main():
             last = float(loss.item())
         torch.cuda.synchronize(dev)
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        sampler.end()
         e2e = {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "img/s",
                "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": d2h_bytes, "timing": "host wall clock around K public-API steps, "
                "each with pinned H2D input copy + loss.item(); max over ranks", "last_loss": last}
+    clocks_note = "samples inside the timed regions"
+
+    def few_samples_somewhere() -> bool:      # every rank must take the same decision (collectives inside a step)
+        if sampler.proc is None:              # no nvidia-smi on this box: nothing to wait for
+            return False
+        return max_over_ranks(1.0 if sampler.in_window_samples() < 3 else 0.0) > 0.5
+
+    if few_samples_somewhere():
+        # K steps can be shorter than nvidia-smi's 100 ms period: keep the same load running (untimed, after
+        # the measurement) until a few samples exist, so that a throttled or clock-locked GPU is still caught
+        sampler.begin()
+        for _ in range(8):
+            for _ in range(25):
+                trainer.step_device()
+            torch.cuda.synchronize(dev)
+            if not few_samples_somewhere():
+                break
+        sampler.end()
+        clocks_note = "timed regions + identical untimed steps right after them (timed region < sampling period)"
     clocks = sampler.stop()
+    clocks["window"] = clocks_note
 
     value = B * world * args.steps / (dev_ms / 1e3)
     if rank == 0:
