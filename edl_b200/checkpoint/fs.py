@@ -94,6 +94,9 @@ class HDFSClient(FS):
     def download(self, remote, local): self._run(["-get", remote, local])
 
 
+BDFS = HDFSClient        # the reference's name for the same client (fleet.utils.fs / BDFS(hdfs_name, ugi, time_out, sleep))
+
+
 def get_fs(hdfs_name=None, hdfs_ugi=None):
     """HDFS when configured *and* the CLI exists, else LocalFS."""
     if hdfs_name and hdfs_ugi:
