@@ -19,6 +19,7 @@ watch events are pushed with ``watch_id``.  Run standalone with
 from __future__ import annotations
 
 import argparse
+import os
 import logging
 import socket
 import socketserver
@@ -97,6 +98,39 @@ class KVState:
         self._next_lease = int(time.time() * 1000) % (1 << 30) + 1
         self.events = deque(maxlen=history)      # (rev, type, key, kv-wire)
         self.watchers: Dict[Tuple[int, int], "_Watcher"] = {}
+
+    # -- durability ------------------------------------------------------------------------
+    def snapshot(self) -> bytes:
+        """Consistent image of keys, revision counter and leases (remaining TTLs); watchers / history are not
+        part of it -- clients re-watch from their last seen revision and get a compaction-style full resync."""
+        with self.lock:
+            now = time.monotonic()
+            return msgpack.packb({
+                "rev": self.rev, "next_lease": self._next_lease,
+                "kv": [[k, v.value, v.create_rev, v.mod_rev, v.version, v.lease] for k, v in self.kv.items()],
+                "leases": [[l.id, l.ttl, max(0.0, l.expiry - now)] for l in self.leases.values()],
+            }, use_bin_type=True)
+
+    def restore(self, blob: bytes, lease_grace: float = 0.0):
+        """Load a snapshot.  Leases get at least ``lease_grace`` seconds so that clients that survived the
+        store restart can refresh them before their keys expire."""
+        d = msgpack.unpackb(blob, raw=False)
+        with self.lock:
+            self.rev = int(d["rev"])
+            self._next_lease = max(self._next_lease, int(d["next_lease"]))
+            self.kv = {k: _KeyValue(val, cr, mr, ver, lease) for k, val, cr, mr, ver, lease in d["kv"]}
+            self.leases = {}
+            now = time.monotonic()
+            for lid, ttl, remaining in d["leases"]:
+                le = _Lease(lid, ttl)
+                le.expiry = now + max(remaining, lease_grace)
+                self.leases[lid] = le
+            for k, v in self.kv.items():
+                if v.lease:
+                    if v.lease in self.leases:
+                        self.leases[v.lease].keys.add(k)
+                    else:
+                        v.lease = 0
 
     # -- mutations (call with lock held) ---------------------------------------------------
     def _emit(self, typ: str, key: str, wire: dict):
@@ -298,8 +332,21 @@ class _Server(socketserver.ThreadingTCPServer):
 class KVServer:
     """In-process handle: ``KVServer(port=0).start()``; ``.endpoint`` is ``"127.0.0.1:port"``."""
 
-    def __init__(self, host: str = "127.0.0.1", port: int = 0):
+    def __init__(self, host: str = "127.0.0.1", port: int = 0, data_dir: Optional[str] = None,
+                 snapshot_interval: float = 2.0):
         self.state = KVState()
+        # optional durability (etcd keeps a data dir; a job whose coordination store restarts should not
+        # lose its cluster / state / job-status keys): periodic atomic snapshots, reloaded on start
+        self.data_dir, self.snapshot_interval = data_dir, snapshot_interval
+        self._snap_rev = -1
+        if data_dir:
+            os.makedirs(data_dir, exist_ok=True)
+            path = os.path.join(data_dir, "snapshot.bin")
+            if os.path.exists(path):
+                with open(path, "rb") as f:
+                    self.state.restore(f.read(), lease_grace=10.0)
+                self._snap_rev = self.state.rev
+                logger.info("restored %d keys at revision %d from %s", len(self.state.kv), self.state.rev, path)
         self.server = _Server((host, port), _Handler)
         self.server.state = self.state
         self.host, self.port = self.server.server_address[:2]
@@ -317,16 +364,43 @@ class KVServer:
         e = threading.Thread(target=self._expire_loop, name="kv-expire", daemon=True)
         e.start()
         self._threads = [t, e]
+        if self.data_dir:
+            sn = threading.Thread(target=self._snapshot_loop, name="kv-snapshot", daemon=True)
+            sn.start()
+            self._threads.append(sn)
         return self
 
     def _expire_loop(self):
         while not self._stop.wait(0.1):
             self.state.expire()
 
+    def save_snapshot(self):
+        if not self.data_dir or self.state.rev == self._snap_rev:
+            return
+        blob, rev = self.state.snapshot(), self.state.rev
+        tmp = os.path.join(self.data_dir, "snapshot.bin.tmp")
+        with open(tmp, "wb") as f:
+            f.write(blob)
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(tmp, os.path.join(self.data_dir, "snapshot.bin"))      # atomic: readers never see a torn file
+        self._snap_rev = rev
+
+    def _snapshot_loop(self):
+        while not self._stop.wait(self.snapshot_interval):
+            try:
+                self.save_snapshot()
+            except OSError as e:
+                logger.warning("snapshot failed: %s", e)
+
     def stop(self):
         self._stop.set()
         self.server.shutdown()
         self.server.server_close()
+        try:
+            self.save_snapshot()
+        except OSError:
+            pass
 
     def __enter__(self):
         return self.start()
@@ -340,9 +414,11 @@ def main(argv=None):
     ap.add_argument("--host", default="0.0.0.0")
     ap.add_argument("--port", type=int, default=2379)
     ap.add_argument("--log_level", type=int, default=20)
+    ap.add_argument("--data_dir", default=None, help="keep periodic snapshots here and reload them on start")
+    ap.add_argument("--snapshot_interval", type=float, default=2.0)
     args = ap.parse_args(argv)
     logging.basicConfig(level=args.log_level)
-    srv = KVServer(args.host, args.port).start()
+    srv = KVServer(args.host, args.port, args.data_dir, args.snapshot_interval).start()
     logger.info("kv store listening on %s", srv.endpoint)
     try:
         while True:

@@ -92,3 +92,37 @@ def test_etcd_client_surface(etcd):
     assert "perm" in [s.server for s in etcd.get_service("svc")]
     etcd.remove_service("svc")
     assert etcd.get_service("svc") == []
+
+
+def test_snapshot_restart_keeps_keys_revisions_and_leases(tmp_path):
+    import time
+    from edl_b200.store.client import KVClient
+    from edl_b200.store.kv_server import KVServer
+
+    d = str(tmp_path / "kvdata")
+    srv = KVServer(port=0, data_dir=d, snapshot_interval=0.1).start()
+    c = KVClient([srv.endpoint])
+    c.connect()
+    c.put("/job/status", b"RUNNING")
+    lease = c.lease(30.0)
+    c.put("/job/pods/a", b"pod-a", lease.id)
+    c.put("/job/status", b"SUCCEED")
+    _, meta = c.get("/job/status")
+    rev, version = meta["mod_revision"], meta["version"]
+    port = srv.port
+    c.close()
+    srv.stop()                                   # final snapshot on stop
+    srv2 = KVServer(port=port, data_dir=d).start()
+    try:
+        c2 = KVClient([srv2.endpoint])
+        c2.connect()
+        v, meta = c2.get("/job/status")
+        assert v == b"SUCCEED" and meta["mod_revision"] == rev and meta["version"] == version
+        v, meta = c2.get("/job/pods/a")
+        assert v == b"pod-a" and meta["lease"] == lease.id
+        assert c2.lease_keepalive(lease.id) > 0            # the lease survived and can be refreshed
+        r = c2.put("/job/new", b"x")
+        assert r["kv"]["mod_revision"] > rev if "kv" in r else True
+        c2.close()
+    finally:
+        srv2.stop()
