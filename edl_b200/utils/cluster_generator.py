@@ -64,12 +64,22 @@ class Generator:
         return self._dead.is_set()
 
     # ------------------------------------------------------------------ core
+    def _limit(self):
+        """Pod count the job may use right now: ``max_nodes`` unless a scheduler asked for fewer (ScaleIn)."""
+        try:
+            v = self._etcd.get_value(constants.ETCD_SCALE, "target")
+            if v:
+                return max(self._job_env.min_nodes, min(self._job_env.max_nodes, int(v)))
+        except Exception:  # noqa: BLE001
+            pass
+        return self._job_env.max_nodes
+
     def _build_from_scratch(self, resource, failed):
         live = {pid: p for pid, p in resource.items() if pid not in failed}
         if self._pod_id not in live:
             raise EdlGenerateClusterError("leader {} has no resource record".format(self._pod_id))
         ordered = [live[self._pod_id]] + [p for pid, p in sorted(live.items()) if pid != self._pod_id]
-        ordered = ordered[:self._job_env.max_nodes]
+        ordered = ordered[:self._limit()]
         c = edl_cluster.Cluster()
         c._pods = ordered
         c.new_stage()
@@ -77,7 +87,7 @@ class Generator:
         return c
 
     def _append_inited(self, current, resource, inited):
-        room = self._job_env.max_nodes - len(current.pods)
+        room = self._limit() - len(current.pods)
         have = current.get_pods_ids_set()
         new = [resource[pid] for pid in sorted(inited) if pid in resource and pid not in have][:max(0, room)]
         if not new:
@@ -103,7 +113,11 @@ class Generator:
             if disappeared or bad:
                 logger.info("pods disappeared:%s failed:%s -> rebuilding the cluster", sorted(disappeared), sorted(bad))
                 new_cluster = self._build_from_scratch(resource, failed)
-            elif len(current.pods) < self._job_env.max_nodes:
+            elif len(current.pods) > self._limit():
+                logger.info("scale-in requested: %d pods -> %d", len(current.pods), self._limit())
+                keep = {p.id: resource[p.id] for p in current.pods if p.id in resource}     # current members only
+                new_cluster = self._build_from_scratch(keep, failed)
+            elif len(current.pods) < self._limit():
                 waiting = (set(resource) - cur_ids) & (inited | (set(resource) - running - succeed - failed))
                 if waiting and not edl_train_status.any_near_the_end(etcd, cur_ids, timeout=5):
                     new_cluster = self._append_inited(current, resource, waiting)

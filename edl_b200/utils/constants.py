@@ -19,6 +19,7 @@ ETCD_TRAIN_STATUS = "train_status"
 ETCD_CLUSTER = "cluster"
 ETCD_READER = "reader"
 ETCD_STATE = "state"
+ETCD_SCALE = "scale"        # scale/target = pod count an external scheduler asked for (ScaleIn / ScaleOut RPCs)
 ETCD_POD_LEADER = "0"   # key of the leader record inside the rank table
 
 ETCD_CONN_TIMEOUT = _f("EDL_ETCD_CONN_TIMEOUT", 6)
@@ -30,7 +31,7 @@ RESCALE_BARRIER_TIMEOUT = _f("EDL_RESCALE_BARRIER_TIMEOUT", 60)
 KILL_GRACE = _f("EDL_KILL_GRACE", 3)
 
 ALL_TABLES = [ETCD_POD_RESOURCE, ETCD_POD_RANK, ETCD_POD_STATUS, ETCD_JOB_STATUS, ETCD_TRAIN_STATUS,
-              ETCD_CLUSTER, ETCD_READER, ETCD_STATE]
+              ETCD_CLUSTER, ETCD_READER, ETCD_STATE, ETCD_SCALE]
 
 
 def clean_etcd(etcd):

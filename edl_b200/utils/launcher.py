@@ -43,6 +43,15 @@ class Launcher:
                     c.close()
             except exceptions.EdlException as e:
                 last_err = e
+                # evicted (scale-in / cluster full): the stored cluster of a NEW stage does not list this pod --
+                # hand it to the caller, whose _adopt() then lets the pod leave quietly instead of timing out
+                try:
+                    cur = edl_cluster.load_from_etcd(self._etcd, timeout=3)
+                except exceptions.EdlException:
+                    cur = None
+                if (self._cluster is not None and cur is not None and cur.stage != self._cluster.stage
+                        and cur.get_pod_by_id(self._pod.id) is None):       # (a joiner keeps waiting to be appended)
+                    return cur
                 time.sleep(min(1.0, constants.POLL_INTERVAL))
         raise exceptions.EdlBarrierError("barrier did not complete in {}s: {}".format(timeout, last_err))
 

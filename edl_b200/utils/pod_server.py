@@ -19,10 +19,23 @@ class PodServerServicer:
         if leader_id != self._pod_id:
             raise exceptions.EdlLeaderError("this pod {} is not the leader {}".format(self._pod_id, leader_id))
 
+    # ScaleOut / ScaleIn: the hooks an external scheduler uses to resize a running job.  The reference
+    # declares them but leaves them empty (python/edl/utils/pod_server.py:47-67).  Here the leader records
+    # the requested pod count under ``scale/target``; the cluster generator (same pod) honours it on its
+    # next pass: surplus pods drop out of the rank table (they idle as stand-bys), a raised target lets
+    # waiting pods back in.  ``nodes_range`` still bounds the target.
+    def _set_target(self, target):
+        from . import constants
+
+        target = max(self._job_env.min_nodes, min(self._job_env.max_nodes, int(target)))
+        self._etcd.set_server_permanent(constants.ETCD_SCALE, "target", str(target))
+        return target
+
     def ScaleOut(self, request, context):
         status = schema.common.Status()
         try:
             self._check_leader()
+            self._set_target(self._job_env.max_nodes)
         except exceptions.EdlException as e:
             exceptions.serialize(status, e)
         return status
@@ -31,6 +44,9 @@ class PodServerServicer:
         status = schema.common.Status()
         try:
             self._check_leader()
+            cluster = edl_cluster.load_from_etcd(self._etcd, timeout=3)
+            cur = len(cluster.pods) if cluster is not None else self._job_env.max_nodes
+            self._set_target(cur - max(0, int(request.num)))
         except exceptions.EdlException as e:
             exceptions.serialize(status, e)
         return status

@@ -120,6 +120,35 @@ def test_generator_barrier_scale_out_and_in(etcd, kv_server):
         time.sleep(0.1)
     assert c.get_pods_ids_list() == [pods[0].id, pods[2].id]
     assert [t.global_rank for p in c.pods for t in p.trainers] == [0, 1]
+    # ---- scheduler-driven resize through the leader's ScaleIn / ScaleOut RPCs
+    je.min_nodes = 1                                     # (shared job env) wider range for this part
+    regs[1] = resource_pods.Register(je, pods[1].id, pods[1].to_json(), etcd=etcd)       # pod 1 comes back
+    train_status.save_to_etcd(etcd, pods[0].id, train_status.TrainStatus.RUNNING)
+    edl_status.save_pod_status_to_etcd(etcd, pods[1].id, edl_status.Status.INITIAL)
+
+    def wait_pods(n, not_stage):
+        deadline = time.time() + 15
+        while time.time() < deadline:
+            cc = edl_cluster.load_from_etcd(etcd)
+            if len(cc.pods) == n and cc.stage != not_stage:
+                return cc
+            time.sleep(0.1)
+        raise AssertionError("cluster did not reach %d pods: %s" % (n, edl_cluster.load_from_etcd(etcd).get_pods_ids_list()))
+
+    c3 = wait_pods(3, c.stage)
+    lcli = pod_server_client.Client(pods[0].endpoint)
+    with pytest.raises(exceptions.EdlLeaderError):
+        pod_server_client.Client(pods[2].endpoint).scale_in(1)        # only the leader takes resize requests
+    lcli.scale_in(1)
+    c2 = wait_pods(2, c3.stage)
+    assert c2.pods[0].id == pods[0].id and len(c2.get_pods_ids_set() & {pods[1].id, pods[2].id}) == 1
+    for p in c2.pods:
+        edl_status.save_pod_status_to_etcd(etcd, p.id, edl_status.Status.RUNNING)
+    dropped = ({p.id for p in pods} - c2.get_pods_ids_set()).pop()
+    edl_status.save_pod_status_to_etcd(etcd, dropped, edl_status.Status.INITIAL)   # an evicted pod re-enters as a joiner
+    lcli.scale_out()
+    c3b = wait_pods(3, c2.stage)
+    assert c3b.get_pods_ids_set() == {p.id for p in pods}
     leader.stop()
     for r in (regs[0], regs[2]):
         r.stop()
