@@ -233,7 +233,29 @@ class ElasticManager:
         kvs, _ = self.etcd.get_prefix(self.node_prefix)
         self._node_keys = [kv["key"] for kv in kvs]
         self.hosts = [kv["value"].decode() for kv in kvs]
+        if len(self.hosts) != self.np and self.hosts:
+            self._adapt_np(len(self.hosts))
         return len(self.hosts) == self.np
+
+    def _adapt_np(self, live: int):
+        """Fault-tolerance levels (doc/edl_live_fault_tolerance.md:81-96): 1 = wait for a replacement node
+        (np never changes), 2 = shrink to the surviving nodes, 3 = fully elastic (shrink and grow).  The new np
+        is published in the store so that every node takes the same decision; a node only shrinks after the
+        membership has been stable for one lease TTL (a late starter is not a lost node)."""
+        if self.elastic_level < 2 or live == self.np:
+            return
+        if live > self.np and self.elastic_level < 3:
+            return
+        now = time.time()
+        if getattr(self, "_np_candidate", None) != live:
+            self._np_candidate, self._np_since = live, now
+            return
+        if now - self._np_since < self.node_ttl:
+            return
+        logger.info("fault-tolerance level %d: np %d -> %d", self.elastic_level, self.np, live)
+        self.np = live
+        self.etcd.put(self.np_path, "%d" % live)
+        self._np_candidate = None
 
     def _update_hosts(self):
         assert len(self.hosts) != 0, "hosts empty"
@@ -268,6 +290,7 @@ class ElasticManager:
         if self.stopped:
             return
         self.launcher = launcher(self.args)
+        self._np_at_launch = self.np
         self.launcher.launch()
 
     def watch(self):
@@ -280,7 +303,9 @@ class ElasticManager:
                 if completed:
                     return ElasticStatus.COMPLETED
                 return ElasticStatus.RESTART if self.elastic_level == 1 else ElasticStatus.ERROR
-            if self.enable and not self._completed() and not self._match():
+            if self.enable and not self._completed() and (not self._match() or self.np != self._np_at_launch):
+                # membership differs from np, or np itself changed (scheduler resize / level-2 shrink):
+                # the running trainers have a stale world size
                 self.launcher.stop()
                 return ElasticStatus.HOLD
             time.sleep(self.poll_s)
