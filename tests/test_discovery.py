@@ -80,9 +80,15 @@ def test_two_discovery_servers_redirect(kv_server):
     p1, p2 = find_free_ports(2)
     with DiscoveryServer("127.0.0.1:%d" % p1, [kv_server.endpoint]) as s1, \
             DiscoveryServer("127.0.0.1:%d" % p2, [kv_server.endpoint]) as s2:
-        time.sleep(0.5)   # let both learn about each other
+        names = ("SvcA", "SvcB", "SvcC", "SvcD", "SvcE", "SvcF")
+        deadline = time.time() + 15            # let both learn about each other (watch-driven, no fixed sleep)
+        while time.time() < deadline:
+            if all(s1.table._owner(n)[0] == s2.table._owner(n)[0] for n in names) and \
+                    {s1.table._owner(n)[0] for n in names} == {s1.server, s2.server}:
+                break
+            time.sleep(0.1)
         owners = set()
-        for name in ("SvcA", "SvcB", "SvcC", "SvcD", "SvcE", "SvcF"):
+        for name in names:
             owners.add(s1.table._owner(name)[0])
             assert s1.table._owner(name)[0] == s2.table._owner(name)[0]
         assert owners == {s1.server, s2.server}                         # the ring spreads services
