@@ -22,7 +22,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from edl_b200 import ops  # noqa: E402
-from edl_b200.models.ctr_dnn import CtrDnn, auc  # noqa: E402
+from edl_b200.models.ctr_dnn import CtrDnn, DeepFM, auc  # noqa: E402
 from edl_b200.parallel import ElasticDataParallel  # noqa: E402
 
 
@@ -75,6 +75,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1000)
     ap.add_argument("--vocab", type=int, default=100001, help="1000001 in the reference")
     ap.add_argument("--lr", type=float, default=1e-4)
+    ap.add_argument("--model", default="ctr_dnn", choices=["ctr_dnn", "deepfm"])
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
@@ -93,7 +94,7 @@ def main():
         result["sweep"] = sweep(dev, world, rank)
     else:
         torch.manual_seed(0)
-        model = CtrDnn(sparse_feature_dim=args.vocab).to(dev)
+        model = (DeepFM if args.model == "deepfm" else CtrDnn)(sparse_feature_dim=args.vocab).to(dev)
         dp = ElasticDataParallel(model, bucket_cap_mb=64)
         opt = ops.FlatAdam(dp.flat, lr=args.lr)
         gen = torch.Generator(device=dev).manual_seed(100 + rank)

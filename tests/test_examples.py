@@ -113,3 +113,35 @@ def test_nlp_student_and_teacher_examples(tmp_path):
     assert float(out.strip().splitlines()[-1].split()[-1]) > 0.9          # dev acc on the separable toy corpus
     out = run(["examples/distill/nlp/fine_tune.py", "--epochs", "1", "--samples", "128", "--vocab", "400", "--save", str(tmp_path / "t.pt")])
     assert "epoch 0 loss" in out and (tmp_path / "t.pt").exists()
+
+
+@pytest.mark.parametrize("model", ["ctr_dnn", "deepfm"])
+def test_ctr_example_trains(model):
+    out = run(["examples/ctr/train.py", "--model", model, "--steps", "12", "--batch", "64", "--vocab", "101"])
+    assert "step 10 loss" in out and "examples_per_s" in out
+
+
+def test_deepfm_second_order_term_matches_pairwise_sum():
+    """The (sum^2 - sum of squares)/2 identity against the explicit sum over slot pairs."""
+    import torch
+
+    from edl_b200.models.ctr_dnn import DeepFM
+
+    torch.manual_seed(0)
+    m = DeepFM(sparse_feature_dim=31, embedding_size=4, num_sparse=5, num_dense=3, hidden=(8,))
+    for t in m.first_order:
+        torch.nn.init.normal_(t.weight)
+    dense = torch.rand(6, 3)
+    ids = torch.randint(0, 31, (6, 5, 1))
+    logit = m(dense, ids)
+    assert logit.shape == (6, 2) and torch.all(logit[:, 0] == 0)
+    embs = m.slot_embeddings(ids)
+    pair = sum((embs[i] * embs[j]).sum(1) for i in range(5) for j in range(i + 1, 5))
+    first = m.dense_first(dense)[:, 0] + sum(m.first_order[s](ids[:, s])[:, 0] for s in range(5))
+    x = torch.cat(embs + [dense], 1)
+    for fc in m.fcs:
+        x = torch.relu(fc(x))
+    want = first + pair + m.out(x)[:, 0]
+    assert torch.allclose(logit[:, 1], want, atol=1e-5)
+    logit[:, 1].sum().backward()
+    assert all(t.weight.grad is not None for t in m.tables)

@@ -241,6 +241,29 @@ def test_embedding_bag(dtype):
     assert _rel(out, ref) < 1e-2 and _rel(table.grad, tr.grad) < 2e-2
 
 
+@pytest.mark.parametrize("cls", ["CtrDnn", "DeepFM"])
+def test_ctr_models_use_native_embedding_bag(cls):
+    """The CTR networks on a GPU (own gather-mean / scatter-add kernels) against the same weights on the CPU."""
+    import copy
+
+    from edl_b200.models import ctr_dnn
+
+    torch.manual_seed(0)
+    cpu = getattr(ctr_dnn, cls)(sparse_feature_dim=997, embedding_size=10, num_sparse=6, hidden=(32, 32))
+    gpu = copy.deepcopy(cpu).to(DEV)
+    dense = torch.rand(64, 13)
+    ids = torch.randint(0, 997, (64, 6, 2))
+    ops.reset_launches()
+    out = gpu(dense.to(DEV), ids.to(DEV))
+    assert ops.launches() >= 6, "embedding-bag kernels were not launched"
+    ref = cpu(dense, ids)
+    assert _rel(out.cpu(), ref) < 1e-3
+    out[:, 1].sum().backward()
+    ref[:, 1].sum().backward()
+    for a, b in zip(gpu.tables, cpu.tables):
+        assert _rel(a.weight.grad.cpu(), b.weight.grad) < 1e-3
+
+
 def test_normalize_u8():
     torch.manual_seed(0)
     x = torch.randint(0, 256, (4, 20, 24, 3), device=DEV, dtype=torch.uint8)
