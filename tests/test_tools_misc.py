@@ -69,3 +69,22 @@ def test_step_profiler_window(tmp_path):
     off = StepProfiler(enabled=False)
     off.step()
     assert off.prof is None
+
+
+def test_rescale_bench_runs_on_gloo(tmp_path):
+    """tools/bench_rescale.py end to end on CPU: 3 ranks -> 2 -> 3 in place (rebuild + sync_from + LR rescale),
+    then the stop-resume path through a versioned checkpoint."""
+    out = tmp_path / "rescale.json"
+    port = 29000 + os.getpid() % 900
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "3", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "bench_rescale.py"), "--cpu", "--model", "ResNet18_vd",
+           "--width", "0.125", "--image", "32", "--classes", "10", "--batch-per-gpu", "4", "--drop", "1", "--steps", "2",
+           "--ckpt-dir", str(tmp_path / "ck"), "--out", str(out)]
+    p = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, CUDA_VISIBLE_DEVICES="", MASTER_PORT=str(port)),
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    res = json.loads(out.read_text())
+    assert res["replicas_identical_after_grow"] is True and res["comm_error"] == 0
+    for k in ("shrink_inplace_s", "grow_inplace_s", "shrink_stop_resume_s", "grow_stop_resume_s", "checkpoint_save_s"):
+        assert res[k] > 0
+    assert any(d.startswith("__edl_checkpoint__.") for d in os.listdir(tmp_path / "ck"))
