@@ -1,0 +1,339 @@
+// Weight gradient of the 3x3 / stride 1 / pad 1 NHWC convolution on tcgen05 (wgrad third).
+// The reference gets it from cuDNN through Paddle's conv2d_grad (example/distill/resnet/models/
+// resnet_vd.py:153-162); round 1 of this repo also used the library kernel on the side stream.
+//
+//   dW[co, r, s, ci] = sum over pixels (n, h, w) of  dY[n, h, w, co] * X[n, h + r - 1, w + s - 1, ci]
+//
+// As a GEMM per filter tap: M = Cout, N = Cin, K = pixels, both operands "MN-major" (the channel dimension is
+// the contiguous one in NHWC, the reduction runs over pixels):
+//   A tile = 4-D TMA box {64 ch, W, BH, NB} of dY          -> smem [KB pixel rows][64 ch = 128 B], 128B swizzle
+//   B tile = the SAME box of X shifted by (s - 1, r - 1)    -> out-of-image pixels are zero-filled by the TMA
+//                                                              unit (= the padding; no im2col, no index math)
+// One CTA owns a 128 (Cout) x 64 (Cin) tile of ONE FILTER ROW r: the dY tile of a pixel block is loaded once
+// and multiplied with the three shifted X tiles (s = 0, 1, 2) into three TMEM accumulators, so dY crosses
+// L2 -> SM once per row instead of once per tap.  The pixel reduction is split over gridDim.z CTAs; partial
+// tiles are pushed with coalesced red.global.add.v4.f32 into an all-zero fp32 workspace laid out like the
+// KRSC weight, and the LAST CTA of a tile converts it to bf16 straight into the flat gradient bucket
+// (+= when accumulating) and re-zeroes the workspace -- the same fused finalize as the 1x1 wgrad GEMM (gemm.cu).
+//
+//   warp 0      : TMA producer (2 + 3 box loads per pixel block into a 3-stage ring)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (3 accumulators x 64 fp32 columns)
+//   warps 2..5  : epilogue (tcgen05.ld -> smem staging -> vector reductions / finalize)
+#include <cuda.h>
+
+#include "gemm.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace edl {
+namespace {
+
+constexpr int kBlockM = 128;      // Cout rows per tile
+constexpr int kBlockN = 64;       // Cin columns per tile (one 128-byte swizzle span)
+constexpr int kMaxKB = 112;       // pixel rows per K block (multiple of 16; 112 = 2x56 = 4x28 = 8x14 = 16x7)
+constexpr int kUmmaK = 16;
+constexpr int kStages = 3;
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kChunkBytes = kMaxKB * 128;                 // one [KB][64 ch] operand chunk (stride in the ring)
+constexpr int kStageBytes = (2 + 3) * kChunkBytes;        // A: 2 chunks of 64 Cout; B: 3 taps x 64 Cin
+constexpr int kBarOffset = kStages * kStageBytes;
+constexpr int kSmemTotal = kBarOffset + 256 + 1024;
+constexpr uint32_t kTmemCols = 256;                       // 3 x 64 accumulator columns, power of two
+constexpr int kPitch = kBlockN * 4 + 16;                  // fp32 staging row pitch (bytes)
+constexpr int kVecPerRow = kBlockN / 4;
+
+struct WgradParams {
+  int Cout, Cin;
+  int BH, NB, HB;            // box rows / images, row blocks per image
+  int KB;                    // pixel rows per block = W * BH * NB (multiple of 16, <= kMaxKB)
+  int total_kb, kb_per_split;
+  int tiles_n;
+  float* ws;                 // fp32 [Cout][9*Cin], all zero on entry and on exit
+  __nv_bfloat16* out;        // bf16 [Cout][9*Cin] (KRSC)
+  int* counters;             // [tiles * 3], zero on entry and on exit
+  int accumulate;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+                     const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // blockIdx.x = (tile * 3 + r); tile = mt * tiles_n + nt
+  const int r = blockIdx.x % 3;
+  const int tile = blockIdx.x / 3;
+  const int m0 = (tile / p.tiles_n) * kBlockM;
+  const int n0 = (tile % p.tiles_n) * kBlockN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  int kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > p.total_kb) kb_end = p.total_kb;
+  const int num_kb = kb_end - kb_begin;
+  const bool two_chunks = m0 + 64 < p.Cout;     // Cout == 64: rows 64..127 of the accumulators are never stored
+  const uint32_t chunk_tx = (uint32_t)p.KB * 128u;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmDy);
+    ptx::prefetch_tmap(&tmX);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      // ------------------------------------------------------------ TMA producer
+      if (lane == 0) {
+        for (int i = 0; i < num_kb; ++i) {
+          const int st = i % kStages;
+          const uint32_t ph = (i / kStages) & 1;
+          ptx::mbar_wait(&empty_bar[st], ph ^ 1);
+          uint8_t* sa = smem + st * kStageBytes;
+          uint8_t* sb = sa + 2 * kChunkBytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[st], chunk_tx * (two_chunks ? 5u : 4u));
+          const int kb = kb_begin + i;
+          const int h0 = (kb % p.HB) * p.BH;
+          const int img0 = (kb / p.HB) * p.NB;
+          ptx::tma_load_4d(sa, &tmDy, &full_bar[st], m0, 0, h0, img0);
+          if (two_chunks) ptx::tma_load_4d(sa + kChunkBytes, &tmDy, &full_bar[st], m0 + 64, 0, h0, img0);
+#pragma unroll
+          for (int s = 0; s < 3; ++s)
+            ptx::tma_load_4d(sb + s * kChunkBytes, &tmX, &full_bar[st], n0, s - 1, h0 + r - 1, img0);
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------ MMA issuer (one thread)
+      if (lane == 0) {
+        constexpr uint32_t idesc = ptx::make_idesc(1, 1, kBlockM, kBlockN, 1, 1);
+        const int ksteps = p.KB / kUmmaK;
+        for (int i = 0; i < num_kb; ++i) {
+          const int st = i % kStages;
+          const uint32_t ph = (i / kStages) & 1;
+          ptx::mbar_wait(&full_bar[st], ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + st * kStageBytes);
+          const uint32_t sb = sa + 2 * kChunkBytes;
+          for (int k = 0; k < ksteps; ++k) {
+            // MN-major, 128B swizzle: 16 pixel rows = 2048 B per UMMA_K step, 8-row groups 1024 B apart,
+            // the second 64-channel chunk of A one ring chunk further
+            const uint64_t da = ptx::make_smem_desc(sa + k * 2048, kChunkBytes, 1024);
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const uint64_t db = ptx::make_smem_desc(sb + s * kChunkBytes + k * 2048, kChunkBytes, 1024);
+              ptx::umma_f16(tmem_base + s * kBlockN, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit(&empty_bar[st]);
+        }
+        ptx::umma_commit(tmem_full_bar);
+      }
+    } else {
+      // ------------------------------------------------------------ epilogue (warps 2..5)
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const int et = threadIdx.x - 64;
+      ptx::mbar_wait(tmem_full_bar, 0);
+      ptx::tc_fence_after();
+      uint8_t* sf = smem;                        // the ring is drained: fp32 staging tile
+      int rows_valid = p.Cout - m0;
+      if (rows_valid > kBlockM) rows_valid = kBlockM;
+      const int64_t ldw = (int64_t)9 * p.Cin;
+      const bool direct = gridDim.z == 1;
+#pragma unroll 1
+      for (int s = 0; s < 3; ++s) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kBlockN);
+#pragma unroll 1
+        for (int c32 = 0; c32 < kBlockN / 32; ++c32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + c32 * 32, v);
+          ptx::tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(sf + row * kPitch + c32 * 128);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            dst[c] = make_float4(__uint_as_float(v[c * 4]), __uint_as_float(v[c * 4 + 1]),
+                                 __uint_as_float(v[c * 4 + 2]), __uint_as_float(v[c * 4 + 3]));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int64_t col0 = (int64_t)(r * 3 + s) * p.Cin + n0;
+        for (int f = et; f < rows_valid * kVecPerRow; f += kEpiThreads) {
+          const int rr = f / kVecPerRow, c4 = (f % kVecPerRow) * 4;
+          float4 t = *reinterpret_cast<const float4*>(sf + rr * kPitch + c4 * 4);
+          const int64_t off = (int64_t)(m0 + rr) * ldw + col0 + c4;
+          if (direct) {
+            // this CTA saw every pixel: bf16 (+= bucket) straight from the staged tile
+            __nv_bfloat16* o = p.out + off;
+            if (p.accumulate) {
+              const uint2 old = *reinterpret_cast<const uint2*>(o);
+              const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old.x));
+              const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old.y));
+              t.x += a.x; t.y += a.y; t.z += b.x; t.w += b.y;
+            }
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(t.z, t.w);
+            uint2 packed;
+            packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+            packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(o) = packed;
+          } else {
+            red_add_v4(p.ws + off, t.x, t.y, t.z, t.w);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile is reused by the next tap
+      }
+      if (!direct) {
+        // ---- fused finalize by the last-arriving CTA of this (tile, filter row) ----
+        uint32_t* s_last = tmem_slot + 1;
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          const int old = atomicAdd(&p.counters[blockIdx.x], 1);
+          const int last = old == (int)gridDim.z - 1;
+          if (last) p.counters[blockIdx.x] = 0;
+          *s_last = (uint32_t)last;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*s_last != 0u) {
+          __threadfence();
+          const int total = rows_valid * (3 * kVecPerRow);      // the three taps of a row are adjacent in KRSC
+          // when n0 spans the whole Cin they are contiguous; in general tap s starts at (r*3+s)*Cin + n0
+          for (int f = et; f < total; f += kEpiThreads) {
+            const int rr = f / (3 * kVecPerRow);
+            const int rem = f % (3 * kVecPerRow);
+            const int s = rem / kVecPerRow, c4 = (rem % kVecPerRow) * 4;
+            const int64_t off = (int64_t)(m0 + rr) * ldw + (int64_t)(r * 3 + s) * p.Cin + n0 + c4;
+            float4 t = __ldcg(reinterpret_cast<const float4*>(p.ws + off));
+            *reinterpret_cast<float4*>(p.ws + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+            __nv_bfloat16* o = p.out + off;
+            if (p.accumulate) {
+              const uint2 old = *reinterpret_cast<const uint2*>(o);
+              const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old.x));
+              const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old.y));
+              t.x += a.x; t.y += a.y; t.z += b.x; t.w += b.y;
+            }
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(t.z, t.w);
+            uint2 packed;
+            packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+            packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(o) = packed;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+struct WgradGeometry {
+  int BH = 0, NB = 0, KB = 0;
+  bool ok = false;
+};
+
+// Pick the pixel box {W, BH rows, NB images}: W*BH*NB a multiple of 16 (UMMA_K) and <= kMaxKB, as few
+// zero-filled (out-of-image) rows as possible, then as many pixels per block as possible.
+WgradGeometry plan_wgrad(int N, int H, int W) {
+  WgradGeometry best;
+  double best_eff = 0.0;
+  if (W < 1 || W > kMaxKB || H < 1 || N < 1) return best;
+  for (int nb = 1; nb <= 16 && nb <= N; nb *= 2) {
+    for (int bh = 1; bh <= H; ++bh) {      // boxes never exceed the tensor extent (partial last blocks are zero-filled)
+      const int kb = W * bh * nb;
+      if (kb > kMaxKB) break;
+      if (kb % kUmmaK != 0) continue;
+      const int hb = (H + bh - 1) / bh, ng = (N + nb - 1) / nb;
+      const double eff = (double)H * N / ((double)hb * bh * ng * nb);
+      if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && kb > best.KB)) {
+        best_eff = eff;
+        best.BH = bh; best.NB = nb; best.KB = kb; best.ok = true;
+      }
+    }
+  }
+  return best;
+}
+
+}  // namespace
+
+bool conv3x3_wgrad_supported(int N, int H, int W, int Cin, int Cout) {
+  if (Cin % 64 != 0 || Cout % 64 != 0) return false;
+  return plan_wgrad(N, H, W).ok;
+}
+
+const char* conv3x3_wgrad_bf16(const Conv3x3WgradArgs& a, cudaStream_t stream) {
+  if (!conv3x3_wgrad_supported(a.N, a.H, a.W, a.Cin, a.Cout)) return "conv3x3_wgrad: unsupported shape";
+  if (a.ws == nullptr || a.counters == nullptr || a.dW == nullptr) return "conv3x3_wgrad: missing buffers";
+  if (a.device >= 0) {
+    cudaError_t e = cudaSetDevice(a.device);   // tensor-map encoding needs a bound context (see gemm.cu)
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+  }
+  const WgradGeometry geo = plan_wgrad(a.N, a.H, a.W);
+  alignas(64) CUtensorMap tmDy, tmX;
+  {
+    const uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
+    const uint64_t st[3] = {(uint64_t)a.Cout * 2, (uint64_t)a.W * a.Cout * 2, (uint64_t)a.H * a.W * a.Cout * 2};
+    const uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)geo.BH, (uint32_t)geo.NB};
+    if (const char* e = encode_tmap_bf16(&tmDy, a.dY, 4, dims, st, box)) return e;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
+    const uint64_t st[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)geo.BH, (uint32_t)geo.NB};
+    if (const char* e = encode_tmap_bf16(&tmX, a.X, 4, dims, st, box)) return e;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    apply_carveout((const void*)conv3x3_wgrad_kernel);
+    attr_set = true;
+  }
+  WgradParams p;
+  p.Cout = a.Cout; p.Cin = a.Cin;
+  p.BH = geo.BH; p.NB = geo.NB; p.KB = geo.KB;
+  p.HB = (a.H + geo.BH - 1) / geo.BH;
+  p.total_kb = p.HB * ((a.N + geo.NB - 1) / geo.NB);
+  int split = a.split_k < 1 ? 1 : a.split_k;
+  if (split > p.total_kb) split = p.total_kb;
+  p.kb_per_split = (p.total_kb + split - 1) / split;
+  split = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.tiles_n = a.Cin / kBlockN;
+  const int tiles_m = (a.Cout + kBlockM - 1) / kBlockM;
+  p.ws = a.ws;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a.dW);
+  p.counters = a.counters;
+  p.accumulate = a.accumulate ? 1 : 0;
+  dim3 grid(tiles_m * p.tiles_n * 3, 1, split);
+  conv3x3_wgrad_kernel<<<grid, kThreads, kSmemTotal, stream>>>(tmDy, tmX, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+int conv3x3_wgrad_tiles(int Cin, int Cout) { return ((Cout + kBlockM - 1) / kBlockM) * (Cin / kBlockN) * 3; }
+
+int conv3x3_wgrad_kblocks(int N, int H, int W) {
+  const WgradGeometry g = plan_wgrad(N, H, W);
+  if (!g.ok) return 0;
+  return ((H + g.BH - 1) / g.BH) * ((N + g.NB - 1) / g.NB);
+}
+
+}  // namespace edl

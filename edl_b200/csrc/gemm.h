@@ -81,6 +81,24 @@ struct Conv3x3Args {
 bool conv3x3_supported(int N, int H, int W, int Cin, int Cout, bool dgrad, int groups = 1);
 const char* conv3x3_bf16(const Conv3x3Args& args, cudaStream_t stream);
 
+// Weight gradient of the same convolution (conv3x3_wgrad.cu): dW[Cout,3,3,Cin] (+)= sum_pixels dY x shifted X, pixel
+// reduction split over `split_k` CTAs with the fused fp32 -> bf16 finalize of the 1x1 wgrad GEMM.
+struct Conv3x3WgradArgs {
+  const void* X = nullptr;    // bf16 NHWC [N, H, W, Cin]   (the convolution's input)
+  const void* dY = nullptr;   // bf16 NHWC [N, H, W, Cout]
+  void* dW = nullptr;         // bf16 KRSC [Cout, 3, 3, Cin] (e.g. a window of the flat gradient bucket)
+  float* ws = nullptr;        // fp32 [Cout * 9 * Cin] all-zero workspace (left all-zero)
+  int* counters = nullptr;    // >= conv3x3_wgrad_tiles(Cin, Cout) zero ints (left zero)
+  int N = 0, H = 0, W = 0, Cin = 0, Cout = 0;
+  int split_k = 1;
+  bool accumulate = false;    // dW += result instead of dW = result
+  int device = -1;
+};
+bool conv3x3_wgrad_supported(int N, int H, int W, int Cin, int Cout);
+int conv3x3_wgrad_tiles(int Cin, int Cout);
+int conv3x3_wgrad_kblocks(int N, int H, int W);   // pixel blocks of the reduction (upper bound for split_k)
+const char* conv3x3_wgrad_bf16(const Conv3x3WgradArgs& args, cudaStream_t stream);
+
 // Persistent variants (gemm_persist.cu): one CTA per SM streams tiles, double-buffered TMEM accumulators,
 // epilogue overlapped with the next tile's MMAs.  Used by gemm_bf16 / conv3x3_bf16 when enabled (default).
 void set_persistent_gemm(bool on);

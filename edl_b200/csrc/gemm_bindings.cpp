@@ -212,6 +212,43 @@ bool conv3x3_supported(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cou
   return edl::conv3x3_supported((int)n, (int)h, (int)w, (int)cin, (int)cout, dgrad, (int)groups);
 }
 
+// dW (+)= wgrad of the 3x3 / stride 1 / pad 1 conv.  x [N,Cin,H,W], dy [N,Cout,H,W] channels_last; dw KRSC
+// [Cout,3,3,Cin] bf16 contiguous; ws fp32 zeros (>= dw.numel()), counters int32 zeros.
+void conv3x3_wgrad(const Tensor& x, const Tensor& dy, Tensor& dw, Tensor& ws, Tensor& counters, int64_t split_k,
+                   bool accumulate) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 4 && dy.dim() == 4 && dw.dim() == 4);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && dy.scalar_type() == at::kBFloat16 && dw.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast) && dy.is_contiguous(at::MemoryFormat::ChannelsLast),
+              "conv3x3_wgrad needs channels_last activations");
+  TORCH_CHECK(dw.is_contiguous() && dw.size(1) == 3 && dw.size(2) == 3, "dw must be KRSC [Cout,3,3,Cin]");
+  TORCH_CHECK(ws.scalar_type() == at::kFloat && ws.is_contiguous() && ws.numel() >= dw.numel());
+  edl::Conv3x3WgradArgs a;
+  a.X = x.data_ptr();
+  a.dY = dy.data_ptr();
+  a.dW = dw.data_ptr();
+  a.ws = ws.data_ptr<float>();
+  a.N = x.size(0);
+  a.H = x.size(2);
+  a.W = x.size(3);
+  a.Cin = x.size(1);
+  a.Cout = dy.size(1);
+  TORCH_CHECK(dy.size(0) == a.N && dy.size(2) == a.H && dy.size(3) == a.W && dw.size(0) == a.Cout && dw.size(3) == a.Cin);
+  TORCH_CHECK(counters.scalar_type() == at::kInt && counters.is_contiguous() &&
+              counters.numel() >= edl::conv3x3_wgrad_tiles(a.Cin, a.Cout));
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(a.dW) % 8 == 0, "dw window must be 8-byte aligned");
+  a.counters = counters.data_ptr<int>();
+  a.split_k = (int)split_k;
+  a.accumulate = accumulate;
+  a.device = x.device().index();
+  c10::cuda::CUDAGuard guard(x.device());
+  const char* err = edl::conv3x3_wgrad_bf16(a, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(err == nullptr, "edl conv3x3_wgrad failed: ", err);
+}
+
+bool conv3x3_wgrad_supported(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cout) {
+  return edl::conv3x3_wgrad_supported((int)n, (int)h, (int)w, (int)cin, (int)cout);
+}
+
 // inference 3x3 conv (optionally grouped) with the folded-BN scale / shift / ReLU epilogue
 void conv3x3_infer(const Tensor& x, const Tensor& w, Tensor& y, const c10::optional<Tensor>& col_scale,
                    const c10::optional<Tensor>& col_shift, bool relu, int64_t groups) {
@@ -250,4 +287,8 @@ void register_gemm_bindings(pybind11::module_& m) {
   m.def("conv3x3_supported", &conv3x3_supported);
   m.def("conv3x3_infer", &conv3x3_infer);
   m.def("gemm_bf16_ship", &gemm_bf16_ship);
+  m.def("conv3x3_wgrad", &conv3x3_wgrad);
+  m.def("conv3x3_wgrad_supported", &conv3x3_wgrad_supported);
+  m.def("conv3x3_wgrad_tiles", &edl::conv3x3_wgrad_tiles);
+  m.def("conv3x3_wgrad_kblocks", &edl::conv3x3_wgrad_kblocks);
 }

@@ -413,8 +413,16 @@ class _Conv3x3Fn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             sink, ready = ctx.sink, ctx.ready
             side = _SIDE["stream"] if sink is not None else None
+            own = OWN_WGRAD3 and conv3x3_wgrad_supported(x, w)
 
             def wgrad():
+                if own:
+                    out = conv3x3_wgrad(x, dy, w.shape, sink)
+                    if sink is None:
+                        return out
+                    if ready is not None:
+                        ready()
+                    return None
                 gw = _ConvLibFn._bwd(dy, x, wv, cfg, [False, True, False])[1].permute(0, 2, 3, 1)
                 if sink is None:
                     return gw.contiguous()
@@ -433,6 +441,45 @@ class _Conv3x3Fn(torch.autograd.Function):
             else:
                 dw = wgrad()
         return dx, dw, None, None, None, None
+
+
+# EXPERIMENTAL until it has been validated on a GPU (written after the round-1 GPU budget was spent):
+# EDL_OWN_WGRAD3=1 routes the 3x3 weight gradient through csrc/conv3x3_wgrad.cu instead of the library kernel.
+OWN_WGRAD3 = __import__("os").environ.get("EDL_OWN_WGRAD3", "0") == "1"
+
+
+def conv3x3_wgrad_supported(x, weight_krsc) -> bool:
+    from . import native
+
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and weight_krsc.dtype == torch.bfloat16 and x.dim() == 4):
+        return False
+    n, c, h, w = x.shape
+    cout, kh, kw, cin = weight_krsc.shape
+    return kh == 3 and kw == 3 and cin == c and native().conv3x3_wgrad_supported(n, h, w, cin, cout)
+
+
+def conv3x3_wgrad(x, dy, weight_shape, sink=None, split_k: Optional[int] = None):
+    """dW [Cout, 3, 3, Cin] of the 3x3 / stride 1 / pad 1 convolution on the tcgen05 kernel
+    (csrc/conv3x3_wgrad.cu).  With ``sink`` (a flat bf16 window of the gradient bucket) the result is ADDED
+    into it by the kernel's fused finalize and ``None`` is returned; otherwise a new tensor is returned."""
+    from . import native, count_launch
+
+    x, dy = _cl(x), _cl(dy)
+    cout, _, _, cin = weight_shape
+    n, _, h, w = x.shape
+    tiles = native().conv3x3_wgrad_tiles(cin, cout)
+    ws, counters = _splitk_workspace(x.device, cout * 9 * cin, tiles)
+    if split_k is None:
+        kblocks = native().conv3x3_wgrad_kblocks(n, h, w)
+        # one wave of CTAs, at least two pixel blocks per CTA (same rule as the 1x1 wgrad split)
+        split_k = max(1, min(max(1, _NUM_SMS // tiles), max(1, kblocks // 2)))
+    if sink is not None:
+        out, acc = sink.view(weight_shape), True
+    else:
+        out, acc = torch.empty(tuple(weight_shape), device=x.device, dtype=torch.bfloat16), False
+    native().conv3x3_wgrad(x, dy, out, ws, counters, int(split_k), acc)
+    count_launch()
+    return None if sink is not None else out
 
 
 def conv3x3(x, weight_krsc, stats: Optional[torch.Tensor] = None):
