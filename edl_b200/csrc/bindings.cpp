@@ -7,6 +7,7 @@
 
 #include "gemm.h"
 #include "kernels.h"
+#include "launch.h"
 
 namespace {
 
@@ -412,6 +413,8 @@ void register_gemm_bindings(pybind11::module_& m);  // gemm_bindings.cpp
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "edl_b200 sm_100a kernels";
   m.def("bn_set_stream_kernels", &edl::bn_set_stream_kernels);
+  m.def("set_pdl", &edl::set_pdl, "programmatic dependent launch for the hot kernels (EDL_PDL=1)");
+  m.def("pdl_enabled", &edl::pdl_enabled);
   m.def("set_smem_carveout_policy", &edl::set_smem_carveout_policy);
   m.def("bn_fused_fits", &bn_fused_fits);
   m.def("bn_fwd_fused", &bn_fwd_fused);

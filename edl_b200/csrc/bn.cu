@@ -12,6 +12,7 @@
 //                   + bn_bwd_apply  (dx, optional dresidual, param grads).
 // All kernels are HBM-bound streaming kernels: 128-bit loads, 8 channels per thread, grid sized
 // to a multiple of the 148 SMs.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -415,6 +416,14 @@ void set_smem_carveout_policy(bool prefer_max_shared) {
   cudaDeviceSetCacheConfig(prefer_max_shared ? cudaFuncCachePreferShared : cudaFuncCachePreferNone);
 }
 bool smem_carveout_policy() { return g_prefer_max_shared; }
+
+// programmatic dependent launch switch (launch.h); EDL_PDL=1 turns it on at load time
+static bool g_pdl = [] {
+  const char* e = getenv("EDL_PDL");
+  return e != nullptr && e[0] == '1';
+}();
+bool pdl_enabled() { return g_pdl; }
+void set_pdl(bool on) { g_pdl = on; }
 void apply_carveout(const void* kernel) {
   if (g_prefer_max_shared)
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

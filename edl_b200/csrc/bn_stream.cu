@@ -12,6 +12,7 @@
 // can hold the per-channel coefficients / accumulators in registers).  Other shapes use bn.cu.
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace edl {
@@ -55,6 +56,10 @@ EDL_DEVICE Ring<NT> ring_init(uint8_t* smem_raw) {
     ptx::fence_barrier_init();
   }
   __syncthreads();
+  // programmatic dependent launch: the ring set-up above overlapped the previous kernel's tail; every kernel of
+  // this file calls ring_init() before its first global access
+  pdl_wait();
+  pdl_launch_dependents();
   return r;
 }
 
@@ -409,7 +414,7 @@ void bn_stats_stream(const void* x, float* sums, int64_t M, int C, cudaStream_t 
   const int64_t total = M * C;
   const size_t smem = ring_smem_bytes<1>() > kConsumers * 16 * 4 ? ring_smem_bytes<1>() : kConsumers * 16 * 4 + 256;
   set_smem(bn_stats_stream_kernel, smem);
-  bn_stats_stream_kernel<<<reduce_grid(total), kThreads, smem, s>>>(BF(x), sums, total, C);
+  launch_pdl(bn_stats_stream_kernel, dim3(reduce_grid(total)), dim3(kThreads), smem, s, BF(x), sums, total, C);
 }
 
 void bn_apply_stream(const void* x, const void* res, void* y, const float* sums, const float* gamma,
@@ -419,13 +424,13 @@ void bn_apply_stream(const void* x, const void* res, void* y, const float* sums,
   const int64_t total = M * C;
   if (res != nullptr) {
     set_smem(bn_apply_stream_kernel<true>, ring_smem_bytes<2>());
-    bn_apply_stream_kernel<true><<<stream_grid(total), kThreads, ring_smem_bytes<2>(), s>>>(
+    launch_pdl(bn_apply_stream_kernel<true>, dim3(stream_grid(total)), dim3(kThreads), ring_smem_bytes<2>(), s,
         BF(x), BF(res), BFW(y), sums, gamma, beta, running_mean, running_var, saved_mean, saved_rstd, total, C,
         eps, momentum, relu ? 1 : 0);
   } else {
     set_smem(bn_apply_stream_kernel<false>, ring_smem_bytes<1>());
-    bn_apply_stream_kernel<false><<<stream_grid(total), kThreads, ring_smem_bytes<1>(), s>>>(
-        BF(x), nullptr, BFW(y), sums, gamma, beta, running_mean, running_var, saved_mean, saved_rstd, total, C,
+    launch_pdl(bn_apply_stream_kernel<false>, dim3(stream_grid(total)), dim3(kThreads), ring_smem_bytes<1>(), s,
+        BF(x), (const __nv_bfloat16*)nullptr, BFW(y), sums, gamma, beta, running_mean, running_var, saved_mean, saved_rstd, total, C,
         eps, momentum, relu ? 1 : 0);
   }
 }
@@ -437,8 +442,8 @@ void bn_bwd_reduce_stream(const void* dy, const void* x, const void* y, const fl
 #define LAUNCH(R, Y, NT)                                                                                   \
   {                                                                                                        \
     set_smem(bn_bwd_reduce_stream_kernel<R, Y>, ring_smem_bytes<NT>());                                    \
-    bn_bwd_reduce_stream_kernel<R, Y><<<reduce_grid(total), kThreads, ring_smem_bytes<NT>(), s>>>(         \
-        BF(dy), BF(x), BF(y), gamma, beta, saved_mean, saved_rstd, dsums, total, C);                       \
+    launch_pdl(bn_bwd_reduce_stream_kernel<R, Y>, dim3(reduce_grid(total)), dim3(kThreads),                \
+               ring_smem_bytes<NT>(), s, BF(dy), BF(x), BF(y), gamma, beta, saved_mean, saved_rstd, dsums, total, C);                       \
   }
   if (!relu) LAUNCH(false, false, 2)
   else if (y != nullptr) LAUNCH(true, true, 3)
@@ -454,8 +459,8 @@ void bn_bwd_apply_stream(const void* dy, const void* x, const void* y, const flo
 #define LAUNCH(R, Y, NT)                                                                                   \
   {                                                                                                        \
     set_smem(bn_bwd_apply_stream_kernel<R, Y>, ring_smem_bytes<NT>());                                     \
-    bn_bwd_apply_stream_kernel<R, Y><<<stream_grid(total), kThreads, ring_smem_bytes<NT>(), s>>>(          \
-        BF(dy), BF(x), BF(y), gamma, beta, saved_mean, saved_rstd, dsums, BFW(dx), BFW(dres), dgamma, dbeta, \
+    launch_pdl(bn_bwd_apply_stream_kernel<R, Y>, dim3(stream_grid(total)), dim3(kThreads),                 \
+               ring_smem_bytes<NT>(), s, BF(dy), BF(x), BF(y), gamma, beta, saved_mean, saved_rstd, dsums, BFW(dx), BFW(dres), dgamma, dbeta, \
         total, C, accumulate ? 1 : 0);                                                                     \
   }
   if (!relu) LAUNCH(false, false, 2)

@@ -97,6 +97,15 @@ EDL_DEVICE float warp_max(float v) {
   return v;
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-serialization
+// attribute (launch.h) may start while its predecessor in the stream is still running: everything up to
+// pdl_wait() -- barrier init, TMEM allocation, tensor-map prefetch -- overlaps the predecessor's tail, and
+// pdl_wait() returns once the predecessor grid has completed and its memory is visible.  Both instructions are
+// no-ops for a normally launched kernel.  RULE: a kernel launched through launch_pdl() must execute pdl_wait()
+// before its first access to global memory.
+EDL_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+EDL_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <typename T>
 EDL_DEVICE T ceil_div(T a, T b) {
   return (a + b - 1) / b;

@@ -20,6 +20,7 @@
 
 #include "gemm.h"
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace edl {
@@ -183,6 +184,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  // everything above is CTA-local set-up; under programmatic dependent launch it overlapped the tail of the
+  // previous kernel in the stream.  From here on global memory is touched.
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
   const int rows_tile = kConv ? p.BN * p.BH * p.W : kBlockM;
   const uint32_t a_bytes = kConv ? (uint32_t)rows_tile * 128u : (uint32_t)L::kABytes;
@@ -580,9 +585,9 @@ const char* launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   }
   const int total = p.tiles_m * p.tiles_n;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  kern<<<grid, kThreads, L::kTotal, stream>>>(tmA, tmB, tmD, tmAdd != nullptr ? *tmAdd : tmD,
-                                              tmBnX != nullptr ? *tmBnX : tmD, tmBnY != nullptr ? *tmBnY : tmD, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)L::kTotal, stream, tmA, tmB, tmD,
+                             tmAdd != nullptr ? *tmAdd : tmD, tmBnX != nullptr ? *tmBnX : tmD,
+                             tmBnY != nullptr ? *tmBnY : tmD, p);
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
