@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--teacher-fp8", action="store_true", help="distill mode: e4m3 tcgen05 GEMMs for the teacher's 1x1 convs")
     ap.add_argument("--no-fused-bn", action="store_true", help="A/B: disable the SM-resident fused BN kernels")
     ap.add_argument("--no-stream-bn", action="store_true", help="A/B: disable the cp.async.bulk BN kernels")
+    ap.add_argument("--pdl", action="store_true", help="A/B (experimental): programmatic dependent launch of the hot kernels")
+    ap.add_argument("--own-wgrad3", action="store_true", help="A/B (experimental): tcgen05 3x3 weight-gradient kernel")
     return ap.parse_args()
 
 
@@ -244,6 +246,10 @@ def main():
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.pdl:
+        os.environ["EDL_PDL"] = "1"            # read when the extension is loaded
+    if args.own_wgrad3:
+        os.environ["EDL_OWN_WGRAD3"] = "1"     # read when edl_b200.ops.gemm is imported
 
     import torch
     import torch.distributed as dist
@@ -399,6 +405,7 @@ def main():
                        "parallelism": "dp%d" % world, "optimizer": "SGD-momentum 0.9 wd 1e-4 (fused, fp32 master)",
                        "loss": "soft-label cross-entropy (teacher-score shaped targets)",
                        "cuda_graph": not args.no_graph, "conv_impl": args.conv_impl,
+                       "pdl": bool(args.pdl), "own_wgrad3": bool(args.own_wgrad3),
                        "allreduce": getattr(getattr(trainer, "dp", None), "algo_pref", "nccl"),
                        "l2": "per-step working set (~GBs of activations) >> 126 MB L2, no explicit flush",
                        "baseline_note": "vs_baseline divides by the published 8xV100 1828 img/s (BASELINE.md P1)"},
