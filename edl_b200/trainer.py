@@ -25,6 +25,22 @@ from .models.resnet_vd import ConvBNAct
 from .parallel import ElasticDataParallel
 
 
+class LossHandle:
+    """Result of ``StudentTrainer.step_pipelined``: the loss of one step, readable once its asynchronous
+    device -> pinned-host copy has landed.  At most ``StudentTrainer._LOSS_SLOTS`` handles are live at a time."""
+
+    __slots__ = ("_ev", "_host", "_value")
+
+    def __init__(self, ev, host, value=None):
+        self._ev, self._host, self._value = ev, host, value
+
+    def item(self) -> float:
+        if self._value is None:
+            self._ev.synchronize()
+            self._value = float(self._host[0])
+        return self._value
+
+
 class StepArena:
     """One flat fp32 scratch buffer holding every BN layer's forward (sum, sum^2) and backward
     (dbeta, dgamma) accumulators; zeroed with a single memset per step."""
@@ -176,6 +192,55 @@ class StudentTrainer:
         self.static_x.copy_(images, non_blocking=True)
         self.static_t.copy_(targets, non_blocking=True)
         return self.step_device()
+
+    # ------------------------------------------------------------------ double-buffered feed
+    def _pipe_init(self):
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._stage_x = [torch.empty_like(self.static_x) for _ in range(2)]
+        self._stage_t = [torch.empty_like(self.static_t) for _ in range(2)]
+        self._stage_ready = [torch.cuda.Event() for _ in range(2)]
+        self._stage_free = [torch.cuda.Event() for _ in range(2)]
+        cur = torch.cuda.current_stream(self.device)
+        for ev in self._stage_free:
+            ev.record(cur)
+        self._loss_host = torch.zeros(self._LOSS_SLOTS, dtype=torch.float32).pin_memory()
+        self._loss_ev = [torch.cuda.Event() for _ in range(self._LOSS_SLOTS)]
+        self._pipe_i = 0
+
+    _LOSS_SLOTS = 4
+
+    def step_pipelined(self, images: torch.Tensor, targets: torch.Tensor) -> "LossHandle":
+        """``step()`` with the host work taken off the critical path (the reference feeds its trainers through
+        a double-buffered reader: ``use_double_buffer`` of the Paddle data loader used by
+        example/distill/resnet/train_with_fleet.py).
+
+        The pinned-host -> device copy of THIS batch goes to one of two staging buffers on a copy stream, so
+        it overlaps the previous step still running on the GPU; the step stream then moves it into the
+        graph's static input (device-to-device) and replays the step.  The loss is copied to pinned host
+        memory asynchronously; the returned handle's ``item()`` waits for that copy only -- read it one step
+        late (``h = step_pipelined(b[i+1]); prev.item()``) and the host never stalls the GPU."""
+        if not self.cuda:
+            return LossHandle(None, None, float(self.step(images, targets)))
+        if getattr(self, "_copy_stream", None) is None:
+            self._pipe_init()
+        k = self._pipe_i % 2
+        j = self._pipe_i % self._LOSS_SLOTS
+        self._pipe_i += 1
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free[k])           # the slot's previous contents were consumed two steps ago
+        with torch.cuda.stream(cs):
+            self._stage_x[k].copy_(images, non_blocking=True)
+            self._stage_t[k].copy_(targets, non_blocking=True)
+            self._stage_ready[k].record(cs)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._stage_ready[k])
+        self.static_x.copy_(self._stage_x[k], non_blocking=True)
+        self.static_t.copy_(self._stage_t[k], non_blocking=True)
+        self._stage_free[k].record(cur)
+        self.step_device()
+        self._loss_host[j:j + 1].copy_(self.static_loss.view(1), non_blocking=True)
+        self._loss_ev[j].record(cur)
+        return LossHandle(self._loss_ev[j], self._loss_host[j:j + 1])
 
     def set_lr(self, lr: float):
         self.opt.set_lr(lr)

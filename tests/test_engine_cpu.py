@@ -290,3 +290,21 @@ def test_elastic_rebuild_in_place_gloo():
         assert p.exitcode == 0
     d0, d1, d2, world = q.get(timeout=5)
     assert d0 < 1e-6 and d1 > 1e-6 and d2 < 1e-6 and world == 2
+
+
+def test_step_pipelined_cpu_fallback_matches_step():
+    from edl_b200.models import ResNetVd, to_train_dtype
+    from edl_b200.trainer import StudentTrainer
+
+    def run(pipelined):
+        torch.manual_seed(0)
+        m = to_train_dtype(ResNetVd(18, class_dim=10, width_mult=0.125), torch.float32, torch.device("cpu")).train()
+        tr = StudentTrainer(m, 4, image_shape=(3, 32, 32), num_classes=10, lr=0.05, use_graph=False, dtype=torch.float32)
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(4, 3, 32, 32, generator=g).contiguous(memory_format=torch.channels_last)
+        t = torch.softmax(torch.randn(4, 10, generator=g), -1)
+        if pipelined:
+            return [tr.step_pipelined(x, t).item() for _ in range(3)]
+        return [float(tr.step(x, t)) for _ in range(3)]
+
+    assert run(True) == run(False)

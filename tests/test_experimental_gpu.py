@@ -125,3 +125,35 @@ def test_programmatic_dependent_launch_matches_plain_launches():
         assert torch.equal(cap, want)
     finally:
         C.set_pdl(False)
+
+
+def test_step_pipelined_matches_step():
+    """Double-buffered feed: same losses as the synchronous public step, handles readable one step late."""
+    from edl_b200.models import ResNetVd, to_train_dtype
+    from edl_b200.trainer import StudentTrainer
+
+    def run(pipelined):
+        torch.manual_seed(0)
+        m = to_train_dtype(ResNetVd(18, class_dim=16, width_mult=0.25), torch.bfloat16, torch.device(DEV)).train()
+        tr = StudentTrainer(m, 8, image_shape=(3, 32, 32), num_classes=16, lr=0.05, use_graph=True)
+        g = torch.Generator().manual_seed(1)
+        xs = [torch.randn(8, 3, 32, 32, generator=g).bfloat16().contiguous(memory_format=torch.channels_last).pin_memory()
+              for _ in range(3)]
+        ts = [torch.softmax(torch.randn(8, 16, generator=g), -1).bfloat16().pin_memory() for _ in range(3)]
+        losses, prev = [], None
+        for i in range(9):
+            if pipelined:
+                h = tr.step_pipelined(xs[i % 3], ts[i % 3])
+                if prev is not None:
+                    losses.append(prev.item())
+                prev = h
+            else:
+                losses.append(float(tr.step(xs[i % 3], ts[i % 3]).item()))
+        if pipelined:
+            losses.append(prev.item())
+        return losses
+
+    a, b = run(False), run(True)
+    assert len(a) == len(b) == 9
+    for u, v in zip(a, b):
+        assert abs(u - v) <= 2e-2 * max(1.0, abs(u)), (a, b)
