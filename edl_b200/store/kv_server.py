@@ -416,8 +416,18 @@ def main(argv=None):
     ap.add_argument("--log_level", type=int, default=20)
     ap.add_argument("--data_dir", default=None, help="keep periodic snapshots here and reload them on start")
     ap.add_argument("--snapshot_interval", type=float, default=2.0)
+    ap.add_argument("--native", action="store_true",
+                    help="exec the C++ / epoll build of this server (store/native/kv_server.cpp) instead")
     args = ap.parse_args(argv)
     logging.basicConfig(level=args.log_level)
+    if args.native or os.environ.get("EDL_KV_NATIVE", "0") == "1":
+        from . import native_server
+
+        cmd = [native_server.build(), "--host", args.host, "--port", str(args.port),
+               "--snapshot_interval", str(args.snapshot_interval)]
+        if args.data_dir:
+            cmd += ["--data_dir", args.data_dir]
+        os.execv(cmd[0], cmd)
     srv = KVServer(args.host, args.port, args.data_dir, args.snapshot_interval).start()
     logger.info("kv store listening on %s", srv.endpoint)
     try:

@@ -37,11 +37,18 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip_multi)
 
 
-@pytest.fixture
-def kv_server():
-    from edl_b200.store import KVServer
+def _kv_impls():
+    from edl_b200.store import native_server
 
-    srv = KVServer().start()
+    return ["python", "native"] if native_server.available() else ["python"]
+
+
+@pytest.fixture(params=_kv_impls())
+def kv_server(request):
+    """The coordination store: every test that uses it runs against the Python server and the C++ one."""
+    from edl_b200.store import KVServer, NativeKVServer
+
+    srv = (NativeKVServer if request.param == "native" else KVServer)().start()
     yield srv
     srv.stop()
 

@@ -126,3 +126,68 @@ def test_snapshot_restart_keeps_keys_revisions_and_leases(tmp_path):
         c2.close()
     finally:
         srv2.stop()
+
+
+@pytest.mark.parametrize("first,second", [("python", "native"), ("native", "python")])
+def test_python_and_native_servers_share_the_snapshot_format(tmp_path, first, second):
+    """Either server can take over the other's data directory (same msgpack snapshot, same lease grace)."""
+    from edl_b200.store import NativeKVServer, native_server
+
+    if not native_server.available():
+        pytest.skip("no C++ compiler for the native store")
+    impl = {"python": KVServer, "native": NativeKVServer}
+    d = str(tmp_path / "kvdata")
+    srv = impl[first](port=0, data_dir=d, snapshot_interval=0.1).start()
+    c = KVClient([srv.endpoint])
+    lease = c.lease(30.0)
+    c.put("/job/pods/a", b"\x00binary\xff", lease.id)
+    for i in range(3):
+        c.put("/job/status", "v%d" % i)
+    _, meta = c.get("/job/status")
+    c.close()
+    srv.stop()                                        # final snapshot on stop (SIGTERM for the native server)
+    srv2 = impl[second](port=0, data_dir=d).start()
+    try:
+        c2 = KVClient([srv2.endpoint])
+        v, m2 = c2.get("/job/status")
+        assert v == b"v2" and m2 == meta
+        v, m3 = c2.get("/job/pods/a")
+        assert v == b"\x00binary\xff" and m3["lease"] == lease.id
+        assert c2.lease_keepalive(lease.id) > 0
+        assert c2.put("/job/new", b"x")["kv"]["mod_revision"] == meta["mod_revision"] + 1
+        c2.lease_revoke(lease.id)
+        assert c2.get("/job/pods/a")[0] is None
+        c2.close()
+    finally:
+        srv2.stop()
+
+
+def test_native_server_error_paths_and_many_clients(kv_server):
+    """Unknown lease / unknown method come back as errors (not a dropped connection); 16 clients hammering one
+    key through compare-and-swap transactions never lose an update."""
+    from edl_b200.store import StoreError
+
+    c = KVClient(kv_server.endpoint)
+    with pytest.raises(StoreError):
+        c.put("/e/x", b"1", lease=123456789)
+    with pytest.raises(StoreError):
+        c.call({"method": "no_such_method"})
+    assert c.get("/e/x")[0] is None
+    c.put("/cnt", "0")
+    n_threads, n_incr = 16, 25
+
+    def worker():
+        cl = KVClient(kv_server.endpoint)
+        for _ in range(n_incr):
+            while True:
+                v, _ = cl.get("/cnt")
+                ok, _ = cl.txn([{"key": "/cnt", "value": v}], [{"op": "put", "key": "/cnt", "value": str(int(v) + 1)}])
+                if ok:
+                    break
+        cl.close()
+
+    ts = [threading.Thread(target=worker) for _ in range(n_threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert c.get("/cnt")[0] == str(n_threads * n_incr).encode()
+    c.close()
