@@ -26,6 +26,11 @@ class NoValidEndpoint(StoreError):
     pass
 
 
+class StoreRequestError(StoreError):
+    """The server processed the request and rejected it (unknown lease, malformed transaction, ...): not a
+    transport problem, so the client neither reconnects nor resends."""
+
+
 class Lease:
     def __init__(self, client: "KVClient", lease_id: int, ttl: float):
         self.client, self.id, self.ttl = client, lease_id, ttl
@@ -116,10 +121,12 @@ class KVClient:
         with self._conn_lock:
             if self._sock is sock:
                 self._sock = None
+        # ... that was sent on THIS socket (a reconnect may already have requests in flight on a new one)
         with self._plock:
             for slot in self._pending.values():
-                slot["resp"] = None
-                slot["ev"].set()
+                if slot.get("sock") is sock:
+                    slot["resp"] = None
+                    slot["ev"].set()
 
     def _dispatch(self, cb, events, rev):
         with self._plock:
@@ -154,7 +161,7 @@ class KVClient:
             raise StoreError("not connected")
         rid = next(self._ids)
         req = dict(req, id=rid)
-        slot = {"ev": threading.Event(), "resp": None}
+        slot = {"ev": threading.Event(), "resp": None, "sock": sock}
         with self._plock:
             self._pending[rid] = slot
         try:
@@ -170,7 +177,7 @@ class KVClient:
         if resp is None:
             raise StoreError("connection lost")
         if not resp.get("ok"):
-            raise StoreError(resp.get("error", "store error"))
+            raise StoreRequestError(resp.get("error", "store error"))
         return resp
 
     def call(self, req: dict) -> dict:
@@ -181,6 +188,8 @@ class KVClient:
             try:
                 self.connect()
                 return self._call_once(req)
+            except StoreRequestError:
+                raise            # the server answered: the connection is fine and a resend would not change the answer
             except (StoreError, OSError):
                 with self._conn_lock:
                     if self._sock is not None:

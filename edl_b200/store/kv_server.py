@@ -195,7 +195,7 @@ class KVState:
             return {"put": self._put(op["key"], op.get("value", b""), int(op.get("lease", 0)))}
         if t == "delete":
             if op.get("prefix"):
-                n = sum(self._delete(k) for k in [k for k in self.kv if k.startswith(op["key"])])
+                n = sum(self._delete(k) for k in sorted(k for k in self.kv if k.startswith(op["key"])))
             else:
                 n = self._delete(op["key"])
             return {"deleted": n}
@@ -263,7 +263,7 @@ class KVState:
         le = self.leases.pop(lid, None)
         if le is None:
             return
-        for k in list(le.keys):
+        for k in sorted(le.keys):        # deterministic (key order): watchers of both server builds see the same stream
             self._delete(k)
 
     def expire(self):

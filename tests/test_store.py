@@ -191,3 +191,23 @@ def test_native_server_error_paths_and_many_clients(kv_server):
     [t.join() for t in ts]
     assert c.get("/cnt")[0] == str(n_threads * n_incr).encode()
     c.close()
+
+
+def test_rejected_request_does_not_reconnect_or_duplicate_the_next_one(kv_server):
+    """Regression (found by tests/test_store_differential.py): an application-level error used to be treated like a
+    transport error -- the client closed its socket and resent, and the old reader thread then failed the NEXT
+    request, which was in flight on the new socket, so that one was executed twice."""
+    from edl_b200.store import StoreRequestError
+
+    c = KVClient(kv_server.endpoint)
+    c.put("/n", "0")
+    sock = c._sock
+    for i in range(20):
+        with pytest.raises(StoreRequestError):
+            c.put("/bad", b"x", lease=424242)                 # unknown lease
+        ok, _ = c.txn([{"key": "/n", "value": str(i)}], [{"op": "put", "key": "/n", "value": str(i + 1)}])
+        assert ok, "the compare-and-swap after a rejected request was applied twice"
+    assert c._sock is sock, "a rejected request must not cost the connection"
+    _, meta = c.get("/n")
+    assert meta["version"] == 21
+    c.close()
