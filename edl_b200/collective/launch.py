@@ -9,6 +9,10 @@ from ..utils.pod import Pod
 
 def main(argv=None):
     args = args_utils.parse_args(argv)
+    if args.rescale_mode:
+        import os
+
+        os.environ["EDL_RESCALE_MODE"] = args.rescale_mode      # trainers inherit it
     logger = log_utils.get_logger(args.log_level)
     job_env = edl_env.JobEnv(args_utils.convert_args_to_dict(args))
     etcd = EtcdClient(endpoints=job_env.etcd_endpoints, root=job_env.job_id, timeout=constants.ETCD_CONN_TIMEOUT)

@@ -15,6 +15,9 @@ def parse_args(argv=None):
     p.add_argument("--hdfs_name", type=str, default=None)
     p.add_argument("--hdfs_ugi", type=str, default=None)
     p.add_argument("--hdfs_path", type=str, default=None, help="checkpoint path visible to all trainers")
+    p.add_argument("--rescale_mode", type=str, default=None, choices=["restart", "inplace"],
+                   help="restart (reference behaviour: kill and restart trainers on every membership change) or "
+                        "inplace (trainers that own an ElasticContext keep running; env EDL_RESCALE_MODE)")
     p.add_argument("training_script", type=str, help="the single-GPU training program")
     p.add_argument("training_script_args", nargs=argparse.REMAINDER)
     return p.parse_args(argv)

@@ -107,6 +107,14 @@ class Launcher:
                 t0 = time.time()
                 logger.info("cluster changed; re-barrier")
                 new_cluster = self._barrier(constants.RESCALE_BARRIER_TIMEOUT)
+                if self._inplace_possible():
+                    done = self._rescale_in_place(new_cluster, t0)
+                    if done is not None:
+                        if done == "evicted":
+                            return True
+                        time.sleep(poll)
+                        continue
+                    logger.warning("in-place rescale was not acknowledged; falling back to stop-resume")
                 train_process.terminate(self._procs)
                 self._watcher.stop()
                 if not self._adopt(new_cluster):
@@ -120,6 +128,65 @@ class Launcher:
                 logger.info("rescaled to %d trainers in %.2fs", self._cluster.get_trainers_nranks(),
                             self.last_rescale_s)
             time.sleep(poll)
+
+    # ------------------------------------------------------------------ in-place rescale (edl_b200/elastic.py)
+    def _inplace_possible(self):
+        """Mode requested, every local trainer alive and owning an ElasticContext (it announced itself)."""
+        from .. import elastic
+
+        if not elastic.inplace_requested():
+            return False
+        try:
+            for tp in self._procs:
+                if tp.proc.poll() is not None:
+                    return False
+                key = elastic.capable_key(self._job_env.job_id, self._pod.id, tp.local_rank)
+                if self._etcd.kv.get(key)[0] is None:
+                    return False
+        except Exception as e:  # noqa: BLE001
+            logger.debug("in-place capability check failed: %s", e)
+            return False
+        return bool(self._procs)
+
+    def _rescale_in_place(self, new_cluster, t0):
+        """Leave the trainers running; they switch stages themselves.  Returns "ok", "evicted" or None (= fall
+        back to stop-resume: some trainer did not enter the new stage in time)."""
+        from .. import elastic
+
+        job = self._job_env.job_id
+        mine = new_cluster.get_pod_by_id(self._pod.id)
+        if mine is None:
+            logger.info("pod %s is not part of the new cluster; its trainers leave by themselves", self._pod.id)
+            rc = train_process.wait_all(self._procs, timeout=constants.INPLACE_ACK_TIMEOUT)
+            if rc == -1:
+                train_process.terminate(self._procs)
+            self._watcher.stop()
+            return "evicted"
+        deadline = time.time() + constants.INPLACE_ACK_TIMEOUT
+        want = [elastic.ready_key(job, new_cluster.stage, t.global_rank) for t in mine.trainers]
+        while time.time() < deadline:
+            if any(tp.proc.poll() is not None for tp in self._procs):
+                return None
+            try:
+                if all(self._etcd.kv.get(k)[0] == b"survivor" for k in want):
+                    break
+                latest = edl_cluster.load_from_etcd(self._etcd, timeout=3)
+                if latest is not None and latest.stage != new_cluster.stage:
+                    break      # superseded: the watcher below picks the newer stage up right away
+            except exceptions.EdlException:
+                pass
+            time.sleep(0.1)
+        else:
+            return None
+        self._watcher.stop()
+        self._adopt(new_cluster)
+        self._watcher = cluster_watcher.Watcher(self._job_env, self._cluster, etcd=self._etcd)
+        self.rescales += 1
+        self.inplace_rescales = getattr(self, "inplace_rescales", 0) + 1
+        self.last_rescale_s = time.time() - t0
+        logger.info("rescaled IN PLACE to %d trainers in %.2fs (trainer processes kept)",
+                    self._cluster.get_trainers_nranks(), self.last_rescale_s)
+        return "ok"
 
     # ------------------------------------------------------------------ tear-down
     def _exit(self, ok):

@@ -3,6 +3,11 @@
 CPU / gloo plumbing config (BASELINE.json configs[0]; reference workload:
 example/fit_a_line/fluid/fit_a_line.py:26-44, which runs it in parameter-server mode).
 
+With ``EDL_RESCALE_MODE=inplace`` (launcher flag ``--rescale_mode inplace``) the trainer owns an
+``ElasticContext``: on a membership change it stays alive, re-rendezvouses through the store, rebuilds the
+data-parallel engine for the new world, hands its state to joiners by broadcast and rescales the LR -- no
+process restart, no checkpoint reload (edl_b200/elastic.py).  Otherwise (the reference's stop-resume):
+
 Started by the elastic launcher; every (re)start it
   1. joins the process group described by the launcher's environment,
   2. reloads the newest checkpoint (params + optimizer + epoch cursor + State JSON),
@@ -26,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 import edl_b200 as edl  # noqa: E402
 from edl_b200 import ops  # noqa: E402
+from edl_b200 import elastic  # noqa: E402
 from edl_b200.checkpoint import LocalFS, TrainStatus, load_check_point, save_check_point  # noqa: E402
 from edl_b200.models.small import FitALine  # noqa: E402
 from edl_b200.parallel import ElasticDataParallel  # noqa: E402
@@ -50,8 +56,15 @@ def main():
     ap.add_argument("--report", type=str, default=os.environ.get("FIT_REPORT_DIR", ""))
     args = ap.parse_args()
 
-    env = edl.init_distributed("gloo")
-    world, rank = env.size, env.global_rank
+    inplace = elastic.inplace_requested()
+    ctx = info = None
+    if inplace:
+        ctx = elastic.ElasticContext("gloo", check_every=int(os.environ.get("EDL_INPLACE_CHECK_EVERY", "5")))
+        info = ctx.start()
+        world, rank = info.size, info.rank
+    else:
+        env = edl.init_distributed("gloo")
+        world, rank = env.size, env.global_rank
     torch.manual_seed(0)
     model = FitALine()
     dp = ElasticDataParallel(model)
@@ -62,26 +75,49 @@ def main():
     state.register_adjust_function([edl_state.linear_scale_lr(lambda: opt.lr, opt.set_lr)])
 
     fs = LocalFS()
-    tensors, train_status, state_json = load_check_point(args.ckpt, fs, trainer_id=rank)
-    prev_world = world
-    if tensors is not None:
-        model.load_state_dict(tensors["model"])
-        dp.flat.sync_master_from_params()
-        opt.load_state_dict(tensors["optim"])
-        if state_json:
-            saved = json.loads(state_json)
-            prev_world = int(saved.get("world", world))
-            opt.set_lr(float(saved.get("lr", opt.lr)))
-    state.adjust(prev_world, world)          # LR <- LR * world / prev_world
+
+    def take_state_from(root, cursor, prev_world):
+        """Collective over the (new) world: parameters, optimizer state, LR, the epoch cursor of ``root`` and the
+        world size that LR belongs to.  Returns (cursor, prev_world) as ``root`` sees them."""
+        if world <= 1:
+            return cursor, prev_world
+        dp.broadcast_parameters(root)
+        for st in opt.state.values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    dp.broadcast_tensor(v, root)
+        box = [cursor, opt.lr, prev_world]
+        dist.broadcast_object_list(box, src=root)
+        opt.set_lr(float(box[1]))
+        return box[0], int(box[2])
+
+    if inplace and info.root is not None:
+        # joining a RUNNING job: the survivors hand their state over, the checkpoint is not read
+        start_epoch, prev_world = take_state_from(info.root, None, world)
+        state.adjust(prev_world, world)
+    else:
+        tensors, train_status, state_json = load_check_point(args.ckpt, fs, trainer_id=rank)
+        prev_world = world
+        if tensors is not None:
+            model.load_state_dict(tensors["model"])
+            dp.flat.sync_master_from_params()
+            opt.load_state_dict(tensors["optim"])
+            if state_json:
+                saved = json.loads(state_json)
+                prev_world = int(saved.get("world", world))
+                opt.set_lr(float(saved.get("lr", opt.lr)))
+        state.adjust(prev_world, world)          # LR <- LR * world / prev_world
+        start_epoch = train_status.next()
 
     x, y = synthetic_housing()
     n = x.shape[0]
-    start_epoch = train_status.next()
     loss = torch.zeros(())
-    for epoch in range(start_epoch, args.epochs):
+    epoch = start_epoch
+    while epoch < args.epochs:
         g = torch.Generator().manual_seed(epoch)          # shuffle seed = epoch: reproducible after resume
         perm = torch.randperm(n, generator=g)
         shard = perm[rank::world]
+        switch = False
         for i in range(0, len(shard) - args.batch + 1, args.batch):
             idx = shard[i:i + args.batch]
             dp.zero_grad()
@@ -90,6 +126,25 @@ def main():
             dp.finish()
             opt.step()
             edl.notify_end_one_batch(None, state)
+            if inplace and ctx.poll():
+                switch = True
+                break
+        if inplace and not switch:
+            switch = ctx.poll(force=True)                  # epoch boundary: every rank asks, every rank agrees
+        if switch:
+            try:
+                info = ctx.rescale()
+            except elastic.EdlEvicted:
+                print("rank %d: pod left the job (scale-in); exiting" % rank, flush=True)
+                ctx.close()
+                return 0
+            old_world, world, rank = world, info.size, info.rank
+            dp.rebuild(None)                               # new process group => new gradient buffers / bucket plan
+            epoch, prev_world = take_state_from(info.root, epoch, old_world)
+            state.adjust(prev_world, world)                # LR follows the world size
+            print("rescaled in place: world %d -> %d, rank %d, pid %d, %.2fs" % (
+                old_world, world, rank, os.getpid(), info.rendezvous_s), flush=True)
+            continue                                       # redo this epoch with the new sharding
         edl.notify_end_one_epoch(state)
         if world > 1:
             dist.all_reduce(loss)
@@ -103,11 +158,15 @@ def main():
                 os.makedirs(args.report, exist_ok=True)
                 with open(os.path.join(args.report, "epochs.jsonl"), "a") as f:
                     f.write(json.dumps({"epoch": epoch, "world": world, "lr": opt.lr, "loss": float(loss),
-                                        "t": time.time()}) + "\n")
+                                        "t": time.time(), "pid": os.getpid()}) + "\n")
         if world > 1:
             dist.barrier()
         if args.epoch_sleep:
             time.sleep(args.epoch_sleep)
+        epoch += 1
+    if ctx is not None:
+        ctx.close()
+        return 0
     if world > 1:
         dist.destroy_process_group()
     return 0

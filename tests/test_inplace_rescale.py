@@ -1,0 +1,123 @@
+"""In-place elastic rescale end to end (edl_b200/elastic.py): real launchers, real gloo collectives, one store.
+
+pod A alone -> pod B joins: A's trainer KEEPS ITS PROCESS, re-rendezvouses through the store, hands its state to
+B's trainer by broadcast and doubles the LR -> the leader's ScaleIn RPC evicts B: B's trainer leaves quietly, A's
+trainer continues alone (same process, LR halved) -> the job finishes and is recorded SUCCEED."""
+import json
+import os
+import subprocess
+import sys
+import time
+import uuid
+
+import pytest
+import torch.distributed as dist
+
+from edl_b200.discovery.etcd_client import EtcdClient
+from edl_b200.utils import leader_pod, pod_server_client, status as edl_status
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TRAIN = os.path.join(ROOT, "examples", "fit_a_line", "train.py")
+
+
+def _launch(endpoint, job, log_dir, report, ckpt, epochs):
+    env = dict(os.environ)
+    env.update({"PYTHONPATH": ROOT, "CUDA_VISIBLE_DEVICES": "", "PADDLE_RUNNING_PLATFORM": "", "EDL_POD_IP": "127.0.0.1",
+                "FIT_REPORT_DIR": report, "EDL_INPLACE_CHECK_EVERY": "3", "EDL_INPLACE_ACK_TIMEOUT": "40"})
+    cmd = [sys.executable, "-u", "-m", "edl_b200.collective.launch", "--nodes_range", "1:2", "--nproc_per_node", "1",
+           "--etcd_endpoints", endpoint, "--job_id", job, "--log_dir", log_dir, "--log_level", "10",
+           "--hdfs_path", ckpt, "--rescale_mode", "inplace",
+           TRAIN, "--epochs", str(epochs), "--epoch_sleep", "0.05", "--ckpt", ckpt]
+    return subprocess.Popen(cmd, env=env, stdout=open(log_dir + ".launcher.log", "w"), stderr=subprocess.STDOUT,
+                            start_new_session=True)
+
+
+@pytest.mark.slow
+def test_join_and_scale_in_without_restarting_the_survivor(kv_server, tmp_path):
+    job = "inplace_" + uuid.uuid4().hex[:6]
+    report, ckpt = str(tmp_path / "report"), str(tmp_path / "ckpt")
+
+    def epochs():
+        p = os.path.join(report, "epochs.jsonl")
+        return [json.loads(l) for l in open(p)] if os.path.exists(p) else []
+
+    def wait_world(w, timeout, min_new=3):
+        n0 = len(epochs())
+        deadline = time.time() + timeout
+        while time.time() < deadline:
+            e = epochs()
+            if len(e) >= n0 + min_new and all(x["world"] == w for x in e[-min_new:]):
+                return e
+            time.sleep(0.2)
+        logs = "".join(open(f).read()[-3000:] for f in (str(tmp_path / "logA.launcher.log"), str(tmp_path / "logB.launcher.log"))
+                       if os.path.exists(f))
+        raise AssertionError("world never became %d: %s\n%s" % (w, epochs()[-4:], logs))
+
+    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 260)
+    b = None
+    try:
+        e1 = wait_world(1, 60)
+        pid_a = e1[-1]["pid"]
+        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 260)
+        e2 = wait_world(2, 90)
+        assert e2[-1]["pid"] == pid_a, "the surviving trainer was restarted on scale-out"
+        assert abs(e2[-1]["lr"] - 2 * e1[-1]["lr"]) < 1e-9                       # linear LR rescale, in place
+        # scheduler-driven scale-in through the leader's RPC: the evicted pod leaves quietly
+        etcd = EtcdClient([kv_server.endpoint], root=job)
+        etcd.init()
+        leader = leader_pod.load_from_etcd(etcd, timeout=5)
+        cli = pod_server_client.Client(leader.endpoint)
+        cli.scale_in(1)
+        cli.close()
+        e1b = wait_world(1, 90)
+        assert e1b[-1]["pid"] == pid_a, "the surviving trainer was restarted on scale-in"
+        assert abs(e1b[-1]["lr"] - e1[-1]["lr"]) < 1e-9
+        assert b.wait(timeout=60) == 0                                           # evicted pod: clean exit
+        assert a.wait(timeout=120) == 0
+        assert edl_status.load_job_status_from_etcd(etcd) == edl_status.Status.SUCCEED
+        ep = [x["epoch"] for x in epochs()]
+        assert ep == sorted(set(ep)), "an epoch was reported twice: %s" % ep
+        assert epochs()[-1]["loss"] < e1[0]["loss"]
+        log_a = open(str(tmp_path / "logA.launcher.log")).read()
+        assert log_a.count("rescaled IN PLACE") >= 2 and "falling back to stop-resume" not in log_a
+        worker = open(str(tmp_path / "logA" / "workerlog.0")).read()
+        assert worker.count("rescaled in place") >= 2
+        etcd.close()
+    finally:
+        for p in (a, b):
+            if p is not None and p.poll() is None:
+                os.killpg(os.getpgid(p.pid), 9)
+
+
+def test_rendezvous_store_and_commit_protocol(kv_server):
+    """KVRendezvousStore semantics torch relies on + the commit / withdraw exclusion of the stage rendezvous."""
+    from edl_b200 import elastic
+    from edl_b200.store import KVClient
+
+    kv = KVClient(kv_server.endpoint)
+    st = elastic.KVRendezvousStore(kv, "/t/pg/", timeout_s=0.3)
+    assert isinstance(st, dist.Store)
+    st.set("a", b"1")
+    assert st.get("a") == b"1" and st.check(["a"]) and not st.check(["a", "zz"])
+    assert [st.add("cnt", 2), st.add("cnt", 3)] == [2, 5] and st.get("cnt") == b"5"
+    assert st.compare_set("cas", b"", b"x") == b"x" and st.compare_set("cas", b"nope", b"y") == b"x"
+    assert st.compare_set("cas", b"x", b"y") == b"y"
+    with pytest.raises(RuntimeError):
+        st.get("never")
+    assert st.num_keys() == 3 and st.delete_key("a") and st.num_keys() == 2
+    # commit needs every ready key; a withdrawal is only possible while the commit record is absent
+    job, stage = "j", "S"
+    keys = [elastic.ready_key(job, stage, r) for r in range(2)]
+    ckey = elastic.commit_key(job, stage)
+    kv.put(keys[0], b"survivor")
+    commit = lambda: kv.txn([{"key": k, "target": "version", "op": ">", "value": 0} for k in keys] +  # noqa: E731
+                            [{"key": ckey, "target": "version", "op": "==", "value": 0}],
+                            [{"op": "put", "key": ckey, "value": b"{}"}])[0]
+    withdraw = lambda k: kv.txn([{"key": ckey, "target": "version", "op": "==", "value": 0}],  # noqa: E731
+                                [{"op": "delete", "key": k}])[0]
+    assert not commit()                       # rank 1 has not arrived
+    kv.put(keys[1], b"joiner")
+    assert withdraw(keys[1]) and not commit()  # withdrew in time: the stage cannot be committed without it
+    kv.put(keys[1], b"joiner")
+    assert commit() and not withdraw(keys[1]) and not commit()   # committed: nobody can leave, nobody commits twice
+    kv.close()

@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""Rescale recovery time through the real launcher (BASELINE.json "rescale recovery time after +-1 pod"), CPU / gloo,
+fit_a_line: pod A runs alone, pod B joins, the leader's ScaleIn RPC evicts B.  Measured for the reference's
+stop-resume mode and for the in-place mode (edl_b200/elastic.py):
+
+  join   = first epoch reported at world 2  -  launch of pod B          (includes B's interpreter + torch import)
+  stall  = longest gap between two consecutive epoch reports around the change (what training actually lost)
+  leave  = first epoch reported at world 1  -  ScaleIn RPC
+
+    python tools/bench_elastic_launch.py [--native-store] [--out profiles/elastic_launch_cpu.json]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+import uuid
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+TRAIN = os.path.join(ROOT, "examples", "fit_a_line", "train.py")
+
+from edl_b200.discovery.etcd_client import EtcdClient  # noqa: E402
+from edl_b200.store import KVServer, NativeKVServer  # noqa: E402
+from edl_b200.utils import leader_pod, pod_server_client  # noqa: E402
+
+
+def launch(endpoint, job, tmp, name, mode):
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", PADDLE_RUNNING_PLATFORM="", EDL_POD_IP="127.0.0.1",
+               FIT_REPORT_DIR=os.path.join(tmp, "report"), EDL_INPLACE_CHECK_EVERY="3",
+               EDL_ETCD_TTL="1.5", EDL_POLL_INTERVAL="0.3", EDL_KILL_GRACE="1")
+    cmd = [sys.executable, "-u", "-m", "edl_b200.collective.launch", "--nodes_range", "1:2", "--nproc_per_node", "1",
+           "--etcd_endpoints", endpoint, "--job_id", job, "--log_dir", os.path.join(tmp, "log" + name),
+           "--hdfs_path", os.path.join(tmp, "ckpt"), "--rescale_mode", mode,
+           TRAIN, "--epochs", "100000", "--epoch_sleep", "0.02", "--ckpt", os.path.join(tmp, "ckpt")]
+    return subprocess.Popen(cmd, env=env, stdout=open(os.path.join(tmp, name + ".log"), "w"), stderr=subprocess.STDOUT,
+                            start_new_session=True)
+
+
+def run(mode, server_cls):
+    tmp = tempfile.mkdtemp(prefix="edl_elastic_")
+    job = "bench_" + uuid.uuid4().hex[:6]
+
+    def epochs():
+        p = os.path.join(tmp, "report", "epochs.jsonl")
+        return [json.loads(l) for l in open(p)] if os.path.exists(p) else []
+
+    def wait_world(w, timeout=120, min_new=5):
+        n0 = len(epochs())
+        deadline = time.time() + timeout
+        while time.time() < deadline:
+            e = epochs()
+            if len(e) >= n0 + min_new and all(x["world"] == w for x in e[-min_new:]):
+                return e
+            time.sleep(0.05)
+        raise RuntimeError("world never became %d (%s)" % (w, mode))
+
+    def stall(e, t_event):
+        ts = [x["t"] for x in e if x["t"] > t_event - 2.0]
+        return max(b - a for a, b in zip(ts[:-1], ts[1:]))
+
+    with server_cls() as srv:
+        a = launch(srv.endpoint, job, tmp, "A", mode)
+        b = None
+        try:
+            wait_world(1)
+            t_join = time.time()
+            b = launch(srv.endpoint, job, tmp, "B", mode)
+            e = wait_world(2)
+            join = min(x["t"] for x in e if x["world"] == 2 and x["t"] > t_join) - t_join
+            join_stall = stall(e, t_join)
+            pids_before = {x["pid"] for x in e if x["world"] == 1}
+            survivor_kept = e[-1]["pid"] in pids_before
+            etcd = EtcdClient([srv.endpoint], root=job)
+            etcd.init()
+            cli = pod_server_client.Client(leader_pod.load_from_etcd(etcd, timeout=5).endpoint)
+            t_leave = time.time()
+            cli.scale_in(1)
+            cli.close()
+            e = wait_world(1)
+            leave = min(x["t"] for x in e if x["world"] == 1 and x["t"] > t_leave) - t_leave
+            leave_stall = stall(e, t_leave)
+            etcd.close()
+            return {"mode": mode, "store": server_cls.__name__, "join_s": join, "join_stall_s": join_stall,
+                    "leave_s": leave, "leave_stall_s": leave_stall, "survivor_process_kept": survivor_kept,
+                    "steady_epoch_s": sorted(y["t"] - x["t"] for x, y in zip(e[-5:-1], e[-4:]))[1]}
+        finally:
+            for p in (a, b):
+                if p is not None and p.poll() is None:
+                    os.killpg(os.getpgid(p.pid), 9)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--native-store", action="store_true")
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    cls = NativeKVServer if args.native_store else KVServer
+    res = [run("restart", cls), run("inplace", cls)]
+    for r in res:
+        print(json.dumps(r))
+    if args.out:
+        with open(args.out, "w") as f:
+            json.dump({"note": "CPU / gloo, fit_a_line, test timing constants (TTL 1.5 s, polls 0.3 s, kill grace 1 s); "
+                               "the reference's constants are 15 s / 3 s / 3 s (BASELINE.md)", "runs": res}, f, indent=1)
