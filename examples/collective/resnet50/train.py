@@ -2,6 +2,11 @@
 """Elastic ResNet training (reference workload: example/collective/resnet50/train_with_fleet.py,
 launched through ``python -m paddle_edl.collective.launch``, train_pretrain.sh:36-61).
 
+With ``--rescale_mode inplace`` on the launcher (``EDL_RESCALE_MODE=inplace``) the trainer is NOT restarted on a
+membership change: it re-rendezvouses through the store (``edl_b200.elastic.ElasticContext``), re-plans the fused
+all-reduce for the new world (``StudentTrainer.rebuild``), hands parameters / momentum / step counters to joiners
+over the fabric (``sync_from``) and rescales the LR.  Otherwise, the reference's stop-resume:
+
 Every (re)start: join the stage's process group, reload the newest atomic checkpoint, rescale the
 learning rate to the world size (``lr = base_lr * batch * world / 256`` -- the reference's rule,
 :129-141) and continue from ``train_status.next()``.  Data is synthetic unless ``--data_dir`` points
@@ -23,7 +28,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.a
 sys.path.insert(0, ROOT)
 
 import edl_b200 as edl  # noqa: E402
-from edl_b200 import ops  # noqa: E402
+from edl_b200 import elastic, ops  # noqa: E402
 from edl_b200.checkpoint import LocalFS, TrainStatus, load_check_point, save_check_point  # noqa: E402
 from edl_b200.models import VGG, ResNet, ResNetVd, to_train_dtype  # noqa: E402
 from edl_b200.ops.optim import cosine_decay_with_warmup, piecewise_decay_with_warmup, scaled_lr  # noqa: E402
@@ -54,8 +59,14 @@ def parse():
 
 def main():
     args = parse()
-    env = edl.init_distributed()
-    world, rank = env.size, env.global_rank
+    ctx = info = None
+    if elastic.inplace_requested():
+        ctx = elastic.ElasticContext(check_every=int(os.environ.get("EDL_INPLACE_CHECK_EVERY", "20")))
+        info = ctx.start()
+        env, world, rank = ctx.env, info.size, info.rank
+    else:
+        env = edl.init_distributed()
+        world, rank = env.size, env.global_rank
     cuda = torch.cuda.is_available()
     dev = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
     bs = args.batch_size if not args.total_batch_size else max(1, args.total_batch_size // world)
@@ -74,22 +85,39 @@ def main():
                         lr=base_lr, target_kind="labels", use_graph=cuda, dtype=dtype,
                         loss_fn=lambda z, t: ops.soft_cross_entropy(z, t, "labels", label_smoothing=args.label_smoothing))
     fs = LocalFS()
-    tensors, ts, _ = load_check_point(args.ckpt, fs, trainer_id=rank, map_location=dev)
-    if tensors is not None:
-        tr.load_state_dict(tensors)
+
+    def take_cursor_from(root, cursor):
+        """Parameters, momentum and the (epoch, iteration, step) cursor of ``root``: the in-place state handoff."""
+        if world <= 1:
+            return cursor
+        tr.sync_from(root)
+        box = [cursor]
+        dist.broadcast_object_list(box, src=root)
+        return box[0]
+
+    if ctx is not None and info.root is not None:
+        epoch, it0, step = take_cursor_from(info.root, None)        # joined a running job: nothing is read from disk
+    else:
+        tensors, ts, _ = load_check_point(args.ckpt, fs, trainer_id=rank, map_location=dev)
+        if tensors is not None:
+            tr.load_state_dict(tensors)
+        epoch, it0, step = ts.next(), 0, ts.global_step
     steps_per_epoch = args.steps_per_epoch or max(1, args.total_images // (bs * world))
-    step = ts.global_step
     etcd = None
     if env.etcd_endpoints:
         from edl_b200.discovery.etcd_client import EtcdClient
         etcd = EtcdClient(env.etcd_endpoints, root=env.job_id)
         etcd.init()
     meter = StepMeter(bs, world)
-    for epoch in range(ts.next(), args.epochs):
+    lr = base_lr
+    while epoch < args.epochs:
         g = torch.Generator().manual_seed(epoch * 1000 + rank)       # pass_id as seed: reproducible after resume
         t0, seen = time.time(), 0
         n_steps = steps_per_epoch if not args.max_steps else min(steps_per_epoch, args.max_steps)
-        for it in range(n_steps):
+        it = it0
+        it0 = 0
+        switch = False
+        while it < n_steps:
             lr = (cosine_decay_with_warmup(step, base_lr, steps_per_epoch, args.epochs) if args.lr_strategy.startswith("cosine")
                   else piecewise_decay_with_warmup(step, base_lr, steps_per_epoch, [30, 60, 80]))
             tr.set_lr(lr)
@@ -97,11 +125,35 @@ def main():
             y = torch.randint(0, args.class_dim, (bs,), generator=g)
             loss = tr.step(x.pin_memory() if cuda else x, y.pin_memory() if cuda else y)
             step += 1
+            it += 1
             seen += bs
             meter.step()
-            if it % 10 == 0 and rank == 0:
+            if (it - 1) % 10 == 0 and rank == 0:
                 print("Pass %d trainbatch %d loss %.4f lr %.5f speed %.1f img/s" % (
-                    epoch, it, float(loss), lr, seen * world / max(1e-6, time.time() - t0)), flush=True)
+                    epoch, it - 1, float(loss), lr, seen * world / max(1e-6, time.time() - t0)), flush=True)
+            if ctx is not None and ctx.poll():
+                switch = True
+                break
+        if ctx is not None and not switch:
+            switch = ctx.poll(force=True)
+        if switch:
+            try:
+                info = ctx.rescale()
+            except elastic.EdlEvicted:
+                print("rank %d: pod left the job (scale-in); exiting" % rank, flush=True)
+                ctx.close()
+                return
+            old_world, world, rank = world, info.size, info.rank
+            tr.rebuild(None)                                    # new symmetric slab + bucket plan; graph re-captured lazily
+            epoch, it0, step = take_cursor_from(info.root, (epoch, it, step))
+            base_lr = scaled_lr(args.lr, bs, world)             # lr = base * batch * world / 256
+            steps_per_epoch = args.steps_per_epoch or max(1, args.total_images // (bs * world))
+            meter = StepMeter(bs, world)
+            print("rescaled in place: world %d -> %d, rank %d, pid %d, rendezvous %.2fs" % (
+                old_world, world, rank, os.getpid(), info.rendezvous_s), flush=True)
+            if it0 < (steps_per_epoch if not args.max_steps else min(steps_per_epoch, args.max_steps)):
+                continue                                        # finish this epoch with the new world
+            it0 = 0
         if etcd is not None and epoch >= args.epochs - 2 and env.pod_id:
             edl_train_status.save_to_etcd(etcd, env.pod_id, edl_train_status.TrainStatus.NEARTHEEND)   # no more scale-out
         if rank == 0:
@@ -109,8 +161,11 @@ def main():
                              state_json=json.dumps({"world": world, "lr": lr}))
         if world > 1:
             dist.barrier()
+        epoch += 1
     write_benchmark_log(rank, dict(meter.summary(), model=args.model, batch_size=bs))   # reference: benchmark_logs/log_<id>
-    if world > 1:
+    if ctx is not None:
+        ctx.close()
+    elif world > 1:
         dist.destroy_process_group()
 
 

@@ -121,3 +121,54 @@ def test_rendezvous_store_and_commit_protocol(kv_server):
     kv.put(keys[1], b"joiner")
     assert commit() and not withdraw(keys[1]) and not commit()   # committed: nobody can leave, nobody commits twice
     kv.close()
+
+
+@pytest.mark.slow
+def test_resnet_trainer_rescales_in_place(kv_server, tmp_path):
+    """The flagship trainer path (StudentTrainer.rebuild + sync_from) under the launcher, CPU / gloo, tiny ResNet_vd:
+    pod B joins mid-epoch, A's trainer stays alive, both finish the job with identical parameters."""
+    job = "inplace_rn_" + uuid.uuid4().hex[:6]
+    ckpt = str(tmp_path / "ckpt")
+    script = os.path.join(ROOT, "examples", "collective", "resnet50", "train.py")
+
+    def launch(name):
+        env = dict(os.environ)
+        env.update({"PYTHONPATH": ROOT, "CUDA_VISIBLE_DEVICES": "", "PADDLE_RUNNING_PLATFORM": "", "EDL_POD_IP": "127.0.0.1",
+                    "EDL_INPLACE_CHECK_EVERY": "4", "EDL_INPLACE_ACK_TIMEOUT": "60", "OMP_NUM_THREADS": "2"})
+        cmd = [sys.executable, "-u", "-m", "edl_b200.collective.launch", "--nodes_range", "1:2", "--nproc_per_node", "1",
+               "--etcd_endpoints", kv_server.endpoint, "--job_id", job, "--log_dir", str(tmp_path / ("log" + name)),
+               "--hdfs_path", ckpt, "--rescale_mode", "inplace", script, "--model", "ResNet18_vd", "--width_mult", "0.125",
+               "--image_size", "32", "--class_dim", "10", "--batch_size", "4", "--epochs", "2", "--steps_per_epoch", "240",
+               "--ckpt", ckpt]
+        return subprocess.Popen(cmd, env=env, stdout=open(str(tmp_path / (name + ".launcher.log")), "w"),
+                                stderr=subprocess.STDOUT, start_new_session=True)
+
+    def worker_log(name):
+        p = tmp_path / ("log" + name) / "workerlog.0"
+        return p.read_text() if p.exists() else ""
+
+    a = launch("A")
+    b = None
+    try:
+        deadline = time.time() + 120
+        while "trainbatch 10 " not in worker_log("A"):
+            assert time.time() < deadline and a.poll() is None, worker_log("A")[-2000:]
+            time.sleep(0.2)
+        b = launch("B")
+        assert a.wait(timeout=400) == 0, worker_log("A")[-3000:]
+        assert b.wait(timeout=120) == 0, worker_log("B")[-3000:]
+        la, lb = worker_log("A"), worker_log("B")
+        assert "rescaled in place: world 1 -> 2" in la, la[-3000:]
+        assert "Traceback" not in la and "Traceback" not in lb
+        assert "falling back to stop-resume" not in (tmp_path / "A.launcher.log").read_text()
+        etcd = EtcdClient([kv_server.endpoint], root=job)
+        etcd.init()
+        assert edl_status.load_job_status_from_etcd(etcd) == edl_status.Status.SUCCEED
+        etcd.close()
+        from edl_b200.checkpoint import load_check_point
+        tensors, ts, state_json = load_check_point(ckpt)
+        assert tensors is not None and ts.epoch_no == 1 and json.loads(state_json)["world"] == 2
+    finally:
+        for p in (a, b):
+            if p is not None and p.poll() is None:
+                os.killpg(os.getpgid(p.pid), 9)
