@@ -232,7 +232,9 @@ def distill_main(args, world, rank, dev):
             "data": "synthetic images, random-init student and teacher", "impl": "edl",
             "config": {"model": "ResNet%d_vd student + %s teacher" % (args.layers, args.teacher),
                        "students": n_students, "teachers": n_students, "batch_per_gpu": B,
-                       "global_batch": B * n_students, "transport": "peer_ship + GEMM->peer-ship epilogue over NVSwitch peer memory, student/teacher pipelined by one batch",
+                       "global_batch": B * n_students,
+                       "transport": "peer_ship + GEMM->peer-ship epilogue over NVSwitch peer memory, "
+                                    "student/teacher pipelined by one batch",
                        "teacher_dtype": "e4m3 1x1 convs + bf16" if args.teacher_fp8 else "bf16",
                        "parallelism": "dp%d + %d teacher GPUs" % (n_students, n_students),
                        "baseline_note": "vs_baseline divides by the published 1514 img/s (8xV100 + 40xP4, BASELINE.md P3)"},

@@ -18,7 +18,6 @@ import json
 import logging
 import random
 import threading
-import time
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
 
 logger = logging.getLogger("edl.jobserver")

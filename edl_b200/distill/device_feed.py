@@ -22,7 +22,7 @@ All kernels take their sequence number from a device counter, so both sides are 
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 

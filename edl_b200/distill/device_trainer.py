@@ -8,7 +8,6 @@ Each student rank ``s`` is paired with teacher rank ``n_students + s``.
 from __future__ import annotations
 
 import torch
-import torch.distributed as dist
 
 from .. import ops
 from ..trainer import StudentTrainer

@@ -52,8 +52,7 @@ class DiscoveryClient:
         if code in (Code.OK, Code.ALREADY_REGISTER):
             with self._lock:
                 if registering or res.version != self._version:
-                    if registering or len(res.servers) > 0 or res.version != self._version:
-                        self._servers = list(res.servers) if (registering or res.servers or res.version != self._version) else self._servers
+                    self._servers = list(res.servers)
                     self._version = res.version
             self._registered.set()
             return True

@@ -67,7 +67,8 @@ __all__ = [
     "batch_norm_act", "BatchNormAct2d", "scale_shift_act", "bn_stats_into",
     "soft_cross_entropy", "topk_accuracy",
     "max_pool_3x3_s2", "avg_pool_2x2", "global_avg_pool",
-    "FlatSGDMomentum", "FlatAdam", "gemm_bf16", "linear_bf16", "conv1x1", "conv_lib", "conv3x3", "conv3x3_supported", "conv3x3_infer", "conv3x3_infer_supported",
+    "FlatSGDMomentum", "FlatAdam", "gemm_bf16", "linear_bf16", "conv1x1", "conv_lib", "conv3x3",
+    "conv3x3_supported", "conv3x3_infer", "conv3x3_infer_supported",
     "conv3x3_wgrad", "conv3x3_wgrad_supported",
     "rope", "rope_tables", "embedding_bag_mean", "normalize_u8", "DynamicLossScaler", "set_fused_bn", "drop_bn_hook",
 ]

@@ -149,7 +149,8 @@ class ImageBatchLoader:
                         out_q.put(err)
                         return
                     labels = torch.tensor([self.samples[si][1] for si in ids], dtype=torch.int64)
-                    flips = (torch.rand(len(ids)) < 0.5).to(torch.uint8) if self.train else torch.zeros(len(ids), dtype=torch.uint8)
+                    flips = ((torch.rand(len(ids)) < 0.5).to(torch.uint8) if self.train
+                             else torch.zeros(len(ids), dtype=torch.uint8))
                     out_q.put((buf, labels, flips))
                 out_q.put(None)
             except Exception as e:  # noqa: BLE001

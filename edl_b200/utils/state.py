@@ -12,14 +12,12 @@
 Persistence: JSON in the store at ``state/<name>``, written only by the leader through a
 compare-and-put on ``rank/0`` (same guard as the reference, state.py:186-200).
 """
-import json
-import time
 
 from . import constants, unique_name
 from . import train_status as edl_train_status
 from .error_utils import handle_errors_until_timeout
 from .exceptions import EdlEtcdIOError, EdlTableError
-from .json_serializable import Serializable, SerializableBase
+from .json_serializable import Serializable
 from .string_utils import bytes_to_string
 
 

@@ -121,7 +121,8 @@ def main():
             lr = (cosine_decay_with_warmup(step, base_lr, steps_per_epoch, args.epochs) if args.lr_strategy.startswith("cosine")
                   else piecewise_decay_with_warmup(step, base_lr, steps_per_epoch, [30, 60, 80]))
             tr.set_lr(lr)
-            x = torch.randn(bs, 3, args.image_size, args.image_size, generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
+            x = torch.randn(bs, 3, args.image_size, args.image_size, generator=g).to(dtype)
+            x = x.contiguous(memory_format=torch.channels_last)
             y = torch.randint(0, args.class_dim, (bs,), generator=g)
             loss = tr.step(x.pin_memory() if cuda else x, y.pin_memory() if cuda else y)
             step += 1

@@ -63,7 +63,8 @@ def sweep(dev, world, rank):
                 busbw = (mb << 20) * 2 * (world - 1) / world / (ms.item() * 1e-3) / 1e9
                 out.append({"MB": mb, "algo": algo, "blocks": nblocks, "ms": ms.item(), "busbw_GBps": busbw})
                 if rank == 0:
-                    print("allreduce fp32 %4d MB %-8s blocks %2d: %8.3f ms  busbw %7.1f GB/s" % (mb, algo, nblocks, ms.item(), busbw), flush=True)
+                    print("allreduce fp32 %4d MB %-8s blocks %2d: %8.3f ms  busbw %7.1f GB/s" % (
+                        mb, algo, nblocks, ms.item(), busbw), flush=True)
         pool._off -= 0   # slices are bump-allocated; the pool is sized for the largest one only
         pool._off = pool._sig_total
     return out

@@ -87,7 +87,8 @@ class Collector:
         return {"t": round(now, 1), "submitted": len(self.jobs),
                 "pending": sum(1 for j in self.jobs.values() if j.status == PENDING),
                 "running_trainers": sum(j.parallelism for j in self.jobs.values()),
-                "gpu_util": "%d/%d" % (used, alloc), "jobs": {n: "%s:%d" % (j.status, j.parallelism) for n, j in self.jobs.items()}}
+                "gpu_util": "%d/%d" % (used, alloc),
+                "jobs": {n: "%s:%d" % (j.status, j.parallelism) for n, j in self.jobs.items()}}
 
 
 def main():

@@ -1,3 +1,4 @@
+"""Shared fixtures: fast control-plane timing, the coordination store (Python and C++ builds), a store client."""
 import os
 import sys
 

@@ -89,7 +89,6 @@ def _worker(rank, world, port, q):
         assert pool.check_error() == 0
 
         # ---- engine end to end: 2 ranks with different data stay bit-identical and match 1-proc math
-        from edl_b200 import ops
         from edl_b200.models import ResNetVd, to_train_dtype
         from edl_b200.trainer import StudentTrainer
 

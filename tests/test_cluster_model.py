@@ -2,7 +2,6 @@
 (reference tests: test_pod.py, test_cluster.py, test_resource_pods.py, test_leader_pod.py,
 test_cluster_generator.py, test_cluster_watcher.py)."""
 import time
-import uuid
 
 import pytest
 

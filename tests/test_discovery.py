@@ -2,7 +2,6 @@
 teacher up/down propagation, client timeout, redirect between two discovery servers."""
 import time
 
-import pytest
 
 from edl_b200.discovery.etcd_client import EtcdClient
 from edl_b200.distill.balance_table import Service

@@ -1,11 +1,9 @@
 """DistillReader pipeline: ordering, batch reassembly for the 3 reader kinds, teacher failure /
 retire / join mid-stream, real gRPC teacher (reference: distill_reader_test.py:21-52 with a NOP
 teacher; here additionally a live TeacherServer on CPU)."""
-import threading
 import time
 
 import numpy as np
-import pytest
 import torch
 
 from edl_b200.distill import distill_worker

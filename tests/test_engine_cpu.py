@@ -1,9 +1,7 @@
 """CPU-side logic of the training engine: flat storage, bucket planning, fused-optimizer reference
 path, gloo data-parallel equivalence (world_size 2)."""
 import os
-import sys
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

@@ -3,7 +3,6 @@ removed by the JobServer schedule while training keeps resuming from atomic chec
 rescaled to the world size (BASELINE.json config 0; reference demo: README.md:121-160)."""
 import json
 import os
-import sys
 import threading
 import time
 import urllib.request

@@ -10,7 +10,6 @@ import sys
 import time
 import uuid
 
-import pytest
 
 from edl_b200.discovery.etcd_client import EtcdClient
 from edl_b200.utils import cluster as edl_cluster, status as edl_status

@@ -4,8 +4,8 @@ import torch
 import torch.nn.functional as F
 
 from edl_b200 import ops
-from edl_b200.models import ResNetVd, to_train_dtype, ConvBNAct
-from edl_b200.models.resnet_vd import Bottleneck, BasicBlock
+from edl_b200.models import ResNetVd, to_train_dtype
+from edl_b200.models.resnet_vd import Bottleneck
 from edl_b200.trainer import StudentTrainer
 
 pytestmark = pytest.mark.gpu

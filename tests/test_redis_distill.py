@@ -8,7 +8,7 @@ import time
 import numpy as np
 
 from edl_b200.distill import distill_worker
-from edl_b200.distill.distill_reader import DistillReader, DynamicServiceDiscover
+from edl_b200.distill.distill_reader import DistillReader
 from edl_b200.distill.redis.balance_server import HEADER, MAGIC, BalanceServer, pack_frame
 from edl_b200.distill.redis.client import Client
 from edl_b200.distill.redis.redis_store import RedisStore

@@ -6,7 +6,7 @@ import os
 import pytest
 import torch
 
-from edl_b200.checkpoint import (LocalFS, TrainStatus, clean_redundant, latest_version, list_versions,
+from edl_b200.checkpoint import (LocalFS, TrainStatus, latest_version, list_versions,
                                  load_check_point, save_check_point)
 from edl_b200.collective import serializable
 from edl_b200.utils import constants, exceptions, state as edl_state

@@ -88,3 +88,9 @@ def test_rescale_bench_runs_on_gloo(tmp_path):
     for k in ("shrink_inplace_s", "grow_inplace_s", "shrink_stop_resume_s", "grow_stop_resume_s", "checkpoint_save_s"):
         assert res[k] > 0
     assert any(d.startswith("__edl_checkpoint__.") for d in os.listdir(tmp_path / "ck"))
+
+
+def test_lint_gate_is_clean():
+    """tools/lint.py (docstrings, line length, unused imports, bare excepts, mutable defaults) over the whole tree."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "lint.py")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout[-3000:]
