@@ -31,6 +31,20 @@ def pytest_collection_modifyitems(config, items):
         ngpu = 0
     skip_gpu = pytest.mark.skip(reason="needs a CUDA device")
     skip_multi = pytest.mark.skip(reason="needs >= 2 CUDA devices")
+    # multi-process end-to-end modules take tens of seconds per test: they run against ONE store build (the C++
+    # one when it can be built); the store semantics themselves are covered for both builds by test_store*.py,
+    # test_cluster_model.py and test_discovery.py
+    e2e = ("test_launch.py", "test_liveft.py", "test_jobserver_elastic.py", "test_inplace_rescale.py")
+    drop = "[python]" if "native" in _kv_impls() else "[native]"
+    kept, deselected = [], []
+    for item in items:
+        if item.nodeid.split("::")[0].endswith(e2e) and item.nodeid.endswith(drop):
+            deselected.append(item)
+        else:
+            kept.append(item)
+    if deselected:
+        config.hook.pytest_deselected(items=deselected)
+        items[:] = kept
     for item in items:
         if "gpu" in item.keywords and ngpu < 1:
             item.add_marker(skip_gpu)

@@ -79,7 +79,8 @@ def test_two_discovery_servers_redirect(kv_server):
     p1, p2 = find_free_ports(2)
     with DiscoveryServer("127.0.0.1:%d" % p1, [kv_server.endpoint]) as s1, \
             DiscoveryServer("127.0.0.1:%d" % p2, [kv_server.endpoint]) as s2:
-        names = ("SvcA", "SvcB", "SvcC", "SvcD", "SvcE", "SvcF")
+        # enough names that the ring cannot put all of them on one server whatever the (random) ports hash to
+        names = ("SvcA",) + tuple("Svc%02d" % i for i in range(40))
         deadline = time.time() + 15            # let both learn about each other (watch-driven, no fixed sleep)
         while time.time() < deadline:
             if all(s1.table._owner(n)[0] == s2.table._owner(n)[0] for n in names) and \

@@ -53,12 +53,12 @@ def test_join_and_scale_in_without_restarting_the_survivor(kv_server, tmp_path):
                        if os.path.exists(f))
         raise AssertionError("world never became %d: %s\n%s" % (w, epochs()[-4:], logs))
 
-    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 260)
+    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 170)
     b = None
     try:
         e1 = wait_world(1, 60)
         pid_a = e1[-1]["pid"]
-        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 260)
+        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 170)
         e2 = wait_world(2, 90)
         assert e2[-1]["pid"] == pid_a, "the surviving trainer was restarted on scale-out"
         assert abs(e2[-1]["lr"] - 2 * e1[-1]["lr"]) < 1e-9                       # linear LR rescale, in place
