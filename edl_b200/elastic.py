@@ -22,6 +22,10 @@ Its design document lists "no restart" as future work.  Here, with ``EDL_RESCALE
   cursor from it over the fabric (``ElasticDataParallel.broadcast_parameters``) instead of reading the checkpoint;
   ``root is None`` means nobody survived (cold start or stop-resume fallback) and the checkpoint is the source.
 
+* a collective that FAILS because a peer died is the same thing triggered differently: ``recover()`` drops the
+  broken group, waits for the store to publish the new stage and rejoins as a survivor (hot recovery; the
+  reference restarts every trainer of the job and reloads the checkpoint).
+
 The launcher side (utils/launcher.py) leaves the trainers of a surviving pod alone when they have announced an
 ElasticContext and acknowledges the switch by waiting for their ready keys; anything else -- a trainer that does
 not answer in time, a trainer that died -- falls back to the reference's stop-resume for that pod, and the
@@ -153,7 +157,7 @@ class StageInfo:
     root: Optional[int]          # rank to take the training state from; None = load the checkpoint
     survivor: bool               # this trainer carried its state over from the previous stage
     prev_size: int               # world size this trainer ran with before (== size on a cold start)
-    rendezvous_s: float = 0.0    # seconds spent from "membership known" to "process group ready"
+    rendezvous_s: float = 0.0    # seconds from leaving the old process group to having the new one
 
 
 class ElasticContext:
@@ -324,16 +328,52 @@ class ElasticContext:
         """Leave the old process group, run the stage rendezvous, build the new group.  Raises
         :class:`EdlEvicted` when this trainer's pod is not part of the new stage."""
         old = self.info
+        t0 = time.time()
         if dist.is_initialized():
             dist.destroy_process_group()
         self._changed.clear()
         info = self._rendezvous(survivor=True, prev_size=old.size)
         self._init_group(info)
+        info.rendezvous_s = time.time() - t0          # old group torn down -> new group usable
         self.info = info
         self._steps = 0
         self._on_cluster_event(None, None)
         logger.info("trainer moved in place from stage %s (%d ranks) to %s as rank %d/%d in %.2fs", old.stage,
                     old.size, info.stage, info.rank, info.size, info.rendezvous_s)
+        return info
+
+    def recover(self, wait_s: Optional[float] = None) -> StageInfo:
+        """Hot recovery after a FAILED collective (a peer died mid-step; gloo raises, our all-reduce kernels time
+        out into ``check_comm_error()``): abandon the broken group at once -- closing its sockets is what makes the
+        other survivors' collectives fail fast too --, wait until the store has noticed the loss (the dead pod's
+        lease expires, the leader publishes a new stage), then rejoin as a survivor exactly like ``rescale()``.
+        The caller discards the interrupted step and takes ``StageInfo.root``'s state: every survivor ends up on the
+        root's last completed optimizer step, whatever each of them had applied of the broken one."""
+        old = self.info
+        try:
+            if dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception as e:  # noqa: BLE001 - the group is broken anyway
+            logger.warning("destroying the broken process group: %s", e)
+        wait_s = wait_s if wait_s is not None else constants.ETCD_TTL * 2 + 4 * constants.POLL_INTERVAL + 10
+        deadline = time.time() + wait_s
+        while time.time() < deadline:
+            c = edl_cluster.load_from_etcd(self._etcd, timeout=10)
+            if c is not None and c.stage != old.stage:
+                break
+            time.sleep(0.1)
+        else:
+            raise TimeoutError("a collective failed but the membership did not change within %.0fs" % wait_s)
+        self._changed.clear()
+        t0 = time.time()
+        info = self._rendezvous(survivor=True, prev_size=old.size)
+        self._init_group(info)
+        info.rendezvous_s = time.time() - t0          # new stage published -> new group usable
+        self.info = info
+        self._steps = 0
+        self._on_cluster_event(None, None)
+        logger.info("trainer recovered in place from stage %s (%d ranks) to %s as rank %d/%d", old.stage, old.size,
+                    info.stage, info.rank, info.size)
         return info
 
     def close(self):

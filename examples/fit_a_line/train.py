@@ -117,23 +117,35 @@ def main():
         g = torch.Generator().manual_seed(epoch)          # shuffle seed = epoch: reproducible after resume
         perm = torch.randperm(n, generator=g)
         shard = perm[rank::world]
-        switch = False
-        for i in range(0, len(shard) - args.batch + 1, args.batch):
-            idx = shard[i:i + args.batch]
-            dp.zero_grad()
-            loss = torch.nn.functional.mse_loss(dp(x[idx]), y[idx])
-            loss.backward()
-            dp.finish()
-            opt.step()
-            edl.notify_end_one_batch(None, state)
-            if inplace and ctx.poll():
-                switch = True
-                break
-        if inplace and not switch:
-            switch = ctx.poll(force=True)                  # epoch boundary: every rank asks, every rank agrees
+        switch = broken = False
+        try:
+            for i in range(0, len(shard) - args.batch + 1, args.batch):
+                idx = shard[i:i + args.batch]
+                dp.zero_grad()
+                loss = torch.nn.functional.mse_loss(dp(x[idx]), y[idx])
+                loss.backward()
+                dp.finish()
+                opt.step()
+                edl.notify_end_one_batch(None, state)
+                if inplace and ctx.poll():
+                    switch = True
+                    break
+            if inplace and not switch:
+                switch = ctx.poll(force=True)              # epoch boundary: every rank asks, every rank agrees
+            if not switch:
+                edl.notify_end_one_epoch(state)
+                if world > 1:
+                    dist.all_reduce(loss)
+                    loss /= world
+                    dist.barrier()                         # everybody finished the epoch before it is checkpointed
+        except RuntimeError as e:                          # a peer died inside a collective (gloo raises)
+            if not inplace:
+                raise
+            print("rank %d: collective failed (%s); recovering in place" % (rank, str(e).splitlines()[0][:120]), flush=True)
+            switch = broken = True
         if switch:
             try:
-                info = ctx.rescale()
+                info = ctx.recover() if broken else ctx.rescale()
             except elastic.EdlEvicted:
                 print("rank %d: pod left the job (scale-in); exiting" % rank, flush=True)
                 ctx.close()
@@ -142,13 +154,9 @@ def main():
             dp.rebuild(None)                               # new process group => new gradient buffers / bucket plan
             epoch, prev_world = take_state_from(info.root, epoch, old_world)
             state.adjust(prev_world, world)                # LR follows the world size
-            print("rescaled in place: world %d -> %d, rank %d, pid %d, %.2fs" % (
-                old_world, world, rank, os.getpid(), info.rendezvous_s), flush=True)
+            print("%s in place: world %d -> %d, rank %d, pid %d, %.2fs" % (
+                "recovered" if broken else "rescaled", old_world, world, rank, os.getpid(), info.rendezvous_s), flush=True)
             continue                                       # redo this epoch with the new sharding
-        edl.notify_end_one_epoch(state)
-        if world > 1:
-            dist.all_reduce(loss)
-            loss /= world
         if rank == 0:
             save_check_point(args.ckpt, {"model": model.state_dict(), "optim": opt.state_dict()},
                              TrainStatus(epoch, state.global_step_no), fs, trainer_id=0,
@@ -159,8 +167,6 @@ def main():
                 with open(os.path.join(args.report, "epochs.jsonl"), "a") as f:
                     f.write(json.dumps({"epoch": epoch, "world": world, "lr": opt.lr, "loss": float(loss),
                                         "t": time.time(), "pid": os.getpid()}) + "\n")
-        if world > 1:
-            dist.barrier()
         if args.epoch_sleep:
             time.sleep(args.epoch_sleep)
         epoch += 1

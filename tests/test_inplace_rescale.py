@@ -172,3 +172,55 @@ def test_resnet_trainer_rescales_in_place(kv_server, tmp_path):
         for p in (a, b):
             if p is not None and p.poll() is None:
                 os.killpg(os.getpgid(p.pid), 9)
+
+
+@pytest.mark.slow
+def test_hot_recovery_when_a_pod_dies_hard(kv_server, tmp_path):
+    """Pod B is SIGKILLed while both pods train: A's trainer sees its collective fail, drops the broken group, waits
+    for the store to publish the smaller stage and carries on ALONE IN THE SAME PROCESS (the reference -- and this
+    launcher's restart mode -- kill and restart every trainer of the job)."""
+    job = "hot_" + uuid.uuid4().hex[:6]
+    report, ckpt = str(tmp_path / "report"), str(tmp_path / "ckpt")
+
+    def epochs():
+        p = os.path.join(report, "epochs.jsonl")
+        return [json.loads(l) for l in open(p)] if os.path.exists(p) else []
+
+    def wait_world(w, timeout, min_new=3):
+        n0 = len(epochs())
+        deadline = time.time() + timeout
+        while time.time() < deadline:
+            e = epochs()
+            if len(e) >= n0 + min_new and all(x["world"] == w for x in e[-min_new:]):
+                return e
+            time.sleep(0.2)
+        raise AssertionError("world never became %d: %s\n%s" % (w, epochs()[-4:],
+                                                                  open(str(tmp_path / "logA.launcher.log")).read()[-3000:]))
+
+    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 200)
+    b = None
+    try:
+        e1 = wait_world(1, 60)
+        pid_a = e1[-1]["pid"]
+        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 200)
+        wait_world(2, 90)
+        import psutil
+
+        victims = [psutil.Process(b.pid)] + psutil.Process(b.pid).children(recursive=True)
+        for v in victims:                                     # launcher B AND its trainer (own session) die without a word
+            try:
+                v.kill()
+            except psutil.NoSuchProcess:
+                pass
+        e1b = wait_world(1, 90)
+        assert e1b[-1]["pid"] == pid_a, "the survivor was restarted instead of recovering in place"
+        assert abs(e1b[-1]["lr"] - e1[-1]["lr"]) < 1e-9
+        assert a.wait(timeout=120) == 0
+        worker = open(str(tmp_path / "logA" / "workerlog.0")).read()
+        assert "recovered in place: world 2 -> 1" in worker, worker[-2000:]
+        ep = [x["epoch"] for x in epochs()]
+        assert ep == sorted(set(ep))
+    finally:
+        for p in (a, b):
+            if p is not None and p.poll() is None:
+                os.killpg(os.getpgid(p.pid), 9)
