@@ -307,16 +307,23 @@ class ElasticContext:
                     "checkpoint" if info.root is None else "rank %d" % info.root)
         return info
 
-    def poll(self, force: bool = False) -> bool:
+    def poll(self, force: bool = False, agree=None) -> bool:
         """Call once per training step.  True on EVERY rank of the current stage at the same step as soon as any
         of them has seen the membership change (the decision rides on a 1-element MAX all-reduce every
-        ``check_every`` steps)."""
+        ``check_every`` steps).  ``agree`` (e.g. ``ElasticDataParallel.agree``) replaces the library all-reduce by
+        a collective with a timeout: ``flag -> (max flag, error word)``; a non-zero error word raises
+        ``RuntimeError`` so that the caller's hot-recovery path (``recover()``) takes over."""
         if self.standalone or self.info is None:
             return False
         self._steps += 1
         if not force and self._steps % self.check_every != 0:
             return False
         flag = 1.0 if (self._changed.is_set() and self._joiners_ready()) else 0.0
+        if agree is not None and self.info.size > 1:
+            flag, err = agree(flag)
+            if err:
+                raise RuntimeError("collective timed out waiting for peer %d (dead pod?)" % (err - 1))
+            return flag > 0.5
         if self.info.size > 1 and dist.is_initialized():
             dev = torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu")
             t = torch.tensor([flag], device=dev)

@@ -309,6 +309,27 @@ class ElasticDataParallel:
     def check_comm_error(self) -> int:
         return self.pool.check_error() if self.pool is not None else 0
 
+    def agree(self, flag: float):
+        """(max of ``flag`` over the ranks, comm error word).  The agreement ``ElasticContext.poll`` needs, routed
+        through our own scalar all-gather kernel when the ranks share symmetric memory: unlike a library
+        all-reduce it has the ``globaltimer`` timeout, so a DEAD peer shows up as a non-zero error word a few
+        seconds later instead of a hung process -- the trigger for ``ElasticContext.recover()`` on GPUs."""
+        if self.world <= 1:
+            return float(flag), 0
+        if self.use_symm and self.slices:
+            from ..ops import native, count_launch
+
+            sl = max(self.slices.values(), key=lambda x: x.tensor.numel())
+            inp = torch.tensor([float(flag), 0.0], device=self.device, dtype=torch.float32)
+            out = torch.zeros(self.world * 2, device=self.device, dtype=torch.float32)
+            native().comm_allgather_scalars(sl.data_ptrs, sl.sig_ptrs, self.rank, inp, out, min(self.timeout_s, 10.0))
+            count_launch()
+            err = self.check_comm_error()                     # host sync: the kernel above has finished
+            return float(out.view(self.world, 2)[:, 0].max().item()), err
+        t = torch.tensor([float(flag)], device=self.device if self.device.type == "cuda" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t.item()), 0
+
     def rebuild(self, group: Optional[dist.ProcessGroup]):
         """Elastic stage change: new group => new symmetric slab, new bucket plan.  Parameters,
         master weights and optimizer state stay where they are (no process restart)."""

@@ -132,11 +132,11 @@ def main():
             if (it - 1) % 10 == 0 and rank == 0:
                 print("Pass %d trainbatch %d loss %.4f lr %.5f speed %.1f img/s" % (
                     epoch, it - 1, float(loss), lr, seen * world / max(1e-6, time.time() - t0)), flush=True)
-            if ctx is not None and ctx.poll():
+            if ctx is not None and ctx.poll(agree=tr.dp.agree):
                 switch = True
                 break
         if ctx is not None and not switch:
-            switch = ctx.poll(force=True)
+            switch = ctx.poll(force=True, agree=tr.dp.agree)
         if switch:
             try:
                 info = ctx.rescale()

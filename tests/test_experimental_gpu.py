@@ -157,3 +157,48 @@ def test_step_pipelined_matches_step():
     assert len(a) == len(b) == 9
     for u, v in zip(a, b):
         assert abs(u - v) <= 2e-2 * max(1.0, abs(u)), (a, b)
+
+
+def _agree_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    try:
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        from edl_b200.models import ResNetVd, to_train_dtype
+        from edl_b200.parallel import ElasticDataParallel
+
+        m = to_train_dtype(ResNetVd(18, class_dim=16, width_mult=0.25), torch.bfloat16, dev)
+        dp = ElasticDataParallel(m)
+        assert dp.agree(0.0) == (0.0, 0)
+        assert dp.agree(1.0 if rank == world - 1 else 0.0) == (1.0, 0)        # any rank's flag reaches every rank
+        for _ in range(5):
+            assert dp.agree(0.0) == (0.0, 0)
+        if rank == 0:
+            q.put("ok")
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+
+        q.put("rank %d: %s\n%s" % (rank, e, traceback.format_exc()))
+        raise
+
+
+@pytest.mark.multigpu
+def test_agreement_through_the_scalar_allgather_kernel():
+    import torch.multiprocessing as mp
+
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + os.getpid() % 1000
+    procs = [ctx.Process(target=_agree_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = q.get(timeout=300)
+    [p.join(60) for p in procs]
+    assert res == "ok", res
