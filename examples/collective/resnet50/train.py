@@ -110,6 +110,7 @@ def main():
         etcd.init()
     meter = StepMeter(bs, world)
     lr = base_lr
+    progress = os.environ.get("EDL_PROGRESS_FILE", "")
     while epoch < args.epochs:
         g = torch.Generator().manual_seed(epoch * 1000 + rank)       # pass_id as seed: reproducible after resume
         t0, seen = time.time(), 0
@@ -129,6 +130,10 @@ def main():
             it += 1
             seen += bs
             meter.step()
+            if progress and rank == 0 and step % 5 == 0:
+                with open(progress, "a") as fh:       # machine-readable heartbeat (tools/bench_elastic_launch.py)
+                    fh.write(json.dumps({"t": time.time(), "step": step, "epoch": epoch, "world": world,
+                                         "pid": os.getpid(), "loss": float(loss)}) + "\n")
             if (it - 1) % 10 == 0 and rank == 0:
                 print("Pass %d trainbatch %d loss %.4f lr %.5f speed %.1f img/s" % (
                     epoch, it - 1, float(loss), lr, seen * world / max(1e-6, time.time() - t0)), flush=True)

@@ -10,4 +10,9 @@ timeout 600 $TR --master-port 29611 tools/bench_comm.py --sweep --exposed --out 
 timeout 600 $TR --master-port 29612 tools/bench_rescale.py --drop $(( N >= 4 ? 2 : 1 )) --out gpurun_out/rescale_${N}gpu.json > gpurun_out/rescale_${N}gpu.log 2>&1
 timeout 600 $TR --master-port 29613 examples/ctr/train.py --sweep --out gpurun_out/ctr_sweep_${N}gpu.json > gpurun_out/ctr_sweep_${N}gpu.log 2>&1
 timeout 300 $TR --master-port 29614 examples/ctr/train.py --model deepfm --steps 30 --vocab 1000001 --out gpurun_out/ctr_deepfm_${N}gpu.json > gpurun_out/ctr_deepfm_${N}gpu.log 2>&1
+# launcher-level recovery time with real GPU trainers: pod A = first half of the GPUs, pod B = second half
+timeout 900 python tools/bench_elastic_launch.py --native-store --trainer resnet --gpus-per-pod $(( N / 2 )) \
+  --out gpurun_out/elastic_launch_${N}gpu.json > gpurun_out/elastic_launch_${N}gpu.log 2>&1
+EDL_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -q -k agreement > gpurun_out/agree_test.log 2>&1
+tail -n 3 gpurun_out/elastic_launch_${N}gpu.log gpurun_out/agree_test.log
 tail -n 3 gpurun_out/comm_${N}gpu.log gpurun_out/rescale_${N}gpu.log gpurun_out/ctr_sweep_${N}gpu.log gpurun_out/ctr_deepfm_${N}gpu.log

@@ -8,6 +8,8 @@ stop-resume mode and for the in-place mode (edl_b200/elastic.py):
   leave  = first epoch reported at world 1  -  ScaleIn RPC
 
     python tools/bench_elastic_launch.py [--native-store] [--out profiles/elastic_launch_cpu.json]
+    python tools/bench_elastic_launch.py --trainer resnet --gpus-per-pod 4 --out gpurun_out/elastic_launch_8gpu.json
+        # on an 8-GPU box: pod A = GPUs 0-3, pod B = GPUs 4-7, ResNet50_vd, 4 -> 8 -> 4 trainers
 """
 import argparse
 import json
@@ -27,14 +29,28 @@ from edl_b200.store import KVServer, NativeKVServer  # noqa: E402
 from edl_b200.utils import leader_pod, pod_server_client  # noqa: E402
 
 
+CFG = {"trainer": "fit", "gpus_per_pod": 0}
+RESNET = os.path.join(ROOT, "examples", "collective", "resnet50", "train.py")
+
+
 def launch(endpoint, job, tmp, name, mode):
-    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", PADDLE_RUNNING_PLATFORM="", EDL_POD_IP="127.0.0.1",
-               FIT_REPORT_DIR=os.path.join(tmp, "report"), EDL_INPLACE_CHECK_EVERY="3",
+    g = CFG["gpus_per_pod"]
+    first = 0 if name == "A" else g
+    env = dict(os.environ, PYTHONPATH=ROOT, PADDLE_RUNNING_PLATFORM="", EDL_POD_IP="127.0.0.1",
+               CUDA_VISIBLE_DEVICES=",".join(str(first + i) for i in range(g)),
+               FIT_REPORT_DIR=os.path.join(tmp, "report"), EDL_PROGRESS_FILE=os.path.join(tmp, "report", "epochs.jsonl"),
+               EDL_INPLACE_CHECK_EVERY="3" if CFG["trainer"] == "fit" else "10",
                EDL_ETCD_TTL="1.5", EDL_POLL_INTERVAL="0.3", EDL_KILL_GRACE="1")
-    cmd = [sys.executable, "-u", "-m", "edl_b200.collective.launch", "--nodes_range", "1:2", "--nproc_per_node", "1",
+    os.makedirs(os.path.join(tmp, "report"), exist_ok=True)
+    if CFG["trainer"] == "fit":
+        script = [TRAIN, "--epochs", "100000", "--epoch_sleep", "0.02", "--ckpt", os.path.join(tmp, "ckpt")]
+    else:
+        script = [RESNET, "--model", "ResNet50_vd", "--epochs", "1000", "--steps_per_epoch", "400",
+                  "--ckpt", os.path.join(tmp, "ckpt")]
+    cmd = [sys.executable, "-u", "-m", "edl_b200.collective.launch", "--nodes_range", "1:2",
+           "--nproc_per_node", str(max(1, g)),
            "--etcd_endpoints", endpoint, "--job_id", job, "--log_dir", os.path.join(tmp, "log" + name),
-           "--hdfs_path", os.path.join(tmp, "ckpt"), "--rescale_mode", mode,
-           TRAIN, "--epochs", "100000", "--epoch_sleep", "0.02", "--ckpt", os.path.join(tmp, "ckpt")]
+           "--hdfs_path", os.path.join(tmp, "ckpt"), "--rescale_mode", mode] + script
     return subprocess.Popen(cmd, env=env, stdout=open(os.path.join(tmp, name + ".log"), "w"), stderr=subprocess.STDOUT,
                             start_new_session=True)
 
@@ -61,17 +77,19 @@ def run(mode, server_cls):
         ts = [x["t"] for x in e if x["t"] > t_event - 2.0]
         return max(b - a for a, b in zip(ts[:-1], ts[1:]))
 
+    w1 = max(1, CFG["gpus_per_pod"])
+    w2 = 2 * w1
     with server_cls() as srv:
         a = launch(srv.endpoint, job, tmp, "A", mode)
         b = None
         try:
-            wait_world(1)
+            wait_world(w1)
             t_join = time.time()
             b = launch(srv.endpoint, job, tmp, "B", mode)
-            e = wait_world(2)
-            join = min(x["t"] for x in e if x["world"] == 2 and x["t"] > t_join) - t_join
+            e = wait_world(w2, timeout=300)
+            join = min(x["t"] for x in e if x["world"] == w2 and x["t"] > t_join) - t_join
             join_stall = stall(e, t_join)
-            pids_before = {x["pid"] for x in e if x["world"] == 1}
+            pids_before = {x["pid"] for x in e if x["world"] == w1 and x["t"] < t_join}
             survivor_kept = e[-1]["pid"] in pids_before
             etcd = EtcdClient([srv.endpoint], root=job)
             etcd.init()
@@ -79,8 +97,8 @@ def run(mode, server_cls):
             t_leave = time.time()
             cli.scale_in(1)
             cli.close()
-            e = wait_world(1)
-            leave = min(x["t"] for x in e if x["world"] == 1 and x["t"] > t_leave) - t_leave
+            e = wait_world(w1, timeout=300)
+            leave = min(x["t"] for x in e if x["world"] == w1 and x["t"] > t_leave) - t_leave
             leave_stall = stall(e, t_leave)
             etcd.close()
             return {"mode": mode, "store": server_cls.__name__, "join_s": join, "join_stall_s": join_stall,
@@ -95,13 +113,17 @@ def run(mode, server_cls):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--native-store", action="store_true")
+    ap.add_argument("--trainer", default="fit", choices=["fit", "resnet"])
+    ap.add_argument("--gpus-per-pod", type=int, default=0, help="GPUs (= trainers) per pod; 0 = CPU / gloo")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
+    CFG.update(trainer=args.trainer, gpus_per_pod=args.gpus_per_pod)
     cls = NativeKVServer if args.native_store else KVServer
     res = [run("restart", cls), run("inplace", cls)]
     for r in res:
         print(json.dumps(r))
     if args.out:
         with open(args.out, "w") as f:
-            json.dump({"note": "CPU / gloo, fit_a_line, test timing constants (TTL 1.5 s, polls 0.3 s, kill grace 1 s); "
+            json.dump({"trainer": CFG["trainer"], "gpus_per_pod": CFG["gpus_per_pod"],
+                       "note": "fit_a_line runs are CPU / gloo; test timing constants (TTL 1.5 s, polls 0.3 s, kill grace 1 s); "
                                "the reference's constants are 15 s / 3 s / 3 s (BASELINE.md)", "runs": res}, f, indent=1)
