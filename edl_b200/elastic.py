@@ -147,6 +147,28 @@ class KVRendezvousStore(dist.Store):
     def set_timeout(self, timeout):
         self._t = timeout.total_seconds() if hasattr(timeout, "total_seconds") else float(timeout)
 
+    # extended API (symmetric-memory and NCCL bootstrap use it when the store advertises it)
+    def has_extended_api(self):
+        return True
+
+    def append(self, key, value):
+        k = self._p + key
+        add = value if isinstance(value, (bytes, bytearray)) else str(value).encode()
+        while True:
+            v, meta = self._kv.get(k)
+            cmp_ = [{"key": k, "target": "version", "op": "==", "value": meta["version"] if meta else 0}]
+            ok, _ = self._kv.txn(cmp_, [{"op": "put", "key": k, "value": (v or b"") + bytes(add)}])
+            if ok:
+                return
+
+    def multi_get(self, keys):
+        return [self.get(k) for k in keys]
+
+    def multi_set(self, keys, values):
+        ops = [{"op": "put", "key": self._p + k, "value": v if isinstance(v, (bytes, bytearray)) else str(v).encode()}
+               for k, v in zip(keys, values)]
+        self._kv.txn([], ops)
+
 
 @dataclass
 class StageInfo:

@@ -105,6 +105,11 @@ def test_rendezvous_store_and_commit_protocol(kv_server):
     with pytest.raises(RuntimeError):
         st.get("never")
     assert st.num_keys() == 3 and st.delete_key("a") and st.num_keys() == 2
+    assert st.has_extended_api()
+    st.append("log", b"ab")
+    st.append("log", b"cd")
+    st.multi_set(["m1", "m2"], [b"x", b"yy"])
+    assert st.multi_get(["log", "m1", "m2"]) == [b"abcd", b"x", b"yy"]
     # commit needs every ready key; a withdrawal is only possible while the commit record is absent
     job, stage = "j", "S"
     keys = [elastic.ready_key(job, stage, r) for r in range(2)]
