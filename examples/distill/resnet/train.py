@@ -29,7 +29,7 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), 
 sys.path.insert(0, ROOT)
 
 import edl_b200 as edl  # noqa: E402
-from edl_b200 import ops  # noqa: E402
+from edl_b200 import elastic, ops  # noqa: E402
 from edl_b200.checkpoint import LocalFS, TrainStatus, load_check_point, save_check_point  # noqa: E402
 from edl_b200.models import ResNetVd, to_train_dtype  # noqa: E402
 from edl_b200.ops.optim import cosine_decay_with_warmup, piecewise_decay_with_warmup, scaled_lr  # noqa: E402
@@ -129,8 +129,14 @@ def batches_of(stream, bs):
 
 def main():
     args = parse()
-    env = edl.init_distributed()
-    world, rank = env.size, env.global_rank
+    ctx = None
+    if elastic.inplace_requested():       # launcher --rescale_mode inplace: survive membership changes (edl_b200/elastic.py)
+        ctx = elastic.ElasticContext(check_every=int(os.environ.get("EDL_INPLACE_CHECK_EVERY", "20")))
+        info = ctx.start()
+        world, rank = info.size, info.rank
+    else:
+        env = edl.init_distributed()
+        world, rank = env.size, env.global_rank
     cuda = torch.cuda.is_available()
     dev = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
     c, h, w = (int(v) for v in args.image_shape.split(","))
@@ -159,11 +165,25 @@ def main():
     if args.use_dgc:
         tr.opt.dp = tr.dp
     fs = LocalFS()
-    tensors, ts, _ = load_check_point(args.checkpoint, fs, trainer_id=rank, map_location=dev)
-    if tensors is not None:
-        tr.load_state_dict(tensors)
+
+    def take_cursor_from(root, cursor):
+        """In-place state handoff: parameters, optimizer state and the (epoch, step) cursor of ``root``."""
+        if world <= 1:
+            return cursor
+        tr.sync_from(root)
+        box = [cursor]
+        dist.broadcast_object_list(box, src=root)
+        return box[0]
+
+    if ctx is not None and info.root is not None:
+        first_epoch, step = take_cursor_from(info.root, None)       # joined a running job: nothing read from disk
+    else:
+        tensors, ts, _ = load_check_point(args.checkpoint, fs, trainer_id=rank, map_location=dev)
+        if tensors is not None:
+            tr.load_state_dict(tensors)
+        first_epoch, step = ts.next(), ts.global_step
     steps_per_epoch = max(1, args.total_images // (bs * world))
-    step = ts.global_step
+    shard = {"rank": rank, "world": world}                         # the data stream follows the current stage
 
     dr = None
     if args.use_distill_service:
@@ -177,16 +197,22 @@ def main():
     epoch_box = [0]
     reader = None
     if dr is not None:
-        reader = dr.set_sample_list_generator(lambda: batches_of(sample_stream(args, rank, world, epoch_box[0]), bs))
+        reader = dr.set_sample_list_generator(
+            lambda: batches_of(sample_stream(args, shard["rank"], shard["world"], epoch_box[0]), bs))
 
     onehot_eye = None
     prof = StepProfiler(100, 105, "./profile_pass_0", enabled=args.profile, rank=rank)
-    for epoch in range(ts.next(), args.num_epochs):
+    epoch = first_epoch
+    while epoch < args.num_epochs:
         epoch_box[0] = epoch
         it = reader() if reader is not None else batches_of(sample_stream(args, rank, world, epoch), bs)
         t0, seen = time.time(), 0
+        switch = False
         for bi, batch in enumerate(it):
             if args.max_steps and bi >= args.max_steps:
+                break
+            if ctx is not None and bi > 0 and ctx.poll(agree=tr.dp.agree):
+                switch = True
                 break
             lr = (cosine_decay_with_warmup(step, base_lr, steps_per_epoch, args.num_epochs)
                   if args.lr_strategy.startswith("cosine")
@@ -218,6 +244,24 @@ def main():
             if bi % args.fetch_steps == 0 and rank == 0:
                 print("Pass %d, batch %d, loss %.5f, lr %.5f, speed %.1f img/s" % (
                     epoch, bi, float(loss), lr, seen * world / max(1e-6, time.time() - t0)), flush=True)
+        if ctx is not None and not switch:
+            switch = ctx.poll(force=True, agree=tr.dp.agree)
+        if switch:
+            if hasattr(it, "close"):
+                it.close()                                      # stop the (distill) reader of the old shard
+            try:
+                info = ctx.rescale()
+            except elastic.EdlEvicted:
+                print("rank %d: pod left the job (scale-in); exiting" % rank, flush=True)
+                break
+            old_world, world, rank = world, info.size, info.rank
+            shard.update(rank=rank, world=world)
+            tr.rebuild(None)
+            epoch, step = take_cursor_from(info.root, (epoch, step))
+            base_lr = scaled_lr(args.lr, bs, world)
+            steps_per_epoch = max(1, args.total_images // (bs * world))
+            print("rescaled in place: world %d -> %d, rank %d, pid %d" % (old_world, world, rank, os.getpid()), flush=True)
+            continue                                            # this epoch again, re-sharded for the new world
         if args.do_test:
             val = batches_of(sample_stream(args, rank, world, 10 ** 6), bs)
             ev = tr.evaluate((torch.from_numpy(np.stack([s[0] for s in b])), torch.from_numpy(np.concatenate([s[1] for s in b])))
@@ -229,9 +273,12 @@ def main():
                              state_json=json.dumps({"world": world, "lr": base_lr}))
         if world > 1:
             dist.barrier()
+        epoch += 1
     if dr is not None:
         dr.stop()
-    if world > 1:
+    if ctx is not None:
+        ctx.close()
+    elif world > 1:
         dist.destroy_process_group()
 
 
