@@ -330,6 +330,13 @@ const char* conv3x3_wgrad_bf16(const Conv3x3WgradArgs& a, cudaStream_t stream) {
 
 int conv3x3_wgrad_tiles(int Cin, int Cout) { return ((Cout + kBlockM - 1) / kBlockM) * (Cin / kBlockN) * 3; }
 
+void conv3x3_wgrad_plan(int N, int H, int W, int* bh, int* nb, int* kb) {
+  const WgradGeometry g = plan_wgrad(N, H, W);
+  *bh = g.ok ? g.BH : 0;
+  *nb = g.ok ? g.NB : 0;
+  *kb = g.ok ? g.KB : 0;
+}
+
 int conv3x3_wgrad_kblocks(int N, int H, int W) {
   const WgradGeometry g = plan_wgrad(N, H, W);
   if (!g.ok) return 0;

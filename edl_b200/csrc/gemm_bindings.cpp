@@ -245,6 +245,12 @@ void conv3x3_wgrad(const Tensor& x, const Tensor& dy, Tensor& dw, Tensor& ws, Te
   TORCH_CHECK(err == nullptr, "edl conv3x3_wgrad failed: ", err);
 }
 
+std::vector<int64_t> conv3x3_wgrad_plan(int64_t n, int64_t h, int64_t w) {
+  int bh = 0, nb = 0, kb = 0;
+  edl::conv3x3_wgrad_plan((int)n, (int)h, (int)w, &bh, &nb, &kb);
+  return {bh, nb, kb};
+}
+
 bool conv3x3_wgrad_supported(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cout) {
   return edl::conv3x3_wgrad_supported((int)n, (int)h, (int)w, (int)cin, (int)cout);
 }
@@ -291,4 +297,5 @@ void register_gemm_bindings(pybind11::module_& m) {
   m.def("conv3x3_wgrad_supported", &conv3x3_wgrad_supported);
   m.def("conv3x3_wgrad_tiles", &edl::conv3x3_wgrad_tiles);
   m.def("conv3x3_wgrad_kblocks", &edl::conv3x3_wgrad_kblocks);
+  m.def("conv3x3_wgrad_plan", &conv3x3_wgrad_plan);
 }

@@ -1,0 +1,55 @@
+"""Host-side check of the 3x3 weight-gradient kernel's algorithm (csrc/conv3x3_wgrad.cu) without a GPU: the pixel-box
+planner is called through the built extension, and the kernel's data movement -- 4-D boxes {64 ch, W, BH rows, NB images}
+of dY and of X shifted by (s-1, r-1), out-of-image elements zero-filled, one [Cout, Cin] product per tap accumulated over
+the pixel blocks, result laid out KRSC -- is replayed with torch ops and compared with autograd's weight gradient.
+What this cannot cover (descriptors, swizzle, barriers) is what tests/test_experimental_gpu.py is for."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from edl_b200 import ops
+
+pytestmark = pytest.mark.skipif(not ops.native_available(), reason="extension not built")
+
+
+def _box(t, n0, nb, h0, bh, w0, w):
+    """TMA tile semantics: t[n0:n0+nb, h0:h0+bh, w0:w0+w, :] with everything outside the tensor read as zero."""
+    N, H, W, C = t.shape
+    out = torch.zeros(nb, bh, w, C, dtype=t.dtype)
+    ns, hs, ws = max(n0, 0), max(h0, 0), max(w0, 0)
+    ne, he, we = min(n0 + nb, N), min(h0 + bh, H), min(w0 + w, W)
+    if ns < ne and hs < he and ws < we:
+        out[ns - n0:ne - n0, hs - h0:he - h0, ws - w0:we - w0] = t[ns:ne, hs:he, ws:we]
+    return out
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(4, 56, 56, 8, 6), (8, 28, 28, 5, 7), (8, 14, 14, 4, 4), (32, 7, 7, 3, 5),
+                                            (3, 6, 8, 4, 4), (5, 14, 14, 2, 3), (2, 4, 28, 3, 3), (6, 10, 16, 2, 2)])
+def test_pixel_box_replay_matches_autograd(n, h, w, cin, cout):
+    bh, nb, kb = ops.native().conv3x3_wgrad_plan(n, h, w)
+    if kb == 0:
+        assert not ops.native().conv3x3_wgrad_supported(n, h, w, 64, 64)
+        pytest.skip("geometry not supported by the planner")
+    assert kb == w * bh * nb and kb % 16 == 0 and kb <= 112 and bh <= h and nb <= n
+    hb, ng = -(-h // bh), -(-n // nb)
+    assert ops.native().conv3x3_wgrad_kblocks(n, h, w) == hb * ng
+    torch.manual_seed(0)
+    x = torch.randn(n, h, w, cin, dtype=torch.float64)          # NHWC like the kernel sees it
+    dy = torch.randn(n, h, w, cout, dtype=torch.float64)
+    dw = torch.zeros(cout, 3, 3, cin, dtype=torch.float64)     # KRSC
+    for kblk in range(hb * ng):
+        h0, img0 = (kblk % hb) * bh, (kblk // hb) * nb
+        a = _box(dy, img0, nb, h0, bh, 0, w).reshape(kb, cout)                  # [pixels, Cout]  (MN-major A)
+        for r in range(3):
+            for s in range(3):
+                b = _box(x, img0, nb, h0 + r - 1, bh, s - 1, w).reshape(kb, cin)  # same box, shifted (MN-major B)
+                dw[:, r, s, :] += a.t() @ b
+    wt = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.permute(0, 3, 1, 2), wt, None, 1, 1).backward(dy.permute(0, 3, 1, 2))
+    assert torch.allclose(dw, wt.grad.permute(0, 2, 3, 1), atol=1e-9)
+
+
+def test_resnet_stage_geometries_waste_nothing():
+    for n, hw in ((32, 56), (32, 28), (32, 14), (32, 7)):
+        bh, nb, kb = ops.native().conv3x3_wgrad_plan(n, hw, hw)
+        assert kb == 112 and hw % bh == 0 and n % nb == 0, (hw, bh, nb, kb)      # every MMA row is a real pixel
