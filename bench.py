@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--teacher-fp8", action="store_true", help="distill mode: e4m3 tcgen05 GEMMs for the teacher's 1x1 convs")
     ap.add_argument("--no-fused-bn", action="store_true", help="A/B: disable the SM-resident fused BN kernels")
     ap.add_argument("--no-stream-bn", action="store_true", help="A/B: disable the cp.async.bulk BN kernels")
+    ap.add_argument("--teacher-fuse-res", action="store_true",
+                    help="A/B (experimental, distill mode): residual add of the teacher's blocks inside the GEMM epilogue")
     ap.add_argument("--pdl", action="store_true", help="A/B (experimental): programmatic dependent launch of the hot kernels")
     ap.add_argument("--own-wgrad3", action="store_true", help="A/B (experimental): tcgen05 3x3 weight-gradient kernel")
     return ap.parse_args()
@@ -236,6 +238,7 @@ def distill_main(args, world, rank, dev):
                        "transport": "peer_ship + GEMM->peer-ship epilogue over NVSwitch peer memory, "
                                     "student/teacher pipelined by one batch",
                        "teacher_dtype": "e4m3 1x1 convs + bf16" if args.teacher_fp8 else "bf16",
+                       "teacher_fuse_res": bool(args.teacher_fuse_res), "pdl": bool(args.pdl),
                        "parallelism": "dp%d + %d teacher GPUs" % (n_students, n_students),
                        "baseline_note": "vs_baseline divides by the published 1514 img/s (8xV100 + 40xP4, BASELINE.md P3)"},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "link_error": err}))
@@ -252,6 +255,8 @@ def main():
         os.environ["EDL_PDL"] = "1"            # read when the extension is loaded
     if args.own_wgrad3:
         os.environ["EDL_OWN_WGRAD3"] = "1"     # read when edl_b200.ops.gemm is imported
+    if args.teacher_fuse_res:
+        os.environ["EDL_TEACHER_FUSE_RES"] = "1"   # read when edl_b200.models.resnext is imported
 
     import torch
     import torch.distributed as dist

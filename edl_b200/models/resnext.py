@@ -41,6 +41,20 @@ class FoldedConv(nn.Module):
         s = gamma.float() * torch.rsqrt(var.float() + eps)
         self.scale.copy_(s)
         self.shift.copy_(beta.float() - mean.float() * s)
+        self._w_scaled = None
+
+    def _scaled_weight(self):
+        """bf16 [Cout, Cin] weights with the folded-BN scale multiplied in (cached; inference weights are frozen)."""
+        key = (self.weight.data_ptr(), self.weight._version, self.scale._version)
+        if getattr(self, "_w_scaled", None) is None or self._w_scaled[0] != key:
+            w = (self.weight.view(self.cout, self.cin).float() * self.scale.float()[:, None]).to(self.weight.dtype)
+            self._w_scaled = (key, w.contiguous())
+        return self._w_scaled[1]
+
+    def _residual_fusable(self, residual, y):
+        return (ops.native().persistent_gemm_enabled() and residual.shape == y.shape and residual.dtype == y.dtype
+                and residual.is_contiguous(memory_format=torch.channels_last) and self.cout % 8 == 0
+                and residual.data_ptr() % 16 == 0)
 
     # ---- fp8 (e4m3) mode of the 1x1 convolutions: see ops/fp8.py -------------------------------
     def fp8_eligible(self):
@@ -89,6 +103,13 @@ class FoldedConv(nn.Module):
                 ops.gemm_bf16(x2, self.weight.view(self.cout, self.cin), out=y2, col_scale=self.scale,
                               col_shift=self.shift, relu=self.relu)
                 return y
+            if FUSE_RESIDUAL and self._residual_fusable(residual, y):
+                # y = relu(x W'^T + residual + shift) in ONE kernel: the folded-BN scale lives in the weights
+                # (W' = scale[:, None] * W), the residual tile is fetched by TMA into the epilogue's staging
+                # buffer (the addend path of the persistent GEMM) -- no separate scale/shift/add/ReLU pass
+                ops.gemm_bf16(x2, self._scaled_weight(), out=y2, col_shift=self.shift, relu=self.relu,
+                              add=residual.permute(0, 2, 3, 1).reshape(-1, self.cout))
+                return y
             ops.gemm_bf16(x2, self.weight.view(self.cout, self.cin), out=y2)
             return ops.scale_shift_act(y, self.scale, self.shift, residual, self.relu)
         if (self.k == 3 and residual is None and self.own_conv3 and self.stride in (1, 2)
@@ -103,6 +124,11 @@ class FoldedConv(nn.Module):
             return y
         y = F.conv2d(x, self.weight.permute(0, 3, 1, 2), None, self.stride, (self.k - 1) // 2, 1, self.groups)
         return ops.scale_shift_act(y, self.scale, self.shift, residual, self.relu)
+
+
+# EXPERIMENTAL until validated on a GPU (tests/test_experimental_gpu.py): EDL_TEACHER_FUSE_RES=1 folds the residual add
+# of every block's last 1x1 convolution into its GEMM epilogue (scale_shift_act was 0.63 ms of the 5.87 ms forward).
+FUSE_RESIDUAL = __import__("os").environ.get("EDL_TEACHER_FUSE_RES", "0") == "1"
 
 
 class ResNeXtBlock(nn.Module):

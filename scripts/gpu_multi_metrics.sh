@@ -10,6 +10,13 @@ timeout 600 $TR --master-port 29611 tools/bench_comm.py --sweep --exposed --out 
 timeout 600 $TR --master-port 29612 tools/bench_rescale.py --drop $(( N >= 4 ? 2 : 1 )) --out gpurun_out/rescale_${N}gpu.json > gpurun_out/rescale_${N}gpu.log 2>&1
 timeout 600 $TR --master-port 29613 examples/ctr/train.py --sweep --out gpurun_out/ctr_sweep_${N}gpu.json > gpurun_out/ctr_sweep_${N}gpu.log 2>&1
 timeout 300 $TR --master-port 29614 examples/ctr/train.py --model deepfm --steps 30 --vocab 1000001 --out gpurun_out/ctr_deepfm_${N}gpu.json > gpurun_out/ctr_deepfm_${N}gpu.log 2>&1
+# distill mode A/B: teacher residual fused into the GEMM epilogue (validate with tests/test_experimental_gpu.py first)
+for flags in "" "--teacher-fuse-res" "--teacher-fuse-res --pdl"; do
+  tag=$(echo "distill$flags" | tr -d ' -')
+  timeout 400 $TR --master-port 29615 bench.py --gpus $N --mode distill --steps 60 --warmup 8 $flags \
+    > gpurun_out/ab_${tag}_${N}gpu.json 2> gpurun_out/ab_${tag}_${N}gpu.err
+  echo "$tag: $(head -c 240 gpurun_out/ab_${tag}_${N}gpu.json)"
+done
 # launcher-level recovery time with real GPU trainers: pod A = first half of the GPUs, pod B = second half
 timeout 900 python tools/bench_elastic_launch.py --native-store --trainer resnet --gpus-per-pod $(( N / 2 )) \
   --out gpurun_out/elastic_launch_${N}gpu.json > gpurun_out/elastic_launch_${N}gpu.log 2>&1

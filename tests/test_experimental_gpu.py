@@ -202,3 +202,35 @@ def test_agreement_through_the_scalar_allgather_kernel():
     res = q.get(timeout=300)
     [p.join(60) for p in procs]
     assert res == "ok", res
+
+
+def test_teacher_residual_fused_into_the_gemm_epilogue(monkeypatch):
+    """EDL_TEACHER_FUSE_RES: relu(conv1x1 * scale + shift + residual) as one persistent-GEMM launch (scale folded into
+    the weights, residual tile by TMA) against the two-kernel path and against fp32 math."""
+    from edl_b200.models import resnext
+
+    torch.manual_seed(0)
+    conv = resnext.FoldedConv(256, 512, 1, relu=True).to(DEV)
+    conv.weight.data = (torch.randn_like(conv.weight.float()) * 0.05).to(torch.bfloat16)
+    conv.load_bn(torch.rand(512, device=DEV) + 0.5, torch.randn(512, device=DEV) * 0.1,
+                 torch.randn(512, device=DEV) * 0.1, torch.rand(512, device=DEV) + 0.5)
+    x = torch.randn(8, 256, 14, 14, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    res = torch.randn(8, 512, 14, 14, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    monkeypatch.setattr(resnext, "FUSE_RESIDUAL", False)
+    two = conv(x, residual=res)
+    monkeypatch.setattr(resnext, "FUSE_RESIDUAL", True)
+    ops.reset_launches()
+    one = conv(x, residual=res)
+    assert ops.launches() == 1
+    w = conv.weight.view(512, 256).float()
+    ref = torch.relu(torch.einsum("nchw,oc->nohw", x.float(), w) * conv.scale[None, :, None, None]
+                     + conv.shift[None, :, None, None] + res.float())
+    assert _rel(two, ref) < 1e-2 and _rel(one, ref) < 1e-2, (_rel(two, ref), _rel(one, ref))
+    # whole teacher: same logits either way
+    m = resnext.to_inference_dtype(resnext.ResNeXt_tiny(), torch.bfloat16, DEV).eval()
+    xi = torch.randn(4, 3, 64, 64, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    monkeypatch.setattr(resnext, "FUSE_RESIDUAL", False)
+    a = m(xi).float()
+    monkeypatch.setattr(resnext, "FUSE_RESIDUAL", True)
+    b = m(xi).float()
+    assert _rel(b, a) < 2e-2
