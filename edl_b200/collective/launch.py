@@ -23,6 +23,19 @@ def main(argv=None):
     pod = Pod().from_env(job_env)
     launcher = edl_launcher.Launcher(job_env=job_env, pod=pod, etcd=etcd, args=args)
     launcher.init()
+    try:
+        import signal
+
+        # SIGTERM = "this pod has to go" (scheduler, k8s): leave gracefully instead of vanishing (launcher.request_leave);
+        # a second SIGTERM, or SIGKILL after the grace period, still ends the process the hard way
+        def _on_term(signum, frame):
+            if launcher._leave:
+                raise SystemExit(128 + signum)
+            launcher.request_leave()
+
+        signal.signal(signal.SIGTERM, _on_term)
+    except ValueError:      # not the main thread (embedded use): no handler
+        pass
     ok = launcher.launch()
     etcd.close()
     return 0 if ok else 1

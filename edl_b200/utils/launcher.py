@@ -18,6 +18,8 @@ class Launcher:
         self._watcher = None
         self._procs = []
         self._cluster = None
+        self._leave = False         # SIGTERM / request_leave(): announce the departure, let the job re-plan first
+        self._leaving_since = None
         self.rescales = 0          # number of stage changes survived
         self.last_rescale_s = None  # wall seconds from "change seen" to "trainers restarted"
 
@@ -54,6 +56,10 @@ class Launcher:
                     return cur
                 time.sleep(min(1.0, constants.POLL_INTERVAL))
         raise exceptions.EdlBarrierError("barrier did not complete in {}s: {}".format(timeout, last_err))
+
+    def request_leave(self):
+        """Ask the pod to leave the job gracefully (called from the SIGTERM handler of collective/launch.py)."""
+        self._leave = True
 
     def _adopt(self, cluster):
         """Take this pod's record (rank, global trainer ranks) from the agreed cluster; False if evicted."""
@@ -99,7 +105,21 @@ class Launcher:
             if not alive:
                 logger.info("all trainers of pod %s finished", self._pod.id)
                 return True
-            if self._resource_register.is_stopped() or self._leader_register.is_stopped():
+            if self._leave and self._leaving_since is None:
+                # graceful departure (SIGTERM from the scheduler, k8s pod deletion with a grace period): give up the
+                # leadership and the resource key FIRST, keep the trainers alive.  The (new) leader publishes a stage
+                # without this pod; in-place trainers agree on the switch and the ones of this pod leave by
+                # themselves, restart-mode pods re-barrier -- nobody's collective is broken by a vanished peer.
+                self._leaving_since = time.time()
+                logger.info("pod %s is leaving: releasing leadership and resource registration", self._pod.id)
+                self._leader_register.stop()
+                self._resource_register.stop()
+            if self._leaving_since is not None:
+                if time.time() - self._leaving_since > constants.LEAVE_GRACE:
+                    logger.warning("the job did not re-plan within %.0fs; stopping trainers", constants.LEAVE_GRACE)
+                    train_process.terminate(self._procs)
+                    return True
+            elif self._resource_register.is_stopped() or self._leader_register.is_stopped():
                 logger.error("lost the store registration; stopping trainers")
                 train_process.terminate(self._procs)
                 return False

@@ -229,3 +229,47 @@ def test_hot_recovery_when_a_pod_dies_hard(kv_server, tmp_path):
         for p in (a, b):
             if p is not None and p.poll() is None:
                 os.killpg(os.getpgid(p.pid), 9)
+
+
+@pytest.mark.slow
+def test_sigterm_is_a_graceful_leave(kv_server, tmp_path):
+    """SIGTERM to a launcher (scheduler eviction, k8s pod deletion) = announce the departure first: the pod gives up its
+    registrations, the job re-plans without it, its trainers leave at the agreed step -- the survivor never sees a
+    broken collective (no hot recovery needed) and keeps its process."""
+    import signal
+
+    job = "leave_" + uuid.uuid4().hex[:6]
+    report, ckpt = str(tmp_path / "report"), str(tmp_path / "ckpt")
+
+    def epochs():
+        p = os.path.join(report, "epochs.jsonl")
+        return [json.loads(l) for l in open(p)] if os.path.exists(p) else []
+
+    def wait_world(w, timeout, min_new=3):
+        n0 = len(epochs())
+        deadline = time.time() + timeout
+        while time.time() < deadline:
+            e = epochs()
+            if len(e) >= n0 + min_new and all(x["world"] == w for x in e[-min_new:]):
+                return e
+            time.sleep(0.2)
+        raise AssertionError("world never became %d: %s" % (w, epochs()[-4:]))
+
+    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 170)
+    b = None
+    try:
+        pid_a = wait_world(1, 60)[-1]["pid"]
+        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 170)
+        wait_world(2, 90)
+        b.send_signal(signal.SIGTERM)                             # the launcher only; its trainer is left alone
+        e1 = wait_world(1, 60)
+        assert e1[-1]["pid"] == pid_a
+        assert b.wait(timeout=60) == 0
+        assert a.wait(timeout=120) == 0
+        worker = open(str(tmp_path / "logA" / "workerlog.0")).read()
+        assert "rescaled in place: world 2 -> 1" in worker and "collective failed" not in worker, worker[-2000:]
+        assert "is leaving" in open(str(tmp_path / "logB.launcher.log")).read()
+    finally:
+        for p in (a, b):
+            if p is not None and p.poll() is None:
+                os.killpg(os.getpgid(p.pid), 9)
