@@ -29,7 +29,8 @@ POLL_INTERVAL = _f("EDL_POLL_INTERVAL", 3)          # generator / watcher / lead
 BARRIER_TIMEOUT = _f("EDL_BARRIER_TIMEOUT", 600)
 RESCALE_BARRIER_TIMEOUT = _f("EDL_RESCALE_BARRIER_TIMEOUT", 60)
 KILL_GRACE = _f("EDL_KILL_GRACE", 3)
-LEAVE_GRACE = _f("EDL_LEAVE_GRACE", 25)           # s a SIGTERMed pod waits for the job to re-plan without it (k8s default grace: 30 s)
+# seconds a SIGTERMed pod waits for the job to re-plan without it (k8s default grace period: 30 s)
+LEAVE_GRACE = _f("EDL_LEAVE_GRACE", 25)
 INPLACE_ACK_TIMEOUT = _f("EDL_INPLACE_ACK_TIMEOUT", 60)   # s a launcher waits for its trainers to enter the new stage in place
 
 ALL_TABLES = [ETCD_POD_RESOURCE, ETCD_POD_RANK, ETCD_POD_STATUS, ETCD_JOB_STATUS, ETCD_TRAIN_STATUS,
