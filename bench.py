@@ -251,6 +251,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
+    if os.environ.get("EDL_FAKE_HOST_SPLIT"):  # A/B of the hierarchical all-reduce: ranks [0, k) and [k, N) play two hosts
+        os.environ["EDL_FAKE_HOST"] = "node%d" % (int(os.environ.get("RANK", "0")) // int(os.environ["EDL_FAKE_HOST_SPLIT"]))
     if args.pdl:
         os.environ["EDL_PDL"] = "1"            # read when the extension is loaded
     if args.own_wgrad3:

@@ -28,6 +28,27 @@ import torch.distributed as dist
 from .flat import FlatParams
 
 
+def _host_id() -> str:
+    """Identity of the NVSwitch domain a rank lives in: host name + boot id (containers of one machine share both)."""
+    import socket
+
+    boot = ""
+    try:
+        with open("/proc/sys/kernel/random/boot_id") as f:
+            boot = f.read().strip()
+    except OSError:
+        pass
+    return socket.gethostname() + ":" + boot
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 @dataclass
 class Bucket:
     dtype: torch.dtype
@@ -88,7 +109,7 @@ class ElasticDataParallel:
     def __init__(self, module: torch.nn.Module, group: Optional[dist.ProcessGroup] = None,
                  bucket_cap_mb: float = 16.0, overlap: bool = True, comm_blocks: int = 32,
                  algo: str = "auto", timeout_s: float = 60.0, average: bool = True,
-                 check_finite: bool = False, track_sqnorm: bool = False):
+                 check_finite: bool = False, track_sqnorm: bool = False, hierarchical: str = "auto"):
         # one engine per module: a second engine on the same parameters would leave the first one's
         # autograd hooks installed (they would fire, and launch reductions, during the new engine's backward)
         old = getattr(module, "_edl_dp_engine", None)
@@ -111,6 +132,9 @@ class ElasticDataParallel:
             self.found_inf = torch.zeros(1, dtype=torch.int32, device=self.device)
         if track_sqnorm and self.device.type == "cuda":
             self.sqnorm = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # "auto": two-level reduction as soon as the ranks span more than one host (NVSwitch domain); "off": never
+        # (one flat group; across hosts that means the library path); the reference's use_hierarchical_allreduce knob
+        self.hierarchical = os.environ.get("EDL_HIERARCHICAL_ALLREDUCE", hierarchical)
         self.overlap_wgrad = os.environ.get("EDL_OVERLAP_WGRAD", "1") == "1"
         self.enabled = True     # False: gradients stay local (DGC exchanges them itself)
         self._bind_group(group)
@@ -128,7 +152,9 @@ class ElasticDataParallel:
         else:
             self.world, self.rank = 1, 0
         self.backend = dist.get_backend(group) if self.world > 1 else "none"
-        self.use_symm = (self.world > 1 and self.device.type == "cuda"
+        self._plan_hierarchy(group)
+        symm_world = self.local_world if self.hier else self.world
+        self.use_symm = (symm_world > 1 and self.device.type == "cuda"
                          and self.algo_pref != "nccl")
         self.pool = None
         if self.use_symm:
@@ -139,7 +165,7 @@ class ElasticDataParallel:
                 if p.requires_grad:
                     need += (p.numel() + 256) * p.element_size()
             need += 4 << 20
-            self.pool = SymmetricPool(need, group=group, device=self.device)
+            self.pool = SymmetricPool(need, group=self.local_group if self.hier else group, device=self.device)
         if self.device.type == "cuda" and getattr(self, "comm_stream", None) is None:
             # all-reduce kernels: high priority (few CTAs, on the critical path of the optimizer step);
             # weight-gradient kernels: LOW priority -- they only have to finish before their bucket is
@@ -148,6 +174,46 @@ class ElasticDataParallel:
             self.wgrad_stream = torch.cuda.Stream(device=self.device, priority=0)
             self._main_stream = None
             self._comm_used = False
+
+    def _plan_hierarchy(self, group):
+        """Peer memory only reaches the GPUs of one NVSwitch domain.  When the ranks span several hosts the
+        reduction becomes two-level (the reference's ``use_hierarchical_allreduce``, example/distill/resnet/
+        train_with_fleet.py:90-91,360-362): our kernels inside a host, the library collective across hosts on 1/L of
+        every bucket per rank.  Hosts must hold the same number of ranks; otherwise one flat library group."""
+        self.hier, self.local_group, self.cross_group = False, group, None
+        self.local_world, self.local_rank = self.world, self.rank
+        if self.world <= 1 or self.hierarchical == "off":
+            return
+        fake = os.environ.get("EDL_FAKE_HOST")
+        if not fake and os.environ.get("LOCAL_WORLD_SIZE") == str(self.world) and group is None:
+            return                       # torchrun started every rank of the job on this host: nothing to find out
+        me = fake or _host_id()
+        hosts = [None] * self.world
+        dist.all_gather_object(hosts, me, group=group)
+        if len(set(hosts)) <= 1:
+            return
+        nodes: Dict[str, List[int]] = {}
+        for r, h in enumerate(hosts):
+            nodes.setdefault(h, []).append(r)
+        sizes = {len(v) for v in nodes.values()}
+        if len(sizes) != 1:
+            self.algo_pref = "nccl"          # uneven hosts: flat library all-reduce
+            return
+        to_global = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+        L = sizes.pop()
+        node_lists = list(nodes.values())
+        # every member creates every subgroup in the same order (local synchronisation: ranks outside `group`,
+        # e.g. the teachers of a distill job, do not take part)
+        for members in node_lists:
+            g = dist.new_group(ranks=[to_global(r) for r in members], use_local_synchronization=True) \
+                if self.rank in members else None
+            if g is not None:
+                self.local_group, self.local_rank = g, members.index(self.rank)
+        for l in range(L):
+            members = [n[l] for n in node_lists]
+            if self.rank in members:
+                self.cross_group = dist.new_group(ranks=[to_global(r) for r in members], use_local_synchronization=True)
+        self.local_world, self.hier = L, True
 
     def _grad_alloc(self, numel, dtype, device):
         sl = self.pool.alloc(numel, dtype)
@@ -160,7 +226,7 @@ class ElasticDataParallel:
         has_mc = self.pool.has_multicast if self.pool is not None else False
         for b in self.buckets:
             esz = 2 if b.dtype in (torch.bfloat16, torch.float16) else 4
-            b.algo = choose_algo(b.numel * esz, self.world, has_mc, self.algo_pref) \
+            b.algo = choose_algo(b.numel * esz, self.local_world if self.hier else self.world, has_mc, self.algo_pref) \
                 if self.use_symm else ("nccl" if self.world > 1 else "none")
         self.bucket_of = {}
         for bi, b in enumerate(self.buckets):
@@ -216,6 +282,8 @@ class ElasticDataParallel:
         b.launched = True
         g = self.flat.groups[b.dtype]
         scale = 1.0 / self.world if self.average else 1.0
+        if self.hier:
+            return self._launch_hier(b, g, scale)
         if b.algo in ("twoshot", "multimem"):
             from ..ops import native, count_launch
 
@@ -248,6 +316,60 @@ class ElasticDataParallel:
                 if self.average:
                     view.mul_(scale)
 
+    def _local_allreduce(self, b: Bucket, g, scale: float, final: bool):
+        """Sum (x scale) of the bucket over the ranks of this host: our kernel over peer memory, or the library on CPU."""
+        view = g.grad[b.start:b.start + b.numel]
+        if self.local_world <= 1:
+            if scale != 1.0:
+                view.mul_(scale)
+            return
+        if self.use_symm:
+            from ..ops import native, count_launch
+
+            sl = self.slices[b.dtype]
+            off = b.start * g.grad.element_size()
+            native().allreduce_twoshot(
+                [p + off for p in sl.data_ptrs], sl.sig_ptrs, (sl.mc_ptr + off) if sl.mc_ptr else 0,
+                self.local_rank, g.grad, b.numel, scale, self.found_inf if final else None,
+                self.sqnorm if final else None, b.algo == "multimem", self.comm_blocks, self.timeout_s)
+            count_launch()
+            self.comm_launches += 1
+        else:
+            dist.all_reduce(view, group=self.local_group)
+            if scale != 1.0:
+                view.mul_(scale)
+
+    def _launch_hier(self, b: Bucket, g, scale: float):
+        """Two-level all-reduce of one bucket: (1) sum inside the host, (2) rank l of every host all-reduces slice l
+        across hosts (1/L of the bucket per NIC), (3) the slices are put back together inside the host by a second
+        local sum over buffers that are zero outside the owned slice, with the 1/world scale and the finite check."""
+        L = self.local_world
+        per = -(-b.numel // L)
+        per = -(-per // 8) * 8                                  # slices stay 16-byte aligned
+        lo = min(b.numel, self.local_rank * per)
+        hi = min(b.numel, lo + per)
+        view = g.grad[b.start:b.start + b.numel]
+        cuda = self.device.type == "cuda"
+        if cuda:
+            for st in {torch.cuda.current_stream(self.device), self._main_stream,
+                       self.wgrad_stream if self.overlap_wgrad else None}:
+                if st is not None and st != self.comm_stream:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    self.comm_stream.wait_event(ev)
+            self._comm_used = True
+        ctx = torch.cuda.stream(self.comm_stream) if cuda else _NullCtx()
+        with ctx:
+            self._local_allreduce(b, g, 1.0, final=False)
+            if hi > lo:
+                dist.all_reduce(view[lo:hi], group=self.cross_group)
+            if L > 1:
+                if lo > 0:
+                    view[:lo].zero_()
+                if hi < b.numel:
+                    view[hi:].zero_()
+            self._local_allreduce(b, g, scale, final=True)
+
     def finish(self):
         """Call after ``backward()``: flush buckets whose parameters received no gradient, then make
         the compute stream wait for the communication stream."""
@@ -255,7 +377,7 @@ class ElasticDataParallel:
             b.pending = 0
         self._launch_ready()
         if self.device.type == "cuda" and (self.world > 1 or self.overlap_wgrad):
-            if self.use_symm or self.overlap_wgrad:
+            if self.use_symm or self.overlap_wgrad or self.hier:
                 cur = torch.cuda.current_stream(self.device)
                 # only streams that took part in this step (a stream without forked work is not part
                 # of a CUDA-graph capture and must not be joined into it)
@@ -316,7 +438,7 @@ class ElasticDataParallel:
         seconds later instead of a hung process -- the trigger for ``ElasticContext.recover()`` on GPUs."""
         if self.world <= 1:
             return float(flag), 0
-        if self.use_symm and self.slices:
+        if self.use_symm and self.slices and not self.hier:
             from ..ops import native, count_launch
 
             sl = max(self.slices.values(), key=lambda x: x.tensor.numel())
@@ -354,7 +476,7 @@ class ElasticDataParallel:
             return
         for g in self.flat.groups.values():
             src = g.master if g.master is not None else g.param
-            if self.use_symm:
+            if self.use_symm and not self.hier:
                 self._broadcast_tensor(src, root)
                 if g.master is not None:
                     g.param.copy_(g.master.to(g.param.dtype))
@@ -369,7 +491,7 @@ class ElasticDataParallel:
         """Broadcast any contiguous device tensor (e.g. optimizer state) from ``root`` of the current group."""
         if self.world <= 1:
             return
-        if self.use_symm:
+        if self.use_symm and not self.hier:
             self._broadcast_tensor(t, root)
         else:
             dist.broadcast(t, src=dist.get_global_rank(self.group, root) if self.group else root, group=self.group)

@@ -20,6 +20,9 @@ done
 # launcher-level recovery time with real GPU trainers: pod A = first half of the GPUs, pod B = second half
 timeout 900 python tools/bench_elastic_launch.py --native-store --trainer resnet --gpus-per-pod $(( N / 2 )) \
   --out gpurun_out/elastic_launch_${N}gpu.json > gpurun_out/elastic_launch_${N}gpu.log 2>&1
-EDL_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -q -k agreement > gpurun_out/agree_test.log 2>&1
+EDL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_experimental_gpu.py -q -k "agreement or hierarchical" > gpurun_out/agree_test.log 2>&1
+# hierarchical all-reduce overhead: the same box pretending to be 2 hosts (EDL_FAKE_HOST is read per rank)
+EDL_FAKE_HOST_SPLIT=$(( N / 2 )) timeout 400 $TR --master-port 29616 bench.py --gpus $N --steps 60 --warmup 5 \
+  > gpurun_out/bench_hier_${N}gpu.json 2> gpurun_out/bench_hier_${N}gpu.err
 tail -n 3 gpurun_out/elastic_launch_${N}gpu.log gpurun_out/agree_test.log
 tail -n 3 gpurun_out/comm_${N}gpu.log gpurun_out/rescale_${N}gpu.log gpurun_out/ctr_sweep_${N}gpu.log gpurun_out/ctr_deepfm_${N}gpu.log

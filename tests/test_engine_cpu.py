@@ -306,3 +306,57 @@ def test_step_pipelined_cpu_fallback_matches_step():
         return [float(tr.step(x, t)) for _ in range(3)]
 
     assert run(True) == run(False)
+
+
+def _hier_worker(rank, world, port, q, fake_hosts):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if fake_hosts:
+        os.environ["EDL_FAKE_HOST"] = "node%d" % (rank // 2)       # 2 "hosts" x 2 ranks
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(37, 301), torch.nn.Tanh(), torch.nn.Linear(301, 53), torch.nn.Tanh(),
+                            torch.nn.Linear(53, 8)).double()          # odd sizes: slices that do not divide evenly
+    dp = ElasticDataParallel(m, bucket_cap_mb=0.01)
+    assert dp.hier == bool(fake_hosts) and (not fake_hosts or (dp.local_world == 2 and dp.local_rank == rank % 2))
+    assert len(dp.buckets) >= 2
+    opt = ops.FlatSGDMomentum(dp.flat, lr=0.05)
+    torch.manual_seed(100)
+    xs = torch.randn(8, 37).double()
+    ts = torch.softmax(torch.randn(8, 8), -1).double()
+    x, t = xs[rank * 2:(rank + 1) * 2], ts[rank * 2:(rank + 1) * 2]
+    for _ in range(3):
+        dp.zero_grad()
+        loss = ops.soft_cross_entropy(dp(x), t)
+        loss.backward()
+        dp.finish()
+        opt.step()
+    assert dp.agree(1.0 if rank == 3 else 0.0) == (1.0, 0)
+    dp.broadcast_parameters(0)
+    flat = torch.cat([(g.master if g.master is not None else g.param).flatten().double() for g in dp.flat.groups.values()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    if rank == 0:
+        q.put((float(max((gathered[0] - g).abs().max() for g in gathered)), flat.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_hierarchical_allreduce_matches_the_flat_one():
+    """Ranks on two (fake) hosts: sum inside the host, 1/L slice per rank across hosts, second local sum -- same
+    parameters as the flat all-reduce after three optimizer steps (float64: summation order is the only difference)."""
+    ctx = mp.get_context("spawn")
+    results = []
+    for fake in (False, True):
+        q = ctx.Queue()
+        port = 29500 + (os.getpid() + 7 + int(fake)) % 2000
+        procs = [ctx.Process(target=_hier_worker, args=(r, 4, port, q, fake)) for r in range(4)]
+        for p in procs:
+            p.start()
+        spread, flat = q.get(timeout=90)
+        for p in procs:
+            p.join(60)
+            assert p.exitcode == 0
+        assert spread == 0.0                     # every rank holds identical parameters
+        results.append(flat)
+    assert torch.allclose(results[0], results[1], rtol=1e-9, atol=1e-12)

@@ -234,3 +234,61 @@ def test_teacher_residual_fused_into_the_gemm_epilogue(monkeypatch):
     monkeypatch.setattr(resnext, "FUSE_RESIDUAL", True)
     b = m(xi).float()
     assert _rel(b, a) < 2e-2
+
+
+def _hier_gpu_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    try:
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        os.environ["EDL_FAKE_HOST"] = "node%d" % (rank // 2)              # 2 fake hosts x 2 GPUs on one box
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        from edl_b200.models import ResNetVd, to_train_dtype
+        from edl_b200.trainer import StudentTrainer
+
+        torch.manual_seed(0)
+        m = to_train_dtype(ResNetVd(18, class_dim=16, width_mult=0.25), torch.bfloat16, dev).train()
+        for use_graph in (False, True):
+            tr = StudentTrainer(m, 8, image_shape=(3, 32, 32), num_classes=16, lr=0.05, use_graph=use_graph, bucket_cap_mb=0.25)
+            assert tr.dp.hier and tr.dp.local_world == 2 and tr.dp.use_symm
+            torch.manual_seed(100 + rank)
+            x = torch.randn(8, 3, 32, 32).bfloat16().contiguous(memory_format=torch.channels_last).pin_memory()
+            t = torch.softmax(torch.randn(8, 16), -1).bfloat16().pin_memory()
+            for _ in range(4):
+                tr.step(x, t)
+            torch.cuda.synchronize()
+            flat = torch.cat([g.param.flatten().float() for g in tr.dp.flat.groups.values()])
+            outs = [torch.empty_like(flat) for _ in range(world)]
+            dist.all_gather(outs, flat)
+            assert all(torch.equal(outs[0], o) for o in outs), "ranks diverged (graph=%s)" % use_graph
+            assert torch.isfinite(flat).all() and tr.dp.check_comm_error() == 0
+        if rank == 0:
+            q.put("ok")
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+
+        q.put("rank %d: %s\n%s" % (rank, e, traceback.format_exc()))
+        raise
+
+
+@pytest.mark.multigpu
+def test_hierarchical_allreduce_on_fake_hosts():
+    """Two-level gradient reduction (NVSwitch kernels inside a 'host', NCCL on 1/L slices across): 4 GPUs of one box
+    pretending to be 2 hosts; replicas must stay bit-identical, eagerly and inside the step graph."""
+    import torch.multiprocessing as mp
+
+    world = 4
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs 4 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + os.getpid() % 1000
+    procs = [ctx.Process(target=_hier_gpu_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = q.get(timeout=400)
+    [p.join(60) for p in procs]
+    assert res == "ok", res
