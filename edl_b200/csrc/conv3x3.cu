@@ -346,6 +346,8 @@ const char* conv3x3_bf16(const Conv3x3Args& a, cudaStream_t stream) {
   if (!conv3x3_supported(a.N, a.H, a.W, a.Cin, a.Cout, a.dgrad, a.groups)) return "conv3x3: unsupported shape";
   if (!persistent_gemm_enabled() && (a.groups > 1 || a.col_scale != nullptr || a.col_shift != nullptr || a.relu))
     return "conv3x3: groups / inference epilogue need the persistent kernel";
+  if (a.stride != 1 && (a.stride != 2 || a.dgrad || !persistent_gemm_enabled()))
+    return "conv3x3: stride 2 is implemented for fprop on the persistent kernel only";
   if (a.device >= 0) {
     cudaError_t e = cudaSetDevice(a.device);   // tensor-map encoding needs a bound context (see gemm.cu)
     if (e != cudaSuccess) return cudaGetErrorString(e);

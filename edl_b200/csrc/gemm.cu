@@ -455,11 +455,20 @@ const char* encode_tmap_bf16(void* out, const void* ptr, int rank, const uint64_
 
 const char* encode_tmap(void* out, const void* ptr, int rank, const uint64_t* dims,
                         const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes) {
+  return encode_tmap_strided(out, ptr, rank, dims, strides_bytes, box, nullptr, elem_bytes);
+}
+
+// elem_strides (optional): traversal stride per dimension.  With stride t the unit loads ceil(box / t) elements
+// along that dimension (every t-th one), i.e. box[i] = n * t selects n elements -- how a stride-2 convolution reads
+// its input without an im2col or a subsampling pass.
+const char* encode_tmap_strided(void* out, const void* ptr, int rank, const uint64_t* dims,
+                                const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                                int elem_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return "cuTensorMapEncodeTiled entry point not found";
   cuuint64_t d[5], st[4];
   cuuint32_t b[5], es[5];
-  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = elem_strides != nullptr ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
   CUresult r = fn(reinterpret_cast<CUtensorMap*>(out),
                   elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,

@@ -76,6 +76,8 @@ struct Conv3x3Args {
   bool relu = false;
   int groups = 1;              // grouped fprop: Cin/groups % 64 == 0, Cout/groups == 64 or % 128 == 0; Wt is
                                // [Cout, 3, 3, Cin/groups]
+  int stride = 1;              // 1 or 2 (fprop on the persistent kernel only).  N, H, W are the OUTPUT geometry; with
+                               // stride 2 the input X is [N, 2H, 2W, Cin] and is sampled by the TMA traversal stride
   int device = -1;
 };
 bool conv3x3_supported(int N, int H, int W, int Cin, int Cout, bool dgrad, int groups = 1);
@@ -113,6 +115,9 @@ const char* encode_tmap_bf16(void* out, const void* ptr, int rank, const uint64_
                              const uint64_t* strides_bytes, const uint32_t* box);
 const char* encode_tmap(void* out, const void* ptr, int rank, const uint64_t* dims,
                         const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes);
+const char* encode_tmap_strided(void* out, const void* ptr, int rank, const uint64_t* dims,
+                                const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                                int elem_bytes);
 
 // FP8 (e4m3) inference GEMM (gemm_fp8.cu): D[M,N] bf16 = relu?((A[M,K] * B[N,K]^T) * col_scale[n] + col_shift[n])
 // A, B e4m3 bytes, K-major; col_scale carries act_scale * weight_scale[n] (* folded BN scale).

@@ -245,6 +245,38 @@ void conv3x3_wgrad(const Tensor& x, const Tensor& dy, Tensor& dw, Tensor& ws, Te
   TORCH_CHECK(err == nullptr, "edl conv3x3_wgrad failed: ", err);
 }
 
+// 3x3 / pad 1 / STRIDE 2 fprop (dense or grouped) on the persistent kernel: x [N, Cin, 2H, 2W], y [N, Cout, H, W]
+// channels_last.  Training use: col_stats (BN statistics of y); inference use: col_scale / col_shift / relu.
+void conv3x3_s2(const Tensor& x, const Tensor& w, Tensor& y, const c10::optional<Tensor>& col_stats,
+                const c10::optional<Tensor>& col_scale, const c10::optional<Tensor>& col_shift, bool relu,
+                int64_t groups) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 4 && y.dim() == 4 && w.dim() == 4);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && y.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast) && y.is_contiguous(at::MemoryFormat::ChannelsLast));
+  TORCH_CHECK(w.is_contiguous() && w.size(1) == 3 && w.size(2) == 3);
+  edl::Conv3x3Args a;
+  a.X = x.data_ptr();
+  a.Wt = w.data_ptr();
+  a.Y = y.data_ptr();
+  a.N = y.size(0);
+  a.H = y.size(2);
+  a.W = y.size(3);
+  a.Cin = x.size(1);
+  a.Cout = w.size(0);
+  a.groups = (int)groups;
+  a.stride = 2;
+  TORCH_CHECK(x.size(0) == a.N && x.size(2) == 2 * a.H && x.size(3) == 2 * a.W, "stride-2 conv needs an even input: x is 2H x 2W");
+  TORCH_CHECK(w.size(3) * groups == a.Cin && y.size(1) == a.Cout);
+  a.col_stats = optp<float>(col_stats);
+  a.col_scale = optp<float>(col_scale);
+  a.col_shift = optp<float>(col_shift);
+  a.relu = relu;
+  a.device = x.device().index();
+  c10::cuda::CUDAGuard guard(x.device());
+  const char* err = edl::conv3x3_bf16(a, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(err == nullptr, "edl conv3x3_s2 failed: ", err);
+}
+
 std::vector<int64_t> conv3x3_wgrad_plan(int64_t n, int64_t h, int64_t w) {
   int bh = 0, nb = 0, kb = 0;
   edl::conv3x3_wgrad_plan((int)n, (int)h, (int)w, &bh, &nb, &kb);
@@ -298,4 +330,5 @@ void register_gemm_bindings(pybind11::module_& m) {
   m.def("conv3x3_wgrad_tiles", &edl::conv3x3_wgrad_tiles);
   m.def("conv3x3_wgrad_kblocks", &edl::conv3x3_wgrad_kblocks);
   m.def("conv3x3_wgrad_plan", &conv3x3_wgrad_plan);
+  m.def("conv3x3_s2", &conv3x3_s2);
 }

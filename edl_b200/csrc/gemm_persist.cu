@@ -59,6 +59,7 @@ struct PersistParams {
   // conv view (modes 2, 3)
   int n_img, H, W, kc_blocks, c_in_w, BH, BN, tiles_h;
   int cin_g, cout_g;              // grouped fprop: channels per group (cout_g == N for a dense conv)
+  int stride;                     // conv fprop: 1, or 2 (input rows 2*h + r - 1; the columns come from the tensor map)
 };
 
 template <int BLOCK_N, int STAGES, bool BNR = false>
@@ -227,7 +228,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int dw = kDgrad ? 1 - sft : sft - 1;
             // grouped fprop: the N tile lies in one group; its input channels start at group * cin_g
             const int cbase_in = (MODE == 2) ? (n0 / p.cout_g) * p.cin_g : 0;
-            ptx::tma_load_4d(sa, &tmA, &full_bar[s], cbase_in + kc * kBlockK, dw, h0 + dh, img0);
+            ptx::tma_load_4d(sa, &tmA, &full_bar[s], cbase_in + kc * kBlockK, dw, h0 * p.stride + dh, img0);
             if (!kBMN) {
               ptx::tma_load_2d(sb, &tmB, &full_bar[s], tap * p.c_in_w + kc * kBlockK, n0);
             } else {
@@ -669,11 +670,16 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
   const bool n64 = cout_g <= 64;
   const int bn = n64 ? 64 : 128;
   alignas(64) CUtensorMap tmX, tmW, tmY;
+  const int sd = a.stride == 2 ? 2 : 1;
+  if (sd == 2 && (dg || 2 * a.W > 256 || 2 * BH > 256)) return "conv3x3 stride 2: fprop only, output width <= 128";
   {
-    const uint64_t dims[4] = {(uint64_t)cx, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
-    const uint64_t st[3] = {(uint64_t)cx * 2, (uint64_t)a.W * cx * 2, (uint64_t)a.H * a.W * cx * 2};
-    const uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)BH, (uint32_t)BN};
-    if (const char* e = encode_tmap_bf16(&tmX, a.X, 4, dims, st, box)) return e;
+    // stride 2: the input is [N, 2H, 2W, C]; a box that spans 2W x 2BH elements with traversal stride 2 in w and h
+    // delivers the W x BH pixels a filter tap needs, starting at column s - 1 and row 2*h0 + r - 1
+    const uint64_t dims[4] = {(uint64_t)cx, (uint64_t)a.W * sd, (uint64_t)a.H * sd, (uint64_t)a.N};
+    const uint64_t st[3] = {(uint64_t)cx * 2, (uint64_t)a.W * sd * cx * 2, (uint64_t)a.H * sd * a.W * sd * cx * 2};
+    const uint32_t box[4] = {64, (uint32_t)(a.W * sd), (uint32_t)(BH * sd), (uint32_t)BN};
+    const uint32_t es[4] = {1, (uint32_t)sd, (uint32_t)sd, 1};
+    if (const char* e = encode_tmap_strided(&tmX, a.X, 4, dims, st, box, es, 2)) return e;
   }
   {
     const uint64_t dims[4] = {(uint64_t)cy, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
@@ -696,6 +702,7 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
   p.relu = (!dg && a.relu) ? 1 : 0;
   p.cin_g = cin_g; p.cout_g = cout_g;
   p.n_img = a.N; p.H = a.H; p.W = a.W; p.c_in_w = w_cin; p.BH = BH; p.BN = BN; p.tiles_h = tiles_h;
+  p.stride = sd;
   if (dg && a.bn.x != nullptr) {
     alignas(64) CUtensorMap tmBx, tmBy;
     const uint64_t dims[4] = {(uint64_t)cy, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};

@@ -58,6 +58,14 @@ class ConvBNAct(nn.Module):
                 stats = self.fwd_stats if self.fwd_stats is not None else torch.zeros(
                     2 * self.cout, device=x.device, dtype=torch.float32)
             return ops.conv3x3(x, self.weight, stats), stats
+        if (self.k == 3 and self.stride == 2 and self.groups == 1 and self.impl != "cudnn" and self.own_conv3
+                and ops.gemm.CONV3_S2 and ops.conv3x3_s2_supported(x, self.weight)):
+            # experimental (EDL_CONV3_S2=1): stride-2 fprop on the tcgen05 kernel, statistics in its epilogue
+            stats = None
+            if want_stats:
+                stats = self.fwd_stats if self.fwd_stats is not None else torch.zeros(
+                    2 * self.cout, device=x.device, dtype=torch.float32)
+            return ops.conv3x3_s2(x, self.weight, stats), stats
         if self.split_backward and torch.is_grad_enabled() and self.weight.requires_grad:
             # library conv whose wgrad half runs on the side stream (ops/gemm.py:_ConvLibFn)
             return ops.conv_lib(x, self.weight, self.stride, (self.k - 1) // 2, self.groups), None

@@ -112,6 +112,10 @@ class FoldedConv(nn.Module):
                 return y
             ops.gemm_bf16(x2, self.weight.view(self.cout, self.cin), out=y2)
             return ops.scale_shift_act(y, self.scale, self.shift, residual, self.relu)
+        if (self.k == 3 and residual is None and self.own_conv3 and self.stride == 2 and ops.gemm.CONV3_S2
+                and ops.conv3x3_s2_supported(x, self.weight, self.groups)):
+            # experimental (EDL_CONV3_S2=1): true stride-2 kernel, a quarter of the MMAs of the path below
+            return ops.conv3x3_s2_infer(x, self.weight, self.scale, self.shift, self.relu, self.groups)
         if (self.k == 3 and residual is None and self.own_conv3 and self.stride in (1, 2)
                 and ops.conv3x3_infer_supported(x, self.weight, self.groups)):
             # dense or grouped 3x3 on the persistent tcgen05 kernel, folded BN + ReLU in its epilogue

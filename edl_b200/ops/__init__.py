@@ -59,7 +59,8 @@ from .loss import soft_cross_entropy, topk_accuracy  # noqa: E402
 from .pool import max_pool_3x3_s2, avg_pool_2x2, global_avg_pool  # noqa: E402
 from .optim import FlatSGDMomentum, FlatAdam  # noqa: E402
 from .gemm import (gemm_bf16, linear_bf16, conv1x1, conv_lib, conv3x3, conv3x3_supported, conv3x3_infer,  # noqa: E402
-                   conv3x3_infer_supported, conv3x3_wgrad, conv3x3_wgrad_supported)
+                   conv3x3_infer_supported, conv3x3_wgrad, conv3x3_wgrad_supported, conv3x3_s2, conv3x3_s2_infer,
+                   conv3x3_s2_supported)
 from .misc import rope, rope_tables, embedding_bag_mean, normalize_u8, DynamicLossScaler  # noqa: E402
 
 __all__ = [
@@ -69,6 +70,6 @@ __all__ = [
     "max_pool_3x3_s2", "avg_pool_2x2", "global_avg_pool",
     "FlatSGDMomentum", "FlatAdam", "gemm_bf16", "linear_bf16", "conv1x1", "conv_lib", "conv3x3",
     "conv3x3_supported", "conv3x3_infer", "conv3x3_infer_supported",
-    "conv3x3_wgrad", "conv3x3_wgrad_supported",
+    "conv3x3_wgrad", "conv3x3_wgrad_supported", "conv3x3_s2", "conv3x3_s2_infer", "conv3x3_s2_supported",
     "rope", "rope_tables", "embedding_bag_mean", "normalize_u8", "DynamicLossScaler", "set_fused_bn", "drop_bn_hook",
 ]

@@ -490,6 +490,67 @@ def conv3x3(x, weight_krsc, stats: Optional[torch.Tensor] = None):
     return _Conv3x3Fn.apply(x, weight_krsc, stats, sink, ready, getattr(x, "_edl_bn_hook", None))
 
 
+# EXPERIMENTAL until validated on a GPU: EDL_CONV3_S2=1 runs 3x3 / pad 1 / STRIDE 2 forward convolutions (student:
+# first block of stages 2-4; teacher: the grouped ones, today "stride 1 then subsample" = 4x the MMA work) on the
+# persistent tcgen05 kernel; the input is sampled by the TMA traversal stride (csrc/gemm_persist.cu).
+CONV3_S2 = __import__("os").environ.get("EDL_CONV3_S2", "0") == "1"
+
+
+def conv3x3_s2_supported(x, weight_krsc, groups=1) -> bool:
+    from . import native
+
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and weight_krsc.dtype == torch.bfloat16 and x.dim() == 4):
+        return False
+    n, c, h, w = x.shape
+    cout, kh, kw, cin_g = weight_krsc.shape
+    return (kh == 3 and kw == 3 and cin_g * groups == c and h % 2 == 0 and w % 2 == 0 and w // 2 <= 128
+            and native().persistent_gemm_enabled()
+            and native().conv3x3_supported(n, h // 2, w // 2, c, cout, False, groups))
+
+
+def _conv3x3_s2_launch(x, weight_krsc, stats, scale, shift, relu, groups):
+    from . import native, count_launch
+
+    x = _cl(x)
+    n, _, h, w = x.shape
+    y = torch.empty((n, weight_krsc.shape[0], h // 2, w // 2), device=x.device, dtype=x.dtype,
+                    memory_format=torch.channels_last)
+    native().conv3x3_s2(x, weight_krsc, y, stats, scale, shift, relu, groups)
+    count_launch()
+    return y
+
+
+@torch.no_grad()
+def conv3x3_s2_infer(x, weight_krsc, scale=None, shift=None, relu=False, groups=1):
+    """Inference 3x3 / pad 1 / stride 2 convolution (dense or grouped) with the folded-BN epilogue."""
+    return _conv3x3_s2_launch(x, weight_krsc, None, scale, shift, relu, groups)
+
+
+class _Conv3x3S2Fn(torch.autograd.Function):
+    """Training form: forward on the tcgen05 kernel (BN statistics in its epilogue); the backward of the three
+    stride-2 layers stays on the library kernels (dgrad on the critical path, wgrad on the side stream)."""
+
+    @staticmethod
+    def forward(ctx, x, w, stats, sink, ready):
+        x = _cl(x)
+        y = _conv3x3_s2_launch(x, w, stats, None, None, False, 1)
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (2, 1, 1)
+        ctx.sink, ctx.ready = sink, ready
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx, dw = _ConvLibFn.backward(ctx, _cl(dy))[:2]
+        return dx, dw, None, None, None
+
+
+def conv3x3_s2(x, weight_krsc, stats: Optional[torch.Tensor] = None):
+    sink = getattr(weight_krsc, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
+    ready = getattr(weight_krsc, "_edl_grad_ready", None) if sink is not None else None
+    return _Conv3x3S2Fn.apply(x, weight_krsc, stats, sink, ready)
+
+
 def conv3x3_infer_supported(x, weight_krsc, groups=1) -> bool:
     from . import native
 

@@ -11,7 +11,7 @@ timeout 600 $TR --master-port 29612 tools/bench_rescale.py --drop $(( N >= 4 ? 2
 timeout 600 $TR --master-port 29613 examples/ctr/train.py --sweep --out gpurun_out/ctr_sweep_${N}gpu.json > gpurun_out/ctr_sweep_${N}gpu.log 2>&1
 timeout 300 $TR --master-port 29614 examples/ctr/train.py --model deepfm --steps 30 --vocab 1000001 --out gpurun_out/ctr_deepfm_${N}gpu.json > gpurun_out/ctr_deepfm_${N}gpu.log 2>&1
 # distill mode A/B: teacher residual fused into the GEMM epilogue (validate with tests/test_experimental_gpu.py first)
-for flags in "" "--teacher-fuse-res" "--teacher-fuse-res --pdl"; do
+for flags in "" "--teacher-fuse-res" "--teacher-fuse-res --conv3-s2" "--teacher-fuse-res --conv3-s2 --pdl"; do
   tag=$(echo "distill$flags" | tr -d ' -')
   timeout 400 $TR --master-port 29615 bench.py --gpus $N --mode distill --steps 60 --warmup 8 $flags \
     > gpurun_out/ab_${tag}_${N}gpu.json 2> gpurun_out/ab_${tag}_${N}gpu.err

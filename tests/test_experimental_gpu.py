@@ -292,3 +292,34 @@ def test_hierarchical_allreduce_on_fake_hosts():
     res = q.get(timeout=400)
     [p.join(60) for p in procs]
     assert res == "ok", res
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w,groups", [(4, 128, 128, 56, 56, 1), (4, 256, 256, 28, 28, 1), (8, 512, 512, 14, 14, 1),
+                                                   (2, 64, 128, 12, 20, 1), (2, 512, 512, 28, 28, 8), (2, 256, 256, 16, 16, 4)])
+def test_conv3x3_stride2_fprop(n, cin, cout, h, w, groups):
+    """3x3 / pad 1 / stride 2 forward on the persistent kernel (input sampled by the TMA traversal stride): training form
+    with BN statistics, inference form with folded BN + ReLU, dense and grouped."""
+    torch.manual_seed(0)
+    x = torch.randn(n, cin, h, w, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, 3, 3, cin // groups, device=DEV) * 0.05).bfloat16()
+    if not ops.conv3x3_s2_supported(x, wt, groups):
+        pytest.skip("shape not supported")
+    ref = F.conv2d(x.float(), wt.permute(0, 3, 1, 2).float(), None, 2, 1, 1, groups)
+    scale = torch.rand(cout, device=DEV) + 0.5
+    shift = torch.randn(cout, device=DEV) * 0.1
+    y = ops.conv3x3_s2_infer(x, wt, scale, shift, True, groups)
+    want = torch.relu(ref * scale[None, :, None, None] + shift[None, :, None, None])
+    assert y.shape == want.shape and _rel(y, want) < 1e-2
+    if groups == 1:
+        stats = torch.zeros(2 * cout, device=DEV)
+        xg = x.clone().requires_grad_(True)
+        wg = wt.clone().requires_grad_(True)
+        yt = ops.conv3x3_s2(xg, wg, stats)
+        assert _rel(yt, ref) < 1e-2
+        assert _rel(stats[:cout], yt.float().sum((0, 2, 3))) < 2e-3
+        dy = torch.randn_like(yt)
+        yt.backward(dy)
+        xr = x.float().requires_grad_(True)
+        wr = wt.float().requires_grad_(True)
+        F.conv2d(xr, wr.permute(0, 3, 1, 2), None, 2, 1).backward(dy.float())
+        assert _rel(xg.grad, xr.grad) < 1e-2 and _rel(wg.grad, wr.grad) < 1e-2

@@ -53,3 +53,42 @@ def test_resnet_stage_geometries_waste_nothing():
     for n, hw in ((32, 56), (32, 28), (32, 14), (32, 7)):
         bh, nb, kb = ops.native().conv3x3_wgrad_plan(n, hw, hw)
         assert kb == 112 and hw % bh == 0 and n % nb == 0, (hw, bh, nb, kb)      # every MMA row is a real pixel
+
+
+def _strided_box(t, n0, nb, h0, bh2, w0, w2, stride):
+    """TMA tile with a traversal stride: a box spanning bh2 x w2 source elements from (h0, w0) delivers every
+    ``stride``-th one (ceil(span / stride) per dimension); elements outside the tensor read as zero."""
+    N, H, W, C = t.shape
+    hs, ws = range(h0, h0 + bh2, stride), range(w0, w0 + w2, stride)
+    out = torch.zeros(nb, len(hs), len(ws), C, dtype=t.dtype)
+    for bi in range(nb):
+        if not 0 <= n0 + bi < N:
+            continue
+        for i, h in enumerate(hs):
+            for j, w in enumerate(ws):
+                if 0 <= h < H and 0 <= w < W:
+                    out[bi, i, j] = t[n0 + bi, h, w]
+    return out
+
+
+@pytest.mark.parametrize("n,ho,wo,cin,cout", [(2, 4, 6, 3, 5), (3, 7, 7, 4, 4), (1, 14, 14, 2, 3)])
+def test_stride2_fprop_replay_matches_conv2d(n, ho, wo, cin, cout):
+    """The stride-2 mode of the persistent conv kernel (csrc/gemm_persist.cu): output tile = BH rows x Wo columns; for
+    tap (r, s) the A operand is the input box starting at row 2*h0 + r - 1, column s - 1, spanning 2*BH x 2*Wo source
+    elements with traversal stride 2."""
+    torch.manual_seed(0)
+    x = torch.randn(n, 2 * ho, 2 * wo, cin, dtype=torch.float64)            # NHWC input, twice the output size
+    wt = torch.randn(cout, 3, 3, cin, dtype=torch.float64)                  # KRSC
+    y = torch.zeros(n, ho, wo, cout, dtype=torch.float64)
+    bh = 2 if ho % 2 == 0 else 1                                            # any row tiling works the same way
+    for img in range(n):
+        for h0 in range(0, ho, bh):
+            rows = min(bh, ho - h0)
+            acc = torch.zeros(bh * wo, cout, dtype=torch.float64)
+            for r in range(3):
+                for s in range(3):
+                    a = _strided_box(x, img, 1, 2 * h0 + r - 1, 2 * bh, s - 1, 2 * wo, 2).reshape(bh * wo, cin)
+                    acc += a @ wt[:, r, s, :].t()
+            y[img, h0:h0 + rows] = acc.reshape(bh, wo, cout)[:rows]
+    ref = F.conv2d(x.permute(0, 3, 1, 2), wt.permute(0, 3, 1, 2), None, 2, 1).permute(0, 2, 3, 1)
+    assert torch.allclose(y, ref, atol=1e-9)
