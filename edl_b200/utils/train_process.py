@@ -50,6 +50,20 @@ def trainer_env(job_env, cluster, pod, trainer):
     }
 
 
+def _child_setup():
+    """Runs in the forked child before exec: own session (so the whole trainer tree can be signalled as a group) and
+    PR_SET_PDEATHSIG, so a launcher that is SIGKILLed or crashes never leaves orphan trainers holding GPUs and
+    spinning in collectives (Linux only; silently skipped elsewhere)."""
+    os.setsid()
+    try:
+        import ctypes
+
+        libc = ctypes.CDLL("libc.so.6", use_errno=True)
+        libc.prctl(1, int(signal.SIGKILL), 0, 0, 0)      # PR_SET_PDEATHSIG = 1
+    except Exception:  # noqa: BLE001
+        pass
+
+
 def start(job_env, cluster, pod, training_script, training_script_args, log_dir=None):
     base_env = dict(os.environ)
     # proxies can make peers unreachable during communicator bootstrap
@@ -64,9 +78,9 @@ def start(job_env, cluster, pod, training_script, training_script_args, log_dir=
         if log_dir is not None:
             os.makedirs(log_dir, exist_ok=True)
             fn = open(os.path.join(log_dir, "workerlog.%d" % idx), "a")
-            proc = subprocess.Popen(cmd, env=env, stdout=fn, stderr=fn, start_new_session=True)
+            proc = subprocess.Popen(cmd, env=env, stdout=fn, stderr=fn, preexec_fn=_child_setup)
         else:
-            proc = subprocess.Popen(cmd, env=env, start_new_session=True)
+            proc = subprocess.Popen(cmd, env=env, preexec_fn=_child_setup)
         tp = TrainerProc()
         tp.proc, tp.rank, tp.log_fn, tp.local_rank, tp.cmd = proc, t.global_rank, fn, idx, cmd
         tp.log_offset = fn.tell() if fn else None

@@ -105,9 +105,20 @@ def run(mode, server_cls):
                     "leave_s": leave, "leave_stall_s": leave_stall, "survivor_process_kept": survivor_kept,
                     "steady_epoch_s": sorted(y["t"] - x["t"] for x, y in zip(e[-5:-1], e[-4:]))[1]}
         finally:
+            import psutil
+
             for p in (a, b):
-                if p is not None and p.poll() is None:
-                    os.killpg(os.getpgid(p.pid), 9)
+                if p is None:
+                    continue
+                try:
+                    tree = [psutil.Process(p.pid)] + psutil.Process(p.pid).children(recursive=True)
+                except psutil.NoSuchProcess:
+                    continue
+                for q in tree:            # launchers AND their trainers (own sessions): nothing may outlive the bench
+                    try:
+                        q.kill()
+                    except psutil.NoSuchProcess:
+                        pass
 
 
 if __name__ == "__main__":
