@@ -104,6 +104,8 @@ const char* conv3x3_wgrad_bf16(const Conv3x3WgradArgs& args, cudaStream_t stream
 
 // Persistent variants (gemm_persist.cu): one CTA per SM streams tiles, double-buffered TMEM accumulators,
 // epilogue overlapped with the next tile's MMAs.  Used by gemm_bf16 / conv3x3_bf16 when enabled (default).
+void set_bnr_mode(int mode);   // fused BN-backward reduction: 1 = shuffle transpose in registers, 2 = column loop over staged tiles
+int get_bnr_mode();
 void set_persistent_gemm(bool on);
 bool persistent_gemm_enabled();
 const char* gemm_bf16_persistent(const GemmArgs& args, cudaStream_t stream);

@@ -319,6 +319,8 @@ void register_gemm_bindings(pybind11::module_& m) {
   m.def("gemm_bf16", &gemm_bf16);
   m.def("conv3x3", &conv3x3);
   m.def("set_persistent_gemm", &edl::set_persistent_gemm);
+  m.def("set_bnr_mode", &edl::set_bnr_mode);
+  m.def("get_bnr_mode", &edl::get_bnr_mode);
   m.def("persistent_gemm_enabled", &edl::persistent_gemm_enabled);
   m.def("gemm_fp8", &gemm_fp8);
   m.def("quantize_e4m3", &quantize_e4m3);

@@ -17,6 +17,7 @@
 //        2 = 3x3/s1/p1 conv fprop, 3 = 3x3/s1/p1 conv dgrad (see conv3x3.cu for the shifted-box trick).
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 
 #include "gemm.h"
 #include "kernels.h"
@@ -62,7 +63,7 @@ struct PersistParams {
   int stride;                     // conv fprop: 1, or 2 (input rows 2*h + r - 1; the columns come from the tensor map)
 };
 
-template <int BLOCK_N, int STAGES, bool BNR = false>
+template <int BLOCK_N, int STAGES, int BNR = 0>
 struct PSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -130,7 +131,7 @@ EDL_DEVICE void issue_bn_tiles(const PersistParams& p, int tt, int rows_tile, ui
   }
 }
 
-template <int BLOCK_N, int STAGES, int MODE, bool BNR>
+template <int BLOCK_N, int STAGES, int MODE, int BNR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
@@ -329,7 +330,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           asm volatile("bar.sync 2, 256;" ::: "memory");
           const_n0 = n0;
         }
-        ptx::mbar_wait(bn_bar, tc & 1);
+        if (BNR == 1) ptx::mbar_wait(bn_bar, tc & 1);     // mode 2 waits where it reads x / y
       }
       ptx::mbar_wait(&tmem_full[slot], aph);
       ptx::tc_fence_after();
@@ -386,7 +387,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
         }
-        if (BNR) {
+        if (BNR == 1) {
           // dy = the bf16 value this tile stores; masked by the ReLU of the BN layer, reduced per channel
           const uint32_t xrow = ptx::smem_u32(sx) + (cbase >> 6) * (kBlockM * 128) + row * 128;
           const uint32_t yrow = ptx::smem_u32(sy) + (cbase >> 6) * (kBlockM * 128) + row * 128;
@@ -452,7 +453,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       ptx::fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (BNR && et == 0 && t + (int)gridDim.x < total_tiles)   // x / y buffers are free: prefetch the next tile's
+      if (BNR == 1 && et == 0 && t + (int)gridDim.x < total_tiles)   // x / y buffers are free: prefetch the next tile's
         issue_bn_tiles<BLOCK_N, kConv>(p, t + (int)gridDim.x, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
       if (et == 0) {
 #pragma unroll
@@ -462,6 +463,89 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else tma_store_4d_p(&tmD, sd + hh * (kBlockM * 128), n0 + hh * 64, 0, h0, img0);
         }
         ptx::tma_store_commit();
+      }
+      if (BNR == 2) {
+        // BatchNorm-backward reduction of the tile just staged: per channel sum(dy_m) and sum(dy_m * xhat), dy_m = the
+        // STORED bf16 gradient masked by the layer's ReLU.  Same scheme as the forward statistics below -- a thread owns
+        // a pair of adjacent columns and every kSplit-th row, eight independent row loads in flight -- reading the
+        // gradient from the staging tile and x (/ y) from the tiles the producer fetched by TMA.  (The first version
+        // reduced in registers with a 31-shuffle transpose per 32 columns and pass: 46-59 us per short-K dgrad kernel
+        // instead of 15 us, profiles/README.md.)
+        ptx::mbar_wait(bn_bar, tc & 1);
+        constexpr int kPairs = BLOCK_N / 2;
+        constexpr int kSplit = kEpiThreads / kPairs;
+        const int pair = et % kPairs;
+        const int part = et / kPairs;
+        const int col = pair * 2;
+        const bool valid = n0 + col < p.N;
+        const int half = col >> 6, cc = col & 63, chunk = cc >> 3, within = cc & 7;
+        const uint32_t toff = half * (kBlockM * 128) + within * 2;
+        const uint32_t based = ptx::smem_u32(sd) + toff, basex = ptx::smem_u32(sx) + toff, basey = ptx::smem_u32(sy) + toff;
+        const float4 k0 = reinterpret_cast<const float4*>(sconst)[col];          // mean, rstd, scale, shift
+        const float4 k1 = reinterpret_cast<const float4*>(sconst)[col + 1];
+        const bool relu = p.bn_relu != 0, has_y = p.bn_has_y != 0;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        auto accum_rows = [&](int r_begin, int r_end) {
+          int rr = r_begin + part;
+          for (; rr + 7 * kSplit < r_end; rr += 8 * kSplit) {
+            uint32_t wd[8], wx[8], wy[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int r = rr + u * kSplit;
+              const uint32_t o = r * 128 + ((chunk ^ (r & 7)) << 4);
+              wd[u] = ptx::lds32(based + o);
+              wx[u] = ptx::lds32(basex + o);
+              wy[u] = has_y ? ptx::lds32(basey + o) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wd[u]));
+              const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wx[u]));
+              const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wy[u]));
+              const bool m0 = !relu || (has_y ? y.x > 0.f : fmaf(x.x, k0.z, k0.w) > 0.f);
+              const bool m1 = !relu || (has_y ? y.y > 0.f : fmaf(x.y, k1.z, k1.w) > 0.f);
+              const float d0 = m0 ? d.x : 0.f, d1 = m1 ? d.y : 0.f;
+              s0 += d0; q0 = fmaf(d0, (x.x - k0.x) * k0.y, q0);
+              s1 += d1; q1 = fmaf(d1, (x.y - k1.x) * k1.y, q1);
+            }
+          }
+          for (; rr < r_end; rr += kSplit) {
+            const uint32_t o = rr * 128 + ((chunk ^ (rr & 7)) << 4);
+            const uint32_t wd = ptx::lds32(based + o), wx = ptx::lds32(basex + o), wy = has_y ? ptx::lds32(basey + o) : 0u;
+            const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wd));
+            const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wx));
+            const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wy));
+            const bool m0 = !relu || (has_y ? y.x > 0.f : fmaf(x.x, k0.z, k0.w) > 0.f);
+            const bool m1 = !relu || (has_y ? y.y > 0.f : fmaf(x.y, k1.z, k1.w) > 0.f);
+            const float d0 = m0 ? d.x : 0.f, d1 = m1 ? d.y : 0.f;
+            s0 += d0; q0 = fmaf(d0, (x.x - k0.x) * k0.y, q0);
+            s1 += d1; q1 = fmaf(d1, (x.y - k1.x) * k1.y, q1);
+          }
+        };
+        if (valid) {
+          // only rows that are real pixels of the tensor: the others hold stale shared memory
+          if (!kConv) {
+            int rows_valid = p.M - m0;
+            if (rows_valid > kBlockM) rows_valid = kBlockM;
+            accum_rows(0, rows_valid);
+          } else {
+            const int rows_per_img = p.BH * p.W;
+            int hv = p.H - h0;
+            if (hv > p.BH) hv = p.BH;
+            for (int b = 0; b < p.BN && img0 + b < p.n_img; ++b) accum_rows(b * rows_per_img, b * rows_per_img + hv * p.W);
+          }
+          float* dst = local_stats ? sstats : p.bn_dsums;
+          atomicAdd(&dst[n0 + col], s0);
+          atomicAdd(&dst[p.N + n0 + col], q0);
+          if (n0 + col + 1 < p.N) {
+            atomicAdd(&dst[n0 + col + 1], s1);
+            atomicAdd(&dst[p.N + n0 + col + 1], q1);
+          }
+        }
+        // everybody is done with this tile's x / y: fetch the next tile's while its MMAs run
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (et == 0 && t + (int)gridDim.x < total_tiles)
+          issue_bn_tiles<BLOCK_N, kConv>(p, t + (int)gridDim.x, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
       }
       if (!BNR && p.col_stats != nullptr) {
         // Per-channel sum / sum of squares of the STORED bf16 values, from the staged tile.  A thread owns
@@ -569,8 +653,14 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 bool g_persistent = true;
+// fused BatchNorm-backward reduction in the dgrad epilogue: 1 = in-register shuffle transpose (validated at kernel
+// level in round 1, epilogue-bound), 2 = column-pair loop over the staged tiles (written afterwards, EDL_BNR_MODE=2)
+int g_bnr_mode = [] {
+  const char* e = getenv("EDL_BNR_MODE");
+  return (e != nullptr && e[0] == '2') ? 2 : 1;
+}();
 
-template <int BLOCK_N, int STAGES, int MODE, bool BNR = false>
+template <int BLOCK_N, int STAGES, int MODE, int BNR = 0>
 const char* launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const PersistParams& p,
                      cudaStream_t stream, const CUtensorMap* tmAdd = nullptr, const CUtensorMap* tmBnX = nullptr,
                      const CUtensorMap* tmBnY = nullptr) {
@@ -592,6 +682,8 @@ const char* launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
+int bnr_mode() { return g_bnr_mode; }
+
 const char* tmap2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
                    uint32_t box_inner, uint32_t box_outer) {
   const uint64_t dims[2] = {inner, outer};
@@ -611,6 +703,8 @@ void fill_bn(PersistParams& p, const BnBwdFuse& bn) {
 }
 }  // namespace
 
+void set_bnr_mode(int mode) { g_bnr_mode = mode == 2 ? 2 : 1; }
+int get_bnr_mode() { return g_bnr_mode; }
 void set_persistent_gemm(bool on) { g_persistent = on; }
 bool persistent_gemm_enabled() { return g_persistent; }
 
@@ -652,8 +746,11 @@ const char* gemm_bf16_persistent(const GemmArgs& g, cudaStream_t stream) {
     if (has_y)
       if (const char* e = tmap2d(&tmBy, g.bn.y, g.N, g.M, g.ldd, 64, kBlockM)) return e;
     fill_bn(p, g.bn);
-    return n64 ? launch_p<64, 4, 1, true>(tmA, tmB, tmD, p, stream, padd, &tmBx, has_y ? &tmBy : nullptr)
-               : launch_p<128, 3, 1, true>(tmA, tmB, tmD, p, stream, padd, &tmBx, has_y ? &tmBy : nullptr);
+    if (bnr_mode() == 2)
+      return n64 ? launch_p<64, 4, 1, 2>(tmA, tmB, tmD, p, stream, padd, &tmBx, has_y ? &tmBy : nullptr)
+                 : launch_p<128, 3, 1, 2>(tmA, tmB, tmD, p, stream, padd, &tmBx, has_y ? &tmBy : nullptr);
+    return n64 ? launch_p<64, 4, 1, 1>(tmA, tmB, tmD, p, stream, padd, &tmBx, has_y ? &tmBy : nullptr)
+               : launch_p<128, 3, 1, 1>(tmA, tmB, tmD, p, stream, padd, &tmBx, has_y ? &tmBy : nullptr);
   }
   if (!g.b_mn_major)
     return n64 ? launch_p<64, 6, 0>(tmA, tmB, tmD, p, stream, padd) : launch_p<128, 5, 0>(tmA, tmB, tmD, p, stream, padd);
@@ -713,8 +810,11 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
     if (has_y)
       if (const char* e = encode_tmap_bf16(&tmBy, a.bn.y, 4, dims, st, box)) return e;
     fill_bn(p, a.bn);
-    return n64 ? launch_p<64, 4, 3, true>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr)
-               : launch_p<128, 3, 3, true>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr);
+    if (bnr_mode() == 2)
+      return n64 ? launch_p<64, 4, 3, 2>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr)
+                 : launch_p<128, 3, 3, 2>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr);
+    return n64 ? launch_p<64, 4, 3, 1>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr)
+               : launch_p<128, 3, 3, 1>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr);
   }
   if (!dg) return n64 ? launch_p<64, 6, 2>(tmX, tmW, tmY, p, stream) : launch_p<128, 5, 2>(tmX, tmW, tmY, p, stream);
   return n64 ? launch_p<64, 6, 3>(tmX, tmW, tmY, p, stream) : launch_p<128, 5, 3>(tmX, tmW, tmY, p, stream);

@@ -323,3 +323,44 @@ def test_conv3x3_stride2_fprop(n, cin, cout, h, w, groups):
         wr = wt.float().requires_grad_(True)
         F.conv2d(xr, wr.permute(0, 3, 1, 2), None, 2, 1).backward(dy.float())
         assert _rel(xg.grad, xr.grad) < 1e-2 and _rel(wg.grad, wr.grad) < 1e-2
+
+
+@pytest.fixture
+def bnr_mode2():
+    C = ops.native()
+    C.set_bnr_mode(2)
+    yield
+    C.set_bnr_mode(1)
+
+
+@pytest.mark.parametrize("m,k,n", [(2048, 64, 32), (5000, 64, 128), (6272, 512, 256), (300, 64, 1024), (100352, 64, 256)])
+@pytest.mark.parametrize("relu,has_y", [(True, False), (True, True), (False, False)])
+def test_bnr_mode2_gemm(bnr_mode2, m, k, n, relu, has_y):
+    """Fused BatchNorm-backward reduction, column-loop version (EDL_BNR_MODE=2): same contract as mode 1
+    (tests/test_persist_gpu.py), 1x1 dgrad epilogue."""
+    from test_persist_gpu import _bn_ref_sums, _hook
+
+    torch.manual_seed(5)
+    a = torch.randn(m, k, device=DEV).bfloat16()
+    w = (torch.randn(k, n, device=DEV) * 0.1).bfloat16()
+    x = torch.randn(m, n, device=DEV).bfloat16()
+    y = torch.randn(m, n, device=DEV).bfloat16() if has_y else None
+    h = _hook(x, y, n, relu)
+    d = ops.gemm_bf16(a, w, b_mn_major=True, bn=h)
+    assert h.done and _rel(d, a.float() @ w.float()) < 1e-2
+    assert _rel(h.dsums, _bn_ref_sums(d, x, y, h.mean, h.rstd, h.gamma, h.beta, relu)) < 1e-4
+
+
+@pytest.mark.parametrize("nb,c,hh,ww", [(8, 64, 16, 16), (32, 256, 14, 14), (5, 64, 11, 20), (8, 256, 2, 2), (32, 64, 56, 56)])
+def test_bnr_mode2_conv3x3(bnr_mode2, nb, c, hh, ww):
+    from test_persist_gpu import _bn_ref_sums, _hook
+
+    torch.manual_seed(6)
+    dy = torch.randn(nb, c, hh, ww, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(c, 3, 3, c, device=DEV) * 0.05).bfloat16()
+    x = torch.randn(nb, c, hh, ww, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    h = _hook(x, None, c, True)
+    dx = torch.empty_like(x)
+    ops.native().conv3x3(dy, wt, dx, True, None, h.as_list(nb * hh * ww, c), True)
+    d2, x2 = dx.permute(0, 2, 3, 1).reshape(-1, c), x.permute(0, 2, 3, 1).reshape(-1, c)
+    assert _rel(h.dsums, _bn_ref_sums(d2, x2, None, h.mean, h.rstd, h.gamma, h.beta, True)) < 1e-4
