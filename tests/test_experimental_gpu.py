@@ -364,3 +364,31 @@ def test_bnr_mode2_conv3x3(bnr_mode2, nb, c, hh, ww):
     ops.native().conv3x3(dy, wt, dx, True, None, h.as_list(nb * hh * ww, c), True)
     d2, x2 = dx.permute(0, 2, 3, 1).reshape(-1, c), x.permute(0, 2, 3, 1).reshape(-1, c)
     assert _rel(h.dsums, _bn_ref_sums(d2, x2, None, h.mean, h.rstd, h.gamma, h.beta, True)) < 1e-4
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("m,k,n,with_add", [(100352, 64, 256, False), (100352, 64, 256, True), (25088, 512, 128, True),
+                                            (6272, 1024, 2048, False)])
+def test_bnr_many_tiles_per_cta_and_addend(mode, m, k, n, with_add):
+    """What the round-1 kernel tests did not cover and the model needs: several tiles per persistent CTA (x / y prefetch,
+    barrier parities, constant reloads when the N tile changes) and the residual-gradient addend together with the
+    BatchNorm reduction (every block's first 1x1 convolution).  Run for both reduction modes: if mode 1 fails here, this
+    is the 'model-level mismatch' of NOTES.md."""
+    from test_persist_gpu import _bn_ref_sums, _hook
+
+    C = ops.native()
+    C.set_bnr_mode(mode)
+    try:
+        torch.manual_seed(7)
+        a = torch.randn(m, k, device=DEV).bfloat16()
+        w = (torch.randn(k, n, device=DEV) * 0.05).bfloat16()
+        x = torch.randn(m, n, device=DEV).bfloat16()
+        y = torch.randn(m, n, device=DEV).bfloat16()
+        add = torch.randn(m, n, device=DEV).bfloat16() if with_add else None
+        h = _hook(x, y, n, True)
+        d = ops.gemm_bf16(a, w, b_mn_major=True, bn=h, add=add)
+        ref = a.float() @ w.float() + (add.float() if with_add else 0.0)
+        assert h.done and _rel(d, ref) < 1e-2
+        assert _rel(h.dsums, _bn_ref_sums(d, x, y, h.mean, h.rstd, h.gamma, h.beta, True)) < 1e-4
+    finally:
+        C.set_bnr_mode(1)
