@@ -392,3 +392,39 @@ def test_bnr_many_tiles_per_cta_and_addend(mode, m, k, n, with_add):
         assert _rel(h.dsums, _bn_ref_sums(d, x, y, h.mean, h.rstd, h.gamma, h.beta, True)) < 1e-4
     finally:
         C.set_bnr_mode(1)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fused_bn_backward_matches_unfused_at_model_level(monkeypatch, mode):
+    """EDL_FUSE_BN_BWD at model level: ResNet50_vd gradients with the BatchNorm reductions riding in the dgrad epilogues
+    against the same model with the stand-alone reduction kernels (NOTES.md open item 1)."""
+    import copy
+
+    from edl_b200.models import ResNet50_vd, to_train_dtype
+    from edl_b200.ops import gemm as G
+
+    C = ops.native()
+    torch.manual_seed(0)
+    base = to_train_dtype(ResNet50_vd(class_dim=100), torch.bfloat16, torch.device(DEV)).train()
+    x = torch.randn(8, 3, 96, 96, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    t = torch.softmax(torch.randn(8, 100, device=DEV), -1).bfloat16()
+
+    def grads(fuse):
+        m = copy.deepcopy(base)
+        monkeypatch.setattr(G, "FUSE_BN_BWD", fuse)
+        ops.reset_launches()
+        loss = ops.soft_cross_entropy(m(x), t)
+        loss.backward()
+        torch.cuda.synchronize()
+        return float(loss), ops.launches(), {n: p.grad.float().clone() for n, p in m.named_parameters()}
+
+    C.set_bnr_mode(mode)
+    try:
+        l0, n0, g0 = grads(False)
+        l1, n1, g1 = grads(True)
+    finally:
+        C.set_bnr_mode(1)
+    assert abs(l0 - l1) < 1e-3
+    assert n1 < n0 - 20, "the fused path should launch ~40 kernels fewer (%d vs %d)" % (n1, n0)
+    worst = max((_rel(g1[k], g0[k]), k) for k in g0)
+    assert worst[0] < 3e-2, worst
