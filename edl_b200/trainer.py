@@ -98,6 +98,7 @@ class StudentTrainer:
                 backoff_factor=0.5 if dynamic_loss_scaling else 1.0)
             self.scaler.found_inf = self.dp.found_inf
             self.scaler.attach(self.opt, self.dp)
+        self._guard_comm_error()
         # recompute runs every block's forward twice: the pre-zeroed accumulate-into arena slices would
         # be summed twice, so those runs let each op allocate its own scratch
         self.arena = StepArena(model, self.device) if self.cuda and not getattr(model, "recompute", False) else None
@@ -271,10 +272,27 @@ class StudentTrainer:
         return {"acc1": float(counts[0]) / n, "acc5": float(counts[1]) / n, "n": int(counts[2])}
 
     # ------------------------------------------------------------------ elastic
+    def _guard_comm_error(self):
+        """In-place elastic mode: make the fused optimizer skip its update on device while the fabric's error word is
+        set.  A peer that died mid-step makes our all-reduce kernels time out with partial sums in the gradient buffer;
+        with the optimizer's ``found_inf`` pointer aimed at that word, every step from the broken one on is a no-op --
+        no host round trip, graph replays included -- until ``ElasticContext.poll(agree=dp.agree)`` notices, ``recover()``
+        rebuilds the group and the parameters are still those of the last good step."""
+        from . import elastic
+
+        if (self.scaler is not None or not elastic.inplace_requested() or self.dp.pool is None
+                or not hasattr(self.opt, "set_found_inf")):
+            return
+        w = ops.native().comm_error_word_offset()
+        self.opt.set_found_inf(self.dp.pool.sig_tensor()[w:w + 1])
+
     def rebuild(self, group):
         """World-size change: re-plan the communication, drop the captured graph."""
         self.graph = None
         self.dp.rebuild(group)
+        if self.scaler is None and hasattr(self.opt, "set_found_inf"):
+            self.opt.set_found_inf(None)          # the old pool (and its error word) is gone
+        self._guard_comm_error()
 
     @torch.no_grad()
     def sync_from(self, root: int = 0):
