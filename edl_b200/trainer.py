@@ -278,10 +278,10 @@ class StudentTrainer:
         with the optimizer's ``found_inf`` pointer aimed at that word, every step from the broken one on is a no-op --
         no host round trip, graph replays included -- until ``ElasticContext.poll(agree=dp.agree)`` notices, ``recover()``
         rebuilds the group and the parameters are still those of the last good step."""
-        from . import elastic
+        import os
 
-        if (self.scaler is not None or not elastic.inplace_requested() or self.dp.pool is None
-                or not hasattr(self.opt, "set_found_inf")):
+        if (os.environ.get("EDL_RESCALE_MODE", "").lower() != "inplace" or self.scaler is not None
+                or self.dp.pool is None or not hasattr(self.opt, "set_found_inf")):
             return
         w = ops.native().comm_error_word_offset()
         self.opt.set_found_inf(self.dp.pool.sig_tensor()[w:w + 1])
