@@ -18,13 +18,43 @@ class Launcher:
         self._watcher = None
         self._procs = []
         self._cluster = None
+        self._metrics = None
         self._leave = False         # SIGTERM / request_leave(): announce the departure, let the job re-plan first
         self._leaving_since = None
         self.rescales = 0          # number of stage changes survived
         self.last_rescale_s = None  # wall seconds from "change seen" to "trainers restarted"
 
     # ------------------------------------------------------------------ set-up
+    def _publish(self):
+        """Prometheus text metrics of this pod's launcher (EDL_METRICS_PORT): what a scheduler / dashboard needs to see
+        elastic events -- the reference only has the status tables in etcd."""
+        if self._metrics is None:
+            return
+        labels = {"job": str(self._job_env.job_id), "pod": str(self._pod.id)[:8]}
+        m = self._metrics
+        m.set("edl_launcher_rescales_total", self.rescales, labels)
+        m.set("edl_launcher_inplace_rescales_total", getattr(self, "inplace_rescales", 0), labels)
+        m.set("edl_launcher_last_rescale_seconds", self.last_rescale_s or 0.0, labels)
+        m.set("edl_launcher_world_size", self._cluster.get_trainers_nranks() if self._cluster is not None else 0, labels)
+        m.set("edl_launcher_pods", len(self._cluster.pods) if self._cluster is not None else 0, labels)
+        m.set("edl_launcher_is_leader", 1 if (self._leader_register is not None and self._leader_register.is_leader()) else 0,
+              labels)
+        m.set("edl_launcher_leaving", 1 if self._leaving_since is not None else 0, labels)
+        m.set("edl_launcher_trainers_alive", sum(1 for tp in self._procs if tp.proc.poll() is None), labels)
+
     def init(self):
+        import os
+
+        self._metrics = None
+        port = os.environ.get("EDL_METRICS_PORT")
+        if port:
+            from .metrics import MetricsExporter
+
+            try:
+                self._metrics = MetricsExporter(int(port)).start()
+                logger.info("launcher metrics on port %d", self._metrics.port)
+            except OSError as e:
+                logger.warning("metrics endpoint not started: %s", e)
         self._pod_server = pod_server.PodServer(self._job_env, self._pod.id, etcd=self._etcd).start()
         self._pod.port = self._pod_server.port
         edl_status.save_pod_status_to_etcd(self._etcd, self._pod.id, edl_status.Status.INITIAL, timeout=30)
@@ -97,6 +127,7 @@ class Launcher:
                                           self._args.training_script_args, log_dir=je.log_dir)
         poll = min(constants.POLL_INTERVAL, 1.0)
         while True:
+            self._publish()
             alive, failed = train_process.watch(self._procs)
             if failed is not None:
                 logger.error("a trainer exited with code %s", failed)
@@ -147,6 +178,7 @@ class Launcher:
                 self.last_rescale_s = time.time() - t0
                 logger.info("rescaled to %d trainers in %.2fs", self._cluster.get_trainers_nranks(),
                             self.last_rescale_s)
+                self._publish()
             time.sleep(poll)
 
     # ------------------------------------------------------------------ in-place rescale (edl_b200/elastic.py)
@@ -235,6 +267,8 @@ class Launcher:
             train_process.terminate(self._procs)
         if self._pod_server is not None:
             self._pod_server.stop()
+        if getattr(self, "_metrics", None) is not None:
+            self._metrics.stop()
 
     def __enter__(self):
         return self

@@ -72,7 +72,14 @@ def test_elastic_join_and_leave(kv_server, tmp_path):
     rec = str(tmp_path / "rec")
     done = str(tmp_path / "done.flag")
     env = {"DEMO_RECORD_DIR": rec, "DEMO_RUN_SECONDS": "120", "DEMO_DONE_FLAG": done}
-    a = _launch(kv_server.endpoint, job, "1:2", str(tmp_path / "logA"), env, gpus="0")
+    from edl_b200.utils.network_utils import find_free_ports
+    mport = find_free_ports(1)[0]
+    a = _launch(kv_server.endpoint, job, "1:2", str(tmp_path / "logA"), dict(env, EDL_METRICS_PORT=str(mport)), gpus="0")
+
+    def metrics():
+        import urllib.request
+        body = urllib.request.urlopen("http://127.0.0.1:%d/metrics" % mport, timeout=5).read().decode()
+        return {ln.split("{")[0]: float(ln.rsplit(" ", 1)[1]) for ln in body.splitlines() if ln}
 
     def worlds():
         return sorted((json.load(open(f))["t"], json.load(open(f))["WORLD_SIZE"]) for f in glob.glob(rec + "/start_*.json"))
@@ -91,6 +98,10 @@ def test_elastic_join_and_leave(kv_server, tmp_path):
     b = _launch(kv_server.endpoint, job, "1:2", str(tmp_path / "logB"), env, gpus="1")
     wait_for(lambda: [w for _, w in worlds()].count("2") == 2, 60, "both pods restarted with world 2")
     join_latency = max(t for t, w in worlds() if w == "2") - t_join
+    wait_for(lambda: metrics().get("edl_launcher_world_size") == 2, 10, "launcher metrics to show world 2")
+    m = metrics()                                  # the launcher's Prometheus endpoint saw the elastic event
+    assert m["edl_launcher_world_size"] == 2 and m["edl_launcher_rescales_total"] >= 1 and m["edl_launcher_is_leader"] == 1
+    assert m["edl_launcher_trainers_alive"] == 1 and m["edl_launcher_last_rescale_seconds"] > 0
     os.killpg(os.getpgid(b.pid), signal.SIGKILL)   # pod B dies hard (no clean deregistration)
     t_leave = time.time()
     wait_for(lambda: [w for _, w in worlds()][-1] == "1" and len(worlds()) == 4, 60, "A back to world 1")
