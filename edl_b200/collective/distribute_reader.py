@@ -139,7 +139,9 @@ class Reader:
     """``Reader(file_list, file_splitter_cls, batch_size, cache_capcity=100)`` -- iterate to get
     ``{"meta", "data"}`` dicts.  ``pod_id / leader_endpoint / etcd / pod_ids`` default to the
     launcher-provided trainer environment (one reader per pod: use it from the pod's rank-0
-    trainer, or give each trainer its own ``name``)."""
+    trainer, or give each trainer its own ``name``).  ``cache_capcity`` is also the balancing granularity: the
+    accesser prefetches that many batches, so a small value hands batches out at the pace they are consumed and the
+    work stealing then keeps the pods finishing together; a large one favours throughput of the fetch path."""
 
     def __init__(self, file_list, file_splitter_cls, batch_size, cache_capcity=100, name=None, pod_id=None,
                  leader_endpoint=None, etcd=None, pod_ids=None, is_leader=None, data_checkpoint=None,

@@ -193,6 +193,7 @@ class ElasticContext:
         self._steps = 0
         self._changed = threading.Event()
         self._stage_pods = set()
+        self._stage_pod_list = []
         self._watch_id = None
         self._etcd = etcd
         self._own_etcd = etcd is None
@@ -282,6 +283,7 @@ class ElasticContext:
                 if committed is not None:
                     rec = json.loads(committed.decode())
                     self._stage_pods = cluster.get_pods_ids_set()
+                    self._stage_pod_list = cluster.get_pods_ids_list()
                     return StageInfo(stage=stage, rank=rank, size=size, rank_in_pod=rip, root=rec["root"],
                                      survivor=survivor, prev_size=prev_size, rendezvous_s=time.time() - t0)
                 latest = edl_cluster.load_from_etcd(self._etcd, timeout=10)
@@ -352,6 +354,32 @@ class ElasticContext:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             flag = float(t.item())
         return flag > 0.5
+
+    def should_switch(self) -> bool:
+        """Local (non-collective) form of ``poll()``: the membership changed and every joiner is waiting.  For loops
+        whose ranks do not run in lock step (e.g. the elastic data reader, where pods consume different numbers of
+        batches); each rank then calls ``rescale()`` on its own and the stage rendezvous brings them together."""
+        return (not self.standalone) and self._changed.is_set() and self._joiners_ready()
+
+    @property
+    def pod_ids(self):
+        """Pod ids of the committed stage, leader first (what ``collective.distribute_reader.Reader`` wants)."""
+        c = edl_cluster.load_from_etcd(self._etcd, timeout=10)
+        if c is not None and self.info is not None and c.stage == self.info.stage:
+            return c.get_pods_ids_list()
+        return list(self._stage_pod_list)
+
+    @property
+    def etcd(self):
+        return self._etcd
+
+    def allgather_object(self, obj):
+        """Every rank's ``obj`` (rank order) over the current stage's process group."""
+        if self.info is None or self.info.size <= 1 or not dist.is_initialized():
+            return [obj]
+        out = [None] * self.info.size
+        dist.all_gather_object(out, obj)
+        return out
 
     def rescale(self) -> StageInfo:
         """Leave the old process group, run the stage rendezvous, build the new group.  Raises

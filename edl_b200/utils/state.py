@@ -40,6 +40,16 @@ class DataCheckpoint(Serializable):
 
         return is_processed(record_no, self.processed_data.get(str(file_idx), []))
 
+    def merge(self, other):
+        """Union with another pod's consumed ranges (``other``: DataCheckpoint or its ``processed_data`` dict) -- what the
+        trainers of a new stage exchange after an in-place rescale so that the re-created reader skips everything ANY pod
+        has already trained on."""
+        data = other.processed_data if isinstance(other, DataCheckpoint) else (other or {})
+        for key, ranges in data.items():
+            for b, e in ranges:
+                self.mark(key, b, e)
+        return self
+
 
 class EpochAttr(Serializable):
     def __init__(self):

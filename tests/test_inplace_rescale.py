@@ -273,3 +273,60 @@ def test_sigterm_is_a_graceful_leave(kv_server, tmp_path):
         for p in (a, b):
             if p is not None and p.poll() is None:
                 os.killpg(os.getpgid(p.pid), 9)
+
+
+@pytest.mark.slow
+def test_elastic_reader_consumes_every_record_once_across_an_inplace_join(kv_server, tmp_path):
+    """Elastic data plane + in-place rescale: pod A starts reading alone, pod B joins mid-epoch; the pods exchange their
+    consumed ranges at the stage rendezvous and re-create the balanced reader -- no record is lost, none is read twice,
+    and A's process survives."""
+    job = "reader_" + uuid.uuid4().hex[:6]
+    out = tmp_path / "out"
+    out.mkdir()
+    files = []
+    for i, n in enumerate([150, 90, 120, 60]):
+        p = tmp_path / ("f%d.txt" % i)
+        p.write_text("".join("file%d-line%d\n" % (i, j) for j in range(n)))
+        files.append(str(p))
+    demo = os.path.join(ROOT, "tests", "elastic_reader_demo.py")
+
+    def launch(name):
+        env = dict(os.environ)
+        env.update({"PYTHONPATH": ROOT, "CUDA_VISIBLE_DEVICES": "", "PADDLE_RUNNING_PLATFORM": "", "EDL_POD_IP": "127.0.0.1",
+                    "READER_DEMO_OUT": str(out), "EDL_INPLACE_ACK_TIMEOUT": "60", "READER_DEMO_STEP": "0.15"})
+        cmd = [sys.executable, "-u", "-m", "edl_b200.collective.launch", "--nodes_range", "1:2", "--nproc_per_node", "1",
+               "--etcd_endpoints", kv_server.endpoint, "--job_id", job, "--log_dir", str(tmp_path / ("log" + name)),
+               "--rescale_mode", "inplace", demo, ",".join(files)]
+        return subprocess.Popen(cmd, env=env, stdout=open(str(tmp_path / (name + ".launcher.log")), "w"),
+                                stderr=subprocess.STDOUT, start_new_session=True)
+
+    def records():
+        rows = []
+        for f in out.glob("consumed_*.jsonl"):
+            rows += [json.loads(l) for l in open(f)]
+        return rows
+
+    a = launch("A")
+    b = None
+    try:
+        deadline = time.time() + 90
+        while len(records()) < 24:
+            assert time.time() < deadline and a.poll() is None, (tmp_path / "A.launcher.log").read_text()[-3000:]
+            time.sleep(0.1)
+        b = launch("B")
+        assert a.wait(timeout=240) == 0, (tmp_path / "logA" / "workerlog.0").read_text()[-3000:]
+        assert b.wait(timeout=120) == 0, (tmp_path / "logB" / "workerlog.0").read_text()[-3000:]
+        rows = records()
+        seen = [(r["file"], r["rec"]) for r in rows]
+        want = {(i, j) for i, n in enumerate([150, 90, 120, 60]) for j in range(n)}
+        assert len(seen) == len(set(seen)), "records consumed twice: %d" % (len(seen) - len(set(seen)))
+        assert set(seen) == want, "records lost: %d" % len(want - set(seen))
+        by_pid = {}
+        for r in rows:
+            by_pid.setdefault(r["pid"], set()).add(r["world"])
+        assert len(by_pid) == 2 and any(w == {1, 2} for w in by_pid.values()), by_pid   # A read at world 1 AND 2: same process
+        assert "reader demo rescaled in place: 1 -> 2" in (tmp_path / "logA" / "workerlog.0").read_text()
+    finally:
+        for p in (a, b):
+            if p is not None and p.poll() is None:
+                os.killpg(os.getpgid(p.pid), 9)
