@@ -265,6 +265,7 @@ struct Conn {
   int fd = -1;
   uint64_t cid = 0;
   std::string in, out;
+  size_t out_off = 0;          // bytes of `out` already sent (a slow watcher must not cost a memmove per send)
   bool want_write = false, dead = false;
 };
 
@@ -758,10 +759,10 @@ int main(int argc, char** argv) {
   double last_expire = now_s(), last_snap = now_s();
 
   auto flush = [&](Conn* c) {
-    while (!c->out.empty()) {
-      const ssize_t n = send(c->fd, c->out.data(), c->out.size(), MSG_NOSIGNAL);
+    while (c->out_off < c->out.size()) {
+      const ssize_t n = send(c->fd, c->out.data() + c->out_off, c->out.size() - c->out_off, MSG_NOSIGNAL);
       if (n > 0) {
-        c->out.erase(0, (size_t)n);
+        c->out_off += (size_t)n;
       } else if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) {
         break;
       } else if (n < 0 && errno == EINTR) {
@@ -769,8 +770,16 @@ int main(int argc, char** argv) {
       } else {
         c->dead = true;
         c->out.clear();
+        c->out_off = 0;
         return;
       }
+    }
+    if (c->out_off == c->out.size()) {
+      c->out.clear();
+      c->out_off = 0;
+    } else if (c->out_off > (1u << 20) && c->out_off * 2 > c->out.size()) {
+      c->out.erase(0, c->out_off);          // compact rarely, not per send
+      c->out_off = 0;
     }
     epoll_event e {};
     e.events = EPOLLIN | (c->out.empty() ? 0u : (uint32_t)EPOLLOUT);
