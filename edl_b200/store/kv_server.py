@@ -21,6 +21,7 @@ from __future__ import annotations
 import argparse
 import os
 import logging
+import queue
 import socket
 import socketserver
 import struct
@@ -284,21 +285,55 @@ class _Watcher:
         self.conn, self.wid, self.prefix, self.end = conn, wid, prefix, end
 
     def push(self, events, rev):
-        try:
-            send_msg(self.conn.sock, {"watch_id": self.wid, "events": events, "revision": rev},
-                     self.conn.wlock)
-        except OSError:
-            pass
+        self.conn.send({"watch_id": self.wid, "events": events, "revision": rev})
 
 
 class _Conn:
+    """One client connection.  Everything that goes out -- responses and watch events, in the order they were
+    produced -- is queued and written by the connection's own writer thread: ``push`` is called under the state lock,
+    and a client that stops reading (a paused process, a dead network path) must stall only itself, never the store.
+    A connection whose backlog exceeds ``MAX_BACKLOG`` messages is dropped (its client reconnects and re-watches)."""
+
     _next = 0
+    MAX_BACKLOG = 20000
 
     def __init__(self, sock):
         _Conn._next += 1
         self.cid = _Conn._next
         self.sock = sock
-        self.wlock = threading.Lock()
+        self.closed = False
+        self._q = queue.Queue()
+        self._writer = threading.Thread(target=self._write_loop, daemon=True, name="kv-conn-writer")
+        self._writer.start()
+
+    def send(self, obj):
+        if self.closed:
+            return
+        if self._q.qsize() > self.MAX_BACKLOG:
+            logger.warning("connection %d does not read its messages (%d queued): dropping it", self.cid, self._q.qsize())
+            self.close()
+            return
+        self._q.put(msgpack.packb(obj, use_bin_type=True))
+
+    def _write_loop(self):
+        while True:
+            data = self._q.get()
+            if data is None:
+                return
+            try:
+                self.sock.sendall(_HDR.pack(len(data)) + data)
+            except OSError:
+                self.closed = True
+                return
+
+    def close(self):
+        if not self.closed:
+            self.closed = True
+            try:
+                self.sock.shutdown(socket.SHUT_RDWR)      # wakes the reader (and a writer blocked in sendall)
+            except OSError:
+                pass
+        self._q.put(None)
 
 
 class _Handler(socketserver.BaseRequestHandler):
@@ -316,11 +351,14 @@ class _Handler(socketserver.BaseRequestHandler):
                 except Exception as e:  # noqa: BLE001 - errors travel back to the client
                     resp = {"ok": False, "error": "%s: %s" % (type(e).__name__, e)}
                 resp["id"] = req.get("id")
-                send_msg(self.request, resp, conn.wlock)
+                conn.send(resp)
+                if conn.closed:
+                    break
         except OSError:
             pass
         finally:
             state.drop_conn(conn.cid)
+            conn.close()
 
 
 class _Server(socketserver.ThreadingTCPServer):

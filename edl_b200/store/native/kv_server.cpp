@@ -292,8 +292,16 @@ Value kv_wire(const std::string& key, const KeyValue& kv) {
   return w;
 }
 
+constexpr size_t kMaxBacklogBytes = 64u << 20;   // a client that does not read its messages is dropped, not buffered forever
+
 void queue_msg(Conn* c, const Value& msg) {
   if (c->dead) return;
+  if (c->out.size() - c->out_off > kMaxBacklogBytes) {
+    c->dead = true;            // it reconnects and re-watches from its last seen revision
+    c->out.clear();
+    c->out_off = 0;
+    return;
+  }
   std::string body;
   encode(msg, body);
   put_be(c->out, body.size(), 4);

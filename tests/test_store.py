@@ -211,3 +211,29 @@ def test_rejected_request_does_not_reconnect_or_duplicate_the_next_one(kv_server
     _, meta = c.get("/n")
     assert meta["version"] == 21
     c.close()
+
+
+def test_a_watcher_that_never_reads_cannot_stall_the_store(kv_server):
+    """Head-of-line blocking: a client subscribes to a prefix and then stops reading its socket (paused process, dead
+    network path).  Other clients' writes must keep their latency; the store buffers for the slow one (and eventually
+    drops it) instead of blocking under its lock."""
+    import socket
+    import struct
+
+    import msgpack
+
+    host, port = kv_server.endpoint.rsplit(":", 1)
+    stuck = socket.create_connection((host, int(port)))
+    stuck.setsockopt(socket.SOL_SOCKET, socket.SO_RCVBUF, 4096)
+    body = msgpack.packb({"method": "watch", "watch_id": 1, "key": "/hol/", "start_revision": 0, "id": 1}, use_bin_type=True)
+    stuck.sendall(struct.pack("!I", len(body)) + body)          # ... and never recv()
+    c = KVClient(kv_server.endpoint)
+    payload = b"x" * 65536
+    t0 = time.time()
+    for i in range(400):                                        # 26 MB of events for the watcher that is not listening
+        c.put("/hol/%d" % (i % 8), payload)
+    dt = time.time() - t0
+    assert dt < 20, "writes stalled behind a watcher that does not read (%.1fs)" % dt
+    assert c.get("/hol/3")[0] == payload
+    c.close()
+    stuck.close()
