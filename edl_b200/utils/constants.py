@@ -29,6 +29,8 @@ POLL_INTERVAL = _f("EDL_POLL_INTERVAL", 3)          # generator / watcher / lead
 BARRIER_TIMEOUT = _f("EDL_BARRIER_TIMEOUT", 600)
 RESCALE_BARRIER_TIMEOUT = _f("EDL_RESCALE_BARRIER_TIMEOUT", 60)
 KILL_GRACE = _f("EDL_KILL_GRACE", 3)
+# seconds a launcher waits, after one of its trainers died, for the membership to change before it declares the job failed
+COLLATERAL_GRACE = _f("EDL_COLLATERAL_GRACE", ETCD_TTL + 3 * POLL_INTERVAL + 1)
 # seconds a SIGTERMed pod waits for the job to re-plan without it (k8s default grace period: 30 s)
 LEAVE_GRACE = _f("EDL_LEAVE_GRACE", 25)
 INPLACE_ACK_TIMEOUT = _f("EDL_INPLACE_ACK_TIMEOUT", 60)   # s a launcher waits for its trainers to enter the new stage in place

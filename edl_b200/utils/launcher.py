@@ -129,11 +129,23 @@ class Launcher:
         while True:
             self._publish()
             alive, failed = train_process.watch(self._procs)
+            collateral = False
             if failed is not None:
+                # A trainer that dies because a PEER pod died (its collective raised: gloo resets the connection at
+                # once, NCCL after its watchdog) is collateral damage of a membership change, not a job failure: give
+                # the store the time it needs to notice the dead pod (lease expiry + a generator round); if the
+                # cluster changes, fall through to the rescale path below, which restarts this pod's trainers.
                 logger.error("a trainer exited with code %s", failed)
-                train_process.terminate(self._procs)
-                return False
-            if not alive:
+                grace = constants.COLLATERAL_GRACE
+                deadline = time.time() + grace
+                while time.time() < deadline and not self._watcher.changed and self._leaving_since is None:
+                    time.sleep(min(poll, 0.2))
+                if not self._watcher.changed:
+                    train_process.terminate(self._procs)
+                    return False
+                logger.warning("... while the membership changed: treating the exit as collateral, restarting trainers")
+                collateral = True
+            if not alive and not collateral:
                 logger.info("all trainers of pod %s finished", self._pod.id)
                 return True
             if self._leave and self._leaving_since is None:

@@ -20,13 +20,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TRAIN = os.path.join(ROOT, "examples", "fit_a_line", "train.py")
 
 
-def _launch(endpoint, job, log_dir, report, ckpt, epochs):
+def _launch(endpoint, job, log_dir, report, ckpt, epochs, mode="inplace"):
     env = dict(os.environ)
     env.update({"PYTHONPATH": ROOT, "CUDA_VISIBLE_DEVICES": "", "PADDLE_RUNNING_PLATFORM": "", "EDL_POD_IP": "127.0.0.1",
                 "FIT_REPORT_DIR": report, "EDL_INPLACE_CHECK_EVERY": "3", "EDL_INPLACE_ACK_TIMEOUT": "40"})
     cmd = [sys.executable, "-u", "-m", "edl_b200.collective.launch", "--nodes_range", "1:2", "--nproc_per_node", "1",
            "--etcd_endpoints", endpoint, "--job_id", job, "--log_dir", log_dir, "--log_level", "10",
-           "--hdfs_path", ckpt, "--rescale_mode", "inplace",
+           "--hdfs_path", ckpt, "--rescale_mode", mode,
            TRAIN, "--epochs", str(epochs), "--epoch_sleep", "0.05", "--ckpt", ckpt]
     return subprocess.Popen(cmd, env=env, stdout=open(log_dir + ".launcher.log", "w"), stderr=subprocess.STDOUT,
                             start_new_session=True)
@@ -326,6 +326,59 @@ def test_elastic_reader_consumes_every_record_once_across_an_inplace_join(kv_ser
             by_pid.setdefault(r["pid"], set()).add(r["world"])
         assert len(by_pid) == 2 and any(w == {1, 2} for w in by_pid.values()), by_pid   # A read at world 1 AND 2: same process
         assert "reader demo rescaled in place: 1 -> 2" in (tmp_path / "logA" / "workerlog.0").read_text()
+    finally:
+        for p in (a, b):
+            if p is not None and p.poll() is None:
+                os.killpg(os.getpgid(p.pid), 9)
+
+
+@pytest.mark.slow
+def test_restart_mode_survives_a_hard_pod_death(kv_server, tmp_path):
+    """Stop-resume mode, pod B SIGKILLed: A's trainer dies of the broken collective (gloo) BEFORE the store has noticed
+    the dead pod.  The launcher treats a trainer exit that coincides with a membership change as collateral damage,
+    restarts its trainers for the smaller stage and the job still succeeds (it used to be declared FAILED)."""
+    import psutil
+
+    job = "collateral_" + uuid.uuid4().hex[:6]
+    report, ckpt = str(tmp_path / "report"), str(tmp_path / "ckpt")
+
+    def epochs():
+        p = os.path.join(report, "epochs.jsonl")
+        return [json.loads(l) for l in open(p)] if os.path.exists(p) else []
+
+    def wait_world(w, timeout, min_new=3):
+        n0 = len(epochs())
+        deadline = time.time() + timeout
+        while time.time() < deadline:
+            e = epochs()
+            if len(e) >= n0 + min_new and all(x["world"] == w for x in e[-min_new:]):
+                return e
+            time.sleep(0.2)
+        raise AssertionError("world never became %d: %s\n%s" % (w, epochs()[-4:],
+                                                                  open(str(tmp_path / "logA.launcher.log")).read()[-3000:]))
+
+    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 150, mode="restart")
+    b = None
+    try:
+        pid1 = wait_world(1, 60)[-1]["pid"]
+        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 150, mode="restart")
+        wait_world(2, 90)
+        for v in [psutil.Process(b.pid)] + psutil.Process(b.pid).children(recursive=True):
+            try:
+                v.kill()
+            except psutil.NoSuchProcess:
+                pass
+        e = wait_world(1, 90)
+        assert e[-1]["pid"] != pid1                              # restart mode: a NEW trainer process carries on
+        assert a.wait(timeout=120) == 0
+        log_a = open(str(tmp_path / "logA.launcher.log")).read()
+        assert "treating the exit as collateral" in log_a
+        etcd = EtcdClient([kv_server.endpoint], root=job)
+        etcd.init()
+        assert edl_status.load_job_status_from_etcd(etcd) == edl_status.Status.SUCCEED
+        etcd.close()
+        ep = [x["epoch"] for x in epochs()]
+        assert ep == sorted(ep), ep
     finally:
         for p in (a, b):
             if p is not None and p.poll() is None:

@@ -29,7 +29,7 @@ from edl_b200.store import KVServer, NativeKVServer  # noqa: E402
 from edl_b200.utils import leader_pod, pod_server_client  # noqa: E402
 
 
-CFG = {"trainer": "fit", "gpus_per_pod": 0}
+CFG = {"trainer": "fit", "gpus_per_pod": 0, "leave": "scale_in"}
 RESNET = os.path.join(ROOT, "examples", "collective", "resnet50", "train.py")
 
 
@@ -93,15 +93,26 @@ def run(mode, server_cls):
             survivor_kept = e[-1]["pid"] in pids_before
             etcd = EtcdClient([srv.endpoint], root=job)
             etcd.init()
-            cli = pod_server_client.Client(leader_pod.load_from_etcd(etcd, timeout=5).endpoint)
             t_leave = time.time()
-            cli.scale_in(1)
-            cli.close()
+            if CFG["leave"] == "scale_in":
+                cli = pod_server_client.Client(leader_pod.load_from_etcd(etcd, timeout=5).endpoint)
+                cli.scale_in(1)
+                cli.close()
+            elif CFG["leave"] == "sigterm":
+                b.terminate()
+            else:
+                import psutil
+
+                for q in [psutil.Process(b.pid)] + psutil.Process(b.pid).children(recursive=True):
+                    try:
+                        q.kill()
+                    except psutil.NoSuchProcess:
+                        pass
             e = wait_world(w1, timeout=300)
             leave = min(x["t"] for x in e if x["world"] == w1 and x["t"] > t_leave) - t_leave
             leave_stall = stall(e, t_leave)
             etcd.close()
-            return {"mode": mode, "store": server_cls.__name__, "join_s": join, "join_stall_s": join_stall,
+            return {"mode": mode, "leave": CFG["leave"], "store": server_cls.__name__, "join_s": join, "join_stall_s": join_stall,
                     "leave_s": leave, "leave_stall_s": leave_stall, "survivor_process_kept": survivor_kept,
                     "steady_epoch_s": sorted(y["t"] - x["t"] for x, y in zip(e[-5:-1], e[-4:]))[1]}
         finally:
@@ -126,9 +137,12 @@ if __name__ == "__main__":
     ap.add_argument("--native-store", action="store_true")
     ap.add_argument("--trainer", default="fit", choices=["fit", "resnet"])
     ap.add_argument("--gpus-per-pod", type=int, default=0, help="GPUs (= trainers) per pod; 0 = CPU / gloo")
+    ap.add_argument("--leave", default="scale_in", choices=["scale_in", "sigterm", "kill"],
+                    help="how pod B leaves: the leader's ScaleIn RPC, SIGTERM to its launcher (graceful leave), or SIGKILL "
+                         "of launcher and trainers (hot recovery in place / restart of everybody in restart mode)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
-    CFG.update(trainer=args.trainer, gpus_per_pod=args.gpus_per_pod)
+    CFG.update(trainer=args.trainer, gpus_per_pod=args.gpus_per_pod, leave=args.leave)
     cls = NativeKVServer if args.native_store else KVServer
     res = [run("restart", cls), run("inplace", cls)]
     for r in res:
