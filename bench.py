@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--fuse-bn-bwd", type=int, default=0, choices=[0, 1, 2],
                     help="A/B (experimental): BatchNorm-backward reduction inside the dgrad epilogues; 1 = shuffle "
                          "version of round 1, 2 = column-loop version (EDL_FUSE_BN_BWD=1 + EDL_BNR_MODE)")
+    ap.add_argument("--own-stem1", action="store_true", help="A/B (experimental): direct kernel for the first stem convolution")
     ap.add_argument("--conv3-s2", action="store_true",
                     help="A/B (experimental): stride-2 3x3 forward convolutions on the tcgen05 kernel (student and teacher)")
     ap.add_argument("--pdl", action="store_true", help="A/B (experimental): programmatic dependent launch of the hot kernels")
@@ -265,6 +266,8 @@ def main():
     if args.fuse_bn_bwd:
         os.environ["EDL_FUSE_BN_BWD"] = "1"        # read when edl_b200.ops.gemm is imported
         os.environ["EDL_BNR_MODE"] = str(args.fuse_bn_bwd)   # read when the extension is loaded
+    if args.own_stem1:
+        os.environ["EDL_OWN_STEM1"] = "1"          # read when edl_b200.ops.gemm is imported
     if args.conv3_s2:
         os.environ["EDL_CONV3_S2"] = "1"           # read when edl_b200.ops.gemm is imported
     if args.teacher_fuse_res:
@@ -448,7 +451,7 @@ def main():
                        "parallelism": "dp%d" % world, "optimizer": "SGD-momentum 0.9 wd 1e-4 (fused, fp32 master)",
                        "loss": "soft-label cross-entropy (teacher-score shaped targets)",
                        "cuda_graph": not args.no_graph, "conv_impl": args.conv_impl,
-                       "pdl": bool(args.pdl), "own_wgrad3": bool(args.own_wgrad3), "conv3_s2": bool(args.conv3_s2),
+                       "pdl": bool(args.pdl), "own_wgrad3": bool(args.own_wgrad3), "conv3_s2": bool(args.conv3_s2), "own_stem1": bool(args.own_stem1),
                        "fuse_bn_bwd": args.fuse_bn_bwd,
                        "allreduce": getattr(getattr(trainer, "dp", None), "algo_pref", "nccl"),
                        "l2": "per-step working set (~GBs of activations) >> 126 MB L2, no explicit flush",

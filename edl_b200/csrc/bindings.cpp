@@ -336,6 +336,26 @@ void rope(const Tensor& x, const Tensor& cosv, const Tensor& sinv, Tensor& y, bo
             x.size(2), inverse, cur_stream());
 }
 
+// y [N,32,Ho,Wo] = conv3x3/s2/p1(x [N,3,H,W], w KRSC [32,3,3,3]), channels_last bf16; stats fp32 [64] += (sum, sum^2) of y
+void stem_conv3x3s2(const Tensor& x, const Tensor& w, Tensor& y, const c10::optional<Tensor>& stats) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.size(1) == 3 && x.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast) && y.is_contiguous(at::MemoryFormat::ChannelsLast));
+  TORCH_CHECK(w.scalar_type() == at::kBFloat16 && w.is_contiguous() && w.dim() == 4 && w.size(0) == 32 && w.size(1) == 3 &&
+              w.size(2) == 3 && w.size(3) == 3, "stem weight must be KRSC [32,3,3,3] bf16");
+  const int64_t H = x.size(2), W = x.size(3);
+  TORCH_CHECK(y.scalar_type() == at::kBFloat16 && y.size(0) == x.size(0) && y.size(1) == 32 &&
+              y.size(2) == (H - 1) / 2 + 1 && y.size(3) == (W - 1) / 2 + 1);
+  float* st = nullptr;
+  if (stats.has_value() && stats->defined()) {
+    TORCH_CHECK(stats->scalar_type() == at::kFloat && stats->numel() >= 64 && stats->is_contiguous() &&
+                reinterpret_cast<uintptr_t>(stats->data_ptr()) % 16 == 0);
+    st = stats->data_ptr<float>();
+  }
+  c10::cuda::CUDAGuard guard(x.device());
+  edl::stem_conv3x3s2(x.data_ptr(), w.data_ptr(), y.data_ptr(), st, (int)x.size(0), (int)H, (int)W,
+                      at::cuda::getCurrentCUDAStream().stream());
+}
+
 void embedding_bag_fwd(const Tensor& table, const Tensor& ids, Tensor& out) {
   TORCH_CHECK(table.is_cuda() && table.is_contiguous() && ids.is_contiguous() && ids.scalar_type() == at::kLong);
   c10::cuda::CUDAGuard g(table.device());
@@ -443,6 +463,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("comm_error_word_offset", &edl::comm_error_word_offset);
   m.def("rope", &rope);
   m.def("embedding_bag_fwd", &embedding_bag_fwd);
+  m.def("stem_conv3x3s2", &stem_conv3x3s2);
   m.def("embedding_bag_bwd", &embedding_bag_bwd);
   m.def("normalize_u8", &normalize_u8);
   m.def("peer_ship", &peer_ship);

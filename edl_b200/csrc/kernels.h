@@ -113,6 +113,9 @@ void comm_allgather_scalars(const CommHandles& h, const float* in, float* out, i
 // ---- misc.cu ----
 void rope(const void* x, const float* cosv, const float* sinv, void* y, int64_t T, int H, int D,
           bool inverse, cudaStream_t s);
+// ---- stem.cu: first stem convolution (3 -> 32, 3x3 / stride 2 / pad 1, NHWC bf16) + BN statistics of its output ----
+void stem_conv3x3s2(const void* x, const void* w, void* y, float* stats, int N, int H, int W, cudaStream_t s);
+
 void embedding_bag_fwd(const void* table, bool bf16, const int64_t* ids, void* out, int64_t B, int L,
                        int D, cudaStream_t s);
 void embedding_bag_bwd(const void* dout, bool bf16, const int64_t* ids, float* dtable, int64_t B, int L,

@@ -58,6 +58,14 @@ class ConvBNAct(nn.Module):
                 stats = self.fwd_stats if self.fwd_stats is not None else torch.zeros(
                     2 * self.cout, device=x.device, dtype=torch.float32)
             return ops.conv3x3(x, self.weight, stats), stats
+        if (self.k == 3 and self.stride == 2 and self.cin == 3 and self.cout == 32 and self.impl != "cudnn"
+                and ops.gemm.OWN_STEM1 and ops.stem_conv_supported(x, self.weight)):
+            # experimental (EDL_OWN_STEM1=1): direct kernel for the K = 27 stem convolution, statistics fused
+            stats = None
+            if want_stats:
+                stats = self.fwd_stats if self.fwd_stats is not None else torch.zeros(
+                    2 * self.cout, device=x.device, dtype=torch.float32)
+            return ops.stem_conv(x, self.weight, stats), stats
         if (self.k == 3 and self.stride == 2 and self.groups == 1 and self.impl != "cudnn" and self.own_conv3
                 and ops.gemm.CONV3_S2 and ops.conv3x3_s2_supported(x, self.weight)):
             # experimental (EDL_CONV3_S2=1): stride-2 fprop on the tcgen05 kernel, statistics in its epilogue

@@ -551,6 +551,48 @@ def conv3x3_s2(x, weight_krsc, stats: Optional[torch.Tensor] = None):
     return _Conv3x3S2Fn.apply(x, weight_krsc, stats, sink, ready)
 
 
+# EXPERIMENTAL until validated on a GPU: EDL_OWN_STEM1=1 runs the first stem convolution (3 -> 32 channels, 3x3 /
+# stride 2) on the direct kernel of csrc/stem.cu with the BatchNorm statistics fused in (the library kernel takes 74 us
+# for what is ~5 us of memory traffic, plus a separate statistics pass).
+OWN_STEM1 = __import__("os").environ.get("EDL_OWN_STEM1", "0") == "1"
+
+
+def stem_conv_supported(x, weight_krsc) -> bool:
+    return (x.is_cuda and x.dtype == torch.bfloat16 and weight_krsc.dtype == torch.bfloat16 and x.dim() == 4
+            and x.shape[1] == 3 and tuple(weight_krsc.shape) == (32, 3, 3, 3))
+
+
+class _StemConvFn(torch.autograd.Function):
+    """conv3x3 / stride 2 / pad 1, 3 -> 32 channels: forward on the direct kernel (+ BN statistics); the weight gradient
+    (and, if anybody asks for it, the input gradient) on the library kernels like every other k x k convolution."""
+
+    @staticmethod
+    def forward(ctx, x, w, stats, sink, ready):
+        from . import native, count_launch
+
+        x = _cl(x)
+        n, _, h, wd = x.shape
+        y = torch.empty((n, 32, (h - 1) // 2 + 1, (wd - 1) // 2 + 1), device=x.device, dtype=x.dtype,
+                        memory_format=torch.channels_last)
+        native().stem_conv3x3s2(x, w, y, stats)
+        count_launch()
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (2, 1, 1)
+        ctx.sink, ctx.ready = sink, ready
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx, dw = _ConvLibFn.backward(ctx, _cl(dy))[:2]
+        return dx, dw, None, None, None
+
+
+def stem_conv(x, weight_krsc, stats: Optional[torch.Tensor] = None):
+    sink = getattr(weight_krsc, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
+    ready = getattr(weight_krsc, "_edl_grad_ready", None) if sink is not None else None
+    return _StemConvFn.apply(x, weight_krsc, stats, sink, ready)
+
+
 def conv3x3_infer_supported(x, weight_krsc, groups=1) -> bool:
     from . import native
 

@@ -428,3 +428,23 @@ def test_fused_bn_backward_matches_unfused_at_model_level(monkeypatch, mode):
     assert n1 < n0 - 20, "the fused path should launch ~40 kernels fewer (%d vs %d)" % (n1, n0)
     worst = max((_rel(g1[k], g0[k]), k) for k in g0)
     assert worst[0] < 3e-2, worst
+
+
+@pytest.mark.parametrize("n,h,w", [(4, 224, 224), (3, 64, 96), (2, 33, 47)])
+def test_stem_conv_direct_kernel(n, h, w):
+    """EDL_OWN_STEM1: 3 -> 32 channel 3x3 / stride 2 stem convolution on the direct kernel with fused BN statistics."""
+    torch.manual_seed(0)
+    x = torch.randn(n, 3, h, w, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(32, 3, 3, 3, device=DEV) * 0.2).bfloat16().requires_grad_(True)
+    stats = torch.zeros(64, device=DEV)
+    y = ops.stem_conv(x, wt, stats)
+    ref = F.conv2d(x.float(), wt.detach().permute(0, 3, 1, 2).float(), None, 2, 1)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert _rel(y, ref) < 1e-2
+    yf = y.float()
+    assert _rel(stats[:32], yf.sum((0, 2, 3))) < 2e-3 and _rel(stats[32:], (yf * yf).sum((0, 2, 3))) < 2e-3
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    wr = wt.detach().float().requires_grad_(True)
+    F.conv2d(x.float(), wr.permute(0, 3, 1, 2), None, 2, 1).backward(dy.float())
+    assert _rel(wt.grad, wr.grad) < 1e-2
