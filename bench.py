@@ -451,7 +451,8 @@ def main():
                        "parallelism": "dp%d" % world, "optimizer": "SGD-momentum 0.9 wd 1e-4 (fused, fp32 master)",
                        "loss": "soft-label cross-entropy (teacher-score shaped targets)",
                        "cuda_graph": not args.no_graph, "conv_impl": args.conv_impl,
-                       "pdl": bool(args.pdl), "own_wgrad3": bool(args.own_wgrad3), "conv3_s2": bool(args.conv3_s2), "own_stem1": bool(args.own_stem1),
+                       "pdl": bool(args.pdl), "own_wgrad3": bool(args.own_wgrad3), "conv3_s2": bool(args.conv3_s2),
+                       "own_stem1": bool(args.own_stem1),
                        "fuse_bn_bwd": args.fuse_bn_bwd,
                        "allreduce": getattr(getattr(trainer, "dp", None), "algo_pref", "nccl"),
                        "l2": "per-step working set (~GBs of activations) >> 126 MB L2, no explicit flush",
