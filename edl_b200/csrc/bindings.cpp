@@ -429,6 +429,7 @@ void wait_flag_async(const Tensor& flag, const c10::optional<Tensor>& seq, int64
 }  // namespace
 
 void register_gemm_bindings(pybind11::module_& m);  // gemm_bindings.cpp
+void register_jpeg_bindings(pybind11::module_& m);  // jpeg_decode.cpp
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "edl_b200 sm_100a kernels";
@@ -472,4 +473,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("slot_ack", &slot_ack);
   m.def("wait_flag_async", &wait_flag_async);
   register_gemm_bindings(m);
+  register_jpeg_bindings(m);
 }

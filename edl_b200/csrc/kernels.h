@@ -123,6 +123,16 @@ void embedding_bag_bwd(const void* dout, bool bf16, const int64_t* ids, float* d
 void normalize_u8(const uint8_t* x, void* y, int64_t N, int H, int W, const float* mean,
                   const float* stdv, const uint8_t* flip, cudaStream_t s);
 
+// ---- augment.cu: random-resized crop + flip + normalise from decoded uint8 RGB images of different sizes ----
+struct AugmentItem {   // one per output image; 32 bytes = 8 x int32 (the Python side fills an int32 [N, 8] tensor)
+  int64_t offset;      // byte offset of the decoded image (interleaved RGB) inside the pool buffer
+  int pitch;           // bytes per source row
+  int y, x, ch, cw;    // crop box inside the source image
+  int flip;            // mirror horizontally
+};
+void crop_resize_normalize(const uint8_t* pool, const AugmentItem* items, void* y, int N, int S, const float* mean,
+                           const float* stdv, cudaStream_t s);
+
 // ---- logit_ship.cu (teacher -> student over NVSwitch peer memory, fused with the loss) ----
 void peer_ship(const void* src, void* dst_peer, int64_t nbytes, void* flag_peer, const void* seq_ptr,
                uint32_t seq_imm, void* done_counter, cudaStream_t s);

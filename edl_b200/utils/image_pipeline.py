@@ -7,6 +7,10 @@ crop and resize straight into a pinned staging batch (a quarter of the fp32 byte
 mask travels as one byte per image, and the fused ``normalize_u8`` kernel produces the bf16 channels_last
 tensor on the device (``ops/misc.py``).
 
+``ImageBatchLoader(decode="nvjpeg")`` is the DALI-style path (example/distill/resnet/dali.py:60-106): worker threads
+only read file bytes, ``GpuJpegAugmenter`` decodes the batch on the GPU (nvJPEG, ``csrc/jpeg_decode.cpp``) and ONE kernel
+does random-resized crop + flip + normalisation (``csrc/augment.cu``); pixels never visit the host.
+
 File list format = the reference's ``train_list.txt`` / ``val_list.txt``: one ``relative/path.jpg label`` per line.
 Elastic sharding: ``rank`` / ``world`` select every world-th line after a per-epoch shuffle with a shared seed.
 """
@@ -80,7 +84,10 @@ class ImageBatchLoader:
 
     def __init__(self, samples: List[Tuple[str, int]], batch_size: int, size: int = 224, train: bool = True,
                  rank: int = 0, world: int = 1, seed: int = 0, threads: int = 8, prefetch: int = 4,
-                 drop_last: bool = True, pin: Optional[bool] = None):
+                 drop_last: bool = True, pin: Optional[bool] = None, decode: str = "cpu"):
+        assert decode in ("cpu", "nvjpeg"), decode
+        self.decode = decode
+        self._augmenters = {}
         self.samples, self.bs, self.size, self.train = samples, batch_size, size, train
         self.rank, self.world, self.seed = rank, world, seed
         self.threads, self.prefetch, self.drop_last = max(1, threads), max(1, prefetch), drop_last
@@ -122,8 +129,12 @@ class ImageBatchLoader:
                 b, j, si, buf = item
                 path, _ = self.samples[si]
                 try:
-                    img = decode_train(path, self.size, rng) if self.train else decode_eval(path, self.size)
-                    buf[j].copy_(torch.from_numpy(np.ascontiguousarray(img)))
+                    if self.decode == "nvjpeg":                      # bytes only: the GPU decodes and augments
+                        with open(path, "rb") as fh:
+                            buf[j] = fh.read()
+                    else:
+                        img = decode_train(path, self.size, rng) if self.train else decode_eval(path, self.size)
+                        buf[j].copy_(torch.from_numpy(np.ascontiguousarray(img)))
                     err = None
                 except Exception as e:  # noqa: BLE001
                     err = e
@@ -136,7 +147,7 @@ class ImageBatchLoader:
             try:
                 for b in range(nb):
                     ids = idx[b * self.bs:(b + 1) * self.bs]
-                    buf = alloc(len(ids))
+                    buf = [None] * len(ids) if self.decode == "nvjpeg" else alloc(len(ids))
                     with lock:
                         results[b] = (0, None)
                     for j, si in enumerate(ids):
@@ -151,7 +162,10 @@ class ImageBatchLoader:
                     labels = torch.tensor([self.samples[si][1] for si in ids], dtype=torch.int64)
                     flips = ((torch.rand(len(ids)) < 0.5).to(torch.uint8) if self.train
                              else torch.zeros(len(ids), dtype=torch.uint8))
-                    out_q.put((buf, labels, flips))
+                    if self.decode == "nvjpeg":
+                        out_q.put(JpegBatch(self, buf, labels, self.seed * 7919 + self.epoch * 104729 + self.rank * 31 + b))
+                    else:
+                        out_q.put((buf, labels, flips))
                 out_q.put(None)
             except Exception as e:  # noqa: BLE001
                 out_q.put(e)
@@ -175,10 +189,134 @@ class ImageBatchLoader:
                 work_q.put(None)
 
 
+    def augmenter(self, device) -> "GpuJpegAugmenter":
+        key = str(device)
+        if key not in self._augmenters:
+            self._augmenters[key] = GpuJpegAugmenter(device, self.size)
+        return self._augmenters[key]
+
+
+class JpegBatch:
+    """What ``ImageBatchLoader(decode="nvjpeg")`` yields: undecoded files + labels; ``to_device_batch`` turns it into
+    the device batch.  ``seed`` makes the crops / flips of a batch reproducible whatever thread consumes it."""
+
+    def __init__(self, loader: ImageBatchLoader, blobs: List[bytes], labels: torch.Tensor, seed: int):
+        self.loader, self.blobs, self.labels, self.seed = loader, blobs, labels, seed
+
+    def __len__(self):
+        return len(self.blobs)
+
+
+def eval_crop_box(h: int, w: int, size: int = 224, resize_short: int = 256):
+    """The centre crop of ``decode_eval`` expressed in SOURCE pixels: resizing the short side to ``resize_short`` and
+    cutting ``size`` x ``size`` out of the middle = resampling the centred square of side size/resize_short * short."""
+    side = max(1, min(min(h, w), int(round(min(h, w) * size / float(resize_short)))))
+    return (h - side) // 2, (w - side) // 2, side, side
+
+
+def augment_reference(img: np.ndarray, box, flip: bool, size: int, mean=None, std=None) -> np.ndarray:
+    """NumPy model of ``csrc/augment.cu`` for ONE image (uint8 [H, W, 3] -> float32 [size, size, 3]): bilinear
+    resample of the crop box with cv2.INTER_LINEAR's geometry (half-pixel centres, edge clamp), mirror, normalise."""
+    from ..ops.misc import IMAGENET_MEAN, IMAGENET_STD
+
+    mean = IMAGENET_MEAN if mean is None else mean
+    std = IMAGENET_STD if std is None else std
+    y, x, ch, cw = box
+    crop = img[y:y + ch, x:x + cw].astype(np.float32)
+
+    def taps(n_src, n_dst, mirror):
+        o = np.arange(n_dst, dtype=np.float32)
+        if mirror:
+            o = n_dst - 1 - o
+        f = (o + 0.5) * (np.float32(n_src) / np.float32(n_dst)) - 0.5
+        i0 = np.floor(f).astype(np.int64)
+        a = (f - i0).astype(np.float32)
+        a[i0 < 0] = 0.0
+        i0 = np.clip(i0, 0, n_src - 1)
+        i1 = np.clip(i0 + 1, 0, n_src - 1)
+        return i0, i1, a
+
+    y0, y1, ay = taps(ch, size, False)
+    x0, x1, ax = taps(cw, size, flip)
+    ay, ax = ay[:, None, None], ax[None, :, None]
+    out = ((1 - ax) * (1 - ay) * crop[y0][:, x0] + ax * (1 - ay) * crop[y0][:, x1]
+           + (1 - ax) * ay * crop[y1][:, x0] + ax * ay * crop[y1][:, x1])
+    return ((out / 255.0 - np.asarray(mean, np.float32)) / np.asarray(std, np.float32)).astype(np.float32)
+
+
+class GpuJpegAugmenter:
+    """JPEG files (bytes) -> normalised bf16 channels_last batch on ``device`` without a host round trip:
+    nvJPEG batched decode into one pooled uint8 buffer (images keep their own sizes), then the fused
+    crop / resize / flip / normalise kernel.  Images nvJPEG cannot take (CMYK, corrupt headers) are decoded with OpenCV
+    and uploaded into the same pool.  All GPU work is queued on the caller's current stream."""
+
+    ALIGN = 256
+
+    def __init__(self, device, size: int = 224, backend: str = "default", cpu_threads: int = 4, mean=None, std=None):
+        from .. import ops
+        from ..ops.misc import IMAGENET_MEAN, IMAGENET_STD
+
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("GpuJpegAugmenter needs a CUDA device (use decode='cpu' on hosts without one)")
+        self.size = size
+        self.mean, self.std = list(mean or IMAGENET_MEAN), list(std or IMAGENET_STD)
+        self._native = ops.native()
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._dec = self._native.JpegDecoder(index, backend, cpu_threads)
+        self._pool = torch.empty(0, dtype=torch.uint8, device=self.device)
+        self._items_host = None
+
+    def plan(self, dims, rng: random.Random, train: bool):
+        """Crop boxes, flips and pool offsets for images of the given (h, w): int32 [N, 8] rows of ``AugmentItem``."""
+        items = np.zeros((len(dims), 8), dtype=np.int32)
+        offs = items.view(np.int64)                            # [N, 4] view (little endian)
+        off = 0
+        for i, (h, w) in enumerate(dims):
+            y, x, ch, cw = _random_resized_crop_box(h, w, rng) if train else eval_crop_box(h, w, self.size)
+            flip = 1 if (train and rng.random() < 0.5) else 0
+            items[i, 2:] = (3 * w, y, x, ch, cw, flip)
+            offs[i, 0] = off                                   # int64 offset = the first two int32 words of the row
+            off += (h * 3 * w + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        return items, off
+
+    def __call__(self, blobs: List[bytes], rng: Optional[random.Random] = None, train: bool = True) -> torch.Tensor:
+        from .. import ops
+
+        rng = rng or random.Random()
+        info = self._dec.image_info(blobs)
+        dims = [(h, w) for h, w, _ in info]
+        items, total = self.plan(dims, rng, train)
+        if self._pool.numel() < total:
+            self._pool = torch.empty(int(total * 1.25), dtype=torch.uint8, device=self.device)
+        offsets = [int(v) for v in items.view(np.int64)[:, 0]]
+        gpu = [i for i, (_, _, c) in enumerate(info) if c in (1, 3)]
+        with torch.cuda.device(self.device):
+            if gpu:
+                self._dec.decode([blobs[i] for i in gpu], self._pool, [offsets[i] for i in gpu],
+                                 [3 * dims[i][1] for i in gpu], [dims[i][0] for i in gpu])
+            for i in set(range(len(blobs))) - set(gpu):              # CMYK & co: CPU decode, same pool
+                import cv2
+
+                img = cv2.cvtColor(cv2.imdecode(np.frombuffer(blobs[i], np.uint8), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+                flat = torch.from_numpy(np.ascontiguousarray(img)).reshape(-1)
+                self._pool[offsets[i]:offsets[i] + flat.numel()].copy_(flat)
+            y = torch.empty((len(blobs), self.size, self.size, 3), dtype=torch.bfloat16, device=self.device)
+            self._items_host = torch.from_numpy(items).pin_memory()   # kept until the next call (async H2D source)
+            self._native.crop_resize_normalize(self._pool, self._items_host.to(self.device, non_blocking=True), y,
+                                               self.mean, self.std)
+            ops.count_launch()
+        return y.permute(0, 3, 1, 2)
+
+
 def to_device_batch(batch, device, dtype=torch.bfloat16):
-    """(uint8 NHWC pinned, labels, flips) -> (normalised channels_last images on ``device``, labels on ``device``)."""
+    """(uint8 NHWC pinned, labels, flips) -> (normalised channels_last images on ``device``, labels on ``device``);
+    a ``JpegBatch`` (``decode="nvjpeg"``) is decoded and augmented on the device instead."""
     from .. import ops
 
+    if isinstance(batch, JpegBatch):
+        x = batch.loader.augmenter(device)(batch.blobs, random.Random(batch.seed), batch.loader.train)
+        return (x.to(dtype) if x.dtype != dtype else x), batch.labels.to(device, non_blocking=True)
     img, labels, flips = batch
     x = ops.normalize_u8(img.to(device, non_blocking=True), flip=flips.to(device, non_blocking=True))
     return x.to(dtype) if x.dtype != dtype else x, labels.to(device, non_blocking=True)

@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--width_mult", type=float, default=1.0)
     ap.add_argument("--ckpt", default=os.environ.get("PADDLE_EDL_HDFS_PATH") or "./resnet_ckpt")
     ap.add_argument("--max_steps", type=int, default=0, help="stop an epoch early (smoke runs)")
+    ap.add_argument("--solo_step_sleep", type=float, default=0.0,
+                    help="elastic demos / tests: seconds to sleep per step while the job has ONE trainer, so that a "
+                         "second pod has time to join whatever the speed of the box")
     return ap.parse_args()
 
 
@@ -130,6 +133,8 @@ def main():
             it += 1
             seen += bs
             meter.step()
+            if args.solo_step_sleep and world == 1:
+                time.sleep(args.solo_step_sleep)
             if progress and rank == 0 and step % 5 == 0:
                 with open(progress, "a") as fh:       # machine-readable heartbeat (tools/bench_elastic_launch.py)
                     fh.write(json.dumps({"t": time.time(), "step": step, "epoch": epoch, "world": world,

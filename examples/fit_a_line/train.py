@@ -54,6 +54,8 @@ def main():
     ap.add_argument("--ckpt", type=str, default=os.environ.get("PADDLE_EDL_HDFS_PATH") or "./fit_a_line_ckpt")
     ap.add_argument("--epoch_sleep", type=float, default=0.0, help="slow epochs down (elastic demos)")
     ap.add_argument("--report", type=str, default=os.environ.get("FIT_REPORT_DIR", ""))
+    ap.add_argument("--finish_file", type=str, default=os.environ.get("FIT_FINISH_FILE", ""),
+                    help="stop at the first epoch end at which this file exists (--epochs stays the upper bound)")
     args = ap.parse_args()
 
     inplace = elastic.inplace_requested()
@@ -118,6 +120,7 @@ def main():
         perm = torch.randperm(n, generator=g)
         shard = perm[rank::world]
         switch = broken = False
+        stop = torch.zeros(1)
         try:
             for i in range(0, len(shard) - args.batch + 1, args.batch):
                 idx = shard[i:i + args.batch]
@@ -138,6 +141,10 @@ def main():
                     dist.all_reduce(loss)
                     loss /= world
                     dist.barrier()                         # everybody finished the epoch before it is checkpointed
+                if args.finish_file:                       # every rank must take the same decision
+                    stop.fill_(1.0 if os.path.exists(args.finish_file) else 0.0)
+                    if world > 1:
+                        dist.all_reduce(stop, op=dist.ReduceOp.MAX)
         except RuntimeError as e:                          # a peer died inside a collective (gloo raises)
             if not inplace:
                 raise
@@ -170,6 +177,8 @@ def main():
         if args.epoch_sleep:
             time.sleep(args.epoch_sleep)
         epoch += 1
+        if float(stop) > 0:
+            break
     if ctx is not None:
         ctx.close()
         return 0

@@ -448,3 +448,76 @@ def test_stem_conv_direct_kernel(n, h, w):
     wr = wt.detach().float().requires_grad_(True)
     F.conv2d(x.float(), wr.permute(0, 3, 1, 2), None, 2, 1).backward(dy.float())
     assert _rel(wt.grad, wr.grad) < 1e-2
+
+
+# ------------------------------------------------------------------ DALI-style input path (nvJPEG + fused augmentation)
+def _jpeg_blobs(sizes, seed=0, quality=95):
+    import cv2
+    import numpy as np
+
+    rng = np.random.RandomState(seed)
+    blobs, imgs = [], []
+    for h, w in sizes:
+        img = cv2.GaussianBlur(rng.randint(0, 256, (h, w, 3)).astype(np.uint8), (9, 9), 0)
+        ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, quality])
+        assert ok
+        blobs.append(enc.tobytes())
+        imgs.append(cv2.cvtColor(cv2.imdecode(enc, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB))
+    return blobs, imgs
+
+
+def test_crop_resize_normalize_kernel_matches_the_numpy_model():
+    import random
+
+    import numpy as np
+
+    from edl_b200.utils import image_pipeline as ip
+
+    sizes = [(375, 500), (64, 48), (600, 401), (224, 224), (33, 1000)]
+    rng = np.random.RandomState(1)
+    imgs = [rng.randint(0, 256, (h, w, 3)).astype(np.uint8) for h, w in sizes]
+    aug = ip.GpuJpegAugmenter.__new__(ip.GpuJpegAugmenter)
+    aug.size = 224
+    for train in (True, False):
+        items, total = aug.plan(sizes, random.Random(5), train)
+        pool = torch.zeros(total, dtype=torch.uint8, device=DEV)
+        for img, off in zip(imgs, items.view(np.int64)[:, 0]):
+            pool[int(off):int(off) + img.size] = torch.from_numpy(img.reshape(-1)).to(DEV)
+        y = torch.empty((len(sizes), 224, 224, 3), dtype=torch.bfloat16, device=DEV)
+        ops.native().crop_resize_normalize(pool, torch.from_numpy(items).to(DEV), y, [0.485, 0.456, 0.406],
+                                           [0.229, 0.224, 0.225])
+        for i, img in enumerate(imgs):
+            want = torch.from_numpy(ip.augment_reference(img, tuple(items[i, 3:7]), bool(items[i, 7]), 224))
+            assert (y[i].float().cpu() - want).abs().max().item() < 0.03, (train, i)      # bf16 output rounding
+
+
+@pytest.mark.parametrize("backend", ["default", "hardware"])
+def test_nvjpeg_batched_decode_and_fused_augmentation(backend):
+    import random
+
+    import numpy as np
+
+    from edl_b200.utils import image_pipeline as ip
+
+    sizes = [(375, 500), (64, 48), (480, 640), (224, 224), (301, 203), (500, 333)]
+    blobs, imgs = _jpeg_blobs(sizes)
+    try:
+        aug = ip.GpuJpegAugmenter(DEV, 224, backend=backend)
+    except RuntimeError as e:
+        if backend == "hardware":
+            pytest.skip("no NVJPG engine backend: %s" % e)
+        raise
+    assert [(h, w) for h, w, _ in aug._dec.image_info(blobs)] == sizes
+    x = aug(blobs, random.Random(11), train=True)
+    torch.cuda.synchronize()
+    assert x.shape == (6, 3, 224, 224) and x.dtype == torch.bfloat16 and bool(torch.isfinite(x.float()).all())
+    items, _ = aug.plan(sizes, random.Random(11), True)               # same seed => same boxes
+    for i, img in enumerate(imgs):
+        # decoded pixels: IDCT / chroma upsampling differ slightly between libjpeg-turbo and nvJPEG
+        off = int(items.view(np.int64)[i, 0])
+        got = aug._pool[off:off + img.size].view(img.shape).cpu().numpy().astype(np.int32)
+        assert np.abs(got - img.astype(np.int32)).mean() < 2.0, (i, np.abs(got - img.astype(np.int32)).mean())
+        want = torch.from_numpy(ip.augment_reference(img, tuple(items[i, 3:7]), bool(items[i, 7]), 224))
+        assert (x[i].permute(1, 2, 0).float().cpu() - want).abs().mean().item() < 0.05, i
+    x1 = aug(blobs[:1], random.Random(11), train=False)               # single-image path + eval crop
+    assert x1.shape == (1, 3, 224, 224)

@@ -59,3 +59,65 @@ def test_missing_file_raises(tmp_path):
     ld = ip.ImageBatchLoader([(str(tmp_path / "nope.jpg"), 0)] * 4, 4, size=16, train=False, threads=1, pin=False)
     with pytest.raises(IOError):
         list(ld)
+
+
+# ------------------------------------------------------------------ DALI-style path: host-side pieces (no GPU needed)
+def _photo(h, w, seed):
+    rng = np.random.RandomState(seed)
+    img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    return cv2.GaussianBlur(img, (5, 5), 0)
+
+
+@pytest.mark.parametrize("box", [(10, 20, 200, 300), (0, 0, 375, 500), (100, 100, 50, 40), (7, 3, 301, 17), (0, 0, 64, 64)])
+@pytest.mark.parametrize("flip", [False, True])
+def test_augment_reference_has_cv2_bilinear_geometry(box, flip):
+    """The NumPy model of csrc/augment.cu = crop -> cv2.resize(INTER_LINEAR) -> mirror, up to cv2's integer rounding."""
+    img = _photo(375, 500, 1)
+    y, x, ch, cw = box
+    want = cv2.resize(img[y:y + ch, x:x + cw], (64, 64), interpolation=cv2.INTER_LINEAR).astype(np.float32)
+    want = want[:, ::-1] if flip else want
+    got = ip.augment_reference(img, box, flip, 64, mean=(0, 0, 0), std=(1, 1, 1)) * 255.0
+    assert np.abs(got - want).max() < 1.0
+    m = ip.augment_reference(img, box, flip, 64)                      # ImageNet statistics
+    assert abs(float(m[5, 6, 1]) - (got[5, 6, 1] / 255.0 - 0.456) / 0.224) < 1e-4
+
+
+def test_eval_crop_box_matches_resize_then_center_crop():
+    img = _photo(300, 420, 2)
+    box = ip.eval_crop_box(300, 420, 224, 256)
+    assert box[2] == box[3] == round(300 * 224 / 256) and box[0] == (300 - box[2]) // 2
+    s = 256 / 300.0
+    big = cv2.resize(img, (int(round(420 * s)), 256), interpolation=cv2.INTER_LINEAR)
+    yy, xx = (big.shape[0] - 224) // 2, (big.shape[1] - 224) // 2
+    want = big[yy:yy + 224, xx:xx + 224].astype(np.float32)
+    got = ip.augment_reference(img, box, False, 224, mean=(0, 0, 0), std=(1, 1, 1)) * 255.0
+    assert np.abs(got - want).mean() < 4.0                            # same pixels up to a sub-pixel phase
+
+
+def test_augment_plan_packs_items_for_the_kernel():
+    import random
+
+    aug = ip.GpuJpegAugmenter.__new__(ip.GpuJpegAugmenter)            # plan() is pure host code
+    aug.size = 224
+    dims = [(375, 500), (64, 48), (1200, 1600)]
+    items, total = aug.plan(dims, random.Random(0), train=True)
+    assert items.shape == (3, 8) and items.dtype == np.int32
+    offs = items.view(np.int64)[:, 0]
+    assert offs[0] == 0 and all(o % 256 == 0 for o in offs) and total >= offs[2] + 1200 * 1600 * 3
+    assert offs[1] >= 375 * 500 * 3 and offs[2] >= offs[1] + 64 * 48 * 3
+    for (h, w), row in zip(dims, items):
+        pitch, y, x, ch, cw, flip = row[2:]
+        assert pitch == 3 * w and 0 <= y and y + ch <= h and 0 <= x and x + cw <= w and flip in (0, 1)
+    ev, _ = aug.plan(dims, random.Random(0), train=False)
+    assert list(ev[0, 3:]) == [*ip.eval_crop_box(375, 500, 224), 0]
+
+
+def test_nvjpeg_mode_ships_file_bytes(tmp_path):
+    samples = _dataset(tmp_path, 8)
+    ld = ip.ImageBatchLoader(samples, 4, size=32, train=True, seed=3, threads=2, pin=False, decode="nvjpeg")
+    batches = list(ld)
+    assert len(batches) == 2 and all(isinstance(b, ip.JpegBatch) and len(b) == 4 for b in batches)
+    assert all(blob[:2] == b"\xff\xd8" for b in batches for blob in b.blobs)          # JPEG SOI marker
+    assert batches[0].seed != batches[1].seed and batches[0].labels.dtype == torch.int64
+    with pytest.raises(RuntimeError):
+        ip.to_device_batch(batches[0], "cpu")                         # this path needs a CUDA device

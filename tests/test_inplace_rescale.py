@@ -23,13 +23,20 @@ TRAIN = os.path.join(ROOT, "examples", "fit_a_line", "train.py")
 def _launch(endpoint, job, log_dir, report, ckpt, epochs, mode="inplace"):
     env = dict(os.environ)
     env.update({"PYTHONPATH": ROOT, "CUDA_VISIBLE_DEVICES": "", "PADDLE_RUNNING_PLATFORM": "", "EDL_POD_IP": "127.0.0.1",
-                "FIT_REPORT_DIR": report, "EDL_INPLACE_CHECK_EVERY": "3", "EDL_INPLACE_ACK_TIMEOUT": "40"})
+                "FIT_REPORT_DIR": report, "EDL_INPLACE_CHECK_EVERY": "3", "EDL_INPLACE_ACK_TIMEOUT": "40",
+                # `epochs` is only an upper bound: the test ends the job (_finish) once it has seen what it wanted,
+                # so a slow pod start on a loaded box cannot make the job finish under the test's feet
+                "FIT_FINISH_FILE": report + ".finish"})
     cmd = [sys.executable, "-u", "-m", "edl_b200.collective.launch", "--nodes_range", "1:2", "--nproc_per_node", "1",
            "--etcd_endpoints", endpoint, "--job_id", job, "--log_dir", log_dir, "--log_level", "10",
            "--hdfs_path", ckpt, "--rescale_mode", mode,
            TRAIN, "--epochs", str(epochs), "--epoch_sleep", "0.05", "--ckpt", ckpt]
     return subprocess.Popen(cmd, env=env, stdout=open(log_dir + ".launcher.log", "w"), stderr=subprocess.STDOUT,
                             start_new_session=True)
+
+
+def _finish(report):
+    open(report + ".finish", "w").close()
 
 
 @pytest.mark.slow
@@ -53,12 +60,12 @@ def test_join_and_scale_in_without_restarting_the_survivor(kv_server, tmp_path):
                        if os.path.exists(f))
         raise AssertionError("world never became %d: %s\n%s" % (w, epochs()[-4:], logs))
 
-    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 170)
+    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 2000)
     b = None
     try:
         e1 = wait_world(1, 60)
         pid_a = e1[-1]["pid"]
-        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 170)
+        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 2000)
         e2 = wait_world(2, 90)
         assert e2[-1]["pid"] == pid_a, "the surviving trainer was restarted on scale-out"
         assert abs(e2[-1]["lr"] - 2 * e1[-1]["lr"]) < 1e-9                       # linear LR rescale, in place
@@ -72,6 +79,7 @@ def test_join_and_scale_in_without_restarting_the_survivor(kv_server, tmp_path):
         e1b = wait_world(1, 90)
         assert e1b[-1]["pid"] == pid_a, "the surviving trainer was restarted on scale-in"
         assert abs(e1b[-1]["lr"] - e1[-1]["lr"]) < 1e-9
+        _finish(report)
         assert b.wait(timeout=60) == 0                                           # evicted pod: clean exit
         assert a.wait(timeout=120) == 0
         assert edl_status.load_job_status_from_etcd(etcd) == edl_status.Status.SUCCEED
@@ -144,7 +152,7 @@ def test_resnet_trainer_rescales_in_place(kv_server, tmp_path):
                "--etcd_endpoints", kv_server.endpoint, "--job_id", job, "--log_dir", str(tmp_path / ("log" + name)),
                "--hdfs_path", ckpt, "--rescale_mode", "inplace", script, "--model", "ResNet18_vd", "--width_mult", "0.125",
                "--image_size", "32", "--class_dim", "10", "--batch_size", "4", "--epochs", "2", "--steps_per_epoch", "240",
-               "--ckpt", ckpt]
+               "--solo_step_sleep", "0.4", "--ckpt", ckpt]     # alone, epoch 0 lasts >= 96 s: B joins whatever the load
         return subprocess.Popen(cmd, env=env, stdout=open(str(tmp_path / (name + ".launcher.log")), "w"),
                                 stderr=subprocess.STDOUT, start_new_session=True)
 
@@ -202,12 +210,12 @@ def test_hot_recovery_when_a_pod_dies_hard(kv_server, tmp_path):
         raise AssertionError("world never became %d: %s\n%s" % (w, epochs()[-4:],
                                                                   open(str(tmp_path / "logA.launcher.log")).read()[-3000:]))
 
-    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 200)
+    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 2000)
     b = None
     try:
         e1 = wait_world(1, 60)
         pid_a = e1[-1]["pid"]
-        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 200)
+        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 2000)
         wait_world(2, 90)
         import psutil
 
@@ -220,6 +228,7 @@ def test_hot_recovery_when_a_pod_dies_hard(kv_server, tmp_path):
         e1b = wait_world(1, 90)
         assert e1b[-1]["pid"] == pid_a, "the survivor was restarted instead of recovering in place"
         assert abs(e1b[-1]["lr"] - e1[-1]["lr"]) < 1e-9
+        _finish(report)
         assert a.wait(timeout=120) == 0
         worker = open(str(tmp_path / "logA" / "workerlog.0")).read()
         assert "recovered in place: world 2 -> 1" in worker, worker[-2000:]
@@ -255,15 +264,16 @@ def test_sigterm_is_a_graceful_leave(kv_server, tmp_path):
             time.sleep(0.2)
         raise AssertionError("world never became %d: %s" % (w, epochs()[-4:]))
 
-    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 170)
+    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 2000)
     b = None
     try:
         pid_a = wait_world(1, 60)[-1]["pid"]
-        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 170)
+        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 2000)
         wait_world(2, 90)
         b.send_signal(signal.SIGTERM)                             # the launcher only; its trainer is left alone
         e1 = wait_world(1, 60)
         assert e1[-1]["pid"] == pid_a
+        _finish(report)
         assert b.wait(timeout=60) == 0
         assert a.wait(timeout=120) == 0
         worker = open(str(tmp_path / "logA" / "workerlog.0")).read()
@@ -357,11 +367,11 @@ def test_restart_mode_survives_a_hard_pod_death(kv_server, tmp_path):
         raise AssertionError("world never became %d: %s\n%s" % (w, epochs()[-4:],
                                                                   open(str(tmp_path / "logA.launcher.log")).read()[-3000:]))
 
-    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 150, mode="restart")
+    a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 2000, mode="restart")
     b = None
     try:
         pid1 = wait_world(1, 60)[-1]["pid"]
-        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 150, mode="restart")
+        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 2000, mode="restart")
         wait_world(2, 90)
         for v in [psutil.Process(b.pid)] + psutil.Process(b.pid).children(recursive=True):
             try:
@@ -370,6 +380,7 @@ def test_restart_mode_survives_a_hard_pod_death(kv_server, tmp_path):
                 pass
         e = wait_world(1, 90)
         assert e[-1]["pid"] != pid1                              # restart mode: a NEW trainer process carries on
+        _finish(report)
         assert a.wait(timeout=120) == 0
         log_a = open(str(tmp_path / "logA.launcher.log")).read()
         assert "treating the exit as collateral" in log_a
