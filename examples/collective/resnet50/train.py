@@ -54,10 +54,36 @@ def parse():
     ap.add_argument("--width_mult", type=float, default=1.0)
     ap.add_argument("--ckpt", default=os.environ.get("PADDLE_EDL_HDFS_PATH") or "./resnet_ckpt")
     ap.add_argument("--max_steps", type=int, default=0, help="stop an epoch early (smoke runs)")
+    ap.add_argument("--data_dir", default=None,
+                    help="ImageNet-style directory with train_list.txt ('relative/path.jpg label' per line); synthetic if unset")
+    ap.add_argument("--use_dali", type=lambda v: str(v).lower() in ("1", "true", "yes"), default=False,
+                    help="the reference's flag for GPU-side decoding: JPEGs are decoded by nvJPEG and cropped / resized / "
+                         "normalised by one kernel on the training GPU (ImageBatchLoader(decode='nvjpeg')); default: "
+                         "OpenCV worker threads + uint8 H2D + normalize_u8")
+    ap.add_argument("--reader_threads", type=int, default=8)
     ap.add_argument("--solo_step_sleep", type=float, default=0.0,
                     help="elastic demos / tests: seconds to sleep per step while the job has ONE trainer, so that a "
                          "second pod has time to join whatever the speed of the box")
     return ap.parse_args()
+
+
+def file_feed(args, bs, rank, world, epoch, skip, dev, dtype, cuda):
+    """Batches of the ImageNet-style file list for this rank and epoch, ``skip`` batches in (resume / in-place rescale
+    mid-epoch).  Reference: the DALI / cv2 readers of example/collective/resnet50/train_with_fleet.py (--use_dali)."""
+    if not args.data_dir:
+        return None
+    from edl_b200.utils import image_pipeline as ip
+
+    samples = ip.read_file_list(os.path.join(args.data_dir, "train_list.txt"))
+    ld = ip.ImageBatchLoader(samples, bs, size=args.image_size, train=True, rank=rank, world=world, seed=0,
+                             threads=args.reader_threads, decode="nvjpeg" if (args.use_dali and cuda) else "cpu")
+    ld.set_epoch(epoch)
+
+    def gen():
+        for i, batch in enumerate(ld):
+            if i >= skip:
+                yield ip.to_device_batch(batch, dev, dtype)
+    return gen()
 
 
 def main():
@@ -71,6 +97,9 @@ def main():
         env = edl.init_distributed()
         world, rank = env.size, env.global_rank
     cuda = torch.cuda.is_available()
+    if args.data_dir:
+        from edl_b200.utils import image_pipeline
+        args.total_images = len(image_pipeline.read_file_list(os.path.join(args.data_dir, "train_list.txt")))
     dev = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
     bs = args.batch_size if not args.total_batch_size else max(1, args.total_batch_size // world)
     torch.manual_seed(0)
@@ -121,14 +150,22 @@ def main():
         it = it0
         it0 = 0
         switch = False
+        feed = file_feed(args, bs, rank, world, epoch, it, dev, dtype, cuda)
         while it < n_steps:
             lr = (cosine_decay_with_warmup(step, base_lr, steps_per_epoch, args.epochs) if args.lr_strategy.startswith("cosine")
                   else piecewise_decay_with_warmup(step, base_lr, steps_per_epoch, [30, 60, 80]))
             tr.set_lr(lr)
-            x = torch.randn(bs, 3, args.image_size, args.image_size, generator=g).to(dtype)
-            x = x.contiguous(memory_format=torch.channels_last)
-            y = torch.randint(0, args.class_dim, (bs,), generator=g)
-            loss = tr.step(x.pin_memory() if cuda else x, y.pin_memory() if cuda else y)
+            if feed is not None:
+                try:
+                    x, y = next(feed)                                # already on the device (or CPU tensors without one)
+                except StopIteration:
+                    break                                            # this rank's shard is exhausted: epoch over
+                loss = tr.step(x, y)
+            else:
+                x = torch.randn(bs, 3, args.image_size, args.image_size, generator=g).to(dtype)
+                x = x.contiguous(memory_format=torch.channels_last)
+                y = torch.randint(0, args.class_dim, (bs,), generator=g)
+                loss = tr.step(x.pin_memory() if cuda else x, y.pin_memory() if cuda else y)
             step += 1
             it += 1
             seen += bs

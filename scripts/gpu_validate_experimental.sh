@@ -31,6 +31,11 @@ run_group bnr2     400 "bnr_mode2 or bnr_many_tiles"
 run_group bnmodel  300 "fused_bn_backward_matches"
 run_group teacher  300 "teacher_residual"
 run_group pipeline 200 "step_pipelined"
+run_group jpeg     300 "crop_resize_normalize or nvjpeg"
+if [ "${OK[jpeg]}" = 0 ]; then
+  timeout 300 python tools/bench_loader.py --images 2048 --threads 8 > gpurun_out/loader_bench.jsonl 2> gpurun_out/loader_bench.err
+  sed 's/^/loader: /' gpurun_out/loader_bench.jsonl | tee -a "$SUMMARY"
+fi
 
 bench() {       # tag, flags...
   local tag=$1; shift

@@ -55,6 +55,26 @@ def test_collective_resnet_example_models(tmp_path, model):
     assert "Pass 0 trainbatch 0" in out
 
 
+def test_collective_resnet_example_reads_a_jpeg_file_list(tmp_path):
+    """--data_dir: train_list.txt + JPEGs through ImageBatchLoader (cv2 threads on a box without a GPU; --use_dali
+    switches to nvJPEG + the fused augmentation kernel on one)."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+
+    rng = np.random.RandomState(0)
+    data = tmp_path / "data"
+    data.mkdir()
+    lines = []
+    for i in range(12):
+        cv2.imwrite(str(data / ("im%02d.jpg" % i)), rng.randint(0, 256, (40 + i, 50, 3)).astype(np.uint8))
+        lines.append("im%02d.jpg %d" % (i, i % 10))
+    (data / "train_list.txt").write_text("\n".join(lines) + "\n")
+    out = run(["examples/collective/resnet50/train.py", "--model", "ResNet18_vd", "--width_mult", "0.125", "--image_size", "32",
+               "--class_dim", "10", "--batch_size", "4", "--epochs", "2", "--data_dir", str(data), "--use_dali", "true",
+               "--reader_threads", "2", "--ckpt", str(tmp_path / "ck")])
+    assert "Pass 0 trainbatch 0" in out and "Pass 1 trainbatch 0" in out
+
+
 def test_seqfile_roundtrip_and_ctr_dump(tmp_path):
     import io
     import struct
