@@ -99,8 +99,13 @@ def main():
     for f in sorted(glob.glob(os.path.join(SRC, "kernels*.log")) + glob.glob(os.path.join(SRC, "kineto*.txt"))):
         txt = "".join(l for l in open(f) if not l.startswith("W0"))
         open(os.path.join(OUT, os.path.basename(f).replace(".log", ".txt")), "w").write(txt)
-    bench = {}
-    for f in sorted(glob.glob(os.path.join(SRC, "bench*.json"))):
+    # earlier rounds' records stay: gpurun_out/ is scratch and starts empty in a re-created container
+    bench_path = os.path.join(OUT, "bench_runs.json")
+    try:
+        bench = json.load(open(bench_path))
+    except (OSError, ValueError):
+        bench = {}
+    for f in sorted(glob.glob(os.path.join(SRC, "bench*.json")) + glob.glob(os.path.join(SRC, "ab_*.json"))):
         try:
             line = [l for l in open(f).read().splitlines() if l.startswith("{")][-1]
             d = json.loads(line)
@@ -109,7 +114,11 @@ def main():
             bench[os.path.basename(f)[:-5]]["config"] = {k: (d.get("config") or {}).get(k) for k in ("model", "batch_per_gpu", "cuda_graph", "conv_impl", "allreduce", "parallelism")}
         except Exception:
             pass
-    json.dump(bench, open(os.path.join(OUT, "bench_runs.json"), "w"), indent=1)
+    json.dump(bench, open(bench_path, "w"), indent=1)
+    for name in ("experimental_summary.txt", "loader_bench.jsonl"):       # scripts/gpu_validate_experimental.sh
+        src = os.path.join(SRC, name)
+        if os.path.exists(src):
+            open(os.path.join(OUT, name), "w").write(open(src).read())
     print("wrote", len(os.listdir(OUT)), "files to", OUT)
 
 
