@@ -197,6 +197,118 @@ allreduce_twoshot_kernel(CommCtx c, int64_t n, Epilogue e) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused gradient reduce-scatter -> SGD-momentum -> parameter all-gather, ONE kernel per bucket (SURVEY K7 + K10).
+//
+// The reference runs NCCL all-reduce, then one Paddle `momentum` op per tensor on every rank
+// (example/distill/resnet/train_with_fleet.py:106-122,332-333): every rank applies the same update to the same
+// 25.6 M parameters.  Here rank r owns slice r of the bucket: it pulls the summed gradient of its slice out of the
+// switch (multimem.ld_reduce, or W peer loads), updates ITS slice of the fp32 master weights and momentum -- the
+// optimizer work and state traffic drop by the world size -- and pushes the new bf16 parameters of that slice into
+// every rank's parameter buffer (multimem.st / peer stores).  The NVLink traffic equals a two-shot all-reduce
+// (gradients in, parameters out); the separate optimizer pass over the bucket and the end-of-backward join
+// before it disappear.  Master / momentum outside the owned slice go stale on purpose; the host consolidates them
+// (ElasticDataParallel.consolidate_optimizer_state) before a checkpoint or a stage change.
+// A bucket is skipped as a whole (no update, no parameter store) when this rank's error word is set: a peer died
+// and the sum would be partial -- the elastic hot-recovery path takes over from the last good parameters.
+struct FusedSgd {
+  void* pdata[kMaxWorld];    // every rank's bf16 parameter window (bucket offset applied)
+  void* mc_param;            // multicast alias of that window or nullptr
+  float* master;             // local fp32 master weights of the bucket
+  float* mom;                // local fp32 momentum of the bucket
+  const float* wd_mask;      // optional per-element weight-decay mask of the bucket
+  const float* lr;           // device scalar
+  const int* found_inf;      // optional device flag: non-zero => skip the update
+  float momentum, wd;
+  int nesterov;
+};
+
+template <bool kMultimem>
+__global__ void __launch_bounds__(kCommThreads)
+allreduce_sgd_kernel(CommCtx c, int64_t n, Epilogue e, FusedSgd f) {
+  using T = __nv_bfloat16;
+  const uint32_t epoch = comm_epoch_begin(c);
+  comm_barrier<false>(c, kSigStart, epoch);
+  const bool broken = *reinterpret_cast<volatile uint32_t*>(c.sig[c.rank] + kSigError) != 0u ||
+                      (f.found_inf != nullptr && *f.found_inf != 0);
+  constexpr int VE = 8;
+  const int64_t nvec = n / VE;
+  const int64_t slice_cap = (nvec + c.world - 1) / c.world;
+  const int64_t base = slice_cap * c.rank;
+  int64_t slice_vecs = nvec - base;
+  if (slice_vecs > slice_cap) slice_vecs = slice_cap;
+  if (slice_vecs < 0 || broken) slice_vecs = 0;
+  const float lr = *f.lr;
+  bool bad = false;
+  float sq = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slice_vecs;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = base + i;
+    // optimizer state of this vector: issued before the (long-latency) cross-GPU gradient fetch
+    const float4 w0 = *reinterpret_cast<const float4*>(f.master + v * 8);
+    const float4 w1 = *reinterpret_cast<const float4*>(f.master + v * 8 + 4);
+    const float4 m0 = *reinterpret_cast<const float4*>(f.mom + v * 8);
+    const float4 m1 = *reinterpret_cast<const float4*>(f.mom + v * 8 + 4);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if constexpr (kMultimem) {
+      bf16x8 g = multimem_ld_reduce_bf16(reinterpret_cast<const char*>(c.mc_data) + v * 16);
+      unpack8(g, acc);
+    } else {
+      int4 raw[kMaxWorld];
+#pragma unroll
+      for (int p = 0; p < kMaxWorld; ++p) {
+        if (p < c.world) {
+          int peer = c.rank + p;
+          if (peer >= c.world) peer -= c.world;
+          raw[p] = ld_peer(reinterpret_cast<const int4*>(c.data[peer]) + v);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < kMaxWorld; ++p)
+        if (p < c.world) Vec<T>::add(acc, raw[p]);
+    }
+    apply_epilogue<T>(acc, e, bad, sq);
+    float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    float wdm[8];
+    if (f.wd_mask != nullptr) {
+      const float4 k0 = *reinterpret_cast<const float4*>(f.wd_mask + v * 8);
+      const float4 k1 = *reinterpret_cast<const float4*>(f.wd_mask + v * 8 + 4);
+      wdm[0] = k0.x; wdm[1] = k0.y; wdm[2] = k0.z; wdm[3] = k0.w;
+      wdm[4] = k1.x; wdm[5] = k1.y; wdm[6] = k1.z; wdm[7] = k1.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float wd = f.wd_mask != nullptr ? f.wd * wdm[k] : f.wd;
+      const float gg = fmaf(wd, w[k], acc[k]);
+      mv[k] = fmaf(f.momentum, mv[k], gg);
+      const float upd = f.nesterov ? fmaf(f.momentum, mv[k], gg) : mv[k];
+      w[k] = fmaf(-lr, upd, w[k]);
+    }
+    *reinterpret_cast<float4*>(f.master + v * 8) = make_float4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<float4*>(f.master + v * 8 + 4) = make_float4(w[4], w[5], w[6], w[7]);
+    *reinterpret_cast<float4*>(f.mom + v * 8) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+    *reinterpret_cast<float4*>(f.mom + v * 8 + 4) = make_float4(mv[4], mv[5], mv[6], mv[7]);
+    const bf16x8 packed = pack8(w);
+    if constexpr (kMultimem) {
+      multimem_st_bf16(reinterpret_cast<char*>(f.mc_param) + v * 16, packed);
+    } else {
+      const int4& raw = *reinterpret_cast<const int4*>(&packed);
+#pragma unroll
+      for (int p = 0; p < kMaxWorld; ++p) {
+        if (p < c.world) {
+          int peer = c.rank + p;
+          if (peer >= c.world) peer -= c.world;
+          st_peer(reinterpret_cast<int4*>(f.pdata[peer]) + v, raw);
+        }
+      }
+    }
+  }
+  finish_epilogue(e, bad, sq);
+  comm_barrier<true>(c, kSigEnd, epoch);
+  comm_epoch_end(c, epoch);
+}
+
+// ---------------------------------------------------------------------------------------------
 // broadcast from `root` into every rank's symmetric buffer (state hand-off to joiners).
 __global__ void __launch_bounds__(kCommThreads)
 broadcast_kernel(CommCtx c, int root, int64_t nbytes) {
@@ -293,6 +405,30 @@ void allreduce_twoshot(const CommHandles& h, bool is_bf16, int64_t n, float scal
     else
       allreduce_twoshot_kernel<float, false><<<nblocks, kCommThreads, 0, stream>>>(c, n, e);
   }
+}
+
+void allreduce_sgd(const CommHandles& h, void* const* param_ptrs, void* mc_param, float* master, float* mom,
+                   const float* wd_mask, int64_t n, float scale, int* found_inf_out, float* sqnorm,
+                   const float* lr, const int* skip_flag, float momentum, float wd, bool nesterov, bool multimem,
+                   int nblocks, cudaStream_t stream) {
+  CommCtx c = make_ctx(h);
+  Epilogue e{scale, found_inf_out, sqnorm};
+  FusedSgd f{};
+  for (int i = 0; i < kMaxWorld; ++i) f.pdata[i] = i < h.world ? param_ptrs[i] : nullptr;
+  f.mc_param = mc_param;
+  f.master = master;
+  f.mom = mom;
+  f.wd_mask = wd_mask;
+  f.lr = lr;
+  f.found_inf = skip_flag;
+  f.momentum = momentum;
+  f.wd = wd;
+  f.nesterov = nesterov ? 1 : 0;
+  nblocks = clamp_blocks(nblocks);
+  if (multimem && h.mc_data != nullptr && mc_param != nullptr)
+    allreduce_sgd_kernel<true><<<nblocks, kCommThreads, 0, stream>>>(c, n, e, f);
+  else
+    allreduce_sgd_kernel<false><<<nblocks, kCommThreads, 0, stream>>>(c, n, e, f);
 }
 
 void comm_broadcast(const CommHandles& h, int root, int64_t nbytes, int nblocks,

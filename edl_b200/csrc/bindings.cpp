@@ -307,6 +307,49 @@ void allreduce_twoshot(const std::vector<int64_t>& data_ptrs, const std::vector<
                          multimem, (int)nblocks, cur_stream());
 }
 
+// one bf16 bucket: gradient reduce-scatter -> SGD-momentum on the owned slice -> parameter all-gather
+void allreduce_sgd(const std::vector<int64_t>& grad_ptrs, const std::vector<int64_t>& sig_ptrs, int64_t mc_grad,
+                   const std::vector<int64_t>& param_ptrs, int64_t mc_param, int64_t rank, Tensor& master,
+                   Tensor& mom, const c10::optional<Tensor>& wd_mask, const Tensor& lr, double scale,
+                   const c10::optional<Tensor>& found_inf_out, const c10::optional<Tensor>& sqnorm,
+                   const c10::optional<Tensor>& skip_flag, double momentum, double wd, bool nesterov,
+                   bool multimem, int64_t nblocks, double timeout_s) {
+  auto h = make_handles(grad_ptrs, sig_ptrs, mc_grad, rank, timeout_s);
+  check_f32(master, "master");
+  check_f32(mom, "mom");
+  check_f32(lr, "lr");
+  const int64_t n = master.numel();
+  TORCH_CHECK(n % 8 == 0 && mom.numel() == n, "fused bucket must be a multiple of 8 elements");
+  TORCH_CHECK(param_ptrs.size() == grad_ptrs.size());
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(master.data_ptr()) % 16 == 0 && reinterpret_cast<uintptr_t>(mom.data_ptr()) % 16 == 0);
+  void* pp[16] = {};
+  for (size_t i = 0; i < param_ptrs.size(); ++i) pp[i] = reinterpret_cast<void*>(param_ptrs[i]);
+  c10::cuda::CUDAGuard g(master.device());
+  edl::allreduce_sgd(h, pp, reinterpret_cast<void*>(mc_param), master.data_ptr<float>(), mom.data_ptr<float>(),
+                     opt_ptr<float>(wd_mask), n, (float)scale, opt_ptr<int>(found_inf_out), opt_ptr<float>(sqnorm),
+                     lr.data_ptr<float>(), opt_ptr<int>(skip_flag), (float)momentum, (float)wd, nesterov, multimem,
+                     (int)nblocks, cur_stream());
+}
+
+void grad_sqnorm(const Tensor& grad, Tensor& out) {
+  TORCH_CHECK(grad.is_cuda() && grad.is_contiguous());
+  check_f32(out, "out");
+  const bool gbf = grad.scalar_type() == at::kBFloat16;
+  TORCH_CHECK(gbf || grad.scalar_type() == at::kFloat);
+  c10::cuda::CUDAGuard g(grad.device());
+  edl::grad_sqnorm(grad.data_ptr(), gbf, grad.numel(), out.data_ptr<float>(), cur_stream());
+}
+
+void clip_scale(const Tensor& parts, int64_t nparts, int64_t stride, double max_norm, Tensor& grad_scale,
+                const c10::optional<Tensor>& norm_out) {
+  check_f32(parts, "parts");
+  check_f32(grad_scale, "grad_scale");
+  TORCH_CHECK(nparts >= 1 && (nparts - 1) * stride < parts.numel());
+  c10::cuda::CUDAGuard g(parts.device());
+  edl::clip_scale(parts.data_ptr<float>(), (int)nparts, (int)stride, (float)max_norm, grad_scale.data_ptr<float>(),
+                  opt_ptr<float>(norm_out), cur_stream());
+}
+
 void comm_broadcast(const std::vector<int64_t>& data_ptrs, const std::vector<int64_t>& sig_ptrs,
                     int64_t rank, int64_t root, int64_t nbytes, int64_t nblocks, double timeout_s,
                     const Tensor& local) {
@@ -430,6 +473,7 @@ void wait_flag_async(const Tensor& flag, const c10::optional<Tensor>& seq, int64
 
 void register_gemm_bindings(pybind11::module_& m);  // gemm_bindings.cpp
 void register_jpeg_bindings(pybind11::module_& m);  // jpeg_decode.cpp
+void register_vmm_bindings(pybind11::module_& m);   // vmm.cpp
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "edl_b200 sm_100a kernels";
@@ -458,6 +502,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gap_bwd", &gap_bwd);
   m.def("allreduce_oneshot", &allreduce_oneshot);
   m.def("allreduce_twoshot", &allreduce_twoshot);
+  m.def("allreduce_sgd", &allreduce_sgd);
+  m.def("grad_sqnorm", &grad_sqnorm);
+  m.def("clip_scale", &clip_scale);
   m.def("comm_broadcast", &comm_broadcast);
   m.def("comm_allgather_scalars", &comm_allgather_scalars);
   m.def("comm_sig_words", &edl::comm_sig_words);
@@ -474,4 +521,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("wait_flag_async", &wait_flag_async);
   register_gemm_bindings(m);
   register_jpeg_bindings(m);
+  register_vmm_bindings(m);
 }

@@ -21,6 +21,8 @@ constexpr int kSigEpoch = 2 * kMaxCommBlocks * kMaxWorld;      // [blocks]   (lo
 constexpr int kSigScratch = kSigEpoch + kMaxCommBlocks;        // [world][8] floats: per-rank partials
 constexpr int kSigError = kSigScratch + kMaxWorld * 8;         // [1] error word (local)
 constexpr int kSigWords = kSigError + 8;
+// how long a barrier still waits once this rank's error word is set (a peer already timed out)
+constexpr unsigned long long kCommBrokenGraceNs = 200ull * 1000ull;
 
 struct CommCtx {
   void* data[kMaxWorld];      // peer pointers to the symmetric payload buffer
@@ -66,10 +68,18 @@ EDL_DEVICE void comm_barrier(const CommCtx& c, int slot, uint32_t epoch) {
     const int peer = threadIdx.x;
     st_release_sys(c.sig[peer] + slot + blockIdx.x * kMaxWorld + c.rank, epoch);
     const uint32_t* mine = c.sig[c.rank] + slot + blockIdx.x * kMaxWorld + peer;
+    // The error word is sticky for the lifetime of the pool (one elastic stage).  Once ANY barrier of this rank
+    // has timed out, a peer is gone: every later barrier -- the second one of the same kernel, the other CTAs, the
+    // next buckets, the next graph replays -- gives up after a short grace period instead of the full timeout, so
+    // a dead peer costs one timeout in total and the host sees the error at its next poll.
+    volatile uint32_t* errw = c.sig[c.rank] + kSigError;
     const unsigned long long t0 = globaltimer_ns();
+    unsigned long long limit = (*errw != 0u) ? kCommBrokenGraceNs : c.timeout_ns;
+    uint32_t spins = 0;
     while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-      if (c.timeout_ns != 0 && globaltimer_ns() - t0 > c.timeout_ns) {
-        atomicExch(c.sig[c.rank] + kSigError, 1u + (uint32_t)peer);
+      if ((++spins & 63u) == 0u && limit != 0 && *errw != 0u && limit > kCommBrokenGraceNs) limit = kCommBrokenGraceNs;
+      if (limit != 0 && globaltimer_ns() - t0 > limit) {
+        atomicCAS(c.sig[c.rank] + kSigError, 0u, 1u + (uint32_t)peer);   // keep the first culprit
         break;
       }
     }

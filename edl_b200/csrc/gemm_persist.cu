@@ -653,11 +653,11 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 bool g_persistent = true;
-// fused BatchNorm-backward reduction in the dgrad epilogue: 1 = in-register shuffle transpose (validated at kernel
-// level in round 1, epilogue-bound), 2 = column-pair loop over the staged tiles (written afterwards, EDL_BNR_MODE=2)
+// fused BatchNorm-backward reduction in the dgrad epilogue: 2 (default) = column-pair loop over the staged tiles,
+// 1 = the round-1 in-register shuffle transpose (epilogue-bound; EDL_BNR_MODE=1 keeps it selectable for A/B)
 int g_bnr_mode = [] {
   const char* e = getenv("EDL_BNR_MODE");
-  return (e != nullptr && e[0] == '2') ? 2 : 1;
+  return (e != nullptr && e[0] == '1') ? 1 : 2;
 }();
 
 template <int BLOCK_N, int STAGES, int MODE, int BNR = 0>

@@ -67,6 +67,12 @@ void adam_step(void* param_lp, float* master, float* m, float* v, const void* gr
                const int* found_inf, const float* step, float beta1, float beta2, float eps,
                float wd, bool decoupled, cudaStream_t stream);
 
+// sum(g^2) of a flat gradient buffer into *out (+=), and the global-norm clip factor
+//   grad_scale = min(1, max_norm / (sqrt(sum of parts) + 1e-6))   (parts: one squared-norm partial per rank)
+void grad_sqnorm(const void* grad, bool grad_is_bf16, int64_t n, float* out, cudaStream_t stream);
+void clip_scale(const float* parts, int nparts, int stride, float max_norm, float* grad_scale, float* norm_out,
+                cudaStream_t stream);
+
 // ---- loss.cu ----
 void soft_ce_fwd(const void* logits, bool logits_bf16, const void* target, bool target_bf16,
                  const int64_t* labels, float* loss_out, float* row_stats, int N, int C, int mode,
@@ -105,6 +111,11 @@ void allreduce_oneshot(const CommHandles& h, void* out, bool is_bf16, int64_t n,
                        int* found_inf, float* sqnorm, int nblocks, cudaStream_t stream);
 void allreduce_twoshot(const CommHandles& h, bool is_bf16, int64_t n, float scale, int* found_inf,
                        float* sqnorm, bool multimem, int nblocks, cudaStream_t stream);
+// fused reduce-scatter -> SGD-momentum -> parameter all-gather of one bf16 bucket (allreduce.cu)
+void allreduce_sgd(const CommHandles& h, void* const* param_ptrs, void* mc_param, float* master, float* mom,
+                   const float* wd_mask, int64_t n, float scale, int* found_inf_out, float* sqnorm,
+                   const float* lr, const int* skip_flag, float momentum, float wd, bool nesterov, bool multimem,
+                   int nblocks, cudaStream_t stream);
 void comm_broadcast(const CommHandles& h, int root, int64_t nbytes, int nblocks,
                     cudaStream_t stream);
 void comm_allgather_scalars(const CommHandles& h, const float* in, float* out, int count,

@@ -137,6 +137,52 @@ adam_kernel(__nv_bfloat16* __restrict__ param_lp, float* __restrict__ master,
   }
 }
 
+template <typename GradT>
+__global__ void __launch_bounds__(kThreads)
+grad_sqnorm_kernel(const GradT* __restrict__ grad, int64_t n, float* __restrict__ out) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  float sq = 0.f;
+  if constexpr (sizeof(GradT) == 2) {
+    const int64_t nvec = n / 8;
+    for (int64_t i = tid; i < nvec; i += nthreads) {
+      float g[8];
+      unpack8(ld_stream(grad + i * 8), g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sq = fmaf(g[k], g[k], sq);
+    }
+    for (int64_t i = nvec * 8 + tid; i < n; i += nthreads) {
+      const float g = __bfloat162float(grad[i]);
+      sq = fmaf(g, g, sq);
+    }
+  } else {
+    for (int64_t i = tid; i < n; i += nthreads) sq = fmaf(grad[i], grad[i], sq);
+  }
+  __shared__ float sh[kThreads / 32];
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
+// one warp: global-norm clip factor from the per-rank squared-norm partials (SURVEY K9 "clip")
+__global__ void clip_scale_kernel(const float* __restrict__ parts, int nparts, int stride, float max_norm,
+                                  float* __restrict__ grad_scale, float* __restrict__ norm_out) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 32) s += parts[(int64_t)i * stride];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) {
+    const float norm = sqrtf(s);
+    // a non-finite norm leaves the scale at 1: the found_inf machinery (loss scaling) owns that case
+    *grad_scale = (norm == norm && norm > max_norm) ? max_norm / (norm + 1e-6f) : 1.f;
+    if (norm_out != nullptr) *norm_out = norm;
+  }
+}
+
 inline int grid_for(int64_t n_items) {
   int64_t blocks = (n_items + kThreads - 1) / kThreads;
   int64_t cap = (int64_t)kNumSMs * 8;
@@ -161,6 +207,20 @@ void sgd_momentum(void* param_lp, float* master, float* mom, const void* grad, b
     sgd_momentum_kernel<float><<<grid, kThreads, 0, stream>>>(
         reinterpret_cast<__nv_bfloat16*>(param_lp), master, mom,
         reinterpret_cast<const float*>(grad), wd_mask, n, a);
+}
+
+void grad_sqnorm(const void* grad, bool grad_is_bf16, int64_t n, float* out, cudaStream_t stream) {
+  int grid = grid_for((n + 7) / 8);
+  if (grid > kNumSMs * 2) grid = kNumSMs * 2;
+  if (grad_is_bf16)
+    grad_sqnorm_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(grad), n, out);
+  else
+    grad_sqnorm_kernel<float><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const float*>(grad), n, out);
+}
+
+void clip_scale(const float* parts, int nparts, int stride, float max_norm, float* grad_scale, float* norm_out,
+                cudaStream_t stream) {
+  clip_scale_kernel<<<1, 32, 0, stream>>>(parts, nparts, stride, max_norm, grad_scale, norm_out);
 }
 
 void adam_step(void* param_lp, float* master, float* m, float* v, const void* grad,

@@ -240,12 +240,13 @@ def _bn_fusable(hook, x, channels) -> bool:
             and channels % 8 == 0 and native().persistent_gemm_enabled())
 
 
-# EXPERIMENTAL, off by default.  The epilogue reduction itself is exact (tests/test_persist_gpu.py checks it
-# against the fp32 reference for 1x1 / 3x3 / residual-mask / partial-tile cases), but (a) with 31+31 shuffles
-# and 64 extra shared loads per 32 columns the short-K dgrad kernels become epilogue-bound: 46-59 us instead
-# of 15 us + a 12-14 us streaming reduce kernel (profiles/README.md), and (b) the model-level gradient
-# comparison still shows a mismatch that is not understood yet.  Kept for round 2.
-FUSE_BN_BWD = __import__("os").environ.get("EDL_FUSE_BN_BWD", "0") == "1"
+# ON by default since round 2 (EDL_FUSE_BN_BWD=0 turns it off): the BatchNorm-backward reduction of a conv's input
+# gradient rides in that conv's dgrad epilogue as a column-pair loop over the staged tiles (csrc/gemm_persist.cu,
+# bnr mode 2).  Validated on B200 at kernel level and at model level against the stand-alone reduction kernels with
+# the run-to-run atomics noise as yardstick (tests/test_persist_gpu.py); removes 44 bn_bwd_reduce launches per
+# ResNet50_vd step: 4.746 -> 4.618 ms (profiles/bench_runs.json).  The round-1 shuffle version (mode 1, 46-59 us per
+# short-K dgrad kernel) stays selectable with EDL_BNR_MODE=1.
+FUSE_BN_BWD = __import__("os").environ.get("EDL_FUSE_BN_BWD", "1") == "1"
 
 
 class _LinearFn(torch.autograd.Function):
@@ -490,10 +491,10 @@ def conv3x3(x, weight_krsc, stats: Optional[torch.Tensor] = None):
     return _Conv3x3Fn.apply(x, weight_krsc, stats, sink, ready, getattr(x, "_edl_bn_hook", None))
 
 
-# EXPERIMENTAL until validated on a GPU: EDL_CONV3_S2=1 runs 3x3 / pad 1 / STRIDE 2 forward convolutions (student:
-# first block of stages 2-4; teacher: the grouped ones, today "stride 1 then subsample" = 4x the MMA work) on the
-# persistent tcgen05 kernel; the input is sampled by the TMA traversal stride (csrc/gemm_persist.cu).
-CONV3_S2 = __import__("os").environ.get("EDL_CONV3_S2", "0") == "1"
+# 3x3 / pad 1 / STRIDE 2 forward convolutions (student: first block of stages 2-4; teacher: the grouped ones, which
+# round 1 ran as "stride 1 then subsample" = 4x the MMA work) on the persistent tcgen05 kernel; the input is sampled
+# by the TMA traversal stride (csrc/gemm_persist.cu).  Validated on B200 in round 2, on by default (EDL_CONV3_S2=0: off).
+CONV3_S2 = __import__("os").environ.get("EDL_CONV3_S2", "1") == "1"
 
 
 def conv3x3_s2_supported(x, weight_krsc, groups=1) -> bool:
@@ -551,10 +552,9 @@ def conv3x3_s2(x, weight_krsc, stats: Optional[torch.Tensor] = None):
     return _Conv3x3S2Fn.apply(x, weight_krsc, stats, sink, ready)
 
 
-# EXPERIMENTAL until validated on a GPU: EDL_OWN_STEM1=1 runs the first stem convolution (3 -> 32 channels, 3x3 /
-# stride 2) on the direct kernel of csrc/stem.cu with the BatchNorm statistics fused in (the library kernel takes 74 us
-# for what is ~5 us of memory traffic, plus a separate statistics pass).
-OWN_STEM1 = __import__("os").environ.get("EDL_OWN_STEM1", "0") == "1"
+# The first stem convolution (3 -> 32 channels, 3x3 / stride 2) runs on the direct kernel of csrc/stem.cu with the
+# BatchNorm statistics fused in.  Validated on B200 in round 2, on by default (EDL_OWN_STEM1=0: library kernel).
+OWN_STEM1 = __import__("os").environ.get("EDL_OWN_STEM1", "1") == "1"
 
 
 def stem_conv_supported(x, weight_krsc) -> bool:

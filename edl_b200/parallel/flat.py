@@ -111,6 +111,20 @@ class FlatParams:
                 if self.direct_sinks:
                     e.param._edl_grad_sink = gview
 
+    def rebind_params(self, param_alloc: Callable, dtypes=None):
+        """Move the flat model-precision parameters of the given dtype groups into storage provided by
+        ``param_alloc(numel, dtype, device)`` (a window of symmetric memory: the fused reduce-scatter -> SGD ->
+        all-gather kernel stores the new parameters into every rank's copy).  Values are carried over."""
+        for dt, g in self.groups.items():
+            if dtypes is not None and dt not in dtypes:
+                continue
+            new = param_alloc(g.numel, g.dtype, self.device)
+            with torch.no_grad():
+                new.copy_(g.param)
+            g.param = new
+            for e in g.entries:
+                e.param.data = g.param[e.offset:e.offset + e.numel].view(e.param.shape)
+
     def sync_master_from_params(self):
         for g in self.groups.values():
             if g.master is not None:

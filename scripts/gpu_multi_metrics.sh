@@ -27,7 +27,7 @@ for sec in $SECTIONS; do
         --out gpurun_out/rescale_${N}gpu.json > gpurun_out/rescale_${N}gpu.log 2>&1
       tail -n 2 gpurun_out/rescale_${N}gpu.log ;;
     tests)
-      EDL_TEST_EXPERIMENTAL=1 timeout 500 python -m pytest tests/test_experimental_gpu.py -q -k "agreement or hierarchical" \
+      timeout 500 python -m pytest tests/test_round2_gpu.py -q -k "agreement or hierarchical" \
         > gpurun_out/multi_tests.log 2>&1
       tail -n 3 gpurun_out/multi_tests.log ;;
     launch)

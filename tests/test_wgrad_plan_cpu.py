@@ -2,7 +2,7 @@
 planner is called through the built extension, and the kernel's data movement -- 4-D boxes {64 ch, W, BH rows, NB images}
 of dY and of X shifted by (s-1, r-1), out-of-image elements zero-filled, one [Cout, Cin] product per tap accumulated over
 the pixel blocks, result laid out KRSC -- is replayed with torch ops and compared with autograd's weight gradient.
-What this cannot cover (descriptors, swizzle, barriers) is what tests/test_experimental_gpu.py is for."""
+What this cannot cover (descriptors, swizzle, barriers) is what tests/test_round2_gpu.py is for."""
 import pytest
 import torch
 import torch.nn.functional as F

@@ -8,6 +8,8 @@ captures exactly the kernel of interest.
   bnbwd  N C H W [fused|stream|regs] [res]
   bnfwd  N C H W [fused|stream|regs] [res]
   conv3 / conv3dgrad  N CIN COUT H W   tcgen05 implicit-GEMM 3x3 convolution
+  wgrad3 N CIN COUT H W [SPLIT]        tcgen05 3x3 weight gradient
+  sgd | softce B | rope T H D          fused optimizer / loss / rotary kernels
 """
 import os
 import sys
@@ -73,5 +75,32 @@ elif op in ("conv3", "conv3dgrad"):
     y = torch.empty(n, k if op == "conv3" else c, h, w, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
     st = torch.zeros(2 * k, device=dev)
     run(lambda: ops.native().conv3x3(x, wt, y, op != "conv3", st if op == "conv3" else None, None, False))
+elif op == "wgrad3":
+    n, c, k, h, w = [int(v) for v in a[:5]]          # batch, Cin, Cout, H, W
+    from edl_b200.ops import gemm as G
+    x = torch.randn(n, c, h, w, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    dy = (torch.randn(n, k, h, w, device=dev) * 0.1).bfloat16().contiguous(memory_format=torch.channels_last)
+    sink = torch.zeros(k * 9 * c, device=dev, dtype=torch.bfloat16)
+    split = int(a[5]) if len(a) > 5 else None
+    run(lambda: G.conv3x3_wgrad(x, dy, (k, 3, 3, c), sink, split_k=split))
+elif op == "sgd":
+    from edl_b200.parallel import FlatParams
+    lin = torch.nn.Linear(5000, 5000, bias=False).to(dev)
+    lin.weight.data = lin.weight.data.bfloat16()
+    flat = FlatParams(lin)
+    opt = ops.FlatSGDMomentum(flat, lr=0.1)
+    for g in flat.groups.values():
+        g.grad.normal_()
+    run(lambda: opt.step())
+elif op == "softce":
+    z = torch.randn(int(a[0]), 1000, device=dev).bfloat16().requires_grad_(True)
+    tt = torch.softmax(torch.randn(int(a[0]), 1000, device=dev), -1).bfloat16()
+    run(lambda: ops.soft_cross_entropy(z, tt).backward())
+elif op == "rope":
+    T, H, D = int(a[0]), int(a[1]), int(a[2])
+    xq = torch.randn(T, H, D, device=dev).bfloat16()
+    from edl_b200.ops.misc import rope, rope_tables
+    cos, sin = rope_tables(T, D, device=dev)
+    run(lambda: rope(xq, cos, sin))
 else:
     raise SystemExit("unknown op " + op)
