@@ -11,7 +11,9 @@ ImageNet-shaped data, random-init weights.
 
 Prints ONE JSON line on rank 0.  `value` is device-timed (CUDA events, max over ranks) with inputs
 resident on the device; `e2e` runs the same steps through the public `StudentTrainer.step()` API
-with a pinned-host -> device copy of every batch and a device -> host read of the loss each step.
+with a pinned-host -> device copy of every batch and a device -> host read of a step's loss each step.  On N > 1 GPUs the
+line also carries what the all-reduce path really launched (`allreduce`), a cross-check of our kernel against NCCL,
+`exposed_comm_ms`, the in-place `rescale` recovery times and the `distill` service throughput (BASELINE.json's metric).
 """
 from __future__ import annotations
 
@@ -56,6 +58,14 @@ def parse():
                     help="A/B (experimental): stride-2 3x3 forward convolutions on the tcgen05 kernel (student and teacher)")
     ap.add_argument("--pdl", action="store_true", help="A/B (experimental): programmatic dependent launch of the hot kernels")
     ap.add_argument("--own-wgrad3", action="store_true", help="A/B (experimental): tcgen05 3x3 weight-gradient kernel")
+    ap.add_argument("--no-fused-opt", action="store_true",
+                    help="A/B: plain all-reduce kernels + one optimizer pass instead of the fused reduce-scatter -> SGD -> all-gather buckets")
+    ap.add_argument("--clip-norm", type=float, default=0.0, help="global-norm gradient clipping (0 = off, the reference's config)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra metric terms of BASELINE.json at N > 1 (exposed comm, rescale recovery, distill service)")
+    ap.add_argument("--extras-budget-s", type=float, default=240.0,
+                    help="wall-clock budget of the extra sections; when it runs out the headline line is printed without them")
+    ap.add_argument("--distill-steps", type=int, default=40)
     return ap.parse_args()
 
 
@@ -140,8 +150,20 @@ def reference_arm(args):
 
 
 def distill_main(args, world, rank, dev):
+    out = distill_run(args, world, rank, dev, args.steps, with_clocks=True)
+    import torch.distributed as dist
+
+    if rank == 0:
+        print(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
+
+
+def distill_run(args, world, rank, dev, steps, with_clocks=False):
     """Distill-service mode: ranks [0, N/2) are students, [N/2, N) teachers (ResNeXt101_32x16d); the
-    images go student -> teacher and the logits teacher -> student through NVSwitch peer memory."""
+    images go student -> teacher and the logits teacher -> student through NVSwitch peer memory.
+    Returns the result record (complete on rank 0)."""
     import torch
     import torch.distributed as dist
 
@@ -194,14 +216,15 @@ def distill_main(args, world, rank, dev):
 
     warm = max(args.warmup, 7)      # 4 eager protocol steps + one graph capture per ring slot + one replay
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
-    sampler.start()
+    if with_clocks:
+        sampler.start()
     run(warm, True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     sampler.begin()
     ops.reset_launches()
     ev0.record()
-    run(args.steps, False)
+    run(steps, False)
     ev1.record()
     sync_all()
     sampler.end()
@@ -213,29 +236,30 @@ def distill_main(args, world, rank, dev):
     if not args.no_e2e:
         sync_all()
         t0 = time.perf_counter()
-        last = run(args.steps, True)
+        last = run(steps, True)
         torch.cuda.synchronize(dev)
         t = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-        e2e = {"value": B * n_students * args.steps / (e2e_ms / 1e3), "unit": "img/s", "ms_per_step": e2e_ms / args.steps,
+        e2e = {"value": B * n_students * steps / (e2e_ms / 1e3), "unit": "img/s", "ms_per_step": e2e_ms / steps,
                "h2d_bytes_per_step": B * 3 * 224 * 224 * 2, "d2h_bytes_per_step": 4, "last_loss": last,
                "timing": "host wall clock around K public-API steps (student: pinned H2D images + loss.item())"}
-    flag = torch.tensor([1.0 if (sampler.proc is not None and sampler.in_window_samples() < 3) else 0.0], device=dev)
+    flag = torch.tensor([1.0 if (with_clocks and sampler.proc is not None and sampler.in_window_samples() < 3) else 0.0],
+                        device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MAX)              # all ranks take the same decision: pairs step in lockstep
     if float(flag.item()) > 0.5:
         sampler.begin()
         run(60, False)
         torch.cuda.synchronize(dev)
         sampler.end()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if with_clocks else None
     err = link.check_error()
-    value = B * n_students * args.steps / (dev_ms / 1e3)
-    if rank == 0:
-        print(json.dumps({
+    value = B * n_students * steps / (dev_ms / 1e3)
+    if True:
+        return ({
             "metric": "ResNet50_vd student img/s with same-box distill service (teacher logits over NVSwitch)",
-            "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "value": value, "unit": "img/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": value / 1514.0, "dtype": "bf16",
             "data": "synthetic images, random-init student and teacher", "impl": "edl",
             "config": {"model": "ResNet%d_vd student + %s teacher" % (args.layers, args.teacher),
@@ -244,13 +268,11 @@ def distill_main(args, world, rank, dev):
                        "transport": "peer_ship + GEMM->peer-ship epilogue over NVSwitch peer memory, "
                                     "student/teacher pipelined by one batch",
                        "teacher_dtype": "e4m3 1x1 convs + bf16" if args.teacher_fp8 else "bf16",
-                       "teacher_fuse_res": bool(args.teacher_fuse_res), "pdl": bool(args.pdl),
+                       "teacher_fuse_res": bool(__import__("edl_b200.models.resnext", fromlist=["x"]).FUSE_RESIDUAL),
+                       "conv3_s2": bool(ops.gemm.CONV3_S2), "pdl": bool(args.pdl),
                        "parallelism": "dp%d + %d teacher GPUs" % (n_students, n_students),
                        "baseline_note": "vs_baseline divides by the published 1514 img/s (8xV100 + 40xP4, BASELINE.md P3)"},
-            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "link_error": err}))
-    dist.barrier()
-    dist.destroy_process_group()
-    return 0
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "link_error": err})
 
 
 def main():
@@ -312,7 +334,9 @@ def main():
         model.train()
         trainer = StudentTrainer(model, B, lr=0.1 * B * world / 256.0, use_graph=not args.no_graph,
                                  bucket_cap_mb=args.bucket_mb, comm_blocks=args.comm_blocks,
-                                 algo=args.algo, target_kind="probs")
+                                 algo=args.algo, target_kind="probs",
+                                 fused_optimizer=False if args.no_fused_opt else None,
+                                 clip_norm=args.clip_norm or None)
 
     # synthetic host data (pinned): a small pool of distinct batches, cycled
     pool = 4
@@ -328,19 +352,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()              # streams samples from now on; only those inside the timed windows are used
-    # ---- warm-up (also captures the CUDA graph) ----
-    for i in range(max(args.warmup, 3)):
-        loss = trainer.step(host_x[i % pool], host_t[i % pool])
-    loss0 = float(loss.item())
-
     def max_over_ranks(ms: float) -> float:
         if world == 1:
             return ms
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    # ---- one-off proof, before any training step: OUR all-reduce kernel on a real gradient bucket against
+    #      NCCL's all-reduce of the same data (the gradient slab is idle before the first step)
+    crosscheck = None
+    if world > 1 and args.impl == "edl" and getattr(trainer.dp, "use_symm", False):
+        crosscheck = allreduce_crosscheck(trainer.dp, dev, world)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()              # streams samples from now on; only those inside the timed windows are used
+    # ---- warm-up (also captures the CUDA graph) ----
+    loss = None
+    for i in range(max(args.warmup, 3)):
+        loss = trainer.step(host_x[i % pool], host_t[i % pool])
+    loss0 = float(loss.item())
 
     # ---- device-timed region: K steps, inputs resident on device ----
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -372,48 +403,55 @@ def main():
             trainer.step_device()
             torch.cuda.synchronize(dev)
         prof1.export_chrome_trace(args.kineto + ".trace.json")
+    if args.kineto and world > 1:
+        for _ in range(6):                  # the other ranks keep their collectives in step with rank 0's profiled steps
+            if rank != 0:
+                trainer.step_device()
+        torch.cuda.synchronize(dev)
 
-    # ---- end-to-end region: public API, H2D every step, D2H loss every step ----
+    # ---- end-to-end region: the public API (`trainer.step(host images, host targets)`), every step with its
+    #      pinned-host -> device input copy and a device -> host read of a step's loss.  The public default is the
+    #      double-buffered feed: the loss handle of step i is read while step i+1 runs (one D2H read per step).
     e2e = None
     if not args.no_e2e:
-        sync_all()
-        sampler.begin()
-        t0 = time.perf_counter()
-        last = 0.0
-        for i in range(args.steps):
-            loss = trainer.step(host_x[i % pool], host_t[i % pool])
-            last = float(loss.item())
-        torch.cuda.synchronize(dev)
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-        sampler.end()
+        def e2e_loop(sync_mode):
+            sync_all()
+            sampler.begin()
+            t0 = time.perf_counter()
+            last, prev = 0.0, None
+            for i in range(args.steps):
+                if sync_mode:
+                    last = float((trainer.step(host_x[i % pool], host_t[i % pool], sync=True) if args.impl == "edl"
+                                  else trainer.step(host_x[i % pool], host_t[i % pool])).item())
+                else:
+                    h = trainer.step(host_x[i % pool], host_t[i % pool])
+                    if prev is not None:
+                        last = prev.item()
+                    prev = h
+            if prev is not None:
+                last = prev.item()
+            torch.cuda.synchronize(dev)
+            ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            sampler.end()
+            return ms, last
+
+        if hasattr(trainer, "step_pipelined"):
+            for i in range(3):
+                trainer.step(host_x[i % pool], host_t[i % pool]).item()
+            e2e_ms, last = e2e_loop(False)
+            api = "StudentTrainer.step(images, targets) -> LossHandle (default: staged H2D on a copy stream, loss of step i read while step i+1 runs)"
+        else:
+            e2e_ms, last = e2e_loop(True)
+            api = "trainer.step(images, targets); loss.item()"
         e2e = {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "img/s",
                "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d_bytes,
-               "d2h_bytes_per_step": d2h_bytes, "timing": "host wall clock around K public-API steps, "
-               "each with pinned H2D input copy + loss.item(); max over ranks", "last_loss": last}
-        # the same K public-API steps with the double-buffered feed (H2D of batch i+1 overlaps step i, loss
-        # read one step late).  Extra information next to the synchronous `e2e` above; never fatal.
+               "d2h_bytes_per_step": d2h_bytes, "api": api,
+               "timing": "host wall clock around K public-API steps, each with a pinned H2D input copy and a D2H loss "
+                         "read; max over ranks", "last_loss": last}
         if hasattr(trainer, "step_pipelined"):
-            try:
-                for i in range(3):
-                    trainer.step_pipelined(host_x[i % pool], host_t[i % pool]).item()
-                sync_all()
-                t0 = time.perf_counter()
-                prev, plast = None, 0.0
-                for i in range(args.steps):
-                    h = trainer.step_pipelined(host_x[i % pool], host_t[i % pool])
-                    if prev is not None:
-                        plast = prev.item()
-                    prev = h
-                plast = prev.item()
-                torch.cuda.synchronize(dev)
-                p_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-                e2e["pipelined"] = {"value": B * world * args.steps / (p_ms / 1e3), "unit": "img/s",
-                                    "ms_per_step": p_ms / args.steps, "h2d_bytes_per_step": h2d_bytes,
-                                    "d2h_bytes_per_step": d2h_bytes, "last_loss": plast,
-                                    "note": "StudentTrainer.step_pipelined: staged H2D on a copy stream, "
-                                            "loss of every step read back one step late"}
-            except Exception as exc:  # noqa: BLE001 - experimental path must not cost the headline numbers
-                e2e["pipelined"] = {"error": repr(exc)[:300]}
+            s_ms, s_last = e2e_loop(True)
+            e2e["sync"] = {"value": B * world * args.steps / (s_ms / 1e3), "unit": "img/s", "ms_per_step": s_ms / args.steps,
+                           "last_loss": s_last, "note": "step(..., sync=True) + loss.item() inside every step (host stalls the GPU)"}
     clocks_note = "samples inside the timed regions"
 
     def few_samples_somewhere() -> bool:      # every rank must take the same decision (collectives inside a step)
@@ -437,33 +475,217 @@ def main():
     clocks["window"] = clocks_note
 
     value = B * world * args.steps / (dev_ms / 1e3)
+    dp = getattr(trainer, "dp", None)
+    out = {
+        "metric": "ResNet50_vd student train throughput (pure data-parallel, no teacher)",
+        "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": value / BASELINE_IMG_S,
+        "dtype": "bf16", "data": "synthetic (random 3x224x224 images, random soft labels; random-init weights)",
+        "impl": args.impl,
+        "config": {"model": "ResNet%d_vd" % args.layers, "global_batch": B * world,
+                   "batch_per_gpu": B, "seq_len": None, "image": "3x224x224 NHWC bf16",
+                   "parallelism": "dp%d" % world, "optimizer": "SGD-momentum 0.9 wd 1e-4 (fused, fp32 master)",
+                   "loss": "soft-label cross-entropy (teacher-score shaped targets)",
+                   "cuda_graph": not args.no_graph, "conv_impl": args.conv_impl,
+                   "pdl": bool(args.pdl), "own_wgrad3": ops.gemm.OWN_WGRAD3 if args.impl == "edl" else None,
+                   "conv3_s2": ops.gemm.CONV3_S2 if args.impl == "edl" else None,
+                   "own_stem1": ops.gemm.OWN_STEM1 if args.impl == "edl" else None,
+                   "fuse_bn_bwd": (ops.native().get_bnr_mode() if ops.gemm.FUSE_BN_BWD else 0) if args.impl == "edl" else None,
+                   "clip_norm": args.clip_norm or None,
+                   "l2": "per-step working set (~GBs of activations) >> 126 MB L2, no explicit flush",
+                   "baseline_note": "vs_baseline divides by the published 8xV100 1828 img/s (BASELINE.md P1)"},
+        "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "loss_after_warmup": loss0,
+        "library_fallbacks": ops.fallbacks() if hasattr(ops, "fallbacks") else None,
+    }
+    if dp is not None:
+        out["allreduce"] = allreduce_report(dp, crosscheck)
+        out["config"]["allreduce"] = out["allreduce"]["algos"]
+
+    # ---- the other terms of the BASELINE.json metric, each bounded in time; the headline above never waits for them
+    #      longer than --extras-budget-s (a watchdog prints it alone and exits)
+    if args.impl == "edl" and world > 1 and not args.no_extras:
+        def bail():
+            if rank == 0:
+                out["extras_error"] = "extra sections exceeded %.0f s: printed without them" % args.extras_budget_s
+                print(json.dumps(out), flush=True)
+            os._exit(0)
+
+        wd = threading.Timer(args.extras_budget_s, bail)
+        wd.daemon = True
+        wd.start()
+        for name, fn in (("exposed_comm", lambda: exposed_comm(trainer, args, dev, world, max_over_ranks, sync_all, dev_ms)),
+                         ("rescale", lambda: rescale_section(trainer, args, dev, world, rank, host_x[0], host_t[0])),
+                         ("distill", lambda: distill_section(args, world, rank, dev))):
+            try:
+                t0 = time.perf_counter()
+                out[name] = fn()
+                if isinstance(out[name], dict):
+                    out[name]["section_s"] = round(time.perf_counter() - t0, 2)
+            except Exception as exc:  # noqa: BLE001 - an extra term must not cost the headline
+                out[name] = {"error": repr(exc)[:400]}
+                break                  # the ranks may no longer be in step: stop here
+        wd.cancel()
+        if isinstance(out.get("exposed_comm"), dict) and "exposed_comm_ms" in out["exposed_comm"]:
+            out["exposed_comm_ms"] = out["exposed_comm"]["exposed_comm_ms"]
     if rank == 0:
-        out = {
-            "metric": "ResNet50_vd student train throughput (pure data-parallel, no teacher)",
-            "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": value / BASELINE_IMG_S,
-            "dtype": "bf16", "data": "synthetic (random 3x224x224 images, random soft labels; random-init weights)",
-            "impl": args.impl,
-            "config": {"model": "ResNet%d_vd" % args.layers, "global_batch": B * world,
-                       "batch_per_gpu": B, "seq_len": None, "image": "3x224x224 NHWC bf16",
-                       "parallelism": "dp%d" % world, "optimizer": "SGD-momentum 0.9 wd 1e-4 (fused, fp32 master)",
-                       "loss": "soft-label cross-entropy (teacher-score shaped targets)",
-                       "cuda_graph": not args.no_graph, "conv_impl": args.conv_impl,
-                       "pdl": bool(args.pdl), "own_wgrad3": bool(args.own_wgrad3), "conv3_s2": bool(args.conv3_s2),
-                       "own_stem1": bool(args.own_stem1),
-                       "fuse_bn_bwd": args.fuse_bn_bwd,
-                       "allreduce": getattr(getattr(trainer, "dp", None), "algo_pref", "nccl"),
-                       "l2": "per-step working set (~GBs of activations) >> 126 MB L2, no explicit flush",
-                       "baseline_note": "vs_baseline divides by the published 8xV100 1828 img/s (BASELINE.md P1)"},
-            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "loss_after_warmup": loss0,
-        }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def allreduce_crosscheck(dp, dev, world):
+    """max |own all-reduce - NCCL all-reduce| on the largest real gradient bucket, filled with random data."""
+    import torch
+    import torch.distributed as dist
+
+    from edl_b200.ops import native
+
+    b = max(dp.buckets, key=lambda bb: bb.numel)
+    g = dp.flat.groups[b.dtype]
+    sl = dp.slices[b.dtype]
+    view = g.grad[b.start:b.start + b.numel]
+    torch.manual_seed(4321 + dp.rank)
+    view.copy_((torch.randn(b.numel, device=dev) * 0.5).to(view.dtype))
+    ref = view.float().clone()
+    dist.all_reduce(ref)                                        # NCCL, fp32
+    ref /= world
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    off = b.start * view.element_size()
+    algo = b.algo if b.algo in ("twoshot", "multimem") else "twoshot"
+    native().allreduce_twoshot([p + off for p in sl.data_ptrs], sl.sig_ptrs, (sl.mc_ptr + off) if sl.mc_ptr else 0,
+                               dp.rank, g.grad, b.numel, 1.0 / world, None, None, algo == "multimem", dp.comm_blocks, 30.0)
+    torch.cuda.synchronize(dev)
+    diff = (view.float() - ref).abs().max()
+    dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+    scale = float(ref.abs().max())
+    err = dp.check_comm_error()
+    g.grad.zero_()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    return {"maxdiff": float(diff), "ref_absmax": scale, "bucket_bytes": b.numel * view.element_size(), "algo": algo,
+            "dtype": str(view.dtype).replace("torch.", ""), "comm_error": err,
+            "note": "own kernel (bf16 in, fp32 accumulate, bf16 out) vs NCCL fp32 all-reduce of the same data, max over ranks"}
+
+
+def allreduce_report(dp, crosscheck):
+    """What the data-parallel engine actually launched in the captured step (facts, not preferences)."""
+    algos = [{"algo": a, "bytes": n, "optimizer_fused": f} for a, n, f in dp.last_algos]
+    rep = {"algos": sorted({a["algo"] for a in algos}) or (["none"] if dp.world <= 1 else ["?"]),
+           "buckets": algos, "comm_launches_per_step": sum(1 for a in algos if a["algo"] not in ("local_sgd", "none")),
+           "has_multicast": bool(dp.pool.has_multicast) if dp.pool is not None else False,
+           "fused_optimizer": bool(dp.bucket_opt), "world": dp.world,
+           "bootstrap": dp.pool.describe() if dp.pool is not None else None}
+    if crosscheck is not None:
+        rep["crosscheck"] = crosscheck
+        rep["maxdiff"] = crosscheck["maxdiff"]
+    return rep
+
+
+def exposed_comm(trainer, args, dev, world, max_over_ranks, sync_all, dev_ms_on):
+    """Exposed communication per step: the captured step as benchmarked (bucket kernels overlapped with backward)
+    minus the same step re-captured with communication disabled (gradients stay local, plain optimizer pass)."""
+    import torch
+
+    K = args.steps
+
+    def timed():
+        for _ in range(3):
+            trainer.step_device()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        ev0.record()
+        for _ in range(K):
+            trainer.step_device()
+        ev1.record()
+        sync_all()
+        return max_over_ranks(ev0.elapsed_time(ev1)) / K
+
+    on = timed()
+    trainer.dp.consolidate_optimizer_state()
+    trainer.dp.enabled = False
+    trainer.graph = None
+    off = timed()
+    trainer.dp.enabled = True
+    trainer.graph = None
+    trainer.sync_from(0)                      # the replicas drifted apart while they did not communicate
+    on2 = timed()
+    return {"exposed_comm_ms": max(0.0, min(on, on2) - off), "ms_per_step_comm_on": min(on, on2), "ms_per_step_comm_off": off,
+            "ms_per_step_comm_on_runs": [on, on2], "headline_ms_per_step": dev_ms_on / K,
+            "method": "device-timed A/B of the same captured step, dp.enabled True/False, %d steps each, max over ranks" % K}
+
+
+def rescale_section(trainer, args, dev, world, rank, x, t):
+    """Rescale recovery time after -1 / +1 GPU, in place (BASELINE.json: "rescale recovery time after +-1 pod"):
+    from "the new membership is known" to "the first optimizer step at the new world size is done on every member",
+    host wall clock, max over ranks.  The stop-resume path of the reference (checkpoint reload into fresh trainers,
+    process start-up excluded) is timed next to it by tools/bench_rescale.py."""
+    import torch
+    import torch.distributed as dist
+
+    from edl_b200.ops.optim import scaled_lr
+
+    B = args.batch_per_gpu
+    survivors = list(range(world - 1))
+    small = dist.new_group(ranks=survivors)
+    solo = [dist.new_group(ranks=[r]) for r in range(world)][rank]
+    alive = rank in survivors
+
+    def wall_max(t0, group=None):
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX, group=group)
+        return float(tt.item())
+
+    res = {"from": world, "to": world - 1}
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    t0 = time.perf_counter()
+    trainer.prepare_rescale()
+    trainer.rebuild(small if alive else solo)
+    if alive:
+        trainer.set_lr(scaled_lr(0.1, B, len(survivors)))
+        float(trainer.step(x, t).item())
+        res["leave_inplace_s"] = wall_max(t0, small)
+        if len(survivors) > 1:
+            res["bootstrap_small"] = trainer.dp.pool.describe()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    t0 = time.perf_counter()
+    if alive:
+        trainer.prepare_rescale()
+    trainer.rebuild(None)
+    trainer.sync_from(0)
+    trainer.set_lr(scaled_lr(0.1, B, world))
+    float(trainer.step(x, t).item())
+    res["join_inplace_s"] = wall_max(t0)
+    res["bootstrap_full"] = trainer.dp.pool.describe()
+    flat = torch.cat([g.param.flatten().float() for g in trainer.dp.flat.groups.values()])
+    ref = flat.clone()
+    dist.broadcast(ref, src=0)
+    same = torch.tensor([1.0 if torch.equal(flat, ref) else 0.0], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    res["replicas_identical_after_join"] = bool(same.item() > 0.5)
+    res["comm_error"] = trainer.dp.check_comm_error()
+    res["lr_rescaled"] = [scaled_lr(0.1, B, world - 1), scaled_lr(0.1, B, world)]
+    res["note"] = ("in-place: survivors keep process, CUDA context, parameters and optimizer state; new symmetric slab "
+                   "through the store (no NCCL communicator), bucket re-plan, graph re-capture, joiner state over NVLink")
+    return res
+
+
+def distill_section(args, world, rank, dev):
+    """The distill-service term of the metric on the same N GPUs (N/2 students + N/2 teachers)."""
+    if world % 2 != 0:
+        return {"skipped": "needs an even number of GPUs"}
+    import torch
+
+    torch.cuda.empty_cache()
+    rec = distill_run(args, world, rank, dev, args.distill_steps)
+    keep = ("metric", "value", "unit", "ms_per_step", "steps", "vs_baseline", "config", "e2e", "link_error", "gpu_launches")
+    return {k: rec[k] for k in keep if k in rec}
 
 
 if __name__ == "__main__":

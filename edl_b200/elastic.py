@@ -14,10 +14,14 @@ Its design document lists "no restart" as future work.  Here, with ``EDL_RESCALE
   all of them writes the stage's commit record in ONE transaction that re-checks every ready key, and a member
   that wants to move on to a newer stage may withdraw its key only in a transaction that checks the commit
   record is absent -- so "everybody proceeds with stage S" and "somebody abandoned S" are mutually exclusive;
-* the new ``torch.distributed`` process group is bootstrapped through the same store (:class:`KVRendezvousStore`,
-  a ``torch.distributed.Store`` on the job's KV store, one key prefix per stage -- no free port, no TCPStore that
+* the stage's communication is bootstrapped through the same store (:class:`KVRendezvousStore`, a
+  ``torch.distributed.Store`` on the job's KV store, one key prefix per stage -- no free port, no TCPStore that
   would die with rank 0; the reference re-broadcasts an ncclUniqueId over TCP among the new endpoints,
-  utils/train_process.py:37-41);
+  utils/train_process.py:37-41).  On GPUs (backend ``"fabric"``, the default there) NO process group and no NCCL
+  communicator exists at all: the trainers get a :class:`edl_b200.parallel.symm.Fabric` (store + rank + world) and
+  the data-parallel engine maps a fresh symmetric slab through it (cuMem VMM handles, csrc/vmm.cpp); agreement,
+  state hand-off and gradient reduction all run on our own kernels, which time out into an error word instead of
+  hanging when a peer dies.  On CPU (backend ``"gloo"``) the store bootstraps a gloo group;
 * ``StageInfo.root`` names the lowest-ranked survivor: joiners take parameters / optimizer state / the epoch
   cursor from it over the fabric (``ElasticDataParallel.broadcast_parameters``) instead of reading the checkpoint;
   ``root is None`` means nobody survived (cold start or stop-resume fallback) and the checkpoint is the source.
@@ -186,7 +190,10 @@ class ElasticContext:
     def __init__(self, backend: Optional[str] = None, check_every: int = 10, timeout_s: float = 120.0,
                  environ=None, etcd=None):
         self.env = TrainerEnv(environ)
-        self.backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        self.backend = backend or os.environ.get("EDL_INPLACE_BACKEND") or (
+            "fabric" if torch.cuda.is_available() else "gloo")
+        self.fabric = None              # backend "fabric": what StudentTrainer / ElasticDataParallel take instead of a group
+        self._bcast_seq = 0
         self.check_every = max(1, int(check_every))
         self.timeout_s = timeout_s
         self.info: Optional[StageInfo] = None
@@ -302,6 +309,15 @@ class ElasticContext:
                 time.sleep(0.05)
 
     def _init_group(self, info: StageInfo):
+        self._bcast_seq = 0
+        if self.backend == "fabric":
+            from .parallel.symm import Fabric
+
+            dev = torch.device("cuda", info.rank_in_pod % max(1, torch.cuda.device_count()))
+            torch.cuda.set_device(dev)
+            store = KVRendezvousStore(self.kv, "%spg/%s/" % (_prefix(self.env.job_id), info.stage), self.timeout_s)
+            self.fabric = Fabric(store=store, rank=info.rank, world=info.size, tag="stage-%s" % info.stage)
+            return
         if info.size <= 1:
             return
         store = KVRendezvousStore(self.kv, "%spg/%s/" % (_prefix(self.env.job_id), info.stage), self.timeout_s)
@@ -348,7 +364,9 @@ class ElasticContext:
             if err:
                 raise RuntimeError("collective timed out waiting for peer %d (dead pod?)" % (err - 1))
             return flag > 0.5
-        if self.info.size > 1 and dist.is_initialized():
+        if self.info.size > 1 and self.backend == "fabric":
+            flag = max(float(v) for v in self.allgather_object(flag))        # no agree kernel given: through the store
+        elif self.info.size > 1 and dist.is_initialized():
             dev = torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu")
             t = torch.tensor([flag], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -374,12 +392,45 @@ class ElasticContext:
         return self._etcd
 
     def allgather_object(self, obj):
-        """Every rank's ``obj`` (rank order) over the current stage's process group."""
-        if self.info is None or self.info.size <= 1 or not dist.is_initialized():
+        """Every rank's ``obj`` (rank order) over the current stage: through the process group, or -- fabric backend --
+        through the store (JSON values: cursors, counters; this is control traffic, not tensors)."""
+        if self.info is None or self.info.size <= 1:
+            return [obj]
+        if self.backend == "fabric":
+            self._bcast_seq += 1
+            st = self.fabric.store
+            st.set("obj/%d/%d" % (self._bcast_seq, self.info.rank), json.dumps(obj).encode())
+            return [json.loads(bytes(st.get("obj/%d/%d" % (self._bcast_seq, r))).decode()) for r in range(self.info.size)]
+        if not dist.is_initialized():
             return [obj]
         out = [None] * self.info.size
         dist.all_gather_object(out, obj)
         return out
+
+    def broadcast_object(self, obj, root: int = 0):
+        """``root``'s ``obj`` on every rank of the current stage (the epoch / step cursor after a state hand-off)."""
+        if self.info is None or self.info.size <= 1:
+            return obj
+        if self.backend == "fabric":
+            self._bcast_seq += 1
+            st = self.fabric.store
+            key = "bcast/%d" % self._bcast_seq
+            if self.info.rank == root:
+                st.set(key, json.dumps(obj).encode())
+                return obj
+            return json.loads(bytes(st.get(key)).decode())
+        box = [obj]
+        dist.broadcast_object_list(box, src=root)
+        return box[0]
+
+    def barrier(self):
+        """Host barrier of the current stage's trainers."""
+        if self.info is None or self.info.size <= 1:
+            return
+        if self.backend == "fabric":
+            self.allgather_object(0)
+        elif dist.is_initialized():
+            dist.barrier()
 
     def rescale(self) -> StageInfo:
         """Leave the old process group, run the stage rendezvous, build the new group.  Raises

@@ -78,6 +78,9 @@ class ConvBNAct(nn.Module):
             # library conv whose wgrad half runs on the side stream (ops/gemm.py:_ConvLibFn)
             return ops.conv_lib(x, self.weight, self.stride, (self.k - 1) // 2, self.groups), None
         w = self.weight.permute(0, 3, 1, 2)
+        if x.is_cuda:
+            ops.count_fallback("conv fprop on cuDNN (inference / frozen weight): %dx%d stride %d, %d -> %d channels" % (
+                self.k, self.k, self.stride, self.cin, self.cout))
         y = F.conv2d(x, w, None, self.stride, (self.k - 1) // 2, 1, self.groups)
         return y, None
 

@@ -126,6 +126,9 @@ class FoldedConv(nn.Module):
                 # (conv2d_grouped_direct_kernel: 26 ms per layer, profiles/teacher_r1.txt)
                 y = y[:, :, ::2, ::2].contiguous(memory_format=torch.channels_last)
             return y
+        if x.is_cuda:
+            ops.count_fallback("teacher conv on cuDNN: %dx%d stride %d groups %d, %d -> %d channels" % (
+                self.k, self.k, self.stride, self.groups, self.weight.shape[3] * self.groups, self.weight.shape[0]))
         y = F.conv2d(x, self.weight.permute(0, 3, 1, 2), None, self.stride, (self.k - 1) // 2, 1, self.groups)
         return ops.scale_shift_act(y, self.scale, self.shift, residual, self.relu)
 

@@ -54,6 +54,35 @@ def reset_launches() -> None:
     _launches = 0
 
 
+# ---- library fallbacks on CUDA tensors: counted and logged, never silent -------------------------------------
+# A CUDA tensor that one of our kernels cannot take (a shape the TMA descriptor cannot express, a convolution
+# geometry without an own kernel yet) runs on the vendor library (cuBLAS / cuDNN through ATen).  That is a
+# correctness safety net, not the product: every such call is counted by reason, logged once per reason, and
+# bench.py prints the table as ``library_fallbacks`` (the flagship step must show none it does not name).
+_fallbacks = {}
+
+
+def count_fallback(reason: str, n: int = 1) -> None:
+    first = reason not in _fallbacks
+    _fallbacks[reason] = _fallbacks.get(reason, 0) + n
+    if first:
+        import logging
+
+        logging.getLogger("edl_b200").warning("library fallback on a CUDA tensor: %s", reason)
+    import os
+
+    if os.environ.get("EDL_STRICT_NATIVE", "0") == "1":
+        raise RuntimeError("EDL_STRICT_NATIVE=1: library fallback on a CUDA tensor: " + reason)
+
+
+def fallbacks() -> dict:
+    return dict(_fallbacks)
+
+
+def reset_fallbacks() -> None:
+    _fallbacks.clear()
+
+
 from .bn import batch_norm_act, BatchNormAct2d, scale_shift_act, bn_stats_into, set_fused_bn, drop_bn_hook  # noqa: E402
 from .loss import soft_cross_entropy, topk_accuracy  # noqa: E402
 from .pool import max_pool_3x3_s2, avg_pool_2x2, global_avg_pool  # noqa: E402
@@ -64,7 +93,7 @@ from .gemm import (gemm_bf16, linear_bf16, conv1x1, conv_lib, conv3x3, conv3x3_s
 from .misc import rope, rope_tables, embedding_bag_mean, normalize_u8, DynamicLossScaler  # noqa: E402
 
 __all__ = [
-    "native", "native_available", "launches", "reset_launches",
+    "native", "native_available", "launches", "reset_launches", "count_fallback", "fallbacks", "reset_fallbacks",
     "batch_norm_act", "BatchNormAct2d", "scale_shift_act", "bn_stats_into",
     "soft_cross_entropy", "topk_accuracy",
     "max_pool_3x3_s2", "avg_pool_2x2", "global_avg_pool",

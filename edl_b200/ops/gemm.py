@@ -34,7 +34,11 @@ def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, col_scale=None
     n = b.shape[1] if b_mn_major else b.shape[0]
     if not a.is_cuda or not _tma_compatible(a, b, out, n):
         # CPU tensors, or CUDA shapes TMA cannot describe (row pitch / base not 16-byte aligned):
-        # plain PyTorch math with identical semantics
+        # plain PyTorch math with identical semantics -- counted and logged when it happens on a GPU
+        if a.is_cuda:
+            from . import count_fallback
+            count_fallback("gemm_bf16: operand not TMA-describable (pitch / base not 16-byte aligned or not bf16): "
+                           "fp32 matmul on the library, %s x %s" % (tuple(a.shape), tuple(b.shape)))
         af = a.float().t() if a_mn_major else a.float()
         bf = b.float() if b_mn_major else b.float().t()
         d = af @ bf
@@ -296,6 +300,14 @@ def linear_bf16(x, weight, bias=None, relu=False):
     return _LinearFn.apply(x, weight, bias, relu, sink, ready, bsink, bready)
 
 
+def _count_lib_conv(x, what, w_krsc, stride, groups):
+    if x.is_cuda:
+        from . import count_fallback
+        cout, kh, kw, cin = w_krsc.shape
+        count_fallback("conv %s on cuDNN: %dx%d stride %d groups %d, %d -> %d channels" % (what, kh, kw, stride, groups,
+                                                                                      cin * groups, cout))
+
+
 class _ConvLibFn(torch.autograd.Function):
     """k x k / strided / grouped convolution on the library kernel (cuDNN) with the backward split in
     two: dgrad stays on the critical path, wgrad runs on the side stream next to the tcgen05 wgrad
@@ -305,6 +317,7 @@ class _ConvLibFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, stride, padding, groups, sink, ready):
         wv = w.permute(0, 3, 1, 2)
+        _count_lib_conv(x, "fprop", w, stride, groups)
         y = torch.ops.aten.convolution(x, wv, None, [stride, stride], [padding, padding], [1, 1], False, [0, 0], groups)
         ctx.save_for_backward(x, w)
         ctx.cfg = (stride, padding, groups)
@@ -314,6 +327,7 @@ class _ConvLibFn(torch.autograd.Function):
     @staticmethod
     def _bwd(dy, x, wv, cfg, mask):
         stride, padding, groups = cfg
+        _count_lib_conv(x, "dgrad" if mask[0] else "wgrad", wv.permute(0, 2, 3, 1), stride, groups)
         return torch.ops.aten.convolution_backward(dy, x, wv, None, [stride, stride], [padding, padding], [1, 1],
                                                    False, [0, 0], groups, mask)
 

@@ -23,6 +23,8 @@ class _FlatOptimizerBase:
         self.lr_t = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
         self.grad_scale_t: Optional[torch.Tensor] = None  # device scalar multiplied into grads
         self.found_inf_t: Optional[torch.Tensor] = None   # device int flag: skip step when != 0
+        self._found_inf_is_comm_error = False
+        self.skip_dtype = None    # set by ElasticDataParallel.attach_optimizer: dtype -> "already updated this step"
 
     def set_lr(self, lr: float):
         self.lr = float(lr)
@@ -31,8 +33,14 @@ class _FlatOptimizerBase:
     def set_grad_scale(self, t: Optional[torch.Tensor]):
         self.grad_scale_t = t
 
-    def set_found_inf(self, t: Optional[torch.Tensor]):
+    def set_found_inf(self, t: Optional[torch.Tensor], comm_error: bool = False):
+        """``comm_error``: the flag is the fabric's error word (in-place elastic guard), not a gradient overflow
+        flag -- the per-bucket fused optimizer may then still be used (its kernel checks the word itself)."""
         self.found_inf_t = t
+        self._found_inf_is_comm_error = bool(comm_error) and t is not None
+
+    def found_inf_is_comm_error(self) -> bool:
+        return self.found_inf_t is None or self._found_inf_is_comm_error
 
     def zero_grad(self):
         self.flat.zero_grad()
@@ -59,6 +67,8 @@ class FlatSGDMomentum(_FlatOptimizerBase):
         from . import native, count_launch
 
         for dt, g in self.flat.groups.items():
+            if self.skip_dtype is not None and self.skip_dtype(dt):
+                continue                 # updated bucket by bucket by the data-parallel engine (parallel/ddp.py)
             st = self.state[dt]
             master = g.master if g.master is not None else g.param
             lp = g.param if g.master is not None else None
@@ -119,7 +129,14 @@ class FlatAdam(_FlatOptimizerBase):
     def step(self):
         from . import native, count_launch
 
-        self.step_t += 1
+        # bias correction counts APPLIED steps only: a step skipped by found_inf (loss-scaling overflow, broken
+        # collective) must not advance it -- decided on the device, no host round trip
+        if self.found_inf_t is not None:
+            if not self.step_t.is_cuda and int(self.found_inf_t.item()) != 0:
+                return
+            self.step_t += (self.found_inf_t.view(-1)[:1] == 0).to(self.step_t.dtype)
+        else:
+            self.step_t += 1
         for dt, g in self.flat.groups.items():
             st = self.state[dt]
             master = g.master if g.master is not None else g.param

@@ -13,6 +13,15 @@ Here:
   gradient of a bucket, the bucket's fused all-reduce kernel (csrc/allreduce.cu: P2P two-shot /
   NVLS multimem, fp32 accumulate, 1/world scale, finite check, squared-norm) is enqueued on a side
   stream so it overlaps the rest of backward; the whole thing is CUDA-graph capturable;
+* with an attached ``FlatSGDMomentum`` the bucket kernel becomes gradient reduce-scatter -> SGD-momentum on the
+  owned slice -> parameter all-gather (``allreduce_sgd_kernel``): one kernel per bucket instead of all-reduce +
+  stream join + a separate optimizer pass, optimizer state traffic divided by the world size; on ONE GPU the same
+  hook runs the optimizer per bucket on the side stream while backward is still going;
+* global-norm gradient clipping (``clip_norm``): the bucket kernels accumulate sum(g^2) of the slices they reduce,
+  one scalar all-gather kernel + one tiny kernel turn the partials into the device-resident clip factor the
+  optimizer kernel multiplies into the gradients -- no extra pass over the gradients;
+* the ranks of a stage meet either through a ``torch.distributed`` group or -- in-place elastic mode on GPUs --
+  through a ``Fabric`` (store + rank + world, parallel/symm.py): no process group, no NCCL communicator at all;
 * CPU / gloo groups (the fit_a_line plumbing config) fall back to ``dist.all_reduce``.
 """
 from __future__ import annotations
@@ -59,6 +68,7 @@ class Bucket:
     pending: int = 0
     launched: bool = False
     algo: str = "twoshot"
+    fused_opt: bool = False    # the bucket kernel also runs the optimizer (and, on > 1 rank, all-gathers parameters)
 
 
 def plan_buckets(flat: FlatParams, cap_bytes: int) -> List[Bucket]:
@@ -109,7 +119,8 @@ class ElasticDataParallel:
     def __init__(self, module: torch.nn.Module, group: Optional[dist.ProcessGroup] = None,
                  bucket_cap_mb: float = 16.0, overlap: bool = True, comm_blocks: int = 32,
                  algo: str = "auto", timeout_s: float = 60.0, average: bool = True,
-                 check_finite: bool = False, track_sqnorm: bool = False, hierarchical: str = "auto"):
+                 check_finite: bool = False, track_sqnorm: bool = False, hierarchical: str = "auto",
+                 fabric=None, clip_norm: Optional[float] = None):
         # one engine per module: a second engine on the same parameters would leave the first one's
         # autograd hooks installed (they would fire, and launch reductions, during the new engine's backward)
         old = getattr(module, "_edl_dp_engine", None)
@@ -128,31 +139,49 @@ class ElasticDataParallel:
         self.slices = {}
         self.found_inf = None
         self.sqnorm = None
+        self.clip_norm = float(clip_norm) if clip_norm else None
+        self.param_slices = {}
+        self.opt = None                 # attach_optimizer()
+        self.bucket_opt = False         # optimizer runs per bucket inside / right after the reduction
+        self.state_sharded = False      # fused mode on > 1 rank: every rank only updates its slices of master / momentum
+        self.state_complete = True      # False between a fused step and the next consolidate / localize
+        self.last_algos = []            # what the last step actually launched: (algo, bytes, fused)
         if check_finite:
             self.found_inf = torch.zeros(1, dtype=torch.int32, device=self.device)
-        if track_sqnorm and self.device.type == "cuda":
+        if (track_sqnorm or self.clip_norm) and self.device.type == "cuda":
             self.sqnorm = torch.zeros(1, dtype=torch.float32, device=self.device)
+            self.clip_scale_t = torch.ones(1, dtype=torch.float32, device=self.device)
+            self.grad_norm_t = torch.zeros(1, dtype=torch.float32, device=self.device)
         # "auto": two-level reduction as soon as the ranks span more than one host (NVSwitch domain); "off": never
         # (one flat group; across hosts that means the library path); the reference's use_hierarchical_allreduce knob
         self.hierarchical = os.environ.get("EDL_HIERARCHICAL_ALLREDUCE", hierarchical)
         self.overlap_wgrad = os.environ.get("EDL_OVERLAP_WGRAD", "1") == "1"
         self.enabled = True     # False: gradients stay local (DGC exchanges them itself)
-        self._bind_group(group)
+        self._bind_group(group, fabric)
         self.flat = FlatParams(module, grad_alloc=self._grad_alloc if self.pool is not None else None)
         self._plan()
         self._install_hooks()
         self.comm_launches = 0
 
     # ------------------------------------------------------------------ group / memory
-    def _bind_group(self, group):
+    def _bind_group(self, group, fabric=None):
         self.group = group
-        if dist.is_available() and dist.is_initialized():
-            self.world = dist.get_world_size(group)
-            self.rank = dist.get_rank(group)
+        self.fabric = fabric
+        if fabric is not None:
+            # no process group: the stage's members meet in a key-value store, everything that moves between GPUs
+            # moves through our own kernels over the symmetric slab (in-place elastic mode on one NVSwitch domain)
+            self.world, self.rank = fabric.world, fabric.rank
+            self.backend = "fabric" if self.world > 1 else "none"
+            self.hier, self.local_group, self.cross_group = False, None, None
+            self.local_world, self.local_rank = self.world, self.rank
         else:
-            self.world, self.rank = 1, 0
-        self.backend = dist.get_backend(group) if self.world > 1 else "none"
-        self._plan_hierarchy(group)
+            if dist.is_available() and dist.is_initialized():
+                self.world = dist.get_world_size(group)
+                self.rank = dist.get_rank(group)
+            else:
+                self.world, self.rank = 1, 0
+            self.backend = dist.get_backend(group) if self.world > 1 else "none"
+            self._plan_hierarchy(group)
         symm_world = self.local_world if self.hier else self.world
         self.use_symm = (symm_world > 1 and self.device.type == "cuda"
                          and self.algo_pref != "nccl")
@@ -163,9 +192,11 @@ class ElasticDataParallel:
             need = 0
             for p in self.module.parameters():
                 if p.requires_grad:
-                    need += (p.numel() + 256) * p.element_size()
+                    # gradients + (fused optimizer) the bf16 parameter shadow every rank stores into
+                    need += (p.numel() + 256) * p.element_size() * (2 if p.element_size() == 2 else 1)
             need += 4 << 20
-            self.pool = SymmetricPool(need, group=self.local_group if self.hier else group, device=self.device)
+            self.pool = SymmetricPool(need, group=self.local_group if self.hier else group, device=self.device,
+                                      fabric=fabric)
         if self.device.type == "cuda" and getattr(self, "comm_stream", None) is None:
             # all-reduce kernels: high priority (few CTAs, on the critical path of the optimizer step);
             # weight-gradient kernels: LOW priority -- they only have to finish before their bucket is
@@ -232,7 +263,58 @@ class ElasticDataParallel:
         for bi, b in enumerate(self.buckets):
             for eid in b.entry_ids:
                 self.bucket_of[eid] = bi
+        self._plan_bucket_optimizer()
         self._reset_pending()
+
+    # ------------------------------------------------------------------ optimizer inside the bucket hook
+    def attach_optimizer(self, opt, fused: Optional[bool] = None):
+        """Let the engine run ``opt`` (a ``FlatSGDMomentum`` on this engine's flat buffers) bucket by bucket: inside
+        the reduction kernel on > 1 rank, right behind the bucket's last gradient on one.  ``fused=None`` follows
+        ``EDL_FUSED_OPT`` (default on).  Not used with loss scaling, clipping (both need every gradient before any
+        update), the hierarchical or library reduction paths, or weight-decay masks on a single rank."""
+        self.opt = opt
+        if fused is None:
+            fused = os.environ.get("EDL_FUSED_OPT", "1") == "1"
+        self._want_bucket_opt = bool(fused)
+        opt.skip_dtype = self._opt_skips
+        self._plan_bucket_optimizer()
+
+    def _opt_skips(self, dtype) -> bool:
+        """Asked by ``opt.step()``: was this dtype group already updated by the bucket kernels of this step?"""
+        return self.bucket_opt and self.enabled and dtype in self._fused_dtypes
+
+    def _plan_bucket_optimizer(self):
+        self._fused_dtypes = set()
+        was_sharded = self.state_sharded
+        self.bucket_opt = False
+        opt = self.opt
+        ok = (opt is not None and getattr(self, "_want_bucket_opt", False) and self.device.type == "cuda"
+              and type(opt).__name__ == "FlatSGDMomentum" and opt.found_inf_is_comm_error()
+              and opt.grad_scale_t is None and self.clip_norm is None and self.found_inf is None
+              and not self.hier and (self.world == 1 or self.use_symm))
+        if ok:
+            for dt, g in self.flat.groups.items():
+                # > 1 rank: bf16 groups with fp32 masters (the kernel stores bf16 parameters into every rank's
+                # shadow); 1 rank: any group (plain per-bucket optimizer launches)
+                if self.world > 1 and not (dt == torch.bfloat16 and g.master is not None):
+                    continue
+                if self.world > 1 and any(b.algo not in ("twoshot", "multimem") for b in self.buckets if b.dtype == dt):
+                    continue
+                self._fused_dtypes.add(dt)
+            self.bucket_opt = bool(self._fused_dtypes)
+        for b in self.buckets:
+            b.fused_opt = self.bucket_opt and b.dtype in self._fused_dtypes
+        if self.bucket_opt and self.world > 1:
+            if not self.param_slices:
+                self.flat.rebind_params(self._param_alloc, dtypes=self._fused_dtypes)
+            self.state_sharded = True
+        elif was_sharded:
+            self.state_sharded = False
+
+    def _param_alloc(self, numel, dtype, device):
+        sl = self.pool.alloc(numel, dtype)
+        self.param_slices[dtype] = sl
+        return sl.tensor
 
     def _reset_pending(self):
         for b in self.buckets:
@@ -275,12 +357,44 @@ class ElasticDataParallel:
             self._launch(self.buckets[self._next])
             self._next += 1
 
+    def _join_producers(self):
+        """The bucket's gradients were written on the main stream (BN, pools, ...) and on the weight-gradient
+        stream: whatever consumes them on the communication stream waits for both."""
+        for st in {torch.cuda.current_stream(self.device), self._main_stream,
+                   self.wgrad_stream if self.overlap_wgrad else None}:
+            if st is not None and st != self.comm_stream:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                self.comm_stream.wait_event(ev)
+        self._comm_used = True
+
+    def _bucket_optimizer_local(self, b: Bucket, g):
+        """One rank: the optimizer of this bucket right behind its last gradient, on the side stream, while the
+        rest of backward still runs (the separate whole-model optimizer pass at the end of the step disappears)."""
+        from ..ops import native, count_launch
+
+        opt, st = self.opt, self.opt.state[b.dtype]
+        lo, hi = b.start, b.start + b.numel
+        master = g.master if g.master is not None else g.param
+        lp = g.param[lo:hi] if g.master is not None else None
+        self._join_producers()
+        with torch.cuda.stream(self.comm_stream):
+            native().sgd_momentum(lp, master[lo:hi], st["mom"][lo:hi], g.grad[lo:hi],
+                                  st["wd_mask"][lo:hi] if st["wd_mask"] is not None else None, opt.lr_t, None,
+                                  opt.found_inf_t, opt.momentum, opt.weight_decay, opt.nesterov)
+        count_launch()
+        self.last_algos.append(("local_sgd", b.numel * g.grad.element_size(), True))
+
     def _launch(self, b: Bucket):
-        if b.launched or self.world <= 1 or not self.enabled:
+        if b.launched or not self.enabled:
             b.launched = True
             return
         b.launched = True
         g = self.flat.groups[b.dtype]
+        if self.world <= 1:
+            if b.fused_opt:
+                self._bucket_optimizer_local(b, g)
+            return
         scale = 1.0 / self.world if self.average else 1.0
         if self.hier:
             return self._launch_hier(b, g, scale)
@@ -290,23 +404,28 @@ class ElasticDataParallel:
             sl = self.slices[b.dtype]
             esz = g.grad.element_size()
             off = b.start * esz
-            # the bucket's gradients were written on the main stream (BN, pools, ...) and on the
-            # weight-gradient stream: the reduction waits for both
-            for st in {torch.cuda.current_stream(self.device), self._main_stream,
-                       self.wgrad_stream if self.overlap_wgrad else None}:
-                if st is not None and st != self.comm_stream:
-                    ev = torch.cuda.Event()
-                    ev.record(st)
-                    self.comm_stream.wait_event(ev)
-            self._comm_used = True
+            self._join_producers()
             with torch.cuda.stream(self.comm_stream):
-                native().allreduce_twoshot(
-                    [p + off for p in sl.data_ptrs], sl.sig_ptrs, (sl.mc_ptr + off) if sl.mc_ptr else 0,
-                    self.rank, g.grad, b.numel, scale, self.found_inf, self.sqnorm,
-                    b.algo == "multimem", self.comm_blocks, self.timeout_s)
+                if b.fused_opt:
+                    opt, st, ps = self.opt, self.opt.state[b.dtype], self.param_slices[b.dtype]
+                    lo, hi = b.start, b.start + b.numel
+                    self.state_complete = False
+                    native().allreduce_sgd(
+                        [p + off for p in sl.data_ptrs], sl.sig_ptrs, (sl.mc_ptr + off) if sl.mc_ptr else 0,
+                        [p + off for p in ps.data_ptrs], (ps.mc_ptr + off) if ps.mc_ptr else 0, self.rank,
+                        g.master[lo:hi], st["mom"][lo:hi], st["wd_mask"][lo:hi] if st["wd_mask"] is not None else None,
+                        opt.lr_t, scale, None, self.sqnorm, opt.found_inf_t, opt.momentum, opt.weight_decay,
+                        opt.nesterov, b.algo == "multimem", self.comm_blocks, self.timeout_s)
+                else:
+                    native().allreduce_twoshot(
+                        [p + off for p in sl.data_ptrs], sl.sig_ptrs, (sl.mc_ptr + off) if sl.mc_ptr else 0,
+                        self.rank, g.grad, b.numel, scale, self.found_inf, self.sqnorm,
+                        b.algo == "multimem", self.comm_blocks, self.timeout_s)
             count_launch()
             self.comm_launches += 1
+            self.last_algos.append((b.algo + ("+sgd" if b.fused_opt else ""), b.numel * esz, b.fused_opt))
         else:  # nccl / gloo baseline path
+            self.last_algos.append((self.backend, b.numel * g.grad.element_size(), False))
             view = g.grad[b.start:b.start + b.numel]
             if self.device.type == "cuda":
                 w = dist.all_reduce(view, group=self.group, async_op=True)
@@ -376,8 +495,10 @@ class ElasticDataParallel:
         for b in self.buckets:
             b.pending = 0
         self._launch_ready()
-        if self.device.type == "cuda" and (self.world > 1 or self.overlap_wgrad):
-            if self.use_symm or self.overlap_wgrad or self.hier:
+        if self.clip_norm is not None and self.enabled and self.device.type == "cuda":
+            self._launch_clip()
+        if self.device.type == "cuda" and (self.world > 1 or self.overlap_wgrad or self._comm_used):
+            if self.use_symm or self.overlap_wgrad or self.hier or self._comm_used:
                 cur = torch.cuda.current_stream(self.device)
                 # only streams that took part in this step (a stream without forked work is not part
                 # of a CUDA-graph capture and must not be joined into it)
@@ -391,6 +512,8 @@ class ElasticDataParallel:
                 w.wait()
                 if self.average:
                     view.mul_(scale)
+        if self.clip_norm is not None and self.enabled and self.device.type != "cuda":
+            self._clip_cpu()
         if self.found_inf is not None and not (self.use_symm and self.world > 1):
             # the fused all-reduce epilogue raises the flag itself; without it (one rank, NCCL / gloo
             # path) the gradients are scanned here.  Summed gradients carry every rank's inf/nan, so
@@ -399,6 +522,125 @@ class ElasticDataParallel:
                 bad = (~torch.isfinite(g.grad).all()).to(torch.int32).view(1)
                 self.found_inf.copy_(torch.maximum(self.found_inf, bad))
         self._reset_pending()
+
+    # ------------------------------------------------------------------ global-norm clipping
+    def _launch_clip(self):
+        """After the last bucket: turn the squared-norm partials into the clip factor the optimizer kernel multiplies
+        into the gradients.  Symmetric path: every rank's bucket kernels summed g^2 over the slices THAT RANK
+        reduced, so the global norm is the sum over ranks (one scalar all-gather kernel); otherwise every rank holds
+        the complete reduced gradient and one streaming reduction gives the norm."""
+        from ..ops import native, count_launch
+
+        C = native()
+        symm = self.use_symm and self.world > 1 and not self.hier and any(
+            b.algo in ("twoshot", "multimem") for b in self.buckets)
+        if symm:
+            self._comm_used = True
+            with torch.cuda.stream(self.comm_stream):
+                # groups that did not go through our kernels (none today) would be added here
+                sl = max(self.slices.values(), key=lambda x: x.tensor.numel())
+                if getattr(self, "_norm_parts", None) is None or self._norm_parts.numel() != self.world:
+                    self._norm_parts = torch.zeros(self.world, device=self.device, dtype=torch.float32)
+                C.comm_allgather_scalars(sl.data_ptrs, sl.sig_ptrs, self.rank, self.sqnorm, self._norm_parts,
+                                         self.timeout_s)
+                C.clip_scale(self._norm_parts, self.world, 1, self.clip_norm, self.clip_scale_t, self.grad_norm_t)
+            count_launch(2)
+        else:
+            # one rank, or the library / hierarchical paths: join the producers / async works first
+            for w, view, scale in self._works:
+                w.wait()
+                if self.average:
+                    view.mul_(scale)
+            self._works = []
+            if self.overlap_wgrad or self._comm_used:
+                cur = torch.cuda.current_stream(self.device)
+                if self._comm_used:
+                    cur.wait_stream(self.comm_stream)
+                if self.overlap_wgrad:
+                    cur.wait_stream(self.wgrad_stream)
+            self.sqnorm.zero_()
+            for g in self.flat.groups.values():
+                C.grad_sqnorm(g.grad, self.sqnorm)
+            C.clip_scale(self.sqnorm, 1, 1, self.clip_norm, self.clip_scale_t, self.grad_norm_t)
+            count_launch(1 + len(self.flat.groups))
+        if self.opt is not None:
+            self.opt.set_grad_scale(self.clip_scale_t)
+
+    def _clip_cpu(self):
+        total = sum(float(g.grad.float().pow(2).sum()) for g in self.flat.groups.values()) ** 0.5
+        if total > self.clip_norm:
+            for g in self.flat.groups.values():
+                g.grad.mul_(self.clip_norm / (total + 1e-6))
+        self.last_grad_norm = total
+
+    # ------------------------------------------------------------------ sharded optimizer state
+    def owned_ranges(self, dtype, rank: Optional[int] = None, world: Optional[int] = None):
+        """Element ranges of the dtype group's flat buffers whose master weights / momentum THIS rank keeps
+        current in fused mode (slice ``rank`` of every bucket, csrc/allreduce.cu slice rule)."""
+        rank = self.rank if rank is None else rank
+        world = self.world if world is None else world
+        out = []
+        for b in self.buckets:
+            if b.dtype != dtype or not b.fused_opt:
+                continue
+            nvec = b.numel // 8
+            cap = -(-nvec // world)
+            lo = min(nvec, cap * rank)
+            hi = min(nvec, lo + cap)
+            if hi > lo:
+                out.append((b.start + lo * 8, b.start + hi * 8))
+        return out
+
+    @torch.no_grad()
+    def consolidate_optimizer_state(self):
+        """Collective over the current stage: bring master weights and momentum of the fused groups up to date on
+        EVERY rank (each rank only maintained its slices).  Called before a checkpoint is written and before a
+        planned stage change.  Exact: every element is owned by exactly one rank, the others contribute zeros to an
+        fp32 sum that rides on the two-shot kernel through the (idle) gradient slab."""
+        if not (self.state_sharded and self.world > 1):
+            return
+        from ..ops import native, count_launch
+
+        torch.cuda.synchronize(self.device)
+        for dt in self._fused_dtypes:
+            g = self.flat.groups[dt]
+            sl = self.slices[dt]
+            stage = sl.tensor.view(torch.uint8)
+            cap = stage.numel() // 4 // 1024 * 1024                       # fp32 elements per round
+            fstage = stage[:cap * 4].view(torch.float32)
+            own = self.owned_ranges(dt)
+            for t in (g.master, self.opt.state[dt]["mom"]):
+                for off in range(0, t.numel(), cap):
+                    n = min(cap, t.numel() - off)
+                    n8 = -(-n // 4) * 4
+                    fstage[:n8].zero_()
+                    for lo, hi in own:
+                        a, b_ = max(lo, off), min(hi, off + n)
+                        if b_ > a:
+                            fstage[a - off:b_ - off].copy_(t[a:b_])
+                    native().allreduce_twoshot(sl.data_ptrs, sl.sig_ptrs, 0, self.rank, fstage, n8, 1.0, None, None,
+                                               False, self.comm_blocks, self.timeout_s)
+                    count_launch()
+                    t[off:off + n].copy_(fstage[:n])
+            sl.tensor.zero_()
+        torch.cuda.synchronize(self.device)
+        self.state_complete = True
+
+    @torch.no_grad()
+    def localize_optimizer_state(self):
+        """After a FAILED collective (a peer died, its slices are gone): make this rank's optimizer state complete
+        without any communication -- master weights outside the owned slices are re-derived from the bf16
+        parameters (those are replicated and current as of the last good step), momentum there keeps its last
+        consolidated value.  The elastic recovery then takes the root's state for everybody."""
+        if not self.state_sharded:
+            return
+        for dt in self._fused_dtypes:
+            g = self.flat.groups[dt]
+            keep = torch.zeros(g.numel, dtype=torch.bool, device=self.device)
+            for lo, hi in self.owned_ranges(dt):
+                keep[lo:hi] = True
+            g.master.copy_(torch.where(keep, g.master, g.param.float()))
+        self.state_complete = True
 
     # ------------------------------------------------------------------ user-facing
     def __call__(self, *a, **kw):
@@ -421,6 +663,7 @@ class ElasticDataParallel:
                 self.found_inf.zero_()
             if self.sqnorm is not None:
                 self.sqnorm.zero_()
+            self.last_algos = []
             return
         self.flat.zero_grad()
         if self.found_inf is not None:
@@ -452,21 +695,62 @@ class ElasticDataParallel:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return float(t.item()), 0
 
-    def rebuild(self, group: Optional[dist.ProcessGroup]):
-        """Elastic stage change: new group => new symmetric slab, new bucket plan.  Parameters,
-        master weights and optimizer state stay where they are (no process restart)."""
+    def allreduce_scalars(self, t: torch.Tensor) -> torch.Tensor:
+        """Sum of a tiny fp32 tensor (<= 8 values: evaluation counters, flags) over the ranks; our scalar all-gather
+        kernel when the ranks share symmetric memory, else the library."""
+        if self.world <= 1:
+            return t
+        if self.use_symm and self.slices and not self.hier and t.numel() <= 8 and t.is_cuda:
+            from ..ops import native, count_launch
+
+            sl = max(self.slices.values(), key=lambda x: x.tensor.numel())
+            inp = t.detach().to(torch.float32).contiguous().view(-1)
+            out = torch.zeros(self.world * inp.numel(), device=self.device, dtype=torch.float32)
+            native().comm_allgather_scalars(sl.data_ptrs, sl.sig_ptrs, self.rank, inp, out, min(self.timeout_s, 30.0))
+            count_launch()
+            return out.view(self.world, -1).sum(0).view_as(t).to(t.dtype)
+        t = t.clone()
+        dist.all_reduce(t, group=self.group)
+        return t
+
+    def rebuild(self, group: Optional[dist.ProcessGroup] = None, fabric=None):
+        """Elastic stage change: new group (or fabric) => new symmetric slab, new bucket plan.  Parameters,
+        master weights and optimizer state stay where they are (no process restart).  With a sharded optimizer
+        state call ``consolidate_optimizer_state()`` (planned change, old stage still intact) or
+        ``localize_optimizer_state()`` (a peer died) BEFORE this."""
+        if self.state_sharded and not self.state_complete:
+            raise RuntimeError("the optimizer state is sharded across the ranks of the old stage: call "
+                               "consolidate_optimizer_state() (planned change, collective over the OLD stage) or "
+                               "localize_optimizer_state() (a peer died) before rebuild()")
         for h in self._hook_handles:
             h.remove()
         old_pool = self.pool
+        had_param_shadow = bool(self.param_slices)
         self.slices = {}
-        self._bind_group(group)
+        self.param_slices = {}
+        self.state_sharded = False
+        self._norm_parts = None
+        self._bind_group(group, fabric)
         if self.pool is not None:
             self.flat.rebind_grads(self._grad_alloc)
         else:
             self.flat.rebind_grads(lambda n, dt, dev: torch.zeros(n, dtype=dt, device=dev))
+        self._plan()            # re-homes the bf16 parameters into the new slab when the fused optimizer is on
+        if had_param_shadow and not self.param_slices:
+            # the fused path is off in the new stage (one rank left, library path): parameters leave the old slab
+            self.flat.rebind_params(lambda n, dt, dev: torch.empty(n, dtype=dt, device=dev),
+                                    dtypes=[dt for dt, g in self.flat.groups.items() if g.master is not None])
         del old_pool
-        self._plan()
         self._install_hooks()
+
+    def barrier(self):
+        """Host-side barrier of the stage's ranks (store barrier of the pool, else the library's)."""
+        if self.world <= 1:
+            return
+        if self.pool is not None and not self.hier:
+            self.pool.barrier()
+        else:
+            dist.barrier(self.group)
 
     @torch.no_grad()
     def broadcast_parameters(self, root: int = 0):

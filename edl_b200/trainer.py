@@ -26,8 +26,9 @@ from .parallel import ElasticDataParallel
 
 
 class LossHandle:
-    """Result of ``StudentTrainer.step_pipelined``: the loss of one step, readable once its asynchronous
-    device -> pinned-host copy has landed.  At most ``StudentTrainer._LOSS_SLOTS`` handles are live at a time."""
+    """Result of ``StudentTrainer.step``: the loss of one step, readable once its asynchronous device ->
+    pinned-host copy has landed.  At most ``StudentTrainer._LOSS_SLOTS`` unread handles are live at a time
+    (a handle that was never read is overwritten ``_LOSS_SLOTS`` steps later)."""
 
     __slots__ = ("_ev", "_host", "_value")
 
@@ -39,6 +40,15 @@ class LossHandle:
             self._ev.synchronize()
             self._value = float(self._host[0])
         return self._value
+
+    def __float__(self) -> float:
+        return self.item()
+
+    def __format__(self, spec) -> str:
+        return format(self.item(), spec)
+
+    def __repr__(self) -> str:
+        return "LossHandle(%s)" % ("pending" if self._value is None else "%.6f" % self._value)
 
 
 class StepArena:
@@ -71,7 +81,9 @@ class StudentTrainer:
                  bucket_cap_mb: float = 16.0, comm_blocks: int = 32, algo: str = "auto",
                  overlap: bool = True, dtype=torch.bfloat16, input_dtype=None,
                  loss_fn: Optional[Callable] = None, loss_scaling: Optional[float] = None,
-                 dynamic_loss_scaling: bool = True, optimizer: Optional[Callable] = None):
+                 dynamic_loss_scaling: bool = True, optimizer: Optional[Callable] = None,
+                 fabric=None, clip_norm: Optional[float] = None, fused_optimizer: Optional[bool] = None,
+                 comm_timeout_s: Optional[float] = None):
         self.model = model
         self.device = next(model.parameters()).device
         self.cuda = self.device.type == "cuda"
@@ -79,9 +91,15 @@ class StudentTrainer:
         self.dtype = dtype
         self.target_kind = target_kind
         self.loss_fn = loss_fn
-        self.dp = ElasticDataParallel(model, group=group, bucket_cap_mb=bucket_cap_mb,
+        if comm_timeout_s is None:
+            # in-place elastic mode: a dead peer must surface within seconds (the kernels' barrier timeout raises the
+            # fabric's error word, every later barrier then gives up at once); otherwise be patient
+            import os
+            comm_timeout_s = float(os.environ.get("EDL_COMM_TIMEOUT", "10" if os.environ.get(
+                "EDL_RESCALE_MODE", "").lower() == "inplace" else "60"))
+        self.dp = ElasticDataParallel(model, group=group, bucket_cap_mb=bucket_cap_mb, timeout_s=comm_timeout_s,
                                       comm_blocks=comm_blocks, algo=algo, overlap=overlap,
-                                      check_finite=loss_scaling is not None)
+                                      check_finite=loss_scaling is not None, fabric=fabric, clip_norm=clip_norm)
         if optimizer is not None:
             self.opt = optimizer(self.dp.flat)
         else:
@@ -99,6 +117,12 @@ class StudentTrainer:
             self.scaler.found_inf = self.dp.found_inf
             self.scaler.attach(self.opt, self.dp)
         self._guard_comm_error()
+        # the optimizer rides in the bucket hook of the data-parallel engine when nothing needs to see every
+        # gradient first (loss scaling, clipping): fused reduce-scatter -> SGD -> all-gather kernel on > 1 GPU,
+        # per-bucket optimizer launches on the side stream on one (parallel/ddp.py:attach_optimizer)
+        self._fused_optimizer = fused_optimizer
+        if isinstance(self.opt, ops.FlatSGDMomentum):
+            self.dp.attach_optimizer(self.opt, fused=fused_optimizer)
         # recompute runs every block's forward twice: the pre-zeroed accumulate-into arena slices would
         # be summed twice, so those runs let each op allocate its own scratch
         self.arena = StepArena(model, self.device) if self.cuda and not getattr(model, "recompute", False) else None
@@ -159,8 +183,7 @@ class StudentTrainer:
                 self._step_body()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
-        if self.dp.world > 1:
-            dist.barrier(self.dp.group)
+        self.dp.barrier()
         self.graph = torch.cuda.CUDAGraph()
         before = ops.launches()
         with torch.cuda.graph(self.graph, stream=s):
@@ -186,10 +209,16 @@ class StudentTrainer:
         self.steps_done += 1
         return self.static_loss
 
-    def step(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
-        """Public per-step call.  ``images`` / ``targets`` may live on the host (ideally pinned):
-        they are copied into the static device buffers, the step runs, and the device-resident
-        scalar loss is returned (``.item()`` it to read it back)."""
+    def step(self, images: torch.Tensor, targets: torch.Tensor, sync: bool = False):
+        """Public per-step call.  ``images`` / ``targets`` may live on the host (ideally pinned).
+
+        Default (``sync=False``): the double-buffered feed of ``step_pipelined`` -- the host -> device copy of this
+        batch is staged on a copy stream while the previous step still runs, and the returned ``LossHandle`` is
+        readable (``.item()`` / ``float()``) once its asynchronous device -> host copy has landed; read it one step
+        late and the host never stalls the GPU.  ``sync=True``: copy on the caller's stream, run, and return the
+        device-resident scalar loss tensor (the round-1 behaviour)."""
+        if not sync:
+            return self.step_pipelined(images, targets)
         self.static_x.copy_(images, non_blocking=True)
         self.static_t.copy_(targets, non_blocking=True)
         return self.step_device()
@@ -221,7 +250,7 @@ class StudentTrainer:
         memory asynchronously; the returned handle's ``item()`` waits for that copy only -- read it one step
         late (``h = step_pipelined(b[i+1]); prev.item()``) and the host never stalls the GPU."""
         if not self.cuda:
-            return LossHandle(None, None, float(self.step(images, targets)))
+            return LossHandle(None, None, float(self.step(images, targets, sync=True)))
         if getattr(self, "_copy_stream", None) is None:
             self._pipe_init()
         k = self._pipe_i % 2
@@ -266,7 +295,7 @@ class StudentTrainer:
             counts[:2] += hits.to(counts.device)
             counts[2] += labels.numel()
         if self.dp.world > 1:
-            dist.all_reduce(counts, group=self.dp.group)
+            counts = self.dp.allreduce_scalars(counts)
         self.model.train(was_training)
         n = max(1.0, float(counts[2]))
         return {"acc1": float(counts[0]) / n, "acc5": float(counts[1]) / n, "n": int(counts[2])}
@@ -284,29 +313,64 @@ class StudentTrainer:
                 or self.dp.pool is None or not hasattr(self.opt, "set_found_inf")):
             return
         w = ops.native().comm_error_word_offset()
-        self.opt.set_found_inf(self.dp.pool.sig_tensor()[w:w + 1])
+        self.opt.set_found_inf(self.dp.pool.sig_tensor()[w:w + 1], comm_error=True)
 
-    def rebuild(self, group):
-        """World-size change: re-plan the communication, drop the captured graph."""
+    def prepare_rescale(self):
+        """Collective over the OLD stage, before a planned membership change (``ElasticContext.poll()`` said switch):
+        with the fused optimizer every rank only kept its slices of master weights / momentum current."""
+        self.dp.consolidate_optimizer_state()
+
+    def consolidate(self):
+        """Collective: make this rank's optimizer state complete (call on every rank before rank 0 checkpoints)."""
+        self.dp.consolidate_optimizer_state()
+
+    def rebuild(self, group=None, fabric=None, failed: bool = False):
+        """World-size change: re-plan the communication, drop the captured graph.  ``failed=True``: the old stage
+        broke (a peer died); the sharded optimizer state is completed locally instead of collectively."""
         self.graph = None
-        self.dp.rebuild(group)
+        if failed:
+            self.dp.localize_optimizer_state()
+        self.dp.rebuild(group, fabric=fabric)
         if self.scaler is None and hasattr(self.opt, "set_found_inf"):
             self.opt.set_found_inf(None)          # the old pool (and its error word) is gone
         self._guard_comm_error()
+        if getattr(self, "_copy_stream", None) is not None:
+            torch.cuda.synchronize(self.device)
 
     @torch.no_grad()
     def sync_from(self, root: int = 0):
-        """After a join: take parameters, fp32 masters and optimizer state from ``root`` over the fabric
-        (NVSwitch broadcast kernel) instead of re-reading the checkpoint from the file system."""
+        """After a join: take parameters, fp32 masters, optimizer state (tensors AND step counters / learning rate)
+        and the module buffers (BatchNorm running statistics) from ``root`` over the fabric (NVSwitch broadcast
+        kernel) instead of re-reading the checkpoint from the file system."""
         self.dp.broadcast_parameters(root)
         for st in getattr(self.opt, "state", {}).values():
             for v in st.values():
                 if torch.is_tensor(v):
                     self.dp.broadcast_tensor(v, root)
+        for name in ("step_t", "lr_t"):
+            v = getattr(self.opt, name, None)
+            if torch.is_tensor(v):
+                self.dp.broadcast_tensor(v, root)
+        if hasattr(self.opt, "lr_t"):
+            self.opt.lr = float(self.opt.lr_t.item())
+        bufs = [b for b in self.model.buffers() if torch.is_tensor(b) and b.numel() > 0]
+        by_dtype = {}
+        for b in bufs:
+            by_dtype.setdefault(b.dtype, []).append(b)
+        for dt, group in by_dtype.items():              # one broadcast per dtype, not one per BatchNorm layer
+            flat = torch.cat([b.reshape(-1) for b in group])
+            self.dp.broadcast_tensor(flat, root)
+            off = 0
+            for b in group:
+                b.copy_(flat[off:off + b.numel()].view_as(b))
+                off += b.numel()
         if self.cuda:
             torch.cuda.synchronize(self.device)
 
     def state_dict(self):
+        if self.dp.state_sharded and not self.dp.state_complete:
+            raise RuntimeError("the optimizer state is sharded across ranks (fused optimizer): call "
+                               "trainer.consolidate() on EVERY rank before state_dict()")
         return {"model": {k: v for k, v in self.model.state_dict().items()},
                 "optim": self.opt.state_dict(), "steps_done": self.steps_done}
 

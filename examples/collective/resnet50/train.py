@@ -115,6 +115,7 @@ def main():
     base_lr = scaled_lr(args.lr, bs, world)
     tr = StudentTrainer(model, bs, image_shape=(3, args.image_size, args.image_size), num_classes=args.class_dim,
                         lr=base_lr, target_kind="labels", use_graph=cuda, dtype=dtype,
+                        fabric=ctx.fabric if ctx is not None else None,   # GPUs in place: no process group at all
                         loss_fn=lambda z, t: ops.soft_cross_entropy(z, t, "labels", label_smoothing=args.label_smoothing))
     fs = LocalFS()
 
@@ -123,6 +124,8 @@ def main():
         if world <= 1:
             return cursor
         tr.sync_from(root)
+        if ctx is not None:
+            return tuple(ctx.broadcast_object(cursor, root))
         box = [cursor]
         dist.broadcast_object_list(box, src=root)
         return box[0]
@@ -149,7 +152,7 @@ def main():
         n_steps = steps_per_epoch if not args.max_steps else min(steps_per_epoch, args.max_steps)
         it = it0
         it0 = 0
-        switch = False
+        switch, failed = False, ""
         feed = file_feed(args, bs, rank, world, epoch, it, dev, dtype, cuda)
         while it < n_steps:
             lr = (cosine_decay_with_warmup(step, base_lr, steps_per_epoch, args.epochs) if args.lr_strategy.startswith("cosine")
@@ -179,20 +182,36 @@ def main():
             if (it - 1) % 10 == 0 and rank == 0:
                 print("Pass %d trainbatch %d loss %.4f lr %.5f speed %.1f img/s" % (
                     epoch, it - 1, float(loss), lr, seen * world / max(1e-6, time.time() - t0)), flush=True)
-            if ctx is not None and ctx.poll(agree=tr.dp.agree):
-                switch = True
-                break
-        if ctx is not None and not switch:
-            switch = ctx.poll(force=True, agree=tr.dp.agree)
-        if switch:
             try:
-                info = ctx.rescale()
+                if ctx is not None and ctx.poll(agree=tr.dp.agree):
+                    switch = True
+                    break
+            except RuntimeError as e:                            # a collective timed out: a peer is gone
+                failed = str(e)
+                break
+        if ctx is not None and not switch and not failed:
+            try:
+                switch = ctx.poll(force=True, agree=tr.dp.agree)
+            except RuntimeError as e:
+                failed = str(e)
+        if switch or failed:
+            try:
+                if failed:
+                    # hot recovery: the steps since the failure were device-side no-ops (the fused optimizer skips
+                    # its update while the fabric's error word is set), the parameters are those of the last good step
+                    print("rank %d: %s -- recovering in place" % (rank, failed), flush=True)
+                    info = ctx.recover()
+                else:
+                    tr.prepare_rescale()                        # sharded optimizer state made complete (old stage)
+                    info = ctx.rescale()
             except elastic.EdlEvicted:
                 print("rank %d: pod left the job (scale-in); exiting" % rank, flush=True)
                 ctx.close()
                 return
             old_world, world, rank = world, info.size, info.rank
-            tr.rebuild(None)                                    # new symmetric slab + bucket plan; graph re-captured lazily
+            # new symmetric slab + bucket plan; graph re-captured lazily
+            tr.rebuild(None, fabric=ctx.fabric, failed=bool(failed))
+            failed = ""
             epoch, it0, step = take_cursor_from(info.root, (epoch, it, step))
             base_lr = scaled_lr(args.lr, bs, world)             # lr = base * batch * world / 256
             steps_per_epoch = args.steps_per_epoch or max(1, args.total_images // (bs * world))
@@ -204,10 +223,13 @@ def main():
             it0 = 0
         if etcd is not None and epoch >= args.epochs - 2 and env.pod_id:
             edl_train_status.save_to_etcd(etcd, env.pod_id, edl_train_status.TrainStatus.NEARTHEEND)   # no more scale-out
+        tr.consolidate()                 # fused optimizer: every rank's slices of master / momentum -> complete state
         if rank == 0:
             save_check_point(args.ckpt, tr.state_dict(), TrainStatus(epoch, step), fs, trainer_id=0,
                              state_json=json.dumps({"world": world, "lr": lr}))
-        if world > 1:
+        if ctx is not None:
+            ctx.barrier()
+        elif world > 1:
             dist.barrier()
         epoch += 1
     write_benchmark_log(rank, dict(meter.summary(), model=args.model, batch_size=bs))   # reference: benchmark_logs/log_<id>

@@ -88,32 +88,141 @@ def _worker(rank, world, port, q):
         assert torch.equal(out, exp)
         assert pool.check_error() == 0
 
-        # ---- engine end to end: 2 ranks with different data stay bit-identical and match 1-proc math
+        res["pool"] = pool.describe()
+        # ---- fused reduce-scatter -> SGD-momentum -> parameter all-gather kernel against a single-process fp32
+        #      reference of the same update (mean gradient over the ranks, then the plain momentum rule)
+        n = 3_000_000 // 8 * 8
+        gsl, psl = pool.alloc(n, torch.bfloat16), pool.alloc(n, torch.bfloat16)
+        for algo in (["twoshot", "multimem"] if pool.has_multicast else ["twoshot"]):
+            torch.manual_seed(7)
+            master = torch.randn(n, device=dev)
+            mom = torch.randn(n, device=dev) * 0.1
+            torch.manual_seed(50 + rank)
+            grad = (torch.randn(n, device=dev) * 0.5).bfloat16()
+            gathered = [torch.empty_like(grad) for _ in range(world)]
+            dist.all_gather(gathered, grad)
+            gref = sum(g.float() for g in gathered) / world
+            mref = 0.9 * mom + (gref + 1e-4 * master)
+            wref = master - 0.1 * mref
+            gsl.tensor.copy_(grad)
+            psl.tensor.copy_(master.bfloat16())
+            lr = torch.tensor([0.1], device=dev)
+            torch.cuda.synchronize()
+            dist.barrier()
+            C.allreduce_sgd(gsl.data_ptrs, gsl.sig_ptrs, gsl.mc_ptr, psl.data_ptrs, psl.mc_ptr, rank, master, mom, None,
+                            lr, 1.0 / world, None, None, None, 0.9, 1e-4, False, algo == "multimem", 32, 20.0)
+            torch.cuda.synchronize()
+            dist.barrier()
+            # every rank holds the new bf16 parameters of EVERY slice; master / momentum only of its own slice
+            err = ((psl.tensor.float() - wref).abs().max() / wref.abs().max()).item()
+            assert err < 1e-2, ("fused params", algo, err)
+            nvec = n // 8
+            cap = -(-nvec // world)
+            lo, hi = min(nvec, cap * rank) * 8, min(nvec, cap * (rank + 1)) * 8
+            # P2P: fp32 sum of the bf16 gradients goes straight into the update; NVLS: the switch hands back the
+            # fp32-accumulated sum rounded to bf16 (what the unfused path stores, too)
+            tol = 1e-5 if algo == "twoshot" else 4e-3
+            assert torch.allclose(master[lo:hi], wref[lo:hi], rtol=tol, atol=tol), ("fused master", algo)
+            assert torch.allclose(mom[lo:hi], mref[lo:hi], rtol=tol, atol=tol), ("fused momentum", algo)
+            outs = [torch.empty_like(psl.tensor) for _ in range(world)]
+            dist.all_gather(outs, psl.tensor)
+            assert all(torch.equal(outs[0], o) for o in outs), "parameter shadows differ between ranks"
+
+        # ---- engine end to end, against ONE process doing the same global batch in fp32 arithmetic on the reduction
+        import copy
+
         from edl_b200.models import ResNetVd, to_train_dtype
         from edl_b200.trainer import StudentTrainer
 
         torch.manual_seed(0)
-        m = to_train_dtype(ResNetVd(18, class_dim=16, width_mult=0.25), torch.bfloat16, dev).train()
-        for use_graph in (False, True):
-            tr = StudentTrainer(m, 8, image_shape=(3, 32, 32), num_classes=16, lr=0.05, use_graph=use_graph,
-                                bucket_cap_mb=0.25)
-            torch.manual_seed(100 + rank)
-            x = torch.randn(8, 3, 32, 32).bfloat16().contiguous(memory_format=torch.channels_last).pin_memory()
-            t = torch.softmax(torch.randn(8, 16), -1).bfloat16().pin_memory()
+        m0 = to_train_dtype(ResNetVd(18, class_dim=16, width_mult=0.25), torch.bfloat16, dev).train()
+        torch.manual_seed(100 + rank)
+        x = torch.randn(8, 3, 32, 32).bfloat16().contiguous(memory_format=torch.channels_last).pin_memory()
+        t = torch.softmax(torch.randn(8, 16), -1).bfloat16().pin_memory()
+
+        def flat_params(tr):
+            return torch.cat([g.param.flatten().float() for g in tr.dp.flat.groups.values()])
+
+        def flat_grads(tr):
+            return torch.cat([g.grad.flatten().float() for g in tr.dp.flat.groups.values()])
+
+        # reference gradient of step 1: every rank runs its own batch WITHOUT communication, fp32 mean over ranks
+        solo_group = [dist.new_group(ranks=[r]) for r in range(world)][rank]
+        ref_tr = StudentTrainer(copy.deepcopy(m0), 8, image_shape=(3, 32, 32), num_classes=16, lr=0.0, use_graph=False,
+                                group=solo_group, fused_optimizer=False, weight_decay=0.0)
+        ref_tr.step(x, t, sync=True)
+        torch.cuda.synchronize()
+        g_local = flat_grads(ref_tr)
+        g_all = [torch.empty_like(g_local) for _ in range(world)]
+        dist.all_gather(g_all, g_local)
+        g_ref = sum(g_all) / world
+        for fused in (False, True):
+            tr = StudentTrainer(copy.deepcopy(m0), 8, image_shape=(3, 32, 32), num_classes=16, lr=0.0, use_graph=False,
+                                bucket_cap_mb=0.25, fused_optimizer=fused, weight_decay=0.0)
+            assert tr.dp.bucket_opt == fused
+            tr.step(x, t, sync=True)
+            torch.cuda.synchronize()
+            if not fused:       # the reduced gradient itself (the fused kernel never writes it back)
+                err = ((flat_grads(tr) - g_ref).norm() / g_ref.norm()).item()
+                assert err < 2e-2, ("engine gradient vs fp32 single-process mean", err)
+                res["engine_grad_err"] = err
+            res["algos_fused_%s" % fused] = sorted({a for a, _, _ in tr.dp.last_algos})
+        params = {}
+        for use_graph, fused in ((False, True), (True, True), (True, False)):
+            tr = StudentTrainer(copy.deepcopy(m0), 8, image_shape=(3, 32, 32), num_classes=16, lr=0.05,
+                                use_graph=use_graph, bucket_cap_mb=0.25, fused_optimizer=fused)
             for _ in range(4):
                 loss = tr.step(x, t)
+            float(loss)
             torch.cuda.synchronize()
-            flat = torch.cat([g.param.flatten().float() for g in tr.dp.flat.groups.values()])
+            flat = flat_params(tr)
             outs = [torch.empty_like(flat) for _ in range(world)]
             dist.all_gather(outs, flat)
-            assert all(torch.equal(outs[0], o) for o in outs), "ranks diverged (graph=%s)" % use_graph
+            assert all(torch.equal(outs[0], o) for o in outs), "ranks diverged (graph=%s fused=%s)" % (use_graph, fused)
             assert torch.isfinite(flat).all()
             assert tr.dp.comm_launches > 0
-            res["comm_launches_graph_%s" % use_graph] = tr.dp.comm_launches
+            res["comm_launches_graph_%s_fused_%s" % (use_graph, fused)] = tr.dp.comm_launches
+            params[(use_graph, fused)] = flat
+        # the fused and the unfused engines follow the same trajectory (fp32 vs bf16-rounded reduced gradient)
+        drift = ((params[(True, True)] - params[(True, False)]).norm() / params[(True, False)].norm()).item()
+        assert drift < 2e-2, ("fused vs unfused parameters after 4 steps", drift)
+        res["fused_vs_unfused_drift"] = drift
+        # sharded optimizer state -> complete again (checkpoint / planned rescale)
+        tr = StudentTrainer(copy.deepcopy(m0), 8, image_shape=(3, 32, 32), num_classes=16, lr=0.05, use_graph=False,
+                            bucket_cap_mb=0.25, fused_optimizer=True)
+        for _ in range(3):
+            tr.step(x, t)
+        torch.cuda.synchronize()
+        try:
+            tr.state_dict()
+            raise AssertionError("state_dict() of a sharded optimizer state must refuse")
+        except RuntimeError:
+            pass
+        tr.consolidate()
+        for dt, g in tr.dp.flat.groups.items():
+            if g.master is not None:
+                assert torch.equal(g.master.bfloat16(), g.param), "consolidated masters do not match the parameters"
+                outs = [torch.empty_like(tr.opt.state[dt]["mom"]) for _ in range(world)]
+                dist.all_gather(outs, tr.opt.state[dt]["mom"])
+                assert all(torch.equal(outs[0], o) for o in outs), "momentum differs between ranks after consolidate"
+        tr.state_dict()
+
+        # ---- global-norm clipping against the norm of the fp32 reference gradient
+        trc = StudentTrainer(copy.deepcopy(m0), 8, image_shape=(3, 32, 32), num_classes=16, lr=0.0, use_graph=False,
+                             bucket_cap_mb=0.25, clip_norm=0.05, weight_decay=0.0)
+        assert not trc.dp.bucket_opt
+        trc.step(x, t, sync=True)
+        torch.cuda.synchronize()
+        want = float(g_ref.norm())
+        got = float(trc.dp.grad_norm_t.item())
+        assert abs(got - want) / want < 2e-2, ("global gradient norm", got, want)
+        scale = float(trc.dp.clip_scale_t.item())
+        assert abs(scale - min(1.0, 0.05 / (want + 1e-6))) < 2e-2 * max(scale, 1e-3), (scale, want)
+        res["clip"] = {"norm": got, "ref_norm": want, "scale": scale}
 
         # ---- elastic resize without restarting the processes: 2 -> 1 (each rank alone) -> 2
-        solo = [dist.new_group(ranks=[r]) for r in range(world)][rank]
-        tr.rebuild(solo)
+        tr.prepare_rescale()                   # collective over the old stage: sharded optimizer state made complete
+        tr.rebuild(solo_group)
         assert tr.dp.world == 1
         for _ in range(2):
             tr.step(x, t)                      # different data per rank: replicas drift apart

@@ -120,6 +120,9 @@ def exposed(args, dev, world, rank):
         {"bytes": b.numel * (2 if b.dtype == torch.bfloat16 else 4), "algo": b.algo} for b in tr.dp.buckets]}
     res["ms_per_step_with_comm"] = timed(tr.step_device, args.steps, dev)
     # the same step with the reductions switched off: re-capture (the graph bakes the launches in)
+    res["fused_optimizer"] = bool(tr.dp.bucket_opt)
+    res["launched"] = [list(a) for a in tr.dp.last_algos]
+    tr.dp.consolidate_optimizer_state()
     tr.dp.enabled = False
     tr.graph = None
     tr.step(x, t)

@@ -123,6 +123,8 @@ def main():
     # ---- shrink in place: world -> world - drop ------------------------------------------------
     sync()
     t0 = time.perf_counter()
+    tr.prepare_rescale()        # fused optimizer: the sharded master / momentum slices are made complete (old stage)
+    res["consolidate_s"] = wall_max(t0)
     tr.rebuild(small if alive else solo)
     if alive:
         tr.set_lr(scaled_lr(0.1, B, len(survivors)))
@@ -135,6 +137,8 @@ def main():
 
     # ---- grow in place: world - drop -> world (joiners sync from rank 0 over the fabric) --------
     t0 = time.perf_counter()
+    if alive:
+        tr.prepare_rescale()
     tr.rebuild(None)
     tr.sync_from(0)
     tr.set_lr(scaled_lr(0.1, B, world))
@@ -154,6 +158,7 @@ def main():
     fs = LocalFS()
     sync()
     t0 = time.perf_counter()
+    tr.consolidate()
     if rank == 0:
         save_check_point(ckpt_dir, tr.state_dict(), TrainStatus(0), fs)
     dist.barrier()
