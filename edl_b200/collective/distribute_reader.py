@@ -26,23 +26,71 @@ from ..utils.log_utils import logger
 pb = schema.data_server
 
 
+# Record fields travel between pods over plain gRPC: the wire format is DATA ONLY (bytes, str, int, float, bool, None,
+# numpy arrays as dtype + shape + raw buffer, lists / tuples of those).  No pickle: whoever can reach a pod's data
+# server could otherwise execute code in every trainer that fetches from it.
+_NP_OK = frozenset("?bhilqBHILQefd")          # numpy dtype kinds allowed on the wire (no object arrays)
+
+
 def _encode_field(v):
-    if isinstance(v, bytes):
-        return b"b" + v
+    import json
+    import struct
+
+    if isinstance(v, (bytes, bytearray, memoryview)):
+        return b"b" + bytes(v)
     if isinstance(v, str):
         return b"s" + v.encode("utf-8")
-    import pickle
-    return b"p" + pickle.dumps(v)
+    if isinstance(v, (bool, int, float)) or v is None:
+        return b"j" + json.dumps(v).encode()
+    try:
+        import numpy as np
+        if isinstance(v, np.generic):
+            v = np.asarray(v)
+        if isinstance(v, np.ndarray):
+            if v.dtype.char not in _NP_OK:
+                raise TypeError("numpy dtype %s is not allowed in a record field" % v.dtype)
+            head = json.dumps({"d": v.dtype.str, "s": list(v.shape)}).encode()
+            return b"n" + struct.pack("<I", len(head)) + head + np.ascontiguousarray(v).tobytes()
+    except ImportError:
+        pass
+    if isinstance(v, (list, tuple)):
+        parts = [_encode_field(x) for x in v]
+        out = [b"l" if isinstance(v, list) else b"t", struct.pack("<I", len(parts))]
+        for part in parts:
+            out += [struct.pack("<I", len(part)), part]
+        return b"".join(out)
+    raise TypeError("record field of type %s cannot be shipped between pods (bytes, str, numbers, numpy arrays and "
+                    "lists / tuples of those are)" % type(v).__name__)
 
 
 def _decode_field(b):
-    tag, body = b[:1], b[1:]
+    import json
+    import struct
+
+    tag, body = bytes(b[:1]), bytes(b[1:])
     if tag == b"b":
         return body
     if tag == b"s":
         return body.decode("utf-8")
-    import pickle
-    return pickle.loads(body)
+    if tag == b"j":
+        return json.loads(body.decode())
+    if tag == b"n":
+        import numpy as np
+        (n,) = struct.unpack_from("<I", body, 0)
+        head = json.loads(body[4:4 + n].decode())
+        dt = np.dtype(head["d"])
+        if dt.char not in _NP_OK:
+            raise ValueError("refusing numpy dtype %s from the wire" % dt)
+        return np.frombuffer(body[4 + n:], dtype=dt).reshape(head["s"]).copy()
+    if tag in (b"l", b"t"):
+        (count,) = struct.unpack_from("<I", body, 0)
+        off, items = 4, []
+        for _ in range(count):
+            (ln,) = struct.unpack_from("<I", body, off)
+            items.append(_decode_field(body[off + 4:off + 4 + ln]))
+            off += 4 + ln
+        return items if tag == b"l" else tuple(items)
+    raise ValueError("unknown record field tag %r" % tag)
 
 
 class DataGenerator(threading.Thread):
@@ -164,7 +212,8 @@ class Reader:
                 etcd = EtcdClient(env.etcd_endpoints, root=env.job_id)
                 etcd.init()
         self._pod_id, self._pod_ids = pod_id, list(pod_ids or [pod_id])
-        self._server = edl_data_server.DataServer(pod_id).start(addr=server_addr)
+        # the generator may run at most this far ahead of the consumers (back-pressure; nothing is ever evicted)
+        self._server = edl_data_server.DataServer(pod_id, capacity=max(64, 4 * cache_capcity)).start(addr=server_addr)
         if is_leader or (is_leader is None and self._pod_ids[0] == pod_id):
             self._server.servicer.create_reader(self._name, self._file_list, self._pod_ids)
         if etcd is not None:

@@ -98,6 +98,9 @@ struct Conv3x3WgradArgs {
 };
 bool conv3x3_wgrad_supported(int N, int H, int W, int Cin, int Cout);
 int conv3x3_wgrad_tiles(int Cin, int Cout);
+int conv3x3_wgrad_ctas(int Cin, int Cout);        // (tile, filter row) CTAs per K split of the active kernel version
+void set_wgrad3_version(int version, int base_offset_mode);   // 1 = three X loads per block, 2 = one haloed X load (default)
+int get_wgrad3_version();
 int conv3x3_wgrad_kblocks(int N, int H, int W);   // pixel blocks of the reduction (upper bound for split_k)
 void conv3x3_wgrad_plan(int N, int H, int W, int* bh, int* nb, int* kb);   // pixel box {W, bh rows, nb images}, kb = W*bh*nb
 const char* conv3x3_wgrad_bf16(const Conv3x3WgradArgs& args, cudaStream_t stream);

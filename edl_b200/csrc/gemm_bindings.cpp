@@ -280,7 +280,9 @@ void conv3x3_s2(const Tensor& x, const Tensor& w, Tensor& y, const c10::optional
 std::vector<int64_t> conv3x3_wgrad_plan(int64_t n, int64_t h, int64_t w) {
   int bh = 0, nb = 0, kb = 0;
   edl::conv3x3_wgrad_plan((int)n, (int)h, (int)w, &bh, &nb, &kb);
-  return {bh, nb, kb};
+  // box width: W for version 1; for version 2 the box starts at column -1 and spans kb / (bh * nb) >= W + 1 columns
+  const int wb = (bh > 0 && nb > 0) ? kb / (bh * nb) : 0;
+  return {bh, nb, kb, wb};
 }
 
 bool conv3x3_wgrad_supported(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cout) {
@@ -331,6 +333,9 @@ void register_gemm_bindings(pybind11::module_& m) {
   m.def("conv3x3_wgrad_supported", &conv3x3_wgrad_supported);
   m.def("conv3x3_wgrad_tiles", &edl::conv3x3_wgrad_tiles);
   m.def("conv3x3_wgrad_kblocks", &edl::conv3x3_wgrad_kblocks);
+  m.def("conv3x3_wgrad_ctas", &edl::conv3x3_wgrad_ctas);
+  m.def("set_wgrad3_version", &edl::set_wgrad3_version);
+  m.def("get_wgrad3_version", &edl::get_wgrad3_version);
   m.def("conv3x3_wgrad_plan", &conv3x3_wgrad_plan);
   m.def("conv3x3_s2", &conv3x3_s2);
 }

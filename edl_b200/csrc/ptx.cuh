@@ -167,6 +167,12 @@ EDL_DEVICE uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t 
   return d;
 }
 
+// Same, with an explicit "matrix base offset" (bits 49..51): the PTX ISA asks for ((start address >> 7) & 7) when the
+// matrix does not start on the 1024-byte boundary of the 128B-swizzle repeating pattern.
+EDL_DEVICE uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_offset) {
+  return make_smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)(base_offset & 7u) << 49);
+}
+
 // Instruction descriptor for kind::f16 / kind::f8f6f4 with fp32 accumulation.
 //   fmt: kind::f16 -> 0 = f16, 1 = bf16 ; kind::f8f6f4 -> 0 = e4m3, 1 = e5m2
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t a_fmt, uint32_t b_fmt, uint32_t m,

@@ -486,8 +486,9 @@ def conv3x3_wgrad(x, dy, weight_shape, sink=None, split_k: Optional[int] = None)
     ws, counters = _splitk_workspace(x.device, cout * 9 * cin, tiles)
     if split_k is None:
         kblocks = native().conv3x3_wgrad_kblocks(n, h, w)
+        ctas = native().conv3x3_wgrad_ctas(cin, cout)
         # one wave of CTAs, at least two pixel blocks per CTA (same rule as the 1x1 wgrad split)
-        split_k = max(1, min(max(1, _NUM_SMS // tiles), max(1, kblocks // 2)))
+        split_k = max(1, min(max(1, _NUM_SMS // ctas), max(1, kblocks // 2)))
     if sink is not None:
         out, acc = sink.view(weight_shape), True
     else:

@@ -96,10 +96,13 @@ data_server = _NS(_register(_build_file("edl/data_server.proto", "data_server", 
     "ReportBatchDataMetaRequest": [("reader_name", 1, "string", False), ("pod_id", 2, "string", False),
                                    ("data_server_endpoint", 3, "string", False),
                                    ("batch_data_ids", 4, "string", True)],
-    "GetBatchDataMetaRequest": [("reader_name", 1, "string", False), ("pod_id", 2, "string", False)],
+    # ack_seq (extension, field 3): sequence number of the last BatchDataMetaResponse this consumer RECEIVED -- the
+    # leader re-sends its previous answer until it is acknowledged, so a lost response loses no batch ids
+    "GetBatchDataMetaRequest": [("reader_name", 1, "string", False), ("pod_id", 2, "string", False),
+                                ("ack_seq", 3, "uint64", False)],
     "ReachDataEndRequest": [("reader_name", 1, "string", False), ("pod_id", 2, "string", False)],
     "BatchDataMetaResponse": [("status", 1, ".common.Status", False),
-                              ("data", 2, ".data_server.BatchDataMeta", True)],
+                              ("data", 2, ".data_server.BatchDataMeta", True), ("seq", 3, "uint64", False)],
     "BatchDataResponse": [("status", 1, ".common.Status", False), ("data", 2, ".data_server.BatchData", True)],
 }, deps=["edl/common.proto"])))
 

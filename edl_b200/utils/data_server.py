@@ -33,6 +33,7 @@ class PodsData:
     """Leader-side balancer state for one reader."""
 
     def __init__(self, reader_name, file_list, pod_ids, grant=4):
+        self.last = {}           # consumer pod -> (seq, answer): re-sent until the consumer acknowledges it
         self.reader_name = reader_name
         self.file_list = list(file_list)
         self.pod_ids = sorted(pod_ids)
@@ -63,6 +64,21 @@ class PodsData:
                 raise exceptions.EdlPodIDNotExistError(pod_id)
             self.queues[pod_id].ended = True
 
+    def pop_acked(self, pod_id, ack_seq):
+        """Idempotent hand-out: ``ack_seq`` is the sequence number of the last answer the consumer received.  If
+        it is not the one we sent last, that answer was lost on the way: send it again (its ids are already off
+        the queues) instead of handing out new ones.  -> (seq, answer)"""
+        with self.lock:
+            seq, ans = self.last.get(pod_id, (0, None))
+            if ans and ack_seq != seq:
+                return seq, ans
+        ans = self.pop(pod_id)
+        with self.lock:
+            if ans:
+                seq += 1
+                self.last[pod_id] = (seq, ans)
+            return seq, ans
+
     def pop(self, pod_id):
         """-> list of (producer_pod_id, endpoint, [ids]); [] = nothing available *yet*.
         Raises EdlDataEndError when every producer ended and all ids were handed out."""
@@ -91,24 +107,51 @@ class PodsData:
 
 
 class DataServerServicer:
-    def __init__(self, pod_id, is_leader_fn=None):
+    """``capacity`` bounds the producer: ``put_batch`` BLOCKS while that many batches wait to be fetched (nothing
+    is ever evicted: every cached id may already have been reported to the leader and promised to a consumer).
+    Fetched batches move to a small ring of recently served ones so that a consumer whose ``GetBatchData`` answer
+    was lost gets the same batches again when it retries."""
+
+    def __init__(self, pod_id, is_leader_fn=None, capacity=256, served_keep=64):
         self._pod_id = pod_id
         self._is_leader_fn = is_leader_fn
         self._lock = threading.Lock()
+        self._space = threading.Condition(self._lock)
         self._pods_data = {}                      # reader_name -> PodsData (leader only)
         self._batches = OrderedDict()             # batch_data_id -> BatchData pb (every pod)
-        self._capacity = 10000
+        self._served = OrderedDict()              # recently fetched batches (retry safety net)
+        self._capacity = max(32, int(capacity))
+        self._served_keep = served_keep
+        self._closed = False
 
     # ---- local batch cache (producer side)
-    def put_batch(self, batch):
-        with self._lock:
+    def put_batch(self, batch, timeout=None):
+        """Blocks while the cache is full (back-pressure on the generator).  False if the server was closed."""
+        with self._space:
+            while len(self._batches) >= self._capacity and not self._closed:
+                if not self._space.wait(timeout=timeout if timeout is not None else 1.0) and timeout is not None:
+                    raise exceptions.EdlAccessDataError("batch cache of pod {} stayed full for {} s".format(
+                        self._pod_id, timeout))
+            if self._closed:
+                return False
             self._batches[batch.batch_data_id] = batch
-            while len(self._batches) > self._capacity:
-                self._batches.popitem(last=False)
+            return True
 
     def pop_batch(self, batch_id):
-        with self._lock:
-            return self._batches.pop(batch_id, None)
+        with self._space:
+            b = self._batches.pop(batch_id, None)
+            if b is not None:
+                self._served[batch_id] = b
+                while len(self._served) > self._served_keep:
+                    self._served.popitem(last=False)
+                self._space.notify_all()
+                return b
+            return self._served.get(batch_id)       # a retried fetch of something already handed out
+
+    def close(self):
+        with self._space:
+            self._closed = True
+            self._space.notify_all()
 
     # ---- leader registration of a reader
     def create_reader(self, reader_name, file_list, pod_ids):
@@ -159,7 +202,9 @@ class DataServerServicer:
     def GetBatchDataMeta(self, request, context):
         res = pb.BatchDataMetaResponse()
         try:
-            for producer, endpoint, ids in self._reader(request.reader_name).pop(request.pod_id):
+            seq, answer = self._reader(request.reader_name).pop_acked(request.pod_id, int(request.ack_seq))
+            res.seq = seq
+            for producer, endpoint, ids in answer:
                 m = res.data.add()
                 m.reader_name, m.producer_pod_id, m.consumer_pod_id = request.reader_name, producer, request.pod_id
                 m.data_server_endpoint = endpoint or ""
@@ -182,8 +227,11 @@ class DataServerServicer:
 
 
 class DataServer:
-    def __init__(self, pod_id, host="0.0.0.0"):
-        self.servicer = DataServerServicer(pod_id)
+    """``host``: interface to bind -- the pod's own address by default (``start(addr=...)``), NOT 0.0.0.0: the
+    server hands out training records to whoever asks."""
+
+    def __init__(self, pod_id, host=None, capacity=256):
+        self.servicer = DataServerServicer(pod_id, capacity=capacity)
         self._server = None
         self._host = host
         self.port = None
@@ -195,7 +243,7 @@ class DataServer:
             "GetFileList": sv.GetFileList, "ReportBatchDataMeta": sv.ReportBatchDataMeta,
             "ReachDataEnd": sv.ReachDataEnd, "GetBatchDataMeta": sv.GetBatchDataMeta,
             "GetBatchData": sv.GetBatchData})
-        self.port = self._server.add_insecure_port("{}:0".format(self._host))
+        self.port = self._server.add_insecure_port("{}:0".format(self._host or addr))
         assert self.port > 0
         self._server.start()
         self.endpoint = "{}:{}".format(addr, self.port)
@@ -203,6 +251,7 @@ class DataServer:
         return self
 
     def stop(self):
+        self.servicer.close()
         if self._server is not None:
             self._server.stop(0)
             self._server = None

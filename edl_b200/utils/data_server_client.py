@@ -18,6 +18,7 @@ class _Conn:
 class Client:
     def __init__(self):
         self._conns = {}
+        self._acks = {}
         self._lock = threading.Lock()
 
     def _stub(self, endpoint):
@@ -57,12 +58,35 @@ class Client:
             pb.ReachDataEndRequest(reader_name=reader_name, pod_id=pod_id), timeout=10)
         exceptions.deserialize(res.status)
 
+    def _get_batch_data_meta(self, leader_endpoint, reader_name, pod_id, ack_seq, timeout=60):
+        """Retries transport / transient errors only: "the epoch is drained" is an answer, not a failure."""
+        import time
+
+        deadline = time.time() + timeout
+        while True:
+            try:
+                res = self._stub(leader_endpoint).GetBatchDataMeta(
+                    pb.GetBatchDataMetaRequest(reader_name=reader_name, pod_id=pod_id, ack_seq=ack_seq), timeout=10)
+                exceptions.deserialize(res.status)
+                return res
+            except exceptions.EdlDataEndError:
+                raise
+            except exceptions.EdlException:
+                if time.time() >= deadline:
+                    raise
+                time.sleep(0.05)
+
     def get_batch_data_meta(self, leader_endpoint, reader_name, pod_id, timeout=60):
-        """-> list of BatchDataMeta; raises EdlDataEndError when the epoch is drained."""
-        res = self._stub(leader_endpoint).GetBatchDataMeta(
-            pb.GetBatchDataMetaRequest(reader_name=reader_name, pod_id=pod_id), timeout=10)
-        exceptions.deserialize(res.status)
-        return list(res.data)
+        """-> list of BatchDataMeta; raises EdlDataEndError when the epoch is drained.  Safe to retry: the request
+        carries the sequence number of the last answer received, the leader re-sends an unacknowledged answer."""
+        key = (leader_endpoint, reader_name, pod_id)
+        with self._lock:
+            ack = self._acks.get(key, 0)
+        res = self._get_batch_data_meta(leader_endpoint, reader_name, pod_id, ack, timeout=timeout)
+        with self._lock:
+            fresh = int(res.seq) != ack
+            self._acks[key] = int(res.seq)
+        return list(res.data) if fresh else []
 
     @handle_errors_until_timeout
     def get_batch_data(self, meta, timeout=60):

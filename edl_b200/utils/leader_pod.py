@@ -55,6 +55,8 @@ class Register:
                     self._seize_leader()
             except Exception as e:  # noqa: BLE001
                 logger.warning("leader register of %s stopped: %s", self._pod_id, e)
+                with self._lock:
+                    self._is_leader = False     # the lease is gone: rank/0 may already belong to somebody else
                 self._generator.stop()
                 self._dead.set()
                 break
@@ -68,7 +70,13 @@ class Register:
         self._generator.stop()
         if self._is_leader:
             try:
-                self._etcd.remove_server(constants.ETCD_POD_RANK, constants.ETCD_POD_LEADER)
+                # delete rank/0 only while it still names THIS pod (one transaction): after a lost lease a new
+                # leader may own the key, and removing it would take that pod down
+                key = self._etcd.get_full_path(constants.ETCD_POD_RANK, constants.ETCD_POD_LEADER)
+                self._etcd.kv.txn([{"key": key, "value": self._pod_id.encode() if isinstance(self._pod_id, str)
+                                    else self._pod_id}], [{"op": "delete", "key": key}], [])
+                if self._lease is not None:
+                    self._lease.revoke()
             except Exception:  # noqa: BLE001
                 pass
             self._is_leader = False

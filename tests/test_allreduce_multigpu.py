@@ -168,7 +168,8 @@ def _worker(rank, world, port, q):
                 res["engine_grad_err"] = err
             res["algos_fused_%s" % fused] = sorted({a for a, _, _ in tr.dp.last_algos})
         params = {}
-        for use_graph, fused in ((False, True), (True, True), (True, False)):
+        for use_graph, fused in ((False, True), (True, True), (True, False), (True, "again")):
+            again, fused = fused == "again", fused is True
             tr = StudentTrainer(copy.deepcopy(m0), 8, image_shape=(3, 32, 32), num_classes=16, lr=0.05,
                                 use_graph=use_graph, bucket_cap_mb=0.25, fused_optimizer=fused)
             for _ in range(4):
@@ -182,11 +183,13 @@ def _worker(rank, world, port, q):
             assert torch.isfinite(flat).all()
             assert tr.dp.comm_launches > 0
             res["comm_launches_graph_%s_fused_%s" % (use_graph, fused)] = tr.dp.comm_launches
-            params[(use_graph, fused)] = flat
-        # the fused and the unfused engines follow the same trajectory (fp32 vs bf16-rounded reduced gradient)
+            params["again" if again else (use_graph, fused)] = flat
+        # the fused and the unfused engines follow the same trajectory (fp32 vs bf16-rounded reduced gradient); the
+        # yardstick is the run-to-run drift of the unfused engine itself (float atomics in the BatchNorm statistics)
         drift = ((params[(True, True)] - params[(True, False)]).norm() / params[(True, False)].norm()).item()
-        assert drift < 2e-2, ("fused vs unfused parameters after 4 steps", drift)
-        res["fused_vs_unfused_drift"] = drift
+        noise = ((params["again"] - params[(True, False)]).norm() / params[(True, False)].norm()).item()
+        assert drift < max(2e-2, 3 * noise), ("fused vs unfused parameters after 4 steps", drift, noise)
+        res["fused_vs_unfused_drift"] = [drift, noise]
         # sharded optimizer state -> complete again (checkpoint / planned rescale)
         tr = StudentTrainer(copy.deepcopy(m0), 8, image_shape=(3, 32, 32), num_classes=16, lr=0.05, use_graph=False,
                             bucket_cap_mb=0.25, fused_optimizer=True)

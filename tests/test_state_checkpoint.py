@@ -93,3 +93,122 @@ def test_checkpoint_versions_are_atomic(tmp_path):
     tensors, ts, sj = load_check_point(path, fs)
     assert ts.next() == 4 and ts.global_step == 30 and sj == '{"e": 3}'
     assert float(tensors["model"]["weight"][0, 0]) == 3.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Remote file systems: a fake ``hadoop`` CLI (maps "hadoop fs -<cmd>" onto a local directory tree) stands in for
+# HDFS, so HDFSClient / BDFS, the checkpoint upload / download path and the distill conf fetch run for real.
+_FAKE_HADOOP = r'''#!/usr/bin/env python3
+import os, shutil, sys
+root = os.environ["FAKE_HDFS_ROOT"]
+a = sys.argv[1:]
+assert a[0] == "fs", a
+a = a[1:]
+while a and a[0] == "-D":
+    a = a[2:]
+m = lambda p: os.path.join(root, p.lstrip("/"))
+cmd, rest = a[0], [x for x in a[1:] if not x.startswith("-")]
+if cmd == "-ls":
+    p = m(rest[0])
+    if not os.path.isdir(p):
+        sys.exit(1)
+    for f in sorted(os.listdir(p)):
+        full = os.path.join(p, f)
+        print("%s   - u g 0 2020-01-01 00:00 %s" % ("drwxr-xr-x" if os.path.isdir(full) else "-rw-r--r--",
+                                                    os.path.join(rest[0], f)))
+elif cmd == "-test":
+    sys.exit(0 if os.path.exists(m(rest[0])) else 1)
+elif cmd == "-mkdir":
+    os.makedirs(m(rest[0]), exist_ok=True)
+elif cmd == "-rm":
+    p = m(rest[0])
+    shutil.rmtree(p, ignore_errors=True) if os.path.isdir(p) else (os.path.exists(p) and os.remove(p))
+elif cmd == "-mv":
+    os.replace(m(rest[0]), m(rest[1]))
+elif cmd == "-put":
+    src, dst = rest[0], m(rest[1])
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    shutil.copytree(src, dst, dirs_exist_ok=True) if os.path.isdir(src) else shutil.copyfile(src, dst)
+elif cmd == "-get":
+    src, dst = m(rest[0]), rest[1]
+    if os.path.isdir(src):
+        shutil.copytree(src, os.path.join(dst, os.path.basename(src)) if os.path.isdir(dst) else dst, dirs_exist_ok=True)
+    else:
+        shutil.copyfile(src, os.path.join(dst, os.path.basename(src)) if os.path.isdir(dst) else dst)
+else:
+    sys.exit(2)
+'''
+
+
+@pytest.fixture
+def fake_hdfs(tmp_path, monkeypatch):
+    bin_dir, root = tmp_path / "bin", tmp_path / "hdfs"
+    bin_dir.mkdir()
+    root.mkdir()
+    exe = bin_dir / "hadoop"
+    exe.write_text(_FAKE_HADOOP)
+    exe.chmod(0o755)
+    monkeypatch.setenv("PATH", str(bin_dir) + os.pathsep + os.environ["PATH"])
+    monkeypatch.setenv("FAKE_HDFS_ROOT", str(root))
+    return root
+
+
+def test_checkpoint_through_a_remote_file_system(fake_hdfs):
+    """save / load with HDFSClient: tensors are written locally, uploaded under the temporary name and committed by
+    the REMOTE rename; nothing of the checkpoint stays on the local disk (reference: fleet.save_check_point with
+    BDFS, example/collective/resnet50/train_with_fleet.py:422-434)."""
+    from edl_b200.checkpoint import TrainStatus, load_check_point, save_check_point
+    from edl_b200.checkpoint.fs import BDFS, HDFSClient
+
+    fs = HDFSClient("hdfs://fake", "user,pass", time_out=3000, sleep_inter=100)
+    assert BDFS is HDFSClient and fs.available and fs.need_upload_download()
+    sd = {"w": torch.arange(6.0).view(2, 3), "step": 7}
+    assert save_check_point("/job/ckpt", sd, TrainStatus(3, 70), fs) == 0
+    assert save_check_point("/job/ckpt", {"w": sd["w"] * 2, "step": 8}, TrainStatus(4, 80), fs, state_json='{"lr": 0.1}') == 1
+    assert not os.path.exists("/job/ckpt")                                    # nothing leaked onto the local disk
+    names = sorted(os.listdir(fake_hdfs / "job" / "ckpt"))
+    assert names == ["__edl_checkpoint__.0", "__edl_checkpoint__.1"], names
+    tensors, ts, sj = load_check_point("/job/ckpt", fs)
+    assert torch.equal(tensors["w"], sd["w"] * 2) and tensors["step"] == 8 and ts.epoch_no == 4 and sj == '{"lr": 0.1}'
+    old, ts0, _ = load_check_point("/job/ckpt", fs, version=0)
+    assert torch.equal(old["w"], sd["w"]) and ts0.global_step == 70
+    for _ in range(3):                                                        # keep-N on the remote side
+        save_check_point("/job/ckpt", sd, TrainStatus(9), fs, keep=2)
+    assert len(os.listdir(fake_hdfs / "job" / "ckpt")) == 2
+
+
+def test_distill_conf_file_from_hdfs(fake_hdfs, tmp_path, monkeypatch):
+    """python/edl/distill/utils.py:19-34: the teacher's serving conf is downloaded from HDFS when the
+    PADDLE_DISTILL_HDFS_* variables are set."""
+    from edl_b200.distill.utils import get_conf_file
+
+    (fake_hdfs / "conf").mkdir()
+    (fake_hdfs / "conf" / "serving_client_conf.prototxt").write_text('feed_var { name: "image" }\n')
+    monkeypatch.delenv("PADDLE_DISTILL_CONF_FILE", raising=False)
+    monkeypatch.setenv("PADDLE_DISTILL_HDFS_NAME", "hdfs://fake")
+    monkeypatch.setenv("PADDLE_DISTILL_HDFS_UGI", "user,pass")
+    monkeypatch.setenv("PADDLE_DISTILL_HDFS_PATH", "/conf/serving_client_conf.prototxt")
+    dst = str(tmp_path / "serving_conf" / "serving_client_conf.prototxt")
+    assert get_conf_file(dst) == dst and "feed_var" in open(dst).read()
+
+
+def test_leader_key_is_only_removed_by_its_owner(etcd):
+    """A pod that lost its lease must not delete a NEW leader's rank/0 key when it shuts down."""
+    from edl_b200.utils import constants, leader_pod
+
+    class _Gen:
+        def start(self): pass
+        def stop(self): pass
+        def is_stopped(self): return False
+
+    class _Env:
+        etcd_endpoints, job_id = None, "j"
+
+    reg = leader_pod.Register(_Env(), "pod-old", cluster_generator=_Gen(), ttl=5, etcd=etcd)
+    assert reg.is_leader()
+    # somebody else took over (the old leader's lease expired while it was partitioned)
+    etcd.remove_server(constants.ETCD_POD_RANK, constants.ETCD_POD_LEADER)
+    assert etcd.set_server_not_exists(constants.ETCD_POD_RANK, constants.ETCD_POD_LEADER, "pod-new", ttl=30)
+    reg._is_leader = True                      # stale belief of the old leader
+    reg.stop()
+    assert etcd.get_value(constants.ETCD_POD_RANK, constants.ETCD_POD_LEADER) in ("pod-new", b"pod-new")

@@ -115,6 +115,13 @@ def run(mode, server_cls):
             return {"mode": mode, "leave": CFG["leave"], "store": server_cls.__name__, "join_s": join, "join_stall_s": join_stall,
                     "leave_s": leave, "leave_stall_s": leave_stall, "survivor_process_kept": survivor_kept,
                     "steady_epoch_s": sorted(y["t"] - x["t"] for x, y in zip(e[-5:-1], e[-4:]))[1]}
+        except Exception:
+            # keep the evidence: launcher and trainer logs of both pods (gpurun_out/ travels back from the GPU box)
+            import shutil
+            dst = os.path.join(ROOT, "gpurun_out", "elastic_fail_%s_%s" % (mode, CFG["leave"]))
+            shutil.rmtree(dst, ignore_errors=True)
+            shutil.copytree(tmp, dst, ignore=shutil.ignore_patterns("ckpt*", "*.pt"))
+            raise
         finally:
             import psutil
 
@@ -144,7 +151,12 @@ if __name__ == "__main__":
     args = ap.parse_args()
     CFG.update(trainer=args.trainer, gpus_per_pod=args.gpus_per_pod, leave=args.leave)
     cls = NativeKVServer if args.native_store else KVServer
-    res = [run("restart", cls), run("inplace", cls)]
+    res = []
+    for mode in ("restart", "inplace"):
+        try:
+            res.append(run(mode, cls))
+        except Exception as e:  # noqa: BLE001 - the other mode is still worth measuring
+            res.append({"mode": mode, "leave": CFG["leave"], "error": repr(e)[:300]})
     for r in res:
         print(json.dumps(r))
     if args.out:
