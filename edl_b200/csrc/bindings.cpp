@@ -257,6 +257,15 @@ void gap_fwd(const Tensor& x, Tensor& y) {
   edl::gap_fwd(x.data_ptr(), y.data_ptr(), x.size(0), x.size(1) * x.size(2), x.size(3),
                cur_stream());
 }
+void dilate2(const Tensor& x, Tensor& y) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.scalar_type() == at::kBFloat16 &&
+              x.is_contiguous(at::MemoryFormat::ChannelsLast), "dilate2: x must be a channels_last bf16 NCHW tensor");
+  TORCH_CHECK(y.is_cuda() && y.scalar_type() == at::kBFloat16 && y.is_contiguous(at::MemoryFormat::ChannelsLast));
+  TORCH_CHECK(y.size(0) == x.size(0) && y.size(1) == x.size(1) && y.size(2) == 2 * x.size(2) && y.size(3) == 2 * x.size(3));
+  TORCH_CHECK(x.size(1) % 8 == 0);
+  c10::cuda::CUDAGuard g(x.device());
+  edl::dilate2(x.data_ptr(), y.data_ptr(), x.size(0), x.size(2), x.size(3), x.size(1), cur_stream());
+}
 void gap_bwd(const Tensor& dy, Tensor& dx) {
   check_bf16(dy, "dy");
   c10::cuda::CUDAGuard g(dy.device());
@@ -399,6 +408,24 @@ void stem_conv3x3s2(const Tensor& x, const Tensor& w, Tensor& y, const c10::opti
                       at::cuda::getCurrentCUDAStream().stream());
 }
 
+// dw KRSC [32,3,3,3] bf16 (+)= wgrad of the stem convolution; x [N,3,H,W], dy [N,32,H/2,W/2] channels_last bf16
+void stem_wgrad(const Tensor& x, const Tensor& dy, Tensor& dw, Tensor& ws, Tensor& counter, bool accumulate) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.size(1) == 3 && x.scalar_type() == at::kBFloat16 &&
+              x.is_contiguous(at::MemoryFormat::ChannelsLast));
+  TORCH_CHECK(dy.dim() == 4 && dy.size(1) == 32 && dy.scalar_type() == at::kBFloat16 &&
+              dy.is_contiguous(at::MemoryFormat::ChannelsLast) && dy.size(0) == x.size(0) &&
+              dy.size(2) * 2 == x.size(2) && dy.size(3) * 2 == x.size(3));
+  TORCH_CHECK(dw.scalar_type() == at::kBFloat16 && dw.is_contiguous() && dw.numel() == 864);
+  TORCH_CHECK(ws.scalar_type() == at::kFloat && ws.is_contiguous() && ws.numel() >= 864 &&
+              reinterpret_cast<uintptr_t>(ws.data_ptr()) % 16 == 0);
+  TORCH_CHECK(counter.scalar_type() == at::kInt && counter.numel() >= 1);
+  c10::cuda::CUDAGuard guard(x.device());
+  const char* err = edl::stem_wgrad(x.data_ptr(), dy.data_ptr(), ws.data_ptr<float>(), counter.data_ptr<int>(),
+                                    dw.data_ptr(), accumulate, (int)x.size(0), (int)x.size(2), (int)x.size(3),
+                                    at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(err == nullptr, "stem_wgrad: ", err);
+}
+
 void embedding_bag_fwd(const Tensor& table, const Tensor& ids, Tensor& out) {
   TORCH_CHECK(table.is_cuda() && table.is_contiguous() && ids.is_contiguous() && ids.scalar_type() == at::kLong);
   c10::cuda::CUDAGuard g(table.device());
@@ -498,6 +525,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("maxpool3x3s2_bwd", &maxpool3x3s2_bwd);
   m.def("avgpool2x2_fwd", &avgpool2x2_fwd);
   m.def("avgpool2x2_bwd", &avgpool2x2_bwd);
+  m.def("dilate2", &dilate2);
   m.def("gap_fwd", &gap_fwd);
   m.def("gap_bwd", &gap_bwd);
   m.def("allreduce_oneshot", &allreduce_oneshot);
@@ -512,6 +540,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rope", &rope);
   m.def("embedding_bag_fwd", &embedding_bag_fwd);
   m.def("stem_conv3x3s2", &stem_conv3x3s2);
+  m.def("stem_wgrad", &stem_wgrad);
   m.def("embedding_bag_bwd", &embedding_bag_bwd);
   m.def("normalize_u8", &normalize_u8);
   m.def("peer_ship", &peer_ship);

@@ -53,6 +53,8 @@ struct WgradParams {
   __nv_bfloat16* out;        // bf16 [Cout][9*Cin] (KRSC)
   int* counters;             // [tiles * 3], zero on entry and on exit
   int accumulate;
+  int stride;                // 1, or 2: X rows 2*h + r - 1 (the columns are subsampled by the tensor map)
+  float* part;               // split-K partial tiles [split][ctas][128 x 192] (no atomics) or nullptr
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -114,7 +116,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
           if (two_chunks) ptx::tma_load_4d(sa + kChunkBytes, &tmDy, &full_bar[st], m0 + 64, 0, h0, img0);
 #pragma unroll
           for (int s = 0; s < 3; ++s)
-            ptx::tma_load_4d(sb + s * kChunkBytes, &tmX, &full_bar[st], n0, s - 1, h0 + r - 1, img0);
+            ptx::tma_load_4d(sb + s * kChunkBytes, &tmX, &full_bar[st], n0, s - 1, h0 * p.stride + r - 1, img0);
         }
       }
     } else if (warp == 1) {
@@ -190,13 +192,16 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
             packed.x = *reinterpret_cast<const uint32_t*>(&lo);
             packed.y = *reinterpret_cast<const uint32_t*>(&hi);
             *reinterpret_cast<uint2*>(o) = packed;
+          } else if (p.part != nullptr) {
+            *reinterpret_cast<float4*>(p.part + ((int64_t)blockIdx.z * gridDim.x + blockIdx.x) * (kBlockM * 3 * kBlockN) +
+                                       rr * (3 * kBlockN) + s * kBlockN + c4) = t;
           } else {
             red_add_v4(p.ws + off, t.x, t.y, t.z, t.w);
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile is reused by the next tap
       }
-      if (!direct) {
+      if (!direct && p.part == nullptr) {
         // ---- fused finalize by the last-arriving CTA of this (tile, filter row) ----
         uint32_t* s_last = tmem_slot + 1;
         __threadfence();
@@ -284,6 +289,7 @@ struct Wgrad2Params {
   __nv_bfloat16* out;
   int* counters;
   int accumulate;
+  float* part;               // split-K partial tiles [split][ctas][128 x 3*BLOCK_N] (no atomics) or nullptr
 };
 
 template <int BLOCK_N>
@@ -426,13 +432,16 @@ conv3x3_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
             packed.x = *reinterpret_cast<const uint32_t*>(&lo);
             packed.y = *reinterpret_cast<const uint32_t*>(&hi);
             *reinterpret_cast<uint2*>(o) = packed;
+          } else if (p.part != nullptr) {
+            *reinterpret_cast<float4*>(p.part + ((int64_t)blockIdx.z * gridDim.x + blockIdx.x) * (kBlockM * 3 * BLOCK_N) +
+                                       rr * (3 * BLOCK_N) + s * BLOCK_N + c4) = t;
           } else {
             red_add_v4(p.ws + off, t.x, t.y, t.z, t.w);
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      if (!direct) {
+      if (!direct && p.part == nullptr) {
         uint32_t* s_last = tmem_slot + 1;
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -558,8 +567,17 @@ const char* launch_wgrad2(const Conv3x3WgradArgs& a, const Wgrad2Geometry& geo, 
   p.counters = a.counters;
   p.accumulate = a.accumulate ? 1 : 0;
   dim3 grid(tiles_m * p.tiles_n * 3, 1, split);
+  const bool use_part = split > 1 && a.partials != nullptr &&
+                        a.partials_elems >= (int64_t)split * grid.x * kBlockM * 3 * BLOCK_N;
+  p.part = use_part ? a.partials : nullptr;
   kern<<<grid, kThreads, L::kTotal, stream>>>(tmDy, tmX, p);
   cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cudaGetErrorString(e);
+  if (use_part) {
+    splitk_reduce(a.partials, split, (int)grid.x, p.tiles_n, kBlockM, 3 * BLOCK_N, 3, a.Cin, a.Cout, 9 * a.Cin, a.dW,
+                  (int64_t)9 * a.Cin, a.accumulate, stream);
+    e = cudaGetLastError();
+  }
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -603,14 +621,23 @@ void set_wgrad3_version(int version, int base_offset_mode) {
 }
 int get_wgrad3_version() { return g_wgrad3_version; }
 
+bool conv3x3_wgrad_s2_supported(int N, int Ho, int Wo, int Cin, int Cout) {
+  if (Cin % 64 != 0 || Cout % 64 != 0 || 2 * Wo > 256) return false;
+  const WgradGeometry g = plan_wgrad(N, Ho, Wo);
+  return g.ok && 2 * g.BH <= 256;
+}
+
 const char* conv3x3_wgrad_bf16(const Conv3x3WgradArgs& a, cudaStream_t stream) {
-  if (!conv3x3_wgrad_supported(a.N, a.H, a.W, a.Cin, a.Cout)) return "conv3x3_wgrad: unsupported shape";
+  const bool s2 = a.stride == 2;
+  if (s2 ? !conv3x3_wgrad_s2_supported(a.N, a.H, a.W, a.Cin, a.Cout)
+         : !conv3x3_wgrad_supported(a.N, a.H, a.W, a.Cin, a.Cout))
+    return "conv3x3_wgrad: unsupported shape";
   if (a.ws == nullptr || a.counters == nullptr || a.dW == nullptr) return "conv3x3_wgrad: missing buffers";
   if (a.device >= 0) {
     cudaError_t e = cudaSetDevice(a.device);   // tensor-map encoding needs a bound context (see gemm.cu)
     if (e != cudaSuccess) return cudaGetErrorString(e);
   }
-  if (g_wgrad3_version == 2) {
+  if (g_wgrad3_version == 2 && !s2) {
     const Wgrad2Geometry g2 = plan_wgrad2(a.N, a.H, a.W);
     return a.Cin % 128 == 0 ? launch_wgrad2<128>(a, g2, stream) : launch_wgrad2<64>(a, g2, stream);
   }
@@ -622,11 +649,20 @@ const char* conv3x3_wgrad_bf16(const Conv3x3WgradArgs& a, cudaStream_t stream) {
     const uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)geo.BH, (uint32_t)geo.NB};
     if (const char* e = encode_tmap_bf16(&tmDy, a.dY, 4, dims, st, box)) return e;
   }
-  {
+  if (!s2) {
     const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
     const uint64_t st[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2};
     const uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)geo.BH, (uint32_t)geo.NB};
     if (const char* e = encode_tmap_bf16(&tmX, a.X, 4, dims, st, box)) return e;
+  } else {
+    // the input is [N, 2H, 2W, Cin]: a box spanning 2W x 2BH elements with traversal stride 2 delivers the W x BH
+    // input pixels that tap (r, s) pairs with the dY box -- same K-row order, no im2col, no subsample pass
+    const uint64_t H2 = 2ull * a.H, W2 = 2ull * a.W;
+    const uint64_t dims[4] = {(uint64_t)a.Cin, W2, H2, (uint64_t)a.N};
+    const uint64_t st[3] = {(uint64_t)a.Cin * 2, W2 * a.Cin * 2, H2 * W2 * a.Cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)(2 * a.W), (uint32_t)(2 * geo.BH), (uint32_t)geo.NB};
+    const uint32_t es[4] = {1, 2, 2, 1};
+    if (const char* e = encode_tmap_strided(&tmX, a.X, 4, dims, st, box, es, 2)) return e;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -650,9 +686,19 @@ const char* conv3x3_wgrad_bf16(const Conv3x3WgradArgs& a, cudaStream_t stream) {
   p.out = reinterpret_cast<__nv_bfloat16*>(a.dW);
   p.counters = a.counters;
   p.accumulate = a.accumulate ? 1 : 0;
+  p.stride = s2 ? 2 : 1;
   dim3 grid(tiles_m * p.tiles_n * 3, 1, split);
+  const bool use_part = split > 1 && a.partials != nullptr &&
+                        a.partials_elems >= (int64_t)split * grid.x * kBlockM * 3 * kBlockN;
+  p.part = use_part ? a.partials : nullptr;
   conv3x3_wgrad_kernel<<<grid, kThreads, kSmemTotal, stream>>>(tmDy, tmX, p);
   cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cudaGetErrorString(e);
+  if (use_part) {
+    splitk_reduce(a.partials, split, (int)grid.x, p.tiles_n, kBlockM, 3 * kBlockN, 3, a.Cin, a.Cout, 9 * a.Cin, a.dW,
+                  (int64_t)9 * a.Cin, a.accumulate, stream);
+    e = cudaGetLastError();
+  }
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -676,6 +722,13 @@ void conv3x3_wgrad_plan(int N, int H, int W, int* bh, int* nb, int* kb) {
   *bh = g.ok ? g.BH : 0;
   *nb = g.ok ? g.NB : 0;
   *kb = g.ok ? g.KB : 0;
+}
+
+// stride-2 layers always run on the version-1 kernel: pixel blocks / CTAs per split for the split-K heuristic
+int conv3x3_wgrad_s2_kblocks(int N, int Ho, int Wo) {
+  const WgradGeometry g = plan_wgrad(N, Ho, Wo);
+  if (!g.ok) return 0;
+  return ((Ho + g.BH - 1) / g.BH) * ((N + g.NB - 1) / g.NB);
 }
 
 int conv3x3_wgrad_kblocks(int N, int H, int W) {

@@ -46,6 +46,7 @@ struct GemmParams {
   long long ldo;
   int* tile_counters;
   int accumulate;
+  float* part;       // split-K partial tiles [split][tiles][BLOCK_M x BLOCK_N] (no atomics) or nullptr
   // GEMM -> peer ship (see gemm.h)
   uint32_t* ship_flag;
   const uint32_t* ship_seq_ptr;
@@ -318,6 +319,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             packed.y = *reinterpret_cast<const uint32_t*>(&hi);
             *reinterpret_cast<uint2*>(o) = packed;
           }
+        } else if (p.part != nullptr) {
+          // split-K partial tile: plain coalesced 16-byte stores, summed by splitk_reduce_kernel afterwards
+          float* dst = p.part + ((int64_t)blockIdx.z * gridDim.x + tile) * (BLOCK_M * BLOCK_N);
+          for (int f = et; f < BLOCK_M * kVecPerRow; f += kEpiThreads) {
+            const int rr = f / kVecPerRow, c4 = (f % kVecPerRow) * 4;
+            *reinterpret_cast<float4*>(dst + rr * BLOCK_N + c4) = *reinterpret_cast<const float4*>(sf + rr * kPitch + c4 * 4);
+          }
         } else {
         for (int f = et; f < rows_valid * kVecPerRow; f += kEpiThreads) {
           const int rr = f / kVecPerRow, c4 = (f % kVecPerRow) * 4;
@@ -335,7 +343,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         }
-        if (p.tile_counters != nullptr && gridDim.z > 1) {
+        if (p.tile_counters != nullptr && gridDim.z > 1 && p.part == nullptr) {
           // ---- fused finalize by the last-arriving CTA of this output tile (coalesced) ----
           uint32_t* s_last = tmem_slot + 1;
           __threadfence();
@@ -523,6 +531,7 @@ const char* launch_variant(const GemmArgs& g, cudaStream_t stream) {
   p.ldo = g.ldo;
   p.tile_counters = g.tile_counters;
   p.accumulate = g.accumulate_out ? 1 : 0;
+  p.part = nullptr;
   p.ship_flag = EPI == 0 ? reinterpret_cast<uint32_t*>(g.ship_flag) : nullptr;
   p.ship_seq_ptr = reinterpret_cast<const uint32_t*>(g.ship_seq_ptr);
   p.ship_seq_imm = g.ship_seq_imm;
@@ -530,12 +539,112 @@ const char* launch_variant(const GemmArgs& g, cudaStream_t stream) {
   const int tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M;
   const int tiles_n = (g.N + BLOCK_N - 1) / BLOCK_N;
   dim3 grid(tiles_m * tiles_n, 1, split);
+  const bool use_part = EPI == 1 && split > 1 && g.partials != nullptr && g.out_bf16 != nullptr && (g.N % 4) == 0 &&
+                        g.partials_elems >= (int64_t)split * grid.x * BLOCK_M * BLOCK_N;
+  if (use_part) p.part = g.partials;
   kern<<<grid, kGemmThreads, L::kTotal, stream>>>(tmA, tmB, tmD, p);
   cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cudaGetErrorString(e);
+  if (use_part) {
+    splitk_reduce(g.partials, split, (int)grid.x, tiles_n, BLOCK_M, BLOCK_N, 1, 0, g.M, g.N, g.out_bf16, g.ldo,
+                  g.accumulate_out, stream);
+    e = cudaGetLastError();
+  }
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
+// Sum of the split-K partial tiles -> bf16 output (+= when accumulating).  A CTA of 256 threads covers 64 consecutive
+// float4 of a tile row; its 4 thread groups each sum every 4th split (independent 16-byte loads, unrolled so that
+// several are in flight), a shared-memory pass adds the 4 partial sums.  The kernel is latency-bound by construction
+// (a few MB out of L2): the z-parallel layout keeps it at 2-4 us instead of split x load latency.
+constexpr int kRedVec = 64;     // float4 per CTA
+constexpr int kRedZ = 4;        // split groups per CTA
+
+__global__ void __launch_bounds__(kRedVec * kRedZ)
+splitk_reduce_kernel(const float* __restrict__ part, int split, int ctas, int tiles_n, int rows, int cols, int taps,
+                     int cin, int M, int N, __nv_bfloat16* __restrict__ out, long long ldo, int accumulate) {
+  __shared__ float4 sm[kRedZ][kRedVec];
+  const int vec_per_row = cols / 4;
+  const int64_t per_tile = (int64_t)rows * vec_per_row;
+  const int64_t total = (int64_t)ctas * per_tile;
+  const int64_t tile_elems = (int64_t)rows * cols;
+  const int64_t zstride = (int64_t)ctas * tile_elems;
+  const int vl = threadIdx.x % kRedVec, q = threadIdx.x / kRedVec;
+  for (int64_t base = (int64_t)blockIdx.x * kRedVec; base < total; base += (int64_t)gridDim.x * kRedVec) {
+    const int64_t i = base + vl;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool ok = i < total;
+    int m = 0, n = 0;
+    if (ok) {
+      const int t = (int)(i / per_tile);
+      const int rem = (int)(i - (int64_t)t * per_tile);
+      const int rr = rem / vec_per_row, c4 = (rem - rr * vec_per_row) * 4;
+      if (taps == 1) {
+        m = (t / tiles_n) * rows + rr;
+        n = (t % tiles_n) * cols + c4;
+      } else {
+        const int tile = t / 3, r = t - tile * 3, bn = cols / 3;
+        const int s = c4 / bn, cc = c4 - s * bn;
+        m = (tile / tiles_n) * rows + rr;
+        n = (r * 3 + s) * cin + (tile % tiles_n) * bn + cc;
+        ok = (tile % tiles_n) * bn + cc + 3 < cin;
+      }
+      ok = ok && m < M && n + 3 < N;
+      if (ok) {
+        const float* src = part + (int64_t)t * tile_elems + (int64_t)rr * cols + c4;
+        int z = q;
+        for (; z + 3 * kRedZ < split; z += 4 * kRedZ) {
+          const float4 a = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)z * zstride));
+          const float4 b = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)(z + kRedZ) * zstride));
+          const float4 c = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)(z + 2 * kRedZ) * zstride));
+          const float4 d = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)(z + 3 * kRedZ) * zstride));
+          acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+          acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+        }
+        for (; z < split; z += kRedZ) {
+          const float4 a = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)z * zstride));
+          acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        }
+      }
+    }
+    sm[q][vl] = acc;
+    __syncthreads();
+    if (q == 0 && ok) {
+#pragma unroll
+      for (int k = 1; k < kRedZ; ++k) {
+        const float4 o = sm[k][vl];
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+      }
+      __nv_bfloat16* o = out + (int64_t)m * ldo + n;
+      if (accumulate) {
+        const uint2 old = *reinterpret_cast<const uint2*>(o);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old.y));
+        acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
+      }
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y);
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(acc.z, acc.w);
+      uint2 packed;
+      packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+      packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(o) = packed;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
+
+void splitk_reduce(const float* partials, int split, int ctas, int tiles_n, int rows, int cols, int taps, int cin, int M,
+                   int N, void* out_bf16, int64_t ldo, bool accumulate, cudaStream_t stream) {
+  const int64_t total = (int64_t)ctas * rows * (cols / 4);
+  int blocks = (int)((total + kRedVec - 1) / kRedVec);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  if (blocks < 1) blocks = 1;
+  splitk_reduce_kernel<<<blocks, kRedVec * kRedZ, 0, stream>>>(partials, split, ctas, tiles_n, rows, cols, taps, cin, M, N,
+                                                  reinterpret_cast<__nv_bfloat16*>(out_bf16), (long long)ldo,
+                                                  accumulate ? 1 : 0);
+}
 
 const char* gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return "empty GEMM";

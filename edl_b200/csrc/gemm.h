@@ -40,6 +40,12 @@ struct GemmArgs {
   int64_t ldo = 0;
   int* tile_counters = nullptr;       // >= ceil(M/128)*ceil(N/BLOCK_N) zero-initialised ints
   bool accumulate_out = false;
+  // split-K WITHOUT atomics (preferred when given and large enough): every CTA stores its fp32 partial tile into
+  // partials[split][tile][128 x BLOCK_N] with plain coalesced stores and a second small kernel sums the splits into
+  // out_bf16.  fp32 reductions into L2 retire at ~12 requests/ns GPU-wide (profiles/prof_wgrad.ncu.txt: SMs active
+  // 36 % of the kernel, the rest is the reduction queue draining); plain stores do not queue.
+  float* partials = nullptr;
+  int64_t partials_elems = 0;
   int device = -1;                    // CUDA device ordinal of the operands (binds the context)
   // D = A*B + add_src (bf16 [M, N], row pitch ld_add): fuses the gradient accumulation of a tensor with two
   // consumers (residual branch + 1x1 conv) into the dgrad epilogue.  Persistent kernel only.
@@ -57,6 +63,12 @@ struct GemmArgs {
 
 // Returns nullptr on success, else a static error string.
 const char* gemm_bf16(const GemmArgs& args, cudaStream_t stream);
+
+// out[m0 + r][col(c)] (+)= sum over splits of partials[z][tile][r][c]; tiles are [rows x cols] fp32, tile t covers output
+// rows (t / tiles_n) * rows.. and -- taps == 1 -- columns (t % tiles_n) * cols..; taps == 3 (3x3 wgrad): t = tile * 3 + r,
+// column c of the tile is tap s = c / (cols / 3) of filter row r: output column (r * 3 + s) * cin + n0 + c % (cols / 3).
+void splitk_reduce(const float* partials, int split, int ctas, int tiles_n, int rows, int cols, int taps, int cin,
+                   int M, int N, void* out_bf16, int64_t ldo, bool accumulate, cudaStream_t stream);
 
 // 3x3 / stride 1 / pad 1 NHWC convolution as an implicit GEMM (conv3x3.cu): nine shifted TMA tile loads
 // per input-channel block (out-of-bounds rows/columns are zero-filled by the TMA unit = the padding)
@@ -91,12 +103,17 @@ struct Conv3x3WgradArgs {
   void* dW = nullptr;         // bf16 KRSC [Cout, 3, 3, Cin] (e.g. a window of the flat gradient bucket)
   float* ws = nullptr;        // fp32 [Cout * 9 * Cin] all-zero workspace (left all-zero)
   int* counters = nullptr;    // >= conv3x3_wgrad_tiles(Cin, Cout) zero ints (left zero)
-  int N = 0, H = 0, W = 0, Cin = 0, Cout = 0;
+  int N = 0, H = 0, W = 0, Cin = 0, Cout = 0;   // H, W: OUTPUT (= dY) size; the input is stride times as large
   int split_k = 1;
   bool accumulate = false;    // dW += result instead of dW = result
   int device = -1;
+  int stride = 1;             // 2: X is [N, 2H, 2W, Cin], read through the TMA traversal stride (version-1 kernel)
+  float* partials = nullptr;  // split-K without atomics (see GemmArgs::partials): [split][ctas][128 x 3*BLOCK_N]
+  int64_t partials_elems = 0;
 };
 bool conv3x3_wgrad_supported(int N, int H, int W, int Cin, int Cout);
+bool conv3x3_wgrad_s2_supported(int N, int Ho, int Wo, int Cin, int Cout);
+int conv3x3_wgrad_s2_kblocks(int N, int Ho, int Wo);
 int conv3x3_wgrad_tiles(int Cin, int Cout);
 int conv3x3_wgrad_ctas(int Cin, int Cout);        // (tile, filter row) CTAs per K split of the active kernel version
 void set_wgrad3_version(int version, int base_offset_mode);   // 1 = three X loads per block, 2 = one haloed X load (default)

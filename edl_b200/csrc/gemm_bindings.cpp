@@ -47,7 +47,8 @@ void gemm_bf16(const Tensor& A, const Tensor& B, const c10::optional<Tensor>& D,
                int64_t split_k, const c10::optional<Tensor>& out_bf16,
                const c10::optional<Tensor>& tile_counters, bool accumulate_out,
                const c10::optional<Tensor>& add_src,
-               const c10::optional<std::vector<c10::optional<Tensor>>>& bn, bool bn_relu) {
+               const c10::optional<std::vector<c10::optional<Tensor>>>& bn, bool bn_relu,
+               const c10::optional<Tensor>& partials) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.dim() == 2 && B.dim() == 2);
   TORCH_CHECK(A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16);
   TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1, "operands need a contiguous last dim");
@@ -101,6 +102,12 @@ void gemm_bf16(const Tensor& A, const Tensor& B, const c10::optional<Tensor>& D,
   if (bn.has_value()) {
     TORCH_CHECK(g.D != nullptr && g.ldd == g.N, "fused BN reduction needs a dense bf16 output");
     g.bn = parse_bn(bn, bn_relu, (int64_t)g.M * g.N, g.N);
+  }
+  if (partials.has_value() && partials->defined()) {
+    TORCH_CHECK(partials->scalar_type() == at::kFloat && partials->is_contiguous() &&
+                reinterpret_cast<uintptr_t>(partials->data_ptr()) % 16 == 0);
+    g.partials = partials->data_ptr<float>();
+    g.partials_elems = partials->numel();
   }
   g.device = A.device().index();
   c10::cuda::CUDAGuard guard(A.device());
@@ -215,7 +222,7 @@ bool conv3x3_supported(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cou
 // dW (+)= wgrad of the 3x3 / stride 1 / pad 1 conv.  x [N,Cin,H,W], dy [N,Cout,H,W] channels_last; dw KRSC
 // [Cout,3,3,Cin] bf16 contiguous; ws fp32 zeros (>= dw.numel()), counters int32 zeros.
 void conv3x3_wgrad(const Tensor& x, const Tensor& dy, Tensor& dw, Tensor& ws, Tensor& counters, int64_t split_k,
-                   bool accumulate) {
+                   bool accumulate, const c10::optional<Tensor>& partials) {
   TORCH_CHECK(x.is_cuda() && x.dim() == 4 && dy.dim() == 4 && dw.dim() == 4);
   TORCH_CHECK(x.scalar_type() == at::kBFloat16 && dy.scalar_type() == at::kBFloat16 && dw.scalar_type() == at::kBFloat16);
   TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast) && dy.is_contiguous(at::MemoryFormat::ChannelsLast),
@@ -228,17 +235,26 @@ void conv3x3_wgrad(const Tensor& x, const Tensor& dy, Tensor& dw, Tensor& ws, Te
   a.dW = dw.data_ptr();
   a.ws = ws.data_ptr<float>();
   a.N = x.size(0);
-  a.H = x.size(2);
-  a.W = x.size(3);
+  a.H = dy.size(2);
+  a.W = dy.size(3);
   a.Cin = x.size(1);
   a.Cout = dy.size(1);
-  TORCH_CHECK(dy.size(0) == a.N && dy.size(2) == a.H && dy.size(3) == a.W && dw.size(0) == a.Cout && dw.size(3) == a.Cin);
+  // stride 1: x and dy have the same size; stride 2: x is twice as large in both directions
+  a.stride = (x.size(2) == 2 * a.H && x.size(3) == 2 * a.W && a.H != x.size(2)) ? 2 : 1;
+  TORCH_CHECK(dy.size(0) == a.N && x.size(2) == a.stride * a.H && x.size(3) == a.stride * a.W &&
+              dw.size(0) == a.Cout && dw.size(3) == a.Cin, "conv3x3_wgrad: x / dy / dw shapes do not belong together");
   TORCH_CHECK(counters.scalar_type() == at::kInt && counters.is_contiguous() &&
               counters.numel() >= edl::conv3x3_wgrad_tiles(a.Cin, a.Cout));
   TORCH_CHECK(reinterpret_cast<uintptr_t>(a.dW) % 8 == 0, "dw window must be 8-byte aligned");
   a.counters = counters.data_ptr<int>();
   a.split_k = (int)split_k;
   a.accumulate = accumulate;
+  if (partials.has_value() && partials->defined()) {
+    TORCH_CHECK(partials->scalar_type() == at::kFloat && partials->is_contiguous() &&
+                reinterpret_cast<uintptr_t>(partials->data_ptr()) % 16 == 0);
+    a.partials = partials->data_ptr<float>();
+    a.partials_elems = partials->numel();
+  }
   a.device = x.device().index();
   c10::cuda::CUDAGuard guard(x.device());
   const char* err = edl::conv3x3_wgrad_bf16(a, at::cuda::getCurrentCUDAStream().stream());
@@ -288,6 +304,9 @@ std::vector<int64_t> conv3x3_wgrad_plan(int64_t n, int64_t h, int64_t w) {
 bool conv3x3_wgrad_supported(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cout) {
   return edl::conv3x3_wgrad_supported((int)n, (int)h, (int)w, (int)cin, (int)cout);
 }
+bool conv3x3_wgrad_s2_supported(int64_t n, int64_t ho, int64_t wo, int64_t cin, int64_t cout) {
+  return edl::conv3x3_wgrad_s2_supported((int)n, (int)ho, (int)wo, (int)cin, (int)cout);
+}
 
 // inference 3x3 conv (optionally grouped) with the folded-BN scale / shift / ReLU epilogue
 void conv3x3_infer(const Tensor& x, const Tensor& w, Tensor& y, const c10::optional<Tensor>& col_scale,
@@ -331,6 +350,8 @@ void register_gemm_bindings(pybind11::module_& m) {
   m.def("gemm_bf16_ship", &gemm_bf16_ship);
   m.def("conv3x3_wgrad", &conv3x3_wgrad);
   m.def("conv3x3_wgrad_supported", &conv3x3_wgrad_supported);
+  m.def("conv3x3_wgrad_s2_supported", &conv3x3_wgrad_s2_supported);
+  m.def("conv3x3_wgrad_s2_kblocks", &edl::conv3x3_wgrad_s2_kblocks);
   m.def("conv3x3_wgrad_tiles", &edl::conv3x3_wgrad_tiles);
   m.def("conv3x3_wgrad_kblocks", &edl::conv3x3_wgrad_kblocks);
   m.def("conv3x3_wgrad_ctas", &edl::conv3x3_wgrad_ctas);

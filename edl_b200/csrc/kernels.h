@@ -92,6 +92,7 @@ void maxpool3x3s2_bwd(const void* dy, const uint8_t* idx, void* dx, int N, int H
                       cudaStream_t s);
 void avgpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, cudaStream_t s);
 void avgpool2x2_bwd(const void* dy, void* dx, int N, int H, int W, int C, cudaStream_t s);
+void dilate2(const void* x, void* y, int N, int H, int W, int C, cudaStream_t s);   // zero-insertion by 2 (NHWC bf16)
 void gap_fwd(const void* x, void* y, int N, int HW, int C, cudaStream_t s);
 void gap_bwd(const void* dy, void* dx, int N, int HW, int C, cudaStream_t s);
 
@@ -126,6 +127,9 @@ void rope(const void* x, const float* cosv, const float* sinv, void* y, int64_t 
           bool inverse, cudaStream_t s);
 // ---- stem.cu: first stem convolution (3 -> 32, 3x3 / stride 2 / pad 1, NHWC bf16) + BN statistics of its output ----
 void stem_conv3x3s2(const void* x, const void* w, void* y, float* stats, int N, int H, int W, cudaStream_t s);
+// its weight gradient: dw KRSC [32,3,3,3] bf16 (+)= ; ws: >= 864 zero floats (left zero), counter: one zero int (left zero)
+const char* stem_wgrad(const void* x, const void* dy, float* ws, int* counter, void* dw, bool accumulate, int N, int H,
+                       int W, cudaStream_t s);
 
 void embedding_bag_fwd(const void* table, bool bf16, const int64_t* ids, void* out, int64_t B, int L,
                        int D, cudaStream_t s);

@@ -229,6 +229,31 @@ inline int grid_for(int64_t total) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// Zero-insertion ("dilate by 2"): out[n, 2h, 2w, :] = in[n, h, w, :], everything else 0.  The input gradient of a
+// stride-2 convolution is the stride-1 input gradient of its zero-inserted output gradient, so the stride-2 layers
+// reuse the tcgen05 stride-1 dgrad kernel (conv3x3.cu / gemm_persist.cu) instead of the library's strided dgrad.
+__global__ void __launch_bounds__(kThreads)
+dilate2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C) {
+  const int cv = C / 8;
+  const int64_t total = (int64_t)N * (2 * H) * (2 * W) * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    int64_t r = i / cv;
+    const int w2 = (int)(r % (2 * W));
+    r /= 2 * W;
+    const int h2 = (int)(r % (2 * H));
+    const int n = (int)(r / (2 * H));
+    bf16x8 v;
+    if (((h2 | w2) & 1) == 0) {
+      v = ld_stream(in + (((int64_t)n * H + (h2 >> 1)) * W + (w2 >> 1)) * C + c * 8);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v.v[k] = __floats2bfloat162_rn(0.f, 0.f);
+    }
+    st_vec(out + i * 8, v);
+  }
+}
+
 }  // namespace
 
 #define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
@@ -255,6 +280,9 @@ void avgpool2x2_bwd(const void* dy, void* dx, int N, int H, int W, int C, cudaSt
   int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   avgpool2x2_bwd_kernel<<<grid_for((int64_t)N * H * W * (C / 8)), kThreads, 0, s>>>(
       BF(dy), BFW(dx), N, H, W, C, Ho, Wo);
+}
+void dilate2(const void* x, void* y, int N, int H, int W, int C, cudaStream_t s) {
+  dilate2_kernel<<<grid_for((int64_t)N * 4 * H * W * (C / 8)), kThreads, 0, s>>>(BF(x), BFW(y), N, H, W, C);
 }
 void gap_fwd(const void* x, void* y, int N, int HW, int C, cudaStream_t s) {
   dim3 grid((C / 8 + 31) / 32, N);

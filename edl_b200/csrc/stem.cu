@@ -127,6 +127,85 @@ stem_conv3x3s2_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient of the same convolution:  dW[co][r][s][c] = sum over (n, ho, wo) of
+//     dY[n, ho, wo, co] * X[n, 2 ho + r - 1, 2 wo + s - 1, c]
+// (reference: conv2d_grad through cuDNN; round 1 of this repo used the library's wgrad on the side stream).  864
+// outputs, 347 M MACs at batch 32: CUDA cores.  One CTA of 4 warps walks output rows; warp w owns output channels
+// [8w, 8w + 8), LANE l < 27 owns tap l = (r, s, c) -- per output pixel a lane reads ITS input value (consecutive
+// lanes read consecutive floats of the staged input rows) and the warp's 8 dY values (one broadcast 16-byte read)
+// and does 8 FMAs.  Partials go to a tap-major fp32 workspace [27][32] with two 16-byte vector reductions per lane,
+// the last CTA converts to bf16 KRSC (+= the gradient bucket) and re-zeroes the workspace.
+constexpr int kWgThreads = 128;
+
+__global__ void __launch_bounds__(kWgThreads)
+stem_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ ws,
+                  int* __restrict__ counter, __nv_bfloat16* __restrict__ dw, int accumulate, int N, int H, int W,
+                  int Ho, int Wo) {
+  extern __shared__ __align__(16) uint8_t wg_smem[];
+  // xs[3][3 + 3 W + 3] floats: three input rows with one zero pixel on either side; dys[Wo][32] bf16
+  const int xrow = 3 * W + 6;
+  float* xs = reinterpret_cast<float*>(wg_smem);
+  __nv_bfloat16* dys = reinterpret_cast<__nv_bfloat16*>(wg_smem + ((3 * xrow * 4 + 15) / 16) * 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tap = lane < kTaps ? lane : 0;
+  const int r = tap / 9, sc = tap % 9;                 // sc = s * 3 + c
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int rows = N * Ho;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / Ho, ho = row - n * Ho;
+    __syncthreads();                                   // the previous row's tiles are no longer read
+    for (int i = threadIdx.x; i < 3 * xrow; i += kWgThreads) {
+      const int rr = i / xrow, j = i - rr * xrow;      // j = 3 + 3 * w + c  (w = -1 .. W)
+      const int h = 2 * ho + rr - 1;
+      const int wc = j - 3;
+      float v = 0.f;
+      if (h >= 0 && h < H && wc >= 0 && wc < 3 * W) v = __bfloat162float(x[((int64_t)n * H + h) * W * 3 + wc]);
+      xs[i] = v;
+    }
+    const int4* src = reinterpret_cast<const int4*>(dy + (int64_t)row * Wo * kCout);
+    int4* dst = reinterpret_cast<int4*>(dys);
+    for (int i = threadIdx.x; i < Wo * kCout / 8; i += kWgThreads) dst[i] = src[i];
+    __syncthreads();
+    const float* xr = xs + r * xrow + sc;              // + 6 * wo: input column 2 wo + s - 1, channel c
+    const __nv_bfloat16* dr = dys + warp * 8;
+#pragma unroll 4
+    for (int wo = 0; wo < Wo; ++wo) {
+      const float xv = xr[6 * wo];
+      float g[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dr + wo * kCout), g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(g[k], xv, acc[k]);
+    }
+  }
+  if (lane < kTaps) {
+    float* dst = ws + tap * kCout + warp * 8;
+    red_add_v4(dst, acc[0], acc[1], acc[2], acc[3]);
+    red_add_v4(dst + 4, acc[4], acc[5], acc[6], acc[7]);
+  }
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(counter, 1);
+    s_last = old == (int)gridDim.x - 1;
+    if (s_last) *counter = 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int i = threadIdx.x; i < kTaps * kCout; i += kWgThreads) {
+      const int t = i / kCout, co = i - t * kCout;
+      float v = __ldcg(ws + i);
+      ws[i] = 0.f;
+      __nv_bfloat16* o = dw + co * kTaps + t;          // KRSC: [co][(r*3+s)*3+c]
+      if (accumulate) v += __bfloat162float(*o);
+      *o = __float2bfloat16(v);
+    }
+  }
+}
+
 }  // namespace
 
 // x: bf16 NHWC [N, H, W, 3], w: bf16 KRSC [32, 3, 3, 3], y: bf16 NHWC [N, Ho, Wo, 32]; stats (optional): fp32 [64],
@@ -141,6 +220,27 @@ void stem_conv3x3s2(const void* x, const void* w, void* y, float* stats, int N, 
   stem_conv3x3s2_kernel<<<(int)blocks, kThreads, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(w),
       reinterpret_cast<__nv_bfloat16*>(y), stats, N, H, W, Ho, Wo);
+}
+
+const char* stem_wgrad(const void* x, const void* dy, float* ws, int* counter, void* dw, bool accumulate, int N, int H,
+                       int W, cudaStream_t stream) {
+  if ((H & 1) || (W & 1)) return "stem_wgrad: even input sizes only";
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t smem = ((3 * (3 * W + 6) * 4 + 15) / 16) * 16 + (size_t)Wo * kCout * 2;
+  if (smem > 200 * 1024) return "stem_wgrad: image too wide";
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    attr_set = true;
+  }
+  int grid = kNumSMs * 4;
+  if (grid > N * Ho) grid = N * Ho;
+  stem_wgrad_kernel<<<grid, kWgThreads, smem, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), ws, counter,
+      reinterpret_cast<__nv_bfloat16*>(dw), accumulate ? 1 : 0, N, H, W, Ho, Wo);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
 }  // namespace edl

@@ -16,7 +16,7 @@ _NUM_SMS = 148
 
 def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, col_scale=None, col_shift=None,
               relu=False, col_stats=None, out_f32=None, split_k=1, out_bf16=None, tile_counters=None,
-              accumulate_out=False, add=None, bn=None):
+              accumulate_out=False, add=None, bn=None, partials=None):
     """D = op(A) @ op(B): see csrc/gemm.h for the operand conventions.
 
     default        : A [M, K], B [N, K]  -> D [M, N] = A @ B^T
@@ -70,13 +70,15 @@ def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, col_scale=None
                                 and add.stride(0) % 8 == 0 and add.data_ptr() % 16 == 0 and out_f32 is None):
         # the fused addend lives in the persistent kernel's epilogue; otherwise one extra elementwise pass
         native().gemm_bf16(a, b, out, a_mn_major, b_mn_major, col_scale, col_shift, relu, col_stats,
-                           out_f32, int(split_k), out_bf16, tile_counters, bool(accumulate_out), None, None, False)
+                           out_f32, int(split_k), out_bf16, tile_counters, bool(accumulate_out), None, None, False,
+                           partials)
         count_launch()
         out.add_(add)
         return out
     bn_list, bn_relu = (bn.as_list(m, n), bn.relu) if bn is not None else (None, False)
     native().gemm_bf16(a, b, out, a_mn_major, b_mn_major, col_scale, col_shift, relu, col_stats,
-                       out_f32, int(split_k), out_bf16, tile_counters, bool(accumulate_out), add, bn_list, bn_relu)
+                       out_f32, int(split_k), out_bf16, tile_counters, bool(accumulate_out), add, bn_list, bn_relu,
+                       partials)
     count_launch()
     if bn is not None:
         bn.done = True
@@ -135,10 +137,35 @@ def _splitk_workspace(device, numel, tiles):
     return ws
 
 
+# TIMING EXPERIMENT ONLY (never set in a real run: the model does not learn): EDL_DEBUG_SKIP_WGRAD=1 drops every
+# weight-gradient kernel of the tcgen05 / library conv paths, which bounds what faster wgrad kernels could buy.
+_SKIP_WGRAD = __import__("os").environ.get("EDL_DEBUG_SKIP_WGRAD", "0") == "1"
+
+
+_PART = {}
+# split-K without atomics (csrc/gemm.h GemmArgs::partials): EDL_SPLITK_PARTIALS=0 goes back to fp32 reductions
+SPLITK_PARTIALS = __import__("os").environ.get("EDL_SPLITK_PARTIALS", "1") == "1"
+
+
+def _splitk_partials(device):
+    """Per (device, stream) scratch for the split-K partial tiles: 148-296 CTAs x (128 x 384) fp32 at most."""
+    if not SPLITK_PARTIALS:
+        return None
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _PART.get(key)
+    if buf is None:
+        buf = _PART[key] = torch.empty(16 << 20, device=device, dtype=torch.float32)      # 64 MB
+    return buf
+
+
 def _wgrad(dy2, x2, weight_shape, sink, ready):
     """dW[Cout, Cin] = dy2[M, Cout]^T @ x2[M, Cin]: fp32 split-K accumulation whose last CTA per
     tile converts to bf16 straight into the (flat gradient bucket) sink -- no memset / cast / add
     kernels around it."""
+    if _SKIP_WGRAD and sink is not None:
+        if ready is not None:
+            ready()
+        return None
     cout, cin = dy2.shape[1], x2.shape[1]
     split = _split_k_for(cout, cin, dy2.shape[0])
     side = _SIDE["stream"] if (dy2.is_cuda and sink is not None) else None
@@ -162,7 +189,8 @@ def _wgrad_impl(dy2, x2, weight_shape, sink, ready, cout, cin, split):
         else:
             out, acc = torch.empty((cout, cin), device=dy2.device, dtype=torch.bfloat16), False
         gemm_bf16(dy2, x2, a_mn_major=True, b_mn_major=True, out_f32=ws[:cout * cin].view(cout, cin),
-                  split_k=split, out_bf16=out, tile_counters=counters, accumulate_out=acc)
+                  split_k=split, out_bf16=out, tile_counters=counters, accumulate_out=acc,
+                  partials=_splitk_partials(dy2.device) if split > 1 else None)
         if sink is not None:
             if ready is not None:
                 ready()
@@ -344,6 +372,10 @@ class _ConvLibFn(torch.autograd.Function):
             side = _SIDE["stream"] if (dy.is_cuda and sink is not None) else None
 
             def wgrad():
+                if _SKIP_WGRAD and sink is not None:
+                    if ready is not None:
+                        ready()
+                    return None
                 gw = _ConvLibFn._bwd(dy, x, wv, ctx.cfg, [False, True, False])[1].permute(0, 2, 3, 1)
                 if sink is None:
                     return gw.contiguous()
@@ -431,6 +463,10 @@ class _Conv3x3Fn(torch.autograd.Function):
             own = OWN_WGRAD3 and conv3x3_wgrad_supported(x, w)
 
             def wgrad():
+                if _SKIP_WGRAD and sink is not None:
+                    if ready is not None:
+                        ready()
+                    return None
                 if own:
                     out = conv3x3_wgrad(x, dy, w.shape, sink)
                     if sink is None:
@@ -481,20 +517,25 @@ def conv3x3_wgrad(x, dy, weight_shape, sink=None, split_k: Optional[int] = None)
 
     x, dy = _cl(x), _cl(dy)
     cout, _, _, cin = weight_shape
-    n, _, h, w = x.shape
+    n, _, h, w = dy.shape                 # stride 2: x is twice as large; the pixel blocks tile dy
+    s2 = x.shape[2] != h
     tiles = native().conv3x3_wgrad_tiles(cin, cout)
     ws, counters = _splitk_workspace(x.device, cout * 9 * cin, tiles)
     if split_k is None:
-        kblocks = native().conv3x3_wgrad_kblocks(n, h, w)
-        ctas = native().conv3x3_wgrad_ctas(cin, cout)
+        if s2:                           # always the version-1 kernel (its pixel-block plan, 64-wide Cin tiles)
+            kblocks, ctas = native().conv3x3_wgrad_s2_kblocks(n, h, w), tiles
+        else:
+            kblocks = native().conv3x3_wgrad_kblocks(n, h, w)
+            ctas = native().conv3x3_wgrad_ctas(cin, cout)
         # one wave of CTAs, at least two pixel blocks per CTA (same rule as the 1x1 wgrad split)
         split_k = max(1, min(max(1, _NUM_SMS // ctas), max(1, kblocks // 2)))
     if sink is not None:
         out, acc = sink.view(weight_shape), True
     else:
         out, acc = torch.empty(tuple(weight_shape), device=x.device, dtype=torch.bfloat16), False
-    native().conv3x3_wgrad(x, dy, out, ws, counters, int(split_k), acc)
-    count_launch()
+    native().conv3x3_wgrad(x, dy, out, ws, counters, int(split_k), acc,
+                           _splitk_partials(x.device) if split_k > 1 else None)
+    count_launch(2 if (split_k > 1 and SPLITK_PARTIALS) else 1)
     return None if sink is not None else out
 
 
@@ -542,9 +583,35 @@ def conv3x3_s2_infer(x, weight_krsc, scale=None, shift=None, relu=False, groups=
     return _conv3x3_s2_launch(x, weight_krsc, None, scale, shift, relu, groups)
 
 
+# Backward of the stride-2 3x3 convolutions on our own kernels (EDL_OWN_S2_BWD=1; validated on B200, OFF by default:
+# the three layers cost 0.12 ms / step more than the library's strided kernels -- profiles/bench_runs.json "s2lib"):
+#   dgrad: zero-insert dy to the input resolution (csrc/pool.cu:dilate2_kernel) and run the stride-1 tcgen05 dgrad on it
+#          (the transposed stride-2 convolution IS that); 4x the MMAs of a native strided dgrad, but only 3 layers;
+#   wgrad: the version-1 weight-gradient kernel with X read through the TMA traversal stride (csrc/conv3x3_wgrad.cu).
+OWN_S2_BWD = __import__("os").environ.get("EDL_OWN_S2_BWD", "0") == "1"
+
+
+def _s2_dgrad_supported(x, w) -> bool:
+    from . import native
+
+    n, c, h, wd = x.shape
+    cout = w.shape[0]
+    return (OWN_S2_BWD and x.is_cuda and cout % 8 == 0 and h % 2 == 0 and wd % 2 == 0
+            and native().conv3x3_supported(n, h, wd, cout, c, True, 1))
+
+
+def _s2_wgrad_supported(x, w) -> bool:
+    from . import native
+
+    n, c, h, wd = x.shape
+    return (OWN_S2_BWD and x.is_cuda and h % 2 == 0 and wd % 2 == 0
+            and native().conv3x3_wgrad_s2_supported(n, h // 2, wd // 2, c, w.shape[0]))
+
+
 class _Conv3x3S2Fn(torch.autograd.Function):
-    """Training form: forward on the tcgen05 kernel (BN statistics in its epilogue); the backward of the three
-    stride-2 layers stays on the library kernels (dgrad on the critical path, wgrad on the side stream)."""
+    """Training form of the stride-2 3x3 convolution: forward on the tcgen05 kernel (BN statistics in its epilogue),
+    input gradient = stride-1 tcgen05 dgrad of the zero-inserted output gradient, weight gradient on the tcgen05
+    wgrad kernel through a strided tensor map (side stream, straight into the gradient bucket)."""
 
     @staticmethod
     def forward(ctx, x, w, stats, sink, ready):
@@ -557,8 +624,58 @@ class _Conv3x3S2Fn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        dx, dw = _ConvLibFn.backward(ctx, _cl(dy))[:2]
+        from . import native, count_launch
+
+        x, w = ctx.saved_tensors
+        dy = _cl(dy)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            if _s2_dgrad_supported(x, w):
+                n, cout, ho, wo = dy.shape
+                up = torch.empty((n, cout, 2 * ho, 2 * wo), device=dy.device, dtype=dy.dtype,
+                                 memory_format=torch.channels_last)
+                native().dilate2(dy, up)
+                dx = torch.empty_like(x)
+                native().conv3x3(up, w, dx, True, None, None, False)
+                count_launch(2)
+            else:
+                dx = _ConvLibFn._bwd(dy, x, w.permute(0, 3, 1, 2), ctx.cfg, [True, False, False])[0]
+        if ctx.needs_input_grad[1]:
+            if _s2_wgrad_supported(x, w):
+                sink, ready = ctx.sink, ctx.ready
+                side = _SIDE["stream"] if sink is not None else None
+
+                def wgrad():
+                    out = conv3x3_wgrad(x, dy, w.shape, sink)
+                    if sink is not None and ready is not None:
+                        ready()
+                    return out
+
+                if side is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(dy.device))
+                    side.wait_event(ev)
+                    _SIDE["keep"].append((dy, x))
+                    with torch.cuda.stream(side):
+                        dw = wgrad()
+                else:
+                    dw = wgrad()
+            else:
+                ctx2 = ctx
+                saved = ctx.needs_input_grad
+                dw = _ConvLibFn.backward(_NeedsOnlyWeight(ctx2, saved), dy)[1]
         return dx, dw, None, None, None
+
+
+class _NeedsOnlyWeight:
+    """View of an autograd ctx that asks _ConvLibFn.backward for the weight gradient only."""
+
+    def __init__(self, ctx, needs):
+        self._ctx = ctx
+        self.needs_input_grad = (False, needs[1]) + tuple(needs[2:])
+
+    def __getattr__(self, k):
+        return getattr(self._ctx, k)
 
 
 def conv3x3_s2(x, weight_krsc, stats: Optional[torch.Tensor] = None):
@@ -598,7 +715,45 @@ class _StemConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        dx, dw = _ConvLibFn.backward(ctx, _cl(dy))[:2]
+        from . import native, count_launch
+
+        x, w = ctx.saved_tensors
+        dy = _cl(dy)
+        dx = None
+        if ctx.needs_input_grad[0]:      # nobody asks for the gradient of the images; kept for completeness
+            dx = _ConvLibFn._bwd(dy, x, w.permute(0, 3, 1, 2), ctx.cfg, [True, False, False])[0]
+        dw = None
+        if ctx.needs_input_grad[1]:
+            if not (x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and x.shape[3] <= 4096):
+                dw = _ConvLibFn.backward(_NeedsOnlyWeight(ctx, ctx.needs_input_grad), dy)[1]
+                return dx, dw, None, None, None
+            sink, ready = ctx.sink, ctx.ready
+            side = _SIDE["stream"] if sink is not None else None
+
+            def wgrad():
+                if _SKIP_WGRAD and sink is not None:
+                    if ready is not None:
+                        ready()
+                    return None
+                ws, counters = _splitk_workspace(x.device, 1024, 1)
+                out = sink.view(w.shape) if sink is not None else torch.empty_like(w)
+                native().stem_wgrad(x, dy, out, ws, counters, sink is not None)
+                count_launch()
+                if sink is not None:
+                    if ready is not None:
+                        ready()
+                    return None
+                return out
+
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dy.device))
+                side.wait_event(ev)
+                _SIDE["keep"].append((dy, x))
+                with torch.cuda.stream(side):
+                    dw = wgrad()
+            else:
+                dw = wgrad()
         return dx, dw, None, None, None
 
 

@@ -133,6 +133,10 @@ class ElasticDataParallel:
         self.comm_blocks = comm_blocks
         self.algo_pref = os.environ.get("EDL_ALLREDUCE_ALGO", algo)
         self.timeout_s = timeout_s
+        # eager warm-up steps of a (re)built stage: ranks reach their first kernels seconds apart (cold caches, lazy
+        # module loading on a fresh joiner); those launches wait patiently, the captured steady-state step does not
+        self.warm_timeout_s = max(timeout_s, float(os.environ.get("EDL_COMM_WARM_TIMEOUT", "120")))
+        self.warming = False
         self.average = average
         self.device = next(module.parameters()).device
         self.pool = None
@@ -357,6 +361,9 @@ class ElasticDataParallel:
             self._launch(self.buckets[self._next])
             self._next += 1
 
+    def _timeout(self) -> float:
+        return self.warm_timeout_s if self.warming else self.timeout_s
+
     def _join_producers(self):
         """The bucket's gradients were written on the main stream (BN, pools, ...) and on the weight-gradient
         stream: whatever consumes them on the communication stream waits for both."""
@@ -415,12 +422,12 @@ class ElasticDataParallel:
                         [p + off for p in ps.data_ptrs], (ps.mc_ptr + off) if ps.mc_ptr else 0, self.rank,
                         g.master[lo:hi], st["mom"][lo:hi], st["wd_mask"][lo:hi] if st["wd_mask"] is not None else None,
                         opt.lr_t, scale, None, self.sqnorm, opt.found_inf_t, opt.momentum, opt.weight_decay,
-                        opt.nesterov, b.algo == "multimem", self.comm_blocks, self.timeout_s)
+                        opt.nesterov, b.algo == "multimem", self.comm_blocks, self._timeout())
                 else:
                     native().allreduce_twoshot(
                         [p + off for p in sl.data_ptrs], sl.sig_ptrs, (sl.mc_ptr + off) if sl.mc_ptr else 0,
                         self.rank, g.grad, b.numel, scale, self.found_inf, self.sqnorm,
-                        b.algo == "multimem", self.comm_blocks, self.timeout_s)
+                        b.algo == "multimem", self.comm_blocks, self._timeout())
             count_launch()
             self.comm_launches += 1
             self.last_algos.append((b.algo + ("+sgd" if b.fused_opt else ""), b.numel * esz, b.fused_opt))

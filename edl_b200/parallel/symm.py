@@ -141,7 +141,14 @@ class SymmetricPool:
 
     # ------------------------------------------------------------------ NVLS alias
     def _setup_multicast(self, root_name: str) -> int:
-        want = self._slab.mc_supported() and os.environ.get("EDL_DISABLE_MULTICAST", "0") != "1"
+        # In-place elastic mode keeps the NVLS alias OFF unless asked for (EDL_INPLACE_MULTICAST=1): when a member of
+        # a multicast team dies (SIGKILL), a surviving GPU that still issues multimem operations takes a CONTAINED
+        # NVLink error that poisons its CUDA context -- measured on 2 x B200, profiles/elastic_launch_gpu.json -- while
+        # plain peer loads / stores of the dead rank's (still referenced) memory merely make our barriers time out,
+        # which is the event hot recovery is built on.
+        inplace = os.environ.get("EDL_RESCALE_MODE", "").lower() == "inplace"
+        want = (self._slab.mc_supported() and os.environ.get("EDL_DISABLE_MULTICAST", "0") != "1"
+                and (not inplace or os.environ.get("EDL_INPLACE_MULTICAST", "0") == "1"))
         if not self._all_ok("mc_want", want):
             return 0
         ok = True

@@ -178,11 +178,15 @@ class StudentTrainer:
         # weight-gradient side stream (parallel/ddp.py) runs at low priority underneath it
         s = self._cap_stream
         s.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(s):
-            for _ in range(warmup):
-                self._step_body()
-        torch.cuda.current_stream(self.device).wait_stream(s)
-        torch.cuda.synchronize(self.device)
+        self.dp.warming = True                 # eager collectives of the warm-up wait patiently for slower ranks
+        try:
+            with torch.cuda.stream(s):
+                for _ in range(warmup):
+                    self._step_body()
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            torch.cuda.synchronize(self.device)
+        finally:
+            self.dp.warming = False
         self.dp.barrier()
         self.graph = torch.cuda.CUDAGraph()
         before = ops.launches()
@@ -190,6 +194,7 @@ class StudentTrainer:
             self._step_body()
         self.launches_per_step = ops.launches() - before
         torch.cuda.synchronize(self.device)
+        self.dp.barrier()                      # every rank replays its first step within milliseconds of the others
 
     def step_device(self):
         """Run one optimizer step on whatever is currently in the static input buffers."""

@@ -218,9 +218,10 @@ def main():
             meter = StepMeter(bs, world)
             print("rescaled in place: world %d -> %d, rank %d, pid %d, rendezvous %.2fs" % (
                 old_world, world, rank, os.getpid(), info.rendezvous_s), flush=True)
-            if it0 < (steps_per_epoch if not args.max_steps else min(steps_per_epoch, args.max_steps)):
-                continue                                        # finish this epoch with the new world
-            it0 = 0
+            # back to the top with the agreed cursor -- survivors AND joiners then run exactly the same code from
+            # here on (a switch that landed on the epoch boundary included: the step loop is empty, the forced poll,
+            # the checkpoint and the barrier below follow on every rank in the same order)
+            continue
         if etcd is not None and epoch >= args.epochs - 2 and env.pod_id:
             edl_train_status.save_to_etcd(etcd, env.pod_id, edl_train_status.TrainStatus.NEARTHEEND)   # no more scale-out
         tr.consolidate()                 # fused optimizer: every rank's slices of master / momentum -> complete state

@@ -158,6 +158,7 @@ def main():
         model, bs, image_shape=(c, h, w), num_classes=args.class_dim, lr=base_lr, momentum=args.momentum_rate,
         weight_decay=args.l2_decay, target_kind="probs" if soft else "labels",
         use_graph=cuda and not args.use_dgc and not args.use_recompute, dtype=dtype,
+        fabric=ctx.fabric if ctx is not None else None,
         bucket_cap_mb=args.fuse_mb if args.fuse else 1e9, algo=args.allreduce,
         loss_scaling=args.scale_loss if args.fp16 else None, dynamic_loss_scaling=args.use_dynamic_loss_scaling,
         optimizer=opt_factory,
@@ -172,6 +173,8 @@ def main():
             return cursor
         tr.sync_from(root)
         box = [cursor]
+        if ctx is not None:
+            return tuple(ctx.broadcast_object(cursor, root))
         dist.broadcast_object_list(box, src=root)
         return box[0]
 
@@ -250,13 +253,14 @@ def main():
             if hasattr(it, "close"):
                 it.close()                                      # stop the (distill) reader of the old shard
             try:
+                tr.prepare_rescale()                            # fused optimizer: sharded state made complete (old stage)
                 info = ctx.rescale()
             except elastic.EdlEvicted:
                 print("rank %d: pod left the job (scale-in); exiting" % rank, flush=True)
                 break
             old_world, world, rank = world, info.size, info.rank
             shard.update(rank=rank, world=world)
-            tr.rebuild(None)
+            tr.rebuild(None, fabric=ctx.fabric)
             epoch, step = take_cursor_from(info.root, (epoch, step))
             base_lr = scaled_lr(args.lr, bs, world)
             steps_per_epoch = max(1, args.total_images // (bs * world))
@@ -268,10 +272,13 @@ def main():
                              for _, b in zip(range(8), val))
             if rank == 0:
                 print("Pass %d test acc1 %.4f acc5 %.4f (n=%d)" % (epoch, ev["acc1"], ev["acc5"], ev["n"]), flush=True)
+        tr.consolidate()                 # fused optimizer: every rank's slices of master / momentum -> complete state
         if rank == 0:
             save_check_point(args.checkpoint, tr.state_dict(), TrainStatus(epoch, step), fs, trainer_id=0,
                              state_json=json.dumps({"world": world, "lr": base_lr}))
-        if world > 1:
+        if ctx is not None:
+            ctx.barrier()
+        elif world > 1:
             dist.barrier()
         epoch += 1
     if dr is not None:

@@ -98,6 +98,7 @@ def main():
             if it % args.fetch_steps == 0 and rank == 0:
                 print("Pass %d, batch %d, loss %.5f, speed %.1f img/s" % (
                     epoch, it, float(loss), (it + 1) * B * n_students / max(1e-6, time.time() - t0)), flush=True)
+        tr.consolidate()                 # student ranks: sharded optimizer state -> complete (collective of the students)
         if rank == 0 and epoch >= ts.next():
             save_check_point(args.checkpoint, tr.state_dict(), TrainStatus(epoch, step), fs, trainer_id=0)
     assert link.check_error() == 0, "the NVSwitch link reported a timeout"

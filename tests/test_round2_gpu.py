@@ -313,18 +313,29 @@ def test_conv3x3_stride2_fprop(n, cin, cout, h, w, groups):
     want = torch.relu(ref * scale[None, :, None, None] + shift[None, :, None, None])
     assert y.shape == want.shape and _rel(y, want) < 1e-2
     if groups == 1:
-        stats = torch.zeros(2 * cout, device=DEV)
-        xg = x.clone().requires_grad_(True)
-        wg = wt.clone().requires_grad_(True)
-        yt = ops.conv3x3_s2(xg, wg, stats)
-        assert _rel(yt, ref) < 1e-2
-        assert _rel(stats[:cout], yt.float().sum((0, 2, 3))) < 2e-3
-        dy = torch.randn_like(yt)
-        yt.backward(dy)
-        xr = x.float().requires_grad_(True)
-        wr = wt.float().requires_grad_(True)
-        F.conv2d(xr, wr.permute(0, 3, 1, 2), None, 2, 1).backward(dy.float())
-        assert _rel(xg.grad, xr.grad) < 1e-2 and _rel(wg.grad, wr.grad) < 1e-2
+        from edl_b200.ops import gemm as G
+
+        # backward twice: library kernels (the default) and our own path (EDL_OWN_S2_BWD=1: zero-insertion + stride-1
+        # tcgen05 dgrad, wgrad through the TMA traversal stride)
+        for own in (False, True):
+            prev, G.OWN_S2_BWD = G.OWN_S2_BWD, own
+            try:
+                stats = torch.zeros(2 * cout, device=DEV)
+                xg = x.clone().requires_grad_(True)
+                wg = wt.clone().requires_grad_(True)
+                yt = ops.conv3x3_s2(xg, wg, stats)
+                assert _rel(yt, ref) < 1e-2
+                assert _rel(stats[:cout], yt.float().sum((0, 2, 3))) < 2e-3
+                dy = torch.randn_like(yt)
+                ops.reset_fallbacks()
+                yt.backward(dy)
+                assert bool(ops.fallbacks()) != own or not (G._s2_dgrad_supported(x, wt) and G._s2_wgrad_supported(x, wt))
+                xr = x.float().requires_grad_(True)
+                wr = wt.float().requires_grad_(True)
+                F.conv2d(xr, wr.permute(0, 3, 1, 2), None, 2, 1).backward(dy.float())
+                assert _rel(xg.grad, xr.grad) < 1e-2 and _rel(wg.grad, wr.grad) < 1e-2, own
+            finally:
+                G.OWN_S2_BWD = prev
 
 
 @pytest.fixture
@@ -430,7 +441,7 @@ def test_fused_bn_backward_matches_unfused_at_model_level(monkeypatch, mode):
         l1, n1, g1 = grads(True)
     finally:
         C.set_bnr_mode(prev_mode)
-    assert abs(l0 - l1) < max(1e-3, 4 * abs(l0 - l0b)), (l0, l0b, l1)
+    assert abs(l0 - l1) < max(1e-2, 4 * abs(l0 - l0b)), (l0, l0b, l1)
     assert n1 < n0 - 20, "the fused path should launch ~40 kernels fewer (%d vs %d)" % (n1, n0)
     noise = {k: _rel(g0b[k], g0[k]) for k in g0}
     bad = sorted(((_rel(g1[k], g0[k]), noise[k], k) for k in g0 if _rel(g1[k], g0[k]) > max(3e-2, 4 * noise[k])),
