@@ -95,9 +95,13 @@ def plan_buckets(flat: FlatParams, cap_bytes: int) -> List[Bucket]:
                 cur = None
         if cur is not None:
             buckets.append(cur)
-        # the tail padding of the group rides with the last bucket so the buffer is fully covered
-        last = [b for b in buckets if b.dtype == g.dtype][-1]
-        last.numel = g.numel - last.start
+        # every bucket runs up to the start of the next one (entries start on 128-element boundaries, the alignment
+        # gap behind a bucket's last tensor rides with it: kernels want multiples of 16 bytes), and the tail padding
+        # of the group rides with the last bucket so the buffer is fully covered
+        mine = sorted((b for b in buckets if b.dtype == g.dtype), key=lambda b: b.start)
+        for b, nxt in zip(mine, mine[1:]):
+            b.numel = nxt.start - b.start
+        mine[-1].numel = g.numel - mine[-1].start
     buckets.sort(key=lambda b: b.order)
     return buckets
 

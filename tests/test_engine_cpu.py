@@ -360,3 +360,21 @@ def test_hierarchical_allreduce_matches_the_flat_one():
         assert spread == 0.0                     # every rank holds identical parameters
         results.append(flat)
     assert torch.allclose(results[0], results[1], rtol=1e-9, atol=1e-12)
+
+
+def test_buckets_tile_the_flat_buffer_in_16_byte_multiples():
+    """Entries start on 128-element boundaries; the alignment gap behind a bucket's last tensor belongs to that
+    bucket (the two-shot kernels want multiples of 16 bytes -- a DeepFM table with an odd row count broke that)."""
+    from edl_b200.parallel.ddp import plan_buckets
+    from edl_b200.parallel.flat import FlatParams
+
+    m = torch.nn.Sequential(torch.nn.Linear(13, 7), torch.nn.Linear(7, 5), torch.nn.Embedding(1001, 3), torch.nn.Linear(5, 3))
+    flat = FlatParams(m)
+    for cap in (64, 4096, 1 << 20):
+        buckets = plan_buckets(flat, cap)
+        for g in flat.groups.values():
+            mine = sorted((b for b in buckets if b.dtype == g.dtype), key=lambda b: b.start)
+            assert mine[0].start == 0 and sum(b.numel for b in mine) == g.numel
+            assert all(b.numel % 8 == 0 and b.start % 8 == 0 for b in mine)
+            for b, nxt in zip(mine, mine[1:]):
+                assert b.start + b.numel == nxt.start

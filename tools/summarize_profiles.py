@@ -105,16 +105,32 @@ def main():
         bench = json.load(open(bench_path))
     except (OSError, ValueError):
         bench = {}
-    for f in sorted(glob.glob(os.path.join(SRC, "bench*.json")) + glob.glob(os.path.join(SRC, "ab_*.json"))):
+    pats = ("bench*.json", "ab_*.json", "ab2_*.json", "b4_*.json", "b6_*.json", "b7_*.json", "b8_*.json", "b9_*.json",
+            "b10_*.json", "b1[1-9]_*.json")
+    for f in sorted(x for p_ in pats for x in glob.glob(os.path.join(SRC, p_))):
         try:
             line = [l for l in open(f).read().splitlines() if l.startswith("{")][-1]
             d = json.loads(line)
             bench[os.path.basename(f)[:-5]] = {k: d.get(k) for k in ("impl", "n_gpus", "value", "unit", "ms_per_step", "gpu_launches", "clocks")}
             bench[os.path.basename(f)[:-5]]["e2e"] = (d.get("e2e") or {}).get("value")
-            bench[os.path.basename(f)[:-5]]["config"] = {k: (d.get("config") or {}).get(k) for k in ("model", "batch_per_gpu", "cuda_graph", "conv_impl", "allreduce", "parallelism")}
+            bench[os.path.basename(f)[:-5]]["config"] = {k: (d.get("config") or {}).get(k) for k in ("model", "batch_per_gpu", "cuda_graph", "conv_impl", "allreduce", "parallelism", "own_wgrad3", "fuse_bn_bwd", "conv3_s2", "own_stem1")}
+            for extra in ("exposed_comm_ms", "library_fallbacks"):
+                if d.get(extra) is not None:
+                    bench[os.path.basename(f)[:-5]][extra] = d[extra]
+            for extra in ("rescale", "distill", "allreduce", "exposed_comm"):        # multi-GPU metric terms (bench.py extras)
+                if isinstance(d.get(extra), dict):
+                    v = dict(d[extra])
+                    v.pop("buckets", None)
+                    bench[os.path.basename(f)[:-5]][extra] = v
         except Exception:
             pass
     json.dump(bench, open(bench_path, "w"), indent=1)
+    # round 2: multi-GPU sweeps, elastic-launch recovery times, timelines, A/B summaries
+    for pat, dst in (("comm_*gpu.json", None), ("rescale_*gpu.json", None), ("elastic_launch_*gpu*.json", None),
+                     ("ctr_sweep_*gpu.json", None), ("ctr_deepfm_*gpu.json", None), ("prof_allreduce_*gpu.jsonl", None),
+                     ("timeline_r2*.txt", None), ("call*_summary.txt", None), ("wgrad3.json", "wgrad3_microbench.json")):
+        for f in sorted(glob.glob(os.path.join(SRC, pat))):
+            open(os.path.join(OUT, dst or os.path.basename(f)), "w").write(open(f).read())
     for name in ("experimental_summary.txt", "loader_bench.jsonl"):       # scripts/gpu_validate_experimental.sh
         src = os.path.join(SRC, name)
         if os.path.exists(src):
