@@ -79,6 +79,7 @@ def main():
     ap.add_argument("--model", default="ctr_dnn", choices=["ctr_dnn", "deepfm"])
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--out", default="")
+    ap.add_argument("--save", default="", help="rank 0 writes the trained model's state dict here (input of dumper.py)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -120,6 +121,9 @@ def main():
         result["grad_bytes_per_step"] = sum(g.grad.numel() * g.grad.element_size() for g in dp.flat.groups.values())
         if rank == 0:
             print(json.dumps(result))
+            if args.save:
+                os.makedirs(os.path.dirname(os.path.abspath(args.save)), exist_ok=True)
+                torch.save({"model": {k: v.detach().cpu() for k, v in model.state_dict().items()}}, args.save)
     if args.out and rank == 0:
         json.dump(result, open(args.out, "w"), indent=1)
     if world > 1:

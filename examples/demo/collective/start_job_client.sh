@@ -4,4 +4,4 @@
 set -eu
 source "$(dirname "$0")/env.sh"
 python -m paddle_edl.demo.collective.job_client_demo --pod_path "$(dirname "$0")/resnet50/pod.sh" \
-  --nodes_range "${PADDLE_EDLNODES_RANAGE}"
+  --package_sh "$(dirname "$0")/resnet50/package.sh" --nodes_range "${PADDLE_EDLNODES_RANAGE}"

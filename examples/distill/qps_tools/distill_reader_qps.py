@@ -21,6 +21,9 @@ def main():
     ap.add_argument("--teachers", default="127.0.0.1:9292")
     ap.add_argument("--nop", action="store_true", help="use the NOP teacher (measures the pipeline only)")
     ap.add_argument("--samples", type=int, default=2048)
+    ap.add_argument("--teacher_bs", type=int, default=0, help="one teacher batch size (run.sh sweeps it); 0 = sweep 1..32 here")
+    ap.add_argument("--conf_file", default="", help="serving conf (feeds / fetches): parse_config.get_ins_predicts")
+    ap.add_argument("--out", default="", help="append one JSON line per measurement")
     ap.add_argument("--image_size", type=int, default=224)
     args = ap.parse_args()
     distill_worker._NOP_PREDICT_TEST = args.nop
@@ -30,15 +33,26 @@ def main():
         for i in range(0, args.samples, 32):
             yield [(img, np.array([j], dtype="int64")) for j in range(32)]
 
-    for tbs in (1, 2, 4, 8, 16, 32):
-        dr = DistillReader(ins=["image", "label"], predicts=["score"])
+    ins, predicts = ["image", "label"], ["score"]
+    if args.conf_file:
+        from parse_config import get_ins_predicts
+        feeds, _, _, predicts = get_ins_predicts(args.conf_file)
+        ins = feeds + [n for n in ("label",) if n not in feeds]
+    for tbs in ((args.teacher_bs,) if args.teacher_bs else (1, 2, 4, 8, 16, 32)):
+        dr = DistillReader(ins=ins, predicts=predicts)
         dr.set_teacher_batch_size(tbs)
         dr.set_fixed_teacher(args.teachers)
         r = dr.set_sample_list_generator(gen)
         t0, n = time.time(), 0
         for batch in r():
             n += len(batch)
-        print("teacher_batch_size %2d: %8.1f samples/s" % (tbs, n / (time.time() - t0)), flush=True)
+        qps = n / (time.time() - t0)
+        print("teacher_batch_size %2d: %8.1f samples/s" % (tbs, qps), flush=True)
+        if args.out:
+            import json
+            with open(args.out, "a") as fh:
+                fh.write(json.dumps({"teacher_batch_size": tbs, "samples_per_s": qps, "nop": bool(args.nop),
+                                     "teachers": args.teachers, "samples": n}) + "\n")
         dr.stop()
 
 
