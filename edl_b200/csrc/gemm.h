@@ -128,6 +128,7 @@ void set_bnr_mode(int mode);   // fused BN-backward reduction: 1 = shuffle trans
 int get_bnr_mode();
 void set_persistent_gemm(bool on);
 bool persistent_gemm_enabled();
+void set_wide_gemm_tiles(bool on);   // 128 x 256 tiles for large-N inference GEMMs (default on; EDL_GEMM_WIDE=0)
 const char* gemm_bf16_persistent(const GemmArgs& args, cudaStream_t stream);
 const char* conv3x3_bf16_persistent(const Conv3x3Args& args, int BH, int BN, int tiles_h, int tiles_img,
                                     cudaStream_t stream);

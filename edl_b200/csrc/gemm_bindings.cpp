@@ -355,6 +355,7 @@ void register_gemm_bindings(pybind11::module_& m) {
   m.def("conv3x3_wgrad_tiles", &edl::conv3x3_wgrad_tiles);
   m.def("conv3x3_wgrad_kblocks", &edl::conv3x3_wgrad_kblocks);
   m.def("conv3x3_wgrad_ctas", &edl::conv3x3_wgrad_ctas);
+  m.def("set_wide_gemm_tiles", &edl::set_wide_gemm_tiles);
   m.def("set_wgrad3_version", &edl::set_wgrad3_version);
   m.def("get_wgrad3_version", &edl::get_wgrad3_version);
   m.def("conv3x3_wgrad_plan", &conv3x3_wgrad_plan);

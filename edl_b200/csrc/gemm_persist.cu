@@ -162,7 +162,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
-  constexpr uint32_t kTmemCols = 2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : 256));
+  constexpr uint32_t kTmemCols =
+      2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+  static_assert(2 * BLOCK_N <= 512, "two accumulators must fit the 512 TMEM columns");
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -653,6 +655,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 bool g_persistent = true;
+bool g_wide_tiles = [] {
+  const char* e = getenv("EDL_GEMM_WIDE");
+  return !(e != nullptr && e[0] == '0');
+}();
 // fused BatchNorm-backward reduction in the dgrad epilogue: 2 (default) = column-pair loop over the staged tiles,
 // 1 = the round-1 in-register shuffle transpose (epilogue-bound; EDL_BNR_MODE=1 keeps it selectable for A/B)
 int g_bnr_mode = [] {
@@ -706,13 +712,21 @@ void fill_bn(PersistParams& p, const BnBwdFuse& bn) {
 void set_bnr_mode(int mode) { g_bnr_mode = mode == 2 ? 2 : 1; }
 int get_bnr_mode() { return g_bnr_mode; }
 void set_persistent_gemm(bool on) { g_persistent = on; }
+void set_wide_gemm_tiles(bool on) { g_wide_tiles = on; }
 bool persistent_gemm_enabled() { return g_persistent; }
 
 // GEMM front end (EPI 0 semantics of gemm.cu; A K-major)
 const char* gemm_bf16_persistent(const GemmArgs& g, cudaStream_t stream) {
   alignas(64) CUtensorMap tmA, tmB, tmD;
   const bool n64 = g.N <= 64;
-  const int bn = n64 ? 64 : 128;
+  // 128 x 256 tiles for the compute-heavy GEMMs (the teacher's 1x1 convolutions: N = 512 .. 4096, K = 256 .. 4096):
+  // a 128 x 128 tile needs 32 KB of operands per 256 tensor-core cycles = 128 B / clk / SM, about twice what the
+  // L2 -> SM path delivers when every SM pulls (profiles/teacher_r1.txt: 35-40 % of the bf16 peak); with N = 256 the
+  // A tile is reused twice as often and the requirement drops to 96 B / clk.  Both accumulators then fill the TMEM.
+  const bool wide = g_wide_tiles && !g.b_mn_major && g.bn.x == nullptr && g.col_stats == nullptr && g.N % 256 == 0 &&
+                    g.K >= 256 &&
+                    (int64_t)((g.M + kBlockM - 1) / kBlockM) * (g.N / 256) >= kNumSMs;
+  const int bn = n64 ? 64 : (wide ? 256 : 128);
   if (const char* e = tmap2d(&tmA, g.A, g.K, g.M, g.lda, kBlockK, kBlockM)) return e;
   if (!g.b_mn_major) {
     if (const char* e = tmap2d(&tmB, g.B, g.K, g.N, g.ldb, kBlockK, bn)) return e;
@@ -752,8 +766,10 @@ const char* gemm_bf16_persistent(const GemmArgs& g, cudaStream_t stream) {
     return n64 ? launch_p<64, 4, 1, 1>(tmA, tmB, tmD, p, stream, padd, &tmBx, has_y ? &tmBy : nullptr)
                : launch_p<128, 3, 1, 1>(tmA, tmB, tmD, p, stream, padd, &tmBx, has_y ? &tmBy : nullptr);
   }
-  if (!g.b_mn_major)
+  if (!g.b_mn_major) {
+    if (wide) return launch_p<256, 3, 0>(tmA, tmB, tmD, p, stream, padd);
     return n64 ? launch_p<64, 6, 0>(tmA, tmB, tmD, p, stream, padd) : launch_p<128, 5, 0>(tmA, tmB, tmD, p, stream, padd);
+  }
   return n64 ? launch_p<64, 6, 1>(tmA, tmB, tmD, p, stream, padd) : launch_p<128, 5, 1>(tmA, tmB, tmD, p, stream, padd);
 }
 

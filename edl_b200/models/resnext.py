@@ -57,6 +57,26 @@ class FoldedConv(nn.Module):
                 and residual.data_ptr() % 16 == 0)
 
     # ---- fp8 (e4m3) mode of the 1x1 convolutions: see ops/fp8.py -------------------------------
+    def _widened_groups(self):
+        """(weight [Cout, 3, 3, 64], groups) with neighbouring groups merged into 64-input-channel block-diagonal
+        groups, or None when the layer does not need it (>= 64 channels per group) or does not fit the scheme."""
+        cout, kh, kw, cin_g = self.weight.shape
+        if cin_g >= 64 or 64 % cin_g != 0 or self.groups % (64 // cin_g) != 0:
+            return None
+        cached = getattr(self, "_w64", None)
+        if cached is not None and cached[0].device == self.weight.device and cached[2] == self.weight._version:
+            return cached[0], cached[1]
+        merge = 64 // cin_g                       # original groups per widened group
+        cout_g = cout // self.groups
+        w = self.weight.detach()
+        w64 = torch.zeros((cout, kh, kw, 64), dtype=w.dtype, device=w.device)
+        sub = (torch.arange(cout, device=w.device) // cout_g) % merge        # position of o's group inside its block
+        for j in range(merge):
+            rows = (sub == j).nonzero().flatten()
+            w64[rows, :, :, j * cin_g:(j + 1) * cin_g] = w[rows]
+        self._w64 = (w64.contiguous(), self.groups // merge, self.weight._version)
+        return self._w64[0], self._w64[1]
+
     def fp8_eligible(self):
         return self.k == 1 and self.groups == 1 and self.cin % 16 == 0 and self.cout % 8 == 0
 
@@ -112,6 +132,21 @@ class FoldedConv(nn.Module):
                 return y
             ops.gemm_bf16(x2, self.weight.view(self.cout, self.cin), out=y2)
             return ops.scale_shift_act(y, self.scale, self.shift, residual, self.relu)
+        if self.k == 3 and residual is None and self.own_conv3 and self.groups > 1 and x.is_cuda:
+            wide = self._widened_groups()
+            if wide is not None:
+                # 16 / 32 channels per group (ResNeXt101_32x16d stages 1-2): four / two neighbouring groups share one
+                # 64-channel block-diagonal group, so the 64-wide k-blocks of the tcgen05 kernel apply (zeros in the
+                # off-diagonal blocks: 4x / 2x the MMAs of layers that are memory-bound anyway; the library's grouped
+                # kernels took 73-160 us per layer, profiles/teacher_r1.txt)
+                w64, g64 = wide
+                if self.stride == 2 and ops.gemm.CONV3_S2 and ops.conv3x3_s2_supported(x, w64, g64):
+                    return ops.conv3x3_s2_infer(x, w64, self.scale, self.shift, self.relu, g64)
+                if self.stride in (1, 2) and ops.conv3x3_infer_supported(x, w64, g64):
+                    y = ops.conv3x3_infer(x, w64, self.scale, self.shift, self.relu, g64)
+                    if self.stride == 2:
+                        y = y[:, :, ::2, ::2].contiguous(memory_format=torch.channels_last)
+                    return y
         if (self.k == 3 and residual is None and self.own_conv3 and self.stride == 2 and ops.gemm.CONV3_S2
                 and ops.conv3x3_s2_supported(x, self.weight, self.groups)):
             # experimental (EDL_CONV3_S2=1): true stride-2 kernel, a quarter of the MMAs of the path below

@@ -82,6 +82,9 @@ def parse():
       "paddle_edl.utils.image_pipeline) or a directory of .pt shards {'images': uint8 NHWC, 'labels': int64}; synthetic if unset")
     a("--max_steps", type=int, default=0)
     a("--width_mult", type=float, default=1.0)
+    a("--solo_step_sleep", type=float, default=0.0,
+      help="elastic demos / tests: seconds to sleep per step while the job has ONE trainer, so that a second pod has "
+           "time to join whatever the speed of the box")
     return ap.parse_args()
 
 
@@ -244,6 +247,8 @@ def main():
             prof.step()
             step += 1
             seen += bs
+            if args.solo_step_sleep and world == 1:
+                time.sleep(args.solo_step_sleep)
             if bi % args.fetch_steps == 0 and rank == 0:
                 print("Pass %d, batch %d, loss %.5f, lr %.5f, speed %.1f img/s" % (
                     epoch, bi, float(loss), lr, seen * world / max(1e-6, time.time() - t0)), flush=True)

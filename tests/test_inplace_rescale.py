@@ -394,3 +394,58 @@ def test_restart_mode_survives_a_hard_pod_death(kv_server, tmp_path):
         for p in (a, b):
             if p is not None and p.poll() is None:
                 os.killpg(os.getpgid(p.pid), 9)
+
+
+@pytest.mark.slow
+def test_distill_example_rescales_in_place_with_a_live_teacher(kv_server, tmp_path):
+    """The elastic DISTILL example end to end (examples/distill/resnet/train.py, the reference's
+    example/distill/resnet/train_with_fleet.py under the launcher): students pull soft labels from a teacher server
+    through the DistillReader, pod B joins in place while pod A trains, both finish the job."""
+    from edl_b200.distill.teacher_server import TeacherServer
+    from edl_b200.models.teacher_zoo import build
+
+    job = "inplace_distill_" + uuid.uuid4().hex[:6]
+    ckpt = str(tmp_path / "ckpt")
+    script = os.path.join(ROOT, "examples", "distill", "resnet", "train.py")
+    model, feeds, fetches, shapes = build("resnext_tiny")
+    srv = TeacherServer(model, feeds, fetches, shapes).start()
+
+    def launch(name):
+        env = dict(os.environ)
+        env.update({"PYTHONPATH": ROOT, "CUDA_VISIBLE_DEVICES": "", "PADDLE_RUNNING_PLATFORM": "", "EDL_POD_IP": "127.0.0.1",
+                    "EDL_INPLACE_CHECK_EVERY": "4", "EDL_INPLACE_ACK_TIMEOUT": "60", "OMP_NUM_THREADS": "2"})
+        cmd = [sys.executable, "-u", "-m", "edl_b200.collective.launch", "--nodes_range", "1:2", "--nproc_per_node", "1",
+               "--etcd_endpoints", kv_server.endpoint, "--job_id", job, "--log_dir", str(tmp_path / ("log" + name)),
+               "--hdfs_path", ckpt, "--rescale_mode", "inplace", script, "--model", "ResNet18_vd", "--width_mult", "0.125",
+               "--image_shape", "3,64,64", "--class_dim", "16", "--batch_size", "4", "--total_images", "960",
+               "--num_epochs", "2", "--use_distill_service", "1", "--distill_teachers", srv.endpoint,
+               "--teacher_batch_size", "4", "--fetch_steps", "5", "--solo_step_sleep", "0.4", "--checkpoint", ckpt]
+        return subprocess.Popen(cmd, env=env, stdout=open(str(tmp_path / (name + ".launcher.log")), "w"),
+                                stderr=subprocess.STDOUT, start_new_session=True)
+
+    def worker_log(name):
+        p = tmp_path / ("log" + name) / "workerlog.0"
+        return p.read_text() if p.exists() else ""
+
+    a = launch("A")
+    b = None
+    try:
+        deadline = time.time() + 180
+        while "batch 10," not in worker_log("A"):
+            assert time.time() < deadline and a.poll() is None, worker_log("A")[-2000:]
+            time.sleep(0.2)
+        b = launch("B")
+        assert a.wait(timeout=500) == 0, worker_log("A")[-3000:]
+        assert b.wait(timeout=120) == 0, worker_log("B")[-3000:]
+        la, lb = worker_log("A"), worker_log("B")
+        assert "rescaled in place: world 1 -> 2" in la, la[-3000:]
+        assert "Traceback" not in la and "Traceback" not in lb
+        etcd = EtcdClient([kv_server.endpoint], root=job)
+        etcd.init()
+        assert edl_status.load_job_status_from_etcd(etcd) == edl_status.Status.SUCCEED
+        etcd.close()
+    finally:
+        srv.stop()
+        for p in (a, b):
+            if p is not None and p.poll() is None:
+                os.killpg(os.getpgid(p.pid), 9)

@@ -41,6 +41,29 @@ def test_persistent_gemm_matches_reference_and_stats(m, n, k, b_mn):
     assert torch.equal(outs[0], outs[1])          # same MMA order => bit-identical results
 
 
+@pytest.mark.parametrize("m,n,k,res", [(25088, 512, 512, False), (6272, 2048, 1024, True), (100352, 512, 256, True),
+                                       (1568, 4096, 2048, False)])
+def test_wide_tile_gemm_matches_the_128_wide_tiles(m, n, k, res):
+    """128 x 256 tiles (both TMEM accumulators 256 columns wide) for the teacher's large-N 1x1 convolutions: same
+    results as the 128 x 128 tiles, with the folded-BN epilogue and the TMA-fetched residual addend."""
+    torch.manual_seed(2)
+    a = torch.randn(m, k, device=DEV).bfloat16()
+    b = (torch.randn(n, k, device=DEV) * 0.05).bfloat16()
+    sh = torch.randn(n, device=DEV)
+    add = torch.randn(m, n, device=DEV).bfloat16() if res else None
+    ref = a.float() @ b.float().t() + sh + (add.float() if res else 0.0)
+    outs = []
+    try:
+        for wide in (True, False):
+            ops.native().set_wide_gemm_tiles(wide)
+            d = ops.gemm_bf16(a, b, col_shift=sh, relu=True, add=add)
+            assert _rel(d, torch.relu(ref)) < 1e-2, wide
+            outs.append(d)
+    finally:
+        ops.native().set_wide_gemm_tiles(True)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_persistent_gemm_epilogue_scale_shift_relu():
     torch.manual_seed(1)
     m, n, k = 5000, 256, 192
