@@ -58,11 +58,17 @@ def parse():
                     help="A/B (experimental): stride-2 3x3 forward convolutions on the tcgen05 kernel (student and teacher)")
     ap.add_argument("--pdl", action="store_true", help="A/B (experimental): programmatic dependent launch of the hot kernels")
     ap.add_argument("--own-wgrad3", action="store_true", help="A/B (experimental): tcgen05 3x3 weight-gradient kernel")
+    ap.add_argument("--no-library", action="store_true",
+                    help="every convolution of the student on our own kernels (3x3 wgrad v2, stride-2 backward, pixel-pair "
+                         "stem convolutions): no cuDNN / cuBLAS kernel in the step; `library_fallbacks` must come out empty")
     ap.add_argument("--no-fused-opt", action="store_true",
-                    help="A/B: plain all-reduce kernels + one optimizer pass instead of the fused reduce-scatter -> SGD -> all-gather buckets")
-    ap.add_argument("--clip-norm", type=float, default=0.0, help="global-norm gradient clipping (0 = off, the reference's config)")
+                    help="A/B: plain all-reduce kernels + one optimizer pass instead of the fused reduce-scatter -> "
+                         "SGD -> all-gather buckets")
+    ap.add_argument("--clip-norm", type=float, default=0.0,
+                    help="global-norm gradient clipping (0 = off, the reference's config)")
     ap.add_argument("--no-extras", action="store_true",
-                    help="skip the extra metric terms of BASELINE.json at N > 1 (exposed comm, rescale recovery, distill service)")
+                    help="skip the extra metric terms of BASELINE.json at N > 1 (exposed comm, rescale recovery, "
+                         "distill service)")
     ap.add_argument("--extras-budget-s", type=float, default=240.0,
                     help="wall-clock budget of the extra sections; when it runs out the headline line is printed without them")
     ap.add_argument("--distill-steps", type=int, default=40)
@@ -283,6 +289,9 @@ def main():
         os.environ["EDL_FAKE_HOST"] = "node%d" % (int(os.environ.get("RANK", "0")) // int(os.environ["EDL_FAKE_HOST_SPLIT"]))
     if args.pdl:
         os.environ["EDL_PDL"] = "1"            # read when the extension is loaded
+    if args.no_library:
+        for k in ("EDL_OWN_WGRAD3", "EDL_OWN_S2_BWD", "EDL_OWN_STEM23"):
+            os.environ[k] = "1"                # read when edl_b200.ops.gemm is imported
     if args.own_wgrad3:
         os.environ["EDL_OWN_WGRAD3"] = "1"     # read when edl_b200.ops.gemm is imported
     if args.fuse_bn_bwd:
@@ -439,7 +448,8 @@ def main():
             for i in range(3):
                 trainer.step(host_x[i % pool], host_t[i % pool]).item()
             e2e_ms, last = e2e_loop(False)
-            api = "StudentTrainer.step(images, targets) -> LossHandle (default: staged H2D on a copy stream, loss of step i read while step i+1 runs)"
+            api = ("StudentTrainer.step(images, targets) -> LossHandle (default: staged H2D on a copy stream, loss of "
+                   "step i read while step i+1 runs)")
         else:
             e2e_ms, last = e2e_loop(True)
             api = "trainer.step(images, targets); loss.item()"
@@ -450,8 +460,9 @@ def main():
                          "read; max over ranks", "last_loss": last}
         if hasattr(trainer, "step_pipelined"):
             s_ms, s_last = e2e_loop(True)
-            e2e["sync"] = {"value": B * world * args.steps / (s_ms / 1e3), "unit": "img/s", "ms_per_step": s_ms / args.steps,
-                           "last_loss": s_last, "note": "step(..., sync=True) + loss.item() inside every step (host stalls the GPU)"}
+            e2e["sync"] = {"value": B * world * args.steps / (s_ms / 1e3), "unit": "img/s",
+                           "ms_per_step": s_ms / args.steps, "last_loss": s_last,
+                           "note": "step(..., sync=True) + loss.item() inside every step (host stalls the GPU)"}
     clocks_note = "samples inside the timed regions"
 
     def few_samples_somewhere() -> bool:      # every rank must take the same decision (collectives inside a step)
@@ -493,7 +504,7 @@ def main():
                    "conv3_s2": ops.gemm.CONV3_S2 if args.impl == "edl" else None,
                    "own_stem1": ops.gemm.OWN_STEM1 if args.impl == "edl" else None,
                    "fuse_bn_bwd": (ops.native().get_bnr_mode() if ops.gemm.FUSE_BN_BWD else 0) if args.impl == "edl" else None,
-                   "clip_norm": args.clip_norm or None,
+                   "clip_norm": args.clip_norm or None, "no_library": bool(args.no_library),
                    "l2": "per-step working set (~GBs of activations) >> 126 MB L2, no explicit flush",
                    "baseline_note": "vs_baseline divides by the published 8xV100 1828 img/s (BASELINE.md P1)"},
         "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "loss_after_warmup": loss0,

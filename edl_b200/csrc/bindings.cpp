@@ -426,6 +426,28 @@ void stem_wgrad(const Tensor& x, const Tensor& dy, Tensor& dw, Tensor& ws, Tenso
   TORCH_CHECK(err == nullptr, "stem_wgrad: ", err);
 }
 
+void pair_weight_expand(const Tensor& w, Tensor& w2) {
+  check_bf16(w, "w");
+  check_bf16(w2, "w2");
+  TORCH_CHECK(w.dim() == 4 && w.size(1) == 3 && w.size(2) == 3 && w.size(3) == 32 && w2.numel() == 4 * w.numel());
+  c10::cuda::CUDAGuard g(w.device());
+  edl::pair_weight_expand(w.data_ptr(), w2.data_ptr(), (int)w.size(0), cur_stream());
+}
+void pair_weight_fold(const Tensor& dw2, Tensor& dw, bool accumulate) {
+  check_bf16(dw2, "dw2");
+  check_bf16(dw, "dw");
+  TORCH_CHECK(dw.numel() % (9 * 32) == 0 && dw2.numel() == 4 * dw.numel());
+  c10::cuda::CUDAGuard g(dw.device());
+  edl::pair_weight_fold(dw2.data_ptr(), dw.data_ptr(), (int)(dw.numel() / (9 * 32)), accumulate, cur_stream());
+}
+void fold_pair_stats(const Tensor& s2, Tensor& stats) {
+  check_f32(s2, "s2");
+  check_f32(stats, "stats");
+  TORCH_CHECK(s2.numel() == 2 * stats.numel() && stats.numel() % 2 == 0);
+  c10::cuda::CUDAGuard g(stats.device());
+  edl::fold_pair_stats(s2.data_ptr<float>(), stats.data_ptr<float>(), (int)(stats.numel() / 2), cur_stream());
+}
+
 void embedding_bag_fwd(const Tensor& table, const Tensor& ids, Tensor& out) {
   TORCH_CHECK(table.is_cuda() && table.is_contiguous() && ids.is_contiguous() && ids.scalar_type() == at::kLong);
   c10::cuda::CUDAGuard g(table.device());
@@ -541,6 +563,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("embedding_bag_fwd", &embedding_bag_fwd);
   m.def("stem_conv3x3s2", &stem_conv3x3s2);
   m.def("stem_wgrad", &stem_wgrad);
+  m.def("pair_weight_expand", &pair_weight_expand);
+  m.def("pair_weight_fold", &pair_weight_fold);
+  m.def("fold_pair_stats", &fold_pair_stats);
   m.def("embedding_bag_bwd", &embedding_bag_bwd);
   m.def("normalize_u8", &normalize_u8);
   m.def("peer_ship", &peer_ship);

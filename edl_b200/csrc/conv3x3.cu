@@ -361,4 +361,18 @@ const char* conv3x3_bf16(const Conv3x3Args& a, cudaStream_t stream) {
   return cy <= 64 ? launch<64, 4, true>(a, geo, stream) : launch<128, 3, true>(a, geo, stream);
 }
 
+bool conv3x3_dgrad_s2_supported(int N, int Ho, int Wo, int Cin, int Cout) {
+  return persistent_gemm_enabled() && conv3x3_supported(N, Ho, Wo, Cin, Cout, true, 1);
+}
+
+const char* conv3x3_dgrad_s2_bf16(const Conv3x3Args& a, cudaStream_t stream) {
+  if (!conv3x3_dgrad_s2_supported(a.N, a.H, a.W, a.Cin, a.Cout)) return "conv3x3 stride-2 dgrad: unsupported shape";
+  if (a.device >= 0) {
+    cudaError_t e = cudaSetDevice(a.device);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+  }
+  const Geometry geo = plan(a.N, a.H, a.W);
+  return conv3x3_dgrad_s2_persistent(a, geo.BH, geo.BN, geo.tiles_h, geo.tiles_img, stream);
+}
+
 }  // namespace edl

@@ -558,8 +558,8 @@ const char* launch_variant(const GemmArgs& g, cudaStream_t stream) {
 // several are in flight), a shared-memory pass adds the 4 partial sums.  The kernel is latency-bound by construction
 // (a few MB out of L2): the z-parallel layout keeps it at 2-4 us instead of split x load latency.
 constexpr int kRedVec = 64;     // float4 per CTA
-constexpr int kRedZ = 4;        // split groups per CTA
 
+template <int kRedZ>            // split groups per CTA: 4, or 16 for deep splits (few tiles, 32+ partials each)
 __global__ void __launch_bounds__(kRedVec * kRedZ)
 splitk_reduce_kernel(const float* __restrict__ part, int split, int ctas, int tiles_n, int rows, int cols, int taps,
                      int cin, int M, int N, __nv_bfloat16* __restrict__ out, long long ldo, int accumulate) {
@@ -639,11 +639,17 @@ void splitk_reduce(const float* partials, int split, int ctas, int tiles_n, int 
                    int N, void* out_bf16, int64_t ldo, bool accumulate, cudaStream_t stream) {
   const int64_t total = (int64_t)ctas * rows * (cols / 4);
   int blocks = (int)((total + kRedVec - 1) / kRedVec);
-  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   if (blocks < 1) blocks = 1;
-  splitk_reduce_kernel<<<blocks, kRedVec * kRedZ, 0, stream>>>(partials, split, ctas, tiles_n, rows, cols, taps, cin, M, N,
-                                                  reinterpret_cast<__nv_bfloat16*>(out_bf16), (long long)ldo,
-                                                  accumulate ? 1 : 0);
+  auto* out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  if (split >= 32) {
+    if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
+    splitk_reduce_kernel<16><<<blocks, kRedVec * 16, 0, stream>>>(partials, split, ctas, tiles_n, rows, cols, taps, cin,
+                                                                 M, N, out, (long long)ldo, accumulate ? 1 : 0);
+  } else {
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    splitk_reduce_kernel<4><<<blocks, kRedVec * 4, 0, stream>>>(partials, split, ctas, tiles_n, rows, cols, taps, cin, M,
+                                                               N, out, (long long)ldo, accumulate ? 1 : 0);
+  }
 }
 
 const char* gemm_bf16(const GemmArgs& g, cudaStream_t stream) {

@@ -94,6 +94,9 @@ struct Conv3x3Args {
 };
 bool conv3x3_supported(int N, int H, int W, int Cin, int Cout, bool dgrad, int groups = 1);
 const char* conv3x3_bf16(const Conv3x3Args& args, cudaStream_t stream);
+// input gradient of the stride-2 convolution: args.X = dY [N, H, W, Cout], args.Y = dX [N, 2H, 2W, Cin], N/H/W of dY
+bool conv3x3_dgrad_s2_supported(int N, int Ho, int Wo, int Cin, int Cout);
+const char* conv3x3_dgrad_s2_bf16(const Conv3x3Args& args, cudaStream_t stream);
 
 // Weight gradient of the same convolution (conv3x3_wgrad.cu): dW[Cout,3,3,Cin] (+)= sum_pixels dY x shifted X, pixel
 // reduction split over `split_k` CTAs with the fused fp32 -> bf16 finalize of the 1x1 wgrad GEMM.
@@ -130,6 +133,8 @@ void set_persistent_gemm(bool on);
 bool persistent_gemm_enabled();
 void set_wide_gemm_tiles(bool on);   // 128 x 256 tiles for large-N inference GEMMs (default on; EDL_GEMM_WIDE=0)
 const char* gemm_bf16_persistent(const GemmArgs& args, cudaStream_t stream);
+const char* conv3x3_dgrad_s2_persistent(const Conv3x3Args& args, int BH, int BN, int tiles_h, int tiles_img,
+                                        cudaStream_t stream);
 const char* conv3x3_bf16_persistent(const Conv3x3Args& args, int BH, int BN, int tiles_h, int tiles_img,
                                     cudaStream_t stream);
 

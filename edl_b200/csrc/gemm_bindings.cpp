@@ -180,6 +180,33 @@ void conv3x3(const Tensor& x, const Tensor& w, Tensor& y, bool dgrad, const c10:
   TORCH_CHECK(err == nullptr, "edl conv3x3 failed: ", err);
 }
 
+// dx [N,Cin,2H,2W] = input gradient of the 3x3 / pad 1 / stride 2 convolution for dy [N,Cout,H,W]; w KRSC [Cout,3,3,Cin]
+void conv3x3_dgrad_s2(const Tensor& dy, const Tensor& w, Tensor& dx) {
+  TORCH_CHECK(dy.is_cuda() && dy.dim() == 4 && dx.dim() == 4 && w.dim() == 4);
+  TORCH_CHECK(dy.scalar_type() == at::kBFloat16 && dx.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(dy.is_contiguous(at::MemoryFormat::ChannelsLast) && dx.is_contiguous(at::MemoryFormat::ChannelsLast));
+  TORCH_CHECK(w.is_contiguous() && w.size(1) == 3 && w.size(2) == 3, "weight must be KRSC [Cout,3,3,Cin]");
+  edl::Conv3x3Args a;
+  a.X = dy.data_ptr();
+  a.Wt = w.data_ptr();
+  a.Y = dx.data_ptr();
+  a.N = dy.size(0);
+  a.H = dy.size(2);
+  a.W = dy.size(3);
+  a.Cout = w.size(0);
+  a.Cin = w.size(3);
+  a.dgrad = true;
+  TORCH_CHECK(dy.size(1) == a.Cout && dx.size(1) == a.Cin && dx.size(0) == a.N && dx.size(2) == 2 * a.H &&
+              dx.size(3) == 2 * a.W, "conv3x3_dgrad_s2: shapes do not belong together");
+  a.device = dy.device().index();
+  c10::cuda::CUDAGuard guard(dy.device());
+  const char* err = edl::conv3x3_dgrad_s2_bf16(a, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(err == nullptr, "edl conv3x3_dgrad_s2 failed: ", err);
+}
+bool conv3x3_dgrad_s2_supported(int64_t n, int64_t ho, int64_t wo, int64_t cin, int64_t cout) {
+  return edl::conv3x3_dgrad_s2_supported((int)n, (int)ho, (int)wo, (int)cin, (int)cout);
+}
+
 // D bf16 [M,N] = relu?((A8[M,K] * B8[N,K]^T) * col_scale + col_shift); A8/B8 are e4m3 bytes (uint8 / float8 tensors)
 void gemm_fp8(const Tensor& A, const Tensor& B, Tensor& D, const c10::optional<Tensor>& col_scale,
               const c10::optional<Tensor>& col_shift, bool relu) {
@@ -348,6 +375,8 @@ void register_gemm_bindings(pybind11::module_& m) {
   m.def("conv3x3_supported", &conv3x3_supported);
   m.def("conv3x3_infer", &conv3x3_infer);
   m.def("gemm_bf16_ship", &gemm_bf16_ship);
+  m.def("conv3x3_dgrad_s2", &conv3x3_dgrad_s2);
+  m.def("conv3x3_dgrad_s2_supported", &conv3x3_dgrad_s2_supported);
   m.def("conv3x3_wgrad", &conv3x3_wgrad);
   m.def("conv3x3_wgrad_supported", &conv3x3_wgrad_supported);
   m.def("conv3x3_wgrad_s2_supported", &conv3x3_wgrad_s2_supported);

@@ -61,6 +61,11 @@ struct PersistParams {
   int n_img, H, W, kc_blocks, c_in_w, BH, BN, tiles_h;
   int cin_g, cout_g;              // grouped fprop: channels per group (cout_g == N for a dense conv)
   int stride;                     // conv fprop: 1, or 2 (input rows 2*h + r - 1; the columns come from the tensor map)
+  // explicit tap list (conv modes; 0 = the nine standard taps): k-block i belongs to tap i / kc_blocks, which reads the
+  // input box shifted by (tap_dh, tap_dw) and the weight tap tap_w.  Used by the stride-2 dgrad, which is four small
+  // stride-1 convolutions over the output gradient -- one per parity class of the input pixel -- with 1, 2, 2 and 4 taps.
+  int ntaps;
+  signed char tap_dh[9], tap_dw[9], tap_w[9];
 };
 
 template <int BLOCK_N, int STAGES, int BNR = 0>
@@ -224,11 +229,18 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 ptx::tma_load_2d(sb + hh * 8192, &tmB, &full_bar[s], n0 + hh * 64, k0);
             }
           } else {
-            const int tap = i / p.kc_blocks;
+            int tap = i / p.kc_blocks;
             const int kc = i - tap * p.kc_blocks;
-            const int r = tap / 3, sft = tap - r * 3;
-            const int dh = kDgrad ? 1 - r : r - 1;
-            const int dw = kDgrad ? 1 - sft : sft - 1;
+            int dh, dw;
+            if (p.ntaps > 0) {
+              dh = p.tap_dh[tap];
+              dw = p.tap_dw[tap];
+              tap = p.tap_w[tap];
+            } else {
+              const int r = tap / 3, sft = tap - r * 3;
+              dh = kDgrad ? 1 - r : r - 1;
+              dw = kDgrad ? 1 - sft : sft - 1;
+            }
             // grouped fprop: the N tile lies in one group; its input channels start at group * cin_g
             const int cbase_in = (MODE == 2) ? (n0 / p.cout_g) * p.cin_g : 0;
             ptx::tma_load_4d(sa, &tmA, &full_bar[s], cbase_in + kc * kBlockK, dw, h0 * p.stride + dh, img0);
@@ -834,6 +846,65 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
   }
   if (!dg) return n64 ? launch_p<64, 6, 2>(tmX, tmW, tmY, p, stream) : launch_p<128, 5, 2>(tmX, tmW, tmY, p, stream);
   return n64 ? launch_p<64, 6, 3>(tmX, tmW, tmY, p, stream) : launch_p<128, 5, 3>(tmX, tmW, tmY, p, stream);
+}
+
+// Input gradient of the 3x3 / pad 1 / STRIDE 2 convolution (round 2).  dX[n, h, w] = sum over the taps (r, s) with
+// h + 1 - r and w + 1 - s even of dY[n, (h + 1 - r) / 2, (w + 1 - s) / 2] * W[:, r, s, :]: for a fixed parity (h & 1, w & 1)
+// that is a stride-1 convolution of dY with 1, 2, 2 or 4 taps whose result lands on every second pixel of dX.  Four
+// launches of the dgrad mode with an explicit tap list and a strided output tensor map -- 9 tap-MMAs per output-gradient
+// pixel in total, exactly the work of the forward pass (zero-insertion + stride-1 dgrad costs four times that).
+// a.X = dY [N, Ho, Wo, Cout], a.Y = dX [N, 2 Ho, 2 Wo, Cin], a.N / H / W = the dY geometry.
+const char* conv3x3_dgrad_s2_persistent(const Conv3x3Args& a, int BH, int BN, int tiles_h, int tiles_img,
+                                        cudaStream_t stream) {
+  const int cx = a.Cout, cy = a.Cin;
+  const bool n64 = cy <= 64;
+  const int bn = n64 ? 64 : 128;
+  alignas(64) CUtensorMap tmX, tmW;
+  {
+    const uint64_t dims[4] = {(uint64_t)cx, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
+    const uint64_t st[3] = {(uint64_t)cx * 2, (uint64_t)a.W * cx * 2, (uint64_t)a.H * a.W * cx * 2};
+    const uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)BH, (uint32_t)BN};
+    if (const char* e = encode_tmap_bf16(&tmX, a.X, 4, dims, st, box)) return e;
+  }
+  if (const char* e = tmap2d(&tmW, a.Wt, (uint64_t)9 * a.Cin, a.Cout, (uint64_t)9 * a.Cin, 64, kBlockK)) return e;
+  const uint64_t W2 = 2ull * a.W, H2 = 2ull * a.H;
+  for (int ph = 0; ph < 2; ++ph) {
+    for (int pw = 0; pw < 2; ++pw) {
+      alignas(64) CUtensorMap tmY;
+      {
+        // the pixels (2 i + ph, 2 j + pw) of dX as a dense-looking [N, Ho, Wo, Cin] tensor with doubled pixel strides
+        const uint64_t dims[4] = {(uint64_t)cy, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
+        const uint64_t st[3] = {2ull * cy * 2, 2ull * W2 * cy * 2, H2 * W2 * cy * 2};
+        const uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)BH, (uint32_t)BN};
+        const char* base = reinterpret_cast<const char*>(a.Y) + ((uint64_t)ph * W2 + pw) * cy * 2;
+        if (const char* e = encode_tmap_bf16(&tmY, base, 4, dims, st, box)) return e;
+      }
+      PersistParams p{};
+      p.M = tiles_img * tiles_h * kBlockM; p.N = cy; p.K = 9 * cx;
+      p.tiles_m = tiles_img * tiles_h;
+      p.tiles_n = (cy + bn - 1) / bn;
+      p.kc_blocks = cx / kBlockK;
+      p.cin_g = cx; p.cout_g = cy;
+      p.n_img = a.N; p.H = a.H; p.W = a.W; p.c_in_w = a.Cin; p.BH = BH; p.BN = BN; p.tiles_h = tiles_h;
+      p.stride = 1;
+      int nt = 0;
+      for (int r = 0; r < 3; ++r) {
+        if (((ph + 1 - r) & 1) != 0) continue;
+        for (int sft = 0; sft < 3; ++sft) {
+          if (((pw + 1 - sft) & 1) != 0) continue;
+          p.tap_dh[nt] = (signed char)((ph + 1 - r) / 2);      // exact: the numerator is even (0 or 2)
+          p.tap_dw[nt] = (signed char)((pw + 1 - sft) / 2);
+          p.tap_w[nt] = (signed char)(r * 3 + sft);
+          ++nt;
+        }
+      }
+      p.ntaps = nt;
+      p.num_kb = nt * p.kc_blocks;
+      const char* e = n64 ? launch_p<64, 6, 3>(tmX, tmW, tmY, p, stream) : launch_p<128, 5, 3>(tmX, tmW, tmY, p, stream);
+      if (e != nullptr) return e;
+    }
+  }
+  return nullptr;
 }
 
 }  // namespace edl

@@ -125,6 +125,10 @@ void comm_allgather_scalars(const CommHandles& h, const float* in, float* out, i
 // ---- misc.cu ----
 void rope(const void* x, const float* cosv, const float* sinv, void* y, int64_t T, int H, int D,
           bool inverse, cudaStream_t s);
+// pixel-pair form of the 32-channel 3x3 stem convolutions (misc.cu): W [cout,3,3,32] <-> W2 [2*cout,3,3,64]
+void pair_weight_expand(const void* w, void* w2, int cout, cudaStream_t s);
+void pair_weight_fold(const void* dw2, void* dw, int cout, bool accumulate, cudaStream_t s);
+void fold_pair_stats(const float* s2, float* stats, int cout, cudaStream_t s);
 // ---- stem.cu: first stem convolution (3 -> 32, 3x3 / stride 2 / pad 1, NHWC bf16) + BN statistics of its output ----
 void stem_conv3x3s2(const void* x, const void* w, void* y, float* stats, int N, int H, int W, cudaStream_t s);
 // its weight gradient: dw KRSC [32,3,3,3] bf16 (+)= ; ws: >= 864 zero floats (left zero), counter: one zero int (left zero)

@@ -99,7 +99,80 @@ inline int grid_for(int64_t n) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// "Pixel-pair" form of a 3x3 / stride 1 / pad 1 convolution with 32 input channels (the stem convolutions conv1_2 and
+// conv1_3 of ResNet_vd): an NHWC tensor [N, H, W, 32] IS an NHWC tensor [N, H, W/2, 64] (two neighbouring pixels =
+// one 64-channel "pair pixel"), and the convolution becomes a 3x3 convolution over pair pixels with 64 input and
+// 2 * Cout output channels whose weight is a re-arrangement of the original one:
+//     W2[(p, co), r, t, (q, c)] = W[co, r, s, c]   with  s = 2 (t - 1) + q - p + 1   if 0 <= s <= 2, else 0
+// (p = parity of the output pixel inside its pair, q = parity of the input pixel inside its pair, t = tap over pairs).
+// Half of W2 is zero, but the layers are memory-bound and this puts them on the 64-channel k-blocks of the tcgen05
+// 3x3 kernels (fprop, dgrad, wgrad) instead of the vendor library.  Reference call site:
+// example/distill/resnet/models/resnet_vd.py:49-60.
+__global__ void __launch_bounds__(kThreads)
+pair_weight_expand_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ w2, int cout) {
+  // one thread per element of W2 [2*cout][3][3][64]
+  const int total = 2 * cout * 9 * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int qc = i & 63, q = qc >> 5, c = qc & 31;
+    int rest = i >> 6;
+    const int t = rest % 3;
+    rest /= 3;
+    const int r = rest % 3;
+    const int pco = rest / 3;
+    const int p = pco / cout, co = pco - p * cout;
+    const int s = 2 * (t - 1) + q - p + 1;
+    w2[i] = (s >= 0 && s <= 2) ? w[((co * 3 + r) * 3 + s) * 32 + c] : __float2bfloat16(0.f);
+  }
+}
+
+// dW[co, r, s, c] (+)= sum over p of dW2[(p, co), r, t(s, p), (q(s, p), c)]: every element of dW has exactly two sources
+__global__ void __launch_bounds__(kThreads)
+pair_weight_fold_kernel(const __nv_bfloat16* __restrict__ dw2, __nv_bfloat16* __restrict__ dw, int cout, int accumulate) {
+  const int total = cout * 9 * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i & 31;
+    int rest = i >> 5;
+    const int s = rest % 3;
+    rest /= 3;
+    const int r = rest % 3;
+    const int co = rest / 3;
+    float acc = accumulate ? __bfloat162float(dw[i]) : 0.f;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      // s = 2 (t - 1) + q - p + 1  =>  u = s + p - 1 = 2 (t - 1) + q  with q in {0, 1}
+      const int u = s + p - 1;
+      const int q = u & 1;                 // two's complement: -1 & 1 == 1
+      const int t = ((u - q) >> 1) + 1;
+      acc += __bfloat162float(dw2[(((p * cout + co) * 3 + r) * 3 + t) * 64 + q * 32 + c]);
+    }
+    dw[i] = __float2bfloat16(acc);
+  }
+}
+
+// stats[j] += a[j] + a[cout + j] (j < cout) for the sum and the sum of squares halves: the BatchNorm statistics of
+// the pair-pixel output [.., 2 * cout] folded to the real channels
+__global__ void fold_pair_stats_kernel(const float* __restrict__ s2, float* __restrict__ stats, int cout) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < cout) {
+    stats[j] += s2[j] + s2[cout + j];
+    stats[cout + j] += s2[2 * cout + j] + s2[3 * cout + j];
+  }
+}
+
 }  // namespace
+
+void pair_weight_expand(const void* w, void* w2, int cout, cudaStream_t s) {
+  pair_weight_expand_kernel<<<grid_for((int64_t)2 * cout * 9 * 64), kThreads, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(w2), cout);
+}
+void pair_weight_fold(const void* dw2, void* dw, int cout, bool accumulate, cudaStream_t s) {
+  pair_weight_fold_kernel<<<grid_for((int64_t)cout * 9 * 32), kThreads, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dw2), reinterpret_cast<__nv_bfloat16*>(dw), cout, accumulate ? 1 : 0);
+}
+void fold_pair_stats(const float* s2, float* stats, int cout, cudaStream_t s) {
+  fold_pair_stats_kernel<<<(cout + 127) / 128, 128, 0, s>>>(s2, stats, cout);
+}
 
 void rope(const void* x, const float* cosv, const float* sinv, void* y, int64_t T, int H, int D, bool inverse,
           cudaStream_t s) {

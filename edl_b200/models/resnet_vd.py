@@ -58,6 +58,14 @@ class ConvBNAct(nn.Module):
                 stats = self.fwd_stats if self.fwd_stats is not None else torch.zeros(
                     2 * self.cout, device=x.device, dtype=torch.float32)
             return ops.conv3x3(x, self.weight, stats), stats
+        if (self.k == 3 and self.stride == 1 and self.groups == 1 and self.cin == 32 and self.impl != "cudnn"
+                and self.own_conv3 and ops.conv3x3_pair_supported(x, self.weight)):
+            # EDL_OWN_STEM23=1: 32-channel stem convolutions in pixel-pair form on the tcgen05 3x3 kernels
+            stats = None
+            if want_stats:
+                stats = self.fwd_stats if self.fwd_stats is not None else torch.zeros(
+                    2 * self.cout, device=x.device, dtype=torch.float32)
+            return ops.conv3x3_pair(x, self.weight, stats), stats
         if (self.k == 3 and self.stride == 2 and self.cin == 3 and self.cout == 32 and self.impl != "cudnn"
                 and ops.gemm.OWN_STEM1 and ops.stem_conv_supported(x, self.weight)):
             # experimental (EDL_OWN_STEM1=1): direct kernel for the K = 27 stem convolution, statistics fused

@@ -103,6 +103,11 @@ def _split_k_for(m, n, k):
     tiles with K ~ 100k) take the full 148-way split because they have few elements to update."""
     tiles = ((m + 127) // 128) * ((n + 127) // 128 if n > 64 else 1)
     kb = (k + 63) // 64
+    if tiles >= 48:
+        # a third of the SMs already have a tile: no split, hence no partial tiles and no reduce kernel.  The weight
+        # gradients run on the low-priority side stream and are not the critical path: a kernel that keeps 48-147 SMs
+        # busy a little longer leaves the other SMs to the dgrad / BatchNorm chain, which is what limits the step
+        return 1
     want = max(1, _NUM_SMS // tiles)
     return max(1, min(want, max(1, kb // 2)))
 
@@ -527,8 +532,9 @@ def conv3x3_wgrad(x, dy, weight_shape, sink=None, split_k: Optional[int] = None)
         else:
             kblocks = native().conv3x3_wgrad_kblocks(n, h, w)
             ctas = native().conv3x3_wgrad_ctas(cin, cout)
-        # one wave of CTAs, at least two pixel blocks per CTA (same rule as the 1x1 wgrad split)
-        split_k = max(1, min(max(1, _NUM_SMS // ctas), max(1, kblocks // 2)))
+        # one wave of CTAs, at least two pixel blocks per CTA; no split once a third of the SMs have a CTA (same rule
+        # as the 1x1 wgrad split)
+        split_k = 1 if ctas >= 48 else max(1, min(max(1, _NUM_SMS // ctas), max(1, kblocks // 2)))
     if sink is not None:
         out, acc = sink.view(weight_shape), True
     else:
@@ -585,8 +591,9 @@ def conv3x3_s2_infer(x, weight_krsc, scale=None, shift=None, relu=False, groups=
 
 # Backward of the stride-2 3x3 convolutions on our own kernels (EDL_OWN_S2_BWD=1; validated on B200, OFF by default:
 # the three layers cost 0.12 ms / step more than the library's strided kernels -- profiles/bench_runs.json "s2lib"):
-#   dgrad: zero-insert dy to the input resolution (csrc/pool.cu:dilate2_kernel) and run the stride-1 tcgen05 dgrad on it
-#          (the transposed stride-2 convolution IS that); 4x the MMAs of a native strided dgrad, but only 3 layers;
+#   dgrad: four stride-1 tcgen05 launches over dy, one per parity class of the input pixel (1 + 2 + 2 + 4 taps = the
+#          nine tap-MMAs of the forward pass), each storing through a strided tensor map.  (First version: zero-insert
+#          dy with csrc/pool.cu:dilate2_kernel and run the plain stride-1 dgrad: 4x the MMAs, +0.12 ms/step.);
 #   wgrad: the version-1 weight-gradient kernel with X read through the TMA traversal stride (csrc/conv3x3_wgrad.cu).
 OWN_S2_BWD = __import__("os").environ.get("EDL_OWN_S2_BWD", "0") == "1"
 
@@ -596,8 +603,8 @@ def _s2_dgrad_supported(x, w) -> bool:
 
     n, c, h, wd = x.shape
     cout = w.shape[0]
-    return (OWN_S2_BWD and x.is_cuda and cout % 8 == 0 and h % 2 == 0 and wd % 2 == 0
-            and native().conv3x3_supported(n, h, wd, cout, c, True, 1))
+    return (OWN_S2_BWD and x.is_cuda and h % 2 == 0 and wd % 2 == 0
+            and native().conv3x3_dgrad_s2_supported(n, h // 2, wd // 2, c, cout))
 
 
 def _s2_wgrad_supported(x, w) -> bool:
@@ -631,13 +638,11 @@ class _Conv3x3S2Fn(torch.autograd.Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             if _s2_dgrad_supported(x, w):
-                n, cout, ho, wo = dy.shape
-                up = torch.empty((n, cout, 2 * ho, 2 * wo), device=dy.device, dtype=dy.dtype,
-                                 memory_format=torch.channels_last)
-                native().dilate2(dy, up)
+                # four stride-1 launches (1 + 2 + 2 + 4 taps), one per parity class of the input pixel, each storing
+                # through a strided tensor map (csrc/gemm_persist.cu:conv3x3_dgrad_s2_persistent)
                 dx = torch.empty_like(x)
-                native().conv3x3(up, w, dx, True, None, None, False)
-                count_launch(2)
+                native().conv3x3_dgrad_s2(dy, w, dx)
+                count_launch(4)
             else:
                 dx = _ConvLibFn._bwd(dy, x, w.permute(0, 3, 1, 2), ctx.cfg, [True, False, False])[0]
         if ctx.needs_input_grad[1]:
@@ -761,6 +766,111 @@ def stem_conv(x, weight_krsc, stats: Optional[torch.Tensor] = None):
     sink = getattr(weight_krsc, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
     ready = getattr(weight_krsc, "_edl_grad_ready", None) if sink is not None else None
     return _StemConvFn.apply(x, weight_krsc, stats, sink, ready)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 3x3 / stride 1 convolutions with 32 input channels (the stem's conv1_2 / conv1_3) in "pixel-pair" form on the
+# 64-channel tcgen05 kernels (csrc/misc.cu:pair_weight_expand_kernel explains the transform).  EDL_OWN_STEM23=1.
+OWN_STEM23 = __import__("os").environ.get("EDL_OWN_STEM23", "0") == "1"
+
+
+def _pair_view(t):
+    """NHWC [N, H, W, C] seen as [N, H, W/2, 2C] (zero-copy), returned in the NCHW-shaped channels_last form."""
+    n, c, h, w = t.shape
+    return t.as_strided((n, 2 * c, h, w // 2), (h * w * c, 1, w * c, 2 * c))
+
+
+def _unpair_view(t2):
+    n, c2, h, w2 = t2.shape
+    return t2.as_strided((n, c2 // 2, h, 2 * w2), (h * w2 * c2, 1, w2 * c2, c2 // 2))
+
+
+def conv3x3_pair_supported(x, weight_krsc) -> bool:
+    from . import native
+
+    if not (OWN_STEM23 and x.is_cuda and x.dtype == torch.bfloat16 and weight_krsc.dtype == torch.bfloat16 and x.dim() == 4):
+        return False
+    n, c, h, w = x.shape
+    cout, kh, kw, cin = weight_krsc.shape
+    return (kh == 3 and kw == 3 and cin == 32 and c == 32 and w % 2 == 0 and cout % 32 == 0
+            and native().conv3x3_supported(n, h, w // 2, 64, 2 * cout, False, 1)
+            and native().conv3x3_supported(n, h, w // 2, 2 * cout, 64, True, 1))
+
+
+class _Conv3x3PairFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, stats, sink, ready):
+        from . import native, count_launch
+
+        C = native()
+        x = _cl(x)
+        n, _, h, wd = x.shape
+        cout = w.shape[0]
+        w2 = torch.empty((2 * cout, 3, 3, 64), device=x.device, dtype=x.dtype)
+        C.pair_weight_expand(w.contiguous(), w2)
+        x2 = _pair_view(x)
+        y2 = torch.empty((n, 2 * cout, h, wd // 2), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+        s2 = torch.zeros(4 * cout, device=x.device, dtype=torch.float32) if stats is not None else None
+        C.conv3x3(x2, w2, y2, False, s2, None, False)
+        count_launch(2)
+        if stats is not None:
+            C.fold_pair_stats(s2, stats)
+            count_launch()
+        ctx.save_for_backward(x, w, w2)
+        ctx.sink, ctx.ready = sink, ready
+        return _unpair_view(y2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import native, count_launch
+
+        C = native()
+        x, w, w2 = ctx.saved_tensors
+        dy = _cl(dy)
+        x2, dy2 = _pair_view(x), _pair_view(dy)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx2 = torch.empty_like(x2)
+            C.conv3x3(dy2, w2, dx2, True, None, None, False)
+            count_launch()
+            dx = _unpair_view(dx2)
+        dw = None
+        if ctx.needs_input_grad[1]:
+            sink, ready = ctx.sink, ctx.ready
+            side = _SIDE["stream"] if sink is not None else None
+
+            def wgrad():
+                if _SKIP_WGRAD and sink is not None:
+                    if ready is not None:
+                        ready()
+                    return None
+                dw2 = conv3x3_wgrad(x2, dy2, w2.shape, None)
+                out = sink.view(w.shape) if sink is not None else torch.empty_like(w)
+                C.pair_weight_fold(dw2, out, sink is not None)
+                count_launch()
+                if sink is not None:
+                    if ready is not None:
+                        ready()
+                    return None
+                return out
+
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dy.device))
+                side.wait_event(ev)
+                _SIDE["keep"].append((dy, x))
+                with torch.cuda.stream(side):
+                    dw = wgrad()
+                    _SIDE["keep"].append(None)
+            else:
+                dw = wgrad()
+        return dx, dw, None, None, None
+
+
+def conv3x3_pair(x, weight_krsc, stats: Optional[torch.Tensor] = None):
+    sink = getattr(weight_krsc, "_edl_grad_sink", None) if torch.is_grad_enabled() else None
+    ready = getattr(weight_krsc, "_edl_grad_ready", None) if sink is not None else None
+    return _Conv3x3PairFn.apply(x, weight_krsc, stats, sink, ready)
 
 
 def conv3x3_infer_supported(x, weight_krsc, groups=1) -> bool:

@@ -540,3 +540,32 @@ def test_nvjpeg_batched_decode_and_fused_augmentation(backend):
         assert (x[i].permute(1, 2, 0).float().cpu() - want).abs().mean().item() < 0.05, i
     x1 = aug(blobs[:1], random.Random(11), train=False)               # single-image path + eval crop
     assert x1.shape == (1, 3, 224, 224)
+
+
+@pytest.mark.parametrize("n,cout,h,w", [(4, 32, 112, 112), (2, 64, 112, 112), (3, 32, 20, 24)])
+def test_32_channel_conv_in_pixel_pair_form(monkeypatch, n, cout, h, w):
+    """EDL_OWN_STEM23: conv1_2 / conv1_3 of the stem (32 input channels) as a 64-channel convolution over pixel pairs:
+    forward with fused BN statistics, input gradient and weight gradient against the fp32 reference."""
+    from edl_b200.ops import gemm as G
+
+    monkeypatch.setattr(G, "OWN_STEM23", True)
+    torch.manual_seed(0)
+    x = torch.randn(n, 32, h, w, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wt = (torch.randn(cout, 3, 3, 32, device=DEV) * 0.1).bfloat16().requires_grad_(True)
+    if not ops.conv3x3_pair_supported(x, wt):
+        pytest.skip("geometry not supported")
+    stats = torch.zeros(2 * cout, device=DEV)
+    ops.reset_fallbacks()
+    y = ops.conv3x3_pair(x, wt, stats)
+    xr = x.detach().float().requires_grad_(True)
+    wr = wt.detach().float().requires_grad_(True)
+    ref = F.conv2d(xr, wr.permute(0, 3, 1, 2), None, 1, 1)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert _rel(y, ref) < 1e-2
+    yf = y.float()
+    assert _rel(stats[:cout], yf.sum((0, 2, 3))) < 2e-3 and _rel(stats[cout:], (yf * yf).sum((0, 2, 3))) < 2e-3
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    ref.backward(dy.float())
+    assert _rel(x.grad, xr.grad) < 1e-2 and _rel(wt.grad, wr.grad) < 1e-2
+    assert not ops.fallbacks(), ops.fallbacks()

@@ -113,7 +113,9 @@ def main():
             d = json.loads(line)
             bench[os.path.basename(f)[:-5]] = {k: d.get(k) for k in ("impl", "n_gpus", "value", "unit", "ms_per_step", "gpu_launches", "clocks")}
             bench[os.path.basename(f)[:-5]]["e2e"] = (d.get("e2e") or {}).get("value")
-            bench[os.path.basename(f)[:-5]]["config"] = {k: (d.get("config") or {}).get(k) for k in ("model", "batch_per_gpu", "cuda_graph", "conv_impl", "allreduce", "parallelism", "own_wgrad3", "fuse_bn_bwd", "conv3_s2", "own_stem1")}
+            keys = ("model", "batch_per_gpu", "cuda_graph", "conv_impl", "allreduce", "parallelism", "own_wgrad3",
+                    "fuse_bn_bwd", "conv3_s2", "own_stem1", "no_library")
+            bench[os.path.basename(f)[:-5]]["config"] = {k: (d.get("config") or {}).get(k) for k in keys}
             for extra in ("exposed_comm_ms", "library_fallbacks"):
                 if d.get(extra) is not None:
                     bench[os.path.basename(f)[:-5]][extra] = d[extra]
