@@ -131,58 +131,122 @@ stem_conv3x3s2_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
 // ---------------------------------------------------------------------------------------------------------------
 // Weight gradient of the same convolution:  dW[co][r][s][c] = sum over (n, ho, wo) of
 //     dY[n, ho, wo, co] * X[n, 2 ho + r - 1, 2 wo + s - 1, c]
-// (reference: conv2d_grad through cuDNN; round 1 of this repo used the library's wgrad on the side stream).  864
-// outputs, 347 M MACs at batch 32: CUDA cores.  One CTA of 4 warps walks output rows; warp w owns output channels
-// [8w, 8w + 8), LANE l < 27 owns tap l = (r, s, c) -- per output pixel a lane reads ITS input value (consecutive
-// lanes read consecutive floats of the staged input rows) and the warp's 8 dY values (one broadcast 16-byte read)
-// and does 8 FMAs.  Partials go to a tap-major fp32 workspace [27][32] with two 16-byte vector reductions per lane,
-// the last CTA converts to bf16 KRSC (+= the gradient bucket) and re-zeroes the workspace.
+// (reference: conv2d_grad through cuDNN).  As a GEMM: dW^T-free form  D[32 co x 27 taps] = dY^T[32 x P] * Patch[P x 27]
+// with P = 401k output pixels at batch 32 -- far too small an output for tcgen05 tiles (and K = pixels is gathered
+// from three input rows), so the warp-level tensor-core path does it: mma.sync m16n8k16, A = dY^T through
+// ldmatrix.trans from the staged dY row, B = the im2col patch built on the fly from the staged input rows (4 16-bit
+// shared loads per fragment), 8 MMAs per 16 pixels per warp.  The first version of this kernel used CUDA cores
+// (lane = tap, 8 FMAs per shared-memory read): 86-92 us, issue- and latency-bound, and -- because the stem's gradient
+// is the LAST one backward produces -- exposed 1 : 1 at the end of the step (profiles/timeline_r2).  This one is bound
+// by reading dY and X once.  Partials: shared-memory [tap][co] per CTA, then 16-byte vector reductions into a tap-major
+// fp32 workspace; the last CTA converts to bf16 KRSC (+= the gradient bucket) and re-zeroes the workspace.
 constexpr int kWgThreads = 128;
+
+EDL_DEVICE void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+EDL_DEVICE void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
 __global__ void __launch_bounds__(kWgThreads)
 stem_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ ws,
                   int* __restrict__ counter, __nv_bfloat16* __restrict__ dw, int accumulate, int N, int H, int W,
-                  int Ho, int Wo) {
+                  int Ho, int Wo, int Wo16, int xrow) {
   extern __shared__ __align__(16) uint8_t wg_smem[];
-  // xs[3][3 + 3 W + 3] floats: three input rows with one zero pixel on either side; dys[Wo][32] bf16
-  const int xrow = 3 * W + 6;
-  float* xs = reinterpret_cast<float*>(wg_smem);
-  __nv_bfloat16* dys = reinterpret_cast<__nv_bfloat16*>(wg_smem + ((3 * xrow * 4 + 15) / 16) * 16);
+  // xs[3][xrow] bf16: three input rows; the data start at element 8 (16-byte aligned: vector copies), the elements
+  // 5..7 in front of it are pixel -1 (zero), zeros behind the row;  pixel w, channel c  ->  element 8 + 3 w + c
+  // dys[Wo16][32] bf16: one row of dY, zero beyond Wo;  red[32 taps][32 co] fp32
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(wg_smem);
+  __nv_bfloat16* dys = xs + 3 * xrow;
+  float* red = reinterpret_cast<float*>(dys + Wo16 * kCout);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tap = lane < kTaps ? lane : 0;
-  const int r = tap / 9, sc = tap % 9;                 // sc = s * 3 + c
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < 32 * kCout; i += kWgThreads) red[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * xrow; i += kWgThreads) xs[i] = __float2bfloat16(0.f);   // halo + tail stay zero
+  for (int i = threadIdx.x; i < Wo16 * kCout; i += kWgThreads) dys[i] = __float2bfloat16(0.f);   // the tail beyond Wo stays 0
+  float acc[2][4][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  // this lane's B-fragment geometry: tap n = nt * 8 + lane / 4 -> (r, sc = 3 s + c); pixel k0 = (lane % 4) * 2
+  int boff[4];
+  bool bval[4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int tap = nt * 8 + (lane >> 2);
+    bval[nt] = tap < kTaps;
+    const int t = bval[nt] ? tap : 0;
+    boff[nt] = (t / 9) * xrow + (t % 9) + 5 + 6 * ((lane & 3) * 2);   // 8 + 3 (2 p + s - 1) + c = 6 p + (3 s + c) + 5
+  }
+  const uint32_t dys_addr = static_cast<uint32_t>(__cvta_generic_to_shared(dys));
+  // ldmatrix.trans lane address: tile t = lane / 8 -> pixels (t >> 1) * 8 + lane % 8, channels (t & 1) * 8
+  const uint32_t a_lane = (uint32_t)((((lane >> 4) & 1) * 8 + (lane & 7)) * kCout + ((lane >> 3) & 1) * 8) * 2u;
   const int rows = N * Ho;
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int n = row / Ho, ho = row - n * Ho;
     __syncthreads();                                   // the previous row's tiles are no longer read
-    for (int i = threadIdx.x; i < 3 * xrow; i += kWgThreads) {
-      const int rr = i / xrow, j = i - rr * xrow;      // j = 3 + 3 * w + c  (w = -1 .. W)
-      const int h = 2 * ho + rr - 1;
-      const int wc = j - 3;
-      float v = 0.f;
-      if (h >= 0 && h < H && wc >= 0 && wc < 3 * W) v = __bfloat162float(x[((int64_t)n * H + h) * W * 3 + wc]);
-      xs[i] = v;
+    {
+      // 3 W bf16 per input row = a whole number of 16-byte vectors for even W % 8 == 0 rows (224: 84 vectors); the
+      // general case copies the remainder element-wise.  Everything outside [8, 8 + 3 W) was zeroed once below.
+      const int vec_per_row = (W % 8 == 0) ? (3 * W) / 8 : 0;       // 16-byte aligned rows only
+      for (int i = threadIdx.x; i < 3 * vec_per_row; i += kWgThreads) {
+        const int rr = i / vec_per_row, j = i - rr * vec_per_row;
+        const int h = 2 * ho + rr - 1;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (h >= 0 && h < H) v = *reinterpret_cast<const int4*>(x + ((int64_t)n * H + h) * W * 3 + j * 8);
+        *reinterpret_cast<int4*>(xs + rr * xrow + 8 + j * 8) = v;
+      }
+      const int rem0 = vec_per_row * 8, rem = 3 * W - rem0;
+      for (int i = threadIdx.x; i < 3 * rem; i += kWgThreads) {
+        const int rr = i / rem, j = rem0 + (i - rr * rem);
+        const int h = 2 * ho + rr - 1;
+        xs[rr * xrow + 8 + j] = (h >= 0 && h < H) ? x[((int64_t)n * H + h) * W * 3 + j] : __float2bfloat16(0.f);
+      }
     }
     const int4* src = reinterpret_cast<const int4*>(dy + (int64_t)row * Wo * kCout);
     int4* dst = reinterpret_cast<int4*>(dys);
     for (int i = threadIdx.x; i < Wo * kCout / 8; i += kWgThreads) dst[i] = src[i];
     __syncthreads();
-    const float* xr = xs + r * xrow + sc;              // + 6 * wo: input column 2 wo + s - 1, channel c
-    const __nv_bfloat16* dr = dys + warp * 8;
-#pragma unroll 4
-    for (int wo = 0; wo < Wo; ++wo) {
-      const float xv = xr[6 * wo];
-      float g[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(dr + wo * kCout), g);
+    for (int chunk = warp; chunk * 16 < Wo16; chunk += kWgThreads / 32) {
+      const int p0 = chunk * 16;
+      uint32_t a[2][4];
+      ldmatrix_x4_trans(a[0], dys_addr + (uint32_t)(p0 * kCout) * 2u + a_lane);
+      ldmatrix_x4_trans(a[1], dys_addr + (uint32_t)(p0 * kCout + 16) * 2u + a_lane);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = fmaf(g[k], xv, acc[k]);
+      for (int nt = 0; nt < 4; ++nt) {
+        const unsigned short* xp = reinterpret_cast<const unsigned short*>(xs) + boff[nt] + 6 * p0;
+        uint32_t b0 = 0u, b1 = 0u;
+        if (bval[nt]) {
+          b0 = (uint32_t)xp[0] | ((uint32_t)xp[6] << 16);            // pixels k0, k0 + 1
+          b1 = (uint32_t)xp[48] | ((uint32_t)xp[54] << 16);          // pixels k0 + 8, k0 + 9
+        }
+        mma_bf16_16816(acc[0][nt], a[0], b0, b1);
+        mma_bf16_16816(acc[1][nt], a[1], b0, b1);
+      }
     }
   }
-  if (lane < kTaps) {
-    float* dst = ws + tap * kCout + warp * 8;
-    red_add_v4(dst, acc[0], acc[1], acc[2], acc[3]);
-    red_add_v4(dst + 4, acc[4], acc[5], acc[6], acc[7]);
+  // accumulator (mt, nt, i): co = mt * 16 + lane / 4 + (i >= 2 ? 8 : 0), tap = nt * 8 + (lane % 4) * 2 + (i & 1)
+  __syncthreads();
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int co = mt * 16 + (lane >> 2) + ((i & 2) ? 8 : 0);
+        const int tap = nt * 8 + (lane & 3) * 2 + (i & 1);
+        atomicAdd(&red[tap * kCout + co], acc[mt][nt][i]);
+      }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kTaps * kCout / 4; i += kWgThreads) {
+    const float4 v = reinterpret_cast<const float4*>(red)[i];
+    red_add_v4(ws + i * 4, v.x, v.y, v.z, v.w);
   }
   __shared__ int s_last;
   __threadfence();
@@ -226,7 +290,11 @@ const char* stem_wgrad(const void* x, const void* dy, float* ws, int* counter, v
                        int W, cudaStream_t stream) {
   if ((H & 1) || (W & 1)) return "stem_wgrad: even input sizes only";
   const int Ho = H / 2, Wo = W / 2;
-  const size_t smem = ((3 * (3 * W + 6) * 4 + 15) / 16) * 16 + (size_t)Wo * kCout * 2;
+  const int Wo16 = (Wo + 15) / 16 * 16;
+  int xrow = 6 * Wo16 + 24;                            // covers index 6 * (Wo16 - 1) + 8 + 5 + 54 ... and 8 + 3 W
+  if (xrow < 3 * W + 16) xrow = 3 * W + 16;
+  xrow = (xrow + 63) / 8 * 8;
+  const size_t smem = (size_t)3 * xrow * 2 + (size_t)Wo16 * kCout * 2 + 32 * kCout * 4;
   if (smem > 200 * 1024) return "stem_wgrad: image too wide";
   static bool attr_set = false;
   if (!attr_set) {
@@ -238,7 +306,7 @@ const char* stem_wgrad(const void* x, const void* dy, float* ws, int* counter, v
   if (grid > N * Ho) grid = N * Ho;
   stem_wgrad_kernel<<<grid, kWgThreads, smem, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), ws, counter,
-      reinterpret_cast<__nv_bfloat16*>(dw), accumulate ? 1 : 0, N, H, W, Ho, Wo);
+      reinterpret_cast<__nv_bfloat16*>(dw), accumulate ? 1 : 0, N, H, W, Ho, Wo, Wo16, xrow);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

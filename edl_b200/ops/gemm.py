@@ -113,15 +113,33 @@ def _split_k_for(m, n, k):
 
 
 _WS = {}
-_SIDE = {"stream": None, "keep": []}
+_SIDE = {"stream": None, "streams": [], "next": 0, "keep": []}
 
 
 def set_wgrad_stream(stream):
     """Run weight-gradient GEMMs on ``stream`` (the DP engine passes its communication stream): they
     then overlap the dgrad / BN-backward chain of the main stream, and the bucket all-reduces that
     follow on the same stream are naturally ordered behind them.  ``None`` disables the overlap."""
-    _SIDE["stream"] = stream
+    if isinstance(stream, (list, tuple)):
+        _SIDE["streams"] = [st for st in stream if st is not None]
+        _SIDE["stream"] = _SIDE["streams"][0] if _SIDE["streams"] else None
+    else:
+        _SIDE["stream"] = stream
+        _SIDE["streams"] = [stream] if stream is not None else []
+    _SIDE["next"] = 0
     _SIDE["keep"].clear()
+
+
+def _side_stream():
+    """The next weight-gradient stream (round-robin over the engine's side streams): consecutive layers' weight
+    gradients are independent, two of them in flight shorten the side-stream tail that remains after the last
+    dgrad of backward (profiles/timeline_r2: conv1_2 wgrad -> stem wgrad -> last optimizer bucket, 190 us serial)."""
+    sts = _SIDE["streams"]
+    if not sts:
+        return None
+    st = sts[_SIDE["next"] % len(sts)]
+    _SIDE["next"] += 1
+    return st
 
 
 def release_wgrad_keepalive():
@@ -173,7 +191,7 @@ def _wgrad(dy2, x2, weight_shape, sink, ready):
         return None
     cout, cin = dy2.shape[1], x2.shape[1]
     split = _split_k_for(cout, cin, dy2.shape[0])
-    side = _SIDE["stream"] if (dy2.is_cuda and sink is not None) else None
+    side = _side_stream() if (dy2.is_cuda and sink is not None) else None
     if side is not None:
         cur = torch.cuda.current_stream(dy2.device)
         ev = torch.cuda.Event()
@@ -333,6 +351,21 @@ def linear_bf16(x, weight, bias=None, relu=False):
     return _LinearFn.apply(x, weight, bias, relu, sink, ready, bsink, bready)
 
 
+# EDL_PAIR_WGRAD=0: the library's weight gradient for the 32-channel stem convolutions as well
+PAIR_WGRAD = __import__("os").environ.get("EDL_PAIR_WGRAD", "1") == "1"
+
+
+def _pair_wgrad_ok(x, dy, w, cfg) -> bool:
+    from . import native
+
+    if not (PAIR_WGRAD and x.is_cuda and x.dtype == torch.bfloat16 and tuple(cfg) == (1, 1, 1) and w.dim() == 4):
+        return False
+    cout, kh, kw, cin = w.shape
+    n, c, h, wd = x.shape
+    return (kh == 3 and kw == 3 and cin == 32 and c == 32 and wd % 2 == 0 and cout % 32 == 0
+            and native().conv3x3_wgrad_supported(n, h, wd // 2, 64, 2 * cout))
+
+
 def _count_lib_conv(x, what, w_krsc, stride, groups):
     if x.is_cuda:
         from . import count_fallback
@@ -374,10 +407,26 @@ class _ConvLibFn(torch.autograd.Function):
         dw = None
         if ctx.needs_input_grad[1]:
             sink, ready = ctx.sink, ctx.ready
-            side = _SIDE["stream"] if (dy.is_cuda and sink is not None) else None
+            side = _side_stream() if (dy.is_cuda and sink is not None) else None
 
             def wgrad():
                 if _SKIP_WGRAD and sink is not None:
+                    if ready is not None:
+                        ready()
+                    return None
+                if _pair_wgrad_ok(x, dy, w, ctx.cfg):
+                    # 32-input-channel 3x3 / stride 1 layer (the stem's conv1_2 / conv1_3): weight gradient in pixel-pair
+                    # form on the tcgen05 kernel even when fprop / dgrad stay on the library (the library's wgrad of
+                    # these two layers takes 100-110 us each and is the END of backward: profiles/timeline_r2)
+                    from . import native, count_launch
+                    xc, dyc = _cl(x), _cl(dy)
+                    x2, dy2 = _pair_view(xc), _pair_view(dyc)
+                    dw2 = conv3x3_wgrad(x2, dy2, (2 * w.shape[0], 3, 3, 64), None)
+                    out = sink.view(w.shape) if sink is not None else torch.empty_like(w)
+                    native().pair_weight_fold(dw2, out, sink is not None)
+                    count_launch()
+                    if sink is None:
+                        return out
                     if ready is not None:
                         ready()
                     return None
@@ -464,7 +513,7 @@ class _Conv3x3Fn(torch.autograd.Function):
         dw = None
         if ctx.needs_input_grad[1]:
             sink, ready = ctx.sink, ctx.ready
-            side = _SIDE["stream"] if sink is not None else None
+            side = _side_stream() if sink is not None else None
             own = OWN_WGRAD3 and conv3x3_wgrad_supported(x, w)
 
             def wgrad():
@@ -648,7 +697,7 @@ class _Conv3x3S2Fn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             if _s2_wgrad_supported(x, w):
                 sink, ready = ctx.sink, ctx.ready
-                side = _SIDE["stream"] if sink is not None else None
+                side = _side_stream() if sink is not None else None
 
                 def wgrad():
                     out = conv3x3_wgrad(x, dy, w.shape, sink)
@@ -733,7 +782,7 @@ class _StemConvFn(torch.autograd.Function):
                 dw = _ConvLibFn.backward(_NeedsOnlyWeight(ctx, ctx.needs_input_grad), dy)[1]
                 return dx, dw, None, None, None
             sink, ready = ctx.sink, ctx.ready
-            side = _SIDE["stream"] if sink is not None else None
+            side = _side_stream() if sink is not None else None
 
             def wgrad():
                 if _SKIP_WGRAD and sink is not None:
@@ -837,7 +886,7 @@ class _Conv3x3PairFn(torch.autograd.Function):
         dw = None
         if ctx.needs_input_grad[1]:
             sink, ready = ctx.sink, ctx.ready
-            side = _SIDE["stream"] if sink is not None else None
+            side = _side_stream() if sink is not None else None
 
             def wgrad():
                 if _SKIP_WGRAD and sink is not None:

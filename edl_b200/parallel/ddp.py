@@ -71,7 +71,7 @@ class Bucket:
     fused_opt: bool = False    # the bucket kernel also runs the optimizer (and, on > 1 rank, all-gathers parameters)
 
 
-def plan_buckets(flat: FlatParams, cap_bytes: int) -> List[Bucket]:
+def plan_buckets(flat: FlatParams, cap_bytes: int, tail_bytes: int = 512 * 1024) -> List[Bucket]:
     """Cut each dtype group's flat gradient into contiguous buckets of ~cap_bytes.
 
     Flat layout is reverse registration order, so entry 0 of a group is the *last* layer: buckets are
@@ -82,15 +82,25 @@ def plan_buckets(flat: FlatParams, cap_bytes: int) -> List[Bucket]:
     order_of: Dict[int, int] = {i: e.order for i, (_, e) in enumerate(flat.entries())}
     for g in flat.groups.values():
         esz = g.grad.element_size()
+        # the LAST bucket (the first layers' parameters, whose gradients are produced at the very end of backward) is
+        # kept small: its reduction / optimizer kernel cannot overlap anything and is exposed 1 : 1 at the end of the step
+        tail_from = len(g.entries)
+        if tail_bytes > 0 and len(g.entries) > 1 and g.numel * esz > 8 * tail_bytes:
+            acc = 0
+            while tail_from > 1 and acc < tail_bytes:
+                tail_from -= 1
+                acc += g.entries[tail_from].numel * esz
+            if acc >= cap_bytes or tail_from <= 0:
+                tail_from = len(g.entries)            # the group is small anyway: one greedy pass
         cur: Optional[Bucket] = None
-        for e in g.entries:
+        for idx, e in enumerate(g.entries):
             if cur is None:
                 cur = Bucket(dtype=g.dtype, start=e.offset, numel=0)
             cur.entry_ids.append(eid)
             cur.numel = e.offset + e.numel - cur.start
             cur.order = max(cur.order, order_of[eid])
             eid += 1
-            if cur.numel * esz >= cap_bytes:
+            if cur.numel * esz >= cap_bytes or idx + 1 == tail_from:
                 buckets.append(cur)
                 cur = None
         if cur is not None:
@@ -211,6 +221,9 @@ class ElasticDataParallel:
             # reduced, and must not take SMs from the dgrad / BN-backward chain of the main stream
             self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
             self.wgrad_stream = torch.cuda.Stream(device=self.device, priority=0)
+            # a second one: the weight gradients of consecutive layers alternate between the two (ops/gemm.py)
+            self.wgrad_stream2 = (torch.cuda.Stream(device=self.device, priority=0)
+                                  if os.environ.get("EDL_WGRAD_STREAMS", "2") == "2" else None)
             self._main_stream = None
             self._comm_used = False
 
@@ -372,7 +385,8 @@ class ElasticDataParallel:
         """The bucket's gradients were written on the main stream (BN, pools, ...) and on the weight-gradient
         stream: whatever consumes them on the communication stream waits for both."""
         for st in {torch.cuda.current_stream(self.device), self._main_stream,
-                   self.wgrad_stream if self.overlap_wgrad else None}:
+                   self.wgrad_stream if self.overlap_wgrad else None,
+                   self.wgrad_stream2 if self.overlap_wgrad else None}:
             if st is not None and st != self.comm_stream:
                 ev = torch.cuda.Event()
                 ev.record(st)
@@ -482,7 +496,8 @@ class ElasticDataParallel:
         cuda = self.device.type == "cuda"
         if cuda:
             for st in {torch.cuda.current_stream(self.device), self._main_stream,
-                       self.wgrad_stream if self.overlap_wgrad else None}:
+                       self.wgrad_stream if self.overlap_wgrad else None,
+                       self.wgrad_stream2 if self.overlap_wgrad else None}:
                 if st is not None and st != self.comm_stream:
                     ev = torch.cuda.Event()
                     ev.record(st)
@@ -517,6 +532,8 @@ class ElasticDataParallel:
                     cur.wait_stream(self.comm_stream)
                 if self.overlap_wgrad:
                     cur.wait_stream(self.wgrad_stream)
+                    if self.wgrad_stream2 is not None:
+                        cur.wait_stream(self.wgrad_stream2)
                 from ..ops import gemm as _gemm
                 _gemm.release_wgrad_keepalive()
             for w, view, scale in self._works:
@@ -569,6 +586,8 @@ class ElasticDataParallel:
                     cur.wait_stream(self.comm_stream)
                 if self.overlap_wgrad:
                     cur.wait_stream(self.wgrad_stream)
+                    if self.wgrad_stream2 is not None:
+                        cur.wait_stream(self.wgrad_stream2)
             self.sqnorm.zero_()
             for g in self.flat.groups.values():
                 C.grad_sqnorm(g.grad, self.sqnorm)
@@ -667,7 +686,9 @@ class ElasticDataParallel:
             self._comm_used = False
             if self.overlap_wgrad:
                 self.wgrad_stream.wait_stream(self._main_stream)
-                _gemm.set_wgrad_stream(self.wgrad_stream)
+                if self.wgrad_stream2 is not None:
+                    self.wgrad_stream2.wait_stream(self._main_stream)
+                _gemm.set_wgrad_stream([self.wgrad_stream, self.wgrad_stream2])
             else:
                 _gemm.set_wgrad_stream(None)
             if self.found_inf is not None:

@@ -449,7 +449,7 @@ def test_fused_bn_backward_matches_unfused_at_model_level(monkeypatch, mode):
     assert not bad, bad[:8]
 
 
-@pytest.mark.parametrize("n,h,w", [(4, 224, 224), (3, 64, 96), (2, 33, 47)])
+@pytest.mark.parametrize("n,h,w", [(4, 224, 224), (3, 64, 96), (2, 33, 47), (2, 40, 56), (5, 18, 36)])
 def test_stem_conv_direct_kernel(n, h, w):
     """EDL_OWN_STEM1: 3 -> 32 channel 3x3 / stride 2 stem convolution on the direct kernel with fused BN statistics."""
     torch.manual_seed(0)
