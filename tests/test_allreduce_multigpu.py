@@ -266,3 +266,28 @@ def test_allreduce_kernels_and_engine(world):
         p.join(60)
     assert status == "ok", payload
     print(payload)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("leave", ["scale_in", "kill"])
+def test_inplace_rescale_through_the_launcher_on_gpus(tmp_path, leave):
+    """BASELINE config 4 in miniature: ResNet50_vd, pod A = GPU 0, pod B = GPU 1, the real launcher, in-place mode with the
+    fabric backend (no process group, no NCCL): B joins, then leaves by the leader's ScaleIn RPC or dies by SIGKILL; the
+    survivor's trainer must keep its process both times (hot recovery in the SIGKILL case)."""
+    import json
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "elastic.json")
+    env = dict(os.environ, EDL_COMM_TIMEOUT="5")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "bench_elastic_launch.py"), "--native-store",
+                        "--trainer", "resnet", "--gpus-per-pod", "1", "--leave", leave, "--modes", "inplace", "--out", out],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    run = json.load(open(out))["runs"][0]
+    assert "error" not in run, run
+    assert run["survivor_process_kept"] is True, run
+    assert run["leave_stall_s"] < (15.0 if leave == "kill" else 5.0), run

@@ -148,11 +148,12 @@ if __name__ == "__main__":
                     help="how pod B leaves: the leader's ScaleIn RPC, SIGTERM to its launcher (graceful leave), or SIGKILL "
                          "of launcher and trainers (hot recovery in place / restart of everybody in restart mode)")
     ap.add_argument("--out", default="")
+    ap.add_argument("--modes", default="restart,inplace", help="comma-separated subset of restart,inplace")
     args = ap.parse_args()
     CFG.update(trainer=args.trainer, gpus_per_pod=args.gpus_per_pod, leave=args.leave)
     cls = NativeKVServer if args.native_store else KVServer
     res = []
-    for mode in ("restart", "inplace"):
+    for mode in [m for m in args.modes.split(",") if m]:
         try:
             res.append(run(mode, cls))
         except Exception as e:  # noqa: BLE001 - the other mode is still worth measuring
