@@ -101,49 +101,52 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
   if (num_kb > 0) {
     if (warp == 0) {
       // ------------------------------------------------------------ TMA producer
-      if (lane == 0) {
-        for (int i = 0; i < num_kb; ++i) {
-          const int st = i % kStages;
-          const uint32_t ph = (i / kStages) & 1;
-          ptx::mbar_wait(&empty_bar[st], ph ^ 1);
-          uint8_t* sa = smem + st * kStageBytes;
-          uint8_t* sb = sa + 2 * kChunkBytes;
+      // warp-uniform loop, one elected lane issues (gemm_persist.cu explains why not `if (lane == 0)` around the loop)
+      for (int i = 0; i < num_kb; ++i) {
+        const int st = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        ptx::mbar_wait(&empty_bar[st], ph ^ 1);
+        uint8_t* sa = smem + st * kStageBytes;
+        uint8_t* sb = sa + 2 * kChunkBytes;
+        const int kb = kb_begin + i;
+        const int h0 = (kb % p.HB) * p.BH;
+        const int img0 = (kb / p.HB) * p.NB;
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full_bar[st], chunk_tx * (two_chunks ? 5u : 4u));
-          const int kb = kb_begin + i;
-          const int h0 = (kb % p.HB) * p.BH;
-          const int img0 = (kb / p.HB) * p.NB;
           ptx::tma_load_4d(sa, &tmDy, &full_bar[st], m0, 0, h0, img0);
           if (two_chunks) ptx::tma_load_4d(sa + kChunkBytes, &tmDy, &full_bar[st], m0 + 64, 0, h0, img0);
 #pragma unroll
           for (int s = 0; s < 3; ++s)
             ptx::tma_load_4d(sb + s * kChunkBytes, &tmX, &full_bar[st], n0, s - 1, h0 * p.stride + r - 1, img0);
         }
+        __syncwarp();
       }
     } else if (warp == 1) {
       // ------------------------------------------------------------ MMA issuer (one thread)
-      if (lane == 0) {
-        constexpr uint32_t idesc = ptx::make_idesc(1, 1, kBlockM, kBlockN, 1, 1);
-        const int ksteps = p.KB / kUmmaK;
-        for (int i = 0; i < num_kb; ++i) {
-          const int st = i % kStages;
-          const uint32_t ph = (i / kStages) & 1;
-          ptx::mbar_wait(&full_bar[st], ph);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + st * kStageBytes);
-          const uint32_t sb = sa + 2 * kChunkBytes;
+      constexpr uint32_t idesc = ptx::make_idesc(1, 1, kBlockM, kBlockN, 1, 1);
+      const int ksteps = p.KB / kUmmaK;
+      for (int i = 0; i < num_kb; ++i) {
+        const int st = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        ptx::mbar_wait(&full_bar[st], ph);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + st * kStageBytes);
+        const uint32_t sb = sa + 2 * kChunkBytes;
+        // MN-major, 128B swizzle: 16 pixel rows = 2048 B per UMMA_K step (128 in the descriptor's 16-byte units),
+        // 8-row groups 1024 B apart, the second 64-channel chunk of A one ring chunk further
+        const uint64_t da0 = ptx::make_smem_desc(sa, kChunkBytes, 1024);
+        const uint64_t db0 = ptx::make_smem_desc(sb, kChunkBytes, 1024);
+        if (ptx::elect_one()) {
           for (int k = 0; k < ksteps; ++k) {
-            // MN-major, 128B swizzle: 16 pixel rows = 2048 B per UMMA_K step, 8-row groups 1024 B apart,
-            // the second 64-channel chunk of A one ring chunk further
-            const uint64_t da = ptx::make_smem_desc(sa + k * 2048, kChunkBytes, 1024);
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-              const uint64_t db = ptx::make_smem_desc(sb + s * kChunkBytes + k * 2048, kChunkBytes, 1024);
-              ptx::umma_f16(tmem_base + s * kBlockN, da, db, idesc, (i | k) != 0 ? 1u : 0u);
-            }
+            for (int s = 0; s < 3; ++s)
+              ptx::umma_f16(tmem_base + s * kBlockN, da0 + (uint64_t)(k * 128),
+                            db0 + (uint64_t)(s * (kChunkBytes >> 4) + k * 128), idesc, (i | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[st]);
+          if (i == num_kb - 1) ptx::umma_commit(tmem_full_bar);
         }
-        ptx::umma_commit(tmem_full_bar);
+        __syncwarp();
       }
     } else {
       // ------------------------------------------------------------ epilogue (warps 2..5)
@@ -343,35 +346,36 @@ conv3x3_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
 
   if (num_kb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        for (int i = 0; i < num_kb; ++i) {
-          const int st = i % kStages2;
-          const uint32_t ph = (i / kStages2) & 1;
-          ptx::mbar_wait(&empty_bar[st], ph ^ 1);
-          uint8_t* sa = smem + st * L::kStage;
-          uint8_t* sb = sa + 2 * kChunkA2;
+      for (int i = 0; i < num_kb; ++i) {
+        const int st = i % kStages2;
+        const uint32_t ph = (i / kStages2) & 1;
+        ptx::mbar_wait(&empty_bar[st], ph ^ 1);
+        uint8_t* sa = smem + st * L::kStage;
+        uint8_t* sb = sa + 2 * kChunkA2;
+        const int kb = kb_begin + i;
+        const int h0 = (kb % p.HB) * p.BH;
+        const int img0 = (kb / p.HB) * p.NB;
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full_bar[st], chunk_tx * (uint32_t)((two_chunks ? 2 : 1) + L::kNCh));
-          const int kb = kb_begin + i;
-          const int h0 = (kb % p.HB) * p.BH;
-          const int img0 = (kb / p.HB) * p.NB;
           ptx::tma_load_4d(sa, &tmDy, &full_bar[st], m0, -1, h0, img0);
           if (two_chunks) ptx::tma_load_4d(sa + kChunkA2, &tmDy, &full_bar[st], m0 + 64, -1, h0, img0);
 #pragma unroll
           for (int c = 0; c < L::kNCh; ++c)
             ptx::tma_load_4d(sb + c * kChunkB2 + kPad2, &tmX, &full_bar[st], n0 + c * 64, -1, h0 + r - 1, img0);
         }
+        __syncwarp();
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = ptx::make_idesc(1, 1, kBlockM, BLOCK_N, 1, 1);
-        const int ksteps = p.KB / kUmmaK;
-        for (int i = 0; i < num_kb; ++i) {
-          const int st = i % kStages2;
-          const uint32_t ph = (i / kStages2) & 1;
-          ptx::mbar_wait(&full_bar[st], ph);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + st * L::kStage);
-          const uint32_t sb = sa + 2 * kChunkA2 + kPad2;
+      constexpr uint32_t idesc = ptx::make_idesc(1, 1, kBlockM, BLOCK_N, 1, 1);
+      const int ksteps = p.KB / kUmmaK;
+      for (int i = 0; i < num_kb; ++i) {
+        const int st = i % kStages2;
+        const uint32_t ph = (i / kStages2) & 1;
+        ptx::mbar_wait(&full_bar[st], ph);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + st * L::kStage);
+        const uint32_t sb = sa + 2 * kChunkA2 + kPad2;
+        if (ptx::elect_one()) {
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t da = ptx::make_smem_desc(sa + k * 2048, kChunkA2, 1024);
 #pragma unroll
@@ -383,8 +387,9 @@ conv3x3_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
             }
           }
           ptx::umma_commit(&empty_bar[st]);
+          if (i == num_kb - 1) ptx::umma_commit(tmem_full_bar);
         }
-        ptx::umma_commit(tmem_full_bar);
+        __syncwarp();
       }
     } else {
       const int q = warp & 3;

@@ -113,15 +113,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (num_kb > 0) {
     if (warp == 0) {
       // ------------------------------------------------------------ TMA producer
-      if (lane == 0) {
-        for (int i = 0; i < num_kb; ++i) {
-          const int s = i % STAGES;
-          const uint32_t ph = (i / STAGES) & 1;
-          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * L::kStageBytes;
-          uint8_t* sb = sa + L::kABytes;
+      // warp-uniform loop, one elected lane issues (see gemm_persist.cu: loops under `if (lane == 0)` cost a vote +
+      // broadcast sequence per uniform-register operand)
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * L::kStageBytes;
+        uint8_t* sb = sa + L::kABytes;
+        const int k0 = (kb_begin + i) * BLOCK_K;
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
-          const int k0 = (kb_begin + i) * BLOCK_K;
           if (!A_MN) {
             ptx::tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
           } else {
@@ -137,30 +139,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               ptx::tma_load_2d(sb + h * 8192, &tmB, &full_bar[s], n0 + h * 64, k0);
           }
         }
+        __syncwarp();
       }
     } else if (warp == 1) {
-      // ------------------------------------------------------------ MMA issuer (one thread)
-      if (lane == 0) {
-        constexpr uint32_t idesc =
-            ptx::make_idesc(1, 1, BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
-        for (int i = 0; i < num_kb; ++i) {
-          const int s = i % STAGES;
-          const uint32_t ph = (i / STAGES) & 1;
-          ptx::mbar_wait(&full_bar[s], ph);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + s * L::kStageBytes);
-          const uint32_t sb = sa + L::kABytes;
+      // ------------------------------------------------------------ MMA issuer (one elected lane, warp-uniform loop)
+      constexpr uint32_t idesc = ptx::make_idesc(1, 1, BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        ptx::mbar_wait(&full_bar[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + s * L::kStageBytes);
+        const uint32_t sb = sa + L::kABytes;
+        // one descriptor per operand and stage; a k step adds 32 bytes (K-major) or 2048 bytes (MN-major) to the start
+        // address field, which counts 16-byte units
+        const uint64_t da0 = A_MN ? ptx::make_smem_desc(sa, 8192, 1024) : ptx::make_smem_desc(sa, 16, 1024);
+        const uint64_t db0 = B_MN ? ptx::make_smem_desc(sb, 8192, 1024) : ptx::make_smem_desc(sb, 16, 1024);
+        if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = A_MN ? ptx::make_smem_desc(sa + k * 2048, 8192, 1024)
-                                     : ptx::make_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? ptx::make_smem_desc(sb + k * 2048, 8192, 1024)
-                                     : ptx::make_smem_desc(sb + k * 32, 16, 1024);
-            ptx::umma_f16(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            ptx::umma_f16(tmem_base, da0 + (uint64_t)(k * (A_MN ? 128 : 2)), db0 + (uint64_t)(k * (B_MN ? 128 : 2)), idesc,
+                          (i | k) != 0 ? 1u : 0u);
           ptx::umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs have read it
+          if (i == num_kb - 1) ptx::umma_commit(tmem_full_bar);  // accumulator complete
         }
-        ptx::umma_commit(tmem_full_bar);  // accumulator complete
+        __syncwarp();
       }
     } else {
       // ------------------------------------------------------------ epilogue (warps 2..5)

@@ -131,6 +131,14 @@ void set_bnr_mode(int mode);   // fused BN-backward reduction: 1 = shuffle trans
 int get_bnr_mode();
 void set_persistent_gemm(bool on);
 bool persistent_gemm_enabled();
+// CTA-pair (cta_group::2) 256 x 256 tiles for the inference GEMMs (gemm_2cta.cu; default on, EDL_GEMM_PAIR=0)
+bool gemm_pair_supported(const GemmArgs& args);
+const char* gemm_bf16_pair(const GemmArgs& args, cudaStream_t stream);
+void set_pair_gemm(bool on);
+bool get_pair_gemm();
+void set_conv_halo(bool on);         // haloed A tiles for the 3x3 / stride 1 fprop and dgrad (default on; EDL_CONV_HALO=0)
+bool get_conv_halo();
+void set_conv_resident_weights(bool on);   // 64-channel layers / groups: weights resident across a CTA's run of tiles (EDL_CONV_BRES=0)
 void set_wide_gemm_tiles(bool on);   // 128 x 256 tiles for large-N inference GEMMs (default on; EDL_GEMM_WIDE=0)
 const char* gemm_bf16_persistent(const GemmArgs& args, cudaStream_t stream);
 const char* conv3x3_dgrad_s2_persistent(const Conv3x3Args& args, int BH, int BN, int tiles_h, int tiles_img,

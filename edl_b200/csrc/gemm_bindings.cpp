@@ -385,6 +385,11 @@ void register_gemm_bindings(pybind11::module_& m) {
   m.def("conv3x3_wgrad_kblocks", &edl::conv3x3_wgrad_kblocks);
   m.def("conv3x3_wgrad_ctas", &edl::conv3x3_wgrad_ctas);
   m.def("set_wide_gemm_tiles", &edl::set_wide_gemm_tiles);
+  m.def("set_pair_gemm", &edl::set_pair_gemm);
+  m.def("get_pair_gemm", &edl::get_pair_gemm);
+  m.def("set_conv_halo", &edl::set_conv_halo);
+  m.def("get_conv_halo", &edl::get_conv_halo);
+  m.def("set_conv_resident_weights", &edl::set_conv_resident_weights);
   m.def("set_wgrad3_version", &edl::set_wgrad3_version);
   m.def("get_wgrad3_version", &edl::get_wgrad3_version);
   m.def("conv3x3_wgrad_plan", &conv3x3_wgrad_plan);

@@ -78,34 +78,38 @@ gemm_fp8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * L::kStageBytes;
+    // warp-uniform loops, one elected lane issues (see gemm_persist.cu)
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* sa = smem + s * L::kStageBytes;
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
         ptx::tma_load_2d(sa, &tmA, &full_bar[s], i * kBlockKBytes, m0);
         ptx::tma_load_2d(sa + L::kABytes, &tmB, &full_bar[s], i * kBlockKBytes, n0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc(0, 0, kBlockM, BLOCK_N, 0, 0);   // e4m3 x e4m3, K-major
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
-        ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + s * L::kStageBytes);
-        const uint32_t sb = sa + L::kABytes;
+    constexpr uint32_t idesc = ptx::make_idesc(0, 0, kBlockM, BLOCK_N, 0, 0);   // e4m3 x e4m3, K-major
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      ptx::mbar_wait(&full_bar[s], ph);
+      ptx::tc_fence_after();
+      const uint32_t sa = ptx::smem_u32(smem + s * L::kStageBytes);
+      const uint64_t da0 = ptx::make_smem_desc(sa, 16, 1024);
+      const uint64_t db0 = ptx::make_smem_desc(sa + L::kABytes, 16, 1024);
+      if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kBlockKBytes / kUmmaKBytes; ++k)
-          ptx::umma_f8(tmem_base, ptx::make_smem_desc(sa + k * kUmmaKBytes, 16, 1024),
-                       ptx::make_smem_desc(sb + k * kUmmaKBytes, 16, 1024), idesc, (i | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < kBlockKBytes / kUmmaKBytes; ++k)     // start-address field counts 16-byte units
+          ptx::umma_f8(tmem_base, da0 + (uint64_t)(k * (kUmmaKBytes >> 4)), db0 + (uint64_t)(k * (kUmmaKBytes >> 4)), idesc,
+                       (i | k) != 0 ? 1u : 0u);
         ptx::umma_commit(&empty_bar[s]);
+        if (i == num_kb - 1) ptx::umma_commit(tmem_full_bar);
       }
-      ptx::umma_commit(tmem_full_bar);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

@@ -59,6 +59,8 @@ struct PersistParams {
   int bn_relu, bn_has_y;
   // conv view (modes 2, 3)
   int n_img, H, W, kc_blocks, c_in_w, BH, BN, tiles_h;
+  int Wb;                         // halo layout: columns per image row of the A tile (W + 1)
+  int b_res;                      // halo layout, one k-block per tap: the nine B tap tiles stay resident (see kRes)
   int cin_g, cout_g;              // grouped fprop: channels per group (cout_g == N for a dense conv)
   int stride;                     // conv fprop: 1, or 2 (input rows 2*h + r - 1; the columns come from the tensor map)
   // explicit tap list (conv modes; 0 = the nine standard taps): k-block i belongs to tap i / kc_blocks, which reads the
@@ -68,13 +70,19 @@ struct PersistParams {
   signed char tap_dh[9], tap_dw[9], tap_w[9];
 };
 
-template <int BLOCK_N, int STAGES, int BNR = 0>
+// ASTAGES > 0 selects the "haloed A tile" layout of the 3x3 convolution modes (see the kernel): the A tiles (one per filter
+// ROW and k-block, 128 rows + a 1 KB zero pad on either side) and the B tiles (one per filter TAP) then live in two
+// separate rings of ASTAGES and STAGES slots.
+template <int BLOCK_N, int STAGES, int BNR = 0, int ASTAGES = 0>
 struct PSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kPad = 1024;
+  static constexpr int kARegion = kABytes + 2 * kPad;              // halo layout: pad | tile | pad
+  static constexpr int kARingBytes = ASTAGES * kARegion;
   static constexpr int kDBytes = kBlockM * BLOCK_N * 2;
-  static constexpr int kRingBytes = STAGES * kStageBytes;
+  static constexpr int kRingBytes = ASTAGES > 0 ? kARingBytes + STAGES * kBBytes : STAGES * kStageBytes;
   static constexpr int kStatsBytes = 2 * kMaxStatsN * 4;   // CTA-local per-channel (sum, sum^2) accumulators
   static constexpr int kXOffset = kRingBytes + kDBytes;           // BNR: BN input tile x, then BN output tile y
   static constexpr int kXYBytes = BNR ? 2 * kDBytes : 0;
@@ -82,7 +90,7 @@ struct PSmem {
   static constexpr int kConstBytes = BNR ? 4 * BLOCK_N * 4 : 0;    // float4 {mean, rstd, scale, shift} per column
   static constexpr int kStatsOffset = kConstOffset + kConstBytes;
   static constexpr int kBarOffset = kStatsOffset + kStatsBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;
+  static constexpr int kTotal = kBarOffset + 512 + 1024;
 };
 
 EDL_DEVICE void tma_store_4d_p(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
@@ -111,10 +119,8 @@ EDL_DEVICE float warp_colsum32(float (&v)[32], int lane) {
 
 // BNR: TMA loads of the BN input (and output) tile that belongs to output tile `tt`
 template <int BLOCK_N, bool CONV>
-EDL_DEVICE void issue_bn_tiles(const PersistParams& p, int tt, int rows_tile, uint8_t* sx, uint8_t* sy,
+EDL_DEVICE void issue_bn_tiles(const PersistParams& p, int tm, int nn0, int rows_tile, uint8_t* sx, uint8_t* sy,
                                const CUtensorMap* tmX, const CUtensorMap* tmY, uint64_t* bar) {
-  const int tm = tt / p.tiles_n;
-  const int nn0 = (tt - tm * p.tiles_n) * BLOCK_N;
   const int mm0 = tm * kBlockM;
   const int im0 = CONV ? (tm / p.tiles_h) * p.BN : 0;
   const int hh0 = CONV ? (tm % p.tiles_h) * p.BH : 0;
@@ -136,16 +142,33 @@ EDL_DEVICE void issue_bn_tiles(const PersistParams& p, int tt, int rows_tile, ui
   }
 }
 
-template <int BLOCK_N, int STAGES, int MODE, int BNR>
+template <int BLOCK_N, int STAGES, int MODE, int BNR, int ASTAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
                     const __grid_constant__ CUtensorMap tmBnX, const __grid_constant__ CUtensorMap tmBnY,
                     const PersistParams p) {
-  using L = PSmem<BLOCK_N, STAGES, BNR>;
+  using L = PSmem<BLOCK_N, STAGES, BNR, ASTAGES>;
   constexpr bool kConv = MODE >= 2;
   constexpr bool kBMN = MODE == 1 || MODE == 3;
   constexpr bool kDgrad = MODE == 3;
+  // Haloed A tiles (3x3 / stride 1 convolutions): the pixel box of a tile is loaded with one extra column on the LEFT
+  // (Wb = W + 1 columns starting at column -1, zero-filled by TMA), so tile row m = image_row * Wb + (w + 1) and the left /
+  // right neighbour of a pixel is simply tile row m -/+ 1: the right neighbour of the last pixel of an image row is the
+  // halo (zero) column of the next one.  The three taps of a filter row then read the SAME shared-memory tile through
+  // UMMA descriptors whose start address is shifted by -128 / 0 / +128 bytes (the 128-byte swizzle is a function of the
+  // shared-memory address, so whole-row shifts stay consistent with what TMA wrote; zero pads absorb the rows before
+  // the first / after the last).  One A tile per filter row instead of one per tap: a third of the A traffic from L2.
+  // The accumulator rows of the halo column are garbage and are dropped when the epilogue compacts the tile into the
+  // dense [BN][BH][W] staging layout, so statistics, the fused BN-backward reduction and the TMA store are unchanged.
+  constexpr bool kHalo = ASTAGES > 0;
+  static_assert(!kHalo || (kConv && BNR != 1), "halo tiles: conv modes, BNR 0 or 2");
+  // Resident B (64-channel layers / groups: one k-block per tap, the nine tap tiles of an N tile are 72 KB = the whole B
+  // ring): the tiles are ordered N-major and every CTA takes a CONTIGUOUS run of them, so the weights of an N tile (a
+  // group) are loaded once per run instead of once per tile -- slot j of the ring holds tap j, its full / empty barriers
+  // flip once per N-tile change.  profiles/teacher_c22_*.txt: the grouped 14 x 14 layers of the teacher moved 229 MB
+  // from L2 per launch, 147 MB of it the same 2.4 MB of weights fetched by each of the 64 pixel tiles.
+  constexpr bool kRes = kHalo && BLOCK_N == 64 && STAGES == 9;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -162,11 +185,34 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_empty = tmem_full + 2;                  // [2]
   uint64_t* add_bar = tmem_empty + 2;                    // addend tile landed in the staging buffer
   uint64_t* bn_bar = add_bar + 1;                        // BN x (/ y) tiles landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bn_bar + 1);
+  uint64_t* afull_bar = bn_bar + 1;                      // halo layout: the A ring's barriers
+  uint64_t* aempty_bar = afull_bar + (kHalo ? ASTAGES : 0);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + (kHalo ? ASTAGES : 0));
+  static_assert((2 * STAGES + 6 + 2 * ASTAGES) * 8 + 4 <= 512, "barrier block");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
+  const bool res = kRes && p.b_res != 0;
+  int t_begin = blockIdx.x, t_end = total_tiles, t_step = gridDim.x;
+  if (res) {
+    const int per = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    t_begin = blockIdx.x * per;
+    t_end = t_begin + per < total_tiles ? t_begin + per : total_tiles;
+    t_step = 1;
+  }
+  // tile index -> (M tile, first column): M-major normally (neighbouring CTAs share the A tile in L2), N-major when
+  // B is resident
+  auto tile_coords = [&](int t, int& tm, int& n0) {
+    if (res) {
+      const int nt = t / p.tiles_m;
+      tm = t - nt * p.tiles_m;
+      n0 = nt * BLOCK_N;
+    } else {
+      tm = t / p.tiles_n;
+      n0 = (t - tm * p.tiles_n) * BLOCK_N;
+    }
+  };
   constexpr uint32_t kTmemCols =
       2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
   static_assert(2 * BLOCK_N <= 512, "two accumulators must fit the 512 TMEM columns");
@@ -185,11 +231,20 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     ptx::mbar_init(add_bar, 1);
     ptx::mbar_init(bn_bar, 1);
+    for (int s = 0; s < ASTAGES; ++s) {
+      ptx::mbar_init(&afull_bar[s], 1);
+      ptx::mbar_init(&aempty_bar[s], 1);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_slot);
   if (local_stats)
     for (int i = threadIdx.x; i < 2 * p.N; i += kThreads) sstats[i] = 0.f;
+  if (kHalo) {
+    // pads AND tiles: TMA only ever writes the first rows_in rows of a tile, the rows behind them must read as zero
+    for (int i = threadIdx.x; i < L::kARingBytes / 16; i += kThreads) ptx::sts128(ptx::smem_u32(smem) + i * 16, 0u, 0u, 0u, 0u);
+    ptx::fence_proxy_async_smem();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -198,36 +253,82 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   pdl_wait();
   pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
-  const int rows_tile = kConv ? p.BN * p.BH * p.W : kBlockM;
-  const uint32_t a_bytes = kConv ? (uint32_t)rows_tile * 128u : (uint32_t)L::kABytes;
+  const int rows_tile = kConv ? p.BN * p.BH * p.W : kBlockM;            // rows of the (dense) output tile
+  const int rows_in = kHalo ? p.BN * p.BH * p.Wb : rows_tile;          // rows of the A tile
+  const uint32_t a_bytes = kConv ? (uint32_t)rows_in * 128u : (uint32_t)L::kABytes;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The WHOLE warp runs the loops and waits on the barriers; one elected lane issues the copies.  With the loops
+    // inside `if (lane == 0)` every tensor-map / barrier / coordinate operand is a per-thread value that the compiler has to
+    // move into uniform registers with a vote + broadcast + retry sequence per operand (profiles/README.md, "issue-bound").
+    {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int tile_m = t / p.tiles_n;
-        const int n0 = (t - tile_m * p.tiles_n) * BLOCK_N;
+      [[maybe_unused]] uint32_t ita = 0;
+      [[maybe_unused]] int cur_n0 = -1;
+      [[maybe_unused]] uint32_t gcount = 0;
+      for (int t = t_begin; t < t_end; t += t_step) {
+        int tile_m, n0;
+        tile_coords(t, tile_m, n0);
         const int m0 = tile_m * kBlockM;
         const int img0 = kConv ? (tile_m / p.tiles_h) * p.BN : 0;
         const int h0 = kConv ? (tile_m % p.tiles_h) * p.BH : 0;
+        if constexpr (kHalo) {
+          // num_kb counts A steps here: (filter row r, k-block kc); each is followed by its three B tap tiles
+          const int cbase_in = (MODE == 2) ? (n0 / p.cout_g) * p.cin_g : 0;
+          const bool newg = n0 != cur_n0;
+          if (newg) { cur_n0 = n0; ++gcount; }
+          for (int i = 0; i < p.num_kb; ++i, ++ita) {
+            const int r = i / p.kc_blocks, kc = i - r * p.kc_blocks;
+            const int sa_i = ita % ASTAGES;
+            ptx::mbar_wait(&aempty_bar[sa_i], ((ita / ASTAGES) & 1) ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(&afull_bar[sa_i], a_bytes);
+              ptx::tma_load_4d(smem + sa_i * L::kARegion + L::kPad, &tmA, &afull_bar[sa_i], cbase_in + kc * kBlockK, -1,
+                               h0 + (kDgrad ? 1 - r : r - 1), img0);
+            }
+            __syncwarp();
+            if (res && !newg) continue;            // the taps of this N tile are already in their slots
+            for (int sft = 0; sft < 3; ++sft, ++it) {
+              const int s = res ? r * 3 + sft : (int)(it % STAGES);
+              ptx::mbar_wait(&empty_bar[s], res ? ((gcount - 1) & 1) ^ 1 : ((it / STAGES) & 1) ^ 1);
+              uint8_t* sb = smem + L::kARingBytes + s * L::kBBytes;
+              const int tap = r * 3 + sft;
+              if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(&full_bar[s], L::kBBytes);
+                if (!kBMN) {
+                  ptx::tma_load_2d(sb, &tmB, &full_bar[s], tap * p.c_in_w + kc * kBlockK, n0);
+                } else {
+#pragma unroll
+                  for (int hh = 0; hh < BLOCK_N / 64; ++hh)
+                    ptx::tma_load_2d(sb + hh * 8192, &tmB, &full_bar[s], tap * p.c_in_w + n0 + hh * 64, kc * kBlockK);
+                }
+              }
+              __syncwarp();
+            }
+          }
+          continue;
+        }
         for (int i = 0; i < p.num_kb; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[s], a_bytes + L::kBBytes);
           if (!kConv) {
             const int k0 = i * kBlockK;
-            ptx::tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
-            if (!kBMN) {
-              ptx::tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
-            } else {
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(&full_bar[s], a_bytes + L::kBBytes);
+              ptx::tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
+              if (!kBMN) {
+                ptx::tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+              } else {
 #pragma unroll
-              for (int hh = 0; hh < BLOCK_N / 64; ++hh)
-                ptx::tma_load_2d(sb + hh * 8192, &tmB, &full_bar[s], n0 + hh * 64, k0);
+                for (int hh = 0; hh < BLOCK_N / 64; ++hh)
+                  ptx::tma_load_2d(sb + hh * 8192, &tmB, &full_bar[s], n0 + hh * 64, k0);
+              }
             }
+            __syncwarp();
           } else {
             int tap = i / p.kc_blocks;
             const int kc = i - tap * p.kc_blocks;
@@ -243,28 +344,77 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             // grouped fprop: the N tile lies in one group; its input channels start at group * cin_g
             const int cbase_in = (MODE == 2) ? (n0 / p.cout_g) * p.cin_g : 0;
-            ptx::tma_load_4d(sa, &tmA, &full_bar[s], cbase_in + kc * kBlockK, dw, h0 * p.stride + dh, img0);
-            if (!kBMN) {
-              ptx::tma_load_2d(sb, &tmB, &full_bar[s], tap * p.c_in_w + kc * kBlockK, n0);
-            } else {
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(&full_bar[s], a_bytes + L::kBBytes);
+              ptx::tma_load_4d(sa, &tmA, &full_bar[s], cbase_in + kc * kBlockK, dw, h0 * p.stride + dh, img0);
+              if (!kBMN) {
+                ptx::tma_load_2d(sb, &tmB, &full_bar[s], tap * p.c_in_w + kc * kBlockK, n0);
+              } else {
 #pragma unroll
-              for (int hh = 0; hh < BLOCK_N / 64; ++hh)
-                ptx::tma_load_2d(sb + hh * 8192, &tmB, &full_bar[s], tap * p.c_in_w + n0 + hh * 64, kc * kBlockK);
+                for (int hh = 0; hh < BLOCK_N / 64; ++hh)
+                  ptx::tma_load_2d(sb + hh * 8192, &tmB, &full_bar[s], tap * p.c_in_w + n0 + hh * 64, kc * kBlockK);
+              }
             }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // Warp-uniform loops, one elected lane issues (always the same one: tcgen05.commit covers the MMAs of ITS thread).
+    // The descriptors are built once per stage in uniform code; advancing k inside the 128-byte swizzle atom adds 32 bytes
+    // (K-major) or 2048 bytes (MN-major) to the start-address field, i.e. 2 or 128 in the descriptor's 16-byte units.
+    {
       constexpr uint32_t idesc = ptx::make_idesc(1, 1, kBlockM, BLOCK_N, 0, kBMN ? 1 : 0);
       uint32_t it = 0, tc = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
+      [[maybe_unused]] uint32_t ita = 0;
+      [[maybe_unused]] int cur_n0 = -1;
+      [[maybe_unused]] uint32_t gcount = 0;
+      for (int t = t_begin; t < t_end; t += t_step, ++tc) {
         const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
         ptx::mbar_wait(&tmem_empty[slot], aph ^ 1);      // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t acc = tmem_base + slot * BLOCK_N;
+        if constexpr (kHalo) {
+          bool newg = false, lastg = false;
+          if (res) {
+            int tm_, n0_, tm2_, n02_ = -1;
+            tile_coords(t, tm_, n0_);
+            if (t + 1 < t_end) tile_coords(t + 1, tm2_, n02_);
+            newg = n0_ != cur_n0;
+            lastg = n02_ != n0_;                     // the slots are handed back after the last tile of the N tile
+            if (newg) { cur_n0 = n0_; ++gcount; }
+          }
+          for (int i = 0; i < p.num_kb; ++i, ++ita) {
+            const int sa_i = ita % ASTAGES;
+            ptx::mbar_wait(&afull_bar[sa_i], (ita / ASTAGES) & 1);
+            const uint32_t sa = ptx::smem_u32(smem + sa_i * L::kARegion + L::kPad);
+            for (int sft = 0; sft < 3; ++sft, ++it) {
+              const int s = res ? i * 3 + sft : (int)(it % STAGES);
+              if (!res) ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+              else if (newg) ptx::mbar_wait(&full_bar[s], (gcount - 1) & 1);
+              ptx::tc_fence_after();
+              const uint32_t sb = ptx::smem_u32(smem + L::kARingBytes + s * L::kBBytes);
+              const int shift = (kDgrad ? 1 - sft : sft - 1) * 128;      // tile rows are 128 bytes
+              const uint64_t da0 = ptx::make_smem_desc(sa + shift, 16, 1024);
+              const uint64_t db0 = kBMN ? ptx::make_smem_desc(sb, 8192, 1024) : ptx::make_smem_desc(sb, 16, 1024);
+              if (ptx::elect_one()) {
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  ptx::umma_f16(acc, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * (kBMN ? 128 : 2)), idesc,
+                                (i | sft | k) != 0 ? 1u : 0u);
+                if (!res || lastg) ptx::umma_commit(&empty_bar[s]);
+                if (sft == 2) {
+                  ptx::umma_commit(&aempty_bar[sa_i]);
+                  if (i == p.num_kb - 1) ptx::umma_commit(&tmem_full[slot]);
+                }
+              }
+              __syncwarp();
+            }
+          }
+          continue;
+        }
         for (int i = 0; i < p.num_kb; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -272,16 +422,17 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + s * L::kStageBytes);
           const uint32_t sb = sa + L::kABytes;
+          const uint64_t da0 = ptx::make_smem_desc(sa, 16, 1024);
+          const uint64_t db0 = kBMN ? ptx::make_smem_desc(sb, 8192, 1024) : ptx::make_smem_desc(sb, 16, 1024);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t da = ptx::make_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = kBMN ? ptx::make_smem_desc(sb + k * 2048, 8192, 1024)
-                                     : ptx::make_smem_desc(sb + k * 32, 16, 1024);
-            ptx::umma_f16(acc, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              ptx::umma_f16(acc, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * (kBMN ? 128 : 2)), idesc, (i | k) != 0 ? 1u : 0u);
+            ptx::umma_commit(&empty_bar[s]);
+            if (i == p.num_kb - 1) ptx::umma_commit(&tmem_full[slot]);
           }
-          ptx::umma_commit(&empty_bar[s]);
+          __syncwarp();
         }
-        ptx::umma_commit(&tmem_full[slot]);
       }
     }
   } else {
@@ -294,10 +445,13 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int kColsPerGrp = BLOCK_N / 2;
     int const_n0 = -1;
     uint32_t tc = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
+    for (int t = t_begin; t < t_end; t += t_step, ++tc) {
       const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
-      const int tile_m = t / p.tiles_n;
-      const int n0 = (t - tile_m * p.tiles_n) * BLOCK_N;
+      int tile_m, n0;
+      tile_coords(t, tile_m, n0);
+      int next_tm = 0, next_n0 = 0;
+      const bool has_next = t + t_step < t_end;
+      if (has_next) tile_coords(t + t_step, next_tm, next_n0);
       const int m0 = tile_m * kBlockM;
       const int img0 = kConv ? (tile_m / p.tiles_h) * p.BN : 0;
       const int h0 = kConv ? (tile_m % p.tiles_h) * p.BH : 0;
@@ -330,7 +484,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           row_ok = row < rows_tile && img0 + bi < p.n_img && h0 + rr / p.W < p.H;
         }
         if (tc == 0 && et == 0)                               // later tiles are prefetched one tile ahead
-          issue_bn_tiles<BLOCK_N, kConv>(p, t, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
+          issue_bn_tiles<BLOCK_N, kConv>(p, tile_m, n0, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
         if (n0 != const_n0) {
           // per-column constants of the BN layer for this N tile (a CTA usually keeps its N tile)
           if (tc != 0) asm volatile("bar.sync 2, 256;" ::: "memory");   // everybody is done with the old ones
@@ -345,6 +499,14 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const_n0 = n0;
         }
         if (BNR == 1) ptx::mbar_wait(bn_bar, tc & 1);     // mode 2 waits where it reads x / y
+      }
+      // halo layout: accumulator row -> row of the dense staging tile (the halo column's rows are dropped)
+      int srow = row;
+      bool store_ok = true;
+      if (kHalo) {
+        const int ir = row / p.Wb, cw = row - ir * p.Wb;
+        store_ok = cw != 0 && row < rows_in;
+        srow = ir * p.W + cw - 1;
       }
       ptx::mbar_wait(&tmem_full[slot], aph);
       ptx::tc_fence_after();
@@ -382,18 +544,39 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         if (!BNR) {
+          // 32 consecutive per-column constants: eight 16-byte loads when the chunk lies inside the matrix and is aligned
+          // (the scalar form costs 32 load instructions per chunk and thread)
+          const bool vec_cols = n0 + cbase + 32 <= p.N;
           if (p.col_scale != nullptr) {
+            const float* ps = p.col_scale + n0 + cbase;
+            if (vec_cols && (reinterpret_cast<uintptr_t>(ps) & 15) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = n0 + cbase + j;
-              f[j] *= col < p.N ? p.col_scale[col] : 0.f;
+              for (int j = 0; j < 8; ++j) {
+                const float4 v4 = __ldg(reinterpret_cast<const float4*>(ps) + j);
+                f[4 * j] *= v4.x; f[4 * j + 1] *= v4.y; f[4 * j + 2] *= v4.z; f[4 * j + 3] *= v4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int col = n0 + cbase + j;
+                f[j] *= col < p.N ? p.col_scale[col] : 0.f;
+              }
             }
           }
           if (p.col_shift != nullptr) {
+            const float* ps = p.col_shift + n0 + cbase;
+            if (vec_cols && (reinterpret_cast<uintptr_t>(ps) & 15) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = n0 + cbase + j;
-              f[j] += col < p.N ? p.col_shift[col] : 0.f;
+              for (int j = 0; j < 8; ++j) {
+                const float4 v4 = __ldg(reinterpret_cast<const float4*>(ps) + j);
+                f[4 * j] += v4.x; f[4 * j + 1] += v4.y; f[4 * j + 2] += v4.z; f[4 * j + 3] += v4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int col = n0 + cbase + j;
+                f[j] += col < p.N ? p.col_shift[col] : 0.f;
+              }
             }
           }
           if (p.relu) {
@@ -453,7 +636,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         const int half = cbase >> 6;
-        const uint32_t rowp = ptx::smem_u32(sd) + half * (kBlockM * 128) + row * 128;
+        const uint32_t rowp = ptx::smem_u32(sd) + half * (kBlockM * 128) + srow * 128;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int chunk = ((cbase >> 5) & 1) * 4 + c;
@@ -462,13 +645,13 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 8; ++j) v[j] = f[c * 8 + j];
           const bf16x8 pk = pack8(v);
           const uint4 u = *reinterpret_cast<const uint4*>(&pk);
-          ptx::sts128(rowp + ((chunk ^ (row & 7)) << 4), u.x, u.y, u.z, u.w);
+          if (store_ok) ptx::sts128(rowp + ((chunk ^ (srow & 7)) << 4), u.x, u.y, u.z, u.w);
         }
       }
       ptx::fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (BNR == 1 && et == 0 && t + (int)gridDim.x < total_tiles)   // x / y buffers are free: prefetch the next tile's
-        issue_bn_tiles<BLOCK_N, kConv>(p, t + (int)gridDim.x, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
+      if (BNR == 1 && et == 0 && has_next)   // x / y buffers are free: prefetch the next tile's
+        issue_bn_tiles<BLOCK_N, kConv>(p, next_tm, next_n0, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
       if (et == 0) {
 #pragma unroll
         for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) {
@@ -558,8 +741,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         // everybody is done with this tile's x / y: fetch the next tile's while its MMAs run
         asm volatile("bar.sync 3, 256;" ::: "memory");
-        if (et == 0 && t + (int)gridDim.x < total_tiles)
-          issue_bn_tiles<BLOCK_N, kConv>(p, t + (int)gridDim.x, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
+        if (et == 0 && has_next)
+          issue_bn_tiles<BLOCK_N, kConv>(p, next_tm, next_n0, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
       }
       if (!BNR && p.col_stats != nullptr) {
         // Per-channel sum / sum of squares of the STORED bf16 values, from the staged tile.  A thread owns
@@ -673,18 +856,51 @@ bool g_wide_tiles = [] {
 }();
 // fused BatchNorm-backward reduction in the dgrad epilogue: 2 (default) = column-pair loop over the staged tiles,
 // 1 = the round-1 in-register shuffle transpose (epilogue-bound; EDL_BNR_MODE=1 keeps it selectable for A/B)
+// haloed A tiles for the 3x3 / stride 1 convolutions (EDL_CONV_HALO=0 keeps the one-box-per-tap version for A/B)
+bool g_conv_halo = [] {
+  const char* e = getenv("EDL_CONV_HALO");
+  return !(e != nullptr && e[0] == '0');
+}();
+
+bool g_conv_bres = [] {
+  const char* e = getenv("EDL_CONV_BRES");
+  return !(e != nullptr && e[0] == '0');
+}();
+
+// tile geometry with Wb = W + 1 columns per image row (conv3x3.cu's planner with the row width replaced)
+bool halo_geometry(int N, int H, int W, int* BH, int* BN, int* tiles_h, int* tiles_img) {
+  const int wb = W + 1;
+  if (W < 1 || wb > kBlockM || H < 1) return false;
+  int bh = kBlockM / wb;
+  if (bh > H) bh = H;
+  int best = bh;
+  for (int d = bh; d >= 1; --d)
+    if (H % d == 0) { best = d; break; }
+  if (best * 4 < bh * 3) best = bh;
+  int bn = 1;
+  if (best == H) {
+    bn = kBlockM / (H * wb);
+    if (bn < 1) bn = 1;
+    if (bn > N) bn = N;
+  }
+  *BH = best; *BN = bn;
+  *tiles_h = (H + best - 1) / best;
+  *tiles_img = (N + bn - 1) / bn;
+  return true;
+}
+
 int g_bnr_mode = [] {
   const char* e = getenv("EDL_BNR_MODE");
   return (e != nullptr && e[0] == '1') ? 1 : 2;
 }();
 
-template <int BLOCK_N, int STAGES, int MODE, int BNR = 0>
+template <int BLOCK_N, int STAGES, int MODE, int BNR = 0, int ASTAGES = 0>
 const char* launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const PersistParams& p,
                      cudaStream_t stream, const CUtensorMap* tmAdd = nullptr, const CUtensorMap* tmBnX = nullptr,
                      const CUtensorMap* tmBnY = nullptr) {
-  using L = PSmem<BLOCK_N, STAGES, BNR>;
+  using L = PSmem<BLOCK_N, STAGES, BNR, ASTAGES>;
   static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
-  auto kern = gemm_persist_kernel<BLOCK_N, STAGES, MODE, BNR>;
+  auto kern = gemm_persist_kernel<BLOCK_N, STAGES, MODE, BNR, ASTAGES>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -729,6 +945,7 @@ bool persistent_gemm_enabled() { return g_persistent; }
 
 // GEMM front end (EPI 0 semantics of gemm.cu; A K-major)
 const char* gemm_bf16_persistent(const GemmArgs& g, cudaStream_t stream) {
+  if (gemm_pair_supported(g)) return gemm_bf16_pair(g, stream);
   alignas(64) CUtensorMap tmA, tmB, tmD;
   const bool n64 = g.N <= 64;
   // 128 x 256 tiles for the compute-heavy GEMMs (the teacher's 1x1 convolutions: N = 512 .. 4096, K = 256 .. 4096):
@@ -797,7 +1014,14 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
   alignas(64) CUtensorMap tmX, tmW, tmY;
   const int sd = a.stride == 2 ? 2 : 1;
   if (sd == 2 && (dg || 2 * a.W > 256 || 2 * BH > 256)) return "conv3x3 stride 2: fprop only, output width <= 128";
-  {
+  const bool halo = g_conv_halo && sd == 1 && !(dg && a.bn.x != nullptr && bnr_mode() != 2) &&
+                    halo_geometry(a.N, a.H, a.W, &BH, &BN, &tiles_h, &tiles_img);
+  if (halo) {
+    const uint64_t dims[4] = {(uint64_t)cx, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
+    const uint64_t st[3] = {(uint64_t)cx * 2, (uint64_t)a.W * cx * 2, (uint64_t)a.H * a.W * cx * 2};
+    const uint32_t box[4] = {64, (uint32_t)(a.W + 1), (uint32_t)BH, (uint32_t)BN};
+    if (const char* e = encode_tmap_bf16(&tmX, a.X, 4, dims, st, box)) return e;
+  } else {
     // stride 2: the input is [N, 2H, 2W, C]; a box that spans 2W x 2BH elements with traversal stride 2 in w and h
     // delivers the W x BH pixels a filter tap needs, starting at column s - 1 and row 2*h0 + r - 1
     const uint64_t dims[4] = {(uint64_t)cx, (uint64_t)a.W * sd, (uint64_t)a.H * sd, (uint64_t)a.N};
@@ -820,7 +1044,9 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
   p.tiles_m = tiles_img * tiles_h;
   p.tiles_n = (cy + bn - 1) / bn;
   p.kc_blocks = cin_g / kBlockK;
-  p.num_kb = 9 * p.kc_blocks;
+  p.num_kb = (halo ? 3 : 9) * p.kc_blocks;
+  p.Wb = halo ? a.W + 1 : a.W;
+  p.b_res = (halo && n64 && p.kc_blocks == 1 && g_conv_bres) ? 1 : 0;
   p.col_stats = dg ? nullptr : a.col_stats;
   p.col_scale = dg ? nullptr : a.col_scale;
   p.col_shift = dg ? nullptr : a.col_shift;
@@ -838,15 +1064,27 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
     if (has_y)
       if (const char* e = encode_tmap_bf16(&tmBy, a.bn.y, 4, dims, st, box)) return e;
     fill_bn(p, a.bn);
+    if (halo)
+      return n64 ? launch_p<64, 9, 3, 2, 3>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr)
+                 : launch_p<128, 4, 3, 2, 2>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr);
     if (bnr_mode() == 2)
       return n64 ? launch_p<64, 4, 3, 2>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr)
                  : launch_p<128, 3, 3, 2>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr);
     return n64 ? launch_p<64, 4, 3, 1>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr)
                : launch_p<128, 3, 3, 1>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr);
   }
+  if (halo) {
+    if (!dg)
+      return n64 ? launch_p<64, 9, 2, 0, 4>(tmX, tmW, tmY, p, stream) : launch_p<128, 7, 2, 0, 3>(tmX, tmW, tmY, p, stream);
+    return n64 ? launch_p<64, 9, 3, 0, 4>(tmX, tmW, tmY, p, stream) : launch_p<128, 7, 3, 0, 3>(tmX, tmW, tmY, p, stream);
+  }
   if (!dg) return n64 ? launch_p<64, 6, 2>(tmX, tmW, tmY, p, stream) : launch_p<128, 5, 2>(tmX, tmW, tmY, p, stream);
   return n64 ? launch_p<64, 6, 3>(tmX, tmW, tmY, p, stream) : launch_p<128, 5, 3>(tmX, tmW, tmY, p, stream);
 }
+
+void set_conv_halo(bool on) { g_conv_halo = on; }
+void set_conv_resident_weights(bool on) { g_conv_bres = on; }
+bool get_conv_halo() { return g_conv_halo; }
 
 // Input gradient of the 3x3 / pad 1 / STRIDE 2 convolution (round 2).  dX[n, h, w] = sum over the taps (r, s) with
 // h + 1 - r and w + 1 - s even of dY[n, (h + 1 - r) / 2, (w + 1 - s) / 2] * W[:, r, s, :]: for a fixed parity (h & 1, w & 1)

@@ -54,6 +54,7 @@ def test_wide_tile_gemm_matches_the_128_wide_tiles(m, n, k, res):
     ref = a.float() @ b.float().t() + sh + (add.float() if res else 0.0)
     outs = []
     try:
+        ops.native().set_pair_gemm(False)          # these shapes would otherwise take the CTA-pair kernel
         for wide in (True, False):
             ops.native().set_wide_gemm_tiles(wide)
             d = ops.gemm_bf16(a, b, col_shift=sh, relu=True, add=add)
@@ -61,6 +62,36 @@ def test_wide_tile_gemm_matches_the_128_wide_tiles(m, n, k, res):
             outs.append(d)
     finally:
         ops.native().set_wide_gemm_tiles(True)
+        ops.native().set_pair_gemm(True)
+    assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("m,n,k,res,scale", [(25088, 512, 512, False, False), (6272, 2048, 1024, True, False),
+                                             (100352, 512, 256, True, True), (1568, 4096, 2048, False, True),
+                                             (19000, 256, 320, True, False), (9601, 768, 4096, False, False)])
+def test_cta_pair_gemm_matches_the_single_cta_tiles(m, n, k, res, scale):
+    """256 x 256 tiles on two SMs (tcgen05.mma.cta_group::2, csrc/gemm_2cta.cu): same k order per output element as the
+    single-CTA kernel, so the results are bit-identical; M tails that end inside the first / second CTA of a pair, K tails
+    (k = 320: the last k-block is half out of bounds), the addend and the scale / shift / ReLU epilogue."""
+    torch.manual_seed(3)
+    nat = ops.native()
+    a = torch.randn(m, k, device=DEV).bfloat16()
+    b = (torch.randn(n, k, device=DEV) * 0.05).bfloat16()
+    sh = torch.randn(n, device=DEV)
+    sc = (torch.rand(n, device=DEV) + 0.5) if scale else None
+    add = torch.randn(m, n, device=DEV).bfloat16() if res else None
+    ref = a.float() @ b.float().t() + (add.float() if res else 0.0)
+    ref = torch.relu((ref * sc if scale else ref) + sh)
+    assert nat.get_pair_gemm()
+    outs = []
+    try:
+        for pair in (True, False):
+            nat.set_pair_gemm(pair)
+            d = ops.gemm_bf16(a, b, col_scale=sc, col_shift=sh, relu=True, add=add)
+            assert _rel(d, ref) < 1e-2, pair
+            outs.append(d)
+    finally:
+        nat.set_pair_gemm(True)
     assert torch.equal(outs[0], outs[1])
 
 
@@ -86,8 +117,9 @@ def test_persistent_conv3x3_matches_tile_kernel(n, cin, cout, h, w):
         st = torch.zeros(2 * cout, device=DEV)
         y = ops.conv3x3(x, wt, st)
         res.append((y, st))
-    assert torch.equal(res[0][0], res[1][0])
-    assert _rel(res[0][1], res[1][1]) < 1e-4
+    # the haloed-tile version accumulates in (filter row, k-block, tap) order, the tile kernel in (tap, k-block) order
+    assert _rel(res[0][0], res[1][0]) < 2e-3
+    assert _rel(res[0][1], res[1][1]) < 2e-3
     ref = F.conv2d(x.float(), wt.permute(0, 3, 1, 2).float(), None, 1, 1)
     assert _rel(res[0][0], ref) < 1e-2
     if cin <= 64 or cin % 128 == 0:
@@ -98,7 +130,59 @@ def test_persistent_conv3x3_matches_tile_kernel(n, cin, cout, h, w):
             dx = torch.empty_like(x)
             ops.native().conv3x3(dy, wt, dx, True, None, None, False)
             dxs.append(dx)
-        assert torch.equal(dxs[0], dxs[1])
+        assert _rel(dxs[0], dxs[1]) < 2e-3
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w,groups", [(32, 64, 64, 56, 56, 1), (8, 128, 128, 28, 28, 1), (9, 256, 256, 14, 14, 1),
+                                                   (7, 512, 512, 7, 7, 1), (5, 64, 192, 11, 20, 1), (3, 128, 64, 9, 30, 1),
+                                                   (2, 64, 64, 5, 127, 1), (3, 512, 512, 14, 14, 8), (2, 256, 512, 6, 6, 2),
+                                                   (32, 2048, 2048, 14, 14, 32), (40, 192, 192, 7, 7, 3)])
+def test_haloed_conv3x3_tiles_match_the_shifted_box_version(n, cin, cout, h, w, groups):
+    """One A tile per filter row read through three shifted descriptors (EDL_CONV_HALO, the default) against one TMA box per
+    tap, and both against the fp32 convolution: fprop with statistics / folded-BN epilogue, dgrad, grouped fprop."""
+    torch.manual_seed(5)
+    nat = ops.native()
+    x = torch.randn(n, cin, h, w, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, 3, 3, cin // groups, device=DEV) * 0.05).bfloat16()
+    scale = torch.rand(cout, device=DEV) + 0.5
+    shift = torch.randn(cout, device=DEV) * 0.1
+    assert nat.get_conv_halo()
+    outs = []
+    try:
+        for halo, resident in ((True, True), (True, False), (False, False)):
+            nat.set_conv_halo(halo)
+            nat.set_conv_resident_weights(resident)     # 64-channel layers / groups: weights loaded once per run of tiles
+            if groups == 1:
+                st = torch.zeros(2 * cout, device=DEV)
+                y = ops.conv3x3(x, wt, st)
+            else:
+                st = None
+                y = ops.conv3x3_infer(x, wt, scale, shift, relu=True, groups=groups)
+            dx = None
+            if groups == 1 and (cin <= 64 or cin % 128 == 0):
+                dy = torch.randn_like(y)
+                dx = torch.empty_like(x)
+                nat.conv3x3(dy, wt, dx, True, None, None, False)
+            outs.append((y, st, dx, dy if dx is not None else None))
+    finally:
+        nat.set_conv_halo(True)
+        nat.set_conv_resident_weights(True)
+    wf = wt.permute(0, 3, 1, 2).float()
+    ref = F.conv2d(x.float(), wf, None, 1, 1, 1, groups)
+    if groups > 1:
+        ref = torch.relu(ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    assert _rel(outs[0][0], ref) < 1e-2
+    assert _rel(outs[0][0], outs[2][0]) < 2e-3
+    assert torch.equal(outs[0][0], outs[1][0])          # same accumulation order, only the tile schedule differs
+    if outs[0][1] is not None:
+        assert _rel(outs[0][1], outs[1][1]) < 1e-4
+        yf = outs[0][0].float()
+        assert _rel(outs[0][1][:cout], yf.sum((0, 2, 3))) < 2e-3
+        assert _rel(outs[0][1][cout:], (yf * yf).sum((0, 2, 3))) < 2e-3
+    if outs[0][2] is not None:
+        for y, _, dx, dy in outs:
+            dref = torch.nn.grad.conv2d_input(x.shape, wf, dy.float(), 1, 1)
+            assert _rel(dx, dref) < 1e-2
 
 
 def test_conv1x1_fork_sums_both_gradients_in_the_dgrad_epilogue():

@@ -9,6 +9,8 @@ captures exactly the kernel of interest.
   bnfwd  N C H W [fused|stream|regs] [res]
   conv3 / conv3dgrad  N CIN COUT H W   tcgen05 implicit-GEMM 3x3 convolution
   wgrad3 N CIN COUT H W [SPLIT]        tcgen05 3x3 weight gradient
+  conv3g N C COUT H W GROUPS           inference 3x3 (grouped) convolution with folded-BN epilogue (the teacher's layers)
+  gemmi  M K N                         inference 1x1 convolution: GEMM + scale / shift / ReLU epilogue (wide tiles)
   sgd | softce B | rope T H D          fused optimizer / loss / rotary kernels
 """
 import os
@@ -75,6 +77,19 @@ elif op in ("conv3", "conv3dgrad"):
     y = torch.empty(n, k if op == "conv3" else c, h, w, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
     st = torch.zeros(2 * k, device=dev)
     run(lambda: ops.native().conv3x3(x, wt, y, op != "conv3", st if op == "conv3" else None, None, False))
+elif op == "conv3g":
+    n, c, k, h, w, gr = [int(v) for v in a[:6]]
+    x = torch.randn(n, c, h, w, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(k, 3, 3, c // gr, device=dev) * 0.05).bfloat16()
+    sc, sh = torch.rand(k, device=dev) + 0.5, torch.randn(k, device=dev) * 0.1
+    run(lambda: ops.conv3x3_infer(x, wt, sc, sh, relu=True, groups=gr))
+elif op == "gemmi":
+    m, k, n = int(a[0]), int(a[1]), int(a[2])
+    x = torch.randn(m, k, device=dev).bfloat16()
+    w = (torch.randn(n, k, device=dev) * 0.05).bfloat16()
+    y = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+    sc, sh = torch.rand(n, device=dev) + 0.5, torch.randn(n, device=dev) * 0.1
+    run(lambda: ops.gemm_bf16(x, w, out=y, col_scale=sc, col_shift=sh, relu=True))
 elif op == "wgrad3":
     n, c, k, h, w = [int(v) for v in a[:5]]          # batch, Cin, Cout, H, W
     from edl_b200.ops import gemm as G
