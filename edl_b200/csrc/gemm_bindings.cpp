@@ -387,6 +387,7 @@ void register_gemm_bindings(pybind11::module_& m) {
   m.def("set_wide_gemm_tiles", &edl::set_wide_gemm_tiles);
   m.def("set_pair_gemm", &edl::set_pair_gemm);
   m.def("get_pair_gemm", &edl::get_pair_gemm);
+  m.def("set_epilogue_warps", &edl::set_epilogue_warps);
   m.def("set_conv_halo", &edl::set_conv_halo);
   m.def("get_conv_halo", &edl::get_conv_halo);
   m.def("set_conv_resident_weights", &edl::set_conv_resident_weights);

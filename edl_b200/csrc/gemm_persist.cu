@@ -30,9 +30,11 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + kEpiWarps * 32;   // 320
-constexpr int kEpiThreads = kEpiWarps * 32;     // 256
+// Epilogue warps per CTA: 8 (two per TMEM lane quarter, each owns half of the tile's columns) or 16 (four per quarter, a
+// quarter of the columns each).  The short-K layers of the student are bound by the epilogue's instruction LATENCY, not by
+// its issue slots (profiles/prof_c25_fwd_s1.ncu.txt: 35 % of the issue slots used, 0.47 eligible warps per scheduler and
+// cycle with 2.5 resident warps per scheduler), so the 128- and 256-column kernels run 16.
+constexpr int kMaxEpiWarps = 16;
 // BatchNorm statistics are accumulated per CTA in shared memory over ALL the tiles it processes and
 // pushed to global memory once at the end: with one reduction request per tile and column group the
 // L2 retires ~12 requests/ns into the few hot lines, which made the 1568-tile 1x1 convs atomic-bound
@@ -142,13 +144,20 @@ EDL_DEVICE void issue_bn_tiles(const PersistParams& p, int tm, int nn0, int rows
   }
 }
 
-template <int BLOCK_N, int STAGES, int MODE, int BNR, int ASTAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BLOCK_N, int STAGES, int MODE, int BNR, int ASTAGES, int EPIW>
+__global__ void __launch_bounds__(64 + EPIW * 32, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAdd,
                     const __grid_constant__ CUtensorMap tmBnX, const __grid_constant__ CUtensorMap tmBnY,
                     const PersistParams p) {
   using L = PSmem<BLOCK_N, STAGES, BNR, ASTAGES>;
+  constexpr int kEpiWarps = EPIW;
+  constexpr int kThreads = 64 + kEpiWarps * 32;
+  constexpr int kEpiThreads = kEpiWarps * 32;
+  constexpr int kColGroups = kEpiWarps / 4;              // warps per TMEM lane quarter = column groups of the tile
+  static_assert(EPIW == 8 || EPIW == 16, "epilogue warps");
+  static_assert(BLOCK_N / kColGroups >= 32 && (BLOCK_N / kColGroups) % 32 == 0, "a column group is whole 32-column chunks");
+  static_assert(BNR != 1 || EPIW == 8, "the legacy in-register BN reduction assumes 8 epilogue warps");
   constexpr bool kConv = MODE >= 2;
   constexpr bool kBMN = MODE == 1 || MODE == 3;
   constexpr bool kDgrad = MODE == 3;
@@ -196,9 +205,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const bool res = kRes && p.b_res != 0;
   int t_begin = blockIdx.x, t_end = total_tiles, t_step = gridDim.x;
   if (res) {
-    const int per = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-    t_begin = blockIdx.x * per;
-    t_end = t_begin + per < total_tiles ? t_begin + per : total_tiles;
+    // balanced contiguous runs: every CTA gets floor or ceil(total / grid) tiles (all SMs keep loads in flight)
+    t_begin = (int)((long long)blockIdx.x * total_tiles / (int)gridDim.x);
+    t_end = (int)((long long)(blockIdx.x + 1) * total_tiles / (int)gridDim.x);
     t_step = 1;
   }
   // tile index -> (M tile, first column): M-major normally (neighbouring CTAs share the A tile in L2), N-major when
@@ -439,10 +448,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int ew = warp - 2;                 // 0..7
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int grp = ew >> 2;                 // column half owned by this warpgroup
+    const int grp = ew >> 2;                 // column group owned by this warpgroup
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;         // 0..255
-    constexpr int kColsPerGrp = BLOCK_N / 2;
+    constexpr int kColsPerGrp = BLOCK_N / kColGroups;
     int const_n0 = -1;
     uint32_t tc = 0;
     for (int t = t_begin; t < t_end; t += t_step, ++tc) {
@@ -457,7 +466,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int h0 = kConv ? (tile_m % p.tiles_h) * p.BH : 0;
       // the staging tile must have been read by the previous TMA store and by every stats thread
       if (et == 0) ptx::tma_store_wait_read0();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       // addend (if any): TMA-load its tile into the staging buffer (same swizzled layout as the output)
       // while the MMAs of this tile are still running; every thread later adds its own 16-byte pieces
       const bool has_add = !kConv && p.add_src != nullptr;
@@ -487,7 +496,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           issue_bn_tiles<BLOCK_N, kConv>(p, tile_m, n0, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
         if (n0 != const_n0) {
           // per-column constants of the BN layer for this N tile (a CTA usually keeps its N tile)
-          if (tc != 0) asm volatile("bar.sync 2, 256;" ::: "memory");   // everybody is done with the old ones
+          if (tc != 0) asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");   // everybody is done with the old ones
           if (et < BLOCK_N) {
             const int col = n0 + et;
             const bool in = col < p.N;
@@ -495,7 +504,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float scale = in ? p.bn_gamma[col] * rstd : 0.f;
             reinterpret_cast<float4*>(sconst)[et] = make_float4(mean, rstd, scale, in ? p.bn_beta[col] - mean * scale : 0.f);
           }
-          asm volatile("bar.sync 2, 256;" ::: "memory");
+          asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
           const_n0 = n0;
         }
         if (BNR == 1) ptx::mbar_wait(bn_bar, tc & 1);     // mode 2 waits where it reads x / y
@@ -649,7 +658,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       ptx::fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (BNR == 1 && et == 0 && has_next)   // x / y buffers are free: prefetch the next tile's
         issue_bn_tiles<BLOCK_N, kConv>(p, next_tm, next_n0, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
       if (et == 0) {
@@ -740,7 +749,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         // everybody is done with this tile's x / y: fetch the next tile's while its MMAs run
-        asm volatile("bar.sync 3, 256;" ::: "memory");
+        asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");
         if (et == 0 && has_next)
           issue_bn_tiles<BLOCK_N, kConv>(p, next_tm, next_n0, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
       }
@@ -827,7 +836,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (local_stats) {
       // one flush per CTA: only the column groups this CTA touched are non-zero
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       const bool vec_ok = (p.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(stats_dst) & 15) == 0);
       if (vec_ok) {
         for (int i = et * 4; i < 2 * p.N; i += kEpiThreads * 4) {
@@ -894,13 +903,22 @@ int g_bnr_mode = [] {
   return (e != nullptr && e[0] == '1') ? 1 : 2;
 }();
 
-template <int BLOCK_N, int STAGES, int MODE, int BNR = 0, int ASTAGES = 0>
-const char* launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const PersistParams& p,
+// 16 epilogue warps are selectable (EDL_EPI_WARPS=16) but not the default: measured neutral on the teacher (3.95 vs 3.97 ms)
+// and 1 % slower on the student step (4.341 vs 4.302 ms, profiles/bench_runs.json b26_*): in the captured step these
+// kernels wait for DRAM, not for instruction latency as the cold single-kernel ncu capture suggested.
+bool g_epi16 = [] {
+  const char* e = getenv("EDL_EPI_WARPS");
+  return e != nullptr && e[0] == '1' && e[1] == '6';
+}();
+
+template <int BLOCK_N, int STAGES, int MODE, int BNR, int ASTAGES, int EPIW>
+const char* launch_pe(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const PersistParams& p,
                      cudaStream_t stream, const CUtensorMap* tmAdd = nullptr, const CUtensorMap* tmBnX = nullptr,
                      const CUtensorMap* tmBnY = nullptr) {
   using L = PSmem<BLOCK_N, STAGES, BNR, ASTAGES>;
   static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
-  auto kern = gemm_persist_kernel<BLOCK_N, STAGES, MODE, BNR, ASTAGES>;
+  constexpr int kThreads = 64 + EPIW * 32;
+  auto kern = gemm_persist_kernel<BLOCK_N, STAGES, MODE, BNR, ASTAGES, EPIW>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -914,6 +932,16 @@ const char* launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                              tmAdd != nullptr ? *tmAdd : tmD, tmBnX != nullptr ? *tmBnX : tmD,
                              tmBnY != nullptr ? *tmBnY : tmD, p);
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+template <int BLOCK_N, int STAGES, int MODE, int BNR = 0, int ASTAGES = 0>
+const char* launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const PersistParams& p,
+                     cudaStream_t stream, const CUtensorMap* tmAdd = nullptr, const CUtensorMap* tmBnX = nullptr,
+                     const CUtensorMap* tmBnY = nullptr) {
+  if constexpr (BLOCK_N >= 128 && BNR != 1) {
+    if (g_epi16) return launch_pe<BLOCK_N, STAGES, MODE, BNR, ASTAGES, 16>(tmA, tmB, tmD, p, stream, tmAdd, tmBnX, tmBnY);
+  }
+  return launch_pe<BLOCK_N, STAGES, MODE, BNR, ASTAGES, 8>(tmA, tmB, tmD, p, stream, tmAdd, tmBnX, tmBnY);
 }
 
 int bnr_mode() { return g_bnr_mode; }
@@ -1074,14 +1102,17 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
                : launch_p<128, 3, 3, 1>(tmX, tmW, tmY, p, stream, nullptr, &tmBx, has_y ? &tmBy : nullptr);
   }
   if (halo) {
+    // 64-column tiles: six A slots (with resident weights the A ring is all that is in flight: L2 -> SM throughput is
+    // bytes in flight / ~3 us, profiles/prof_c25_conv3g.ncu.txt)
     if (!dg)
-      return n64 ? launch_p<64, 9, 2, 0, 4>(tmX, tmW, tmY, p, stream) : launch_p<128, 7, 2, 0, 3>(tmX, tmW, tmY, p, stream);
-    return n64 ? launch_p<64, 9, 3, 0, 4>(tmX, tmW, tmY, p, stream) : launch_p<128, 7, 3, 0, 3>(tmX, tmW, tmY, p, stream);
+      return n64 ? launch_p<64, 9, 2, 0, 6>(tmX, tmW, tmY, p, stream) : launch_p<128, 7, 2, 0, 3>(tmX, tmW, tmY, p, stream);
+    return n64 ? launch_p<64, 9, 3, 0, 6>(tmX, tmW, tmY, p, stream) : launch_p<128, 7, 3, 0, 3>(tmX, tmW, tmY, p, stream);
   }
   if (!dg) return n64 ? launch_p<64, 6, 2>(tmX, tmW, tmY, p, stream) : launch_p<128, 5, 2>(tmX, tmW, tmY, p, stream);
   return n64 ? launch_p<64, 6, 3>(tmX, tmW, tmY, p, stream) : launch_p<128, 5, 3>(tmX, tmW, tmY, p, stream);
 }
 
+void set_epilogue_warps(int n) { g_epi16 = n >= 16; }
 void set_conv_halo(bool on) { g_conv_halo = on; }
 void set_conv_resident_weights(bool on) { g_conv_bres = on; }
 bool get_conv_halo() { return g_conv_halo; }

@@ -95,6 +95,41 @@ def test_cta_pair_gemm_matches_the_single_cta_tiles(m, n, k, res, scale):
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("m,n,k", [(100352, 256, 64), (25088, 128, 512), (5000, 384, 192)])
+def test_sixteen_epilogue_warps_match_eight(m, n, k):
+    """The 128- / 256-column kernels can run 16 epilogue warps (a quarter of the tile's columns per warpgroup;
+    EDL_EPI_WARPS=16 / set_epilogue_warps(16)) instead of 8: identical outputs, statistics within summation-order noise, for
+    the forward GEMM with BN statistics, the dgrad with the fused BN-backward reduction and the 3x3 convolution."""
+    torch.manual_seed(7)
+    nat = ops.native()
+    a = torch.randn(m, k, device=DEV).bfloat16()
+    b = (torch.randn(n, k, device=DEV) * 0.05).bfloat16()
+    wmn = (torch.randn(k, n, device=DEV) * 0.05).bfloat16()
+    x = torch.randn(m, n, device=DEV).bfloat16()
+    xc = torch.randn(8, 128, 28, 28, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    wc = (torch.randn(128, 3, 3, 128, device=DEV) * 0.05).bfloat16()
+    res = []
+    h = _hook(x, None, n, True)
+    try:
+        for warps in (16, 8):
+            nat.set_epilogue_warps(warps)
+            st = torch.zeros(2 * n, device=DEV)
+            d = ops.gemm_bf16(a, b, col_stats=st)
+            h.dsums = torch.zeros(2 * n, device=DEV)
+            g = ops.gemm_bf16(a, wmn, b_mn_major=True, bn=h)
+            cst = torch.zeros(256, device=DEV)
+            yc = ops.conv3x3(xc, wc, cst)
+            res.append((d, st, g, h.dsums, yc, cst))
+    finally:
+        nat.set_epilogue_warps(8)
+    for i in (0, 2, 4):
+        assert torch.equal(res[0][i], res[1][i]), i
+    for i in (1, 3, 5):
+        assert _rel(res[0][i], res[1][i]) < 1e-4, i
+    assert _rel(res[0][0], a.float() @ b.float().t()) < 1e-2
+    assert _rel(res[0][3], _bn_ref_sums(res[0][2], x, None, h.mean, h.rstd, h.gamma, h.beta, True)) < 5e-3
+
+
 def test_persistent_gemm_epilogue_scale_shift_relu():
     torch.manual_seed(1)
     m, n, k = 5000, 256, 192

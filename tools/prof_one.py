@@ -11,6 +11,7 @@ captures exactly the kernel of interest.
   wgrad3 N CIN COUT H W [SPLIT]        tcgen05 3x3 weight gradient
   conv3g N C COUT H W GROUPS           inference 3x3 (grouped) convolution with folded-BN epilogue (the teacher's layers)
   gemmi  M K N                         inference 1x1 convolution: GEMM + scale / shift / ReLU epilogue (wide tiles)
+  dgradbn M K N [y]                    1x1 dgrad with the fused BatchNorm-backward reduction in its epilogue
   sgd | softce B | rope T H D          fused optimizer / loss / rotary kernels
 """
 import os
@@ -90,6 +91,20 @@ elif op == "gemmi":
     y = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
     sc, sh = torch.rand(n, device=dev) + 0.5, torch.randn(n, device=dev) * 0.1
     run(lambda: ops.gemm_bf16(x, w, out=y, col_scale=sc, col_shift=sh, relu=True))
+elif op == "dgradbn":
+    from edl_b200.ops.bn import BNBackwardHook
+    m, k, n = int(a[0]), int(a[1]), int(a[2])
+    dyv = torch.randn(m, k, device=dev).bfloat16()
+    w = (torch.randn(k, n, device=dev) * 0.1).bfloat16()
+    h = BNBackwardHook()
+    h.x = torch.randn(m, n, device=dev).bfloat16()
+    h.y = torch.randn(m, n, device=dev).bfloat16() if len(a) > 3 else None
+    h.relu = True
+    h.mean, h.rstd = torch.randn(n, device=dev) * 0.1, torch.rand(n, device=dev) + 0.5
+    h.gamma, h.beta = torch.rand(n, device=dev) + 0.5, torch.randn(n, device=dev) * 0.2
+    h.dsums = torch.zeros(2 * n, device=dev)
+    out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+    run(lambda: ops.gemm_bf16(dyv, w, out=out, b_mn_major=True, bn=h))
 elif op == "wgrad3":
     n, c, k, h, w = [int(v) for v in a[:5]]          # batch, Cin, Cout, H, W
     from edl_b200.ops import gemm as G
