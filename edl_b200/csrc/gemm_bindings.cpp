@@ -387,6 +387,12 @@ void register_gemm_bindings(pybind11::module_& m) {
   m.def("set_wide_gemm_tiles", &edl::set_wide_gemm_tiles);
   m.def("set_pair_gemm", &edl::set_pair_gemm);
   m.def("get_pair_gemm", &edl::get_pair_gemm);
+  m.def("set_persist_trace", [](c10::optional<Tensor> t) {
+    if (!t.has_value()) { edl::set_persist_trace(nullptr); return; }
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kLong && t->numel() >= 3 * 16 * 8 && t->is_contiguous(),
+                "trace buffer: contiguous CUDA int64 tensor with at least 384 elements");
+    edl::set_persist_trace(reinterpret_cast<long long*>(t->data_ptr<int64_t>()));
+  });
   m.def("set_epilogue_warps", &edl::set_epilogue_warps);
   m.def("set_conv_halo", &edl::set_conv_halo);
   m.def("get_conv_halo", &edl::get_conv_halo);

@@ -70,7 +70,15 @@ struct PersistParams {
   // stride-1 convolutions over the output gradient -- one per parity class of the input pixel -- with 1, 2, 2 and 4 taps.
   int ntaps;
   signed char tap_dh[9], tap_dw[9], tap_w[9];
+  // debug: per-phase clock64() stamps of CTA 0 (tools/trace_persist.py), [3 roles][kTraceTiles][8 phases]
+  long long* trace;
 };
+constexpr int kTraceTiles = 16;
+#define EDL_TRACE(role, tile, phase)                                                                    \
+  do {                                                                                                  \
+    if (p.trace != nullptr && blockIdx.x == 0 && (tile) < kTraceTiles)                                  \
+      p.trace[((role) * kTraceTiles + (tile)) * 8 + (phase)] = clock64();                               \
+  } while (0)
 
 // ASTAGES > 0 selects the "haloed A tile" layout of the 3x3 convolution modes (see the kernel): the A tiles (one per filter
 // ROW and k-block, 128 rows + a 1 KB zero pad on either side) and the B tiles (one per filter TAP) then live in two
@@ -322,6 +330,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          if (i == 0 && lane == 0) EDL_TRACE(0, (t - t_begin) / t_step, 0);
           uint8_t* sa = smem + s * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           if (!kConv) {
@@ -424,11 +433,14 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           continue;
         }
+        if (lane == 0) EDL_TRACE(1, tc, 0);
         for (int i = 0; i < p.num_kb; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           ptx::mbar_wait(&full_bar[s], ph);
           ptx::tc_fence_after();
+          if (lane == 0 && i == 0) EDL_TRACE(1, tc, 1);
+          if (lane == 0 && i == p.num_kb - 1) EDL_TRACE(1, tc, 2);
           const uint32_t sa = ptx::smem_u32(smem + s * L::kStageBytes);
           const uint32_t sb = sa + L::kABytes;
           const uint64_t da0 = ptx::make_smem_desc(sa, 16, 1024);
@@ -465,8 +477,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int img0 = kConv ? (tile_m / p.tiles_h) * p.BN : 0;
       const int h0 = kConv ? (tile_m % p.tiles_h) * p.BH : 0;
       // the staging tile must have been read by the previous TMA store and by every stats thread
+      if (et == 0) EDL_TRACE(2, tc, 0);
       if (et == 0) ptx::tma_store_wait_read0();
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      if (et == 0) EDL_TRACE(2, tc, 1);
       // addend (if any): TMA-load its tile into the staging buffer (same swizzled layout as the output)
       // while the MMAs of this tile are still running; every thread later adds its own 16-byte pieces
       const bool has_add = !kConv && p.add_src != nullptr;
@@ -519,6 +533,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       ptx::mbar_wait(&tmem_full[slot], aph);
       ptx::tc_fence_after();
+      if (et == 0) EDL_TRACE(2, tc, 2);
       const uint32_t taddr = tmem_base + slot * BLOCK_N + grp * kColsPerGrp + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c32 = 0; c32 < kColsPerGrp / 32; ++c32) {
@@ -657,8 +672,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (store_ok) ptx::sts128(rowp + ((chunk ^ (srow & 7)) << 4), u.x, u.y, u.z, u.w);
         }
       }
+      if (et == 0) EDL_TRACE(2, tc, 3);
       ptx::fence_proxy_async_smem();
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      if (et == 0) EDL_TRACE(2, tc, 4);
       if (BNR == 1 && et == 0 && has_next)   // x / y buffers are free: prefetch the next tile's
         issue_bn_tiles<BLOCK_N, kConv>(p, next_tm, next_n0, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
       if (et == 0) {
@@ -678,6 +695,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // reduced in registers with a 31-shuffle transpose per 32 columns and pass: 46-59 us per short-K dgrad kernel
         // instead of 15 us, profiles/README.md.)
         ptx::mbar_wait(bn_bar, tc & 1);
+        if (et == 0) EDL_TRACE(2, tc, 5);
         constexpr int kPairs = BLOCK_N / 2;
         constexpr int kSplit = kEpiThreads / kPairs;
         const int pair = et % kPairs;
@@ -749,7 +767,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         // everybody is done with this tile's x / y: fetch the next tile's while its MMAs run
+        if (et == 0) EDL_TRACE(2, tc, 6);
         asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");
+        if (et == 0) EDL_TRACE(2, tc, 7);
         if (et == 0 && has_next)
           issue_bn_tiles<BLOCK_N, kConv>(p, next_tm, next_n0, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
       }
@@ -832,6 +852,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
+        if (et == 0) EDL_TRACE(2, tc, 6);
       }
     }
     if (local_stats) {
@@ -859,6 +880,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 bool g_persistent = true;
+long long* g_trace = nullptr;
 bool g_wide_tiles = [] {
   const char* e = getenv("EDL_GEMM_WIDE");
   return !(e != nullptr && e[0] == '0');
@@ -928,9 +950,11 @@ const char* launch_pe(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   }
   const int total = p.tiles_m * p.tiles_n;
   const int grid = total < kNumSMs ? total : kNumSMs;
+  PersistParams pt = p;
+  pt.trace = g_trace;
   cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)L::kTotal, stream, tmA, tmB, tmD,
                              tmAdd != nullptr ? *tmAdd : tmD, tmBnX != nullptr ? *tmBnX : tmD,
-                             tmBnY != nullptr ? *tmBnY : tmD, p);
+                             tmBnY != nullptr ? *tmBnY : tmD, pt);
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -1113,6 +1137,7 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
 }
 
 void set_epilogue_warps(int n) { g_epi16 = n >= 16; }
+void set_persist_trace(long long* buf) { g_trace = buf; }
 void set_conv_halo(bool on) { g_conv_halo = on; }
 void set_conv_resident_weights(bool on) { g_conv_bres = on; }
 bool get_conv_halo() { return g_conv_halo; }

@@ -292,7 +292,8 @@ def _bn_fusable(hook, x, channels) -> bool:
     from . import native
 
     return (hook is not None and FUSE_BN_BWD and not hook.done and x.is_cuda and hook.x.shape == x.shape
-            and channels % 8 == 0 and native().persistent_gemm_enabled())
+            and channels % 8 == 0 and native().persistent_gemm_enabled()
+            and x.numel() * x.element_size() <= FUSE_BN_BWD_MAX_BYTES)
 
 
 # ON by default since round 2 (EDL_FUSE_BN_BWD=0 turns it off): the BatchNorm-backward reduction of a conv's input
@@ -302,6 +303,11 @@ def _bn_fusable(hook, x, channels) -> bool:
 # ResNet50_vd step: 4.746 -> 4.618 ms (profiles/bench_runs.json).  The round-1 shuffle version (mode 1, 46-59 us per
 # short-K dgrad kernel) stays selectable with EDL_BNR_MODE=1.
 FUSE_BN_BWD = __import__("os").environ.get("EDL_FUSE_BN_BWD", "1") == "1"
+# Upper bound on the activation size for which the reduction is fused (EDL_FUSE_BN_BWD_MAX_MB).  The fused epilogue
+# prefetches the BN input / output tiles of ONE tile ahead (64 KB per SM in flight), which is latency-bound on the
+# largest activations (51 MB at 56 x 56 x 256 x 32: 63-75 us per dgrad, kineto_r2_c24 trace); the stand-alone streaming
+# reduction reads them at full bandwidth.
+FUSE_BN_BWD_MAX_BYTES = float(__import__("os").environ.get("EDL_FUSE_BN_BWD_MAX_MB", "1e9")) * (1 << 20)
 
 
 class _LinearFn(torch.autograd.Function):
