@@ -137,6 +137,7 @@ const char* gemm_bf16_pair(const GemmArgs& args, cudaStream_t stream);
 void set_pair_gemm(bool on);
 bool get_pair_gemm();
 void set_persist_trace(long long* buf);   // debug: int64 [3 * 16 * 8] device buffer for clock64() phase stamps of CTA 0, or nullptr
+void set_tc_stats(bool on);          // forward BN statistics as tensor-core Gram / ones products of the staged tile (EDL_TC_STATS)
 void set_epilogue_warps(int n);      // 8 or 16 epilogue warps for the 128 / 256 column persistent kernels (EDL_EPI_WARPS)
 void set_conv_halo(bool on);         // haloed A tiles for the 3x3 / stride 1 fprop and dgrad (default on; EDL_CONV_HALO=0)
 bool get_conv_halo();

@@ -393,6 +393,7 @@ void register_gemm_bindings(pybind11::module_& m) {
                 "trace buffer: contiguous CUDA int64 tensor with at least 384 elements");
     edl::set_persist_trace(reinterpret_cast<long long*>(t->data_ptr<int64_t>()));
   });
+  m.def("set_tc_stats", &edl::set_tc_stats);
   m.def("set_epilogue_warps", &edl::set_epilogue_warps);
   m.def("set_conv_halo", &edl::set_conv_halo);
   m.def("get_conv_halo", &edl::get_conv_halo);

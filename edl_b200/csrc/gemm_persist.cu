@@ -34,7 +34,7 @@ constexpr int kUmmaK = 16;
 // quarter of the columns each).  The short-K layers of the student are bound by the epilogue's instruction LATENCY, not by
 // its issue slots (profiles/prof_c25_fwd_s1.ncu.txt: 35 % of the issue slots used, 0.47 eligible warps per scheduler and
 // cycle with 2.5 resident warps per scheduler), so the 128- and 256-column kernels run 16.
-constexpr int kMaxEpiWarps = 16;
+
 // BatchNorm statistics are accumulated per CTA in shared memory over ALL the tiles it processes and
 // pushed to global memory once at the end: with one reduction request per tile and column group the
 // L2 retires ~12 requests/ns into the few hot lines, which made the 1568-tile 1x1 convs atomic-bound
@@ -63,6 +63,7 @@ struct PersistParams {
   int n_img, H, W, kc_blocks, c_in_w, BH, BN, tiles_h;
   int Wb;                         // halo layout: columns per image row of the A tile (W + 1)
   int b_res;                      // halo layout, one k-block per tap: the nine B tap tiles stay resident (see kRes)
+  int tc_stats;                   // BatchNorm statistics of the stored tile on the tensor cores (see kTcStats)
   int cin_g, cout_g;              // grouped fprop: channels per group (cout_g == N for a dense conv)
   int stride;                     // conv fprop: 1, or 2 (input rows 2*h + r - 1; the columns come from the tensor map)
   // explicit tap list (conv modes; 0 = the nine standard taps): k-block i belongs to tap i / kc_blocks, which reads the
@@ -99,7 +100,9 @@ struct PSmem {
   static constexpr int kConstOffset = kXOffset + kXYBytes;        // BNR: mean, rstd, scale, shift of the tile's columns
   static constexpr int kConstBytes = BNR ? 4 * BLOCK_N * 4 : 0;    // float4 {mean, rstd, scale, shift} per column
   static constexpr int kStatsOffset = kConstOffset + kConstBytes;
-  static constexpr int kBarOffset = kStatsOffset + kStatsBytes;
+  static constexpr int kOnesOffset = kStatsOffset + kStatsBytes;   // bf16 ones [16 x 128], the B operand of the column sums
+  static constexpr int kOnesBytes = (BLOCK_N == 128 && BNR == 0) ? 4096 : 0;
+  static constexpr int kBarOffset = kOnesOffset + kOnesBytes;
   static constexpr int kTotal = kBarOffset + 512 + 1024;
 };
 
@@ -127,7 +130,8 @@ EDL_DEVICE float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-// BNR: TMA loads of the BN input (and output) tile that belongs to output tile `tt`
+// BNR: TMA loads of the BN input (and output) tile of output tile (tm, nn0).  Called by a WHOLE warp (warp-uniform
+// arguments); one elected lane issues.
 template <int BLOCK_N, bool CONV>
 EDL_DEVICE void issue_bn_tiles(const PersistParams& p, int tm, int nn0, int rows_tile, uint8_t* sx, uint8_t* sy,
                                const CUtensorMap* tmX, const CUtensorMap* tmY, uint64_t* bar) {
@@ -138,18 +142,21 @@ EDL_DEVICE void issue_bn_tiles(const PersistParams& p, int tm, int nn0, int rows
 #pragma unroll
   for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) halves += (nn0 + hh * 64 < p.N) ? 1u : 0u;
   const uint32_t tile_bytes = CONV ? (uint32_t)rows_tile * 128u : (uint32_t)(kBlockM * 128);
-  ptx::mbar_arrive_expect_tx(bar, halves * tile_bytes * (p.bn_has_y ? 2u : 1u));
+  if (ptx::elect_one()) {
+    ptx::mbar_arrive_expect_tx(bar, halves * tile_bytes * (p.bn_has_y ? 2u : 1u));
 #pragma unroll
-  for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) {
-    if (nn0 + hh * 64 >= p.N) continue;
-    if (!CONV) {
-      ptx::tma_load_2d(sx + hh * (kBlockM * 128), tmX, bar, nn0 + hh * 64, mm0);
-      if (p.bn_has_y) ptx::tma_load_2d(sy + hh * (kBlockM * 128), tmY, bar, nn0 + hh * 64, mm0);
-    } else {
-      ptx::tma_load_4d(sx + hh * (kBlockM * 128), tmX, bar, nn0 + hh * 64, 0, hh0, im0);
-      if (p.bn_has_y) ptx::tma_load_4d(sy + hh * (kBlockM * 128), tmY, bar, nn0 + hh * 64, 0, hh0, im0);
+    for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) {
+      if (nn0 + hh * 64 >= p.N) continue;
+      if (!CONV) {
+        ptx::tma_load_2d(sx + hh * (kBlockM * 128), tmX, bar, nn0 + hh * 64, mm0);
+        if (p.bn_has_y) ptx::tma_load_2d(sy + hh * (kBlockM * 128), tmY, bar, nn0 + hh * 64, mm0);
+      } else {
+        ptx::tma_load_4d(sx + hh * (kBlockM * 128), tmX, bar, nn0 + hh * 64, 0, hh0, im0);
+        if (p.bn_has_y) ptx::tma_load_4d(sy + hh * (kBlockM * 128), tmY, bar, nn0 + hh * 64, 0, hh0, im0);
+      }
     }
   }
+  __syncwarp();
 }
 
 template <int BLOCK_N, int STAGES, int MODE, int BNR, int ASTAGES, int EPIW>
@@ -186,6 +193,17 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // flip once per N-tile change.  profiles/teacher_c22_*.txt: the grouped 14 x 14 layers of the teacher moved 229 MB
   // from L2 per launch, 147 MB of it the same 2.4 MB of weights fetched by each of the 64 pixel tiles.
   constexpr bool kRes = kHalo && BLOCK_N == 64 && STAGES == 9;
+  // BatchNorm statistics on the tensor cores (128-column tiles, no BNR): the bf16 tile Y that the epilogue packs into the
+  // staging buffer ([128 rows][64 columns x 128 B] halves, 128-byte swizzle) IS a valid MN-major UMMA operand with the
+  // tile ROWS as the contraction dimension.  Two small MMA batches per tile, issued by an epilogue thread right after
+  // the TMA store:
+  //     G[n, n'] = sum_r Y[r, n] Y[r, n']   (A = B = Y, both MN-major; 128 x 128 x 128)   -> diag G = sum of squares
+  //     S[n, j]  = sum_r Y[r, n] * 1        (A = Y, B = a 16 x 128 tile of ones, K-major) -> column sums
+  // accumulated in spare TMEM columns ACROSS the tiles of a CTA that share the N tile and read back once per run -- exact
+  // fp32 sums of the stored bf16 values, in place of the column-pair loop over the staging tile that took 2070 of the
+  // 3850 cycles a short-K tile spends in the epilogue (profiles/trace_persist_c28.txt).
+  constexpr bool kTcStats = BLOCK_N == 128 && BNR == 0 && MODE != 1 && MODE != 3;
+  constexpr uint32_t kGramCol = 2 * BLOCK_N, kSumCol = 3 * BLOCK_N;     // TMEM columns behind the two accumulators
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -204,8 +222,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* bn_bar = add_bar + 1;                        // BN x (/ y) tiles landed
   uint64_t* afull_bar = bn_bar + 1;                      // halo layout: the A ring's barriers
   uint64_t* aempty_bar = afull_bar + (kHalo ? ASTAGES : 0);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + (kHalo ? ASTAGES : 0));
-  static_assert((2 * STAGES + 6 + 2 * ASTAGES) * 8 + 4 <= 512, "barrier block");
+  uint64_t* stat_bar = aempty_bar + (kHalo ? ASTAGES : 0);   // statistics MMAs of a tile have read the staging buffer
+  uint64_t* stage_rdy = stat_bar + 1;                        // the staging buffer holds a complete tile (epilogue -> MMA warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_rdy + 1);
+  static_assert((2 * STAGES + 8 + 2 * ASTAGES) * 8 + 4 <= 512, "barrier block");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -231,7 +251,11 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   };
   constexpr uint32_t kTmemCols =
-      2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+      kTcStats ? 512
+               : (2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512))));
+  // (conv: only the halo layout keeps rows behind the tile at zero; no epilogue constants, so rows outside the matrix are 0)
+  const bool tcs = kTcStats && p.tc_stats != 0 && local_stats && (!kConv || kHalo) && p.col_scale == nullptr &&
+                   p.col_shift == nullptr && p.relu == 0 && p.add_src == nullptr;
   static_assert(2 * BLOCK_N <= 512, "two accumulators must fit the 512 TMEM columns");
 
   if (warp == 0 && lane == 0) {
@@ -248,6 +272,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     ptx::mbar_init(add_bar, 1);
     ptx::mbar_init(bn_bar, 1);
+    ptx::mbar_init(stat_bar, 1);
+    ptx::mbar_init(stage_rdy, 1);
     for (int s = 0; s < ASTAGES; ++s) {
       ptx::mbar_init(&afull_bar[s], 1);
       ptx::mbar_init(&aempty_bar[s], 1);
@@ -257,6 +283,14 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_slot);
   if (local_stats)
     for (int i = threadIdx.x; i < 2 * p.N; i += kThreads) sstats[i] = 0.f;
+  if (tcs) {
+    // ones tile; and a zeroed staging buffer: rows the epilogue never writes (halo layout: rows behind the tile) are
+    // part of the contraction
+    for (int i = threadIdx.x; i < L::kOnesBytes / 16; i += kThreads)
+      ptx::sts128(ptx::smem_u32(smem + L::kOnesOffset) + i * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    for (int i = threadIdx.x; i < L::kDBytes / 16; i += kThreads) ptx::sts128(ptx::smem_u32(sd) + i * 16, 0u, 0u, 0u, 0u);
+    ptx::fence_proxy_async_smem();
+  }
   if (kHalo) {
     // pads AND tiles: TMA only ever writes the first rows_in rows of a tile, the rows behind them must read as zero
     for (int i = threadIdx.x; i < L::kARingBytes / 16; i += kThreads) ptx::sts128(ptx::smem_u32(smem) + i * 16, 0u, 0u, 0u, 0u);
@@ -389,6 +423,37 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       [[maybe_unused]] uint32_t ita = 0;
       [[maybe_unused]] int cur_n0 = -1;
       [[maybe_unused]] uint32_t gcount = 0;
+      // Tensor-core statistics of tile i (see kTcStats), issued from this warp AFTER the main MMAs of tile i + 1 so that
+      // neither the epilogue warps nor the accumulator pipeline wait for them: the batch reads ~100 KB of shared memory
+      // (~2000 cycles at the rate MN-major operands are fetched, profiles/trace_persist_c30.txt).
+      [[maybe_unused]] auto issue_stats = [&](uint32_t i) {
+        if constexpr (kTcStats) {
+          int tm_i, n0_i, tm_p, n0_p = -1;
+          tile_coords(t_begin + (int)i * t_step, tm_i, n0_i);
+          if (i > 0) tile_coords(t_begin + (int)(i - 1) * t_step, tm_p, n0_p);
+          const uint32_t acc_flag = n0_p == n0_i ? 1u : 0u;     // earlier tiles of the same N tile are in the TMEM sums
+          ptx::mbar_wait(stage_rdy, i & 1);
+          ptx::tc_fence_after();
+          constexpr uint32_t idesc_g = ptx::make_idesc(1, 1, kBlockM, BLOCK_N, 1, 1);   // Y^T Y
+          constexpr uint32_t idesc_s = ptx::make_idesc(1, 1, kBlockM, 16, 1, 0);        // Y^T ones
+          // Y as MN-major operand: 64-column halves kBlockM * 128 bytes apart (LBO), 8-row groups 1024 bytes apart (SBO),
+          // one UMMA_K step = 16 tile rows = 2048 bytes = 128 units of the start-address field
+          const uint64_t dy0 = ptx::make_smem_desc(ptx::smem_u32(sd), kBlockM * 128, 1024);
+          // ones tile, K-major: [16 rows][64 k] halves 2048 bytes apart, 32 bytes (2 units) per k step inside a half
+          const uint64_t d10 = ptx::make_smem_desc(ptx::smem_u32(smem + L::kOnesOffset), 16, 1024);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int j = 0; j < kBlockM / kUmmaK; ++j) {
+              const uint64_t dy = dy0 + (uint64_t)(j * 128);
+              const uint64_t d1 = d10 + (uint64_t)((j >> 2) * 128 + (j & 3) * 2);
+              ptx::umma_f16(tmem_base + kGramCol, dy, dy, idesc_g, j != 0 ? 1u : acc_flag);
+              ptx::umma_f16(tmem_base + kSumCol, dy, d1, idesc_s, j != 0 ? 1u : acc_flag);
+            }
+            ptx::umma_commit(stat_bar);
+          }
+          __syncwarp();
+        }
+      };
       for (int t = t_begin; t < t_end; t += t_step, ++tc) {
         const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
         ptx::mbar_wait(&tmem_empty[slot], aph ^ 1);      // epilogue has drained this accumulator
@@ -431,6 +496,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               __syncwarp();
             }
           }
+          if (kTcStats && tcs && tc > 0) issue_stats(tc - 1);
           continue;
         }
         if (lane == 0) EDL_TRACE(1, tc, 0);
@@ -454,7 +520,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           __syncwarp();
         }
+        if (kTcStats && tcs && tc > 0) issue_stats(tc - 1);
       }
+      if (kTcStats && tcs && tc > 0) issue_stats(tc - 1);      // the last tile's
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
@@ -466,6 +534,13 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int kColsPerGrp = BLOCK_N / kColGroups;
     int const_n0 = -1;
     uint32_t tc = 0;
+    // Column sums of the statistics / BN-backward loops stay in registers across the tiles of a run that share the N tile
+    // (a thread always owns the same column pair) and go to the CTA-local accumulators once per run: fp32 atomicAdd on
+    // shared memory is a compare-and-swap loop (ATOMS.CAST.SPIN), and with kSplit threads per column hitting the same
+    // word four times per tile it cost several hundred cycles of every tile (profiles/trace_persist_c32.txt).
+    [[maybe_unused]] float run_s0 = 0.f, run_s1 = 0.f, run_q0 = 0.f, run_q1 = 0.f;
+    [[maybe_unused]] uint32_t stat_batches = 0;      // statistic MMA batches committed so far (phase of stat_bar)
+    [[maybe_unused]] bool stat_acc = false;          // the TMEM statistics hold earlier tiles of the current N tile
     for (int t = t_begin; t < t_end; t += t_step, ++tc) {
       const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
       int tile_m, n0;
@@ -478,21 +553,28 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int h0 = kConv ? (tile_m % p.tiles_h) * p.BH : 0;
       // the staging tile must have been read by the previous TMA store and by every stats thread
       if (et == 0) EDL_TRACE(2, tc, 0);
-      if (et == 0) ptx::tma_store_wait_read0();
+      // (bulk groups belong to the thread that issued the stores: always the elected lane of epilogue warp 0)
+      if (ew == 0) {
+        if (ptx::elect_one()) ptx::tma_store_wait_read0();
+        __syncwarp();
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (et == 0) EDL_TRACE(2, tc, 1);
       // addend (if any): TMA-load its tile into the staging buffer (same swizzled layout as the output)
       // while the MMAs of this tile are still running; every thread later adds its own 16-byte pieces
       const bool has_add = !kConv && p.add_src != nullptr;
       if (has_add) {
-        if (et == 0) {
+        if (ew == 0) {
           uint32_t halves = 0;
 #pragma unroll
           for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) halves += (n0 + hh * 64 < p.N) ? 1u : 0u;
-          ptx::mbar_arrive_expect_tx(add_bar, halves * (kBlockM * 128));
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(add_bar, halves * (kBlockM * 128));
 #pragma unroll
-          for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh)
-            if (n0 + hh * 64 < p.N) ptx::tma_load_2d(sd + hh * (kBlockM * 128), &tmAdd, add_bar, n0 + hh * 64, m0);
+            for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh)
+              if (n0 + hh * 64 < p.N) ptx::tma_load_2d(sd + hh * (kBlockM * 128), &tmAdd, add_bar, n0 + hh * 64, m0);
+          }
+          __syncwarp();
         }
         ptx::mbar_wait(add_bar, tc & 1);
       }
@@ -506,7 +588,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int bi = row / rows_per_img, rr = row - bi * rows_per_img;
           row_ok = row < rows_tile && img0 + bi < p.n_img && h0 + rr / p.W < p.H;
         }
-        if (tc == 0 && et == 0)                               // later tiles are prefetched one tile ahead
+        if (tc == 0 && ew == 0)                               // later tiles are prefetched one tile ahead
           issue_bn_tiles<BLOCK_N, kConv>(p, tile_m, n0, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
         if (n0 != const_n0) {
           // per-column constants of the BN layer for this N tile (a CTA usually keeps its N tile)
@@ -526,10 +608,13 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // halo layout: accumulator row -> row of the dense staging tile (the halo column's rows are dropped)
       int srow = row;
       bool store_ok = true;
-      if (kHalo) {
+      [[maybe_unused]] bool zero_row = false;      // a staging row outside the image: clipped by the store, but it must
+      if (kHalo) {                                 // not reach the tensor-core statistics
         const int ir = row / p.Wb, cw = row - ir * p.Wb;
         store_ok = cw != 0 && row < rows_in;
         srow = ir * p.W + cw - 1;
+        const int bi = ir / p.BH, hr = ir - bi * p.BH;
+        zero_row = img0 + bi >= p.n_img || h0 + hr >= p.H;
       }
       ptx::mbar_wait(&tmem_full[slot], aph);
       ptx::tc_fence_after();
@@ -607,6 +692,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
+          if (kTcStats && kHalo && tcs && zero_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          }
         }
         if (BNR == 1) {
           // dy = the bf16 value this tile stores; masked by the ReLU of the BN layer, reduced per channel
@@ -659,6 +748,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
+        // the previous tile's statistics MMAs read the staging buffer: they must be done before it is overwritten
+        if (kTcStats && tcs && c32 == 0 && stat_batches > 0) ptx::mbar_wait(stat_bar, (stat_batches - 1) & 1);
         const int half = cbase >> 6;
         const uint32_t rowp = ptx::smem_u32(sd) + half * (kBlockM * 128) + srow * 128;
 #pragma unroll
@@ -676,16 +767,53 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::fence_proxy_async_smem();
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (et == 0) EDL_TRACE(2, tc, 4);
-      if (BNR == 1 && et == 0 && has_next)   // x / y buffers are free: prefetch the next tile's
+      if (BNR == 1 && ew == 0 && has_next)   // x / y buffers are free: prefetch the next tile's
         issue_bn_tiles<BLOCK_N, kConv>(p, next_tm, next_n0, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
-      if (et == 0) {
+      if (ew == 0) {
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) {
-          if (n0 + hh * 64 >= p.N) continue;
-          if (!kConv) ptx::tma_store_2d(&tmD, sd + hh * (kBlockM * 128), n0 + hh * 64, m0);
-          else tma_store_4d_p(&tmD, sd + hh * (kBlockM * 128), n0 + hh * 64, 0, h0, img0);
+          for (int hh = 0; hh < (BLOCK_N + 63) / 64; ++hh) {
+            if (n0 + hh * 64 >= p.N) continue;
+            if (!kConv) ptx::tma_store_2d(&tmD, sd + hh * (kBlockM * 128), n0 + hh * 64, m0);
+            else tma_store_4d_p(&tmD, sd + hh * (kBlockM * 128), n0 + hh * 64, 0, h0, img0);
+          }
+          ptx::tma_store_commit();
         }
-        ptx::tma_store_commit();
+        __syncwarp();
+      }
+      if constexpr (kTcStats) {
+        if (tcs) {
+          if (ew == 0) {
+            // every epilogue thread has written its part of the tile (bar.sync above, generic -> async proxy fence before
+            // it): hand the staging buffer to the MMA warp
+            if (ptx::elect_one()) ptx::mbar_arrive(stage_rdy);
+            __syncwarp();
+          }
+          ++stat_batches;
+          stat_acc = true;
+          if (!has_next || next_n0 != n0) {
+            // last tile of this N tile in the CTA's sequence: read the statistics back into the CTA-local accumulators
+            ptx::mbar_wait(stat_bar, (stat_batches - 1) & 1);
+            ptx::tc_fence_after();
+            if (grp == 0) {
+              const int nrow = q * 32 + lane;                 // TMEM lane = column of the tile
+              const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+              uint32_t g[32];
+              ptx::tmem_ld_32x32(lane_addr + kGramCol + q * 32, g);     // the 32 x 32 diagonal block of this quarter
+              const uint32_t s1 = ptx::tmem_ld_32x1(lane_addr + kSumCol);
+              ptx::tmem_ld_wait();
+              uint32_t gd = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) gd = (j == lane) ? g[j] : gd;
+              if (n0 + nrow < p.N) {
+                atomicAdd(&sstats[n0 + nrow], __uint_as_float(s1));
+                atomicAdd(&sstats[p.N + n0 + nrow], __uint_as_float(gd));
+              }
+            }
+            stat_acc = false;
+            ptx::tc_fence_before();       // ordered before the next batch (accumulate = 0) by the bar.sync at the tile top
+          }
+        }
       }
       if (BNR == 2) {
         // BatchNorm-backward reduction of the tile just staged: per channel sum(dy_m) and sum(dy_m * xhat), dy_m = the
@@ -708,7 +836,28 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const float4 k0 = reinterpret_cast<const float4*>(sconst)[col];          // mean, rstd, scale, shift
         const float4 k1 = reinterpret_cast<const float4*>(sconst)[col + 1];
         const bool relu = p.bn_relu != 0, has_y = p.bn_has_y != 0;
+        // s = sum(dy_m), q = sum(dy_m * x) over this thread's rows; sum(dy_m * xhat) = rstd * (q - mean * s) is formed once
+        // per thread and tile below (two instructions per element less than normalising x in the loop).  With the BN
+        // OUTPUT at hand the ReLU mask is a packed bf16 compare and a multiplication by 1.0 / 0.0 (exact).
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+        auto row_update = [&](uint32_t wd, uint32_t wx, uint32_t wy) {
+          __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(&wd);
+          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wx));
+          float2 d;
+          if (relu && has_y) {
+            d2 = __hmul2(d2, __hgt2(*reinterpret_cast<const __nv_bfloat162*>(&wy), zero2));
+            d = __bfloat1622float2(d2);
+          } else {
+            d = __bfloat1622float2(d2);
+            if (relu) {
+              d.x = fmaf(x.x, k0.z, k0.w) > 0.f ? d.x : 0.f;
+              d.y = fmaf(x.y, k1.z, k1.w) > 0.f ? d.y : 0.f;
+            }
+          }
+          s0 += d.x; q0 = fmaf(d.x, x.x, q0);
+          s1 += d.y; q1 = fmaf(d.y, x.y, q1);
+        };
         auto accum_rows = [&](int r_begin, int r_end) {
           int rr = r_begin + part;
           for (; rr + 7 * kSplit < r_end; rr += 8 * kSplit) {
@@ -722,28 +871,11 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               wy[u] = has_y ? ptx::lds32(basey + o) : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wd[u]));
-              const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wx[u]));
-              const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wy[u]));
-              const bool m0 = !relu || (has_y ? y.x > 0.f : fmaf(x.x, k0.z, k0.w) > 0.f);
-              const bool m1 = !relu || (has_y ? y.y > 0.f : fmaf(x.y, k1.z, k1.w) > 0.f);
-              const float d0 = m0 ? d.x : 0.f, d1 = m1 ? d.y : 0.f;
-              s0 += d0; q0 = fmaf(d0, (x.x - k0.x) * k0.y, q0);
-              s1 += d1; q1 = fmaf(d1, (x.y - k1.x) * k1.y, q1);
-            }
+            for (int u = 0; u < 8; ++u) row_update(wd[u], wx[u], wy[u]);
           }
           for (; rr < r_end; rr += kSplit) {
             const uint32_t o = rr * 128 + ((chunk ^ (rr & 7)) << 4);
-            const uint32_t wd = ptx::lds32(based + o), wx = ptx::lds32(basex + o), wy = has_y ? ptx::lds32(basey + o) : 0u;
-            const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wd));
-            const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wx));
-            const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wy));
-            const bool m0 = !relu || (has_y ? y.x > 0.f : fmaf(x.x, k0.z, k0.w) > 0.f);
-            const bool m1 = !relu || (has_y ? y.y > 0.f : fmaf(x.y, k1.z, k1.w) > 0.f);
-            const float d0 = m0 ? d.x : 0.f, d1 = m1 ? d.y : 0.f;
-            s0 += d0; q0 = fmaf(d0, (x.x - k0.x) * k0.y, q0);
-            s1 += d1; q1 = fmaf(d1, (x.y - k1.x) * k1.y, q1);
+            row_update(ptx::lds32(based + o), ptx::lds32(basex + o), has_y ? ptx::lds32(basey + o) : 0u);
           }
         };
         if (valid) {
@@ -758,22 +890,35 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (hv > p.BH) hv = p.BH;
             for (int b = 0; b < p.BN && img0 + b < p.n_img; ++b) accum_rows(b * rows_per_img, b * rows_per_img + hv * p.W);
           }
-          float* dst = local_stats ? sstats : p.bn_dsums;
-          atomicAdd(&dst[n0 + col], s0);
-          atomicAdd(&dst[p.N + n0 + col], q0);
-          if (n0 + col + 1 < p.N) {
-            atomicAdd(&dst[n0 + col + 1], s1);
-            atomicAdd(&dst[p.N + n0 + col + 1], q1);
+          run_s0 += s0; run_q0 += (q0 - k0.x * s0) * k0.y;          // k = {mean, rstd, scale, shift}
+          run_s1 += s1; run_q1 += (q1 - k1.x * s1) * k1.y;
+          if (!has_next || next_n0 != n0) {
+            if (local_stats) {
+              atomicAdd(&sstats[n0 + col], run_s0);
+              atomicAdd(&sstats[p.N + n0 + col], run_q0);
+              if (n0 + col + 1 < p.N) {
+                atomicAdd(&sstats[n0 + col + 1], run_s1);
+                atomicAdd(&sstats[p.N + n0 + col + 1], run_q1);
+              }
+            } else {
+              atomicAdd(&p.bn_dsums[n0 + col], run_s0);
+              atomicAdd(&p.bn_dsums[p.N + n0 + col], run_q0);
+              if (n0 + col + 1 < p.N) {
+                atomicAdd(&p.bn_dsums[n0 + col + 1], run_s1);
+                atomicAdd(&p.bn_dsums[p.N + n0 + col + 1], run_q1);
+              }
+            }
           }
         }
+        if (!has_next || next_n0 != n0) run_s0 = run_s1 = run_q0 = run_q1 = 0.f;
         // everybody is done with this tile's x / y: fetch the next tile's while its MMAs run
         if (et == 0) EDL_TRACE(2, tc, 6);
         asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");
         if (et == 0) EDL_TRACE(2, tc, 7);
-        if (et == 0 && has_next)
+        if (ew == 0 && has_next)
           issue_bn_tiles<BLOCK_N, kConv>(p, next_tm, next_n0, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
       }
-      if (!BNR && p.col_stats != nullptr) {
+      if (!BNR && p.col_stats != nullptr && !tcs) {
         // Per-channel sum / sum of squares of the STORED bf16 values, from the staged tile.  A thread owns
         // a PAIR of adjacent columns (one 32-bit shared load per row) and every kSplit-th row; eight
         // independent loads are in flight per thread (the naive one-column, one-accumulator loop was the
@@ -822,7 +967,12 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int b = 0; b < p.BN && img0 + b < p.n_img; ++b) accum_rows(b * rows_per_img, b * rows_per_img + hv * p.W);
           }
         }
-        if (local_stats) {
+        run_s0 += s0; run_s1 += s1; run_q0 += q0; run_q1 += q1;
+        const bool run_end = !has_next || next_n0 != n0;
+        if (run_end) { s0 = run_s0; s1 = run_s1; q0 = run_q0; q1 = run_q1; run_s0 = run_s1 = run_q0 = run_q1 = 0.f; }
+        if (!run_end) {
+          // the sums travel on in registers
+        } else if (local_stats) {
           if (valid) {
             atomicAdd(&sstats[n0 + col], s0);
             atomicAdd(&sstats[p.N + n0 + col], q0);
@@ -869,7 +1019,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (sstats[i] != 0.f) atomicAdd(&stats_dst[i], sstats[i]);
       }
     }
-    if (et == 0) ptx::tma_store_wait_read0();
+    if (ew == 0) {
+      if (ptx::elect_one()) ptx::tma_store_wait_read0();
+      __syncwarp();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -893,6 +1046,15 @@ bool g_conv_halo = [] {
   return !(e != nullptr && e[0] == '0');
 }();
 
+// BatchNorm statistics of the forward tiles on the tensor cores (EDL_TC_STATS=1).  Exact and validated
+// (tests/test_persist_gpu.py), but NOT faster than the column-pair loop: the two MMA batches read ~100 KB of shared memory
+// per tile as MN-major operands and compete with the TMA store and the next tile's pack for the same shared memory
+// (3600 vs 3850 cycles per short-K tile, the student step 4.403 vs 4.402 ms: profiles/trace_persist_c31.txt), so the loop
+// stays the default.
+bool g_tc_stats = [] {
+  const char* e = getenv("EDL_TC_STATS");
+  return e != nullptr && e[0] == '1';
+}();
 bool g_conv_bres = [] {
   const char* e = getenv("EDL_CONV_BRES");
   return !(e != nullptr && e[0] == '0');
@@ -1022,6 +1184,7 @@ const char* gemm_bf16_persistent(const GemmArgs& g, cudaStream_t stream) {
   p.num_kb = (g.K + kBlockK - 1) / kBlockK;
   p.col_scale = g.col_scale; p.col_shift = g.col_shift; p.relu = g.relu ? 1 : 0;
   p.col_stats = g.col_stats;
+  p.tc_stats = g_tc_stats ? 1 : 0;
   p.add_src = reinterpret_cast<const __nv_bfloat16*>(g.add_src);
   p.ld_add = g.ld_add;
   alignas(64) CUtensorMap tmAdd;
@@ -1099,6 +1262,7 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
   p.num_kb = (halo ? 3 : 9) * p.kc_blocks;
   p.Wb = halo ? a.W + 1 : a.W;
   p.b_res = (halo && n64 && p.kc_blocks == 1 && g_conv_bres) ? 1 : 0;
+  p.tc_stats = (halo && g_tc_stats) ? 1 : 0;
   p.col_stats = dg ? nullptr : a.col_stats;
   p.col_scale = dg ? nullptr : a.col_scale;
   p.col_shift = dg ? nullptr : a.col_shift;
@@ -1137,6 +1301,7 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
 }
 
 void set_epilogue_warps(int n) { g_epi16 = n >= 16; }
+void set_tc_stats(bool on) { g_tc_stats = on; }
 void set_persist_trace(long long* buf) { g_trace = buf; }
 void set_conv_halo(bool on) { g_conv_halo = on; }
 void set_conv_resident_weights(bool on) { g_conv_bres = on; }

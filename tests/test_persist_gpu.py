@@ -130,6 +130,41 @@ def test_sixteen_epilogue_warps_match_eight(m, n, k):
     assert _rel(res[0][3], _bn_ref_sums(res[0][2], x, None, h.mean, h.rstd, h.gamma, h.beta, True)) < 5e-3
 
 
+@pytest.mark.parametrize("kind,shape", [("gemm", (100352, 256, 64)), ("gemm", (5000, 192, 192)), ("gemm", (6272, 1024, 256)),
+                                        ("gemm", (300, 128, 64)), ("conv", (32, 128, 128, 28, 28)), ("conv", (5, 128, 256, 11, 20)),
+                                        ("conv", (9, 256, 256, 14, 14)), ("conv", (7, 512, 512, 7, 7))])
+def test_tensor_core_bn_statistics_match_the_column_loop(kind, shape):
+    """Forward BatchNorm statistics as Gram / ones products of the staged bf16 tile on the tensor cores (128-column kernels,
+    EDL_TC_STATS=1; exact but not faster, so not the default) against the column-pair loop and against fp32 sums of the stored output: M tails, a
+    partial N tile (192), alternating N tiles per CTA (1024 columns), conv tiles with partial patches and tail images."""
+    torch.manual_seed(11)
+    nat = ops.native()
+    if kind == "gemm":
+        m, n, k = shape
+        a = torch.randn(m, k, device=DEV).bfloat16()
+        b = (torch.randn(n, k, device=DEV) * 0.05).bfloat16()
+    else:
+        nb, c, n, h, w = shape
+        x = torch.randn(nb, c, h, w, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+        wt = (torch.randn(n, 3, 3, c, device=DEV) * 0.05).bfloat16()
+    res = []
+    try:
+        for tcs in (True, False):
+            nat.set_tc_stats(tcs)
+            st = torch.zeros(2 * n, device=DEV)
+            y = ops.gemm_bf16(a, b, col_stats=st) if kind == "gemm" else ops.conv3x3(x, wt, st)
+            yf = y.float()
+            dims = 0 if kind == "gemm" else (0, 2, 3)
+            res.append((y, st, torch.cat([yf.sum(dims), (yf * yf).sum(dims)])))
+    finally:
+        nat.set_tc_stats(False)
+    assert torch.equal(res[0][0], res[1][0])
+    for y, st, ref in res:
+        assert _rel(st[n:], ref[n:]) < 1e-4          # sums of squares: no cancellation
+        assert (st[:n] - ref[:n]).abs().max().item() < 2e-3 * ref[n:].sqrt().max().item() + 1e-3
+    assert _rel(res[0][1][n:], res[1][1][n:]) < 1e-4
+
+
 def test_persistent_gemm_epilogue_scale_shift_relu():
     torch.manual_seed(1)
     m, n, k = 5000, 256, 192
