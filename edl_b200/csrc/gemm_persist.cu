@@ -240,6 +240,28 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   // tile index -> (M tile, first column): M-major normally (neighbouring CTAs share the A tile in L2), N-major when
   // B is resident
+  // Incremental form for the role loops (an integer division by a run-time value is ~100 cycles of dependent instructions,
+  // and the epilogue needs the coordinates of this tile and the next: ~440 cycles per tile, profiles/trace_persist_c34.txt)
+  struct TileIt { int tm, ni; };
+  const int step_m = res ? 0 : t_step / p.tiles_n, step_n = res ? 0 : t_step - (t_step / p.tiles_n) * p.tiles_n;
+  auto tile_init = [&](int t) -> TileIt {
+    if (res) {
+      const int nt = t / p.tiles_m;
+      return TileIt{t - nt * p.tiles_m, nt};
+    }
+    const int tm = t / p.tiles_n;
+    return TileIt{tm, t - tm * p.tiles_n};
+  };
+  auto tile_next = [&](TileIt c) -> TileIt {
+    if (res) {
+      if (++c.tm >= p.tiles_m) { c.tm = 0; ++c.ni; }
+    } else {
+      c.tm += step_m;
+      c.ni += step_n;
+      if (c.ni >= p.tiles_n) { c.ni -= p.tiles_n; ++c.tm; }
+    }
+    return c;
+  };
   auto tile_coords = [&](int t, int& tm, int& n0) {
     if (res) {
       const int nt = t / p.tiles_m;
@@ -318,9 +340,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       [[maybe_unused]] uint32_t ita = 0;
       [[maybe_unused]] int cur_n0 = -1;
       [[maybe_unused]] uint32_t gcount = 0;
-      for (int t = t_begin; t < t_end; t += t_step) {
-        int tile_m, n0;
-        tile_coords(t, tile_m, n0);
+      TileIt cur = tile_init(t_begin);
+      for (int t = t_begin; t < t_end; t += t_step, cur = tile_next(cur)) {
+        const int tile_m = cur.tm, n0 = cur.ni * BLOCK_N;
         const int m0 = tile_m * kBlockM;
         const int img0 = kConv ? (tile_m / p.tiles_h) * p.BN : 0;
         const int h0 = kConv ? (tile_m % p.tiles_h) * p.BH : 0;
@@ -454,7 +476,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
         }
       };
-      for (int t = t_begin; t < t_end; t += t_step, ++tc) {
+      TileIt cur = tile_init(t_begin);
+      for (int t = t_begin; t < t_end; t += t_step, ++tc, cur = tile_next(cur)) {
         const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
         ptx::mbar_wait(&tmem_empty[slot], aph ^ 1);      // epilogue has drained this accumulator
         ptx::tc_fence_after();
@@ -462,9 +485,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if constexpr (kHalo) {
           bool newg = false, lastg = false;
           if (res) {
-            int tm_, n0_, tm2_, n02_ = -1;
-            tile_coords(t, tm_, n0_);
-            if (t + 1 < t_end) tile_coords(t + 1, tm2_, n02_);
+            const int n0_ = cur.ni * BLOCK_N;
+            const int n02_ = t + 1 < t_end ? tile_next(cur).ni * BLOCK_N : -1;
             newg = n0_ != cur_n0;
             lastg = n02_ != n0_;                     // the slots are handed back after the last tile of the N tile
             if (newg) { cur_n0 = n0_; ++gcount; }
@@ -539,15 +561,35 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // shared memory is a compare-and-swap loop (ATOMS.CAST.SPIN), and with kSplit threads per column hitting the same
     // word four times per tile it cost several hundred cycles of every tile (profiles/trace_persist_c32.txt).
     [[maybe_unused]] float run_s0 = 0.f, run_s1 = 0.f, run_q0 = 0.f, run_q1 = 0.f;
+    // Software-pipelined accumulator read-out (one or two 32-column chunks per warp): TMEM is read at 64 B / clk / SM, i.e.
+    // >= 1024 cycles for a 128 x 128 fp32 tile (profiles/trace_persist_c33.txt: 1200 of a short-K tile's 3470 cycles).
+    // tcgen05.ld is asynchronous until tcgen05.wait::ld, so the loads of tile t + 1 are issued BEFORE the statistics /
+    // BN-backward loop of tile t (if that tile's MMAs are already complete, which they are in the short-K layers) and
+    // collected at the top of the next iteration.
+    constexpr int kNCh = kColsPerGrp / 32;
+    constexpr bool kPipeLd = kNCh <= 2 && BNR != 1;
+    uint32_t rgn[kPipeLd ? kNCh * 32 : 32];            // kNCh chunks of 32 columns, read with one instruction
+    bool ld_inflight = false;
     [[maybe_unused]] uint32_t stat_batches = 0;      // statistic MMA batches committed so far (phase of stat_bar)
     [[maybe_unused]] bool stat_acc = false;          // the TMEM statistics hold earlier tiles of the current N tile
+    TileIt cur = tile_init(t_begin);
+    // halo layout: accumulator row -> row of the dense staging tile (fixed per thread; the halo column's rows are dropped)
+    int srow = row;
+    bool store_ok = true;
+    [[maybe_unused]] int halo_bi = 0, halo_hr = 0;
+    if (kHalo) {
+      const int ir = row / p.Wb, cw = row - ir * p.Wb;
+      store_ok = cw != 0 && row < rows_in;
+      srow = ir * p.W + cw - 1;
+      halo_bi = ir / p.BH;
+      halo_hr = ir - halo_bi * p.BH;
+    }
     for (int t = t_begin; t < t_end; t += t_step, ++tc) {
       const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
-      int tile_m, n0;
-      tile_coords(t, tile_m, n0);
-      int next_tm = 0, next_n0 = 0;
+      const int tile_m = cur.tm, n0 = cur.ni * BLOCK_N;
       const bool has_next = t + t_step < t_end;
-      if (has_next) tile_coords(t + t_step, next_tm, next_n0);
+      cur = tile_next(cur);
+      const int next_tm = cur.tm, next_n0 = cur.ni * BLOCK_N;
       const int m0 = tile_m * kBlockM;
       const int img0 = kConv ? (tile_m / p.tiles_h) * p.BN : 0;
       const int h0 = kConv ? (tile_m % p.tiles_h) * p.BH : 0;
@@ -605,32 +647,42 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (BNR == 1) ptx::mbar_wait(bn_bar, tc & 1);     // mode 2 waits where it reads x / y
       }
-      // halo layout: accumulator row -> row of the dense staging tile (the halo column's rows are dropped)
-      int srow = row;
-      bool store_ok = true;
-      [[maybe_unused]] bool zero_row = false;      // a staging row outside the image: clipped by the store, but it must
-      if (kHalo) {                                 // not reach the tensor-core statistics
-        const int ir = row / p.Wb, cw = row - ir * p.Wb;
-        store_ok = cw != 0 && row < rows_in;
-        srow = ir * p.W + cw - 1;
-        const int bi = ir / p.BH, hr = ir - bi * p.BH;
-        zero_row = img0 + bi >= p.n_img || h0 + hr >= p.H;
-      }
-      ptx::mbar_wait(&tmem_full[slot], aph);
-      ptx::tc_fence_after();
-      if (et == 0) EDL_TRACE(2, tc, 2);
-      const uint32_t taddr = tmem_base + slot * BLOCK_N + grp * kColsPerGrp + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c32 = 0; c32 < kColsPerGrp / 32; ++c32) {
-        uint32_t rg[32];
-        ptx::tmem_ld_32x32(taddr + c32 * 32, rg);
-        ptx::tmem_ld_wait();
-        if (c32 == kColsPerGrp / 32 - 1) {
-          // accumulator fully in registers: hand it back to the MMA warp before the slow part
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty[slot]);
+      // a staging row outside the image is clipped by the store, but it must not reach the tensor-core statistics
+      [[maybe_unused]] const bool zero_row = kHalo && (img0 + halo_bi >= p.n_img || h0 + halo_hr >= p.H);
+      const uint32_t lane_col = grp * kColsPerGrp + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + slot * BLOCK_N + lane_col;
+      if constexpr (kPipeLd) {
+        if (!ld_inflight) {
+          ptx::mbar_wait(&tmem_full[slot], aph);
+          ptx::tc_fence_after();
+          if constexpr (kNCh == 2) ptx::tmem_ld_32x64(taddr, rgn);
+          else ptx::tmem_ld_32x32(taddr, rgn);
         }
+        ptx::tmem_ld_wait();
+        ld_inflight = false;
+        // accumulator fully in registers: hand it back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[slot]);
+      } else {
+        ptx::mbar_wait(&tmem_full[slot], aph);
+        ptx::tc_fence_after();
+      }
+      if (et == 0) EDL_TRACE(2, tc, 2);
+#pragma unroll
+      for (int c32 = 0; c32 < kColsPerGrp / 32; ++c32) {
+        uint32_t rg1[32];
+        if constexpr (!kPipeLd) {
+          ptx::tmem_ld_32x32(taddr + c32 * 32, rg1);
+          ptx::tmem_ld_wait();
+          if (c32 == kColsPerGrp / 32 - 1) {
+            // accumulator fully in registers: hand it back to the MMA warp before the slow part
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[slot]);
+          }
+        }
+        const uint32_t* rg = kPipeLd ? &rgn[kPipeLd ? c32 * 32 : 0] : rg1;
         const int cbase = grp * kColsPerGrp + c32 * 32;   // first tile column of this chunk
         float f[32];
 #pragma unroll
@@ -781,6 +833,19 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         __syncwarp();
       }
+      if constexpr (kPipeLd) {
+        if (has_next) {
+          const uint32_t nslot = (tc + 1) & 1, naph = ((tc + 1) >> 1) & 1;
+          // only if the next accumulator is complete NOW: blocking here would put the loops below behind its MMAs
+          if (__all_sync(0xffffffffu, ptx::mbar_test_wait(&tmem_full[nslot], naph))) {
+            ptx::tc_fence_after();
+            const uint32_t naddr = tmem_base + nslot * BLOCK_N + lane_col;
+            if constexpr (kNCh == 2) ptx::tmem_ld_32x64(naddr, rgn);
+            else ptx::tmem_ld_32x32(naddr, rgn);
+            ld_inflight = true;
+          }
+        }
+      }
       if constexpr (kTcStats) {
         if (tcs) {
           if (ew == 0) {
@@ -858,14 +923,20 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           s0 += d.x; q0 = fmaf(d.x, x.x, q0);
           s1 += d.y; q1 = fmaf(d.y, x.y, q1);
         };
+        // Row r of a staged tile sits at r * 128 + ((chunk ^ (r & 7)) << 4).  A thread visits rows r0, r0 + kSplit, ...:
+        // with kSplit a multiple of 4 the swizzle term takes two values (even / odd steps), so two base addresses plus
+        // compile-time offsets replace five address instructions per row and load.
+        constexpr bool kFastRows = kSplit % 4 == 0;      // (the 256-column kernels carry no reduction; they only compile this)
         auto accum_rows = [&](int r_begin, int r_end) {
           int rr = r_begin + part;
-          for (; rr + 7 * kSplit < r_end; rr += 8 * kSplit) {
+          uint32_t o0 = rr * 128 + ((chunk ^ (rr & 7)) << 4), o1 = (rr + kSplit) * 128 + ((chunk ^ ((rr + kSplit) & 7)) << 4);
+          for (; rr + 7 * kSplit < r_end; rr += 8 * kSplit, o0 += 8 * kSplit * 128, o1 += 8 * kSplit * 128) {
             uint32_t wd[8], wx[8], wy[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int r = rr + u * kSplit;
-              const uint32_t o = r * 128 + ((chunk ^ (r & 7)) << 4);
+              const uint32_t o = kFastRows ? ((u & 1) ? o1 : o0) + (u >> 1) * (2 * kSplit * 128)
+                                           : (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
               wd[u] = ptx::lds32(based + o);
               wx[u] = ptx::lds32(basex + o);
               wy[u] = has_y ? ptx::lds32(basey + o) : 0u;
@@ -873,8 +944,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int u = 0; u < 8; ++u) row_update(wd[u], wx[u], wy[u]);
           }
-          for (; rr < r_end; rr += kSplit) {
-            const uint32_t o = rr * 128 + ((chunk ^ (rr & 7)) << 4);
+#pragma unroll 1
+          for (int u = 0; rr < r_end; rr += kSplit, ++u) {
+            const uint32_t o = kFastRows ? ((u & 1) ? o1 : o0) + (u >> 1) * (2 * kSplit * 128)
+                                         : (uint32_t)(rr * 128 + ((chunk ^ (rr & 7)) << 4));
             row_update(ptx::lds32(based + o), ptx::lds32(basex + o), has_y ? ptx::lds32(basey + o) : 0u);
           }
         };
@@ -918,6 +991,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (ew == 0 && has_next)
           issue_bn_tiles<BLOCK_N, kConv>(p, next_tm, next_n0, rows_tile, sx, sy, &tmBnX, &tmBnY, bn_bar);
       }
+      if (!BNR && et == 0) EDL_TRACE(2, tc, 5);
       if (!BNR && p.col_stats != nullptr && !tcs) {
         // Per-channel sum / sum of squares of the STORED bf16 values, from the staged tile.  A thread owns
         // a PAIR of adjacent columns (one 32-bit shared load per row) and every kSplit-th row; eight
@@ -932,14 +1006,18 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int half = col >> 6, cc = col & 63, chunk = cc >> 3, within = cc & 7;
         const uint32_t base = ptx::smem_u32(sd) + half * (kBlockM * 128) + within * 2;
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        auto accum_rows = [&](int r_begin, int r_end) {
+        constexpr bool kFastRows = kSplit % 4 == 0;
+        auto accum_rows = [&](int r_begin, int r_end) {      // addressing: see the BN-backward loop above
           int rr = r_begin + part;
-          for (; rr + 7 * kSplit < r_end; rr += 8 * kSplit) {
+          uint32_t o0 = base + rr * 128 + ((chunk ^ (rr & 7)) << 4);
+          uint32_t o1 = base + (rr + kSplit) * 128 + ((chunk ^ ((rr + kSplit) & 7)) << 4);
+          for (; rr + 7 * kSplit < r_end; rr += 8 * kSplit, o0 += 8 * kSplit * 128, o1 += 8 * kSplit * 128) {
             uint32_t w[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int r = rr + u * kSplit;
-              w[u] = ptx::lds32(base + r * 128 + ((chunk ^ (r & 7)) << 4));
+              w[u] = ptx::lds32(kFastRows ? ((u & 1) ? o1 : o0) + (u >> 1) * (2 * kSplit * 128)
+                                          : base + r * 128 + ((chunk ^ (r & 7)) << 4));
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -948,8 +1026,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               s1 += v.y; q1 = fmaf(v.y, v.y, q1);
             }
           }
-          for (; rr < r_end; rr += kSplit) {
-            const uint32_t w = ptx::lds32(base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+#pragma unroll 1
+          for (int u = 0; rr < r_end; rr += kSplit, ++u) {
+            const uint32_t w = ptx::lds32(kFastRows ? ((u & 1) ? o1 : o0) + (u >> 1) * (2 * kSplit * 128)
+                                                    : base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
             const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
             s0 += v.x; q0 = fmaf(v.x, v.x, q0);
             s1 += v.y; q1 = fmaf(v.y, v.y, q1);
@@ -967,6 +1047,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int b = 0; b < p.BN && img0 + b < p.n_img; ++b) accum_rows(b * rows_per_img, b * rows_per_img + hv * p.W);
           }
         }
+        if (et == 0) EDL_TRACE(2, tc, 7);
         run_s0 += s0; run_s1 += s1; run_q0 += q0; run_q1 += q1;
         const bool run_end = !has_next || next_n0 != n0;
         if (run_end) { s0 = run_s0; s1 = run_s1; q0 = run_q0; q1 = run_q1; run_s0 = run_s1 = run_q0 = run_q1 = 0.f; }
