@@ -106,7 +106,7 @@ def main():
     except (OSError, ValueError):
         bench = {}
     pats = ("bench*.json", "ab_*.json", "ab2_*.json", "b4_*.json", "b6_*.json", "b7_*.json", "b8_*.json", "b9_*.json",
-            "b10_*.json", "b1[1-9]_*.json")
+            "b10_*.json", "b1[1-9]_*.json", "b[2-9][0-9]_*.json", "final_bench_*.json")
     for f in sorted(x for p_ in pats for x in glob.glob(os.path.join(SRC, p_))):
         try:
             line = [l for l in open(f).read().splitlines() if l.startswith("{")][-1]
@@ -130,7 +130,9 @@ def main():
     # round 2: multi-GPU sweeps, elastic-launch recovery times, timelines, A/B summaries
     for pat, dst in (("comm_*gpu.json", None), ("rescale_*gpu.json", None), ("elastic_launch_*gpu*.json", None),
                      ("ctr_sweep_*gpu.json", None), ("ctr_deepfm_*gpu.json", None), ("prof_allreduce_*gpu.jsonl", None),
-                     ("timeline_r2*.txt", None), ("call*_summary.txt", None), ("wgrad3.json", "wgrad3_microbench.json")):
+                     ("timeline_r2*.txt", None), ("call*_summary.txt", None), ("wgrad3.json", "wgrad3_microbench.json"),
+                     ("trace_persist_c*.txt", None), ("teacher_c*.txt", None), ("final_*tests.log", None),
+                     ("final_smoke.log", None)):
         for f in sorted(glob.glob(os.path.join(SRC, pat))):
             open(os.path.join(OUT, dst or os.path.basename(f)), "w").write(open(f).read())
     for name in ("experimental_summary.txt", "loader_bench.jsonl"):       # scripts/gpu_validate_experimental.sh
