@@ -21,6 +21,7 @@ import os
 import queue
 import random
 import threading
+import time
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -146,6 +147,8 @@ class ImageBatchLoader:
         def feeder():
             try:
                 for b in range(nb):
+                    if stop.is_set():
+                        return
                     ids = idx[b * self.bs:(b + 1) * self.bs]
                     buf = [None] * len(ids) if self.decode == "nvjpeg" else alloc(len(ids))
                     with lock:
@@ -187,6 +190,18 @@ class ImageBatchLoader:
             stop.set()
             for _ in ws:
                 work_q.put(None)
+            # Join before returning: a daemon thread that is still inside an OpenCV / torch call when the interpreter
+            # finalises takes the process down with "terminate called without an active exception" (observed once in
+            # three runs of the JPEG file-list example).  The feeder may be blocked on a full out_q: drain it.
+            deadline = time.time() + 5.0
+            while fd.is_alive() and time.time() < deadline:
+                try:
+                    out_q.get_nowait()
+                except queue.Empty:
+                    pass
+                fd.join(timeout=0.05)
+            for t in ws:
+                t.join(timeout=max(0.0, deadline - time.time()))
 
 
     def augmenter(self, device) -> "GpuJpegAugmenter":
