@@ -408,6 +408,19 @@ void stem_conv3x3s2(const Tensor& x, const Tensor& w, Tensor& y, const c10::opti
                       at::cuda::getCurrentCUDAStream().stream());
 }
 
+// a [N * Ho * Wo, 160] = im2col of the 7x7 / stride 2 / pad 3 stem convolution of x [N,3,H,W] channels_last bf16
+void stem7_im2col(const Tensor& x, Tensor& a) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.size(1) == 3 && x.scalar_type() == at::kBFloat16 &&
+              x.is_contiguous(at::MemoryFormat::ChannelsLast), "stem7_im2col: x must be [N,3,H,W] channels_last bf16");
+  const int64_t H = x.size(2), W = x.size(3), Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && a.is_contiguous() && a.dim() == 2 &&
+              a.size(0) == x.size(0) * Ho * Wo && a.size(1) == 160, "stem7_im2col: a must be [N*Ho*Wo, 160] bf16");
+  c10::cuda::CUDAGuard guard(x.device());
+  const char* err = edl::stem7_im2col(x.data_ptr(), a.data_ptr(), (int)x.size(0), (int)H, (int)W,
+                                      at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(err == nullptr, err);
+}
+
 // dw KRSC [32,3,3,3] bf16 (+)= wgrad of the stem convolution; x [N,3,H,W], dy [N,32,H/2,W/2] channels_last bf16
 void stem_wgrad(const Tensor& x, const Tensor& dy, Tensor& dw, Tensor& ws, Tensor& counter, bool accumulate) {
   TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.size(1) == 3 && x.scalar_type() == at::kBFloat16 &&
@@ -563,6 +576,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("embedding_bag_fwd", &embedding_bag_fwd);
   m.def("stem_conv3x3s2", &stem_conv3x3s2);
   m.def("stem_wgrad", &stem_wgrad);
+  m.def("stem7_im2col", &stem7_im2col);
   m.def("pair_weight_expand", &pair_weight_expand);
   m.def("pair_weight_fold", &pair_weight_fold);
   m.def("fold_pair_stats", &fold_pair_stats);

@@ -571,7 +571,6 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t rgn[kPipeLd ? kNCh * 32 : 32];            // kNCh chunks of 32 columns, read with one instruction
     bool ld_inflight = false;
     [[maybe_unused]] uint32_t stat_batches = 0;      // statistic MMA batches committed so far (phase of stat_bar)
-    [[maybe_unused]] bool stat_acc = false;          // the TMEM statistics hold earlier tiles of the current N tile
     TileIt cur = tile_init(t_begin);
     // halo layout: accumulator row -> row of the dense staging tile (fixed per thread; the halo column's rows are dropped)
     int srow = row;
@@ -855,7 +854,6 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
           }
           ++stat_batches;
-          stat_acc = true;
           if (!has_next || next_n0 != n0) {
             // last tile of this N tile in the CTA's sequence: read the statistics back into the CTA-local accumulators
             ptx::mbar_wait(stat_bar, (stat_batches - 1) & 1);
@@ -875,7 +873,6 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 atomicAdd(&sstats[p.N + n0 + nrow], __uint_as_float(gd));
               }
             }
-            stat_acc = false;
             ptx::tc_fence_before();       // ordered before the next batch (accumulate = 0) by the bar.sync at the tile top
           }
         }

@@ -132,6 +132,8 @@ void fold_pair_stats(const float* s2, float* stats, int cout, cudaStream_t s);
 // ---- stem.cu: first stem convolution (3 -> 32, 3x3 / stride 2 / pad 1, NHWC bf16) + BN statistics of its output ----
 void stem_conv3x3s2(const void* x, const void* w, void* y, float* stats, int N, int H, int W, cudaStream_t s);
 // its weight gradient: dw KRSC [32,3,3,3] bf16 (+)= ; ws: >= 864 zero floats (left zero), counter: one zero int (left zero)
+// A [N * Ho * Wo, 160] bf16 = im2col of the 7x7 / stride 2 / pad 3 convolution of x [N, H, W, 3] ((r, s, c) order, zero-padded)
+const char* stem7_im2col(const void* x, void* a, int N, int H, int W, cudaStream_t s);
 const char* stem_wgrad(const void* x, const void* dy, float* ws, int* counter, void* dw, bool accumulate, int N, int H,
                        int W, cudaStream_t s);
 

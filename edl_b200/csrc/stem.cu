@@ -311,4 +311,68 @@ const char* stem_wgrad(const void* x, const void* dy, float* ws, int* counter, v
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// im2col of a 7x7 / stride 2 / pad 3 convolution on a 3-channel NHWC image (the ResNeXt / ResNet stem of the teacher):
+// row m = (n, ho, wo) of A [M, 160] holds the 7 x 7 x 3 = 147 window elements in (r, s, c) order -- for a fixed filter row
+// the 21 elements are CONTIGUOUS in the NHWC image -- followed by 13 zeros, so that the tcgen05 GEMM (K blocks of 64, KRSC
+// weights padded to 160 columns) computes the convolution with the folded-BN / ReLU epilogue.  One CTA per output row
+// (n, ho): the seven input rows go to shared memory with coalesced 32-bit loads, every thread then assembles 16-byte
+// pieces of A.  Replaces the library kernel that took 193 us of the teacher's forward (profiles/teacher_c37.txt).
+constexpr int kStem7K = 147, kStem7KP = 160, kStem7Threads = 256;
+
+__global__ void __launch_bounds__(kStem7Threads)
+stem7_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ a, int H, int W, int Ho, int Wo, int rowlen) {
+  extern __shared__ __align__(16) unsigned char stem7_smem[];
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(stem7_smem);        // [7][rowlen]: 9 zeros | 3 W elements | zeros
+  __shared__ int koff[kStem7KP];
+  const int n = blockIdx.x / Ho, ho = blockIdx.x - n * Ho;
+  for (int k = threadIdx.x; k < kStem7KP; k += kStem7Threads) koff[k] = k < kStem7K ? (k / 21) * rowlen + (k % 21) : -1;
+  const int words = rowlen / 2;                                             // rowlen is even
+  for (int r = 0; r < 7; ++r) {
+    const int hi = ho * 2 - 3 + r;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(xs + r * rowlen);
+    if (hi < 0 || hi >= H) {
+      for (int i = threadIdx.x; i < words; i += kStem7Threads) dst[i] = 0u;
+      continue;
+    }
+    const __nv_bfloat16* src = x + ((size_t)n * H + hi) * W * 3;
+    // data starts at element 9 (odd): element-wise copies of the 3 W values, the pads as zeros
+    for (int i = threadIdx.x; i < rowlen; i += kStem7Threads) {
+      const int j = i - 9;
+      xs[r * rowlen + i] = (j >= 0 && j < 3 * W) ? src[j] : __float2bfloat16(0.f);
+    }
+  }
+  __syncthreads();
+  const size_t m0 = ((size_t)n * Ho + ho) * Wo;
+  for (int idx = threadIdx.x; idx < Wo * (kStem7KP / 8); idx += kStem7Threads) {
+    const int wo = idx / (kStem7KP / 8), q = idx - wo * (kStem7KP / 8);
+    const int base = wo * 6;                                                // (wi + 3) * 3 with wi = 2 wo - 3 + s
+    alignas(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int o = koff[q * 8 + e];
+      v[e] = o >= 0 ? xs[o + base] : __float2bfloat16(0.f);
+    }
+    *reinterpret_cast<uint4*>(a + (m0 + wo) * kStem7KP + q * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+const char* stem7_im2col(const void* x, void* a, int N, int H, int W, cudaStream_t stream) {
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  int rowlen = 3 * (W + 6) + 2;                    // index (2 (Wo - 1) + 6) * 3 + 2 + 9 ... stays inside
+  rowlen = (rowlen + 1) / 2 * 2;
+  const size_t smem = (size_t)7 * rowlen * 2;
+  if (smem > 96 * 1024) return "stem7_im2col: image too wide";
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(stem7_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    attr_set = true;
+  }
+  stem7_im2col_kernel<<<N * Ho, kStem7Threads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                             reinterpret_cast<__nv_bfloat16*>(a), H, W, Ho, Wo, rowlen);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
 }  // namespace edl

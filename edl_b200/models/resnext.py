@@ -161,6 +161,9 @@ class FoldedConv(nn.Module):
                 # (conv2d_grouped_direct_kernel: 26 ms per layer, profiles/teacher_r1.txt)
                 y = y[:, :, ::2, ::2].contiguous(memory_format=torch.channels_last)
             return y
+        if (self.k == 7 and self.stride == 2 and self.groups == 1 and residual is None and OWN_STEM7
+                and ops.stem7_supported(x, self.weight)):
+            return ops.stem7_infer(x, self.weight, self.scale, self.shift, self.relu)
         if x.is_cuda:
             ops.count_fallback("teacher conv on cuDNN: %dx%d stride %d groups %d, %d -> %d channels" % (
                 self.k, self.k, self.stride, self.groups, self.weight.shape[3] * self.groups, self.weight.shape[0]))
@@ -171,6 +174,8 @@ class FoldedConv(nn.Module):
 # Validated on B200 in round 2, on by default (EDL_TEACHER_FUSE_RES=0: off): folds the residual add
 # of every block's last 1x1 convolution into its GEMM epilogue (scale_shift_act was 0.63 ms of the 5.87 ms forward).
 FUSE_RESIDUAL = __import__("os").environ.get("EDL_TEACHER_FUSE_RES", "1") == "1"
+# 7x7 stem as im2col + tcgen05 GEMM instead of the library convolution (EDL_TEACHER_OWN_STEM7=0: library)
+OWN_STEM7 = __import__("os").environ.get("EDL_TEACHER_OWN_STEM7", "1") == "1"
 
 
 class ResNeXtBlock(nn.Module):

@@ -749,6 +749,43 @@ def conv3x3_s2(x, weight_krsc, stats: Optional[torch.Tensor] = None):
 OWN_STEM1 = __import__("os").environ.get("EDL_OWN_STEM1", "1") == "1"
 
 
+def stem7_supported(x, weight_krsc) -> bool:
+    """7x7 / stride 2 / pad 3 convolution of a 3-channel image (the teacher's stem) as im2col + tcgen05 GEMM."""
+    return (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] == 3
+            and weight_krsc.dtype == torch.bfloat16 and tuple(weight_krsc.shape[1:]) == (7, 7, 3)
+            and weight_krsc.shape[0] % 8 == 0)
+
+
+_STEM7_W = {}
+
+
+@torch.no_grad()
+def stem7_infer(x, weight_krsc, scale=None, shift=None, relu=False):
+    """y = act(conv7x7/s2/p3(x, w) * scale + shift) for x [N,3,H,W] (channels_last bf16), w KRSC [Cout,7,7,3]:
+    ``stem7_im2col`` writes the windows as rows of a [N*Ho*Wo, 160] matrix ((r, s, c) order = the KRSC weight order, 13 zero
+    columns of padding) and the persistent GEMM applies the folded BatchNorm and the ReLU in its epilogue.  The reference's
+    teacher runs this layer through the serving library (start_local_teacher.sh:24-30)."""
+    from . import native, count_launch
+
+    x = _cl(x)
+    n, _, h, w = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    cout = weight_krsc.shape[0]
+    key = (weight_krsc.data_ptr(), weight_krsc._version, str(weight_krsc.device))
+    wp = _STEM7_W.get(key)
+    if wp is None:
+        _STEM7_W.clear()
+        wp = torch.zeros((cout, 160), device=x.device, dtype=torch.bfloat16)
+        wp[:, :147] = weight_krsc.reshape(cout, 147)
+        _STEM7_W[key] = wp
+    a = torch.empty((n * ho * wo, 160), device=x.device, dtype=torch.bfloat16)
+    native().stem7_im2col(x, a)
+    count_launch()
+    y = torch.empty((n, cout, ho, wo), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    gemm_bf16(a, wp, out=y.permute(0, 2, 3, 1).reshape(-1, cout), col_scale=scale, col_shift=shift, relu=relu)
+    return y
+
+
 def stem_conv_supported(x, weight_krsc) -> bool:
     return (x.is_cuda and x.dtype == torch.bfloat16 and weight_krsc.dtype == torch.bfloat16 and x.dim() == 4
             and x.shape[1] == 3 and tuple(weight_krsc.shape) == (32, 3, 3, 3))

@@ -337,3 +337,43 @@ def test_grouped_conv3x3_inference_with_folded_bn_epilogue(n, c, cout, h, w, gro
     ref = F.conv2d(x.float(), wt.permute(0, 3, 1, 2).float(), None, 1, 1, 1, groups)
     ref = torch.relu(ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
     assert _rel(y, ref) < 1e-2
+
+
+def test_phase_trace_of_the_persistent_kernel():
+    """set_persist_trace: CTA 0 stamps clock64() at the phase boundaries of its first tiles (tools/trace_persist.py)."""
+    nat = ops.native()
+    a = torch.randn(4096 * 8, 64, device=DEV).bfloat16()
+    b = (torch.randn(128, 64, device=DEV) * 0.05).bfloat16()
+    st = torch.zeros(256, device=DEV)
+    buf = torch.zeros(3 * 16 * 8, dtype=torch.int64, device=DEV)
+    nat.set_persist_trace(buf)
+    try:
+        ops.gemm_bf16(a, b, col_stats=st)
+        torch.cuda.synchronize()
+    finally:
+        nat.set_persist_trace(None)
+    t = buf.view(3, 16, 8).cpu()
+    epi = t[2]
+    assert (epi[0, :5] > 0).all()                          # tile 0: loop top .. store issued
+    assert (epi[0, 1:5] >= epi[0, :4]).all()               # in order
+    assert epi[1, 0] > epi[0, 4]                           # the second tile starts after the first one's store
+    buf.zero_()
+    ops.gemm_bf16(a, b, col_stats=st)                      # tracing off: nothing is written
+    torch.cuda.synchronize()
+    assert int(buf.abs().sum()) == 0
+
+
+@pytest.mark.parametrize("n,h,w,cout", [(4, 224, 224, 64), (3, 65, 97, 64), (2, 32, 48, 128)])
+def test_stem7_im2col_gemm_matches_the_convolution(n, h, w, cout):
+    """The teacher's 7x7 / stride 2 / pad 3 stem: im2col kernel (window rows in KRSC order, zero-padded to 160 columns) +
+    persistent GEMM with the folded-BN / ReLU epilogue, against the fp32 convolution; odd sizes exercise the padding."""
+    torch.manual_seed(13)
+    x = torch.randn(n, 3, h, w, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, 7, 7, 3, device=DEV) * 0.05).bfloat16()
+    sc, sh = torch.rand(cout, device=DEV) + 0.5, torch.randn(cout, device=DEV) * 0.1
+    assert ops.stem7_supported(x, wt)
+    y = ops.stem7_infer(x, wt, sc, sh, relu=True)
+    ref = F.conv2d(x.float(), wt.permute(0, 3, 1, 2).float(), None, 2, 3)
+    ref = torch.relu(ref * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert _rel(y, ref) < 1e-2
