@@ -15,6 +15,13 @@ run() {  # name tool budget pytest-args...
     python -m pytest "$@" -x -q -p no:cacheprovider --timeout $((budget - 20)) > "gpurun_out/sanitize_${name}_${tool}.log" 2>&1
   echo "$name / $tool: exit $? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' "gpurun_out/sanitize_${name}_${tool}.log" | tail -2 | tr '\n' ' ')" | tee -a "$SUM"
 }
+# SUBSET=new: only the kernels added at the end of round 2 (CTA-pair GEMM, halo / resident-weight convolutions, stem im2col,
+# tensor-core statistics), with small shapes
+if [ "${SUBSET:-all}" = "new" ]; then
+  run new_kernels memcheck 150 tests/test_persist_gpu.py -k "(cta_pair and 19000) or (haloed and (11-20 or 6-6 or 9-30)) or (stem7 and 65) or (tensor_core_bn and (shape1 or shape5)) or phase_trace"
+  cat "$SUM"
+  exit 0
+fi
 run gemm_wgrad   memcheck  200 tests/test_gemm_gpu.py -k "wgrad or split"
 run persist      memcheck  200 tests/test_persist_gpu.py -k "wide_tile or epilogue or bnr"
 run wgrad3       memcheck  200 tests/test_round2_gpu.py -k "conv3x3_wgrad_tcgen05 and 14-14"
