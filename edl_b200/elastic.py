@@ -28,7 +28,9 @@ Its design document lists "no restart" as future work.  Here, with ``EDL_RESCALE
 
 * a collective that FAILS because a peer died is the same thing triggered differently: ``recover()`` drops the
   broken group, waits for the store to publish the new stage and rejoins as a survivor (hot recovery; the
-  reference restarts every trainer of the job and reloads the checkpoint).
+  reference restarts every trainer of the job and reloads the checkpoint).  If the membership does NOT change -- a
+  false alarm: a stalled rank, a transient transport error -- the same members re-form the same stage under a fresh
+  namespace (``StageInfo.generation``) and continue from rank 0's state (soft reset).
 
 The launcher side (utils/launcher.py) leaves the trainers of a surviving pod alone when they have announced an
 ElasticContext and acknowledges the switch by waiting for their ready keys; anything else -- a trainer that does
@@ -43,7 +45,7 @@ import os
 import threading
 import time
 from dataclasses import dataclass
-from typing import Optional
+from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -184,6 +186,12 @@ class StageInfo:
     survivor: bool               # this trainer carried its state over from the previous stage
     prev_size: int               # world size this trainer ran with before (== size on a cold start)
     rendezvous_s: float = 0.0    # seconds from leaving the old process group to having the new one
+    generation: int = 0          # soft resets of this stage so far (same members, fresh group; see recover())
+
+    @property
+    def group_name(self) -> str:
+        """Namespace of this stage's process group / fabric in the store: unique per (stage, generation)."""
+        return self.stage if self.generation == 0 else "%s~%d" % (self.stage, self.generation)
 
 
 class ElasticContext:
@@ -252,8 +260,10 @@ class ElasticContext:
         except Exception:  # noqa: BLE001 - ask again at the next poll
             return False
 
-    def _rendezvous(self, survivor: bool, prev_size: int) -> StageInfo:
-        """Stage rendezvous through the store (see module docstring); returns once the stage is committed."""
+    def _rendezvous(self, survivor: bool, prev_size: int, soft: Optional[Tuple[str, int]] = None) -> StageInfo:
+        """Stage rendezvous through the store (see module docstring); returns once the stage is committed.
+        ``soft = (stage, generation)``: re-form THAT stage under a fresh key namespace (soft reset after a collective
+        failed although nobody left); if the membership moves on meanwhile, the newer stage is joined as usual."""
         job = self.env.job_id
         t0 = time.time()
         deadline = t0 + self.timeout_s
@@ -270,14 +280,16 @@ class ElasticContext:
                 continue
             rank, size, rip = loc
             stage = cluster.stage
-            my_key = ready_key(job, stage, rank)
+            gen = soft[1] if soft is not None and soft[0] == stage else 0
+            skey = stage if gen == 0 else "%s~%d" % (stage, gen)          # key namespace of this (stage, generation)
+            my_key = ready_key(job, skey, rank)
             self.kv.put(my_key, b"survivor" if survivor else b"joiner")
-            keys = [ready_key(job, stage, r) for r in range(size)]
-            ckey = commit_key(job, stage)
+            keys = [ready_key(job, skey, r) for r in range(size)]
+            ckey = commit_key(job, skey)
             while True:
                 committed, _ = self.kv.get(ckey)
                 if committed is None:
-                    kvs, _ = self.kv.get_prefix("%sready/%s/" % (_prefix(job), stage))
+                    kvs, _ = self.kv.get_prefix("%sready/%s/" % (_prefix(job), skey))
                     have = {kv["key"]: kv["value"] for kv in kvs}
                     if all(k in have for k in keys):
                         flags = [have[k] for k in keys]
@@ -292,7 +304,8 @@ class ElasticContext:
                     self._stage_pods = cluster.get_pods_ids_set()
                     self._stage_pod_list = cluster.get_pods_ids_list()
                     return StageInfo(stage=stage, rank=rank, size=size, rank_in_pod=rip, root=rec["root"],
-                                     survivor=survivor, prev_size=prev_size, rendezvous_s=time.time() - t0)
+                                     survivor=survivor, prev_size=prev_size, rendezvous_s=time.time() - t0,
+                                     generation=gen)
                 latest = edl_cluster.load_from_etcd(self._etcd, timeout=10)
                 if latest is not None and latest.stage != stage:
                     # the membership moved on while this stage was still forming: withdraw -- unless the stage
@@ -315,12 +328,12 @@ class ElasticContext:
 
             dev = torch.device("cuda", info.rank_in_pod % max(1, torch.cuda.device_count()))
             torch.cuda.set_device(dev)
-            store = KVRendezvousStore(self.kv, "%spg/%s/" % (_prefix(self.env.job_id), info.stage), self.timeout_s)
-            self.fabric = Fabric(store=store, rank=info.rank, world=info.size, tag="stage-%s" % info.stage)
+            store = KVRendezvousStore(self.kv, "%spg/%s/" % (_prefix(self.env.job_id), info.group_name), self.timeout_s)
+            self.fabric = Fabric(store=store, rank=info.rank, world=info.size, tag="stage-%s" % info.group_name)
             return
         if info.size <= 1:
             return
-        store = KVRendezvousStore(self.kv, "%spg/%s/" % (_prefix(self.env.job_id), info.stage), self.timeout_s)
+        store = KVRendezvousStore(self.kv, "%spg/%s/" % (_prefix(self.env.job_id), info.group_name), self.timeout_s)
         kwargs = {}
         if self.backend == "nccl":
             dev = torch.device("cuda", info.rank_in_pod % max(1, torch.cuda.device_count()))
@@ -463,25 +476,39 @@ class ElasticContext:
                 dist.destroy_process_group()
         except Exception as e:  # noqa: BLE001 - the group is broken anyway
             logger.warning("destroying the broken process group: %s", e)
+        # A dead pod's lease expires within ETCD_TTL and the leader publishes the smaller stage one poll later.  If the
+        # membership has NOT changed by then, nobody died: the collective failed on a false alarm (a rank stalled longer
+        # than the communication time-out, a transient transport error).  Every member of the stage lands here (the
+        # abandoned group makes the others' collectives fail too), so they re-form the SAME stage under a fresh
+        # namespace -- a soft reset -- and take rank 0's state like after any other recovery.  ``wait_s`` bounds the
+        # whole thing; EDL_SOFT_RESET=0 restores the old behaviour (give up when the membership does not change).
         wait_s = wait_s if wait_s is not None else constants.ETCD_TTL * 2 + 4 * constants.POLL_INTERVAL + 10
-        deadline = time.time() + wait_s
+        soft_after = constants.ETCD_TTL + 3 * constants.POLL_INTERVAL + 1.0
+        soft_ok = os.environ.get("EDL_SOFT_RESET", "1") != "0"
+        t_fail = time.time()
+        deadline = t_fail + wait_s
+        soft = None
         while time.time() < deadline:
             c = edl_cluster.load_from_etcd(self._etcd, timeout=10)
             if c is not None and c.stage != old.stage:
+                break
+            if soft_ok and c is not None and time.time() - t_fail >= soft_after:
+                soft = (old.stage, old.generation + 1)
                 break
             time.sleep(0.1)
         else:
             raise TimeoutError("a collective failed but the membership did not change within %.0fs" % wait_s)
         self._changed.clear()
         t0 = time.time()
-        info = self._rendezvous(survivor=True, prev_size=old.size)
+        info = self._rendezvous(survivor=True, prev_size=old.size, soft=soft)
         self._init_group(info)
         info.rendezvous_s = time.time() - t0          # new stage published -> new group usable
         self.info = info
         self._steps = 0
         self._on_cluster_event(None, None)
-        logger.info("trainer recovered in place from stage %s (%d ranks) to %s as rank %d/%d", old.stage, old.size,
-                    info.stage, info.rank, info.size)
+        logger.info("trainer recovered in place from stage %s (%d ranks) to %s as rank %d/%d%s", old.stage, old.size,
+                    info.group_name, info.rank, info.size,
+                    " (soft reset: the membership did not change)" if info.generation > 0 else "")
         return info
 
     def close(self):

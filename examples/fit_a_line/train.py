@@ -54,6 +54,10 @@ def main():
     ap.add_argument("--ckpt", type=str, default=os.environ.get("PADDLE_EDL_HDFS_PATH") or "./fit_a_line_ckpt")
     ap.add_argument("--epoch_sleep", type=float, default=0.0, help="slow epochs down (elastic demos)")
     ap.add_argument("--report", type=str, default=os.environ.get("FIT_REPORT_DIR", ""))
+    ap.add_argument("--inject_fault_file", type=str, default=os.environ.get("FIT_INJECT_FAULT_FILE", ""),
+                    help="testing: once this file exists, rank --inject_fault_rank raises ONE collective error although "
+                         "every pod is alive (a false alarm: exercises the soft reset of ElasticContext.recover())")
+    ap.add_argument("--inject_fault_rank", type=int, default=int(os.environ.get("FIT_INJECT_FAULT_RANK", "1")))
     ap.add_argument("--finish_file", type=str, default=os.environ.get("FIT_FINISH_FILE", ""),
                     help="stop at the first epoch end at which this file exists (--epochs stays the upper bound)")
     args = ap.parse_args()
@@ -115,6 +119,7 @@ def main():
     n = x.shape[0]
     loss = torch.zeros(())
     epoch = start_epoch
+    injected = False
     while epoch < args.epochs:
         g = torch.Generator().manual_seed(epoch)          # shuffle seed = epoch: reproducible after resume
         perm = torch.randperm(n, generator=g)
@@ -122,6 +127,10 @@ def main():
         switch = broken = False
         stop = torch.zeros(1)
         try:
+            if (inplace and not injected and world > 1 and rank == args.inject_fault_rank and args.inject_fault_file
+                    and os.path.exists(args.inject_fault_file)):
+                injected = True
+                raise RuntimeError("injected collective fault (testing the soft reset)")
             for i in range(0, len(shard) - args.batch + 1, args.batch):
                 idx = shard[i:i + args.batch]
                 dp.zero_grad()

@@ -241,6 +241,63 @@ def test_hot_recovery_when_a_pod_dies_hard(kv_server, tmp_path):
 
 
 @pytest.mark.slow
+def test_false_alarm_is_survived_by_a_soft_reset(kv_server, tmp_path):
+    """A collective fails on one rank although BOTH pods are alive (injected; in production: a rank stalled longer than the
+    communication time-out).  Both trainers drop the group, see that the membership does not change, re-form the same
+    stage under a fresh namespace (generation 1) and continue from rank 0's state -- same processes, same world size."""
+    job = "soft_" + uuid.uuid4().hex[:6]
+    report, ckpt = str(tmp_path / "report"), str(tmp_path / "ckpt")
+    fault = str(tmp_path / "fault.now")
+    os.environ["FIT_INJECT_FAULT_FILE"] = fault
+
+    def epochs():
+        p = os.path.join(report, "epochs.jsonl")
+        return [json.loads(l) for l in open(p)] if os.path.exists(p) else []
+
+    def wait_world(w, timeout, min_new=3):
+        n0 = len(epochs())
+        deadline = time.time() + timeout
+        while time.time() < deadline:
+            e = epochs()
+            if len(e) >= n0 + min_new and all(x["world"] == w for x in e[-min_new:]):
+                return e
+            time.sleep(0.2)
+        raise AssertionError("world never became %d: %s" % (w, epochs()[-4:]))
+
+    a = b = None
+    try:
+        a = _launch(kv_server.endpoint, job, str(tmp_path / "logA"), report, ckpt, 4000)
+        wait_world(1, 60)
+        b = _launch(kv_server.endpoint, job, str(tmp_path / "logB"), report, ckpt, 4000)
+        e2 = wait_world(2, 90)
+        pid_a, lr2 = e2[-1]["pid"], e2[-1]["lr"]
+        open(fault, "w").close()                              # rank 1 raises once
+        deadline = time.time() + 90
+        wa = wb = ""
+        while time.time() < deadline:
+            wa = open(str(tmp_path / "logA" / "workerlog.0")).read()
+            wb = open(str(tmp_path / "logB" / "workerlog.0")).read()
+            if "recovered in place: world 2 -> 2" in wa and "recovered in place: world 2 -> 2" in wb:
+                break
+            time.sleep(0.3)
+        assert "recovered in place: world 2 -> 2" in wa, wa[-2000:]
+        assert "recovered in place: world 2 -> 2" in wb, wb[-2000:]
+        assert "injected collective fault" in wb
+        e3 = wait_world(2, 60)                                # training goes on with both pods ...
+        assert e3[-1]["pid"] == pid_a                         # ... in the same processes, LR untouched
+        assert abs(e3[-1]["lr"] - lr2) < 1e-9
+        _finish(report)
+        assert a.wait(timeout=120) == 0
+        ep = [x["epoch"] for x in epochs()]
+        assert ep == sorted(set(ep))
+    finally:
+        os.environ.pop("FIT_INJECT_FAULT_FILE", None)
+        for p in (a, b):
+            if p is not None and p.poll() is None:
+                os.killpg(os.getpgid(p.pid), 9)
+
+
+@pytest.mark.slow
 def test_sigterm_is_a_graceful_leave(kv_server, tmp_path):
     """SIGTERM to a launcher (scheduler eviction, k8s pod deletion) = announce the departure first: the pod gives up its
     registrations, the job re-plans without it, its trainers leave at the agreed step -- the survivor never sees a
