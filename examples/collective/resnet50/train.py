@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--width_mult", type=float, default=1.0)
     ap.add_argument("--ckpt", default=os.environ.get("PADDLE_EDL_HDFS_PATH") or "./resnet_ckpt")
     ap.add_argument("--max_steps", type=int, default=0, help="stop an epoch early (smoke runs)")
+    ap.add_argument("--inject_fault_file", default=os.environ.get("RESNET_INJECT_FAULT_FILE", ""),
+                    help="testing: once this file exists, rank 1 reports ONE failed collective although every pod is alive "
+                         "(a false alarm: exercises the soft reset of ElasticContext.recover())")
     ap.add_argument("--data_dir", default=None,
                     help="ImageNet-style directory with train_list.txt ('relative/path.jpg label' per line); synthetic if unset")
     ap.add_argument("--use_dali", type=lambda v: str(v).lower() in ("1", "true", "yes"), default=False,
@@ -146,6 +149,7 @@ def main():
     meter = StepMeter(bs, world)
     lr = base_lr
     progress = os.environ.get("EDL_PROGRESS_FILE", "")
+    injected = False
     while epoch < args.epochs:
         g = torch.Generator().manual_seed(epoch * 1000 + rank)       # pass_id as seed: reproducible after resume
         t0, seen = time.time(), 0
@@ -158,17 +162,31 @@ def main():
             lr = (cosine_decay_with_warmup(step, base_lr, steps_per_epoch, args.epochs) if args.lr_strategy.startswith("cosine")
                   else piecewise_decay_with_warmup(step, base_lr, steps_per_epoch, [30, 60, 80]))
             tr.set_lr(lr)
+            if (ctx is not None and world > 1 and rank == 1 and not injected and args.inject_fault_file
+                    and os.path.exists(args.inject_fault_file)):
+                injected = True
+                failed = "injected collective fault (testing the soft reset)"
+                break
             if feed is not None:
                 try:
                     x, y = next(feed)                                # already on the device (or CPU tensors without one)
                 except StopIteration:
                     break                                            # this rank's shard is exhausted: epoch over
-                loss = tr.step(x, y)
             else:
                 x = torch.randn(bs, 3, args.image_size, args.image_size, generator=g).to(dtype)
                 x = x.contiguous(memory_format=torch.channels_last)
                 y = torch.randint(0, args.class_dim, (bs,), generator=g)
-                loss = tr.step(x.pin_memory() if cuda else x, y.pin_memory() if cuda else y)
+                if cuda:
+                    x, y = x.pin_memory(), y.pin_memory()
+            try:
+                loss = tr.step(x, y)
+            except RuntimeError as e:
+                # library collectives (gloo / NCCL process group) RAISE when a peer is gone; the fabric kernels time out
+                # into an error word instead and the poll below reports it
+                if ctx is None:
+                    raise
+                failed = str(e).splitlines()[0][:200]
+                break
             step += 1
             it += 1
             seen += bs

@@ -139,15 +139,17 @@ def test_rendezvous_store_and_commit_protocol(kv_server):
 @pytest.mark.slow
 def test_resnet_trainer_rescales_in_place(kv_server, tmp_path):
     """The flagship trainer path (StudentTrainer.rebuild + sync_from) under the launcher, CPU / gloo, tiny ResNet_vd:
-    pod B joins mid-epoch, A's trainer stays alive, both finish the job with identical parameters."""
+    pod B joins mid-epoch, A's trainer stays alive, a false alarm is survived by a soft reset, both finish the job."""
     job = "inplace_rn_" + uuid.uuid4().hex[:6]
     ckpt = str(tmp_path / "ckpt")
     script = os.path.join(ROOT, "examples", "collective", "resnet50", "train.py")
+    fault = str(tmp_path / "fault.now")
 
     def launch(name):
         env = dict(os.environ)
         env.update({"PYTHONPATH": ROOT, "CUDA_VISIBLE_DEVICES": "", "PADDLE_RUNNING_PLATFORM": "", "EDL_POD_IP": "127.0.0.1",
-                    "EDL_INPLACE_CHECK_EVERY": "4", "EDL_INPLACE_ACK_TIMEOUT": "60", "OMP_NUM_THREADS": "2"})
+                    "EDL_INPLACE_CHECK_EVERY": "4", "EDL_INPLACE_ACK_TIMEOUT": "60", "OMP_NUM_THREADS": "2",
+                    "RESNET_INJECT_FAULT_FILE": fault})
         cmd = [sys.executable, "-u", "-m", "edl_b200.collective.launch", "--nodes_range", "1:2", "--nproc_per_node", "1",
                "--etcd_endpoints", kv_server.endpoint, "--job_id", job, "--log_dir", str(tmp_path / ("log" + name)),
                "--hdfs_path", ckpt, "--rescale_mode", "inplace", script, "--model", "ResNet18_vd", "--width_mult", "0.125",
@@ -168,10 +170,20 @@ def test_resnet_trainer_rescales_in_place(kv_server, tmp_path):
             assert time.time() < deadline and a.poll() is None, worker_log("A")[-2000:]
             time.sleep(0.2)
         b = launch("B")
+        deadline = time.time() + 200
+        while "rescaled in place: world 1 -> 2" not in worker_log("A"):
+            assert time.time() < deadline and a.poll() is None, worker_log("A")[-2000:]
+            time.sleep(0.2)
+        # a false alarm on top: rank 1 reports a failed collective although both pods are alive; both trainers drop the
+        # group, see that nobody left and re-form the same stage (soft reset) -- StudentTrainer.rebuild with an unchanged
+        # world size, state from rank 0
+        open(fault, "w").close()
         assert a.wait(timeout=400) == 0, worker_log("A")[-3000:]
         assert b.wait(timeout=120) == 0, worker_log("B")[-3000:]
         la, lb = worker_log("A"), worker_log("B")
         assert "rescaled in place: world 1 -> 2" in la, la[-3000:]
+        assert "rescaled in place: world 2 -> 2" in la and "rescaled in place: world 2 -> 2" in lb, (la[-2000:], lb[-2000:])
+        assert "injected collective fault" in lb
         assert "Traceback" not in la and "Traceback" not in lb
         assert "falling back to stop-resume" not in (tmp_path / "A.launcher.log").read_text()
         etcd = EtcdClient([kv_server.endpoint], root=job)
