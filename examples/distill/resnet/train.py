@@ -82,6 +82,9 @@ def parse():
       "paddle_edl.utils.image_pipeline) or a directory of .pt shards {'images': uint8 NHWC, 'labels': int64}; synthetic if unset")
     a("--max_steps", type=int, default=0)
     a("--width_mult", type=float, default=1.0)
+    a("--inject_fault_file", default=os.environ.get("DISTILL_INJECT_FAULT_FILE", ""),
+      help="testing: once this file exists, rank 1 reports ONE failed collective although every pod is alive (a false "
+           "alarm: exercises the soft reset of ElasticContext.recover())")
     a("--solo_step_sleep", type=float, default=0.0,
       help="elastic demos / tests: seconds to sleep per step while the job has ONE trainer, so that a second pod has "
            "time to join whatever the speed of the box")
@@ -209,16 +212,26 @@ def main():
     onehot_eye = None
     prof = StepProfiler(100, 105, "./profile_pass_0", enabled=args.profile, rank=rank)
     epoch = first_epoch
+    injected = False
     while epoch < args.num_epochs:
         epoch_box[0] = epoch
         it = reader() if reader is not None else batches_of(sample_stream(args, rank, world, epoch), bs)
         t0, seen = time.time(), 0
-        switch = False
+        switch, failed = False, ""
         for bi, batch in enumerate(it):
             if args.max_steps and bi >= args.max_steps:
                 break
-            if ctx is not None and bi > 0 and ctx.poll(agree=tr.dp.agree):
-                switch = True
+            if (ctx is not None and world > 1 and rank == 1 and not injected and args.inject_fault_file
+                    and os.path.exists(args.inject_fault_file)):
+                injected = True
+                failed = "injected collective fault (testing the soft reset)"
+                break
+            try:
+                if ctx is not None and bi > 0 and ctx.poll(agree=tr.dp.agree):
+                    switch = True
+                    break
+            except RuntimeError as e:                           # a collective timed out: a peer is gone (or a false alarm)
+                failed = str(e).splitlines()[0][:200]
                 break
             lr = (cosine_decay_with_warmup(step, base_lr, steps_per_epoch, args.num_epochs)
                   if args.lr_strategy.startswith("cosine")
@@ -243,7 +256,15 @@ def main():
             else:
                 tgt = y
             x = x.contiguous(memory_format=torch.channels_last)
-            loss = tr.step(x.pin_memory() if cuda else x, tgt.pin_memory() if cuda else tgt)
+            try:
+                loss = tr.step(x.pin_memory() if cuda else x, tgt.pin_memory() if cuda else tgt)
+            except RuntimeError as e:
+                # library collectives raise when a peer is gone; the fabric kernels time out into an error word that the
+                # next poll reports
+                if ctx is None:
+                    raise
+                failed = str(e).splitlines()[0][:200]
+                break
             prof.step()
             step += 1
             seen += bs
@@ -252,20 +273,28 @@ def main():
             if bi % args.fetch_steps == 0 and rank == 0:
                 print("Pass %d, batch %d, loss %.5f, lr %.5f, speed %.1f img/s" % (
                     epoch, bi, float(loss), lr, seen * world / max(1e-6, time.time() - t0)), flush=True)
-        if ctx is not None and not switch:
-            switch = ctx.poll(force=True, agree=tr.dp.agree)
-        if switch:
+        if ctx is not None and not switch and not failed:
+            try:
+                switch = ctx.poll(force=True, agree=tr.dp.agree)
+            except RuntimeError as e:
+                failed = str(e).splitlines()[0][:200]
+        if switch or failed:
             if hasattr(it, "close"):
                 it.close()                                      # stop the (distill) reader of the old shard
             try:
-                tr.prepare_rescale()                            # fused optimizer: sharded state made complete (old stage)
-                info = ctx.rescale()
+                if failed:
+                    # hot recovery (a pod died) or soft reset (false alarm): same process, state from the root rank
+                    print("rank %d: %s -- recovering in place" % (rank, failed), flush=True)
+                    info = ctx.recover()
+                else:
+                    tr.prepare_rescale()                        # fused optimizer: sharded state made complete (old stage)
+                    info = ctx.rescale()
             except elastic.EdlEvicted:
                 print("rank %d: pod left the job (scale-in); exiting" % rank, flush=True)
                 break
             old_world, world, rank = world, info.size, info.rank
             shard.update(rank=rank, world=world)
-            tr.rebuild(None, fabric=ctx.fabric)
+            tr.rebuild(None, fabric=ctx.fabric, failed=bool(failed))
             epoch, step = take_cursor_from(info.root, (epoch, step))
             base_lr = scaled_lr(args.lr, bs, world)
             steps_per_epoch = max(1, args.total_images // (bs * world))

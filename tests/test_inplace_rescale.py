@@ -469,20 +469,23 @@ def test_restart_mode_survives_a_hard_pod_death(kv_server, tmp_path):
 def test_distill_example_rescales_in_place_with_a_live_teacher(kv_server, tmp_path):
     """The elastic DISTILL example end to end (examples/distill/resnet/train.py, the reference's
     example/distill/resnet/train_with_fleet.py under the launcher): students pull soft labels from a teacher server
-    through the DistillReader, pod B joins in place while pod A trains, both finish the job."""
+    through the DistillReader, pod B joins in place while pod A trains, an injected false alarm is survived by a soft reset
+    (ElasticContext.recover() with an unchanged membership), both finish the job."""
     from edl_b200.distill.teacher_server import TeacherServer
     from edl_b200.models.teacher_zoo import build
 
     job = "inplace_distill_" + uuid.uuid4().hex[:6]
     ckpt = str(tmp_path / "ckpt")
     script = os.path.join(ROOT, "examples", "distill", "resnet", "train.py")
+    fault = str(tmp_path / "fault.now")
     model, feeds, fetches, shapes = build("resnext_tiny")
     srv = TeacherServer(model, feeds, fetches, shapes).start()
 
     def launch(name):
         env = dict(os.environ)
         env.update({"PYTHONPATH": ROOT, "CUDA_VISIBLE_DEVICES": "", "PADDLE_RUNNING_PLATFORM": "", "EDL_POD_IP": "127.0.0.1",
-                    "EDL_INPLACE_CHECK_EVERY": "4", "EDL_INPLACE_ACK_TIMEOUT": "60", "OMP_NUM_THREADS": "2"})
+                    "EDL_INPLACE_CHECK_EVERY": "4", "EDL_INPLACE_ACK_TIMEOUT": "60", "OMP_NUM_THREADS": "2",
+                    "DISTILL_INJECT_FAULT_FILE": fault})
         cmd = [sys.executable, "-u", "-m", "edl_b200.collective.launch", "--nodes_range", "1:2", "--nproc_per_node", "1",
                "--etcd_endpoints", kv_server.endpoint, "--job_id", job, "--log_dir", str(tmp_path / ("log" + name)),
                "--hdfs_path", ckpt, "--rescale_mode", "inplace", script, "--model", "ResNet18_vd", "--width_mult", "0.125",
@@ -504,10 +507,16 @@ def test_distill_example_rescales_in_place_with_a_live_teacher(kv_server, tmp_pa
             assert time.time() < deadline and a.poll() is None, worker_log("A")[-2000:]
             time.sleep(0.2)
         b = launch("B")
+        deadline = time.time() + 300
+        while "rescaled in place: world 1 -> 2" not in worker_log("A"):
+            assert time.time() < deadline and a.poll() is None, worker_log("A")[-2000:]
+            time.sleep(0.2)
+        open(fault, "w").close()                              # rank 1 reports one failed collective; nobody left
         assert a.wait(timeout=500) == 0, worker_log("A")[-3000:]
         assert b.wait(timeout=120) == 0, worker_log("B")[-3000:]
         la, lb = worker_log("A"), worker_log("B")
         assert "rescaled in place: world 1 -> 2" in la, la[-3000:]
+        assert "rescaled in place: world 2 -> 2" in la and "rescaled in place: world 2 -> 2" in lb, (la[-2000:], lb[-2000:])
         assert "Traceback" not in la and "Traceback" not in lb
         etcd = EtcdClient([kv_server.endpoint], root=job)
         etcd.init()
