@@ -476,28 +476,25 @@ class ElasticContext:
                 dist.destroy_process_group()
         except Exception as e:  # noqa: BLE001 - the group is broken anyway
             logger.warning("destroying the broken process group: %s", e)
-        # A dead pod's lease expires within ETCD_TTL and the leader publishes the smaller stage one poll later.  If the
-        # membership has NOT changed by then, nobody died: the collective failed on a false alarm (a rank stalled longer
-        # than the communication time-out, a transient transport error).  Every member of the stage lands here (the
-        # abandoned group makes the others' collectives fail too), so they re-form the SAME stage under a fresh
-        # namespace -- a soft reset -- and take rank 0's state like after any other recovery.  ``wait_s`` bounds the
-        # whole thing; EDL_SOFT_RESET=0 restores the old behaviour (give up when the membership does not change).
-        wait_s = wait_s if wait_s is not None else constants.ETCD_TTL * 2 + 4 * constants.POLL_INTERVAL + 10
-        soft_after = constants.ETCD_TTL + 3 * constants.POLL_INTERVAL + 1.0
-        soft_ok = os.environ.get("EDL_SOFT_RESET", "1") != "0"
-        t_fail = time.time()
-        deadline = t_fail + wait_s
-        soft = None
-        while time.time() < deadline:
-            c = edl_cluster.load_from_etcd(self._etcd, timeout=10)
-            if c is not None and c.stage != old.stage:
-                break
-            if soft_ok and c is not None and time.time() - t_fail >= soft_after:
-                soft = (old.stage, old.generation + 1)
-                break
-            time.sleep(0.1)
-        else:
-            raise TimeoutError("a collective failed but the membership did not change within %.0fs" % wait_s)
+        # Nobody may have died: a rank that stalled longer than the communication time-out or a transient transport error
+        # fails a collective just the same, and every member of the stage lands here (the abandoned group makes the
+        # others' collectives fail too).  So the members first try to re-form the SAME stage under a fresh namespace
+        # (generation + 1) -- a soft reset.  If everybody is alive that rendezvous completes at once and they continue
+        # from rank 0's state; if a pod did die, its ready key never appears, the store publishes the smaller stage
+        # (lease expiry + one leader poll) and ``_rendezvous`` withdraws and joins THAT stage as a survivor: the hot
+        # recovery.  EDL_SOFT_RESET=0: wait for a membership change first and give up after ``wait_s`` without one.
+        soft = (old.stage, old.generation + 1)
+        if os.environ.get("EDL_SOFT_RESET", "1") == "0":
+            soft = None
+            wait_s = wait_s if wait_s is not None else constants.ETCD_TTL * 2 + 4 * constants.POLL_INTERVAL + 10
+            deadline = time.time() + wait_s
+            while time.time() < deadline:
+                c = edl_cluster.load_from_etcd(self._etcd, timeout=10)
+                if c is not None and c.stage != old.stage:
+                    break
+                time.sleep(0.1)
+            else:
+                raise TimeoutError("a collective failed but the membership did not change within %.0fs" % wait_s)
         self._changed.clear()
         t0 = time.time()
         info = self._rendezvous(survivor=True, prev_size=old.size, soft=soft)

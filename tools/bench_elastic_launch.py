@@ -40,7 +40,8 @@ def launch(endpoint, job, tmp, name, mode):
                CUDA_VISIBLE_DEVICES=",".join(str(first + i) for i in range(g)),
                FIT_REPORT_DIR=os.path.join(tmp, "report"), EDL_PROGRESS_FILE=os.path.join(tmp, "report", "epochs.jsonl"),
                EDL_INPLACE_CHECK_EVERY="3" if CFG["trainer"] == "fit" else "10",
-               EDL_ETCD_TTL="1.5", EDL_POLL_INTERVAL="0.3", EDL_KILL_GRACE="1")
+               EDL_ETCD_TTL="1.5", EDL_POLL_INTERVAL="0.3", EDL_KILL_GRACE="1",
+               FIT_INJECT_FAULT_FILE=os.path.join(tmp, "fault.now"), RESNET_INJECT_FAULT_FILE=os.path.join(tmp, "fault.now"))
     os.makedirs(os.path.join(tmp, "report"), exist_ok=True)
     if CFG["trainer"] == "fit":
         script = [TRAIN, "--epochs", "100000", "--epoch_sleep", "0.02", "--ckpt", os.path.join(tmp, "ckpt")]
@@ -91,6 +92,16 @@ def run(mode, server_cls):
             join_stall = stall(e, t_join)
             pids_before = {x["pid"] for x in e if x["world"] == w1 and x["t"] < t_join}
             survivor_kept = e[-1]["pid"] in pids_before
+            if CFG["leave"] == "false_alarm":
+                # nobody leaves: rank 1 reports ONE failed collective; both trainers soft-reset (same stage, new generation)
+                t_ev = time.time()
+                open(os.path.join(tmp, "fault.now"), "w").close()
+                time.sleep(1.0)
+                e = wait_world(w2, timeout=120, min_new=8)
+                return {"mode": mode, "leave": "false_alarm", "store": server_cls.__name__, "join_s": join,
+                        "join_stall_s": join_stall, "false_alarm_stall_s": stall(e, t_ev),
+                        "survivor_process_kept": e[-1]["pid"] in {x["pid"] for x in e if x["t"] < t_ev},
+                        "steady_epoch_s": sorted(y["t"] - x["t"] for x, y in zip(e[-5:-1], e[-4:]))[1]}
             etcd = EtcdClient([srv.endpoint], root=job)
             etcd.init()
             t_leave = time.time()
@@ -144,7 +155,7 @@ if __name__ == "__main__":
     ap.add_argument("--native-store", action="store_true")
     ap.add_argument("--trainer", default="fit", choices=["fit", "resnet"])
     ap.add_argument("--gpus-per-pod", type=int, default=0, help="GPUs (= trainers) per pod; 0 = CPU / gloo")
-    ap.add_argument("--leave", default="scale_in", choices=["scale_in", "sigterm", "kill"],
+    ap.add_argument("--leave", default="scale_in", choices=["scale_in", "sigterm", "kill", "false_alarm"],
                     help="how pod B leaves: the leader's ScaleIn RPC, SIGTERM to its launcher (graceful leave), or SIGKILL "
                          "of launcher and trainers (hot recovery in place / restart of everybody in restart mode)")
     ap.add_argument("--out", default="")
