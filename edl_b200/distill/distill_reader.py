@@ -87,6 +87,7 @@ class DistillReader:
         self._epoch = 0
         self._client_factory = None
         self._lock = threading.Lock()
+        self._reader_in_process = os.environ.get("EDL_DISTILL_READER_PROCESS", "0") == "1"
 
     # ------------------------------------------------------------------ configuration
     def set_serving_conf_file(self, conf_file):
@@ -125,6 +126,13 @@ class DistillReader:
     def set_predict_client_factory(self, factory):
         """Plug another teacher transport: ``factory(server, feeds, fetchs, conf) -> PredictClient``."""
         self._client_factory = factory
+
+    def set_reader_process(self, enabled=True):
+        """Run the user's reader generator in a forked process instead of a thread (the reference forks its reader
+        worker): worth it when the reader is Python-heavy (decode / augmentation holding the GIL); costs one pickle of
+        every sample.  Also ``EDL_DISTILL_READER_PROCESS=1``."""
+        self._reader_in_process = bool(enabled)
+        return self
 
     def set_sample_generator(self, reader):
         assert self._reader is None, "reader has already set"
@@ -211,7 +219,8 @@ class DistillReader:
             self._epoch += 1
             epoch = self._epoch
         epoch_stop = threading.Event()
-        t = threading.Thread(target=distill_worker.reader_worker, daemon=True, name="distill-reader",
+        target = distill_worker.reader_process_pump if self._reader_in_process else distill_worker.reader_worker
+        t = threading.Thread(target=target, daemon=True, name="distill-reader",
                              args=(self._reader, self._reader_type, self._teacher_batch_size, self._in_q,
                                    self._out_q, self._sem, epoch_stop, epoch))
         t.start()

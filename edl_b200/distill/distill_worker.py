@@ -89,6 +89,77 @@ def reader_worker(reader, reader_type, teacher_batch_size, in_q, out_q, sem, sto
         out_q.put(_EpochEnd(task_id, epoch, error=e))
 
 
+def _reader_process_main(reader, reader_type, teacher_batch_size, mp_q, stop, epoch):
+    """Child process (forked): the USER's reader runs here, off the student's GIL.  Tasks travel as plain tuples; the
+    parent's pump thread applies the back-pressure semaphore and feeds the predict pool."""
+    local_in, local_out = queue.Queue(), queue.Queue()
+
+    class _NoSem:                      # the bounded mp queue is the back-pressure on this side of the pipe
+        def acquire(self, timeout=None):
+            return True
+
+    t = threading.Thread(target=reader_worker, daemon=True,
+                         args=(reader, reader_type, teacher_batch_size, local_in, local_out, _NoSem(), stop, epoch))
+    t.start()
+    try:
+        while True:
+            try:
+                task = local_in.get(timeout=0.05)
+                mp_q.put(("task", task.task_id, task.batch_id, task.last_of_batch, task.samples))
+                continue
+            except queue.Empty:
+                pass
+            if not t.is_alive() and local_in.empty():
+                break
+        end = local_out.get(timeout=5)
+        mp_q.put(("end", end.n_tasks, repr(end.error) if end.error is not None else None))
+    except Exception as e:  # noqa: BLE001
+        mp_q.put(("end", -1, repr(e)))
+
+
+def reader_process_pump(reader, reader_type, teacher_batch_size, in_q, out_q, sem, stop, epoch):
+    """``reader_worker`` with the user's generator in a FORKED PROCESS (the reference's design,
+    distill_worker.py:46-120: reader and predict workers are processes): a Python-heavy reader (cv2 decode, augmentation
+    in numpy / pure Python) no longer competes with the training loop and the predict threads for the GIL.  Samples are
+    pickled once across the pipe; the thread version stays the default because it hands numpy arrays over by reference."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("fork")       # user readers are closures: not picklable, so no spawn
+    mp_q = ctx.Queue(maxsize=8)
+    child_stop = ctx.Event()
+    proc = ctx.Process(target=_reader_process_main, daemon=True,
+                       args=(reader, reader_type, teacher_batch_size, mp_q, child_stop, epoch))
+    proc.start()
+    n_tasks, error = 0, None
+    try:
+        while True:
+            if stop.is_set():
+                return
+            try:
+                msg = mp_q.get(timeout=0.2)
+            except queue.Empty:
+                if not proc.is_alive():
+                    error = RuntimeError("the distill reader process died (exit code %s)" % proc.exitcode)
+                    break
+                continue
+            if msg[0] == "end":
+                if msg[2] is not None:
+                    error = RuntimeError("reader failed in its process: %s" % msg[2])
+                n_tasks = max(n_tasks, msg[1])
+                break
+            _, task_id, batch_id, last, samples = msg
+            if not _acquire(sem, stop):
+                return
+            in_q.put(Task(task_id, batch_id, last, samples, epoch))
+            n_tasks = task_id + 1
+        out_q.put(_EpochEnd(n_tasks, epoch, error=error))
+    finally:
+        child_stop.set()
+        proc.join(2)
+        if proc.is_alive():
+            proc.terminate()
+
+
 def _acquire(sem, stop):
     while not stop.is_set():
         if sem.acquire(timeout=0.1):

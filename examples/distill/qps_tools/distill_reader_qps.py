@@ -25,12 +25,24 @@ def main():
     ap.add_argument("--conf_file", default="", help="serving conf (feeds / fetches): parse_config.get_ins_predicts")
     ap.add_argument("--out", default="", help="append one JSON line per measurement")
     ap.add_argument("--image_size", type=int, default=224)
+    ap.add_argument("--reader_process", action="store_true", help="DistillReader.set_reader_process(): reader in a forked process")
+    ap.add_argument("--reader_cost_us", type=int, default=0,
+                    help="pure-Python work per sample INSIDE the reader (emulates decode / augmentation that holds the GIL)")
+    ap.add_argument("--consumer_cost_us", type=int, default=0,
+                    help="pure-Python work per sample in the consumer (emulates the training loop's host side)")
     args = ap.parse_args()
     distill_worker._NOP_PREDICT_TEST = args.nop
     img = np.random.rand(3, args.image_size, args.image_size).astype("float32")
 
+    def burn(us):                       # holds the GIL, like Python-level decode / augmentation code does
+        t_end = time.perf_counter() + us * 1e-6
+        while time.perf_counter() < t_end:
+            pass
+
     def gen():
         for i in range(0, args.samples, 32):
+            if args.reader_cost_us:
+                burn(32 * args.reader_cost_us)
             yield [(img, np.array([j], dtype="int64")) for j in range(32)]
 
     ins, predicts = ["image", "label"], ["score"]
@@ -42,17 +54,22 @@ def main():
         dr = DistillReader(ins=ins, predicts=predicts)
         dr.set_teacher_batch_size(tbs)
         dr.set_fixed_teacher(args.teachers)
+        dr.set_reader_process(args.reader_process)
         r = dr.set_sample_list_generator(gen)
         t0, n = time.time(), 0
         for batch in r():
             n += len(batch)
+            if args.consumer_cost_us:
+                burn(len(batch) * args.consumer_cost_us)
         qps = n / (time.time() - t0)
         print("teacher_batch_size %2d: %8.1f samples/s" % (tbs, qps), flush=True)
         if args.out:
             import json
             with open(args.out, "a") as fh:
                 fh.write(json.dumps({"teacher_batch_size": tbs, "samples_per_s": qps, "nop": bool(args.nop),
-                                     "teachers": args.teachers, "samples": n}) + "\n")
+                                     "teachers": args.teachers, "samples": n, "image_size": args.image_size,
+                                     "reader_process": bool(args.reader_process), "reader_cost_us": args.reader_cost_us,
+                                     "consumer_cost_us": args.consumer_cost_us}) + "\n")
         dr.stop()
 
 

@@ -141,3 +141,50 @@ def test_real_grpc_teacher():
                 n += 1
         assert n == 30 and srv.served == 30
         dr.stop()
+
+
+def test_reader_in_a_forked_process_gives_the_same_stream():
+    """set_reader_process(): the user's generator runs in a forked child (the reference forks its reader worker), tasks
+    cross a bounded pipe, ordering / batch boundaries / early break behave exactly like the thread version, a reader
+    exception surfaces in the consumer."""
+    import os
+
+    _EchoClient.fail_servers = set()
+    n, bs = 50, 8
+    pids = []
+
+    def gen():
+        for b in _batches(n, bs):
+            yield [(img, np.array([int(lab[0]), os.getpid()], dtype=np.int64)) for img, lab in b]
+
+    dr = _make().set_reader_process(True)
+    reader = dr.set_sample_list_generator(gen)
+    for epoch in range(3):
+        seen = 0
+        for batch in reader():
+            assert len(batch) == (bs if seen + bs <= n else n - seen)
+            for img, label, score in batch:
+                assert int(label[0]) == seen and float(score[0]) == float(seen)
+                pids.append(int(label[1]))
+                seen += 1
+        assert seen == n
+    assert os.getpid() not in set(pids)                    # the generator really ran elsewhere
+    it = reader()                                          # early break: the child is stopped, the next epoch is complete
+    next(it)
+    it.close()
+    assert sum(len(b) for b in reader()) == n
+    dr.stop()
+
+    def bad():
+        yield from _batches(8, 4)
+        raise ValueError("boom in the reader")
+
+    dr2 = _make().set_reader_process(True)
+    r2 = dr2.set_sample_list_generator(bad)
+    try:
+        for _ in r2():
+            pass
+        raise AssertionError("the reader's exception was swallowed")
+    except RuntimeError as e:
+        assert "boom in the reader" in str(e)
+    dr2.stop()
