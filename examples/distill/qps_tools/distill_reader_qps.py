@@ -25,7 +25,8 @@ def main():
     ap.add_argument("--conf_file", default="", help="serving conf (feeds / fetches): parse_config.get_ins_predicts")
     ap.add_argument("--out", default="", help="append one JSON line per measurement")
     ap.add_argument("--image_size", type=int, default=224)
-    ap.add_argument("--reader_process", action="store_true", help="DistillReader.set_reader_process(): reader in a forked process")
+    ap.add_argument("--reader_process", action="store_true",
+                    help="DistillReader.set_reader_process(): reader in a forked process")
     ap.add_argument("--reader_cost_us", type=int, default=0,
                     help="pure-Python work per sample INSIDE the reader (emulates decode / augmentation that holds the GIL)")
     ap.add_argument("--consumer_cost_us", type=int, default=0,
