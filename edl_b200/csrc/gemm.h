@@ -139,6 +139,7 @@ bool get_pair_gemm();
 void set_persist_trace(long long* buf);   // debug: int64 [3 * 16 * 8] device buffer for clock64() phase stamps of CTA 0, or nullptr
 void set_tc_stats(bool on);          // forward BN statistics as tensor-core Gram / ones products of the staged tile (EDL_TC_STATS)
 void set_epilogue_warps(int n);      // 8 or 16 epilogue warps for the 128 / 256 column persistent kernels (EDL_EPI_WARPS)
+bool conv3x3_halo_plan(int N, int H, int W, int* BH, int* BN, int* tiles_h, int* tiles_img);   // host only
 void set_conv_halo(bool on);         // haloed A tiles for the 3x3 / stride 1 fprop and dgrad (default on; EDL_CONV_HALO=0)
 bool get_conv_halo();
 void set_conv_resident_weights(bool on);   // 64-channel layers / groups: weights resident across a CTA's run of tiles (EDL_CONV_BRES=0)

@@ -395,6 +395,11 @@ void register_gemm_bindings(pybind11::module_& m) {
   });
   m.def("set_tc_stats", &edl::set_tc_stats);
   m.def("set_epilogue_warps", &edl::set_epilogue_warps);
+  m.def("conv3x3_halo_plan", [](int64_t n, int64_t h, int64_t w) -> std::vector<int64_t> {
+    int bh = 0, bn = 0, th = 0, ti = 0;
+    if (!edl::conv3x3_halo_plan((int)n, (int)h, (int)w, &bh, &bn, &th, &ti)) return {};
+    return {bh, bn, th, ti};
+  });
   m.def("set_conv_halo", &edl::set_conv_halo);
   m.def("get_conv_halo", &edl::get_conv_halo);
   m.def("set_conv_resident_weights", &edl::set_conv_resident_weights);

@@ -1381,6 +1381,10 @@ const char* conv3x3_bf16_persistent(const Conv3x3Args& a, int BH, int BN, int ti
 void set_epilogue_warps(int n) { g_epi16 = n >= 16; }
 void set_tc_stats(bool on) { g_tc_stats = on; }
 void set_persist_trace(long long* buf) { g_trace = buf; }
+// the tile geometry of the halo layout, for the CPU replay of its index math (tests/test_halo_plan_cpu.py)
+bool conv3x3_halo_plan(int N, int H, int W, int* BH, int* BN, int* tiles_h, int* tiles_img) {
+  return halo_geometry(N, H, W, BH, BN, tiles_h, tiles_img);
+}
 void set_conv_halo(bool on) { g_conv_halo = on; }
 void set_conv_resident_weights(bool on) { g_conv_bres = on; }
 bool get_conv_halo() { return g_conv_halo; }
